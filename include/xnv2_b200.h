@@ -1,0 +1,127 @@
+/*
+ * xnv2_b200 -- C ABI of the B200-native ExpansionNet v2 captioning path.
+ *
+ * The reference (nighting0le01/On_Device_Image_Captioning) is pure Python/PyTorch and has
+ * no FFI of its own; its "plugin boundary" for this path is the Python class surface
+ *   End_ExpansionNet_v2.forward_enc / forward_dec      models/End_ExpansionNet_v2.py:121-209
+ *   ExpansionNet_v2.forward_enc / forward_dec          models/ExpansionNet_v2.py:76-156
+ *   CaptioningModel.forward(mode=...) / beam_search    legacy_models/captioning_model.py:24-57,111-241
+ *   Captioner.__call__ / beam_search                   models/captioning_model.py:67-110,220-427
+ * Every entry point below names the reference interface it replaces.  The Python shim in
+ * on_device_image_captioning_b200/ binds these symbols with ctypes and re-exposes the
+ * reference's class/method signatures.
+ *
+ * Conventions: every call returns 0 on success and a negative code on failure (never
+ * throws); xn_last_error() gives the message.  All tensor arguments are caller-owned
+ * DEVICE pointers unless the name says host; work is enqueued on the given CUDA stream
+ * (passed as void* == cudaStream_t) and is stream-ordered: the caller synchronises the
+ * stream before reading results.  A handle is bound to one device and is not
+ * thread-safe.  There is no CPU fallback: without a CUDA device xn_create fails.
+ */
+#ifndef XNV2_B200_H
+#define XNV2_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct xn_handle xn_handle;
+
+enum { XN_OK = 0, XN_ERR_ARG = -1, XN_ERR_CUDA = -2, XN_ERR_STATE = -3, XN_ERR_UNSUPPORTED = -4 };
+enum { XN_PREC_FP32 = 0, XN_PREC_BF16 = 1 };
+enum { XN_DTYPE_F32 = 0, XN_DTYPE_I64 = 1 };
+
+/* Model geometry: the constructor arguments of End_ExpansionNet_v2 / ExpansionNet_v2
+ * (models/End_ExpansionNet_v2.py:11-47, models/ExpansionNet_v2.py:10-25). */
+typedef struct xn_config {
+  int32_t has_swin;          /* 1: End_ExpansionNet_v2 (images in), 0: ExpansionNet_v2 (features in) */
+  int32_t img_size, patch_size, in_chans, embed_dim;
+  int32_t n_stages;
+  int32_t depths[4];
+  int32_t swin_heads[4];
+  int32_t window_size;       /* 12 */
+  float   mlp_ratio;         /* 4.0 */
+  int32_t feat_dim;          /* final_swin_dim / img_feature_dim */
+  int32_t d_model, n_enc, n_dec, ff, num_heads;
+  int32_t n_exp_groups;
+  int32_t exp_groups[8];     /* num_exp_enc_list */
+  int32_t num_exp_dec;
+  int32_t vocab;
+  int32_t max_seq_len;       /* rows of pos_encoder */
+  int32_t enc_len;           /* visual tokens entering the expansion encoder (144) */
+} xn_config;
+
+/* Replaces: the model constructor.  `device` is the CUDA ordinal ("rank"). */
+int xn_create(const xn_config* cfg, int device, xn_handle** out);
+int xn_destroy(xn_handle* h);
+const char* xn_last_error(const xn_handle* h);   /* h may be NULL: last error of xn_create */
+
+/* Replaces: model.load_state_dict(checkpoint["model_state_dict"]) (demo.py:100-104,
+ * test.py:453-459).  One call per state_dict entry, key and shape exactly as in the
+ * reference checkpoint.  `data` may be a host or a device pointer
+ * (unified addressing).  Buffers (relative_position_index, attn_mask) are geometry-only:
+ * they are accepted and ignored. */
+int xn_load_tensor(xn_handle* h, const char* key, const void* data, int dtype,
+                   const int64_t* shape, int ndim);
+/* Packs the loaded tensors for the chosen precision; fails if a key is missing. */
+int xn_finalize_weights(xn_handle* h, int precision);
+
+/* Replaces: SwinTransformer.forward_features (models/swin_transformer_mod.py:801-813).
+ * images (B,in_chans,S,S) f32 NCHW -> out (B, L_last, C_last) f32. */
+int xn_forward_swin(xn_handle* h, const float* images, int B, float* out, void* stream);
+
+/* Replaces: forward_enc (models/End_ExpansionNet_v2.py:121-153, models/ExpansionNet_v2.py:76-100).
+ * input: images (has_swin) or features (B,enc_len,feat_dim).  enc_pads_host: B ints (host)
+ * or NULL (== all 0; must be all 0 when has_swin).  out (B,enc_len,d_model) f32. */
+int xn_forward_enc(xn_handle* h, const float* input, int B, const int32_t* enc_pads_host,
+                   float* out, void* stream);
+
+/* Replaces: forward_dec (models/End_ExpansionNet_v2.py:155-209, models/ExpansionNet_v2.py:102-156).
+ * cross (R,enc_len,d_model) f32, tokens (R,t) i64, pads: R host ints or NULL.
+ * out (R,t,vocab) f32: logits, or log-probabilities if apply_log_softmax != 0. */
+int xn_forward_dec(xn_handle* h, const float* cross, int R, const int32_t* enc_pads_host,
+                   const int64_t* tokens, int t, const int32_t* dec_pads_host,
+                   int apply_log_softmax, float* out, void* stream);
+
+/* Replaces: beam_search, 'max' branch (legacy_models/captioning_model.py:111-241 ==
+ * models/captioning_model.py:220-427), including forward_enc.
+ * out_tokens  (B,how_many,max_len) i32, -1 padded, SOS..EOS inclusive
+ * out_len     (B,how_many) i32
+ * out_logprob (B,how_many,max_len) f32, 0 padded                                        */
+int xn_beam_search(xn_handle* h, const float* input, int B, const int32_t* enc_pads_host,
+                   int beam, int max_len, int how_many, int sos_idx, int eos_idx,
+                   int32_t* out_tokens, int32_t* out_len, float* out_logprob, void* stream);
+/* Same, starting from an encoder output already on the device (B,enc_len,d_model). */
+int xn_beam_search_from_enc(xn_handle* h, const float* enc_out, int B, const int32_t* enc_pads_host,
+                            int beam, int max_len, int how_many, int sos_idx, int eos_idx,
+                            int32_t* out_tokens, int32_t* out_len, float* out_logprob, void* stream);
+
+/* End-to-end convenience for callers holding HOST buffers (the call bench.py's e2e leg
+ * times): pinned/pageable host images -> host tokens; copies are issued on `stream` and the
+ * call returns after the results have landed. */
+int xn_caption_host(xn_handle* h, const float* input_host, int B, int beam, int max_len, int how_many,
+                    int sos_idx, int eos_idx, int32_t* out_tokens_host, int32_t* out_len_host,
+                    float* out_logprob_host, void* stream);
+
+/* Counters / introspection. */
+int64_t xn_kernel_launches(const xn_handle* h);      /* kernels of this library launched so far */
+int64_t xn_workspace_bytes(const xn_handle* h);
+int xn_set_option(xn_handle* h, const char* name, int64_t value);   /* e.g. "swin_chunk", "use_graph" */
+
+/* Single-operator entry points (kernel-level parity tests call these through the ABI).
+ * All pointers device, row-major, f32 unless noted. */
+int xn_op_layernorm(xn_handle* h, const float* x, const float* gamma, const float* beta, float* y,
+                    int rows, int C, void* stream);
+int xn_op_linear(xn_handle* h, const float* x, const float* w, const float* bias, const float* residual,
+                 float* y, int M, int N, int K, int act /*0 none,1 gelu,2 relu*/, int precision, void* stream);
+int xn_op_window_attention(xn_handle* h, const float* qkv, const float* bias_table, float* out,
+                           int B, int H, int C, int heads, int shift, int precision, void* stream);
+int xn_op_logsoftmax_topk(xn_handle* h, const float* logits, int rows, int V, int k,
+                          float* top_val, int32_t* top_idx, float* logprob_or_null, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* XNV2_B200_H */

@@ -1,0 +1,371 @@
+// Decoder-step kernels: one new position per row per launch, with cached expansion state.
+//
+// The reference re-decodes the whole prefix every step (models/captioning_model.py:295-304).
+// By causality everything position i contributes -- cond c_i, key K_i, the class
+// projections A_i/B_i, the normalised forward weights of its row-block and q_e.K_i -- never
+// changes once computed, so each step only adds the row-block and the column of position p.
+// Beam reordering never copies that state: `anc[r][i]` names the slot (row) that holds position
+// i of row r's history, and the kernels gather through it.
+#include "kernels.h"
+#include "common.cuh"
+
+namespace xn {
+
+constexpr float kExpEps = 1e-9f;     // reference models/layers.py:208
+constexpr float kCrossFill = -1e4f;  // reference models/layers.py:284
+
+// y = E[tok] * sqrt(d) + P[p]   (reference layers.py:16-17, End_ExpansionNet_v2.py:171-189)
+__global__ void embed_kernel(const int64_t* __restrict__ t64, const int* __restrict__ t32, long tok_stride, int p,
+                             const float* __restrict__ emb, const float* __restrict__ pos, float* __restrict__ x,
+                             long ldx, int R, int d) {
+  const int r = blockIdx.x;
+  const long tok = t64 ? (long)t64[r * tok_stride + p] : (long)t32[r * tok_stride + p];
+  const float sc = sqrtf((float)d);
+  for (int c = threadIdx.x; c < d; c += blockDim.x)
+    x[(long)r * ldx + c] = emb[tok * d + c] * sc + pos[(long)p * d + c];
+}
+cudaError_t launch_embed(const int64_t* tokens64, const int* tokens32, long tok_stride, int p, const float* emb,
+                         const float* pos, float* x, long ldx, int R, int d, cudaStream_t st) {
+  embed_kernel<<<R, 128, 0, st>>>(tokens64, tokens32, tok_stride, p, emb, pos, x, ldx, R, d);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
+// Dynamic expansion, incremental (reference models/layers.py:152-204, restated per position):
+//   z[(i,e),j] = (q_e + c_i).K_j / sqrt(d)
+//   forward  (row-block of p):  Af[(p,e),j] = relu(z)/(sum_{j<=p} relu(z) + eps)          -> cached
+//   backward (output p):        ab[(i,e)]   = relu(z[(i,e),p]) / (sum_{i<=p,e} ... + eps)
+//   out_a[p] = sum_{i,e} ab[(i,e)] * ( sum_{j<=i} Af[(i,e),j] A_j  + b_e + c_i )
+//            = sum_j wA[j] A_j + sum_e sA[e] b_e + sum_i tA[i] c_i
+//   with wA[j] = sum_{i>=j,e} ab[(i,e)] Af[(i,e),j],  sA[e] = sum_i ab[(i,e)],  tA[i] = sum_e ab[(i,e)]
+// One CTA per row.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) dyn_exp_step_kernel(DecState s, int layer, int p, const float* __restrict__ qexp,
+                                                           const float* __restrict__ bexp, int n_exp,
+                                                           const int* __restrict__ row_len,
+                                                           const float* __restrict__ x_in, long ldxi,
+                                                           float* __restrict__ x_out, long ldxo, int d) {
+  extern __shared__ float sm[];
+  const int r = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int P = s.P, np = p + 1;
+  if (row_len && p >= row_len[r]) {            // padded position: the block contributes 0 (all-zero mask rows)
+    for (int c = tid; c < d; c += blockDim.x) x_out[(long)r * ldxo + c] = x_in[(long)r * ldxi + c];
+    return;
+  }
+  int* slot = reinterpret_cast<int*>(sm);      // [P]
+  float* ck_row = sm + P;                      // [P]   c_p . K_j
+  float* ck_col = ck_row + P;                  // [P]   c_i . K_p
+  float* qkp = ck_col + P;                     // [n_exp]
+  float* af = qkp + n_exp;                     // [n_exp][P] forward weights of the new row-block (A)
+  float* bf = af + n_exp * P;                  // [n_exp][P]
+  float* ab = bf + n_exp * P;                  // [P][n_exp] backward weights (A)
+  float* bb = ab + P * n_exp;                  // [P][n_exp]
+  float* wA = bb + P * n_exp;                  // [P]
+  float* wB = wA + P;
+  float* tA = wB + P;
+  float* tB = tA + P;
+  float* sA = tB + P;                          // [n_exp]
+  float* sB = sA + n_exp;
+  float* red = sB + n_exp;                     // [32]
+
+  for (int i = tid; i < np; i += blockDim.x) slot[i] = (i == p || !s.anc) ? r : s.anc[(long)r * P + i];
+  __syncthreads();
+  auto crow = [&](int i) { return s.cache + (((long)layer * P + i) * s.R + slot[i]) * s.cw; };
+  const float* cp = crow(p);                   // [cond | key | A | B | sel] of the new position
+  const float* Kp = cp + d;
+
+  // ---- phase A: the 2p+1+n_exp new dot products, one warp each
+  const int ntask = np + p + n_exp;
+  for (int t = warp; t < ntask; t += (blockDim.x >> 5)) {
+    const float* u;
+    const float* v;
+    if (t < np) { u = cp; v = crow(t) + d; }                       // c_p . K_j
+    else if (t < np + p) { u = crow(t - np); v = Kp; }             // c_i . K_p
+    else { u = qexp + (long)(t - np - p) * d; v = Kp; }            // q_e . K_p
+    float a = 0.f;
+    for (int c = lane * 4; c < d; c += 128) {
+      const float4 x4 = *reinterpret_cast<const float4*>(u + c);
+      const float4 y4 = *reinterpret_cast<const float4*>(v + c);
+      a = fmaf(x4.x, y4.x, a); a = fmaf(x4.y, y4.y, a); a = fmaf(x4.z, y4.z, a); a = fmaf(x4.w, y4.w, a);
+    }
+    a = warp_sum(a);
+    if (lane == 0) {
+      if (t < np) ck_row[t] = a;
+      else if (t < np + p) ck_col[t - np] = a;
+      else qkp[t - np - p] = a;
+    }
+  }
+  __syncthreads();
+  if (tid == 0) ck_col[p] = ck_row[p];
+  float* qk_out = s.qk + (((long)layer * P + p) * s.R + r) * n_exp;
+  for (int e = tid; e < n_exp; e += blockDim.x) qk_out[e] = qkp[e];
+  __syncthreads();
+
+  // ---- phase B: scalar work
+  const float sq = sqrtf((float)d);
+  // forward weights of the new row-block: one warp per expansion e
+  float* fw_out = s.fw + (((long)layer * P + p) * s.R + r) * (2L * n_exp * P);
+  for (int e = warp; e < n_exp; e += (blockDim.x >> 5)) {
+    float za[4], sa = 0.f, sb = 0.f;               // P <= 128 -> up to 4 keys per lane
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const int j = lane + 32 * c;
+      float z = 0.f;
+      if (j < np) {
+        const float qk = (j == p) ? qkp[e] : s.qk[(((long)layer * P + j) * s.R + slot[j]) * n_exp + e];
+        z = (qk + ck_row[j]) / sq;
+        sa += fmaxf(z, 0.f);
+        sb += fmaxf(-z, 0.f);
+      }
+      za[c] = z;
+    }
+    sa = warp_sum(sa) + kExpEps;
+    sb = warp_sum(sb) + kExpEps;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const int j = lane + 32 * c;
+      if (j < np) {
+        const float a = fmaxf(za[c], 0.f) / sa, b = fmaxf(-za[c], 0.f) / sb;
+        af[e * P + j] = a; bf[e * P + j] = b;
+        fw_out[e * P + j] = a; fw_out[(long)n_exp * P + e * P + j] = b;
+      }
+    }
+  }
+  // backward weights for output position p (column p of z)
+  float la = 0.f, lb = 0.f;
+  for (int i = tid; i < np * n_exp; i += blockDim.x) {
+    const int pi = i / n_exp, e = i % n_exp;
+    const float z = (qkp[e] + ck_col[pi]) / sq;
+    const float a = fmaxf(z, 0.f), b = fmaxf(-z, 0.f);
+    ab[i] = a; bb[i] = b;
+    la += a; lb += b;
+  }
+  const float ta = block_sum(la, red) + kExpEps;
+  const float tb = block_sum(lb, red) + kExpEps;
+  __syncthreads();
+  for (int i = tid; i < np * n_exp; i += blockDim.x) { ab[i] = ab[i] / ta; bb[i] = bb[i] / tb; }
+  __syncthreads();
+  // wA[j], wB[j]: thread (j, which)
+  for (int t = tid; t < 2 * np; t += blockDim.x) {
+    const int j = t >> 1, which = t & 1;
+    const float* wsrc = which ? bb : ab;
+    float acc = 0.f;
+    for (int i = j; i < np; ++i) {
+      const float* f = (i == p) ? (which ? bf : af)
+                                : s.fw + (((long)layer * P + i) * s.R + slot[i]) * (2L * n_exp * P) + (which ? (long)n_exp * P : 0);
+      for (int e = 0; e < n_exp; ++e) acc = fmaf(wsrc[i * n_exp + e], f[e * P + j], acc);
+    }
+    (which ? wB : wA)[j] = acc;
+  }
+  for (int t = tid; t < 2 * np; t += blockDim.x) {       // tA[i] = sum_e ab[(i,e)]
+    const int i = t >> 1, which = t & 1;
+    const float* wsrc = which ? bb : ab;
+    float acc = 0.f;
+    for (int e = 0; e < n_exp; ++e) acc += wsrc[i * n_exp + e];
+    (which ? tB : tA)[i] = acc;
+  }
+  for (int t = tid; t < 2 * n_exp; t += blockDim.x) {    // sA[e] = sum_i ab[(i,e)]
+    const int e = t >> 1, which = t & 1;
+    const float* wsrc = which ? bb : ab;
+    float acc = 0.f;
+    for (int i = 0; i < np; ++i) acc += wsrc[i * n_exp + e];
+    (which ? sB : sA)[e] = acc;
+  }
+  __syncthreads();
+
+  // ---- phase C: the d-wide mixes
+  for (int c = tid; c < d; c += blockDim.x) {
+    float oa = 0.f, ob = 0.f;
+    for (int j = 0; j < np; ++j) {
+      const float* cr = crow(j);
+      const float cj = cr[c];
+      oa = fmaf(wA[j], cr[2 * d + c], oa); oa = fmaf(tA[j], cj, oa);
+      ob = fmaf(wB[j], cr[3 * d + c], ob); ob = fmaf(tB[j], cj, ob);
+    }
+    for (int e = 0; e < n_exp; ++e) {
+      const float be = bexp[(long)e * d + c];
+      oa = fmaf(sA[e], be, oa);
+      ob = fmaf(sB[e], be, ob);
+    }
+    const float sg = sigmoidf_(cp[4 * d + c]);
+    x_out[(long)r * ldxo + c] = x_in[(long)r * ldxi + c] + (sg * oa + (1.0f - sg) * ob);
+  }
+}
+
+cudaError_t launch_dyn_exp_step(const DecState& s, int layer, int p, const float* qexp, const float* bexp, int n_exp,
+                                const int* row_len, const float* x_in, long ldxi, float* x_out, long ldxo, int d,
+                                int beam, cudaStream_t st) {
+  (void)beam;
+  if (s.P > 128 || (d & 3) || n_exp > 64) return cudaErrorInvalidValue;
+  const size_t smem = (size_t)(s.P * 7 + n_exp * 3 + 4 * n_exp * s.P + 32) * sizeof(float);
+  if (smem > 48 * 1024) {
+    static size_t configured = 0;
+    if (smem > configured) {
+      cudaError_t e = cudaFuncSetAttribute(dyn_exp_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return e;
+      configured = smem;
+    }
+  }
+  dyn_exp_step_kernel<<<s.R, 256, smem, st>>>(s, layer, p, qexp, bexp, n_exp, row_len, x_in, ldxi, x_out, ldxo, d);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
+// Cross attention for one query position per row (reference models/layers.py:266-295).
+// K/V of the encoder output are projected once per image and shared by its beams; one CTA
+// per (image, head) stages that head's K and V in shared memory and serves all rows of the image.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(160) cross_attn_step_kernel(const float* __restrict__ q, long ldq,
+                                                              const float* __restrict__ kv, long ldkv, int k_off,
+                                                              int v_off, float* __restrict__ out, long ldo,
+                                                              int rows_per_image, int n, int dk,
+                                                              const int* __restrict__ n_valid,
+                                                              const int* __restrict__ row_len, int p) {
+  extern __shared__ float sm[];
+  const int b = blockIdx.x, h = blockIdx.y, tid = threadIdx.x;
+  const int ks = dk + 1;
+  float* Ks = sm;                 // [n][dk+1]
+  float* Vs = Ks + n * ks;        // [n][dk+1]
+  float* qs = Vs + n * ks;        // [dk]
+  float* pr = qs + dk;            // [n]
+  float* red = pr + n;            // [32]
+  for (int i = tid; i < n * dk; i += blockDim.x) {
+    const int j = i / dk, c = i % dk;
+    const float* row = kv + ((long)b * n + j) * ldkv + h * dk + c;
+    Ks[j * ks + c] = row[k_off];
+    Vs[j * ks + c] = row[v_off];
+  }
+  const int nv = n_valid ? n_valid[b] : n;
+  const float sq = sqrtf((float)dk);
+  for (int i = 0; i < rows_per_image; ++i) {
+    const int r = b * rows_per_image + i;
+    __syncthreads();
+    for (int c = tid; c < dk; c += blockDim.x) qs[c] = q[(long)r * ldq + h * dk + c];
+    __syncthreads();
+    const bool row_padded = row_len && p >= row_len[r];
+    float lmax = -INFINITY;
+    for (int j = tid; j < n; j += blockDim.x) {
+      float a = 0.f;
+      for (int c = 0; c < dk; ++c) a = fmaf(qs[c], Ks[j * ks + c], a);
+      a = a / sq;
+      if (row_padded || j >= nv) a = kCrossFill;
+      pr[j] = a;
+      lmax = fmaxf(lmax, a);
+    }
+    const float mx = block_max(lmax, red);
+    float lsum = 0.f;
+    for (int j = tid; j < n; j += blockDim.x) {
+      const float e = expf(pr[j] - mx);
+      pr[j] = e;
+      lsum += e;
+    }
+    const float sum = block_sum(lsum, red);
+    __syncthreads();
+    for (int j = tid; j < n; j += blockDim.x) pr[j] = pr[j] / sum;
+    __syncthreads();
+    for (int c = tid; c < dk; c += blockDim.x) {
+      float o = 0.f;
+      for (int j = 0; j < n; ++j) o = fmaf(pr[j], Vs[j * ks + c], o);
+      out[(long)r * ldo + h * dk + c] = o;
+    }
+  }
+}
+
+cudaError_t launch_cross_attn_step(const float* q, long ldq, const float* kv, long ldkv, int k_off, int v_off,
+                                   float* out, long ldo, int R, int rows_per_image, int n_keys, int heads, int dk,
+                                   const int* n_valid, const int* row_len, int p, cudaStream_t st) {
+  if (R % rows_per_image) return cudaErrorInvalidValue;
+  const size_t smem = ((size_t)2 * n_keys * (dk + 1) + dk + n_keys + 32) * sizeof(float);
+  static size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(cross_attn_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    configured = smem;
+  }
+  cross_attn_step_kernel<<<dim3(R / rows_per_image, heads), 160, smem, st>>>(q, ldq, kv, ldkv, k_off, v_off, out, ldo,
+                                                                            rows_per_image, n_keys, dk, n_valid,
+                                                                            row_len, p);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
+// log-softmax over the vocabulary + top-k (reference End_ExpansionNet_v2.py:204-207 and
+// captioning_model.py:302-317).  One CTA per row; lp = (x - max) - log(sum exp(x - max)).
+// Top-k order: descending value, ties to the lower index.
+// ------------------------------------------------------------------------------------------
+constexpr int kMaxTopK = 8;
+
+__device__ __forceinline__ bool better(float v, int i, float bv, int bi) { return v > bv || (v == bv && i < bi); }
+
+__global__ void __launch_bounds__(256) logsoftmax_topk_kernel(const float* __restrict__ logits, long ld, int V, int k,
+                                                              float* __restrict__ top_val, int* __restrict__ top_idx,
+                                                              float* __restrict__ logprob, long ldlp, int write_mode) {
+  __shared__ float red[32];
+  __shared__ float cv[256];
+  __shared__ int ci[256];
+  __shared__ int win_tid;
+  const int r = blockIdx.x, tid = threadIdx.x;
+  const float* x = logits + (long)r * ld;
+  float lmax = -INFINITY;
+  for (int i = tid; i < V; i += 256) lmax = fmaxf(lmax, x[i]);
+  const float mx = block_max(lmax, red);
+  float ls = 0.f;
+  for (int i = tid; i < V; i += 256) ls += expf(x[i] - mx);
+  const float lse = logf(block_sum(ls, red));
+  __syncthreads();
+  float tv[kMaxTopK];
+  int ti[kMaxTopK];
+#pragma unroll
+  for (int j = 0; j < kMaxTopK; ++j) { tv[j] = -INFINITY; ti[j] = 0x7fffffff; }
+  for (int i = tid; i < V; i += 256) {
+    const float v = (x[i] - mx) - lse;
+    if (write_mode == 1) logprob[(long)r * ldlp + i] = v;
+    if (k > 0 && better(v, i, tv[kMaxTopK - 1], ti[kMaxTopK - 1])) {
+      tv[kMaxTopK - 1] = v; ti[kMaxTopK - 1] = i;
+#pragma unroll
+      for (int j = kMaxTopK - 1; j > 0; --j) {
+        if (better(tv[j], ti[j], tv[j - 1], ti[j - 1])) {
+          const float fv = tv[j]; tv[j] = tv[j - 1]; tv[j - 1] = fv;
+          const int fi = ti[j]; ti[j] = ti[j - 1]; ti[j - 1] = fi;
+        }
+      }
+    }
+  }
+  for (int round = 0; round < k; ++round) {
+    cv[tid] = tv[0]; ci[tid] = ti[0];
+    __syncthreads();
+    if (tid < 32) {
+      float bv = -INFINITY; int bi = 0x7fffffff, bt = 0;
+      for (int t = tid; t < 256; t += 32)
+        if (better(cv[t], ci[t], bv, bi)) { bv = cv[t]; bi = ci[t]; bt = t; }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        const int ot = __shfl_xor_sync(0xffffffffu, bt, o);
+        if (better(ov, oi, bv, bi)) { bv = ov; bi = oi; bt = ot; }
+      }
+      if (tid == 0) {
+        top_val[(long)r * k + round] = bv;
+        top_idx[(long)r * k + round] = bi;
+        win_tid = bt;
+      }
+    }
+    __syncthreads();
+    if (tid == win_tid) {
+#pragma unroll
+      for (int j = 0; j < kMaxTopK - 1; ++j) { tv[j] = tv[j + 1]; ti[j] = ti[j + 1]; }
+      tv[kMaxTopK - 1] = -INFINITY; ti[kMaxTopK - 1] = 0x7fffffff;
+    }
+    __syncthreads();
+  }
+}
+
+cudaError_t launch_logsoftmax_topk(const float* logits, long ld, int rows, int V, int k, float* top_val, int* top_idx,
+                                   float* logprob, long ldlp, int write_mode, cudaStream_t st) {
+  if (k > kMaxTopK) return cudaErrorInvalidValue;
+  logsoftmax_topk_kernel<<<rows, 256, 0, st>>>(logits, ld, V, k, top_val, top_idx, logprob, ldlp, write_mode);
+  return cudaGetLastError();
+}
+
+}  // namespace xn

@@ -1,0 +1,293 @@
+// Bandwidth-bound kernels: LayerNorm (+2x2 merge gather), patch embedding, static-expansion
+// weight normalisation, selector mix, casts.  All reductions are fp32.
+#include "kernels.h"
+#include "common.cuh"
+
+namespace xn {
+
+constexpr float kLnEps = 1e-5f;     // nn.LayerNorm default, used by every LN on the path
+constexpr float kExpEps = 1e-9f;    // expansion eps, reference models/layers.py:106,208
+
+// ------------------------------------------------------------------------------------------
+// LayerNorm over the last dim: one warp per row, three L1-resident passes (mean, var, write).
+// Replaces nn.LayerNorm at swin:342,355,645,778 and layers.py:108-109,210-212, End...:108-110.
+// ------------------------------------------------------------------------------------------
+template <typename OutT>
+__device__ __forceinline__ void store4(OutT* p, float a, float b, float c, float d);
+template <>
+__device__ __forceinline__ void store4<float>(float* p, float a, float b, float c, float d) {
+  *reinterpret_cast<float4*>(p) = make_float4(a, b, c, d);
+}
+template <>
+__device__ __forceinline__ void store4<bf16>(bf16* p, float a, float b, float c, float d) {
+  __nv_bfloat162 lo = __floats2bfloat162_rn(a, b), hi = __floats2bfloat162_rn(c, d);
+  uint2 u;
+  u.x = *reinterpret_cast<uint32_t*>(&lo);
+  u.y = *reinterpret_cast<uint32_t*>(&hi);
+  *reinterpret_cast<uint2*>(p) = u;
+}
+
+template <typename OutT, typename SrcFn>
+__device__ __forceinline__ void ln_row(SrcFn src, const float* __restrict__ g, const float* __restrict__ b,
+                                       OutT* __restrict__ yr, int C, int lane) {
+  float s = 0.f;
+  for (int c = lane * 4; c < C; c += 128) {
+    const float4 v = src(c);
+    s += (v.x + v.y) + (v.z + v.w);
+  }
+  const float mean = warp_sum(s) / (float)C;
+  float q = 0.f;
+  for (int c = lane * 4; c < C; c += 128) {
+    const float4 v = src(c);
+    const float d0 = v.x - mean, d1 = v.y - mean, d2 = v.z - mean, d3 = v.w - mean;
+    q += (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
+  }
+  const float rstd = 1.0f / sqrtf(warp_sum(q) / (float)C + kLnEps);
+  for (int c = lane * 4; c < C; c += 128) {
+    const float4 v = src(c);
+    const float4 gg = *reinterpret_cast<const float4*>(g + c);
+    const float4 bb = *reinterpret_cast<const float4*>(b + c);
+    store4<OutT>(yr + c, (v.x - mean) * rstd * gg.x + bb.x, (v.y - mean) * rstd * gg.y + bb.y,
+                 (v.z - mean) * rstd * gg.z + bb.z, (v.w - mean) * rstd * gg.w + bb.w);
+  }
+}
+
+template <typename OutT>
+__global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, long ldx,
+                                                        const float* __restrict__ g, const float* __restrict__ b,
+                                                        OutT* __restrict__ y, long ldy, long rows, int C) {
+  const long row = (long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const float* xr = x + row * ldx;
+  ln_row<OutT>([&](int c) { return *reinterpret_cast<const float4*>(xr + c); }, g, b, y + row * ldy, C,
+               threadIdx.x & 31);
+}
+
+template <typename OutT>
+cudaError_t launch_layernorm(const float* x, long ldx, const float* gamma, const float* beta, OutT* y, long ldy,
+                             long rows, int C, cudaStream_t st) {
+  if (rows <= 0) return cudaSuccess;
+  if ((C & 3) || (ldx & 3) || (ldy & 3)) return cudaErrorInvalidValue;
+  layernorm_kernel<OutT><<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(x, ldx, gamma, beta, y, ldy, rows, C);
+  return cudaGetLastError();
+}
+template cudaError_t launch_layernorm<float>(const float*, long, const float*, const float*, float*, long, long, int, cudaStream_t);
+template cudaError_t launch_layernorm<bf16>(const float*, long, const float*, const float*, bf16*, long, long, int, cudaStream_t);
+
+// PatchMerging gather + LN(4C): reference swin:482-501.  Output row (b,i,j) concatenates the
+// input tokens (2i,2j), (2i+1,2j), (2i,2j+1), (2i+1,2j+1) in that order.
+template <typename OutT>
+__global__ void __launch_bounds__(256) merge_layernorm_kernel(const float* __restrict__ x, const float* __restrict__ g,
+                                                              const float* __restrict__ b, OutT* __restrict__ y,
+                                                              int B, int H, int C) {
+  const int H2 = H / 2;
+  const long rows = (long)B * H2 * H2;
+  const long row = (long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int bi = (int)(row / (H2 * H2)), rem = (int)(row % (H2 * H2));
+  const int i = rem / H2, j = rem % H2;
+  const float* base = x + (long)bi * H * H * C;
+  auto src = [&](int c) {
+    const int q = c / C, cc = c - q * C;
+    const int dy = q & 1, dx = q >> 1;
+    return *reinterpret_cast<const float4*>(base + ((long)(2 * i + dy) * H + (2 * j + dx)) * C + cc);
+  };
+  ln_row<OutT>(src, g, b, y + row * 4L * C, 4 * C, threadIdx.x & 31);
+}
+
+template <typename OutT>
+cudaError_t launch_merge_layernorm(const float* x, const float* gamma, const float* beta, OutT* y, int B, int H,
+                                   int C, cudaStream_t st) {
+  if (C & 3) return cudaErrorInvalidValue;
+  const long rows = (long)B * (H / 2) * (H / 2);
+  merge_layernorm_kernel<OutT><<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(x, gamma, beta, y, B, H, C);
+  return cudaGetLastError();
+}
+template cudaError_t launch_merge_layernorm<float>(const float*, const float*, const float*, float*, int, int, int, cudaStream_t);
+template cudaError_t launch_merge_layernorm<bf16>(const float*, const float*, const float*, bf16*, int, int, int, cudaStream_t);
+
+// ------------------------------------------------------------------------------------------
+// PatchEmbed (reference swin:611-654): Conv2d(Cin->E, k=stride=P) + flatten + LayerNorm(E).
+// One CTA per (image, patch row): the Cin*P input rows of that patch row are staged in smem
+// (coalesced), the (E x Cin*P*P) filter bank is staged transposed, one warp per patch.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) patch_embed_kernel(const float* __restrict__ img, const float* __restrict__ w,
+                                                          const float* __restrict__ bias, const float* __restrict__ g,
+                                                          const float* __restrict__ be, float* __restrict__ out,
+                                                          int Cin, int S, int P, int E) {
+  extern __shared__ float sm[];
+  const int G = S / P, K = Cin * P * P;
+  float* slab = sm;                       // [Cin*P][S]
+  float* wt = slab + Cin * P * S;         // [K][E]
+  const int b = blockIdx.x / G, py = blockIdx.x % G;
+  for (int i = threadIdx.x; i < Cin * P * S; i += blockDim.x) {
+    const int r = i / S, xcol = i % S, c = r / P, dy = r % P;
+    slab[i] = img[(((long)b * Cin + c) * S + (py * P + dy)) * S + xcol];
+  }
+  for (int i = threadIdx.x; i < K * E; i += blockDim.x) {
+    const int e = i / K, k = i % K;      // w is (E, Cin, P, P) -> k = c*P*P + dy*P + dx
+    wt[k * E + e] = w[i];
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int EP = E / 32;                  // channels per lane (E % 32 == 0, E <= 256)
+  for (int px = warp; px < G; px += nw) {
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = (j < EP) ? bias[lane + 32 * j] : 0.f;
+    for (int k = 0; k < K; ++k) {
+      const int c = k / (P * P), r = k % (P * P), dy = r / P, dx = r % P;
+      const float v = slab[(c * P + dy) * S + px * P + dx];
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (j < EP) acc[j] = fmaf(v, wt[k * E + lane + 32 * j], acc[j]);
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) if (j < EP) s += acc[j];
+    const float mean = warp_sum(s) / (float)E;
+    float q = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) if (j < EP) { const float d = acc[j] - mean; q += d * d; }
+    const float rstd = 1.0f / sqrtf(warp_sum(q) / (float)E + kLnEps);
+    float* o = out + (((long)b * G + py) * G + px) * E;
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if (j < EP) { const int e = lane + 32 * j; o[e] = (acc[j] - mean) * rstd * g[e] + be[e]; }
+  }
+}
+
+cudaError_t launch_patch_embed(const float* img, const float* w, const float* b, const float* gamma,
+                               const float* beta, float* out, int B, int Cin, int S, int P, int E,
+                               cudaStream_t st) {
+  if (E % 32 || E > 256 || S % P) return cudaErrorInvalidValue;
+  const size_t smem = ((size_t)Cin * P * S + (size_t)Cin * P * P * E) * sizeof(float);
+  static size_t configured = 0;
+  if (smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(patch_embed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    configured = smem;
+  }
+  patch_embed_kernel<<<B * (S / P), 256, smem, st>>>(img, w, b, gamma, beta, out, Cin, S, P, E);
+  return cudaGetLastError();
+}
+
+template <typename T>
+__global__ void cast_kernel(const float* __restrict__ x, T* __restrict__ y, long n) {
+  const long i = ((long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i + 3 < n) {
+    const float4 v = *reinterpret_cast<const float4*>(x + i);
+    store4<T>(y + i, v.x, v.y, v.z, v.w);
+  } else {
+    for (long j = i; j < n; ++j) y[j] = from_f32<T>(x[j]);
+  }
+}
+template <typename T>
+cudaError_t launch_cast(const float* x, T* y, long n, cudaStream_t st) {
+  if (n <= 0) return cudaSuccess;
+  cast_kernel<T><<<(unsigned)((n / 4 + 256) / 256), 256, 0, st>>>(x, y, n);
+  return cudaGetLastError();
+}
+template cudaError_t launch_cast<bf16>(const float*, bf16*, long, cudaStream_t);
+template cudaError_t launch_cast<float>(const float*, float*, long, cudaStream_t);
+
+// ------------------------------------------------------------------------------------------
+// Static expansion weights (reference models/layers.py:55-92).
+//   a_fw[b,e,n] = relu(z)[b,e,n]*[n < n_valid_b] / (sum_n ... + eps)          (row normalise)
+//   a_bw[b,n,e] = relu(z)[b,e,n] / (sum_{e' in group(e)} relu(z)[b,e',n] + eps) (per-group)
+// and the same for relu(-z).  Two launches: per-group column sums, then the scaled writes.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) se_group_sum_kernel(const float* __restrict__ z, const int* __restrict__ gstart,
+                                                           float* __restrict__ gsum, int E, int N, int n_groups) {
+  const int b = blockIdx.x, g = blockIdx.y;
+  const int e0 = gstart[g], e1 = gstart[g + 1];
+  for (int n = threadIdx.x; n < N; n += blockDim.x) {
+    float sa = 0.f, sb = 0.f;
+    const float* zp = z + ((long)b * E + e0) * N + n;
+    for (int e = e0; e < e1; ++e, zp += N) {
+      const float v = *zp;
+      sa += fmaxf(v, 0.f);
+      sb += fmaxf(-v, 0.f);
+    }
+    gsum[(((long)b * n_groups + g) * 2 + 0) * N + n] = sa;
+    gsum[(((long)b * n_groups + g) * 2 + 1) * N + n] = sb;
+  }
+}
+
+__global__ void __launch_bounds__(256) se_weights_kernel(const float* __restrict__ z, const int* __restrict__ n_valid,
+                                                         const int* __restrict__ gstart, int n_groups,
+                                                         const float* __restrict__ gsum, float* __restrict__ a_fw,
+                                                         float* __restrict__ b_fw, float* __restrict__ a_bw,
+                                                         float* __restrict__ b_bw, int E, int N, int chunk) {
+  extern __shared__ float zt[];            // [chunk][N]
+  const int b = blockIdx.x, e0 = blockIdx.y * chunk;
+  const int nv = n_valid ? n_valid[b] : N;
+  int g = 0;
+  while (g + 1 < n_groups && gstart[g + 1] <= e0) ++g;
+  const float* zp = z + ((long)b * E + e0) * N;
+  for (int i = threadIdx.x; i < chunk * N; i += blockDim.x) zt[i] = zp[i];
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int e = warp; e < chunk; e += nw) {
+    float sa = 0.f, sb = 0.f;
+    for (int n = lane; n < nv; n += 32) {
+      const float v = zt[e * N + n];
+      sa += fmaxf(v, 0.f);
+      sb += fmaxf(-v, 0.f);
+    }
+    sa = warp_sum(sa) + kExpEps;
+    sb = warp_sum(sb) + kExpEps;
+    float* ao = a_fw + ((long)b * E + e0 + e) * N;
+    float* bo = b_fw + ((long)b * E + e0 + e) * N;
+    for (int n = lane; n < N; n += 32) {
+      const float v = zt[e * N + n];
+      const bool ok = n < nv;
+      ao[n] = ok ? fmaxf(v, 0.f) / sa : 0.f;
+      bo[n] = ok ? fmaxf(-v, 0.f) / sb : 0.f;
+    }
+  }
+  const float* ga = gsum + (((long)b * n_groups + g) * 2 + 0) * N;
+  const float* gb = ga + N;
+  for (int i = threadIdx.x; i < chunk * N; i += blockDim.x) {
+    const int e = i % chunk, n = i / chunk;
+    const float v = zt[e * N + n];
+    const long o = ((long)b * N + n) * E + e0 + e;
+    a_bw[o] = fmaxf(v, 0.f) / (ga[n] + kExpEps);
+    b_bw[o] = fmaxf(-v, 0.f) / (gb[n] + kExpEps);
+  }
+}
+
+cudaError_t launch_static_exp_weights(const float* z, const int* n_valid, const int* group_start, int n_groups,
+                                      float* a_fw, float* b_fw, float* a_bw, float* b_bw, float* gsum_scratch,
+                                      int B, int E, int N, int chunk, cudaStream_t st) {
+  // `chunk` rows of z per CTA; it must divide every group boundary (the engine picks the gcd, <= 32)
+  if (chunk <= 0 || (E % chunk)) return cudaErrorInvalidValue;
+  se_group_sum_kernel<<<dim3(B, n_groups), 160, 0, st>>>(z, group_start, gsum_scratch, E, N, n_groups);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  se_weights_kernel<<<dim3(B, E / chunk), 256, (size_t)chunk * N * sizeof(float), st>>>(
+      z, n_valid, group_start, n_groups, gsum_scratch, a_fw, b_fw, a_bw, b_bw, E, N, chunk);
+  return cudaGetLastError();
+}
+
+// x_out = x_in + sigmoid(sel)*a + (1-sigmoid(sel))*b     (reference layers.py:98-102,118-120)
+__global__ void selector_mix_kernel(const float* __restrict__ xi, long ldxi, const float* __restrict__ sel, long lds,
+                                    const float* __restrict__ a, const float* __restrict__ bb, long ldo,
+                                    float* __restrict__ xo, long ldxo, long rows, int d) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * d) return;
+  const long r = i / d;
+  const int c = (int)(i % d);
+  const float s = sigmoidf_(sel[r * lds + c]);
+  xo[r * ldxo + c] = xi[r * ldxi + c] + (s * a[r * ldo + c] + (1.0f - s) * bb[r * ldo + c]);
+}
+cudaError_t launch_selector_mix(const float* x_in, long ldxi, const float* sel, long lds, const float* out_a,
+                                const float* out_b, long ldo, float* x_out, long ldxo, long rows, int d,
+                                cudaStream_t st) {
+  const long n = rows * d;
+  selector_mix_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(x_in, ldxi, sel, lds, out_a, out_b, ldo, x_out,
+                                                                  ldxo, rows, d);
+  return cudaGetLastError();
+}
+
+}  // namespace xn

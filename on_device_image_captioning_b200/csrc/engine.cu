@@ -1,0 +1,946 @@
+// xnv2_b200 engine: weight store, workspace, forward orchestration and the C ABI
+// (include/xnv2_b200.h).  Host code only launches kernels of this library on the caller's
+// stream; there is no CPU compute path.
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstdarg>
+#include <cstring>
+#include <cmath>
+#include <string>
+#include <vector>
+#include <unordered_map>
+#include <algorithm>
+
+#include "../../include/xnv2_b200.h"
+#include "kernels.h"
+
+using namespace xn;
+
+cudaError_t launch_widen_bf16(const bf16* x, float* y, long n, cudaStream_t st);
+
+namespace {
+
+std::string g_create_error;
+
+struct DevTensor {
+  float* p = nullptr;
+  std::vector<int64_t> shape;
+  size_t n = 0;
+};
+
+struct LinW {
+  const float* w = nullptr;   // (N, K) fp32
+  const bf16* wb = nullptr;   // (N, K) bf16 copy (bf16 mode)
+  const float* b = nullptr;   // (N) or null
+  int N = 0, K = 0;
+};
+
+struct SwinBlockW { const float *n1g, *n1b, *n2g, *n2b, *rpb; LinW qkv, proj, fc1, fc2; };
+struct SwinStageW {
+  int C, H, heads;
+  std::vector<SwinBlockW> blocks;
+  bool has_merge = false;
+  const float *mg = nullptr, *mb = nullptr;
+  LinW red;
+};
+struct EncLayerW { const float *n1g, *n1b, *n2g, *n2b, *qexp, *bexp; LinW kabs, ff1, ff2; };
+struct DecLayerW { const float *n1g, *n1b, *n2g, *n2b, *n3g, *n3b, *qexp, *bexp; LinW dyn5, wq, wo, ff1, ff2; };
+
+struct Arena {
+  char* base = nullptr;
+  size_t cap = 0, off = 0;
+  bool overflow = false;
+  void reset() { off = 0; overflow = false; }
+  template <typename T> T* get(size_t n) {
+    size_t bytes = (n * sizeof(T) + 255) & ~size_t(255);
+    T* p = reinterpret_cast<T*>(base + off);
+    off += bytes;
+    if (off > cap) overflow = true;
+    return p;
+  }
+};
+
+}  // namespace
+
+struct xn_handle {
+  xn_config cfg;
+  int device = 0;
+  int precision = -1;                 // -1: weights not finalised
+  std::string err;
+  std::unordered_map<std::string, DevTensor> raw;
+  std::vector<void*> owned;           // packed buffers
+  // packed views
+  const float *pe_w, *pe_b, *pe_g, *pe_beta, *swin_ng, *swin_nb;
+  std::vector<SwinStageW> stages;
+  std::vector<EncLayerW> enc;
+  std::vector<DecLayerW> dec;
+  LinW input_linear, vocab, enc_reduce, dec_reduce, kv_all;
+  const float *enc_ng, *enc_nb, *dec_ng, *dec_nb, *emb, *pos;
+  int* group_start_dev = nullptr;
+  int n_exp_total = 0, exp_chunk = 8;
+  Arena ws;
+  int64_t launches = 0;
+  int64_t swin_chunk = 32, enc_chunk = 64;
+  float* io_in = nullptr; size_t io_in_cap = 0;     // xn_caption_host staging
+  char* io_out = nullptr; size_t io_out_cap = 0;
+
+  int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    err = buf;
+    return code;
+  }
+};
+
+#define CU(expr)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e_ = (expr);                                                                       \
+    if (e_ != cudaSuccess) return h->fail(XN_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+#define WS_CHECK()                                                                                 \
+  do {                                                                                             \
+    if (h->ws.overflow) return h->fail(XN_ERR_STATE, "workspace overflow: need %zu have %zu (%s:%d)", h->ws.off, h->ws.cap, __FILE__, __LINE__); \
+  } while (0)
+#define KL(n, expr)                                                                                \
+  do {                                                                                             \
+    cudaError_t e_ = (expr);                                                                       \
+    h->launches += (n);                                                                            \
+    if (e_ != cudaSuccess) return h->fail(XN_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+
+namespace {
+
+int ensure_ws(xn_handle* h, size_t bytes, cudaStream_t st) {
+  bytes += 1 << 20;
+  if (h->ws.cap < bytes) {
+    if (h->ws.base) {
+      CU(cudaStreamSynchronize(st));
+      CU(cudaDeviceSynchronize());
+      CU(cudaFree(h->ws.base));
+      h->ws.base = nullptr;
+      h->ws.cap = 0;
+    }
+    CU(cudaMalloc(&h->ws.base, bytes));
+    h->ws.cap = bytes;
+  }
+  h->ws.reset();
+  return 0;
+}
+
+// ---- generic linear: y = act(x W^T / div + b) + res -------------------------------------------
+int lin_f32(xn_handle* h, const float* x, long ldx, const LinW& w, const float* res, long ldr, float* y, long ldy,
+            int M, int act, cudaStream_t st) {
+  GemmArgs g{};
+  g.A = x; g.lda = ldx; g.sA = 0;
+  g.W = w.w; g.ldw = w.K; g.sW = 0;
+  g.C = y; g.ldc = ldy; g.sC = 0;
+  g.bias = w.b; g.res = res; g.ldr = ldr; g.sR = 0;
+  g.M = M; g.N = w.N; g.K = w.K; g.batch = 1; g.div = 0.f; g.act = act; g.w_kn = 0;
+  KL(1, launch_gemm_f32(g, st));
+  return 0;
+}
+int lin_tc(xn_handle* h, const bf16* x, long ldx, const LinW& w, const float* res, long ldr, float* yf, bf16* yb,
+           long ldy, int M, int act, cudaStream_t st) {
+  TcGemmArgs g{};
+  g.A = x; g.lda = ldx; g.W = w.wb; g.ldw = w.K; g.Cf = yf; g.Cb = yb; g.ldc = ldy;
+  g.bias = w.b; g.res = res; g.ldr = ldr; g.M = M; g.N = w.N; g.K = w.K; g.div = 0.f; g.act = act;
+  KL(1, launch_gemm_tc(g, st));
+  return 0;
+}
+
+// activation-type dispatch used by the templated Swin forward
+template <typename T> struct ActOps;
+template <> struct ActOps<float> {
+  static int lin_act(xn_handle* h, const float* x, long ldx, const LinW& w, float* y, long ldy, int M, int act, cudaStream_t st) {
+    return lin_f32(h, x, ldx, w, nullptr, 0, y, ldy, M, act, st);
+  }
+  static int lin_res(xn_handle* h, const float* x, long ldx, const LinW& w, const float* res, long ldr, float* y, long ldy, int M, cudaStream_t st) {
+    return lin_f32(h, x, ldx, w, res, ldr, y, ldy, M, 0, st);
+  }
+};
+template <> struct ActOps<bf16> {
+  static int lin_act(xn_handle* h, const bf16* x, long ldx, const LinW& w, bf16* y, long ldy, int M, int act, cudaStream_t st) {
+    return lin_tc(h, x, ldx, w, nullptr, 0, nullptr, y, ldy, M, act, st);
+  }
+  static int lin_res(xn_handle* h, const bf16* x, long ldx, const LinW& w, const float* res, long ldr, float* y, long ldy, int M, cudaStream_t st) {
+    return lin_tc(h, x, ldx, w, res, ldr, y, nullptr, ldy, M, 0, st);
+  }
+};
+
+// ---- Swin backbone --------------------------------------------------------------------------
+size_t swin_ws_bytes(const xn_config& c, int Bc, int prec) {
+  const size_t G = c.img_size / c.patch_size, L0 = G * G, C0 = c.embed_dim;
+  const size_t act = prec == XN_PREC_BF16 ? 2 : 4;
+  size_t tok = (size_t)Bc * L0 * C0;                 // elements of x at stage 0 (largest)
+  size_t b = 0;
+  b += 2 * tok * 4;                                   // x, x2 (fp32 residual stream, ping-pong over merges)
+  b += tok * act;                                     // xn
+  b += 3 * tok * act;                                 // qkv
+  b += tok * act;                                     // attention out
+  b += (size_t)(c.mlp_ratio * tok) * act + 4096;      // mlp hidden
+  return b + 16 * 256;
+}
+
+template <typename T>
+int swin_forward_chunk(xn_handle* h, const float* img, int Bc, float* out, cudaStream_t st) {
+  const xn_config& c = h->cfg;
+  const int G = c.img_size / c.patch_size;
+  const size_t tok0 = (size_t)Bc * G * G * c.embed_dim;
+  float* x = h->ws.get<float>(tok0);
+  float* x2 = h->ws.get<float>(tok0);
+  T* xn = h->ws.get<T>(tok0);
+  T* qkv = h->ws.get<T>(3 * tok0);
+  T* ao = h->ws.get<T>(tok0);
+  T* hid = h->ws.get<T>((size_t)(c.mlp_ratio * tok0) + 1024);
+  WS_CHECK();
+  KL(1, launch_patch_embed(img, h->pe_w, h->pe_b, h->pe_g, h->pe_beta, x, Bc, c.in_chans, c.img_size, c.patch_size,
+                           c.embed_dim, st));
+  for (size_t si = 0; si < h->stages.size(); ++si) {
+    const SwinStageW& S = h->stages[si];
+    const int C = S.C, H = S.H, M = Bc * H * H;
+    for (size_t bi = 0; bi < S.blocks.size(); ++bi) {
+      const SwinBlockW& W = S.blocks[bi];
+      const int shift = (bi % 2 == 1 && H > c.window_size) ? c.window_size / 2 : 0;
+      KL(1, launch_layernorm<T>(x, C, W.n1g, W.n1b, xn, C, M, C, st));
+      if (int r = ActOps<T>::lin_act(h, xn, C, W.qkv, qkv, 3 * C, M, 0, st)) return r;
+      KL(1, launch_window_attention<T>(qkv, W.rpb, ao, Bc, H, C, S.heads, shift, st));
+      if (int r = ActOps<T>::lin_res(h, ao, C, W.proj, x, C, x, C, M, st)) return r;
+      KL(1, launch_layernorm<T>(x, C, W.n2g, W.n2b, xn, C, M, C, st));
+      if (int r = ActOps<T>::lin_act(h, xn, C, W.fc1, hid, W.fc1.N, M, 1, st)) return r;
+      if (int r = ActOps<T>::lin_res(h, hid, W.fc1.N, W.fc2, x, C, x, C, M, st)) return r;
+    }
+    if (S.has_merge) {
+      const int M4 = Bc * (H / 2) * (H / 2);
+      KL(1, launch_merge_layernorm<T>(x, S.mg, S.mb, xn, Bc, H, C, st));     // xn viewed as (M4, 4C)
+      if (int r = ActOps<T>::lin_res(h, xn, 4 * C, S.red, nullptr, 0, x2, 2 * C, M4, st)) return r;
+      std::swap(x, x2);
+    }
+  }
+  const SwinStageW& Sl = h->stages.back();
+  KL(1, launch_layernorm<float>(x, Sl.C, h->swin_ng, h->swin_nb, out, Sl.C, (long)Bc * Sl.H * Sl.H, Sl.C, st));
+  return 0;
+}
+
+int swin_forward(xn_handle* h, const float* img, int B, float* out, cudaStream_t st) {
+  const xn_config& c = h->cfg;
+  const SwinStageW& Sl = h->stages.back();
+  const size_t img_elems = (size_t)c.in_chans * c.img_size * c.img_size;
+  const size_t out_elems = (size_t)Sl.H * Sl.H * Sl.C;
+  const int chunk = (int)std::max<int64_t>(1, h->swin_chunk);
+  for (int b0 = 0; b0 < B; b0 += chunk) {
+    const int Bc = std::min(chunk, B - b0);
+    h->ws.reset();
+    int r = (h->precision == XN_PREC_BF16) ? swin_forward_chunk<bf16>(h, img + b0 * img_elems, Bc, out + b0 * out_elems, st)
+                                           : swin_forward_chunk<float>(h, img + b0 * img_elems, Bc, out + b0 * out_elems, st);
+    if (r) return r;
+  }
+  return 0;
+}
+
+// ---- expansion encoder ----------------------------------------------------------------------
+size_t enc_ws_bytes(const xn_config& c, int Bc) {
+  const size_t N = c.enc_len, d = c.d_model, E = 0;
+  (void)E;
+  size_t e = 0;
+  for (int i = 0; i < c.n_exp_groups; ++i) e += c.exp_groups[i];
+  const size_t M = (size_t)Bc * N;
+  size_t f = 0;
+  f += M * d;                       // x0
+  f += M * d * c.n_enc;             // xcat
+  f += M * d;                       // xn
+  f += M * 4 * d;                   // kabs
+  f += 5 * (size_t)Bc * e * N;      // z, a_fw, b_fw, a_bw, b_bw
+  f += 2 * (size_t)Bc * e * d;      // CA, CB
+  f += 2 * M * d;                   // outA, outB
+  f += M * c.ff;                    // ff hidden
+  f += (size_t)Bc * c.n_exp_groups * 2 * N;   // group sums
+  f += M * d;                       // pre-norm output
+  return f * 4 + Bc * 4 + 32 * 256;
+}
+
+int enc_body_chunk(xn_handle* h, const float* feats, int Bc, const int* n_valid_dev, float* out, cudaStream_t st) {
+  const xn_config& c = h->cfg;
+  const int N = c.enc_len, d = c.d_model, E = h->n_exp_total, M = Bc * N, ne = c.n_enc;
+  float* x0 = h->ws.get<float>((size_t)M * d);
+  float* xcat = h->ws.get<float>((size_t)M * d * ne);
+  float* xn = h->ws.get<float>((size_t)M * d);
+  float* kabs = h->ws.get<float>((size_t)M * 4 * d);
+  float* z = h->ws.get<float>((size_t)Bc * E * N);
+  float* afw = h->ws.get<float>((size_t)Bc * E * N);
+  float* bfw = h->ws.get<float>((size_t)Bc * E * N);
+  float* abw = h->ws.get<float>((size_t)Bc * E * N);
+  float* bbw = h->ws.get<float>((size_t)Bc * E * N);
+  float* CA = h->ws.get<float>((size_t)Bc * E * d);
+  float* CB = h->ws.get<float>((size_t)Bc * E * d);
+  float* oA = h->ws.get<float>((size_t)M * d);
+  float* oB = h->ws.get<float>((size_t)M * d);
+  float* hid = h->ws.get<float>((size_t)M * c.ff);
+  float* gs = h->ws.get<float>((size_t)Bc * c.n_exp_groups * 2 * N);
+  float* pre = h->ws.get<float>((size_t)M * d);
+  WS_CHECK();
+  const long ldc = (long)d * ne;
+
+  if (int r = lin_f32(h, feats, c.feat_dim, h->input_linear, nullptr, 0, x0, d, M, 0, st)) return r;
+  for (int l = 0; l < ne; ++l) {
+    const EncLayerW& W = h->enc[l];
+    const float* xin = l == 0 ? x0 : xcat + (size_t)(l - 1) * d;
+    const long ldi = l == 0 ? d : ldc;
+    float* xout = xcat + (size_t)l * d;
+    KL(1, launch_layernorm<float>(xin, ldi, W.n1g, W.n1b, xn, d, M, d, st));
+    if (int r = lin_f32(h, xn, d, W.kabs, nullptr, 0, kabs, 4 * d, M, 0, st)) return r;
+    GemmArgs g{};
+    // z[b] = Q (E x d) . key[b]^T / sqrt(d)            reference layers.py:52
+    g.A = W.qexp; g.lda = d; g.sA = 0;
+    g.W = kabs; g.ldw = 4 * d; g.sW = (long)N * 4 * d; g.w_kn = 0;
+    g.C = z; g.ldc = N; g.sC = (long)E * N;
+    g.M = E; g.N = N; g.K = d; g.batch = Bc; g.div = sqrtf((float)d); g.act = 0;
+    KL(1, launch_gemm_f32(g, st));
+    KL(2, launch_static_exp_weights(z, n_valid_dev, h->group_start_dev, c.n_exp_groups, afw, bfw, abw, bbw, gs, Bc, E, N,
+                                    h->exp_chunk, st));
+    // class_a = a_fw . A + bias_exp ; class_b = b_fw . B + bias_exp      layers.py:62-63
+    for (int ab = 0; ab < 2; ++ab) {
+      GemmArgs q{};
+      q.A = ab ? bfw : afw; q.lda = N; q.sA = (long)E * N;
+      q.W = kabs + (size_t)(1 + ab) * d; q.ldw = 4 * d; q.sW = (long)N * 4 * d; q.w_kn = 1;
+      q.C = ab ? CB : CA; q.ldc = d; q.sC = (long)E * d;
+      q.res = W.bexp; q.ldr = d; q.sR = 0;
+      q.M = E; q.N = d; q.K = N; q.batch = Bc;
+      KL(1, launch_gemm_f32(q, st));
+    }
+    // out = bw . class / n_groups                                          layers.py:82-83
+    for (int ab = 0; ab < 2; ++ab) {
+      GemmArgs q{};
+      q.A = ab ? bbw : abw; q.lda = E; q.sA = (long)N * E;
+      q.W = ab ? CB : CA; q.ldw = d; q.sW = (long)E * d; q.w_kn = 1;
+      q.C = ab ? oB : oA; q.ldc = d; q.sC = (long)N * d;
+      q.M = N; q.N = d; q.K = E; q.batch = Bc; q.div = (float)c.n_exp_groups;
+      KL(1, launch_gemm_f32(q, st));
+    }
+    KL(1, launch_selector_mix(xin, ldi, kabs + 3 * (size_t)d, 4 * d, oA, oB, d, xout, ldc, M, d, st));
+    KL(1, launch_layernorm<float>(xout, ldc, W.n2g, W.n2b, xn, d, M, d, st));
+    if (int r = lin_f32(h, xn, d, W.ff1, nullptr, 0, hid, c.ff, M, 2, st)) return r;
+    if (int r = lin_f32(h, hid, c.ff, W.ff2, xout, ldc, xout, ldc, M, 0, st)) return r;
+  }
+  if (int r = lin_f32(h, xcat, ldc, h->enc_reduce, xcat + (size_t)(ne - 1) * d, ldc, pre, d, M, 0, st)) return r;
+  KL(1, launch_layernorm<float>(pre, d, h->enc_ng, h->enc_nb, out, d, M, d, st));
+  return 0;
+}
+
+// encoder on features already on the device; pads handled via n_valid
+int enc_body(xn_handle* h, const float* feats, int B, const int32_t* enc_pads_host, float* out, cudaStream_t st) {
+  const xn_config& c = h->cfg;
+  const int chunk = (int)std::max<int64_t>(1, h->enc_chunk);
+  for (int b0 = 0; b0 < B; b0 += chunk) {
+    const int Bc = std::min(chunk, B - b0);
+    h->ws.reset();
+    int* nv = nullptr;
+    if (enc_pads_host) {
+      bool any = false;
+      std::vector<int> v(Bc);
+      for (int i = 0; i < Bc; ++i) { v[i] = c.enc_len - enc_pads_host[b0 + i]; any |= enc_pads_host[b0 + i] != 0; }
+      if (any) {
+        nv = h->ws.get<int>(Bc);
+        CU(cudaMemcpyAsync(nv, v.data(), Bc * sizeof(int), cudaMemcpyHostToDevice, st));
+        CU(cudaStreamSynchronize(st));   // v is a stack-lifetime host buffer
+      }
+    }
+    if (int r = enc_body_chunk(h, feats + (size_t)b0 * c.enc_len * c.feat_dim, Bc, nv,
+                               out + (size_t)b0 * c.enc_len * c.d_model, st))
+      return r;
+  }
+  return 0;
+}
+
+// ---- decoder --------------------------------------------------------------------------------
+struct DecBufs {
+  DecState s;
+  float *x0, *ycat, *xn, *q, *att, *hid, *pre, *yn, *kv;
+  int R, P;
+};
+
+size_t dec_ws_bytes(const xn_config& c, int R, int P, int n_images, bool own_logits) {
+  const size_t d = c.d_model;
+  size_t f = 0;
+  f += (size_t)c.n_dec * P * R * 5 * d;
+  f += (size_t)c.n_dec * P * R * 2 * c.num_exp_dec * P;
+  f += (size_t)c.n_dec * P * R * c.num_exp_dec;
+  f += (size_t)R * d * (6 + c.n_dec) + (size_t)R * c.ff;
+  f += (size_t)n_images * c.enc_len * c.n_dec * 2 * d;
+  if (own_logits) f += (size_t)R * c.vocab;
+  return f * 4 + 64 * 256;
+}
+
+int dec_alloc(xn_handle* h, DecBufs& D, int R, int P, int n_images) {
+  const xn_config& c = h->cfg;
+  const size_t d = c.d_model;
+  D.R = R; D.P = P;
+  D.s.cache = h->ws.get<float>((size_t)c.n_dec * P * R * 5 * d);
+  D.s.cw = 5 * (int)d;
+  D.s.fw = h->ws.get<float>((size_t)c.n_dec * P * R * 2 * c.num_exp_dec * P);
+  D.s.qk = h->ws.get<float>((size_t)c.n_dec * P * R * c.num_exp_dec);
+  D.s.anc = nullptr; D.s.P = P; D.s.R = R;
+  D.x0 = h->ws.get<float>((size_t)R * d);
+  D.ycat = h->ws.get<float>((size_t)R * d * c.n_dec);
+  D.xn = h->ws.get<float>((size_t)R * d);
+  D.q = h->ws.get<float>((size_t)R * d);
+  D.att = h->ws.get<float>((size_t)R * d);
+  D.hid = h->ws.get<float>((size_t)R * c.ff);
+  D.pre = h->ws.get<float>((size_t)R * d);
+  D.yn = h->ws.get<float>((size_t)R * d);
+  D.kv = h->ws.get<float>((size_t)n_images * c.enc_len * c.n_dec * 2 * d);
+  return 0;
+}
+
+// one decoder position for all rows -> logits (R, V) at `logits` with row stride ldl
+int dec_step(xn_handle* h, DecBufs& D, int p, const int64_t* tok64, const int* tok32, long tok_stride,
+             int rows_per_image, const int* n_valid, const int* row_len, float* logits, long ldl, cudaStream_t st) {
+  const xn_config& c = h->cfg;
+  const int d = c.d_model, R = D.R, nd = c.n_dec;
+  const long ldc = (long)d * nd, ldkv = (long)nd * 2 * d;
+  KL(1, launch_embed(tok64, tok32, tok_stride, p, h->emb, h->pos, D.x0, d, R, d, st));
+  for (int l = 0; l < nd; ++l) {
+    const DecLayerW& W = h->dec[l];
+    const float* xin = l == 0 ? D.x0 : D.ycat + (size_t)(l - 1) * d;
+    const long ldi = l == 0 ? d : ldc;
+    float* xout = D.ycat + (size_t)l * d;
+    KL(1, launch_layernorm<float>(xin, ldi, W.n1g, W.n1b, D.xn, d, R, d, st));
+    float* crow = D.s.cache + (((size_t)l * D.P + p) * R) * D.s.cw;
+    if (int r = lin_f32(h, D.xn, d, W.dyn5, nullptr, 0, crow, D.s.cw, R, 0, st)) return r;
+    KL(1, launch_dyn_exp_step(D.s, l, p, W.qexp, W.bexp, c.num_exp_dec, row_len, xin, ldi, xout, ldc, d, rows_per_image, st));
+    KL(1, launch_layernorm<float>(xout, ldc, W.n2g, W.n2b, D.xn, d, R, d, st));
+    if (int r = lin_f32(h, D.xn, d, W.wq, nullptr, 0, D.q, d, R, 0, st)) return r;
+    KL(1, launch_cross_attn_step(D.q, d, D.kv, ldkv, l * 2 * d, l * 2 * d + d, D.att, d, R, rows_per_image, c.enc_len,
+                                 c.num_heads, d / c.num_heads, n_valid, row_len, p, st));
+    if (int r = lin_f32(h, D.att, d, W.wo, xout, ldc, xout, ldc, R, 0, st)) return r;
+    KL(1, launch_layernorm<float>(xout, ldc, W.n3g, W.n3b, D.xn, d, R, d, st));
+    if (int r = lin_f32(h, D.xn, d, W.ff1, nullptr, 0, D.hid, c.ff, R, 2, st)) return r;
+    if (int r = lin_f32(h, D.hid, c.ff, W.ff2, xout, ldc, xout, ldc, R, 0, st)) return r;
+  }
+  if (int r = lin_f32(h, D.ycat, ldc, h->dec_reduce, D.ycat + (size_t)(nd - 1) * d, ldc, D.pre, d, R, 0, st)) return r;
+  KL(1, launch_layernorm<float>(D.pre, d, h->dec_ng, h->dec_nb, D.yn, d, R, d, st));
+  if (int r = lin_f32(h, D.yn, d, h->vocab, nullptr, 0, logits, ldl, R, 0, st)) return r;
+  return 0;
+}
+
+int upload_ints(xn_handle* h, const std::vector<int>& v, int** dev, cudaStream_t st) {
+  *dev = h->ws.get<int>(v.size());
+  CU(cudaMemcpyAsync(*dev, v.data(), v.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+  CU(cudaStreamSynchronize(st));
+  return 0;
+}
+
+int beam_from_enc(xn_handle* h, const float* enc_out, int B, const int32_t* enc_pads_host, int beam, int L, int how_many,
+                  int sos, int eos, int32_t* out_tokens, int32_t* out_len, float* out_lp, cudaStream_t st, bool reset_ws) {
+  const xn_config& c = h->cfg;
+  if (beam < 1 || beam > 8 || how_many > beam || how_many < 1) return h->fail(XN_ERR_ARG, "requested output per sequence must be lower than beam width (beam<=8)");
+  if (L < 2 || L > c.max_seq_len || L > 128) return h->fail(XN_ERR_ARG, "max_seq_len %d outside [2, %d]", L, std::min(c.max_seq_len, 128));
+  if (beam > c.vocab) return h->fail(XN_ERR_ARG, "beam > vocab");
+  const int R = B * beam, d = c.d_model;
+  if (reset_ws) h->ws.reset();
+  DecBufs D;
+  dec_alloc(h, D, R, L, B);
+  float* logits = h->ws.get<float>((size_t)R * c.vocab);
+  float* topv = h->ws.get<float>((size_t)R * beam);
+  int* topi = h->ws.get<int>((size_t)R * beam);
+  BeamBufs bb;
+  for (int s = 0; s < 2; ++s) {
+    bb.tokens[s] = h->ws.get<int>((size_t)R * L);
+    bb.lps[s] = h->ws.get<float>((size_t)R * L);
+    bb.len[s] = h->ws.get<int>(R);
+    bb.anc[s] = h->ws.get<int>((size_t)R * L);
+  }
+  bb.all_done = h->ws.get<int>(1);
+  int* nv = nullptr;
+  if (enc_pads_host) {
+    std::vector<int> v(B);
+    bool any = false;
+    for (int i = 0; i < B; ++i) { v[i] = c.enc_len - enc_pads_host[i]; any |= enc_pads_host[i] != 0; }
+    if (any) if (int r = upload_ints(h, v, &nv, st)) return r;
+  }
+  WS_CHECK();
+  // cross K/V of all decoder layers, once per image (shared by the beams)
+  if (int r = lin_f32(h, enc_out, d, h->kv_all, nullptr, 0, D.kv, h->kv_all.N, B * c.enc_len, 0, st)) return r;
+  KL(1, launch_beam_init(bb, B, beam, L, sos, st));
+  int src = 0;
+  // step 0: every beam row decodes [SOS]
+  D.s.anc = bb.anc[0];
+  if (int r = dec_step(h, D, 0, nullptr, bb.tokens[0], L, beam, nv, nullptr, logits, c.vocab, st)) return r;
+  KL(1, launch_logsoftmax_topk(logits, c.vocab, R, c.vocab, beam, topv, topi, nullptr, 0, 0, st));
+  KL(1, launch_beam_first(bb, topv, topi, B, beam, L, st));
+  int t_final = 2;
+  for (int t = 2; t < L; ++t) {
+    D.s.anc = bb.anc[src];
+    if (int r = dec_step(h, D, t - 1, nullptr, bb.tokens[src], L, beam, nv, nullptr, logits, c.vocab, st)) return r;
+    KL(1, launch_logsoftmax_topk(logits, c.vocab, R, c.vocab, beam, topv, topi, nullptr, 0, 0, st));
+    KL(1, launch_beam_step(bb, src, topv, topi, B, beam, L, t, eos, st));
+    src ^= 1;
+    t_final = t + 1;
+  }
+  KL(1, launch_beam_finalize(bb, src, B, beam, L, t_final, how_many, out_tokens, out_len, out_lp, st));
+  return 0;
+}
+
+size_t beam_ws_bytes(const xn_config& c, int B, int beam, int L) {
+  const int R = B * beam;
+  return dec_ws_bytes(c, R, L, B, true) + (size_t)R * beam * 8 + (size_t)R * L * 24 + R * 8 + B * 4 + 64 * 256;
+}
+
+const float* rawp(xn_handle* h, const std::string& k, std::vector<int64_t> shape, int* rc) {
+  auto it = h->raw.find(k);
+  if (it == h->raw.end()) { *rc = h->fail(XN_ERR_STATE, "missing state_dict entry '%s'", k.c_str()); return nullptr; }
+  if (it->second.shape != shape) {
+    std::string got, want;
+    for (auto s : it->second.shape) got += std::to_string(s) + ",";
+    for (auto s : shape) want += std::to_string(s) + ",";
+    *rc = h->fail(XN_ERR_STATE, "shape mismatch for '%s': got (%s) expected (%s)", k.c_str(), got.c_str(), want.c_str());
+    return nullptr;
+  }
+  return it->second.p;
+}
+
+}  // namespace
+
+// =============================================================================================
+// C ABI
+// =============================================================================================
+extern "C" {
+
+int xn_create(const xn_config* cfg, int device, xn_handle** out) {
+  if (!cfg || !out) { g_create_error = "null argument"; return XN_ERR_ARG; }
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || device < 0 || device >= ndev) {
+    g_create_error = std::string("no usable CUDA device ") + std::to_string(device) + ": " +
+                     (e != cudaSuccess ? cudaGetErrorString(e) : "ordinal out of range") +
+                     " (xnv2_b200 has no CPU fallback)";
+    return XN_ERR_CUDA;
+  }
+  cudaDeviceProp prop;
+  cudaGetDeviceProperties(&prop, device);
+  if (prop.major != 10) {
+    g_create_error = "xnv2_b200 is built for sm_100a (B200) only; device reports sm_" + std::to_string(prop.major) + std::to_string(prop.minor);
+    return XN_ERR_UNSUPPORTED;
+  }
+  if (cfg->window_size != 12) { g_create_error = "only swin_window_size == 12 is supported"; return XN_ERR_UNSUPPORTED; }
+  if (cfg->d_model % 128 || cfg->d_model % cfg->num_heads) { g_create_error = "d_model must be a multiple of 128 and of num_heads"; return XN_ERR_UNSUPPORTED; }
+  if (cfg->has_swin) {
+    if (cfg->n_stages < 1 || cfg->n_stages > 4) { g_create_error = "1..4 swin stages"; return XN_ERR_ARG; }
+    for (int s = 0; s < cfg->n_stages; ++s) {
+      const int C = cfg->embed_dim << s, H = (cfg->img_size / cfg->patch_size) >> s;
+      if (C != cfg->swin_heads[s] * 32) { g_create_error = "swin head_dim must be 32"; return XN_ERR_UNSUPPORTED; }
+      if (H % 12) { g_create_error = "every swin stage resolution must be a multiple of the window (12)"; return XN_ERR_UNSUPPORTED; }
+    }
+    const int Hl = (cfg->img_size / cfg->patch_size) >> (cfg->n_stages - 1);
+    if (Hl * Hl != cfg->enc_len || (cfg->embed_dim << (cfg->n_stages - 1)) != cfg->feat_dim) {
+      g_create_error = "swin output (L,C) must equal (enc_len, feat_dim)";
+      return XN_ERR_ARG;
+    }
+  }
+  for (int i = 0; i < cfg->n_exp_groups; ++i)
+    if (cfg->exp_groups[i] % 8) { g_create_error = "num_exp_enc_list entries must be multiples of 8"; return XN_ERR_UNSUPPORTED; }
+  xn_handle* h = new xn_handle();
+  h->cfg = *cfg;
+  h->device = device;
+  cudaSetDevice(device);
+  *out = h;
+  return XN_OK;
+}
+
+int xn_destroy(xn_handle* h) {
+  if (!h) return XN_OK;
+  cudaSetDevice(h->device);
+  cudaDeviceSynchronize();
+  for (auto& kv : h->raw) cudaFree(kv.second.p);
+  for (void* p : h->owned) cudaFree(p);
+  if (h->group_start_dev) cudaFree(h->group_start_dev);
+  if (h->ws.base) cudaFree(h->ws.base);
+  if (h->io_in) cudaFree(h->io_in);
+  if (h->io_out) cudaFree(h->io_out);
+  delete h;
+  return XN_OK;
+}
+
+const char* xn_last_error(const xn_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int xn_load_tensor(xn_handle* h, const char* key, const void* data, int dtype, const int64_t* shape, int ndim) {
+  if (!h || !key || !data) return XN_ERR_ARG;
+  cudaSetDevice(h->device);
+  std::string k(key);
+  auto ends = [&](const char* s) { size_t n = strlen(s); return k.size() >= n && k.compare(k.size() - n, n, s) == 0; };
+  if (ends("relative_position_index") || ends("attn_mask")) return XN_OK;   // geometry-only buffers
+  if (dtype != XN_DTYPE_F32) return h->fail(XN_ERR_ARG, "tensor '%s': only f32 parameters are accepted", key);
+  DevTensor t;
+  t.n = 1;
+  for (int i = 0; i < ndim; ++i) { t.shape.push_back(shape[i]); t.n *= (size_t)shape[i]; }
+  auto it = h->raw.find(k);
+  if (it != h->raw.end()) { cudaFree(it->second.p); h->raw.erase(it); }
+  CU(cudaMalloc(&t.p, std::max<size_t>(t.n, 1) * sizeof(float)));
+  CU(cudaMemcpy(t.p, data, t.n * sizeof(float), cudaMemcpyDefault));
+  h->raw[k] = t;
+  h->precision = -1;
+  return XN_OK;
+}
+
+int xn_finalize_weights(xn_handle* h, int precision) {
+  if (!h) return XN_ERR_ARG;
+  if (precision != XN_PREC_FP32 && precision != XN_PREC_BF16) return h->fail(XN_ERR_ARG, "bad precision");
+  cudaSetDevice(h->device);
+  const xn_config& c = h->cfg;
+  for (void* p : h->owned) cudaFree(p);
+  h->owned.clear();
+  h->stages.clear(); h->enc.clear(); h->dec.clear();
+  int rc = 0;
+  const int64_t d = c.d_model, ff = c.ff, V = c.vocab;
+  auto P = [&](const std::string& k, std::vector<int64_t> s) { return rc ? nullptr : rawp(h, k, s, &rc); };
+  auto lin = [&](const std::string& name, int64_t N, int64_t K, bool bias = true) {
+    LinW l;
+    l.w = P(name + ".weight", {N, K});
+    l.b = bias ? P(name + ".bias", {N}) : nullptr;
+    l.N = (int)N; l.K = (int)K;
+    return l;
+  };
+  auto to_bf16 = [&](LinW& l) -> int {
+    if (rc || !l.w) return rc;
+    bf16* p = nullptr;
+    CU(cudaMalloc(&p, (size_t)l.N * l.K * sizeof(bf16)));
+    h->owned.push_back(p);
+    KL(1, launch_cast<bf16>(l.w, p, (long)l.N * l.K, 0));
+    l.wb = p;
+    return 0;
+  };
+  // concatenate row blocks of several (N_i x K) weights (+ biases) into one (sum N_i x K) weight
+  auto concat = [&](const std::vector<LinW>& parts, LinW& outl) -> int {
+    if (rc) return rc;
+    int N = 0, K = parts[0].K;
+    for (auto& p : parts) N += p.N;
+    float *w = nullptr, *b = nullptr;
+    CU(cudaMalloc(&w, (size_t)N * K * sizeof(float)));
+    h->owned.push_back(w);
+    CU(cudaMalloc(&b, (size_t)N * sizeof(float)));
+    h->owned.push_back(b);
+    int n0 = 0;
+    for (auto& p : parts) {
+      CU(cudaMemcpy(w + (size_t)n0 * K, p.w, (size_t)p.N * K * sizeof(float), cudaMemcpyDeviceToDevice));
+      CU(cudaMemcpy(b + n0, p.b, (size_t)p.N * sizeof(float), cudaMemcpyDeviceToDevice));
+      n0 += p.N;
+    }
+    outl.w = w; outl.b = b; outl.N = N; outl.K = K;
+    return 0;
+  };
+
+  if (c.has_swin) {
+    const std::string p = "swin_transf.";
+    h->pe_w = P(p + "patch_embed.proj.weight", {c.embed_dim, c.in_chans, c.patch_size, c.patch_size});
+    h->pe_b = P(p + "patch_embed.proj.bias", {c.embed_dim});
+    h->pe_g = P(p + "patch_embed.norm.weight", {c.embed_dim});
+    h->pe_beta = P(p + "patch_embed.norm.bias", {c.embed_dim});
+    for (int s = 0; s < c.n_stages; ++s) {
+      SwinStageW S;
+      S.C = c.embed_dim << s; S.H = (c.img_size / c.patch_size) >> s; S.heads = c.swin_heads[s];
+      const int64_t C = S.C, hid = (int64_t)(C * c.mlp_ratio);
+      for (int b = 0; b < c.depths[s]; ++b) {
+        const std::string q = p + "layers." + std::to_string(s) + ".blocks." + std::to_string(b) + ".";
+        SwinBlockW W;
+        W.n1g = P(q + "norm1.weight", {C}); W.n1b = P(q + "norm1.bias", {C});
+        W.n2g = P(q + "norm2.weight", {C}); W.n2b = P(q + "norm2.bias", {C});
+        W.rpb = P(q + "attn.relative_position_bias_table", {23 * 23, S.heads});
+        W.qkv = lin(q + "attn.qkv", 3 * C, C); W.proj = lin(q + "attn.proj", C, C);
+        W.fc1 = lin(q + "mlp.fc1", hid, C); W.fc2 = lin(q + "mlp.fc2", C, hid);
+        if (precision == XN_PREC_BF16) {
+          if (to_bf16(W.qkv) || to_bf16(W.proj) || to_bf16(W.fc1) || to_bf16(W.fc2)) return XN_ERR_CUDA;
+        }
+        S.blocks.push_back(W);
+      }
+      if (s < c.n_stages - 1) {
+        const std::string q = p + "layers." + std::to_string(s) + ".downsample.";
+        S.has_merge = true;
+        S.mg = P(q + "norm.weight", {4 * C}); S.mb = P(q + "norm.bias", {4 * C});
+        S.red = lin(q + "reduction", 2 * C, 4 * C, false);
+        if (precision == XN_PREC_BF16 && to_bf16(S.red)) return XN_ERR_CUDA;
+      }
+      h->stages.push_back(S);
+    }
+    h->swin_ng = P(p + "norm.weight", {c.feat_dim});
+    h->swin_nb = P(p + "norm.bias", {c.feat_dim});
+  }
+  int64_t E = 0;
+  std::vector<int> gstart(1, 0);
+  int gcd = 32;
+  for (int i = 0; i < c.n_exp_groups; ++i) { E += c.exp_groups[i]; gstart.push_back((int)E); }
+  auto gcdf = [](int a, int b) { while (b) { int t = a % b; a = b; b = t; } return a; };
+  for (int v : gstart) if (v) gcd = gcdf(gcd, v);
+  h->n_exp_total = (int)E; h->exp_chunk = gcd;
+  if (h->group_start_dev) cudaFree(h->group_start_dev);
+  CU(cudaMalloc(&h->group_start_dev, gstart.size() * sizeof(int)));
+  CU(cudaMemcpy(h->group_start_dev, gstart.data(), gstart.size() * sizeof(int), cudaMemcpyHostToDevice));
+
+  for (int i = 0; i < c.n_enc; ++i) {
+    const std::string q = "encoders." + std::to_string(i) + ".";
+    EncLayerW W;
+    W.n1g = P(q + "norm_1.weight", {d}); W.n1b = P(q + "norm_1.bias", {d});
+    W.n2g = P(q + "norm_2.weight", {d}); W.n2b = P(q + "norm_2.bias", {d});
+    W.qexp = P(q + "stc_exp.query_exp_vectors.weight", {E, d});
+    W.bexp = P(q + "stc_exp.bias_exp_vectors.weight", {E, d});
+    std::vector<LinW> parts = {lin(q + "stc_exp.key_embed", d, d), lin(q + "stc_exp.class_a_embed", d, d),
+                               lin(q + "stc_exp.class_b_embed", d, d), lin(q + "stc_exp.selector_embed", d, d)};
+    W.ff1 = lin(q + "ff.linear_1", ff, d); W.ff2 = lin(q + "ff.linear_2", d, ff);
+    if (rc) return rc;
+    if (concat(parts, W.kabs)) return XN_ERR_CUDA;
+    h->enc.push_back(W);
+  }
+  std::vector<LinW> kvparts;
+  for (int i = 0; i < c.n_dec; ++i) {
+    const std::string q = "decoders." + std::to_string(i) + ".";
+    DecLayerW W;
+    W.n1g = P(q + "norm_1.weight", {d}); W.n1b = P(q + "norm_1.bias", {d});
+    W.n2g = P(q + "norm_2.weight", {d}); W.n2b = P(q + "norm_2.bias", {d});
+    W.n3g = P(q + "norm_3.weight", {d}); W.n3b = P(q + "norm_3.bias", {d});
+    W.qexp = P(q + "dyn_exp.query_exp_vectors.weight", {c.num_exp_dec, d});
+    W.bexp = P(q + "dyn_exp.bias_exp_vectors.weight", {c.num_exp_dec, d});
+    std::vector<LinW> parts = {lin(q + "dyn_exp.cond_embed", d, d), lin(q + "dyn_exp.key_linear", d, d),
+                               lin(q + "dyn_exp.class_a_embed", d, d), lin(q + "dyn_exp.class_b_embed", d, d),
+                               lin(q + "dyn_exp.selector_embed", d, d)};
+    W.wq = lin(q + "mha.Wq", d, d); W.wo = lin(q + "mha.out_linear", d, d);
+    kvparts.push_back(lin(q + "mha.Wk", d, d));
+    kvparts.push_back(lin(q + "mha.Wv", d, d));
+    W.ff1 = lin(q + "ff.linear_1", ff, d); W.ff2 = lin(q + "ff.linear_2", d, ff);
+    if (rc) return rc;
+    if (concat(parts, W.dyn5)) return XN_ERR_CUDA;
+    h->dec.push_back(W);
+  }
+  h->input_linear = lin("input_linear", d, c.feat_dim);
+  h->vocab = lin("vocab_linear", V, d);
+  h->enc_reduce = lin("enc_reduce_group", d, d * c.n_enc);
+  h->dec_reduce = lin("dec_reduce_group", d, d * c.n_dec);
+  h->enc_ng = P("enc_reduce_norm.weight", {d}); h->enc_nb = P("enc_reduce_norm.bias", {d});
+  h->dec_ng = P("dec_reduce_norm.weight", {d}); h->dec_nb = P("dec_reduce_norm.bias", {d});
+  h->emb = P("out_embedder.embed.weight", {V, d});
+  h->pos = P("pos_encoder.weight", {c.max_seq_len, d});
+  if (rc) return rc;
+  if (concat(kvparts, h->kv_all)) return XN_ERR_CUDA;
+  CU(cudaDeviceSynchronize());
+  h->precision = precision;
+  return XN_OK;
+}
+
+#define NEED_READY()                                                                   \
+  if (!h) return XN_ERR_ARG;                                                           \
+  if (h->precision < 0) return h->fail(XN_ERR_STATE, "weights not finalised");         \
+  cudaSetDevice(h->device);                                                            \
+  cudaStream_t st = (cudaStream_t)stream;
+
+int xn_forward_swin(xn_handle* h, const float* images, int B, float* out, void* stream) {
+  NEED_READY();
+  if (!h->cfg.has_swin) return h->fail(XN_ERR_STATE, "model has no Swin backbone");
+  const int Bc = (int)std::min<int64_t>(B, h->swin_chunk);
+  if (int r = ensure_ws(h, swin_ws_bytes(h->cfg, Bc, h->precision), st)) return r;
+  return swin_forward(h, images, B, out, st);
+}
+
+int xn_forward_enc(xn_handle* h, const float* input, int B, const int32_t* enc_pads_host, float* out, void* stream) {
+  NEED_READY();
+  const xn_config& c = h->cfg;
+  const int Bs = (int)std::min<int64_t>(B, h->swin_chunk), Be = (int)std::min<int64_t>(B, h->enc_chunk);
+  const size_t feat_bytes = c.has_swin ? (size_t)B * c.enc_len * c.feat_dim * 4 + 4096 : 0;
+  size_t need = std::max(c.has_swin ? swin_ws_bytes(c, Bs, h->precision) : 0, enc_ws_bytes(c, Be));
+  if (int r = ensure_ws(h, need + feat_bytes, st)) return r;
+  const float* feats = input;
+  if (c.has_swin) {
+    if (enc_pads_host)
+      for (int i = 0; i < B; ++i)
+        if (enc_pads_host[i] != 0) return h->fail(XN_ERR_ARG, "End to End case have no padding");
+    // feature buffer lives at the top of the arena, below it the per-chunk scratch
+    float* fb = reinterpret_cast<float*>(h->ws.base + ((h->ws.cap - feat_bytes) & ~size_t(255)));
+    const size_t keep = h->ws.cap;
+    h->ws.cap = (h->ws.cap - feat_bytes) & ~size_t(255);
+    int r = swin_forward(h, input, B, fb, st);
+    if (!r) r = enc_body(h, fb, B, nullptr, out, st);
+    h->ws.cap = keep;
+    return r;
+  }
+  return enc_body(h, feats, B, enc_pads_host, out, st);
+}
+
+int xn_forward_dec(xn_handle* h, const float* cross, int R, const int32_t* enc_pads_host, const int64_t* tokens, int t,
+                   const int32_t* dec_pads_host, int apply_log_softmax, float* out, void* stream) {
+  NEED_READY();
+  const xn_config& c = h->cfg;
+  if (t < 1 || t > c.max_seq_len || t > 128) return h->fail(XN_ERR_ARG, "sequence length %d outside [1, %d]", t, std::min(c.max_seq_len, 128));
+  if (int r = ensure_ws(h, dec_ws_bytes(c, R, t, R, false) + (size_t)R * 8, st)) return r;
+  DecBufs D;
+  dec_alloc(h, D, R, t, R);
+  WS_CHECK();
+  int *nv = nullptr, *rl = nullptr;
+  if (enc_pads_host && !c.has_swin) {
+    std::vector<int> v(R);
+    bool any = false;
+    for (int i = 0; i < R; ++i) { v[i] = c.enc_len - enc_pads_host[i]; any |= enc_pads_host[i] != 0; }
+    if (any) if (int r = upload_ints(h, v, &nv, st)) return r;
+  }
+  if (dec_pads_host) {
+    std::vector<int> v(R);
+    bool any = false;
+    for (int i = 0; i < R; ++i) { v[i] = t - dec_pads_host[i]; any |= dec_pads_host[i] != 0; }
+    if (any) if (int r = upload_ints(h, v, &rl, st)) return r;
+  }
+  if (int r = lin_f32(h, cross, c.d_model, h->kv_all, nullptr, 0, D.kv, h->kv_all.N, R * c.enc_len, 0, st)) return r;
+  const long ldl = (long)t * c.vocab;
+  for (int p = 0; p < t; ++p) {
+    float* lg = out + (size_t)p * c.vocab;
+    if (int r = dec_step(h, D, p, tokens, nullptr, t, 1, nv, rl, lg, ldl, st)) return r;
+    if (apply_log_softmax) KL(1, launch_logsoftmax_topk(lg, ldl, R, c.vocab, 0, nullptr, nullptr, lg, ldl, 1, st));
+  }
+  return XN_OK;
+}
+
+int xn_beam_search_from_enc(xn_handle* h, const float* enc_out, int B, const int32_t* enc_pads_host, int beam, int max_len,
+                            int how_many, int sos_idx, int eos_idx, int32_t* out_tokens, int32_t* out_len,
+                            float* out_logprob, void* stream) {
+  NEED_READY();
+  if (int r = ensure_ws(h, beam_ws_bytes(h->cfg, B, beam, max_len), st)) return r;
+  return beam_from_enc(h, enc_out, B, h->cfg.has_swin ? nullptr : enc_pads_host, beam, max_len, how_many, sos_idx, eos_idx,
+                       out_tokens, out_len, out_logprob, st, true);
+}
+
+int xn_beam_search(xn_handle* h, const float* input, int B, const int32_t* enc_pads_host, int beam, int max_len, int how_many,
+                   int sos_idx, int eos_idx, int32_t* out_tokens, int32_t* out_len, float* out_logprob, void* stream) {
+  NEED_READY();
+  const xn_config& c = h->cfg;
+  if (how_many > beam) return h->fail(XN_ERR_ARG, "requested output per sequence must be lower than beam width");
+  const int Bs = (int)std::min<int64_t>(B, h->swin_chunk), Be = (int)std::min<int64_t>(B, h->enc_chunk);
+  const size_t enc_bytes = ((size_t)B * c.enc_len * c.d_model * 4 + 4095) & ~size_t(255);
+  const size_t feat_bytes = c.has_swin ? (((size_t)B * c.enc_len * c.feat_dim * 4 + 4095) & ~size_t(255)) : 0;
+  size_t scratch = std::max(std::max(c.has_swin ? swin_ws_bytes(c, Bs, h->precision) : 0, enc_ws_bytes(c, Be)),
+                            beam_ws_bytes(c, B, beam, max_len));
+  if (int r = ensure_ws(h, scratch + enc_bytes + feat_bytes, st)) return r;
+  const size_t keep = h->ws.cap;
+  char* top = h->ws.base + (keep & ~size_t(255));
+  float* enc_out = reinterpret_cast<float*>(top - enc_bytes);
+  float* fb = reinterpret_cast<float*>(top - enc_bytes - feat_bytes);
+  h->ws.cap = (size_t)((top - enc_bytes - feat_bytes) - h->ws.base);
+  int r = 0;
+  if (c.has_swin) {
+    if (enc_pads_host)
+      for (int i = 0; i < B && !r; ++i)
+        if (enc_pads_host[i] != 0) r = h->fail(XN_ERR_ARG, "End to End case have no padding");
+    if (!r) r = swin_forward(h, input, B, fb, st);
+    if (!r) r = enc_body(h, fb, B, nullptr, enc_out, st);
+  } else {
+    r = enc_body(h, input, B, enc_pads_host, enc_out, st);
+  }
+  if (!r) r = beam_from_enc(h, enc_out, B, c.has_swin ? nullptr : enc_pads_host, beam, max_len, how_many, sos_idx, eos_idx,
+                            out_tokens, out_len, out_logprob, st, true);
+  h->ws.cap = keep;
+  return r;
+}
+
+int xn_caption_host(xn_handle* h, const float* input_host, int B, int beam, int max_len, int how_many, int sos_idx,
+                    int eos_idx, int32_t* out_tokens_host, int32_t* out_len_host, float* out_logprob_host, void* stream) {
+  NEED_READY();
+  const xn_config& c = h->cfg;
+  const size_t in_elems = c.has_swin ? (size_t)B * c.in_chans * c.img_size * c.img_size : (size_t)B * c.enc_len * c.feat_dim;
+  const size_t n_out = (size_t)B * how_many * max_len;
+  if (h->io_in_cap < in_elems * 4) {
+    if (h->io_in) { CU(cudaDeviceSynchronize()); cudaFree(h->io_in); h->io_in = nullptr; h->io_in_cap = 0; }
+    CU(cudaMalloc(&h->io_in, in_elems * 4));
+    h->io_in_cap = in_elems * 4;
+  }
+  const size_t out_bytes = n_out * 8 + (size_t)B * how_many * 4 + 1024;
+  if (h->io_out_cap < out_bytes) {
+    if (h->io_out) { CU(cudaDeviceSynchronize()); cudaFree(h->io_out); h->io_out = nullptr; h->io_out_cap = 0; }
+    CU(cudaMalloc(&h->io_out, out_bytes));
+    h->io_out_cap = out_bytes;
+  }
+  float* din = h->io_in;
+  char* dout = h->io_out;
+  int32_t* d_tok = reinterpret_cast<int32_t*>(dout);
+  float* d_lp = reinterpret_cast<float*>(dout + n_out * 4);
+  int32_t* d_len = reinterpret_cast<int32_t*>(dout + n_out * 8);
+  CU(cudaMemcpyAsync(din, input_host, in_elems * 4, cudaMemcpyHostToDevice, st));
+  if (int r = xn_beam_search(h, din, B, nullptr, beam, max_len, how_many, sos_idx, eos_idx, d_tok, d_len, d_lp, stream)) return r;
+  CU(cudaMemcpyAsync(out_tokens_host, d_tok, n_out * 4, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(out_len_host, d_len, (size_t)B * how_many * 4, cudaMemcpyDeviceToHost, st));
+  if (out_logprob_host) CU(cudaMemcpyAsync(out_logprob_host, d_lp, n_out * 4, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  return XN_OK;
+}
+
+int64_t xn_kernel_launches(const xn_handle* h) { return h ? h->launches : 0; }
+int64_t xn_workspace_bytes(const xn_handle* h) { return h ? (int64_t)h->ws.cap : 0; }
+
+int xn_set_option(xn_handle* h, const char* name, int64_t value) {
+  if (!h || !name) return XN_ERR_ARG;
+  std::string n(name);
+  if (n == "swin_chunk") h->swin_chunk = std::max<int64_t>(1, value);
+  else if (n == "enc_chunk") h->enc_chunk = std::max<int64_t>(1, value);
+  else return h->fail(XN_ERR_ARG, "unknown option '%s'", name);
+  return XN_OK;
+}
+
+// ---- single-operator entry points ------------------------------------------------------------
+#define OP_READY()                                   \
+  if (!h) return XN_ERR_ARG;                         \
+  cudaSetDevice(h->device);                          \
+  cudaStream_t st = (cudaStream_t)stream;
+
+int xn_op_layernorm(xn_handle* h, const float* x, const float* gamma, const float* beta, float* y, int rows, int C, void* stream) {
+  OP_READY();
+  KL(1, launch_layernorm<float>(x, C, gamma, beta, y, C, rows, C, st));
+  return XN_OK;
+}
+
+int xn_op_linear(xn_handle* h, const float* x, const float* w, const float* bias, const float* residual, float* y, int M, int N,
+                 int K, int act, int precision, void* stream) {
+  OP_READY();
+  if (precision == XN_PREC_FP32) {
+    LinW l; l.w = w; l.b = bias; l.N = N; l.K = K;
+    return lin_f32(h, x, K, l, residual, N, y, N, M, act, st);
+  }
+  if (!tc_gemm_supported(M, N, K)) return h->fail(XN_ERR_UNSUPPORTED, "tcgen05 GEMM needs K %% 64 == 0 and N %% 8 == 0 (M=%d N=%d K=%d)", M, N, K);
+  if (int r = ensure_ws(h, ((size_t)M * K + (size_t)N * K) * 2 + 8192, st)) return r;
+  bf16* xb = h->ws.get<bf16>((size_t)M * K);
+  bf16* wb = h->ws.get<bf16>((size_t)N * K);
+  KL(1, launch_cast<bf16>(x, xb, (long)M * K, st));
+  KL(1, launch_cast<bf16>(w, wb, (long)N * K, st));
+  LinW l; l.wb = wb; l.b = bias; l.N = N; l.K = K;
+  return lin_tc(h, xb, K, l, residual, N, y, nullptr, N, M, act, st);
+}
+
+int xn_op_window_attention(xn_handle* h, const float* qkv, const float* bias_table, float* out, int B, int H, int C, int heads,
+                           int shift, int precision, void* stream) {
+  OP_READY();
+  if (precision == XN_PREC_FP32) {
+    KL(1, launch_window_attention<float>(qkv, bias_table, out, B, H, C, heads, shift, st));
+    return XN_OK;
+  }
+  const size_t n = (size_t)B * H * H * C;
+  if (int r = ensure_ws(h, n * 4 * 2 + 8192, st)) return r;
+  bf16* qb = h->ws.get<bf16>(3 * n);
+  bf16* ob = h->ws.get<bf16>(n);
+  KL(1, launch_cast<bf16>(qkv, qb, (long)(3 * n), st));
+  KL(1, launch_window_attention<bf16>(qb, bias_table, ob, B, H, C, heads, shift, st));
+  // widen the bf16 result for the caller
+  KL(1, launch_widen_bf16(ob, out, (long)n, st));
+  return XN_OK;
+}
+
+int xn_op_logsoftmax_topk(xn_handle* h, const float* logits, int rows, int V, int k, float* top_val, int32_t* top_idx,
+                          float* logprob_or_null, void* stream) {
+  OP_READY();
+  KL(1, launch_logsoftmax_topk(logits, V, rows, V, k, top_val, top_idx, logprob_or_null, V, logprob_or_null ? 1 : 0, st));
+  return XN_OK;
+}
+
+}  // extern "C"
+
+__global__ void widen_bf16_kernel(const bf16* __restrict__ x, float* __restrict__ y, long n) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) y[i] = __bfloat162float(x[i]);
+}
+cudaError_t launch_widen_bf16(const bf16* x, float* y, long n, cudaStream_t st) {
+  widen_bf16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(x, y, n);
+  return cudaGetLastError();
+}

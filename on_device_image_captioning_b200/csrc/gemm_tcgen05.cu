@@ -1,0 +1,338 @@
+// BF16 GEMM on the 5th-generation tensor cores: tcgen05.mma with the accumulator in TMEM,
+// operands staged in shared memory by TMA (128B swizzle), warp-specialised and persistent.
+//
+//   C (M x N) = act( A (M x K) . W^T (N x K) / div + bias ) + res
+//
+// A and W are bf16 with K contiguous (nn.Linear layout on both sides), accumulation is fp32.
+// This is the contraction behind every nn.Linear of the Swin backbone in the bf16 mode
+// (reference models/swin_transformer_mod.py:214-216,229-233,270 qkv/proj; :109-119 fc1/fc2;
+// :479,499 patch-merging reduction).
+//
+// CTA = 6 warps:  warp 0  TMA producer (one elected lane)
+//                 warp 1  TMEM allocator + MMA issuer (one elected lane)
+//                 warps 2-5  epilogue: tcgen05.ld -> smem transpose -> fused bias/GELU/residual
+//                            -> coalesced global stores
+// Pipelines: a kStages-deep smem ring (full/empty mbarriers, TMA <-> MMA) and a 2-deep TMEM
+// accumulator ring (tmem_full/tmem_empty, MMA <-> epilogue) so the epilogue of tile i overlaps
+// the MMAs of tile i+1.  Tiles are 128 x BN (BN in {128,192,256}), K step 64 (one 128-byte
+// swizzle atom), UMMA shape 128 x BN x 16, cta_group::1.
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <mutex>
+#include "kernels.h"
+#include "common.cuh"
+
+namespace xn {
+
+constexpr int kBM = 128;
+constexpr int kBK = 64;                       // bf16 elements = 128 bytes = swizzle span
+constexpr int kUmmaK = 16;
+constexpr int kTcThreads = 192;
+constexpr uint32_t kABytes = kBM * kBK * 2;   // 16 KB
+
+template <int BN> struct TcCfg {
+  static constexpr uint32_t kBBytes = BN * kBK * 2;
+  static constexpr uint32_t kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = (BN == 256) ? 4 : (BN == 192 ? 5 : 6);
+  static constexpr uint32_t kAccCols = 256;                 // column stride between the two accumulators
+  static constexpr uint32_t kTmemCols = 512;
+  static constexpr uint32_t kStagingBytes = 4 * 32 * 33 * 4;
+  static constexpr uint32_t kSmemBytes = kStages * kStageBytes + kStagingBytes + 256 + 1024;
+};
+
+struct TcEpilogue {
+  float* Cf; bf16* Cb; long ldc;
+  const float* bias;
+  const float* res; long ldr;
+  float div;
+  int act;
+};
+
+// ---------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok = 0;
+  while (!ok) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// UMMA shared-memory descriptor, K-major operand, 128-byte swizzle (cute::UMMA::SmemDescriptor):
+//   [0,14) start address >> 4   [16,30) leading byte offset >> 4 (unused for swizzled K-major)
+//   [32,46) stride byte offset >> 4 (8 rows x 128 B = 1024)   [46,48) version = 1
+//   [61,64) layout type = 2 (SWIZZLE_128B)
+__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t saddr) {
+  return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)(1024u >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+// Instruction descriptor (cute::UMMA::InstrDescriptor): D=F32 [4,6)=1, A=BF16 [7,10)=1, B=BF16 [10,13)=1,
+// A/B K-major (bits 15,16 = 0), N>>3 at [17,23), M>>4 at [24,29).
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+template <int BN>
+__global__ void __launch_bounds__(kTcThreads, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, TcEpilogue ep,
+               int M, int N, int K) {
+  using Cfg = TcCfg<BN>;
+  constexpr int S = Cfg::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;          // SWIZZLE_128B tiles need 1024-B alignment
+  uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t staging = base + S * Cfg::kStageBytes;
+  float* staging_gen = reinterpret_cast<float*>(gen_base + S * Cfg::kStageBytes);
+  const uint32_t bars = staging + Cfg::kStagingBytes;
+  // barrier layout: full[S] | empty[S] | tmem_full[2] | tmem_empty[2] | tmem_ptr
+  auto full_bar = [&](int s) { return bars + 8u * s; };
+  auto empty_bar = [&](int s) { return bars + 8u * (S + s); };
+  auto tfull_bar = [&](int b) { return bars + 8u * (2 * S + b); };
+  auto tempty_bar = [&](int b) { return bars + 8u * (2 * S + 2 + b); };
+  volatile uint32_t* tmem_ptr_gen =
+      reinterpret_cast<volatile uint32_t*>(gen_base + S * Cfg::kStageBytes + Cfg::kStagingBytes + 8 * (2 * S + 4));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m_tiles = (M + kBM - 1) / kBM, n_tiles = (N + BN - 1) / BN;
+  const int total_tiles = m_tiles * n_tiles;
+  const int nkb = (K + kBK - 1) / kBK;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < S; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)tmem_ptr_gen)),
+                 "r"(Cfg::kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_gen;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int m0 = (tile / n_tiles) * kBM, n0 = (tile % n_tiles) * BN;
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          mbar_expect_tx(full_bar(stage), Cfg::kStageBytes);
+          const uint32_t sa = base + stage * Cfg::kStageBytes;
+          tma_load_2d(sa, &tma_a, kb * kBK, m0, full_bar(stage));
+          tma_load_2d(sa + kABytes, &tma_b, kb * kBK, n0, full_bar(stage));
+          if (++stage == S) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(kBM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        const int buf = it & 1;
+        const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
+        mbar_wait(tempty_bar(buf), acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + buf * Cfg::kAccCols;
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t sa = base + stage * Cfg::kStageBytes;
+          const uint64_t adesc = make_sw128_desc(sa);
+          const uint64_t bdesc = make_sw128_desc(sa + kABytes);
+#pragma unroll
+          for (int k = 0; k < kBK / kUmmaK; ++k)   // +32 bytes (>>4 = 2) per UMMA_K step inside the swizzle atom
+            umma_bf16(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (uint32_t)((kb | k) != 0));
+          umma_commit(empty_bar(stage));           // frees the smem slot when these MMAs retire
+          if (++stage == S) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit(tfull_bar(buf));               // accumulator complete -> epilogue
+      }
+    }
+  } else {
+    const int q = warp & 3;                        // TMEM lane quarter this warp may access
+    float* tile_s = staging_gen + (warp - 2) * (32 * 33);
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const int buf = it & 1;
+      const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
+      const int m0 = (tile / n_tiles) * kBM, n0 = (tile % n_tiles) * BN;
+      mbar_wait(tfull_bar(buf), acc_phase);
+      tc_fence_after();
+      const int row_base = m0 + q * 32;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        if (n0 + c0 >= N) break;
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * Cfg::kAccCols + c0, v);
+#pragma unroll
+        for (int c = 0; c < 32; ++c) tile_s[lane * 33 + c] = __uint_as_float(v[c]);
+        __syncwarp();
+        const int col = n0 + c0 + lane;
+        const bool col_ok = col < N;
+        const float bcol = (ep.bias && col_ok) ? ep.bias[col] : 0.f;
+#pragma unroll 4
+        for (int r = 0; r < 32; ++r) {
+          const int row = row_base + r;
+          if (row >= M) break;
+          float x = tile_s[r * 33 + lane];
+          if (ep.div != 0.f) x = x / ep.div;
+          x += bcol;
+          if (ep.act == 1) x = gelu_erf(x);
+          else if (ep.act == 2) x = fmaxf(x, 0.f);
+          if (col_ok) {
+            if (ep.res) x += ep.res[(long)row * ep.ldr + col];
+            if (ep.Cf) ep.Cf[(long)row * ep.ldc + col] = x;
+            else ep.Cb[(long)row * ep.ldc + col] = __float2bfloat16_rn(x);
+          }
+        }
+        __syncwarp();
+      }
+      tc_fence_before();
+      if (lane == 0) mbar_arrive(tempty_bar(buf));
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(Cfg::kTmemCols) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+static bool make_map(CUtensorMap* map, const bf16* ptr, long rows, long cols, long ld, int box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return false;
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstride[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)kBK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<bf16*>(ptr), gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+bool tc_gemm_supported(int M, int N, int K) { return M > 0 && N > 0 && K > 0 && (K % 8) == 0; }
+
+static int sm_count() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+template <int BN>
+static cudaError_t launch_tc(const TcGemmArgs& p, cudaStream_t st) {
+  using Cfg = TcCfg<BN>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmemBytes);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  CUtensorMap ma, mb;
+  if (!make_map(&ma, p.A, p.M, p.K, p.lda, kBM) || !make_map(&mb, p.W, p.N, p.K, p.ldw, BN)) return cudaErrorInvalidValue;
+  TcEpilogue ep{p.Cf, p.Cb, p.ldc, p.bias, p.res, p.ldr, p.div, p.act};
+  const int tiles = ((p.M + kBM - 1) / kBM) * ((p.N + BN - 1) / BN);
+  const int grid = tiles < sm_count() ? tiles : sm_count();
+  gemm_tc_kernel<BN><<<grid, kTcThreads, Cfg::kSmemBytes, st>>>(ma, mb, ep, p.M, p.N, p.K);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_gemm_tc(const TcGemmArgs& p, cudaStream_t st) {
+  if (!tc_gemm_supported(p.M, p.N, p.K) || (p.lda % 8) || (p.ldw % 8) || ((p.Cf != nullptr) == (p.Cb != nullptr)))
+    return cudaErrorInvalidValue;
+  if ((reinterpret_cast<uintptr_t>(p.A) & 15) || (reinterpret_cast<uintptr_t>(p.W) & 15)) return cudaErrorInvalidValue;
+  // pick the tile width with the least padded work; ties go to the wider tile
+  const int cands[3] = {256, 192, 128};
+  int best = 256;
+  long best_waste = -1;
+  for (int bn : cands) {
+    const long waste = (long)((p.N + bn - 1) / bn) * bn - p.N;
+    if (best_waste < 0 || waste < best_waste) { best = bn; best_waste = waste; }
+  }
+  if (best == 256) return launch_tc<256>(p, st);
+  if (best == 192) return launch_tc<192>(p, st);
+  return launch_tc<128>(p, st);
+}
+
+}  // namespace xn

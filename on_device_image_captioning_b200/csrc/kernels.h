@@ -1,0 +1,113 @@
+// Host-side launch prototypes of every xnv2_b200 kernel family.  Each launcher returns the
+// CUDA error of the launch and counts as one "gpu launch" of this library.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+
+namespace xn {
+
+typedef __nv_bfloat16 bf16;
+
+// ---------------------------------------------------------------- GEMM (fp32 FFMA path)
+struct GemmArgs {
+  const float* A; long lda, sA;      // (M x K), K contiguous; sA = batch stride (elements)
+  const float* W; long ldw, sW;      // (N x K) [w_kn=0] or (K x N) [w_kn=1]
+  float* C; long ldc, sC;
+  const float* bias;                 // [N] or nullptr
+  const float* res; long ldr, sR;    // residual added after the activation, or nullptr
+  int M, N, K, batch;
+  float div;                         // != 0: accumulator is divided by this first
+  int act;                           // 0 none, 1 GELU(erf), 2 ReLU
+  int w_kn;
+};
+cudaError_t launch_gemm_f32(const GemmArgs& p, cudaStream_t st);
+
+// ---------------------------------------------------------------- GEMM (bf16 tcgen05 path)
+// C = act(A x W^T + bias) + res, A (M x K) bf16 K-contiguous, W (N x K) bf16 K-contiguous,
+// fp32 accumulation in TMEM.  Output fp32 (Cf) or bf16 (Cb), exactly one non-null.
+struct TcGemmArgs {
+  const bf16* A; long lda;
+  const bf16* W; long ldw;
+  float* Cf; bf16* Cb; long ldc;
+  const float* bias;
+  const float* res; long ldr;        // fp32 residual
+  int M, N, K;
+  float div;
+  int act;
+};
+cudaError_t launch_gemm_tc(const TcGemmArgs& p, cudaStream_t st);
+bool tc_gemm_supported(int M, int N, int K);
+
+// ---------------------------------------------------------------- normalisation / embedding
+template <typename OutT>
+cudaError_t launch_layernorm(const float* x, long ldx, const float* gamma, const float* beta, OutT* y, long ldy,
+                             long rows, int C, cudaStream_t st);
+// PatchMerging front half: gather the 2x2 neighbourhood (order (0,0),(1,0),(0,1),(1,1)) and LayerNorm(4C).
+template <typename OutT>
+cudaError_t launch_merge_layernorm(const float* x, const float* gamma, const float* beta, OutT* y,
+                                   int B, int H, int C, cudaStream_t st);
+// PatchEmbed: conv(k = stride = P) as a K = Cin*P*P dot product + bias + LayerNorm(E).
+cudaError_t launch_patch_embed(const float* img, const float* w, const float* b, const float* gamma,
+                               const float* beta, float* out, int B, int Cin, int S, int P, int E,
+                               cudaStream_t st);
+template <typename T>
+cudaError_t launch_cast(const float* x, T* y, long n, cudaStream_t st);
+
+// ---------------------------------------------------------------- Swin window attention
+// qkv (B*H*H, 3C) token-major in the unshifted frame -> out (B*H*H, C); cyclic shift, window
+// partition/reverse, relative-position bias and the shift mask are index arithmetic.
+template <typename T>
+cudaError_t launch_window_attention(const T* qkv, const float* bias_table, T* out, int B, int H, int C,
+                                    int heads, int shift, cudaStream_t st);
+
+// ---------------------------------------------------------------- static expansion (encoder)
+// z (B, E, N) raw scores (already / sqrt(d)).  Produces forward weights (B,E,N) normalised over
+// the N keys (keys >= n_valid[b] masked) and backward weights (B,N,E) normalised per group.
+cudaError_t launch_static_exp_weights(const float* z, const int* n_valid, const int* group_start, int n_groups,
+                                      float* a_fw, float* b_fw, float* a_bw, float* b_bw, float* gsum_scratch,
+                                      int B, int E, int N, int chunk, cudaStream_t st);
+// x_out = x_in + sigmoid(sel) * out_a + (1 - sigmoid(sel)) * out_b
+cudaError_t launch_selector_mix(const float* x_in, long ldxi, const float* sel, long lds, const float* out_a,
+                                const float* out_b, long ldo, float* x_out, long ldxo, long rows, int d,
+                                cudaStream_t st);
+
+// ---------------------------------------------------------------- decoder step
+struct DecState {
+  // per decoder layer l, position p, row r:  cache[((l*P + p)*R + r)*cw ...] = [cond | key | A | B | sel]
+  float* cache; int cw;        // cw = 5*d
+  float* fw;                   // forward weights of the row-block of position p: ((l*P+p)*R + r)*2*n_exp*P
+  float* qk;                   // q_e . K_p   : ((l*P+p)*R + r)*n_exp
+  const int* anc;              // (R, P): slot (row index) holding position i of row r's history
+  int P;                       // max positions
+  int R;
+};
+cudaError_t launch_embed(const int64_t* tokens64, const int* tokens32, long tok_stride, int p, const float* emb,
+                         const float* pos, float* x, long ldx, int R, int d, cudaStream_t st);
+cudaError_t launch_dyn_exp_step(const DecState& s, int layer, int p, const float* qexp, const float* bexp,
+                                int n_exp, const int* row_len, const float* x_in, long ldxi, float* x_out,
+                                long ldxo, int d, int beam, cudaStream_t st);
+// cross attention of one query position per row against per-image K/V (shared by the beams)
+cudaError_t launch_cross_attn_step(const float* q, long ldq, const float* kv, long ldkv, int k_off, int v_off,
+                                   float* out, long ldo, int R, int rows_per_image, int n_keys, int heads, int dk,
+                                   const int* n_valid, const int* row_len, int p, cudaStream_t st);
+cudaError_t launch_logsoftmax_topk(const float* logits, long ld, int rows, int V, int k, float* top_val,
+                                   int* top_idx, float* logprob, long ldlp, int write_mode, cudaStream_t st);
+
+// ---------------------------------------------------------------- beam search bookkeeping
+struct BeamBufs {
+  int* tokens[2];     // (B, beam, L) ping-pong
+  float* lps[2];      // (B, beam, L)
+  int* len[2];        // (B, beam)
+  int* anc[2];        // (B*beam, L)   slot is local (0..beam-1) + b*beam
+  int* all_done;      // [1]
+};
+cudaError_t launch_beam_init(const BeamBufs& bb, int B, int beam, int L, int sos, cudaStream_t st);
+cudaError_t launch_beam_first(const BeamBufs& bb, const float* top_val, const int* top_idx, int B, int beam,
+                              int L, cudaStream_t st);
+cudaError_t launch_beam_step(const BeamBufs& bb, int src, const float* top_val, const int* top_idx, int B,
+                             int beam, int L, int t, int eos, cudaStream_t st);
+cudaError_t launch_beam_finalize(const BeamBufs& bb, int src, int B, int beam, int L, int t_final, int how_many,
+                                 int* out_tokens, int* out_len, float* out_lp, cudaStream_t st);
+
+}  // namespace xn

@@ -1,0 +1,215 @@
+"""Python handle over the C ABI.  torch is used only for device memory and streams."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from .config import XNConfig
+
+PRECISIONS = {"fp32": _lib.XN_PREC_FP32, "bf16": _lib.XN_PREC_BF16}
+
+
+def _cfg_struct(cfg: XNConfig) -> _lib.XnConfig:
+    s = _lib.XnConfig()
+    s.has_swin = int(cfg.has_swin)
+    s.img_size, s.patch_size, s.in_chans, s.embed_dim = cfg.img_size, cfg.patch_size, cfg.in_chans, cfg.embed_dim
+    s.n_stages = len(cfg.depths)
+    for i, (d, h) in enumerate(zip(cfg.depths, cfg.swin_heads)):
+        s.depths[i] = d
+        s.swin_heads[i] = h
+    s.window_size = cfg.window_size
+    s.mlp_ratio = float(cfg.mlp_ratio)
+    s.feat_dim, s.d_model, s.n_enc, s.n_dec, s.ff, s.num_heads = cfg.feat_dim, cfg.d_model, cfg.n_enc, cfg.n_dec, cfg.ff, cfg.num_heads
+    s.n_exp_groups = len(cfg.num_exp_enc_list)
+    for i, g in enumerate(cfg.num_exp_enc_list):
+        s.exp_groups[i] = g
+    s.num_exp_dec, s.vocab, s.max_seq_len, s.enc_len = cfg.num_exp_dec, cfg.vocab, cfg.max_seq_len, cfg.enc_len
+    return s
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _int_array(v: Optional[Sequence[int]]):
+    if v is None:
+        return None
+    arr = (C.c_int32 * len(v))(*[int(x) for x in v])
+    return arr
+
+
+class Engine:
+    """One model instance bound to one CUDA device."""
+
+    def __init__(self, cfg: XNConfig, device: int = 0):
+        if not torch.cuda.is_available():
+            raise RuntimeError("xnv2_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+        self.lib = _lib.load()
+        self.cfg = cfg
+        self.device = torch.device("cuda", int(device))
+        self._h = C.c_void_p()
+        self._cs = _cfg_struct(cfg)
+        rc = self.lib.xn_create(C.byref(self._cs), int(device), C.byref(self._h))
+        if rc != 0:
+            raise RuntimeError("xn_create failed: " + (self.lib.xn_last_error(None) or b"").decode())
+        self.precision: Optional[str] = None
+
+    # -- plumbing ---------------------------------------------------------------------------
+    def _check(self, rc: int, what: str):
+        if rc != 0:
+            raise RuntimeError(f"{what} failed ({rc}): " + (self.lib.xn_last_error(self._h) or b"").decode())
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self.lib.xn_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def kernel_launches(self) -> int:
+        return int(self.lib.xn_kernel_launches(self._h))
+
+    def set_option(self, name: str, value: int):
+        self._check(self.lib.xn_set_option(self._h, name.encode(), int(value)), "xn_set_option")
+
+    def _f32(self, t: torch.Tensor) -> torch.Tensor:
+        return t.to(device=self.device, dtype=torch.float32).contiguous()
+
+    # -- weights ----------------------------------------------------------------------------
+    def load_state_dict(self, sd: Dict[str, torch.Tensor], precision: str = "fp32"):
+        """Replaces model.load_state_dict(checkpoint['model_state_dict']) (reference demo.py:100-104)."""
+        for k, v in sd.items():
+            if k.endswith("relative_position_index") or k.endswith("attn_mask"):
+                continue
+            if v.is_sparse:                       # pruned checkpoints store sparse tensors (reference test.py:455-457)
+                v = v.to_dense()
+            t = v.detach().to(dtype=torch.float32).contiguous()
+            shape = (C.c_int64 * t.dim())(*t.shape)
+            self._check(self.lib.xn_load_tensor(self._h, k.encode(), C.c_void_p(t.data_ptr()), _lib.XN_DTYPE_F32,
+                                                shape, t.dim()), f"xn_load_tensor({k})")
+        self.finalize(precision)
+
+    def finalize(self, precision: str):
+        self._check(self.lib.xn_finalize_weights(self._h, PRECISIONS[precision]), "xn_finalize_weights")
+        self.precision = precision
+
+    # -- model calls ------------------------------------------------------------------------
+    def forward_swin(self, images: torch.Tensor) -> torch.Tensor:
+        x = self._f32(images)
+        B = x.shape[0]
+        Hl = (self.cfg.img_size // self.cfg.patch_size) >> (len(self.cfg.depths) - 1)
+        out = torch.empty(B, Hl * Hl, self.cfg.feat_dim, device=self.device, dtype=torch.float32)
+        with torch.cuda.device(self.device):
+            self._check(self.lib.xn_forward_swin(self._h, _ptr(x), B, _ptr(out), self._stream()), "xn_forward_swin")
+        return out
+
+    def forward_enc(self, enc_input: torch.Tensor, enc_pads: Optional[Sequence[int]] = None) -> torch.Tensor:
+        x = self._f32(enc_input)
+        B = x.shape[0]
+        out = torch.empty(B, self.cfg.enc_len, self.cfg.d_model, device=self.device, dtype=torch.float32)
+        with torch.cuda.device(self.device):
+            self._check(self.lib.xn_forward_enc(self._h, _ptr(x), B, _int_array(enc_pads), _ptr(out), self._stream()),
+                        "xn_forward_enc")
+        return out
+
+    def forward_dec(self, cross: torch.Tensor, enc_pads: Optional[Sequence[int]], tokens: torch.Tensor,
+                    dec_pads: Optional[Sequence[int]], apply_log_softmax: bool = False) -> torch.Tensor:
+        cr = self._f32(cross)
+        tok = tokens.to(device=self.device, dtype=torch.int64).contiguous()
+        R, t = tok.shape
+        out = torch.empty(R, t, self.cfg.vocab, device=self.device, dtype=torch.float32)
+        with torch.cuda.device(self.device):
+            self._check(self.lib.xn_forward_dec(self._h, _ptr(cr), R, _int_array(enc_pads), _ptr(tok), t,
+                                                _int_array(dec_pads), int(apply_log_softmax), _ptr(out), self._stream()),
+                        "xn_forward_dec")
+        return out
+
+    def beam_search(self, enc_input: torch.Tensor, enc_pads: Optional[Sequence[int]], sos_idx: int, eos_idx: int,
+                    beam_size: int = 3, how_many: int = 1, max_len: int = 20,
+                    from_enc: bool = False) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+        """Device results: tokens (B,how_many,max_len) int32 (-1 padded), lengths (B,how_many) int32,
+        log-probs (B,how_many,max_len) f32 (0 padded)."""
+        x = self._f32(enc_input)
+        B = x.shape[0]
+        tok = torch.empty(B, how_many, max_len, device=self.device, dtype=torch.int32)
+        ln = torch.empty(B, how_many, device=self.device, dtype=torch.int32)
+        lp = torch.empty(B, how_many, max_len, device=self.device, dtype=torch.float32)
+        fn = self.lib.xn_beam_search_from_enc if from_enc else self.lib.xn_beam_search
+        with torch.cuda.device(self.device):
+            self._check(fn(self._h, _ptr(x), B, _int_array(enc_pads), int(beam_size), int(max_len), int(how_many),
+                           int(sos_idx), int(eos_idx), _ptr(tok), _ptr(ln), _ptr(lp), self._stream()), "xn_beam_search")
+        return tok, ln, lp
+
+    def caption_host(self, inputs_host: torch.Tensor, sos_idx: int, eos_idx: int, beam_size: int = 3, how_many: int = 1,
+                     max_len: int = 20, out: Optional[Tuple[torch.Tensor, torch.Tensor, torch.Tensor]] = None):
+        """Host buffers in, host buffers out (H2D/D2H inside the call).  `inputs_host` should be pinned."""
+        assert inputs_host.device.type == "cpu" and inputs_host.dtype == torch.float32 and inputs_host.is_contiguous()
+        B = inputs_host.shape[0]
+        if out is None:
+            out = (torch.empty(B, how_many, max_len, dtype=torch.int32).pin_memory(),
+                   torch.empty(B, how_many, dtype=torch.int32).pin_memory(),
+                   torch.empty(B, how_many, max_len, dtype=torch.float32).pin_memory())
+        tok, ln, lp = out
+        with torch.cuda.device(self.device):
+            self._check(self.lib.xn_caption_host(self._h, _ptr(inputs_host), B, int(beam_size), int(max_len), int(how_many),
+                                                 int(sos_idx), int(eos_idx), _ptr(tok), _ptr(ln), _ptr(lp), self._stream()),
+                        "xn_caption_host")
+        return tok, ln, lp
+
+    # -- single operators (kernel-level tests) ------------------------------------------------
+    def op_layernorm(self, x, gamma, beta):
+        x = self._f32(x); y = torch.empty_like(x)
+        rows = x.numel() // x.shape[-1]
+        self._check(self.lib.xn_op_layernorm(self._h, _ptr(x), _ptr(self._f32(gamma)), _ptr(self._f32(beta)), _ptr(y), rows,
+                                             x.shape[-1], self._stream()), "xn_op_layernorm")
+        return y
+
+    def op_linear(self, x, w, bias=None, residual=None, act: int = 0, precision: str = "fp32"):
+        x = self._f32(x); w = self._f32(w)
+        M, K = x.shape
+        N = w.shape[0]
+        b = self._f32(bias) if bias is not None else None
+        r = self._f32(residual) if residual is not None else None
+        y = torch.empty(M, N, device=self.device, dtype=torch.float32)
+        self._check(self.lib.xn_op_linear(self._h, _ptr(x), _ptr(w), _ptr(b), _ptr(r), _ptr(y), M, N, K, act,
+                                          PRECISIONS[precision], self._stream()), "xn_op_linear")
+        return y
+
+    def op_window_attention(self, qkv, bias_table, B, H, C_, heads, shift, precision: str = "fp32"):
+        qkv = self._f32(qkv); bt = self._f32(bias_table)
+        out = torch.empty(B * H * H, C_, device=self.device, dtype=torch.float32)
+        self._check(self.lib.xn_op_window_attention(self._h, _ptr(qkv), _ptr(bt), _ptr(out), B, H, C_, heads, shift,
+                                                    PRECISIONS[precision], self._stream()), "xn_op_window_attention")
+        return out
+
+    def op_logsoftmax_topk(self, logits, k, want_logprob=False):
+        x = self._f32(logits)
+        rows, V = x.shape
+        tv = torch.empty(rows, max(k, 1), device=self.device, dtype=torch.float32)
+        ti = torch.empty(rows, max(k, 1), device=self.device, dtype=torch.int32)
+        lp = torch.empty_like(x) if want_logprob else None
+        self._check(self.lib.xn_op_logsoftmax_topk(self._h, _ptr(x), rows, V, k, _ptr(tv), _ptr(ti), _ptr(lp), self._stream()),
+                    "xn_op_logsoftmax_topk")
+        return tv, ti, lp
+
+
+def unpack_beam_results(tok: torch.Tensor, ln: torch.Tensor, lp: torch.Tensor) -> Tuple[List[List[List[int]]], torch.Tensor]:
+    """Device/host result buffers -> the reference's return convention: nested token lists (SOS..EOS
+    inclusive, cut at length) and a (B, how_many, max_len_in_batch) zero-padded log-prob tensor
+    (reference models/captioning_model.py:401-425)."""
+    tok_c, ln_c = tok.cpu(), ln.cpu()
+    B, H, _ = tok_c.shape
+    res = [[tok_c[b, j, :int(ln_c[b, j])].tolist() for j in range(H)] for b in range(B)]
+    mx = int(ln_c.max()) if ln_c.numel() else 0
+    return res, lp[:, :, :mx]

@@ -1,0 +1,247 @@
+"""Parity checks of the CUDA path (through the C ABI) against the CPU oracle and the golden
+fixtures.  Each check returns a list of (label, measured, tolerance) triples; pytest asserts
+measured <= tolerance (tests/test_gpu_parity.py) and tools/gpu_selftest.py prints them all.
+
+Tolerances.  fp32 mode: BASELINE.json asks for logits/features within 1e-5 *relative*; we
+measure max|a-b| / max|b| (the tensors are O(1)) and allow 2e-5 on the 24-block Swin output,
+1e-5 elsewhere.  bf16 mode: 2e-3 relative is the stated target for features/logits; measured
+as relative Frobenius error.  Captions: bit-exact token sequences in fp32 mode wherever the
+oracle's decision margin (recorded in the fixture) exceeds 2e-5.
+"""
+from __future__ import annotations
+
+import math
+from typing import List, Tuple
+
+import numpy as np
+import torch
+
+from conftest import golden_setup, sub
+from oracle import xnv2_oracle as O
+from on_device_image_captioning_b200.engine import Engine, unpack_beam_results
+from on_device_image_captioning_b200.config import XNConfig
+
+Triple = Tuple[str, float, float]
+_engines = {}
+
+
+def rel_max(a: torch.Tensor, b: torch.Tensor) -> float:
+    a = a.detach().double().cpu(); b = b.detach().double().cpu()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+def rel_fro(a: torch.Tensor, b: torch.Tensor) -> float:
+    a = a.detach().double().cpu(); b = b.detach().double().cpu()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def bare_engine() -> Engine:
+    if "bare" not in _engines:
+        from on_device_image_captioning_b200.config import swin_tiny_test
+        _engines["bare"] = Engine(swin_tiny_test(), 0)
+    return _engines["bare"]
+
+
+def engine_for(name: str, precision: str):
+    key = (name, precision)
+    if key not in _engines:
+        # keep at most one big model resident per precision
+        for k in [k for k in _engines if k != "bare" and k[0] != name]:
+            _engines.pop(k).close()
+        g, cfg, sd, x, pads = golden_setup(name)
+        e = Engine(cfg, 0)
+        e.load_state_dict(sd, precision)
+        _engines[key] = (e, g, cfg, sd, x, pads)
+    return _engines[key]
+
+
+# ------------------------------------------------------------------ single kernels
+def check_layernorm() -> List[Triple]:
+    e = bare_engine()
+    out = []
+    g = torch.Generator().manual_seed(0)
+    for rows, C in [(7, 192), (1000, 768), (33, 1536), (5, 3072), (64, 512)]:
+        x = torch.randn(rows, C, generator=g) * 3 + 0.5
+        w = torch.rand(C, generator=g) + 0.5
+        b = torch.randn(C, generator=g)
+        y = e.op_layernorm(x, w, b)
+        ref = torch.nn.functional.layer_norm(x, (C,), w, b, 1e-5)
+        out.append((f"layernorm[{rows}x{C}] max-abs", float((y.cpu() - ref).abs().max()), 2e-5))
+    return out
+
+
+def check_linear_fp32() -> List[Triple]:
+    e = bare_engine()
+    out = []
+    g = torch.Generator().manual_seed(1)
+    for (M, N, K, act, res) in [(200, 192, 192, 0, False), (1000, 576, 192, 0, True), (300, 768, 3072, 1, False),
+                                (192, 10000, 512, 0, False), (77, 512, 2048, 2, True), (5, 64, 128, 0, False),
+                                (4096, 2304, 768, 0, False)]:
+        x = torch.randn(M, K, generator=g)
+        w = torch.randn(N, K, generator=g) / math.sqrt(K)
+        b = torch.randn(N, generator=g)
+        r = torch.randn(M, N, generator=g) if res else None
+        y = e.op_linear(x, w, b, r, act, "fp32")
+        ref = torch.nn.functional.linear(x.double(), w.double(), b.double())
+        if act == 1:
+            ref = torch.nn.functional.gelu(ref)
+        elif act == 2:
+            ref = torch.relu(ref)
+        if res:
+            ref = ref + r.double()
+        out.append((f"linear_fp32[{M}x{N}x{K} act{act} res{int(res)}] rel-max", rel_max(y, ref), 1e-5))
+    return out
+
+
+def check_linear_bf16() -> List[Triple]:
+    """tcgen05 GEMM vs an fp64 product of the same bf16-rounded operands (so only the fp32
+    accumulation order differs)."""
+    e = bare_engine()
+    out = []
+    g = torch.Generator().manual_seed(2)
+    for (M, N, K, act, res) in [(128, 128, 64, 0, False), (128, 256, 128, 0, False), (300, 192, 192, 0, True),
+                                (1000, 576, 192, 0, False), (4096, 3072, 768, 1, False), (2500, 768, 3072, 0, True),
+                                (777, 1536, 1536, 0, False), (20000, 384, 384, 0, False), (64, 10000, 512, 0, False)]:
+        x = torch.randn(M, K, generator=g)
+        w = torch.randn(N, K, generator=g) / math.sqrt(K)
+        b = torch.randn(N, generator=g)
+        r = torch.randn(M, N, generator=g) if res else None
+        y = e.op_linear(x, w, b, r, act, "bf16")
+        xb, wb = x.bfloat16().double(), w.bfloat16().double()
+        ref = torch.nn.functional.linear(xb, wb, b.double())
+        if act == 1:
+            ref = torch.nn.functional.gelu(ref)
+        if res:
+            ref = ref + r.double()
+        out.append((f"linear_bf16_tcgen05[{M}x{N}x{K} act{act} res{int(res)}] rel-max", rel_max(y, ref), 2e-5))
+    return out
+
+
+def check_window_attention(precision: str = "fp32") -> List[Triple]:
+    e = bare_engine()
+    out = []
+    g = torch.Generator().manual_seed(3)
+    for (B, H, heads, shift) in [(2, 24, 2, 0), (2, 24, 2, 6), (1, 48, 3, 6), (3, 12, 4, 0)]:
+        C = heads * 32
+        qkv = torch.randn(B * H * H, 3 * C, generator=g)
+        table = torch.randn(529, heads, generator=g) * 0.5
+        y = e.op_window_attention(qkv, table, B, H, C, heads, shift, precision)
+        # oracle: same math through the reference-shaped partition/roll path
+        q_in = qkv.bfloat16().float() if precision == "bf16" else qkv
+        x = q_in.reshape(B, H, H, 3 * C)
+        if shift:
+            x = torch.roll(x, shifts=(-shift, -shift), dims=(1, 2))
+        xw = O._to_windows(x, 12)
+        Bw = xw.shape[0]
+        qkv_w = xw.reshape(Bw, 144, 3, heads, 32).permute(2, 0, 3, 1, 4)
+        q, k, v = qkv_w[0] * (32 ** -0.5), qkv_w[1], qkv_w[2]
+        att = q @ k.transpose(-2, -1)
+        att = att + table[O.relative_position_index(12).reshape(-1)].reshape(144, 144, heads).permute(2, 0, 1).unsqueeze(0)
+        if shift:
+            lab = O._to_windows(O.shift_region_labels(H, 12, shift).reshape(1, H, H, 1).float(), 12).reshape(-1, 144)
+            diff = lab[:, None, :] - lab[:, :, None]
+            mask = torch.where(diff != 0, torch.tensor(-100.0), torch.tensor(0.0))
+            nW = mask.shape[0]
+            att = (att.reshape(Bw // nW, nW, heads, 144, 144) + mask[None, :, None]).reshape(Bw, heads, 144, 144)
+        o = (torch.softmax(att, -1) @ v).transpose(1, 2).reshape(Bw, 144, C)
+        o = O._from_windows(o, 12, B, H, H)
+        if shift:
+            o = torch.roll(o, shifts=(shift, shift), dims=(1, 2))
+        ref = o.reshape(B * H * H, C)
+        tol = 1e-5 if precision == "fp32" else 1e-2
+        out.append((f"window_attention_{precision}[B{B} H{H} heads{heads} shift{shift}] rel-max", rel_max(y, ref), tol))
+    return out
+
+
+def check_logsoftmax_topk() -> List[Triple]:
+    e = bare_engine()
+    g = torch.Generator().manual_seed(4)
+    out = []
+    for rows, V, k in [(6, 10000, 3), (17, 10000, 5), (4, 512, 8), (3, 777, 1)]:
+        x = torch.randn(rows, V, generator=g) * 2
+        tv, ti, lp = e.op_logsoftmax_topk(x, k, want_logprob=True)
+        ref = torch.log_softmax(x, -1)
+        rv, ri = torch.topk(ref, k, sorted=True)
+        out.append((f"logsoftmax[{rows}x{V}] max-abs", float((lp.cpu() - ref).abs().max()), 4e-6))
+        out.append((f"topk[{rows}x{V} k{k}] index mismatches", float((ti.cpu().long() != ri).sum()), 0.0))
+        out.append((f"topk[{rows}x{V} k{k}] value max-abs", float((tv.cpu() - rv).abs().max()), 4e-6))
+    return out
+
+
+# ------------------------------------------------------------------ model-level vs oracle + golden
+def check_encoder(name: str, precision: str = "fp32") -> List[Triple]:
+    e, g, cfg, sd, x, pads = engine_for(name, precision)
+    out = []
+    with torch.no_grad():
+        taps = {}
+        ref = O.forward_enc(sd, cfg, x, pads, taps)
+    tol_feat = 2e-5 if precision == "fp32" else 2e-3
+    fro = precision != "fp32"
+    m = rel_fro if fro else rel_max
+    kind = "rel-fro" if fro else "rel-max"
+    if cfg.has_swin:
+        sw = e.forward_swin(x)
+        out.append((f"{name}/{precision} swin features vs oracle {kind}", m(sw, taps["swin"]), tol_feat))
+        if precision == "fp32":
+            out.append((f"{name}/{precision} swin features vs golden(reference) max-abs",
+                        float(np.abs(sub(sw.cpu()).numpy() - g["swin_sub"]).max()), 5e-5))
+    enc = e.forward_enc(x, pads)
+    out.append((f"{name}/{precision} encoder output vs oracle {kind}", m(enc, ref), tol_feat))
+    if precision == "fp32":
+        out.append((f"{name}/{precision} encoder output vs golden(reference) max-abs",
+                    float(np.abs(sub(enc.cpu()).numpy() - g["enc_sub"]).max()), 2e-5))
+    return out
+
+
+def check_decoder(name: str, precision: str = "fp32") -> List[Triple]:
+    e, g, cfg, sd, x, pads = engine_for(name, precision)
+    out = []
+    with torch.no_grad():
+        enc = O.forward_enc(sd, cfg, x, pads)          # oracle encoder output as the common cross input
+        tok = torch.from_numpy(g["dec_tokens"])
+        dp = g["dec_pads"].tolist()
+        ref_lp = O.forward_dec(sd, cfg, enc, pads, tok, dp, True)
+        ref_lg = O.forward_dec(sd, cfg, enc, pads, tok, dp, False)
+    lg = e.forward_dec(enc, pads, tok, dp, False)
+    lp = e.forward_dec(enc, pads, tok, dp, True)
+    tol = 1e-5 if precision == "fp32" else 2e-3
+    out.append((f"{name}/{precision} teacher-forced logits vs oracle rel-max (incl. padded rows)", rel_max(lg, ref_lg), tol))
+    out.append((f"{name}/{precision} teacher-forced log-probs vs oracle max-abs", float((lp.cpu() - ref_lp).abs().max()),
+                2e-5 if precision == "fp32" else 2e-2))
+    if precision == "fp32":
+        out.append((f"{name}/{precision} logits vs golden(reference) max-abs",
+                    float(np.abs(sub(lg.cpu()).numpy() - g["dec_logits_sub"]).max()), 2e-5))
+        ti = torch.topk(lp.cpu(), 8, dim=-1).indices.numpy()
+        out.append((f"{name}/{precision} top-8 index mismatches vs golden(reference)", float((ti != g["dec_top8_idx"]).sum()), 0.0))
+    return out
+
+
+def check_beam(name: str, precision: str = "fp32") -> List[Triple]:
+    e, g, cfg, sd, x, pads = engine_for(name, precision)
+    m = g["meta"]
+    tok, ln, lp = e.beam_search(x, pads, m["sos"], m["eos"], m["beam"], m["how_many"], m["max_len"])
+    toks, lps = unpack_beam_results(tok, ln, lp)
+    out = []
+    margin = np.minimum(np.minimum(g["vocab_margin"], g["merge_margin"]), g["final_margin"])
+    bad_tok = 0
+    checked = 0
+    for b in range(m["B"]):
+        if precision == "fp32" and margin[b] <= 2e-5:
+            continue                                   # decision closer than the fp32 tolerance: not a parity claim
+        checked += 1
+        for j in range(m["how_many"]):
+            n = int(g["beam_len"][b, j])
+            if toks[b][j] != g["beam_tokens"][b, j, :n].tolist():
+                bad_tok += 1
+    if precision == "fp32":
+        out.append((f"{name}/fp32 caption token sequences differing from the reference ({checked}/{m['B']} images with margin>2e-5)",
+                    float(bad_tok), 0.0))
+        ref_lp = torch.from_numpy(g["beam_logprobs"])
+        if bad_tok == 0 and checked == m["B"] and tuple(lps.shape) == tuple(ref_lp.shape):
+            out.append((f"{name}/fp32 caption log-probs vs reference max-abs", float((lps.cpu() - ref_lp).abs().max()), 2e-5))
+    else:
+        out.append((f"{name}/bf16 caption token sequences differing from the reference (informational)", float(bad_tok), float("inf")))
+    return out
+
+
+ALL_FP32_MODEL_CASES = ["tiny_e2e_peaky", "tiny_e2e_xavier", "feat_peaky_b5", "feat_xavier_b1", "full_e2e_xavier", "full_e2e_peaky"]

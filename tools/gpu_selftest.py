@@ -1,0 +1,57 @@
+"""Run every GPU parity check and print/save all measurements (does not stop at the first
+failure).  Usage on the GPU box:  python tools/gpu_selftest.py [--quick] > gpurun_out/selftest.log"""
+import json
+import os
+import sys
+import time
+import traceback
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def main():
+    import gpu_checks as G
+    quick = "--quick" in sys.argv
+    only = [a for a in sys.argv[1:] if not a.startswith("--")]
+    jobs = [("layernorm", G.check_layernorm), ("linear_fp32", G.check_linear_fp32), ("linear_bf16", G.check_linear_bf16),
+            ("wattn_fp32", lambda: G.check_window_attention("fp32")), ("wattn_bf16", lambda: G.check_window_attention("bf16")),
+            ("logsoftmax_topk", G.check_logsoftmax_topk)]
+    cases = ["tiny_e2e_peaky", "tiny_e2e_xavier", "feat_peaky_b5", "feat_xavier_b1"] + ([] if quick else ["full_e2e_xavier", "full_e2e_peaky"])
+    for c in cases:
+        jobs += [(f"enc:{c}", lambda c=c: G.check_encoder(c, "fp32")), (f"dec:{c}", lambda c=c: G.check_decoder(c, "fp32")),
+                 (f"beam:{c}", lambda c=c: G.check_beam(c, "fp32"))]
+    for c in ["tiny_e2e_peaky"] + ([] if quick else ["full_e2e_xavier"]):
+        jobs += [(f"enc_bf16:{c}", lambda c=c: G.check_encoder(c, "bf16")), (f"beam_bf16:{c}", lambda c=c: G.check_beam(c, "bf16"))]
+    results, nbad = [], 0
+    for name, fn in jobs:
+        if only and not any(o in name for o in only):
+            continue
+        t0 = time.time()
+        try:
+            triples = fn()
+            for (l, v, t) in triples:
+                ok = v <= t
+                nbad += (not ok)
+                print(f"{'PASS' if ok else 'FAIL'}  {l}: {v:.3e} (tol {t:.1e})", flush=True)
+                results.append(dict(check=name, label=l, value=v, tol=t, ok=bool(ok)))
+        except Exception as ex:  # keep going: one GPU call should tell us as much as possible
+            nbad += 1
+            print(f"ERROR {name}: {ex!r}", flush=True)
+            traceback.print_exc()
+            results.append(dict(check=name, label="exception", value=None, tol=None, ok=False, error=repr(ex)))
+            if "CUDA" in repr(ex) or "cuda" in repr(ex):
+                print("CUDA error: stopping", flush=True)
+                break
+        print(f"      [{name} {time.time() - t0:.1f}s]", flush=True)
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    tag = os.environ.get("SELFTEST_TAG", "all")
+    with open(os.path.join(ROOT, "gpurun_out", f"selftest_{tag}.json"), "w") as f:
+        json.dump(results, f, indent=1)
+    print(f"SELFTEST {'OK' if nbad == 0 else 'FAILED'}: {nbad} failing of {len(results)}")
+    return 0 if nbad == 0 else 1
+
+
+if __name__ == "__main__":
+    sys.exit(main())
