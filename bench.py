@@ -1,0 +1,286 @@
+#!/usr/bin/env python
+"""Headline benchmark: captions/sec of the End_ExpansionNet_v2 (Swin-L/384, beam 3, max_len 20)
+captioning path -- BASELINE.json's metric on its configs[1] (batch 64 synthetic 384x384 images
+per GPU).
+
+  python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+  python bench.py --impl reference ...                     # the reference algorithm on the host CPU
+
+A "step" = caption one batch of 64 images per GPU (encoder + beam search, token ids out).  One
+process per GPU (torchrun for N > 1); images are sharded by rank, weights replicated; the only
+collective is the NCCL all-gather of the int32 caption tokens that ends every step.
+`value` is timed with CUDA events with inputs resident in HBM; `e2e` is the same metric through
+the C-ABI call that takes HOST buffers (xn_caption_host: H2D of the images and D2H of the
+tokens inside the timed region).  The line also carries the tensor-core roofline of the
+dominant kernel (the tcgen05 GEMM, event-timed per launch in an extra instrumented step),
+a CPU baseline (the oracle port of the reference algorithm on this host's cores, bounded
+sample) and the SM clocks seen during the timed region.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+BATCH = 64
+BEAM, MAX_LEN, SOS, EOS = 3, 20, 79, 77
+FLOPS_PER_CAPTION = 215.8e9          # Swin 207.84 + encoder 5.37 + cached decode 2.62 GFLOP
+METRIC = "captions_per_sec"
+UNIT = "captions/s"
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(bf16_sustained=d.get("bf16_tflops_sustained"), bf16_burst=d.get("bf16_tflops"), hbm=d.get("hbm_gbs"),
+                    source="measured (MEASURED_PEAKS.json)")
+    return dict(bf16_sustained=1400.0, bf16_burst=1590.0, hbm=6650.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.stop_flag, self.rows = index, threading.Event(), []
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            p = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "200"],
+                                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            return
+        while not self.stop_flag.is_set():
+            line = p.stdout.readline()
+            if not line:
+                break
+            self.rows.append([c.strip() for c in line.split(",")])
+        p.kill()
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith("active")})
+        busy = sorted(sm)[len(sm) // 2:] if sm else []
+        return dict(sm_mhz=statistics.median(busy) if busy else None, sm_max_mhz=max(mx) if mx else None,
+                    reasons=reasons, samples=len(sm))
+
+
+class CpuOracle:
+    """The oracle port of the reference algorithm (whole-prefix re-decode, dense masks) on the host CPU."""
+
+    def __init__(self, threads: int):
+        import torch
+        from on_device_image_captioning_b200 import config as C, synth
+        torch.set_num_threads(threads)
+        self.cfg = C.swin_l_384()
+        self.sd = synth.make_state_dict(self.cfg, 0, "xavier")
+        self.synth = synth
+
+    def captions_per_sec(self, n_images: int, seed: int = 1):
+        import torch
+        from oracle import xnv2_oracle as O
+        x = self.synth.make_images(self.cfg, n_images, seed, "randn")
+        with torch.no_grad():
+            t0 = time.perf_counter()
+            O.beam_search(self.sd, self.cfg, x, [0] * n_images, SOS, EOS, BEAM, 1, MAX_LEN)
+            dt = time.perf_counter() - t0
+        return n_images / dt, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    threads = os.cpu_count() or 1
+    n = 2
+    t_start = time.perf_counter()
+    cpu = CpuOracle(threads)
+    vals = []
+    for i in range(args.warmup + args.steps):
+        v, dt = cpu.captions_per_sec(n, seed=1 + i)
+        if i >= args.warmup:
+            vals.append(v)
+        if vals and time.perf_counter() - t_start > 240:
+            break
+    val = statistics.mean(vals)
+    line = dict(metric=METRIC, value=val, unit=UNIT, impl="reference", n_gpus=args.gpus, steps=len(vals), warmup=args.warmup,
+                ms_per_step=1e3 * n / val, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
+                data="synthetic",
+                config=dict(workload="End_ExpansionNet_v2 Swin-L/384 beam=3 max_len=20 (BASELINE.json configs[1]); "
+                                     f"each step a bounded sample of {n} images on the host CPU", batch=n, beam=BEAM, max_len=MAX_LEN),
+                cpu_baseline=dict(value=val, unit=UNIT, cores=threads, kind="port",
+                                  sample=f"{n} synthetic 384x384 images per step, oracle/xnv2_oracle.py (torch CPU fp32, "
+                                         "reference algorithm: whole-prefix re-decode)"),
+                e2e=dict(value=val, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    print(json.dumps(line))
+    return 0
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from on_device_image_captioning_b200 import config as C, synth
+    from on_device_image_captioning_b200.engine import Engine
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    cfg = C.swin_l_384()
+    eng = Engine(cfg, local)
+    eng.load_state_dict(synth.make_state_dict(cfg, 0, "xavier"), args.precision)
+    if args.swin_chunk:
+        eng.set_option("swin_chunk", args.swin_chunk)
+    B = args.batch
+    n_rot = 3                                            # rotate inputs so they are never L2-resident
+    host = [synth.make_images(cfg, B, seed=100 + rank * n_rot + i, kind="randn").pin_memory() for i in range(n_rot)]
+    devin = [h.to(dev) for h in host]
+    gathered = [torch.empty(B, 1, MAX_LEN, dtype=torch.int32, device=dev) for _ in range(world)]
+
+    def step(i):
+        tok, ln, lp = eng.beam_search(devin[i % n_rot], None, SOS, EOS, BEAM, 1, MAX_LEN)
+        if world > 1:
+            dist.all_gather(gathered, tok)               # the path's only collective: caption token ids
+        return tok
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        step(i)
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    l0 = eng.kernel_launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        step(i)
+    e1.record()
+    barrier()
+    launches = eng.kernel_launches - l0
+    ms = e0.elapsed_time(e1)
+    sampler.stop_flag.set()
+    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    value = world * B * args.steps / (ms / 1e3)
+
+    # ---- end to end: host buffers in, host tokens out, through the C-ABI call a user makes
+    outs = (torch.empty(B, 1, MAX_LEN, dtype=torch.int32).pin_memory(), torch.empty(B, 1, dtype=torch.int32).pin_memory(),
+            torch.empty(B, 1, MAX_LEN, dtype=torch.float32).pin_memory())
+    eng.caption_host(host[0], SOS, EOS, BEAM, 1, MAX_LEN, out=outs)
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        eng.caption_host(host[i % n_rot], SOS, EOS, BEAM, 1, MAX_LEN, out=outs)
+        if world > 1:
+            dist.all_gather(gathered, outs[0].to(dev, non_blocking=True))
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * B * args.steps / (float(t.item()) / 1e3)
+    h2d = host[0].numel() * 4
+    d2h = sum(o.numel() * o.element_size() for o in outs)
+
+    line = None
+    if rank == 0:
+        peaks = _peaks()
+        roofline = None
+        if args.precision != "fp32":
+            # ---- roofline of the dominant kernel: every tcgen05 GEMM launch of one more step, event-timed
+            eng.set_option("profile", 1)
+            step(0)
+            g_ms, g_fl, g_n = eng.profile_read()
+            eng.set_option("profile", 0)
+            achieved = g_fl / (g_ms * 1e-3) / 1e12 if g_ms > 0 else 0.0
+            roofline = dict(bound="tensor", kernel="gemm_tc_kernel (tcgen05.mma, TMA, TMEM)", achieved=achieved,
+                            peak=peaks["bf16_sustained"], unit="TFLOP/s", frac=achieved / peaks["bf16_sustained"],
+                            traffic=None, peak_source=peaks["source"] + ", sustained figure (kernel timed inside a long step)",
+                            launches_timed=g_n, gemm_ms_per_step=g_ms, gemm_share_of_step=g_ms / (ms / args.steps),
+                            algorithmic_tflop_per_step=g_fl / 1e12)
+        # ---- batch-1 latency (BASELINE.json configs[4])
+        lat = {}
+        one = devin[0][:1].contiguous()
+        for name, bm in (("beam3", 3), ("greedy", 1)):
+            ts = []
+            for i in range(3 + 20):
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                eng.beam_search(one, None, SOS, EOS, bm, 1, MAX_LEN)
+                b.record()
+                torch.cuda.synchronize()
+                if i >= 3:
+                    ts.append(a.elapsed_time(b))
+            lat[name + "_p50_ms"] = statistics.median(ts)
+        # ---- CPU baseline: bounded sample on this host's cores
+        threads = os.cpu_count() or 1
+        cpu_v, cpu_dt = CpuOracle(threads).captions_per_sec(2) if not args.no_cpu else (None, None)
+        clocks = sampler.summary()
+        whole_tflops = value / world * FLOPS_PER_CAPTION / 1e12
+        line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
+                    ms_per_step=ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
+                    dtype=args.precision if args.precision != "fp32" else "f32", data="synthetic",
+                    config=dict(workload="End_ExpansionNet_v2 Swin-L/384, N_enc=3 N_dec=3 d=512, beam=3 max_len=20, "
+                                         f"batch {B} synthetic 384x384 images per GPU (BASELINE.json configs[1])",
+                                batch_per_gpu=B, global_batch=B * world, beam=BEAM, max_len=MAX_LEN, parallelism=f"dp{world}",
+                                weights="synthetic xavier-style random init (reference Q5), seed 0",
+                                l2="working set (0.5-0.9 GB of weights + GBs of activations) >> 126 MB L2; inputs rotate over 3 batches",
+                                precision_note="Swin GEMMs on tcgen05 in 16-bit operands with fp32 accumulation; encoder/decoder fp32"
+                                if args.precision != "fp32" else "all fp32 (parity mode)"),
+                    e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h),
+                    gpu_launches=int(launches), roofline=roofline,
+                    whole_path=dict(algorithmic_tflops_per_gpu=whole_tflops, frac_of_tensor_peak=whole_tflops / peaks["bf16_sustained"],
+                                    flops_per_caption=FLOPS_PER_CAPTION),
+                    cpu_baseline=(dict(value=cpu_v, unit=UNIT, cores=threads, kind="port",
+                                       sample="2 synthetic 384x384 images, beam 3, max_len 20, oracle/xnv2_oracle.py (torch CPU fp32, "
+                                              f"{threads} threads), {cpu_dt:.1f} s") if cpu_v else None),
+                    latency_batch1=lat, clocks=clocks)
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default=os.environ.get("XNV2_PRECISION", "bf16"))
+    ap.add_argument("--batch", type=int, default=BATCH)
+    ap.add_argument("--swin-chunk", type=int, default=0)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -108,7 +108,11 @@ int xn_caption_host(xn_handle* h, const float* input_host, int B, int beam, int 
 /* Counters / introspection. */
 int64_t xn_kernel_launches(const xn_handle* h);      /* kernels of this library launched so far */
 int64_t xn_workspace_bytes(const xn_handle* h);
-int xn_set_option(xn_handle* h, const char* name, int64_t value);   /* e.g. "swin_chunk", "use_graph" */
+int xn_set_option(xn_handle* h, const char* name, int64_t value);   /* "swin_chunk", "enc_chunk", "profile" */
+/* With option "profile"=1 every tcgen05 GEMM launch is bracketed by CUDA events on its stream;
+ * this returns the summed device time, the summed algorithmic FLOPs and the launch count since
+ * the option was set (synchronises the device). */
+int xn_profile_read(xn_handle* h, double* ms_total, double* flops_total, int64_t* count);
 
 /* Single-operator entry points (kernel-level parity tests call these through the ABI).
  * All pointers device, row-major, f32 unless noted. */

@@ -44,6 +44,7 @@ _SIGNATURES = {
     "xn_kernel_launches": (C.c_int64, [_P]),
     "xn_workspace_bytes": (C.c_int64, [_P]),
     "xn_set_option": (C.c_int, [_P, C.c_char_p, C.c_int64]),
+    "xn_profile_read": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "xn_op_layernorm": (C.c_int, [_P, _P, _P, _P, _P, _I, _I, _P]),
     "xn_op_linear": (C.c_int, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "xn_op_window_attention": (C.c_int, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),

@@ -81,6 +81,11 @@ struct xn_handle {
   Arena ws;
   int64_t launches = 0;
   int64_t swin_chunk = 32, enc_chunk = 64;
+  // optional per-launch event timing of the tcgen05 GEMMs (bench.py roofline leg)
+  int64_t profile = 0;
+  std::vector<cudaEvent_t> prof_ev;
+  std::vector<double> prof_flops;
+  size_t prof_used = 0;
   float* io_in = nullptr; size_t io_in_cap = 0;     // xn_caption_host staging
   char* io_out = nullptr; size_t io_out_cap = 0;
 
@@ -147,6 +152,17 @@ int lin_tc(xn_handle* h, const bf16* x, long ldx, const LinW& w, const float* re
   TcGemmArgs g{};
   g.A = x; g.lda = ldx; g.W = w.wb; g.ldw = w.K; g.Cf = yf; g.Cb = yb; g.ldc = ldy;
   g.bias = w.b; g.res = res; g.ldr = ldr; g.M = M; g.N = w.N; g.K = w.K; g.div = 0.f; g.act = act;
+  if (h->profile) {
+    if (h->prof_used + 2 > h->prof_ev.size()) {
+      for (int i = 0; i < 2; ++i) { cudaEvent_t e; CU(cudaEventCreate(&e)); h->prof_ev.push_back(e); }
+    }
+    CU(cudaEventRecord(h->prof_ev[h->prof_used], st));
+    KL(1, launch_gemm_tc(g, st));
+    CU(cudaEventRecord(h->prof_ev[h->prof_used + 1], st));
+    h->prof_used += 2;
+    h->prof_flops.push_back(2.0 * M * (double)w.N * w.K);
+    return 0;
+  }
   KL(1, launch_gemm_tc(g, st));
   return 0;
 }
@@ -559,6 +575,7 @@ int xn_destroy(xn_handle* h) {
   if (h->ws.base) cudaFree(h->ws.base);
   if (h->io_in) cudaFree(h->io_in);
   if (h->io_out) cudaFree(h->io_out);
+  for (cudaEvent_t e : h->prof_ev) cudaEventDestroy(e);
   delete h;
   return XN_OK;
 }
@@ -874,9 +891,27 @@ int64_t xn_workspace_bytes(const xn_handle* h) { return h ? (int64_t)h->ws.cap :
 int xn_set_option(xn_handle* h, const char* name, int64_t value) {
   if (!h || !name) return XN_ERR_ARG;
   std::string n(name);
-  if (n == "swin_chunk") h->swin_chunk = std::max<int64_t>(1, value);
+  if (n == "profile") { h->profile = value; h->prof_used = 0; h->prof_flops.clear(); }
+  else if (n == "swin_chunk") h->swin_chunk = std::max<int64_t>(1, value);
   else if (n == "enc_chunk") h->enc_chunk = std::max<int64_t>(1, value);
   else return h->fail(XN_ERR_ARG, "unknown option '%s'", name);
+  return XN_OK;
+}
+
+int xn_profile_read(xn_handle* h, double* ms_total, double* flops_total, int64_t* count) {
+  if (!h) return XN_ERR_ARG;
+  cudaSetDevice(h->device);
+  CU(cudaDeviceSynchronize());
+  double ms = 0, fl = 0;
+  for (size_t i = 0; i + 1 < h->prof_used; i += 2) {
+    float t = 0.f;
+    CU(cudaEventElapsedTime(&t, h->prof_ev[i], h->prof_ev[i + 1]));
+    ms += t;
+  }
+  for (double f : h->prof_flops) fl += f;
+  if (ms_total) *ms_total = ms;
+  if (flops_total) *flops_total = fl;
+  if (count) *count = (int64_t)h->prof_flops.size();
   return XN_OK;
 }
 

@@ -83,6 +83,12 @@ class Engine:
     def set_option(self, name: str, value: int):
         self._check(self.lib.xn_set_option(self._h, name.encode(), int(value)), "xn_set_option")
 
+    def profile_read(self):
+        """(ms, flops, launches) of the event-timed tcgen05 GEMMs since set_option('profile', 1)."""
+        ms, fl, n = C.c_double(), C.c_double(), C.c_int64()
+        self._check(self.lib.xn_profile_read(self._h, C.byref(ms), C.byref(fl), C.byref(n)), "xn_profile_read")
+        return ms.value, fl.value, n.value
+
     def _f32(self, t: torch.Tensor) -> torch.Tensor:
         return t.to(device=self.device, dtype=torch.float32).contiguous()
 
@@ -170,8 +176,9 @@ class Engine:
     # -- single operators (kernel-level tests) ------------------------------------------------
     def op_layernorm(self, x, gamma, beta):
         x = self._f32(x); y = torch.empty_like(x)
+        g, b = self._f32(gamma), self._f32(beta)          # keep the temporaries alive across the launch
         rows = x.numel() // x.shape[-1]
-        self._check(self.lib.xn_op_layernorm(self._h, _ptr(x), _ptr(self._f32(gamma)), _ptr(self._f32(beta)), _ptr(y), rows,
+        self._check(self.lib.xn_op_layernorm(self._h, _ptr(x), _ptr(g), _ptr(b), _ptr(y), rows,
                                              x.shape[-1], self._stream()), "xn_op_layernorm")
         return y
 

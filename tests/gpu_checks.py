@@ -47,7 +47,7 @@ def engine_for(name: str, precision: str):
     if key not in _engines:
         # keep at most one big model resident per precision
         for k in [k for k in _engines if k != "bare" and k[0] != name]:
-            _engines.pop(k).close()
+            _engines.pop(k)[0].close()
         g, cfg, sd, x, pads = golden_setup(name)
         e = Engine(cfg, 0)
         e.load_state_dict(sd, precision)
@@ -206,8 +206,7 @@ def check_decoder(name: str, precision: str = "fp32") -> List[Triple]:
     lp = e.forward_dec(enc, pads, tok, dp, True)
     tol = 1e-5 if precision == "fp32" else 2e-3
     out.append((f"{name}/{precision} teacher-forced logits vs oracle rel-max (incl. padded rows)", rel_max(lg, ref_lg), tol))
-    out.append((f"{name}/{precision} teacher-forced log-probs vs oracle max-abs", float((lp.cpu() - ref_lp).abs().max()),
-                2e-5 if precision == "fp32" else 2e-2))
+    out.append((f"{name}/{precision} teacher-forced log-probs vs oracle rel-max", rel_max(lp, ref_lp), tol))
     if precision == "fp32":
         out.append((f"{name}/{precision} logits vs golden(reference) max-abs",
                     float(np.abs(sub(lg.cpu()).numpy() - g["dec_logits_sub"]).max()), 2e-5))
@@ -238,7 +237,7 @@ def check_beam(name: str, precision: str = "fp32") -> List[Triple]:
                     float(bad_tok), 0.0))
         ref_lp = torch.from_numpy(g["beam_logprobs"])
         if bad_tok == 0 and checked == m["B"] and tuple(lps.shape) == tuple(ref_lp.shape):
-            out.append((f"{name}/fp32 caption log-probs vs reference max-abs", float((lps.cpu() - ref_lp).abs().max()), 2e-5))
+            out.append((f"{name}/fp32 caption log-probs vs reference rel-max", rel_max(lps, ref_lp), 1e-5))
     else:
         out.append((f"{name}/bf16 caption token sequences differing from the reference (informational)", float(bad_tok), float("inf")))
     return out
