@@ -30,7 +30,7 @@ extern "C" {
 typedef struct xn_handle xn_handle;
 
 enum { XN_OK = 0, XN_ERR_ARG = -1, XN_ERR_CUDA = -2, XN_ERR_STATE = -3, XN_ERR_UNSUPPORTED = -4 };
-enum { XN_PREC_FP32 = 0, XN_PREC_BF16 = 1 };
+enum { XN_PREC_FP32 = 0, XN_PREC_BF16 = 1, XN_PREC_FP16 = 2 };   /* 16-bit modes: tcgen05 operands, fp32 accumulate */
 enum { XN_DTYPE_F32 = 0, XN_DTYPE_I64 = 1 };
 
 /* Model geometry: the constructor arguments of End_ExpansionNet_v2 / ExpansionNet_v2

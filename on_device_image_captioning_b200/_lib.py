@@ -12,7 +12,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libxnv2_b200.so")
 
-XN_PREC_FP32, XN_PREC_BF16 = 0, 1
+XN_PREC_FP32, XN_PREC_BF16, XN_PREC_FP16 = 0, 1, 2
 XN_DTYPE_F32, XN_DTYPE_I64 = 0, 1
 
 

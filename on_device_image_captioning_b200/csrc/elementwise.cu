@@ -27,6 +27,15 @@ __device__ __forceinline__ void store4<bf16>(bf16* p, float a, float b, float c,
   *reinterpret_cast<uint2*>(p) = u;
 }
 
+template <>
+__device__ __forceinline__ void store4<f16>(f16* p, float a, float b, float c, float d) {
+  __half2 lo = __floats2half2_rn(a, b), hi = __floats2half2_rn(c, d);
+  uint2 u;
+  u.x = *reinterpret_cast<uint32_t*>(&lo);
+  u.y = *reinterpret_cast<uint32_t*>(&hi);
+  *reinterpret_cast<uint2*>(p) = u;
+}
+
 template <typename OutT, typename SrcFn>
 __device__ __forceinline__ void ln_row(SrcFn src, const float* __restrict__ g, const float* __restrict__ b,
                                        OutT* __restrict__ yr, int C, int lane) {
@@ -73,6 +82,7 @@ cudaError_t launch_layernorm(const float* x, long ldx, const float* gamma, const
 }
 template cudaError_t launch_layernorm<float>(const float*, long, const float*, const float*, float*, long, long, int, cudaStream_t);
 template cudaError_t launch_layernorm<bf16>(const float*, long, const float*, const float*, bf16*, long, long, int, cudaStream_t);
+template cudaError_t launch_layernorm<f16>(const float*, long, const float*, const float*, f16*, long, long, int, cudaStream_t);
 
 // PatchMerging gather + LN(4C): reference swin:482-501.  Output row (b,i,j) concatenates the
 // input tokens (2i,2j), (2i+1,2j), (2i,2j+1), (2i+1,2j+1) in that order.
@@ -105,6 +115,7 @@ cudaError_t launch_merge_layernorm(const float* x, const float* gamma, const flo
 }
 template cudaError_t launch_merge_layernorm<float>(const float*, const float*, const float*, float*, int, int, int, cudaStream_t);
 template cudaError_t launch_merge_layernorm<bf16>(const float*, const float*, const float*, bf16*, int, int, int, cudaStream_t);
+template cudaError_t launch_merge_layernorm<f16>(const float*, const float*, const float*, f16*, int, int, int, cudaStream_t);
 
 // ------------------------------------------------------------------------------------------
 // PatchEmbed (reference swin:611-654): Conv2d(Cin->E, k=stride=P) + flatten + LayerNorm(E).
@@ -189,6 +200,7 @@ cudaError_t launch_cast(const float* x, T* y, long n, cudaStream_t st) {
   return cudaGetLastError();
 }
 template cudaError_t launch_cast<bf16>(const float*, bf16*, long, cudaStream_t);
+template cudaError_t launch_cast<f16>(const float*, f16*, long, cudaStream_t);
 template cudaError_t launch_cast<float>(const float*, float*, long, cudaStream_t);
 
 // ------------------------------------------------------------------------------------------

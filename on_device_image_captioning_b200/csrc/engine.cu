@@ -16,7 +16,7 @@
 
 using namespace xn;
 
-cudaError_t launch_widen_bf16(const bf16* x, float* y, long n, cudaStream_t st);
+cudaError_t launch_widen_16(const void* x, float* y, long n, int fp16, cudaStream_t st);
 
 namespace {
 
@@ -30,7 +30,7 @@ struct DevTensor {
 
 struct LinW {
   const float* w = nullptr;   // (N, K) fp32
-  const bf16* wb = nullptr;   // (N, K) bf16 copy (bf16 mode)
+  const void* wb = nullptr;   // (N, K) 16-bit copy (bf16 / fp16 modes)
   const float* b = nullptr;   // (N) or null
   int N = 0, K = 0;
 };
@@ -147,10 +147,10 @@ int lin_f32(xn_handle* h, const float* x, long ldx, const LinW& w, const float* 
   KL(1, launch_gemm_f32(g, st));
   return 0;
 }
-int lin_tc(xn_handle* h, const bf16* x, long ldx, const LinW& w, const float* res, long ldr, float* yf, bf16* yb,
-           long ldy, int M, int act, cudaStream_t st) {
+int lin_tc(xn_handle* h, const void* x, long ldx, const LinW& w, const float* res, long ldr, float* yf, void* yb,
+           long ldy, int M, int act, int fp16, cudaStream_t st) {
   TcGemmArgs g{};
-  g.A = x; g.lda = ldx; g.W = w.wb; g.ldw = w.K; g.Cf = yf; g.Cb = yb; g.ldc = ldy;
+  g.A = x; g.lda = ldx; g.W = w.wb; g.ldw = w.K; g.Cf = yf; g.Cb = yb; g.ldc = ldy; g.fp16 = fp16;
   g.bias = w.b; g.res = res; g.ldr = ldr; g.M = M; g.N = w.N; g.K = w.K; g.div = 0.f; g.act = act;
   if (h->profile) {
     if (h->prof_used + 2 > h->prof_ev.size()) {
@@ -176,20 +176,37 @@ template <> struct ActOps<float> {
   static int lin_res(xn_handle* h, const float* x, long ldx, const LinW& w, const float* res, long ldr, float* y, long ldy, int M, cudaStream_t st) {
     return lin_f32(h, x, ldx, w, res, ldr, y, ldy, M, 0, st);
   }
+  static cudaError_t attn(const float* qkv, const float* rpb, float* o, int B, int H, int C, int heads, int shift, cudaStream_t st) {
+    return launch_window_attention<float>(qkv, rpb, o, B, H, C, heads, shift, st);
+  }
 };
 template <> struct ActOps<bf16> {
   static int lin_act(xn_handle* h, const bf16* x, long ldx, const LinW& w, bf16* y, long ldy, int M, int act, cudaStream_t st) {
-    return lin_tc(h, x, ldx, w, nullptr, 0, nullptr, y, ldy, M, act, st);
+    return lin_tc(h, x, ldx, w, nullptr, 0, nullptr, y, ldy, M, act, 0, st);
   }
   static int lin_res(xn_handle* h, const bf16* x, long ldx, const LinW& w, const float* res, long ldr, float* y, long ldy, int M, cudaStream_t st) {
-    return lin_tc(h, x, ldx, w, res, ldr, y, nullptr, ldy, M, 0, st);
+    return lin_tc(h, x, ldx, w, res, ldr, y, nullptr, ldy, M, 0, 0, st);
+  }
+  static cudaError_t attn(const bf16* qkv, const float* rpb, bf16* o, int B, int H, int C, int heads, int shift, cudaStream_t st) {
+    return launch_window_attention_mma<bf16>(qkv, rpb, o, B, H, C, heads, shift, st);
+  }
+};
+template <> struct ActOps<f16> {
+  static int lin_act(xn_handle* h, const f16* x, long ldx, const LinW& w, f16* y, long ldy, int M, int act, cudaStream_t st) {
+    return lin_tc(h, x, ldx, w, nullptr, 0, nullptr, y, ldy, M, act, 1, st);
+  }
+  static int lin_res(xn_handle* h, const f16* x, long ldx, const LinW& w, const float* res, long ldr, float* y, long ldy, int M, cudaStream_t st) {
+    return lin_tc(h, x, ldx, w, res, ldr, y, nullptr, ldy, M, 0, 1, st);
+  }
+  static cudaError_t attn(const f16* qkv, const float* rpb, f16* o, int B, int H, int C, int heads, int shift, cudaStream_t st) {
+    return launch_window_attention_mma<f16>(qkv, rpb, o, B, H, C, heads, shift, st);
   }
 };
 
 // ---- Swin backbone --------------------------------------------------------------------------
 size_t swin_ws_bytes(const xn_config& c, int Bc, int prec) {
   const size_t G = c.img_size / c.patch_size, L0 = G * G, C0 = c.embed_dim;
-  const size_t act = prec == XN_PREC_BF16 ? 2 : 4;
+  const size_t act = prec == XN_PREC_FP32 ? 4 : 2;
   size_t tok = (size_t)Bc * L0 * C0;                 // elements of x at stage 0 (largest)
   size_t b = 0;
   b += 2 * tok * 4;                                   // x, x2 (fp32 residual stream, ping-pong over merges)
@@ -222,7 +239,7 @@ int swin_forward_chunk(xn_handle* h, const float* img, int Bc, float* out, cudaS
       const int shift = (bi % 2 == 1 && H > c.window_size) ? c.window_size / 2 : 0;
       KL(1, launch_layernorm<T>(x, C, W.n1g, W.n1b, xn, C, M, C, st));
       if (int r = ActOps<T>::lin_act(h, xn, C, W.qkv, qkv, 3 * C, M, 0, st)) return r;
-      KL(1, launch_window_attention<T>(qkv, W.rpb, ao, Bc, H, C, S.heads, shift, st));
+      KL(1, ActOps<T>::attn(qkv, W.rpb, ao, Bc, H, C, S.heads, shift, st));
       if (int r = ActOps<T>::lin_res(h, ao, C, W.proj, x, C, x, C, M, st)) return r;
       KL(1, launch_layernorm<T>(x, C, W.n2g, W.n2b, xn, C, M, C, st));
       if (int r = ActOps<T>::lin_act(h, xn, C, W.fc1, hid, W.fc1.N, M, 1, st)) return r;
@@ -249,8 +266,9 @@ int swin_forward(xn_handle* h, const float* img, int B, float* out, cudaStream_t
   for (int b0 = 0; b0 < B; b0 += chunk) {
     const int Bc = std::min(chunk, B - b0);
     h->ws.reset();
-    int r = (h->precision == XN_PREC_BF16) ? swin_forward_chunk<bf16>(h, img + b0 * img_elems, Bc, out + b0 * out_elems, st)
-                                           : swin_forward_chunk<float>(h, img + b0 * img_elems, Bc, out + b0 * out_elems, st);
+    int r = (h->precision == XN_PREC_BF16)   ? swin_forward_chunk<bf16>(h, img + b0 * img_elems, Bc, out + b0 * out_elems, st)
+            : (h->precision == XN_PREC_FP16) ? swin_forward_chunk<f16>(h, img + b0 * img_elems, Bc, out + b0 * out_elems, st)
+                                             : swin_forward_chunk<float>(h, img + b0 * img_elems, Bc, out + b0 * out_elems, st);
     if (r) return r;
   }
   return 0;
@@ -603,7 +621,7 @@ int xn_load_tensor(xn_handle* h, const char* key, const void* data, int dtype, c
 
 int xn_finalize_weights(xn_handle* h, int precision) {
   if (!h) return XN_ERR_ARG;
-  if (precision != XN_PREC_FP32 && precision != XN_PREC_BF16) return h->fail(XN_ERR_ARG, "bad precision");
+  if (precision != XN_PREC_FP32 && precision != XN_PREC_BF16 && precision != XN_PREC_FP16) return h->fail(XN_ERR_ARG, "bad precision");
   cudaSetDevice(h->device);
   const xn_config& c = h->cfg;
   for (void* p : h->owned) cudaFree(p);
@@ -619,12 +637,13 @@ int xn_finalize_weights(xn_handle* h, int precision) {
     l.N = (int)N; l.K = (int)K;
     return l;
   };
-  auto to_bf16 = [&](LinW& l) -> int {
+  auto to_bf16 = [&](LinW& l) -> int {      // 16-bit operand copy in the mode's format
     if (rc || !l.w) return rc;
-    bf16* p = nullptr;
-    CU(cudaMalloc(&p, (size_t)l.N * l.K * sizeof(bf16)));
+    void* p = nullptr;
+    CU(cudaMalloc(&p, (size_t)l.N * l.K * 2));
     h->owned.push_back(p);
-    KL(1, launch_cast<bf16>(l.w, p, (long)l.N * l.K, 0));
+    if (precision == XN_PREC_FP16) KL(1, launch_cast<f16>(l.w, reinterpret_cast<f16*>(p), (long)l.N * l.K, 0));
+    else KL(1, launch_cast<bf16>(l.w, reinterpret_cast<bf16*>(p), (long)l.N * l.K, 0));
     l.wb = p;
     return 0;
   };
@@ -666,7 +685,7 @@ int xn_finalize_weights(xn_handle* h, int precision) {
         W.rpb = P(q + "attn.relative_position_bias_table", {23 * 23, S.heads});
         W.qkv = lin(q + "attn.qkv", 3 * C, C); W.proj = lin(q + "attn.proj", C, C);
         W.fc1 = lin(q + "mlp.fc1", hid, C); W.fc2 = lin(q + "mlp.fc2", C, hid);
-        if (precision == XN_PREC_BF16) {
+        if (precision != XN_PREC_FP32) {
           if (to_bf16(W.qkv) || to_bf16(W.proj) || to_bf16(W.fc1) || to_bf16(W.fc2)) return XN_ERR_CUDA;
         }
         S.blocks.push_back(W);
@@ -676,7 +695,7 @@ int xn_finalize_weights(xn_handle* h, int precision) {
         S.has_merge = true;
         S.mg = P(q + "norm.weight", {4 * C}); S.mb = P(q + "norm.bias", {4 * C});
         S.red = lin(q + "reduction", 2 * C, 4 * C, false);
-        if (precision == XN_PREC_BF16 && to_bf16(S.red)) return XN_ERR_CUDA;
+        if (precision != XN_PREC_FP32 && to_bf16(S.red)) return XN_ERR_CUDA;
       }
       h->stages.push_back(S);
     }
@@ -891,6 +910,7 @@ int64_t xn_workspace_bytes(const xn_handle* h) { return h ? (int64_t)h->ws.cap :
 int xn_set_option(xn_handle* h, const char* name, int64_t value) {
   if (!h || !name) return XN_ERR_ARG;
   std::string n(name);
+  if (n == "tc_debug") { set_tc_debug((int)value); return XN_OK; }
   if (n == "profile") { h->profile = value; h->prof_used = 0; h->prof_flops.clear(); }
   else if (n == "swin_chunk") h->swin_chunk = std::max<int64_t>(1, value);
   else if (n == "enc_chunk") h->enc_chunk = std::max<int64_t>(1, value);
@@ -938,10 +958,16 @@ int xn_op_linear(xn_handle* h, const float* x, const float* w, const float* bias
   if (int r = ensure_ws(h, ((size_t)M * K + (size_t)N * K) * 2 + 8192, st)) return r;
   bf16* xb = h->ws.get<bf16>((size_t)M * K);
   bf16* wb = h->ws.get<bf16>((size_t)N * K);
-  KL(1, launch_cast<bf16>(x, xb, (long)M * K, st));
-  KL(1, launch_cast<bf16>(w, wb, (long)N * K, st));
+  const int fp16 = precision == XN_PREC_FP16;
+  if (fp16) {
+    KL(1, launch_cast<f16>(x, reinterpret_cast<f16*>(xb), (long)M * K, st));
+    KL(1, launch_cast<f16>(w, reinterpret_cast<f16*>(wb), (long)N * K, st));
+  } else {
+    KL(1, launch_cast<bf16>(x, xb, (long)M * K, st));
+    KL(1, launch_cast<bf16>(w, wb, (long)N * K, st));
+  }
   LinW l; l.wb = wb; l.b = bias; l.N = N; l.K = K;
-  return lin_tc(h, xb, K, l, residual, N, y, nullptr, N, M, act, st);
+  return lin_tc(h, xb, K, l, residual, N, y, nullptr, N, M, act, fp16, st);
 }
 
 int xn_op_window_attention(xn_handle* h, const float* qkv, const float* bias_table, float* out, int B, int H, int C, int heads,
@@ -955,10 +981,14 @@ int xn_op_window_attention(xn_handle* h, const float* qkv, const float* bias_tab
   if (int r = ensure_ws(h, n * 4 * 2 + 8192, st)) return r;
   bf16* qb = h->ws.get<bf16>(3 * n);
   bf16* ob = h->ws.get<bf16>(n);
-  KL(1, launch_cast<bf16>(qkv, qb, (long)(3 * n), st));
-  KL(1, launch_window_attention<bf16>(qb, bias_table, ob, B, H, C, heads, shift, st));
-  // widen the bf16 result for the caller
-  KL(1, launch_widen_bf16(ob, out, (long)n, st));
+  if (precision == XN_PREC_FP16) {
+    KL(1, launch_cast<f16>(qkv, reinterpret_cast<f16*>(qb), (long)(3 * n), st));
+    KL(1, launch_window_attention_mma<f16>(reinterpret_cast<f16*>(qb), bias_table, reinterpret_cast<f16*>(ob), B, H, C, heads, shift, st));
+  } else {
+    KL(1, launch_cast<bf16>(qkv, qb, (long)(3 * n), st));
+    KL(1, launch_window_attention_mma<bf16>(qb, bias_table, ob, B, H, C, heads, shift, st));
+  }
+  KL(1, launch_widen_16(ob, out, (long)n, precision == XN_PREC_FP16, st));
   return XN_OK;
 }
 
@@ -971,11 +1001,11 @@ int xn_op_logsoftmax_topk(xn_handle* h, const float* logits, int rows, int V, in
 
 }  // extern "C"
 
-__global__ void widen_bf16_kernel(const bf16* __restrict__ x, float* __restrict__ y, long n) {
+__global__ void widen_16_kernel(const void* __restrict__ x, float* __restrict__ y, long n, int fp16) {
   const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) y[i] = __bfloat162float(x[i]);
+  if (i < n) y[i] = fp16 ? __half2float(reinterpret_cast<const f16*>(x)[i]) : __bfloat162float(reinterpret_cast<const bf16*>(x)[i]);
 }
-cudaError_t launch_widen_bf16(const bf16* x, float* y, long n, cudaStream_t st) {
-  widen_bf16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(x, y, n);
+cudaError_t launch_widen_16(const void* x, float* y, long n, int fp16, cudaStream_t st) {
+  widen_16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(x, y, n, fp16);
   return cudaGetLastError();
 }

@@ -36,16 +36,18 @@ template <int BN> struct TcCfg {
   static constexpr int kStages = (BN == 256) ? 4 : (BN == 192 ? 5 : 6);
   static constexpr uint32_t kAccCols = 256;                 // column stride between the two accumulators
   static constexpr uint32_t kTmemCols = 512;
-  static constexpr uint32_t kStagingBytes = 4 * 32 * 33 * 4;
+  static constexpr uint32_t kStagingBytes = 4 * 32 * 36 * 4;   // per epilogue warp: 32 rows x 36 floats (16-B aligned rows)
   static constexpr uint32_t kSmemBytes = kStages * kStageBytes + kStagingBytes + 256 + 1024;
 };
 
 struct TcEpilogue {
-  float* Cf; bf16* Cb; long ldc;
+  float* Cf; void* Cb; long ldc;
+  int fp16;
   const float* bias;
   const float* res; long ldr;
   float div;
   int act;
+  int dbg;     // timing experiments only: 1 = skip the epilogue's global traffic, 2 = skip MMA issue, 4 = skip TMA loads
 };
 
 // ---------------------------------------------------------------- PTX wrappers
@@ -115,8 +117,9 @@ __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t saddr) {
 }
 // Instruction descriptor (cute::UMMA::InstrDescriptor): D=F32 [4,6)=1, A=BF16 [7,10)=1, B=BF16 [10,13)=1,
 // A/B K-major (bits 15,16 = 0), N>>3 at [17,23), M>>4 at [24,29).
-__host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+// A/B format field: 0 = F16, 1 = BF16.
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N, int ab_fmt) {
+  return (1u << 4) | ((uint32_t)ab_fmt << 7) | ((uint32_t)ab_fmt << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
 template <int BN>
@@ -168,6 +171,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         const int m0 = (tile / n_tiles) * kBM, n0 = (tile % n_tiles) * BN;
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
+          if (ep.dbg & 4) { mbar_arrive(full_bar(stage)); if (++stage == S) { stage = 0; phase ^= 1u; } continue; }
           mbar_expect_tx(full_bar(stage), Cfg::kStageBytes);
           const uint32_t sa = base + stage * Cfg::kStageBytes;
           tma_load_2d(sa, &tma_a, kb * kBK, m0, full_bar(stage));
@@ -178,7 +182,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(kBM, BN);
+      const uint32_t idesc = make_idesc(kBM, BN, ep.fp16 ? 0 : 1);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -194,9 +198,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
           const uint32_t sa = base + stage * Cfg::kStageBytes;
           const uint64_t adesc = make_sw128_desc(sa);
           const uint64_t bdesc = make_sw128_desc(sa + kABytes);
+          if (!(ep.dbg & 2)) {
 #pragma unroll
-          for (int k = 0; k < kBK / kUmmaK; ++k)   // +32 bytes (>>4 = 2) per UMMA_K step inside the swizzle atom
-            umma_bf16(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (uint32_t)((kb | k) != 0));
+            for (int k = 0; k < kBK / kUmmaK; ++k)   // +32 bytes (>>4 = 2) per UMMA_K step inside the swizzle atom
+              umma_bf16(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (uint32_t)((kb | k) != 0));
+          }
           umma_commit(empty_bar(stage));           // frees the smem slot when these MMAs retire
           if (++stage == S) { stage = 0; phase ^= 1u; }
         }
@@ -205,7 +211,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     }
   } else {
     const int q = warp & 3;                        // TMEM lane quarter this warp may access
-    float* tile_s = staging_gen + (warp - 2) * (32 * 33);
+    float* tile_s = staging_gen + (warp - 2) * (32 * 36);
+    const int sub_r = lane >> 3, c4 = (lane & 7) * 4;   // coalesced phase: 4 rows x 8 lanes x float4 per instruction
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       const int buf = it & 1;
@@ -219,25 +226,75 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         if (n0 + c0 >= N) break;
         uint32_t v[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * Cfg::kAccCols + c0, v);
+        // transpose through smem: lane == accumulator row; conflict-free 16-byte stores
 #pragma unroll
-        for (int c = 0; c < 32; ++c) tile_s[lane * 33 + c] = __uint_as_float(v[c]);
+        for (int j = 0; j < 8; ++j)
+          *reinterpret_cast<uint4*>(&tile_s[lane * 36 + 4 * j]) = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
         __syncwarp();
-        const int col = n0 + c0 + lane;
-        const bool col_ok = col < N;
-        const float bcol = (ep.bias && col_ok) ? ep.bias[col] : 0.f;
-#pragma unroll 4
-        for (int r = 0; r < 32; ++r) {
+        if (ep.dbg & 1) { __syncwarp(); continue; }
+        const int col = n0 + c0 + c4;
+        const bool vec_ok = (col + 3 < N) && ((ep.ldc & 3) == 0) && (!ep.res || (ep.ldr & 3) == 0);
+        float4 bcol = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (ep.bias) {
+          if (col + 3 < N) bcol = *reinterpret_cast<const float4*>(ep.bias + col);
+          else {
+            if (col < N) bcol.x = ep.bias[col];
+            if (col + 1 < N) bcol.y = ep.bias[col + 1];
+            if (col + 2 < N) bcol.z = ep.bias[col + 2];
+          }
+        }
+        float4 acc[8], rres[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int r = i * 4 + sub_r;
+          acc[i] = *reinterpret_cast<const float4*>(&tile_s[r * 36 + c4]);
+          rres[i] = make_float4(0.f, 0.f, 0.f, 0.f);
           const int row = row_base + r;
-          if (row >= M) break;
-          float x = tile_s[r * 33 + lane];
-          if (ep.div != 0.f) x = x / ep.div;
-          x += bcol;
-          if (ep.act == 1) x = gelu_erf(x);
-          else if (ep.act == 2) x = fmaxf(x, 0.f);
-          if (col_ok) {
-            if (ep.res) x += ep.res[(long)row * ep.ldr + col];
-            if (ep.Cf) ep.Cf[(long)row * ep.ldc + col] = x;
-            else ep.Cb[(long)row * ep.ldc + col] = __float2bfloat16_rn(x);
+          if (ep.res && row < M) {
+            if (vec_ok) rres[i] = *reinterpret_cast<const float4*>(ep.res + (long)row * ep.ldr + col);
+            else {
+              if (col < N) rres[i].x = ep.res[(long)row * ep.ldr + col];
+              if (col + 1 < N) rres[i].y = ep.res[(long)row * ep.ldr + col + 1];
+              if (col + 2 < N) rres[i].z = ep.res[(long)row * ep.ldr + col + 2];
+              if (col + 3 < N) rres[i].w = ep.res[(long)row * ep.ldr + col + 3];
+            }
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int row = row_base + i * 4 + sub_r;
+          float x[4] = {acc[i].x, acc[i].y, acc[i].z, acc[i].w};
+          const float bb[4] = {bcol.x, bcol.y, bcol.z, bcol.w};
+          const float rr[4] = {rres[i].x, rres[i].y, rres[i].z, rres[i].w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            float t = x[e];
+            if (ep.div != 0.f) t = t / ep.div;
+            t += bb[e];
+            if (ep.act == 1) t = gelu_erf(t);
+            else if (ep.act == 2) t = fmaxf(t, 0.f);
+            x[e] = t + rr[e];
+          }
+          if (row < M && col < N) {
+            if (ep.Cf) {
+              float* dst = ep.Cf + (long)row * ep.ldc + col;
+              if (vec_ok) *reinterpret_cast<float4*>(dst) = make_float4(x[0], x[1], x[2], x[3]);
+              else for (int e = 0; e < 4; ++e) if (col + e < N) dst[e] = x[e];
+            } else if (ep.fp16) {
+              f16* dst = reinterpret_cast<f16*>(ep.Cb) + (long)row * ep.ldc + col;
+              if (vec_ok) {
+                __half2 lo = __floats2half2_rn(x[0], x[1]), hi = __floats2half2_rn(x[2], x[3]);
+                uint2 u; u.x = *reinterpret_cast<uint32_t*>(&lo); u.y = *reinterpret_cast<uint32_t*>(&hi);
+                *reinterpret_cast<uint2*>(dst) = u;
+              } else for (int e = 0; e < 4; ++e) if (col + e < N) dst[e] = __float2half_rn(x[e]);
+            } else {
+              bf16* dst = reinterpret_cast<bf16*>(ep.Cb) + (long)row * ep.ldc + col;
+              if (vec_ok) {
+                __nv_bfloat162 lo = __floats2bfloat162_rn(x[0], x[1]), hi = __floats2bfloat162_rn(x[2], x[3]);
+                uint2 u; u.x = *reinterpret_cast<uint32_t*>(&lo); u.y = *reinterpret_cast<uint32_t*>(&hi);
+                *reinterpret_cast<uint2*>(dst) = u;
+              } else for (int e = 0; e < 4; ++e) if (col + e < N) dst[e] = __float2bfloat16_rn(x[e]);
+            }
           }
         }
         __syncwarp();
@@ -274,18 +331,21 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-static bool make_map(CUtensorMap* map, const bf16* ptr, long rows, long cols, long ld, int box_rows) {
+static bool make_map(CUtensorMap* map, const void* ptr, long rows, long cols, long ld, int box_rows, int fp16) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return false;
   cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
   cuuint64_t gstride[1] = {(cuuint64_t)ld * 2};
   cuuint32_t box[2] = {(cuuint32_t)kBK, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<bf16*>(ptr), gdim, gstride, box, estr,
+  CUresult r = fn(map, fp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstride, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS;
 }
+
+int g_tc_debug = 0;
+void set_tc_debug(int v) { g_tc_debug = v; }
 
 bool tc_gemm_supported(int M, int N, int K) { return M > 0 && N > 0 && K > 0 && (K % 8) == 0; }
 
@@ -310,8 +370,8 @@ static cudaError_t launch_tc(const TcGemmArgs& p, cudaStream_t st) {
     configured = true;
   }
   CUtensorMap ma, mb;
-  if (!make_map(&ma, p.A, p.M, p.K, p.lda, kBM) || !make_map(&mb, p.W, p.N, p.K, p.ldw, BN)) return cudaErrorInvalidValue;
-  TcEpilogue ep{p.Cf, p.Cb, p.ldc, p.bias, p.res, p.ldr, p.div, p.act};
+  if (!make_map(&ma, p.A, p.M, p.K, p.lda, kBM, p.fp16) || !make_map(&mb, p.W, p.N, p.K, p.ldw, BN, p.fp16)) return cudaErrorInvalidValue;
+  TcEpilogue ep{p.Cf, p.Cb, p.ldc, p.fp16, p.bias, p.res, p.ldr, p.div, p.act, g_tc_debug};
   const int tiles = ((p.M + kBM - 1) / kBM) * ((p.N + BN - 1) / BN);
   const int grid = tiles < sm_count() ? tiles : sm_count();
   gemm_tc_kernel<BN><<<grid, kTcThreads, Cfg::kSmemBytes, st>>>(ma, mb, ep, p.M, p.N, p.K);

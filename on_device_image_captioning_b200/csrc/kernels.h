@@ -3,11 +3,13 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 
 namespace xn {
 
 typedef __nv_bfloat16 bf16;
+typedef __half f16;
 
 // ---------------------------------------------------------------- GEMM (fp32 FFMA path)
 struct GemmArgs {
@@ -24,12 +26,14 @@ struct GemmArgs {
 cudaError_t launch_gemm_f32(const GemmArgs& p, cudaStream_t st);
 
 // ---------------------------------------------------------------- GEMM (bf16 tcgen05 path)
-// C = act(A x W^T + bias) + res, A (M x K) bf16 K-contiguous, W (N x K) bf16 K-contiguous,
-// fp32 accumulation in TMEM.  Output fp32 (Cf) or bf16 (Cb), exactly one non-null.
+// C = act(A x W^T + bias) + res, A (M x K) and W (N x K) 16-bit (bf16, or fp16 when fp16 != 0),
+// K-contiguous, fp32 accumulation in TMEM.  Output fp32 (Cf) or 16-bit (Cb, same format as the
+// operands), exactly one non-null.
 struct TcGemmArgs {
-  const bf16* A; long lda;
-  const bf16* W; long ldw;
-  float* Cf; bf16* Cb; long ldc;
+  const void* A; long lda;
+  const void* W; long ldw;
+  float* Cf; void* Cb; long ldc;
+  int fp16;
   const float* bias;
   const float* res; long ldr;        // fp32 residual
   int M, N, K;
@@ -38,6 +42,7 @@ struct TcGemmArgs {
 };
 cudaError_t launch_gemm_tc(const TcGemmArgs& p, cudaStream_t st);
 bool tc_gemm_supported(int M, int N, int K);
+void set_tc_debug(int v);   // timing experiments (see TcEpilogue::dbg)
 
 // ---------------------------------------------------------------- normalisation / embedding
 template <typename OutT>
@@ -60,6 +65,10 @@ cudaError_t launch_cast(const float* x, T* y, long n, cudaStream_t st);
 template <typename T>
 cudaError_t launch_window_attention(const T* qkv, const float* bias_table, T* out, int B, int H, int C,
                                     int heads, int shift, cudaStream_t st);
+// tensor-core (mma.sync) variant for the 16-bit modes
+template <typename T>
+cudaError_t launch_window_attention_mma(const T* qkv, const float* bias_table, T* out, int B, int H, int C,
+                                        int heads, int shift, cudaStream_t st);
 
 // ---------------------------------------------------------------- static expansion (encoder)
 // z (B, E, N) raw scores (already / sqrt(d)).  Produces forward weights (B,E,N) normalised over

@@ -1,0 +1,205 @@
+// Swin (shifted-)window attention on tensor cores for the 16-bit modes (bf16 / fp16 operands,
+// fp32 accumulate and fp32 softmax).  Same contract as window_attn.cu: reads only Q/K/V, writes
+// only O; shift, partition, relative-position bias and the shift mask are index arithmetic
+// (reference models/swin_transformer_mod.py:222-269, 397-437).
+//
+// One CTA per (window, head), 9 warps; warp w owns query rows [16w, 16w+16).  Per warp:
+//   S = Q K^T        16 x 144 x 32   -> 18 n8-tiles of mma.sync.m16n8k16, 72 fp32 accumulators
+//   S = S*scale + bias(yi-yj, xi-xj) + mask ;  row softmax in registers (quad shuffles)
+//   O = P V          16 x 32 x 144   -> P re-used straight from the accumulator layout as the
+//                                        A fragment (tiles 2j, 2j+1 -> k-step j), V^T via ldmatrix.trans
+// The 144x144 score matrix never leaves the register file.  (tcgen05 is not used here: the
+// 144-row window does not map onto 128-row UMMA tiles without 44% padding, and the kernel is
+// bounded by its Q/K/V reads, not by the MMA rate.)
+#include <cuda_fp16.h>
+#include "kernels.h"
+#include "common.cuh"
+
+namespace xn {
+
+constexpr int kMmaThreads = 288;
+constexpr int kRowPad = 40;                      // 16-bit elements per smem row (80 B): conflict-free ldmatrix
+
+template <typename T> struct Mma16;
+template <> struct Mma16<bf16> {
+  static __device__ __forceinline__ void mma(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+  }
+  static __device__ __forceinline__ uint32_t pack(float lo, float hi) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&v);
+  }
+};
+template <> struct Mma16<__half> {
+  static __device__ __forceinline__ void mma(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+  }
+  static __device__ __forceinline__ uint32_t pack(float lo, float hi) {
+    __half2 v = __floats2half2_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&v);
+  }
+};
+
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_trans(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kMmaThreads, 2) window_attention_mma_kernel(const T* __restrict__ qkv,
+                                                                              const float* __restrict__ bias_table,
+                                                                              T* __restrict__ out, int H, int C, int heads,
+                                                                              int shift) {
+  __shared__ __align__(16) T Qs[kWinTok * kRowPad];
+  __shared__ __align__(16) T Ks[kWinTok * kRowPad];
+  __shared__ __align__(16) T Vs[kWinTok * kRowPad];
+  __shared__ float bt[532];
+  __shared__ int tok[kWinTok];
+  __shared__ unsigned char lab[kWinTok];
+
+  const int nWs = H / kWin;
+  const int wid = blockIdx.x, head = blockIdx.y;
+  const int b = wid / (nWs * nWs), wrem = wid % (nWs * nWs);
+  const int wy = wrem / nWs, wx = wrem % nWs;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+  if (tid < kWinTok) {
+    const int ty = tid / kWin, tx = tid % kWin;
+    const int hs = wy * kWin + ty, ws_ = wx * kWin + tx;
+    const int h = (hs + shift) % H, w = (ws_ + shift) % H;
+    tok[tid] = (b * H + h) * H + w;
+    int lh = 0, lw = 0;
+    if (shift > 0) {
+      lh = hs < H - kWin ? 0 : (hs < H - shift ? 1 : 2);
+      lw = ws_ < H - kWin ? 0 : (ws_ < H - shift ? 1 : 2);
+    }
+    lab[tid] = (unsigned char)(lh * 3 + lw);
+  }
+  for (int i = tid; i < 529; i += kMmaThreads) bt[i] = bias_table[(long)i * heads + head];
+  __syncthreads();
+
+  // stage Q, K, V: 144 tokens x 3 x 64 bytes, 16-byte chunks
+  for (int i = tid; i < kWinTok * 12; i += kMmaThreads) {
+    const int t = i / 12, r = i % 12, which = r >> 2, ch = r & 3;
+    const uint4 v = *reinterpret_cast<const uint4*>(qkv + (long)tok[t] * 3 * C + which * C + head * kHeadDim + ch * 8);
+    T* dst = (which == 0 ? Qs : (which == 1 ? Ks : Vs)) + t * kRowPad + ch * 8;
+    *reinterpret_cast<uint4*>(dst) = v;
+  }
+  __syncthreads();
+
+  const uint32_t q_base = (uint32_t)__cvta_generic_to_shared(Qs);
+  const uint32_t k_base = (uint32_t)__cvta_generic_to_shared(Ks);
+  const uint32_t v_base = (uint32_t)__cvta_generic_to_shared(Vs);
+  const int m0 = warp * 16;
+
+  // A fragments of Q for the two k16 steps (d 0-15, 16-31)
+  uint32_t qa[2][4];
+  {
+    const int row = m0 + (lane & 7) + ((lane >> 3) & 1) * 8;
+    const int col = (lane >> 4) * 8;
+    ldsm_x4(qa[0], q_base + (row * kRowPad + col) * 2);
+    ldsm_x4(qa[1], q_base + (row * kRowPad + col + 16) * 2);
+  }
+  float s[18][4];
+#pragma unroll
+  for (int nt = 0; nt < 18; ++nt) {
+    s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+    uint32_t kb[4];     // {b0,b1} for d 0-15 and {b0,b1} for d 16-31 of keys nt*8 .. nt*8+7
+    const int krow = nt * 8 + (lane & 7), kcol = (lane >> 3) * 8;
+    ldsm_x4(kb, k_base + (krow * kRowPad + kcol) * 2);
+    Mma16<T>::mma(s[nt], qa[0], kb[0], kb[1]);
+    Mma16<T>::mma(s[nt], qa[1], kb[2], kb[3]);
+  }
+
+  // scale + relative-position bias + shift mask, then the row softmax (rows r0 = m0 + lane/4, r1 = r0 + 8)
+  const float scale = 0.17677669529663687f;
+  const int r0 = m0 + (lane >> 2), r1 = r0 + 8;
+  const int y0 = r0 / kWin, x0 = r0 % kWin, y1 = r1 / kWin, x1 = r1 % kWin;
+  const int l0 = lab[r0], l1 = lab[r1];
+  float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+  for (int nt = 0; nt < 18; ++nt) {
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int j = nt * 8 + (lane & 3) * 2 + e;
+      const int yj = j / kWin, xj = j % kWin, lj = lab[j];
+      float a = s[nt][e] * scale + bt[(y0 - yj + kWin - 1) * (2 * kWin - 1) + (x0 - xj + kWin - 1)];
+      float c = s[nt][2 + e] * scale + bt[(y1 - yj + kWin - 1) * (2 * kWin - 1) + (x1 - xj + kWin - 1)];
+      if (lj != l0) a += -100.0f;
+      if (lj != l1) c += -100.0f;
+      s[nt][e] = a; s[nt][2 + e] = c;
+      mx0 = fmaxf(mx0, a); mx1 = fmaxf(mx1, c);
+    }
+  }
+  mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+  mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+  float sum0 = 0.f, sum1 = 0.f;
+  uint32_t pa[18][2];   // packed probabilities: [nt][0] = row r0 (cols 2q,2q+1), [nt][1] = row r1
+#pragma unroll
+  for (int nt = 0; nt < 18; ++nt) {
+    const float e0 = __expf(s[nt][0] - mx0), e1 = __expf(s[nt][1] - mx0);
+    const float e2 = __expf(s[nt][2] - mx1), e3 = __expf(s[nt][3] - mx1);
+    sum0 += e0 + e1; sum1 += e2 + e3;
+    pa[nt][0] = Mma16<T>::pack(e0, e1);
+    pa[nt][1] = Mma16<T>::pack(e2, e3);
+  }
+  sum0 += __shfl_xor_sync(0xffffffffu, sum0, 1); sum0 += __shfl_xor_sync(0xffffffffu, sum0, 2);
+  sum1 += __shfl_xor_sync(0xffffffffu, sum1, 1); sum1 += __shfl_xor_sync(0xffffffffu, sum1, 2);
+
+  // O = P V : 9 k16 steps over the keys, 4 n8 tiles over head_dim
+  float o[4][4];
+#pragma unroll
+  for (int n = 0; n < 4; ++n) o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.f;
+#pragma unroll
+  for (int ks = 0; ks < 9; ++ks) {
+    uint32_t a[4] = {pa[2 * ks][0], pa[2 * ks][1], pa[2 * ks + 1][0], pa[2 * ks + 1][1]};
+    const int vrow = ks * 16 + ((lane >> 3) & 1) * 8 + (lane & 7);
+    const int vcol = (lane >> 4) * 8;
+    uint32_t vb0[4], vb1[4];                     // d 0-15 and d 16-31
+    ldsm_x4_trans(vb0, v_base + (vrow * kRowPad + vcol) * 2);
+    ldsm_x4_trans(vb1, v_base + (vrow * kRowPad + vcol + 16) * 2);
+    Mma16<T>::mma(o[0], a, vb0[0], vb0[1]);
+    Mma16<T>::mma(o[1], a, vb0[2], vb0[3]);
+    Mma16<T>::mma(o[2], a, vb1[0], vb1[1]);
+    Mma16<T>::mma(o[3], a, vb1[2], vb1[3]);
+  }
+  const float inv0 = 1.0f / sum0, inv1 = 1.0f / sum1;
+
+  // stage the warp's 16 x 32 output tile in its own (now dead) Q rows, then 64-byte row stores
+  __syncwarp();
+  uint32_t* qw = reinterpret_cast<uint32_t*>(Qs);
+#pragma unroll
+  for (int n = 0; n < 4; ++n) {
+    const int col = n * 8 + (lane & 3) * 2;
+    qw[(r0 * kRowPad + col) >> 1] = Mma16<T>::pack(o[n][0] * inv0, o[n][1] * inv0);
+    qw[(r1 * kRowPad + col) >> 1] = Mma16<T>::pack(o[n][2] * inv1, o[n][3] * inv1);
+  }
+  __syncwarp();
+#pragma unroll
+  for (int it = 0; it < 2; ++it) {
+    const int row = m0 + it * 8 + (lane >> 2), ch = lane & 3;
+    const uint4 v = *reinterpret_cast<const uint4*>(Qs + row * kRowPad + ch * 8);
+    *reinterpret_cast<uint4*>(out + (long)tok[row] * C + head * kHeadDim + ch * 8) = v;
+  }
+}
+
+template <typename T>
+cudaError_t launch_window_attention_mma(const T* qkv, const float* bias_table, T* out, int B, int H, int C, int heads,
+                                        int shift, cudaStream_t st) {
+  if (H % kWin || C != heads * kHeadDim) return cudaErrorInvalidValue;
+  const int nW = (H / kWin) * (H / kWin);
+  window_attention_mma_kernel<T><<<dim3(B * nW, heads), kMmaThreads, 0, st>>>(qkv, bias_table, out, H, C, heads, shift);
+  return cudaGetLastError();
+}
+template cudaError_t launch_window_attention_mma<bf16>(const bf16*, const float*, bf16*, int, int, int, int, int, cudaStream_t);
+template cudaError_t launch_window_attention_mma<__half>(const __half*, const float*, __half*, int, int, int, int, int, cudaStream_t);
+
+}  // namespace xn

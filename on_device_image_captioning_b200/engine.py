@@ -9,7 +9,7 @@ import torch
 from . import _lib
 from .config import XNConfig
 
-PRECISIONS = {"fp32": _lib.XN_PREC_FP32, "bf16": _lib.XN_PREC_BF16}
+PRECISIONS = {"fp32": _lib.XN_PREC_FP32, "bf16": _lib.XN_PREC_BF16, "fp16": _lib.XN_PREC_FP16}
 
 
 def _cfg_struct(cfg: XNConfig) -> _lib.XnConfig:

@@ -93,10 +93,11 @@ def check_linear_fp32() -> List[Triple]:
     return out
 
 
-def check_linear_bf16() -> List[Triple]:
-    """tcgen05 GEMM vs an fp64 product of the same bf16-rounded operands (so only the fp32
+def check_linear_bf16(precision: str = "bf16") -> List[Triple]:
+    """tcgen05 GEMM vs an fp64 product of the same 16-bit-rounded operands (so only the fp32
     accumulation order differs)."""
     e = bare_engine()
+    rnd = (lambda t: t.bfloat16()) if precision == "bf16" else (lambda t: t.half())
     out = []
     g = torch.Generator().manual_seed(2)
     for (M, N, K, act, res) in [(128, 128, 64, 0, False), (128, 256, 128, 0, False), (300, 192, 192, 0, True),
@@ -106,14 +107,14 @@ def check_linear_bf16() -> List[Triple]:
         w = torch.randn(N, K, generator=g) / math.sqrt(K)
         b = torch.randn(N, generator=g)
         r = torch.randn(M, N, generator=g) if res else None
-        y = e.op_linear(x, w, b, r, act, "bf16")
-        xb, wb = x.bfloat16().double(), w.bfloat16().double()
+        y = e.op_linear(x, w, b, r, act, precision)
+        xb, wb = rnd(x).double(), rnd(w).double()
         ref = torch.nn.functional.linear(xb, wb, b.double())
         if act == 1:
             ref = torch.nn.functional.gelu(ref)
         if res:
             ref = ref + r.double()
-        out.append((f"linear_bf16_tcgen05[{M}x{N}x{K} act{act} res{int(res)}] rel-max", rel_max(y, ref), 2e-5))
+        out.append((f"linear_{precision}_tcgen05[{M}x{N}x{K} act{act} res{int(res)}] rel-max", rel_max(y, ref), 2e-5))
     return out
 
 
@@ -127,7 +128,7 @@ def check_window_attention(precision: str = "fp32") -> List[Triple]:
         table = torch.randn(529, heads, generator=g) * 0.5
         y = e.op_window_attention(qkv, table, B, H, C, heads, shift, precision)
         # oracle: same math through the reference-shaped partition/roll path
-        q_in = qkv.bfloat16().float() if precision == "bf16" else qkv
+        q_in = qkv.bfloat16().float() if precision == "bf16" else (qkv.half().float() if precision == "fp16" else qkv)
         x = q_in.reshape(B, H, H, 3 * C)
         if shift:
             x = torch.roll(x, shifts=(-shift, -shift), dims=(1, 2))
@@ -148,7 +149,7 @@ def check_window_attention(precision: str = "fp32") -> List[Triple]:
         if shift:
             o = torch.roll(o, shifts=(shift, shift), dims=(1, 2))
         ref = o.reshape(B * H * H, C)
-        tol = 1e-5 if precision == "fp32" else 1e-2
+        tol = {"fp32": 1e-5, "bf16": 1e-2, "fp16": 2e-3}[precision]
         out.append((f"window_attention_{precision}[B{B} H{H} heads{heads} shift{shift}] rel-max", rel_max(y, ref), tol))
     return out
 

@@ -20,12 +20,13 @@ def test_linear_fp32():
     _assert(G.check_linear_fp32())
 
 
-def test_linear_bf16_tcgen05():
+@pytest.mark.parametrize("precision", ["bf16", "fp16"])
+def test_linear_16bit_tcgen05(precision):
     import gpu_checks as G
-    _assert(G.check_linear_bf16())
+    _assert(G.check_linear_bf16(precision))
 
 
-@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("precision", ["fp32", "bf16", "fp16"])
 def test_window_attention(precision):
     import gpu_checks as G
     _assert(G.check_window_attention(precision))

@@ -1,0 +1,41 @@
+"""Event-timed tcgen05 GEMM micro-benchmark over the Swin shapes, with the kernel's debug switches
+(1 = no epilogue global traffic, 2 = no MMA issue, 4 = no TMA loads) to attribute time."""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch
+from on_device_image_captioning_b200 import config as C
+from on_device_image_captioning_b200.engine import Engine
+
+def main():
+    e = Engine(C.swin_tiny_test(), 0)
+    Bc = int(sys.argv[1]) if len(sys.argv) > 1 else 32
+    modes = [int(m) for m in sys.argv[2].split(",")] if len(sys.argv) > 2 else [0, 1, 2, 4, 7]
+    shapes = [("s1.qkv", Bc * 9216, 576, 192, 0, False), ("s1.proj", Bc * 9216, 192, 192, 0, True),
+              ("s1.fc1", Bc * 9216, 768, 192, 1, False), ("s1.fc2", Bc * 9216, 192, 768, 0, True),
+              ("s2.qkv", Bc * 2304, 1152, 384, 0, False), ("s2.fc1", Bc * 2304, 1536, 384, 1, False),
+              ("s3.qkv", Bc * 576, 2304, 768, 0, False), ("s3.proj", Bc * 576, 768, 768, 0, True),
+              ("s3.fc1", Bc * 576, 3072, 768, 1, False), ("s3.fc2", Bc * 576, 768, 3072, 0, True),
+              ("s4.fc1", Bc * 144, 6144, 1536, 1, False), ("big", 8192, 8192, 8192, 0, False)]
+    g = torch.Generator().manual_seed(0)
+    for name, M, N, K, act, res in shapes:
+        x = torch.randn(M, K, generator=g).cuda()
+        w = (torch.randn(N, K, generator=g) / K ** 0.5).cuda()
+        b = torch.randn(N, generator=g).cuda()
+        r = torch.randn(M, N, generator=g).cuda() if res else None
+        line = f"{name:8s} M={M:7d} N={N:5d} K={K:5d} act{act} res{int(res)}:"
+        for mode in modes:
+            e.set_option("tc_debug", mode)
+            e.op_linear(x, w, b, r, act, "bf16")
+            e.set_option("profile", 1)
+            for _ in range(3):
+                e.op_linear(x, w, b, r, act, "bf16")
+            ms, fl, n = e.profile_read()
+            e.set_option("profile", 0)
+            line += f"  dbg{mode}: {ms / n * 1e3:8.1f} us {fl / ms / 1e9:7.1f} TF/s |"
+        e.set_option("tc_debug", 0)
+        print(line, flush=True)
+        del x, w, b, r
+
+if __name__ == "__main__":
+    main()

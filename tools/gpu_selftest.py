@@ -16,7 +16,9 @@ def main():
     quick = "--quick" in sys.argv
     only = [a for a in sys.argv[1:] if not a.startswith("--")]
     jobs = [("layernorm", G.check_layernorm), ("linear_fp32", G.check_linear_fp32), ("linear_bf16", G.check_linear_bf16),
+            ("linear_fp16", lambda: G.check_linear_bf16("fp16")),
             ("wattn_fp32", lambda: G.check_window_attention("fp32")), ("wattn_bf16", lambda: G.check_window_attention("bf16")),
+            ("wattn_fp16", lambda: G.check_window_attention("fp16")),
             ("logsoftmax_topk", G.check_logsoftmax_topk)]
     cases = ["tiny_e2e_peaky", "tiny_e2e_xavier", "feat_peaky_b5", "feat_xavier_b1"] + ([] if quick else ["full_e2e_xavier", "full_e2e_peaky"])
     for c in cases:
@@ -24,6 +26,7 @@ def main():
                  (f"beam:{c}", lambda c=c: G.check_beam(c, "fp32"))]
     for c in ["tiny_e2e_peaky"] + ([] if quick else ["full_e2e_xavier"]):
         jobs += [(f"enc_bf16:{c}", lambda c=c: G.check_encoder(c, "bf16")), (f"beam_bf16:{c}", lambda c=c: G.check_beam(c, "bf16"))]
+        jobs += [(f"enc_fp16:{c}", lambda c=c: G.check_encoder(c, "fp16")), (f"beam_fp16:{c}", lambda c=c: G.check_beam(c, "fp16"))]
     results, nbad = [], 0
     for name, fn in jobs:
         if only and not any(o in name for o in only):
