@@ -16,7 +16,7 @@ namespace xn {
 
 constexpr int GBK = 16;
 
-template <int BM, int BN, int RM, int RN, bool WKN>
+template <int BM, int BN, int RM, int RN, bool WKN, bool DIV>
 __global__ void __launch_bounds__(256) gemm_f32_kernel(GemmArgs p) {
   constexpr int TXN = BN / (4 * RN);        // threads along N
   static_assert((BM / (4 * RM)) * TXN == 256, "tile/thread mismatch");
@@ -135,7 +135,7 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(GemmArgs p) {
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         float x = acc[i][r * 4 + e];
-        if (p.div != 0.f) x = x / p.div;
+        if (DIV) x = x / p.div;     // compile-time: a runtime guard lets the compiler speculate x/0 (slow path)
         if (p.bias && gn + e < p.N) x += p.bias[gn + e];
         if (p.act == 1) x = gelu_erf(x);
         else if (p.act == 2) x = fmaxf(x, 0.f);
@@ -164,14 +164,15 @@ cudaError_t launch_gemm_f32(const GemmArgs& p, cudaStream_t st) {
   if ((p.K & 3) || (p.lda & 3) || (p.ldw & 3)) return cudaErrorInvalidValue;
   const long big_ctas = (long)((p.M + 127) / 128) * ((p.N + 127) / 128) * p.batch;
   const bool small = big_ctas < 148 || p.M < 128 || p.N < 128;
+  const bool dv = p.div != 0.f;
   if (!small) {
     dim3 grid((p.N + 127) / 128, (p.M + 127) / 128, p.batch);
-    if (p.w_kn) gemm_f32_kernel<128, 128, 2, 2, true><<<grid, 256, 0, st>>>(p);
-    else        gemm_f32_kernel<128, 128, 2, 2, false><<<grid, 256, 0, st>>>(p);
+    if (p.w_kn) { if (dv) gemm_f32_kernel<128, 128, 2, 2, true, true><<<grid, 256, 0, st>>>(p); else gemm_f32_kernel<128, 128, 2, 2, true, false><<<grid, 256, 0, st>>>(p); }
+    else        { if (dv) gemm_f32_kernel<128, 128, 2, 2, false, true><<<grid, 256, 0, st>>>(p); else gemm_f32_kernel<128, 128, 2, 2, false, false><<<grid, 256, 0, st>>>(p); }
   } else {
     dim3 grid((p.N + 63) / 64, (p.M + 63) / 64, p.batch);
-    if (p.w_kn) gemm_f32_kernel<64, 64, 1, 1, true><<<grid, 256, 0, st>>>(p);
-    else        gemm_f32_kernel<64, 64, 1, 1, false><<<grid, 256, 0, st>>>(p);
+    if (p.w_kn) { if (dv) gemm_f32_kernel<64, 64, 1, 1, true, true><<<grid, 256, 0, st>>>(p); else gemm_f32_kernel<64, 64, 1, 1, true, false><<<grid, 256, 0, st>>>(p); }
+    else        { if (dv) gemm_f32_kernel<64, 64, 1, 1, false, true><<<grid, 256, 0, st>>>(p); else gemm_f32_kernel<64, 64, 1, 1, false, false><<<grid, 256, 0, st>>>(p); }
   }
   return cudaGetLastError();
 }

@@ -45,8 +45,7 @@ struct TcEpilogue {
   int fp16;
   const float* bias;
   const float* res; long ldr;
-  float div;
-  int act;
+  float scale;  // accumulator multiplier (1 / div); a multiply, never a speculated division
   int dbg;     // timing experiments only: 1 = skip the epilogue's global traffic, 2 = skip MMA issue, 4 = skip TMA loads
 };
 
@@ -122,7 +121,8 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N, int ab_fmt) {
   return (1u << 4) | ((uint32_t)ab_fmt << 7) | ((uint32_t)ab_fmt << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
-template <int BN>
+// OUT: 0 = fp32 output, 1 = 16-bit output (bf16, or fp16 when ep.fp16).  ACT: 0 none, 1 GELU(erf), 2 ReLU.
+template <int BN, int OUT, int ACT>
 __global__ void __launch_bounds__(kTcThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, TcEpilogue ep,
                int M, int N, int K) {
@@ -268,15 +268,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
           const float rr[4] = {rres[i].x, rres[i].y, rres[i].z, rres[i].w};
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            float t = x[e];
-            if (ep.div != 0.f) t = t / ep.div;
-            t += bb[e];
-            if (ep.act == 1) t = gelu_erf(t);
-            else if (ep.act == 2) t = fmaxf(t, 0.f);
+            float t = fmaf(x[e], ep.scale, bb[e]);
+            if (ACT == 1) t = gelu_erf(t);
+            else if (ACT == 2) t = fmaxf(t, 0.f);
             x[e] = t + rr[e];
           }
+          if ((ep.dbg & 8) && x[0] != 1234567.f) continue;   // timing experiment: all the math, no global stores
           if (row < M && col < N) {
-            if (ep.Cf) {
+            if (OUT == 0) {
               float* dst = ep.Cf + (long)row * ep.ldc + col;
               if (vec_ok) *reinterpret_cast<float4*>(dst) = make_float4(x[0], x[1], x[2], x[3]);
               else for (int e = 0; e < 4; ++e) if (col + e < N) dst[e] = x[e];
@@ -360,22 +359,36 @@ static int sm_count() {
   return n;
 }
 
-template <int BN>
+template <int BN, int OUT, int ACT>
 static cudaError_t launch_tc(const TcGemmArgs& p, cudaStream_t st) {
   using Cfg = TcCfg<BN>;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, OUT, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmemBytes);
     if (e != cudaSuccess) return e;
     configured = true;
   }
   CUtensorMap ma, mb;
   if (!make_map(&ma, p.A, p.M, p.K, p.lda, kBM, p.fp16) || !make_map(&mb, p.W, p.N, p.K, p.ldw, BN, p.fp16)) return cudaErrorInvalidValue;
-  TcEpilogue ep{p.Cf, p.Cb, p.ldc, p.fp16, p.bias, p.res, p.ldr, p.div, p.act, g_tc_debug};
+  TcEpilogue ep{p.Cf, p.Cb, p.ldc, p.fp16, p.bias, p.res, p.ldr, p.div != 0.f ? 1.0f / p.div : 1.0f, g_tc_debug};
   const int tiles = ((p.M + kBM - 1) / kBM) * ((p.N + BN - 1) / BN);
   const int grid = tiles < sm_count() ? tiles : sm_count();
-  gemm_tc_kernel<BN><<<grid, kTcThreads, Cfg::kSmemBytes, st>>>(ma, mb, ep, p.M, p.N, p.K);
+  gemm_tc_kernel<BN, OUT, ACT><<<grid, kTcThreads, Cfg::kSmemBytes, st>>>(ma, mb, ep, p.M, p.N, p.K);
   return cudaGetLastError();
+}
+
+template <int BN>
+static cudaError_t launch_tc_bn(const TcGemmArgs& p, cudaStream_t st) {
+  const int out = p.Cf ? 0 : 1;
+  switch (out * 3 + p.act) {
+    case 0: return launch_tc<BN, 0, 0>(p, st);
+    case 1: return launch_tc<BN, 0, 1>(p, st);
+    case 2: return launch_tc<BN, 0, 2>(p, st);
+    case 3: return launch_tc<BN, 1, 0>(p, st);
+    case 4: return launch_tc<BN, 1, 1>(p, st);
+    case 5: return launch_tc<BN, 1, 2>(p, st);
+  }
+  return cudaErrorInvalidValue;
 }
 
 cudaError_t launch_gemm_tc(const TcGemmArgs& p, cudaStream_t st) {
@@ -390,9 +403,10 @@ cudaError_t launch_gemm_tc(const TcGemmArgs& p, cudaStream_t st) {
     const long waste = (long)((p.N + bn - 1) / bn) * bn - p.N;
     if (best_waste < 0 || waste < best_waste) { best = bn; best_waste = waste; }
   }
-  if (best == 256) return launch_tc<256>(p, st);
-  if (best == 192) return launch_tc<192>(p, st);
-  return launch_tc<128>(p, st);
+  if (p.act < 0 || p.act > 2) return cudaErrorInvalidValue;
+  if (best == 256) return launch_tc_bn<256>(p, st);
+  if (best == 192) return launch_tc_bn<192>(p, st);
+  return launch_tc_bn<128>(p, st);
 }
 
 }  // namespace xn

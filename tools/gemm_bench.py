@@ -17,8 +17,11 @@ def main():
               ("s3.qkv", Bc * 576, 2304, 768, 0, False), ("s3.proj", Bc * 576, 768, 768, 0, True),
               ("s3.fc1", Bc * 576, 3072, 768, 1, False), ("s3.fc2", Bc * 576, 768, 3072, 0, True),
               ("s4.fc1", Bc * 144, 6144, 1536, 1, False), ("big", 8192, 8192, 8192, 0, False)]
+    only = sys.argv[3].split(",") if len(sys.argv) > 3 else None
     g = torch.Generator().manual_seed(0)
     for name, M, N, K, act, res in shapes:
+        if only and name not in only:
+            continue
         x = torch.randn(M, K, generator=g).cuda()
         w = (torch.randn(N, K, generator=g) / K ** 0.5).cuda()
         b = torch.randn(N, generator=g).cuda()
