@@ -10,6 +10,7 @@
 #include <vector>
 #include <unordered_map>
 #include <algorithm>
+#include <type_traits>
 
 #include "../../include/xnv2_b200.h"
 #include "kernels.h"
@@ -81,6 +82,19 @@ struct xn_handle {
   Arena ws;
   int64_t launches = 0;
   int64_t swin_chunk = 32, enc_chunk = 64;
+  // CUDA-graph cache of the decode loop (one entry per distinct call shape / buffer set)
+  struct DecodeGraph {
+    const void* enc; int B, beam, L, how_many, sos, eos; const char* ws_base; size_t ws_cap;
+    cudaGraphExec_t exec; int64_t launches; int seen;
+  };
+  std::vector<DecodeGraph> graphs;
+  int64_t use_graph = 1;
+  cudaStream_t gstream = nullptr;      // graphs are captured/replayed here (the caller's stream may be the legacy
+  cudaEvent_t g_in = nullptr, g_out = nullptr;   // default stream, which cannot be captured); ordered with events
+  void drop_graphs() {
+    for (auto& g : graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
+    graphs.clear();
+  }
   // optional per-launch event timing of the tcgen05 GEMMs (bench.py roofline leg)
   int64_t profile = 0;
   std::vector<cudaEvent_t> prof_ev;
@@ -124,6 +138,7 @@ int ensure_ws(xn_handle* h, size_t bytes, cudaStream_t st) {
     if (h->ws.base) {
       CU(cudaStreamSynchronize(st));
       CU(cudaDeviceSynchronize());
+      h->drop_graphs();
       CU(cudaFree(h->ws.base));
       h->ws.base = nullptr;
       h->ws.cap = 0;
@@ -292,15 +307,22 @@ size_t enc_ws_bytes(const xn_config& c, int Bc) {
   f += M * c.ff;                    // ff hidden
   f += (size_t)Bc * c.n_exp_groups * 2 * N;   // group sums
   f += M * d;                       // pre-norm output
-  return f * 4 + Bc * 4 + 32 * 256;
+  f += M * std::max<size_t>(d, c.feat_dim) + M * d * c.n_enc;   // 16-bit staging (counted at 4 B)
+  return f * 4 + Bc * 4 + 40 * 256;
 }
 
+// T = float: everything fp32 (parity mode).  T = bf16/f16: the plain Linear layers (input_linear, the fused
+// key|class_a|class_b|selector projection, FF, reduce group) run on tcgen05 with 16-bit operands; the per-image
+// expansion contractions (z, class, out) and all normalisations stay fp32.
+template <typename T>
 int enc_body_chunk(xn_handle* h, const float* feats, int Bc, const int* n_valid_dev, float* out, cudaStream_t st) {
+  constexpr bool kF32 = std::is_same<T, float>::value;
   const xn_config& c = h->cfg;
   const int N = c.enc_len, d = c.d_model, E = h->n_exp_total, M = Bc * N, ne = c.n_enc;
   float* x0 = h->ws.get<float>((size_t)M * d);
   float* xcat = h->ws.get<float>((size_t)M * d * ne);
-  float* xn = h->ws.get<float>((size_t)M * d);
+  T* xn = h->ws.get<T>((size_t)M * std::max(d, c.feat_dim));
+  T* xcat16 = kF32 ? nullptr : h->ws.get<T>((size_t)M * d * ne);
   float* kabs = h->ws.get<float>((size_t)M * 4 * d);
   float* z = h->ws.get<float>((size_t)Bc * E * N);
   float* afw = h->ws.get<float>((size_t)Bc * E * N);
@@ -311,20 +333,31 @@ int enc_body_chunk(xn_handle* h, const float* feats, int Bc, const int* n_valid_
   float* CB = h->ws.get<float>((size_t)Bc * E * d);
   float* oA = h->ws.get<float>((size_t)M * d);
   float* oB = h->ws.get<float>((size_t)M * d);
-  float* hid = h->ws.get<float>((size_t)M * c.ff);
+  T* hid = h->ws.get<T>((size_t)M * c.ff);
   float* gs = h->ws.get<float>((size_t)Bc * c.n_exp_groups * 2 * N);
   float* pre = h->ws.get<float>((size_t)M * d);
   WS_CHECK();
   const long ldc = (long)d * ne;
+  const int fp16 = std::is_same<T, f16>::value;
+  // y(fp32) = x W^T + b (+res)
+  auto lin_out32 = [&](const float* x32, const T* x16, long ldx, const LinW& w, const float* res, long ldr, float* y, long ldy) -> int {
+    if (kF32) return lin_f32(h, x32, ldx, w, res, ldr, y, ldy, M, 0, st);
+    return lin_tc(h, x16, ldx, w, res, ldr, y, nullptr, ldy, M, 0, fp16, st);
+  };
 
-  if (int r = lin_f32(h, feats, c.feat_dim, h->input_linear, nullptr, 0, x0, d, M, 0, st)) return r;
+  if (kF32) {
+    if (int r = lin_out32(feats, nullptr, c.feat_dim, h->input_linear, nullptr, 0, x0, d)) return r;
+  } else {
+    KL(1, launch_cast<T>(feats, xn, (long)M * c.feat_dim, st));
+    if (int r = lin_out32(nullptr, xn, c.feat_dim, h->input_linear, nullptr, 0, x0, d)) return r;
+  }
   for (int l = 0; l < ne; ++l) {
     const EncLayerW& W = h->enc[l];
     const float* xin = l == 0 ? x0 : xcat + (size_t)(l - 1) * d;
     const long ldi = l == 0 ? d : ldc;
     float* xout = xcat + (size_t)l * d;
-    KL(1, launch_layernorm<float>(xin, ldi, W.n1g, W.n1b, xn, d, M, d, st));
-    if (int r = lin_f32(h, xn, d, W.kabs, nullptr, 0, kabs, 4 * d, M, 0, st)) return r;
+    KL(1, launch_layernorm<T>(xin, ldi, W.n1g, W.n1b, xn, d, M, d, st));
+    if (int r = lin_out32(reinterpret_cast<const float*>(xn), xn, d, W.kabs, nullptr, 0, kabs, 4 * d)) return r;
     GemmArgs g{};
     // z[b] = Q (E x d) . key[b]^T / sqrt(d)            reference layers.py:52
     g.A = W.qexp; g.lda = d; g.sA = 0;
@@ -354,11 +387,21 @@ int enc_body_chunk(xn_handle* h, const float* feats, int Bc, const int* n_valid_
       KL(1, launch_gemm_f32(q, st));
     }
     KL(1, launch_selector_mix(xin, ldi, kabs + 3 * (size_t)d, 4 * d, oA, oB, d, xout, ldc, M, d, st));
-    KL(1, launch_layernorm<float>(xout, ldc, W.n2g, W.n2b, xn, d, M, d, st));
-    if (int r = lin_f32(h, xn, d, W.ff1, nullptr, 0, hid, c.ff, M, 2, st)) return r;
-    if (int r = lin_f32(h, hid, c.ff, W.ff2, xout, ldc, xout, ldc, M, 0, st)) return r;
+    KL(1, launch_layernorm<T>(xout, ldc, W.n2g, W.n2b, xn, d, M, d, st));
+    if (kF32) {
+      if (int r = lin_f32(h, reinterpret_cast<const float*>(xn), d, W.ff1, nullptr, 0, reinterpret_cast<float*>(hid), c.ff, M, 2, st)) return r;
+      if (int r = lin_f32(h, reinterpret_cast<const float*>(hid), c.ff, W.ff2, xout, ldc, xout, ldc, M, 0, st)) return r;
+    } else {
+      if (int r = lin_tc(h, xn, d, W.ff1, nullptr, 0, nullptr, hid, c.ff, M, 2, fp16, st)) return r;
+      if (int r = lin_tc(h, hid, c.ff, W.ff2, xout, ldc, xout, nullptr, ldc, M, 0, fp16, st)) return r;
+    }
   }
-  if (int r = lin_f32(h, xcat, ldc, h->enc_reduce, xcat + (size_t)(ne - 1) * d, ldc, pre, d, M, 0, st)) return r;
+  if (kF32) {
+    if (int r = lin_f32(h, xcat, ldc, h->enc_reduce, xcat + (size_t)(ne - 1) * d, ldc, pre, d, M, 0, st)) return r;
+  } else {
+    KL(1, launch_cast<T>(xcat, xcat16, (long)M * ldc, st));
+    if (int r = lin_tc(h, xcat16, ldc, h->enc_reduce, xcat + (size_t)(ne - 1) * d, ldc, pre, nullptr, d, M, 0, fp16, st)) return r;
+  }
   KL(1, launch_layernorm<float>(pre, d, h->enc_ng, h->enc_nb, out, d, M, d, st));
   return 0;
 }
@@ -381,9 +424,12 @@ int enc_body(xn_handle* h, const float* feats, int B, const int32_t* enc_pads_ho
         CU(cudaStreamSynchronize(st));   // v is a stack-lifetime host buffer
       }
     }
-    if (int r = enc_body_chunk(h, feats + (size_t)b0 * c.enc_len * c.feat_dim, Bc, nv,
-                               out + (size_t)b0 * c.enc_len * c.d_model, st))
-      return r;
+    const float* fin = feats + (size_t)b0 * c.enc_len * c.feat_dim;
+    float* fout = out + (size_t)b0 * c.enc_len * c.d_model;
+    const int r = h->precision == XN_PREC_BF16   ? enc_body_chunk<bf16>(h, fin, Bc, nv, fout, st)
+                  : h->precision == XN_PREC_FP16 ? enc_body_chunk<f16>(h, fin, Bc, nv, fout, st)
+                                                 : enc_body_chunk<float>(h, fin, Bc, nv, fout, st);
+    if (r) return r;
   }
   return 0;
 }
@@ -495,31 +541,91 @@ int beam_from_enc(xn_handle* h, const float* enc_out, int B, const int32_t* enc_
     if (any) if (int r = upload_ints(h, v, &nv, st)) return r;
   }
   WS_CHECK();
-  // cross K/V of all decoder layers, once per image (shared by the beams)
-  if (int r = lin_f32(h, enc_out, d, h->kv_all, nullptr, 0, D.kv, h->kv_all.N, B * c.enc_len, 0, st)) return r;
-  KL(1, launch_beam_init(bb, B, beam, L, sos, st));
-  int src = 0;
-  // step 0: every beam row decodes [SOS]
-  D.s.anc = bb.anc[0];
-  if (int r = dec_step(h, D, 0, nullptr, bb.tokens[0], L, beam, nv, nullptr, logits, c.vocab, st)) return r;
-  KL(1, launch_logsoftmax_topk(logits, c.vocab, R, c.vocab, beam, topv, topi, nullptr, 0, 0, st));
-  KL(1, launch_beam_first(bb, topv, topi, B, beam, L, st));
-  int t_final = 2;
-  for (int t = 2; t < L; ++t) {
-    D.s.anc = bb.anc[src];
-    if (int r = dec_step(h, D, t - 1, nullptr, bb.tokens[src], L, beam, nv, nullptr, logits, c.vocab, st)) return r;
+  // results land in arena buffers (stable addresses -> graph-capturable), then are copied to the caller
+  int32_t* r_tok = h->ws.get<int32_t>((size_t)B * how_many * L);
+  int32_t* r_len = h->ws.get<int32_t>((size_t)B * how_many);
+  float* r_lp = h->ws.get<float>((size_t)B * how_many * L);
+  WS_CHECK();
+  cudaStream_t user_st = st;
+  auto run = [&]() -> int {
+    // cross K/V of all decoder layers, once per image (shared by the beams)
+    if (int r = lin_f32(h, enc_out, d, h->kv_all, nullptr, 0, D.kv, h->kv_all.N, B * c.enc_len, 0, st)) return r;
+    KL(1, launch_beam_init(bb, B, beam, L, sos, st));
+    int src = 0;
+    // step 0: every beam row decodes [SOS]
+    D.s.anc = bb.anc[0];
+    if (int r = dec_step(h, D, 0, nullptr, bb.tokens[0], L, beam, nv, nullptr, logits, c.vocab, st)) return r;
     KL(1, launch_logsoftmax_topk(logits, c.vocab, R, c.vocab, beam, topv, topi, nullptr, 0, 0, st));
-    KL(1, launch_beam_step(bb, src, topv, topi, B, beam, L, t, eos, st));
-    src ^= 1;
-    t_final = t + 1;
+    KL(1, launch_beam_first(bb, topv, topi, B, beam, L, st));
+    int t_final = 2;
+    for (int t = 2; t < L; ++t) {
+      D.s.anc = bb.anc[src];
+      if (int r = dec_step(h, D, t - 1, nullptr, bb.tokens[src], L, beam, nv, nullptr, logits, c.vocab, st)) return r;
+      KL(1, launch_logsoftmax_topk(logits, c.vocab, R, c.vocab, beam, topv, topi, nullptr, 0, 0, st));
+      KL(1, launch_beam_step(bb, src, topv, topi, B, beam, L, t, eos, st));
+      src ^= 1;
+      t_final = t + 1;
+    }
+    KL(1, launch_beam_finalize(bb, src, B, beam, L, t_final, how_many, r_tok, r_len, r_lp, st));
+    return 0;
+  };
+  bool done = false;
+  if (h->use_graph && !nv && !h->profile) {
+    if (!h->gstream) {
+      CU(cudaStreamCreateWithFlags(&h->gstream, cudaStreamNonBlocking));
+      CU(cudaEventCreateWithFlags(&h->g_in, cudaEventDisableTiming));
+      CU(cudaEventCreateWithFlags(&h->g_out, cudaEventDisableTiming));
+    }
+    xn_handle::DecodeGraph* g = nullptr;
+    for (auto& e : h->graphs)
+      if (e.enc == enc_out && e.B == B && e.beam == beam && e.L == L && e.how_many == how_many && e.sos == sos && e.eos == eos &&
+          e.ws_base == h->ws.base && e.ws_cap == h->ws.cap) { g = &e; break; }
+    if (g) {          // hand over from the caller's stream to the graph stream
+      CU(cudaEventRecord(h->g_in, user_st));
+      CU(cudaStreamWaitEvent(h->gstream, h->g_in, 0));
+      st = h->gstream;
+    }
+    if (g && g->exec) {
+      CU(cudaGraphLaunch(g->exec, st));
+      h->launches += g->launches;
+      done = true;
+    } else if (g) {
+      // second identical call: capture the whole decode loop once, then replay it from now on
+      const int64_t l0 = h->launches;
+      CU(cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed));
+      const int rr = run();
+      cudaGraph_t graph = nullptr;
+      cudaError_t ce = cudaStreamEndCapture(st, &graph);
+      if (rr) { if (graph) cudaGraphDestroy(graph); return rr; }
+      if (ce != cudaSuccess) return h->fail(XN_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(ce));
+      g->launches = h->launches - l0;
+      h->launches = l0;
+      cudaError_t ie = cudaGraphInstantiate(&g->exec, graph, 0);
+      cudaGraphDestroy(graph);
+      if (ie != cudaSuccess) { g->exec = nullptr; return h->fail(XN_ERR_CUDA, "graph instantiate failed: %s", cudaGetErrorString(ie)); }
+      CU(cudaGraphLaunch(g->exec, st));
+      h->launches += g->launches;
+      done = true;
+    } else {
+      if (h->graphs.size() > 16) h->drop_graphs();
+      h->graphs.push_back({enc_out, B, beam, L, how_many, sos, eos, h->ws.base, h->ws.cap, nullptr, 0, 1});
+    }
   }
-  KL(1, launch_beam_finalize(bb, src, B, beam, L, t_final, how_many, out_tokens, out_len, out_lp, st));
+  if (done) {         // and back
+    CU(cudaEventRecord(h->g_out, h->gstream));
+    CU(cudaStreamWaitEvent(user_st, h->g_out, 0));
+    st = user_st;
+  }
+  if (!done) if (int r = run()) return r;
+  CU(cudaMemcpyAsync(out_tokens, r_tok, (size_t)B * how_many * L * 4, cudaMemcpyDeviceToDevice, st));
+  CU(cudaMemcpyAsync(out_len, r_len, (size_t)B * how_many * 4, cudaMemcpyDeviceToDevice, st));
+  CU(cudaMemcpyAsync(out_lp, r_lp, (size_t)B * how_many * L * 4, cudaMemcpyDeviceToDevice, st));
   return 0;
 }
 
 size_t beam_ws_bytes(const xn_config& c, int B, int beam, int L) {
   const int R = B * beam;
-  return dec_ws_bytes(c, R, L, B, true) + (size_t)R * beam * 8 + (size_t)R * L * 24 + R * 8 + B * 4 + 64 * 256;
+  return dec_ws_bytes(c, R, L, B, true) + (size_t)R * beam * 8 + (size_t)R * L * 24 + R * 8 + B * 4 + (size_t)R * L * 8 + R * 4 + 64 * 256;
 }
 
 const float* rawp(xn_handle* h, const std::string& k, std::vector<int64_t> shape, int* rc) {
@@ -593,6 +699,8 @@ int xn_destroy(xn_handle* h) {
   if (h->ws.base) cudaFree(h->ws.base);
   if (h->io_in) cudaFree(h->io_in);
   if (h->io_out) cudaFree(h->io_out);
+  h->drop_graphs();
+  if (h->gstream) { cudaStreamDestroy(h->gstream); cudaEventDestroy(h->g_in); cudaEventDestroy(h->g_out); }
   for (cudaEvent_t e : h->prof_ev) cudaEventDestroy(e);
   delete h;
   return XN_OK;
@@ -624,6 +732,7 @@ int xn_finalize_weights(xn_handle* h, int precision) {
   if (precision != XN_PREC_FP32 && precision != XN_PREC_BF16 && precision != XN_PREC_FP16) return h->fail(XN_ERR_ARG, "bad precision");
   cudaSetDevice(h->device);
   const xn_config& c = h->cfg;
+  h->drop_graphs();
   for (void* p : h->owned) cudaFree(p);
   h->owned.clear();
   h->stages.clear(); h->enc.clear(); h->dec.clear();
@@ -725,6 +834,7 @@ int xn_finalize_weights(xn_handle* h, int precision) {
     W.ff1 = lin(q + "ff.linear_1", ff, d); W.ff2 = lin(q + "ff.linear_2", d, ff);
     if (rc) return rc;
     if (concat(parts, W.kabs)) return XN_ERR_CUDA;
+    if (precision != XN_PREC_FP32 && (to_bf16(W.kabs) || to_bf16(W.ff1) || to_bf16(W.ff2))) return XN_ERR_CUDA;
     h->enc.push_back(W);
   }
   std::vector<LinW> kvparts;
@@ -750,6 +860,7 @@ int xn_finalize_weights(xn_handle* h, int precision) {
   h->input_linear = lin("input_linear", d, c.feat_dim);
   h->vocab = lin("vocab_linear", V, d);
   h->enc_reduce = lin("enc_reduce_group", d, d * c.n_enc);
+  if (precision != XN_PREC_FP32 && (to_bf16(h->input_linear) || to_bf16(h->enc_reduce))) return XN_ERR_CUDA;
   h->dec_reduce = lin("dec_reduce_group", d, d * c.n_dec);
   h->enc_ng = P("enc_reduce_norm.weight", {d}); h->enc_nb = P("enc_reduce_norm.bias", {d});
   h->dec_ng = P("dec_reduce_norm.weight", {d}); h->dec_nb = P("dec_reduce_norm.bias", {d});
@@ -910,6 +1021,7 @@ int64_t xn_workspace_bytes(const xn_handle* h) { return h ? (int64_t)h->ws.cap :
 int xn_set_option(xn_handle* h, const char* name, int64_t value) {
   if (!h || !name) return XN_ERR_ARG;
   std::string n(name);
+  if (n == "use_graph") { h->use_graph = value; h->drop_graphs(); return XN_OK; }
   if (n == "tc_debug") { set_tc_debug((int)value); return XN_OK; }
   if (n == "profile") { h->profile = value; h->prof_used = 0; h->prof_flops.clear(); }
   else if (n == "swin_chunk") h->swin_chunk = std::max<int64_t>(1, value);

@@ -17,11 +17,12 @@ namespace xn {
 constexpr int GBK = 16;
 
 template <int BM, int BN, int RM, int RN, bool WKN, bool DIV>
-__global__ void __launch_bounds__(256) gemm_f32_kernel(GemmArgs p) {
+__global__ void __launch_bounds__((BM / (4 * RM)) * (BN / (4 * RN))) gemm_f32_kernel(GemmArgs p) {
   constexpr int TXN = BN / (4 * RN);        // threads along N
-  static_assert((BM / (4 * RM)) * TXN == 256, "tile/thread mismatch");
-  constexpr int LA = BM * GBK / 4 / 256;    // float4 loads per thread for the A tile
-  constexpr int LB = BN * GBK / 4 / 256;
+  constexpr int NT = (BM / (4 * RM)) * TXN; // threads per CTA (64 for the 32x32 tile, otherwise a full 8 warps)
+  constexpr int LA = BM * GBK / 4 / NT;     // float4 loads per thread for the A tile
+  constexpr int LB = BN * GBK / 4 / NT;
+  static_assert(LA >= 1 && LB >= 1, "tile too small for the thread count");
   __shared__ __align__(16) float As[2][GBK][BM + 4];
   __shared__ __align__(16) float Bs[2][GBK][BN + 4];
 
@@ -42,14 +43,14 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(GemmArgs p) {
   auto load_tiles = [&](int k0) {
 #pragma unroll
     for (int i = 0; i < LA; ++i) {
-      const int f = tid + i * 256, row = f >> 2, kq = (f & 3) * 4;
+      const int f = tid + i * NT, row = f >> 2, kq = (f & 3) * 4;
       const int gm = m0 + row, gk = k0 + kq;
       ra[i] = (gm < p.M && gk < p.K) ? *reinterpret_cast<const float4*>(A + (long)gm * p.lda + gk)
                                      : make_float4(0.f, 0.f, 0.f, 0.f);
     }
 #pragma unroll
     for (int i = 0; i < LB; ++i) {
-      const int f = tid + i * 256;
+      const int f = tid + i * NT;
       if (!WKN) {
         const int row = f >> 2, kq = (f & 3) * 4;
         const int gn = n0 + row, gk = k0 + kq;
@@ -73,13 +74,13 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(GemmArgs p) {
   auto store_tiles = [&](int buf) {
 #pragma unroll
     for (int i = 0; i < LA; ++i) {
-      const int f = tid + i * 256, row = f >> 2, kq = (f & 3) * 4;
+      const int f = tid + i * NT, row = f >> 2, kq = (f & 3) * 4;
       As[buf][kq + 0][row] = ra[i].x; As[buf][kq + 1][row] = ra[i].y;
       As[buf][kq + 2][row] = ra[i].z; As[buf][kq + 3][row] = ra[i].w;
     }
 #pragma unroll
     for (int i = 0; i < LB; ++i) {
-      const int f = tid + i * 256;
+      const int f = tid + i * NT;
       if (!WKN) {
         const int row = f >> 2, kq = (f & 3) * 4;
         Bs[buf][kq + 0][row] = rb[i].x; Bs[buf][kq + 1][row] = rb[i].y;
@@ -165,6 +166,14 @@ cudaError_t launch_gemm_f32(const GemmArgs& p, cudaStream_t st) {
   const long big_ctas = (long)((p.M + 127) / 128) * ((p.N + 127) / 128) * p.batch;
   const bool small = big_ctas < 148 || p.M < 128 || p.N < 128;
   const bool dv = p.div != 0.f;
+  // skinny problems (decoder steps: M = rows = images x beam): 32x32 tiles of 64 threads keep >= 100 CTAs in flight
+  const long mid_ctas = (long)((p.M + 63) / 64) * ((p.N + 63) / 64) * p.batch;
+  if (small && mid_ctas < 2 * 148 && !p.w_kn) {
+    dim3 grid((p.N + 31) / 32, (p.M + 31) / 32, p.batch);
+    if (dv) gemm_f32_kernel<32, 32, 1, 1, false, true><<<grid, 64, 0, st>>>(p);
+    else    gemm_f32_kernel<32, 32, 1, 1, false, false><<<grid, 64, 0, st>>>(p);
+    return cudaGetLastError();
+  }
   if (!small) {
     dim3 grid((p.N + 127) / 128, (p.M + 127) / 128, p.batch);
     if (p.w_kn) { if (dv) gemm_f32_kernel<128, 128, 2, 2, true, true><<<grid, 256, 0, st>>>(p); else gemm_f32_kernel<128, 128, 2, 2, true, false><<<grid, 256, 0, st>>>(p); }
