@@ -215,25 +215,31 @@ cudaError_t launch_dyn_exp_step(const DecState& s, int layer, int p, const float
 // K/V of the encoder output are projected once per image and shared by its beams; one CTA
 // per (image, head) stages that head's K and V in shared memory and serves all rows of the image.
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(160) cross_attn_step_kernel(const float* __restrict__ q, long ldq,
-                                                              const float* __restrict__ kv, long ldkv, int k_off,
-                                                              int v_off, float* __restrict__ out, long ldo,
+template <typename KvT, typename OutT>
+__global__ void __launch_bounds__(256) cross_attn_step_kernel(const float* __restrict__ q, long ldq,
+                                                              const KvT* __restrict__ kv, long ldkv, int k_off,
+                                                              int v_off, OutT* __restrict__ out, long ldo,
                                                               int rows_per_image, int n, int dk,
                                                               const int* __restrict__ n_valid,
                                                               const int* __restrict__ row_len, int p) {
   extern __shared__ float sm[];
   const int b = blockIdx.x, h = blockIdx.y, tid = threadIdx.x;
-  const int ks = dk + 1;
-  float* Ks = sm;                 // [n][dk+1]
-  float* Vs = Ks + n * ks;        // [n][dk+1]
-  float* qs = Vs + n * ks;        // [dk]
+  const int kt = n + 1;           // K is staged transposed [dk][n+1]: the score loop reads it conflict-free
+  float* Kt = sm;                 // [dk][n+1]
+  float* Vs = Kt + dk * kt;       // [n][dk]
+  float* qs = Vs + n * dk;        // [dk]
   float* pr = qs + dk;            // [n]
   float* red = pr + n;            // [32]
-  for (int i = tid; i < n * dk; i += blockDim.x) {
-    const int j = i / dk, c = i % dk;
-    const float* row = kv + ((long)b * n + j) * ldkv + h * dk + c;
-    Ks[j * ks + c] = row[k_off];
-    Vs[j * ks + c] = row[v_off];
+  float* po = red + 32;           // [blockDim.x] partial outputs
+  const int dk4 = dk >> 2;
+  for (int i = tid; i < n * dk4; i += blockDim.x) {
+    const int j = i / dk4, c = (i % dk4) * 4;
+    const KvT* row = kv + ((long)b * n + j) * ldkv + h * dk + c;
+    float kk[4], vv[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { kk[e] = to_f32<KvT>(row[k_off + e]); vv[e] = to_f32<KvT>(row[v_off + e]); }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { Kt[(c + e) * kt + j] = kk[e]; Vs[j * dk + c + e] = vv[e]; }
   }
   const int nv = n_valid ? n_valid[b] : n;
   const float sq = sqrtf((float)dk);
@@ -246,7 +252,7 @@ __global__ void __launch_bounds__(160) cross_attn_step_kernel(const float* __res
     float lmax = -INFINITY;
     for (int j = tid; j < n; j += blockDim.x) {
       float a = 0.f;
-      for (int c = 0; c < dk; ++c) a = fmaf(qs[c], Ks[j * ks + c], a);
+      for (int c = 0; c < dk; ++c) a = fmaf(qs[c], Kt[c * kt + j], a);
       a = a / sq;
       if (row_padded || j >= nv) a = kCrossFill;
       pr[j] = a;
@@ -263,30 +269,42 @@ __global__ void __launch_bounds__(160) cross_attn_step_kernel(const float* __res
     __syncthreads();
     for (int j = tid; j < n; j += blockDim.x) pr[j] = pr[j] / sum;
     __syncthreads();
-    for (int c = tid; c < dk; c += blockDim.x) {
+    // out[c] = sum_j p_j V[j][c]: blockDim/dk partial sums per output column, combined in a fixed order
+    const int parts = blockDim.x / dk;
+    const int c = tid % dk, part = tid / dk;
+    if (part < parts) {
       float o = 0.f;
-      for (int j = 0; j < n; ++j) o = fmaf(pr[j], Vs[j * ks + c], o);
-      out[(long)r * ldo + h * dk + c] = o;
+      for (int j = part; j < n; j += parts) o = fmaf(pr[j], Vs[j * dk + c], o);
+      po[part * dk + c] = o;
+    }
+    __syncthreads();
+    if (tid < dk) {
+      float o = 0.f;
+      for (int pp = 0; pp < parts; ++pp) o += po[pp * dk + tid];
+      out[(long)r * ldo + h * dk + tid] = from_f32<OutT>(o);
     }
   }
 }
 
-cudaError_t launch_cross_attn_step(const float* q, long ldq, const float* kv, long ldkv, int k_off, int v_off,
-                                   float* out, long ldo, int R, int rows_per_image, int n_keys, int heads, int dk,
+template <typename KvT, typename OutT>
+cudaError_t launch_cross_attn_step(const float* q, long ldq, const KvT* kv, long ldkv, int k_off, int v_off,
+                                   OutT* out, long ldo, int R, int rows_per_image, int n_keys, int heads, int dk,
                                    const int* n_valid, const int* row_len, int p, cudaStream_t st) {
-  if (R % rows_per_image) return cudaErrorInvalidValue;
-  const size_t smem = ((size_t)2 * n_keys * (dk + 1) + dk + n_keys + 32) * sizeof(float);
+  if (R % rows_per_image || (dk & 3) || dk > 256 || (256 % dk)) return cudaErrorInvalidValue;
+  const size_t smem = ((size_t)dk * (n_keys + 1) + (size_t)n_keys * dk + dk + n_keys + 32 + 256) * sizeof(float);
   static size_t configured = 0;
   if (smem > 48 * 1024 && smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(cross_attn_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(cross_attn_step_kernel<KvT, OutT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     configured = smem;
   }
-  cross_attn_step_kernel<<<dim3(R / rows_per_image, heads), 160, smem, st>>>(q, ldq, kv, ldkv, k_off, v_off, out, ldo,
-                                                                            rows_per_image, n_keys, dk, n_valid,
-                                                                            row_len, p);
+  cross_attn_step_kernel<KvT, OutT><<<dim3(R / rows_per_image, heads), 256, smem, st>>>(
+      q, ldq, kv, ldkv, k_off, v_off, out, ldo, rows_per_image, n_keys, dk, n_valid, row_len, p);
   return cudaGetLastError();
 }
+template cudaError_t launch_cross_attn_step<float, float>(const float*, long, const float*, long, int, int, float*, long, int, int, int, int, int, const int*, const int*, int, cudaStream_t);
+template cudaError_t launch_cross_attn_step<bf16, bf16>(const float*, long, const bf16*, long, int, int, bf16*, long, int, int, int, int, int, const int*, const int*, int, cudaStream_t);
+template cudaError_t launch_cross_attn_step<f16, f16>(const float*, long, const f16*, long, int, int, f16*, long, int, int, int, int, int, const int*, const int*, int, cudaStream_t);
 
 // ------------------------------------------------------------------------------------------
 // log-softmax over the vocabulary + top-k (reference End_ExpansionNet_v2.py:204-207 and

@@ -437,7 +437,8 @@ int enc_body(xn_handle* h, const float* feats, int B, const int32_t* enc_pads_ho
 // ---- decoder --------------------------------------------------------------------------------
 struct DecBufs {
   DecState s;
-  float *x0, *ycat, *xn, *q, *att, *hid, *pre, *yn, *kv;
+  float *x0, *ycat, *q, *pre;
+  void *xn, *att, *hid, *yn, *ycat16, *kv;      // fp32 in the parity mode, 16-bit operands otherwise
   int R, P;
 };
 
@@ -447,8 +448,9 @@ size_t dec_ws_bytes(const xn_config& c, int R, int P, int n_images, bool own_log
   f += (size_t)c.n_dec * P * R * 5 * d;
   f += (size_t)c.n_dec * P * R * 2 * c.num_exp_dec * P;
   f += (size_t)c.n_dec * P * R * c.num_exp_dec;
-  f += (size_t)R * d * (6 + c.n_dec) + (size_t)R * c.ff;
+  f += (size_t)R * d * (6 + 2 * c.n_dec) + (size_t)R * c.ff;
   f += (size_t)n_images * c.enc_len * c.n_dec * 2 * d;
+  f += (size_t)n_images * c.enc_len * d;          // 16-bit copy of the encoder output
   if (own_logits) f += (size_t)R * c.vocab;
   return f * 4 + 64 * 256;
 }
@@ -464,45 +466,90 @@ int dec_alloc(xn_handle* h, DecBufs& D, int R, int P, int n_images) {
   D.s.anc = nullptr; D.s.P = P; D.s.R = R;
   D.x0 = h->ws.get<float>((size_t)R * d);
   D.ycat = h->ws.get<float>((size_t)R * d * c.n_dec);
-  D.xn = h->ws.get<float>((size_t)R * d);
   D.q = h->ws.get<float>((size_t)R * d);
+  D.pre = h->ws.get<float>((size_t)R * d);
+  D.xn = h->ws.get<float>((size_t)R * d);
   D.att = h->ws.get<float>((size_t)R * d);
   D.hid = h->ws.get<float>((size_t)R * c.ff);
-  D.pre = h->ws.get<float>((size_t)R * d);
   D.yn = h->ws.get<float>((size_t)R * d);
+  D.ycat16 = h->ws.get<float>((size_t)R * d * c.n_dec);
   D.kv = h->ws.get<float>((size_t)n_images * c.enc_len * c.n_dec * 2 * d);
   return 0;
 }
 
+// y = act(x W^T + b) + res with fp32 (parity) or tcgen05 16-bit operands; exactly one of yf / y16 is written
+template <typename T>
+int dec_lin(xn_handle* h, const T* x, long ldx, const LinW& w, const float* res, long ldr, float* yf, T* y16, long ldy,
+            int M, int act, cudaStream_t st) {
+  if (std::is_same<T, float>::value)
+    return lin_f32(h, reinterpret_cast<const float*>(x), ldx, w, res, ldr, yf ? yf : reinterpret_cast<float*>(y16), ldy, M, act, st);
+  return lin_tc(h, x, ldx, w, res, ldr, yf, yf ? nullptr : y16, ldy, M, act, std::is_same<T, f16>::value, st);
+}
+
+// cross K/V of all decoder layers, once per image (shared by the beams)
+template <typename T>
+int dec_project_kv(xn_handle* h, DecBufs& D, const float* enc_out, int n_images, cudaStream_t st) {
+  const xn_config& c = h->cfg;
+  const int d = c.d_model, M = n_images * c.enc_len;
+  if (std::is_same<T, float>::value)
+    return lin_f32(h, enc_out, d, h->kv_all, nullptr, 0, reinterpret_cast<float*>(D.kv), h->kv_all.N, M, 0, st);
+  T* e16 = h->ws.get<T>((size_t)M * d);
+  WS_CHECK();
+  KL(1, launch_cast<T>(enc_out, e16, (long)M * d, st));
+  return lin_tc(h, e16, d, h->kv_all, nullptr, 0, nullptr, D.kv, h->kv_all.N, M, 0, std::is_same<T, f16>::value, st);
+}
+
 // one decoder position for all rows -> logits (R, V) at `logits` with row stride ldl
-int dec_step(xn_handle* h, DecBufs& D, int p, const int64_t* tok64, const int* tok32, long tok_stride,
-             int rows_per_image, const int* n_valid, const int* row_len, float* logits, long ldl, cudaStream_t st) {
+template <typename T>
+int dec_step_t(xn_handle* h, DecBufs& D, int p, const int64_t* tok64, const int* tok32, long tok_stride,
+               int rows_per_image, const int* n_valid, const int* row_len, float* logits, long ldl, cudaStream_t st) {
   const xn_config& c = h->cfg;
   const int d = c.d_model, R = D.R, nd = c.n_dec;
   const long ldc = (long)d * nd, ldkv = (long)nd * 2 * d;
+  T* xn = reinterpret_cast<T*>(D.xn);
+  T* att = reinterpret_cast<T*>(D.att);
+  T* hid = reinterpret_cast<T*>(D.hid);
+  T* yn = reinterpret_cast<T*>(D.yn);
   KL(1, launch_embed(tok64, tok32, tok_stride, p, h->emb, h->pos, D.x0, d, R, d, st));
   for (int l = 0; l < nd; ++l) {
     const DecLayerW& W = h->dec[l];
     const float* xin = l == 0 ? D.x0 : D.ycat + (size_t)(l - 1) * d;
     const long ldi = l == 0 ? d : ldc;
     float* xout = D.ycat + (size_t)l * d;
-    KL(1, launch_layernorm<float>(xin, ldi, W.n1g, W.n1b, D.xn, d, R, d, st));
+    KL(1, launch_layernorm<T>(xin, ldi, W.n1g, W.n1b, xn, d, R, d, st));
     float* crow = D.s.cache + (((size_t)l * D.P + p) * R) * D.s.cw;
-    if (int r = lin_f32(h, D.xn, d, W.dyn5, nullptr, 0, crow, D.s.cw, R, 0, st)) return r;
+    if (int r = dec_lin<T>(h, xn, d, W.dyn5, nullptr, 0, crow, nullptr, D.s.cw, R, 0, st)) return r;
     KL(1, launch_dyn_exp_step(D.s, l, p, W.qexp, W.bexp, c.num_exp_dec, row_len, xin, ldi, xout, ldc, d, rows_per_image, st));
-    KL(1, launch_layernorm<float>(xout, ldc, W.n2g, W.n2b, D.xn, d, R, d, st));
-    if (int r = lin_f32(h, D.xn, d, W.wq, nullptr, 0, D.q, d, R, 0, st)) return r;
-    KL(1, launch_cross_attn_step(D.q, d, D.kv, ldkv, l * 2 * d, l * 2 * d + d, D.att, d, R, rows_per_image, c.enc_len,
-                                 c.num_heads, d / c.num_heads, n_valid, row_len, p, st));
-    if (int r = lin_f32(h, D.att, d, W.wo, xout, ldc, xout, ldc, R, 0, st)) return r;
-    KL(1, launch_layernorm<float>(xout, ldc, W.n3g, W.n3b, D.xn, d, R, d, st));
-    if (int r = lin_f32(h, D.xn, d, W.ff1, nullptr, 0, D.hid, c.ff, R, 2, st)) return r;
-    if (int r = lin_f32(h, D.hid, c.ff, W.ff2, xout, ldc, xout, ldc, R, 0, st)) return r;
+    KL(1, launch_layernorm<T>(xout, ldc, W.n2g, W.n2b, xn, d, R, d, st));
+    if (int r = dec_lin<T>(h, xn, d, W.wq, nullptr, 0, D.q, nullptr, d, R, 0, st)) return r;
+    KL(1, (launch_cross_attn_step<T, T>(D.q, d, reinterpret_cast<const T*>(D.kv), ldkv, l * 2 * d, l * 2 * d + d, att, d, R,
+                                        rows_per_image, c.enc_len, c.num_heads, d / c.num_heads, n_valid, row_len, p, st)));
+    if (int r = dec_lin<T>(h, att, d, W.wo, xout, ldc, xout, nullptr, ldc, R, 0, st)) return r;
+    KL(1, launch_layernorm<T>(xout, ldc, W.n3g, W.n3b, xn, d, R, d, st));
+    if (int r = dec_lin<T>(h, xn, d, W.ff1, nullptr, 0, nullptr, hid, c.ff, R, 2, st)) return r;
+    if (int r = dec_lin<T>(h, hid, c.ff, W.ff2, xout, ldc, xout, nullptr, ldc, R, 0, st)) return r;
   }
-  if (int r = lin_f32(h, D.ycat, ldc, h->dec_reduce, D.ycat + (size_t)(nd - 1) * d, ldc, D.pre, d, R, 0, st)) return r;
-  KL(1, launch_layernorm<float>(D.pre, d, h->dec_ng, h->dec_nb, D.yn, d, R, d, st));
-  if (int r = lin_f32(h, D.yn, d, h->vocab, nullptr, 0, logits, ldl, R, 0, st)) return r;
+  const T* ycat_in = reinterpret_cast<const T*>(D.ycat);
+  if (!std::is_same<T, float>::value) {
+    KL(1, launch_cast<T>(D.ycat, reinterpret_cast<T*>(D.ycat16), (long)R * ldc, st));
+    ycat_in = reinterpret_cast<const T*>(D.ycat16);
+  }
+  if (int r = dec_lin<T>(h, ycat_in, ldc, h->dec_reduce, D.ycat + (size_t)(nd - 1) * d, ldc, D.pre, nullptr, d, R, 0, st)) return r;
+  KL(1, launch_layernorm<T>(D.pre, d, h->dec_ng, h->dec_nb, yn, d, R, d, st));
+  if (int r = dec_lin<T>(h, yn, d, h->vocab, nullptr, 0, logits, nullptr, ldl, R, 0, st)) return r;
   return 0;
+}
+
+int dec_step(xn_handle* h, DecBufs& D, int p, const int64_t* tok64, const int* tok32, long tok_stride,
+             int rows_per_image, const int* n_valid, const int* row_len, float* logits, long ldl, cudaStream_t st) {
+  if (h->precision == XN_PREC_BF16) return dec_step_t<bf16>(h, D, p, tok64, tok32, tok_stride, rows_per_image, n_valid, row_len, logits, ldl, st);
+  if (h->precision == XN_PREC_FP16) return dec_step_t<f16>(h, D, p, tok64, tok32, tok_stride, rows_per_image, n_valid, row_len, logits, ldl, st);
+  return dec_step_t<float>(h, D, p, tok64, tok32, tok_stride, rows_per_image, n_valid, row_len, logits, ldl, st);
+}
+int dec_project(xn_handle* h, DecBufs& D, const float* enc_out, int n_images, cudaStream_t st) {
+  if (h->precision == XN_PREC_BF16) return dec_project_kv<bf16>(h, D, enc_out, n_images, st);
+  if (h->precision == XN_PREC_FP16) return dec_project_kv<f16>(h, D, enc_out, n_images, st);
+  return dec_project_kv<float>(h, D, enc_out, n_images, st);
 }
 
 int upload_ints(xn_handle* h, const std::vector<int>& v, int** dev, cudaStream_t st) {
@@ -549,7 +596,7 @@ int beam_from_enc(xn_handle* h, const float* enc_out, int B, const int32_t* enc_
   cudaStream_t user_st = st;
   auto run = [&]() -> int {
     // cross K/V of all decoder layers, once per image (shared by the beams)
-    if (int r = lin_f32(h, enc_out, d, h->kv_all, nullptr, 0, D.kv, h->kv_all.N, B * c.enc_len, 0, st)) return r;
+    if (int r = dec_project(h, D, enc_out, B, st)) return r;
     KL(1, launch_beam_init(bb, B, beam, L, sos, st));
     int src = 0;
     // step 0: every beam row decodes [SOS]
@@ -855,6 +902,7 @@ int xn_finalize_weights(xn_handle* h, int precision) {
     W.ff1 = lin(q + "ff.linear_1", ff, d); W.ff2 = lin(q + "ff.linear_2", d, ff);
     if (rc) return rc;
     if (concat(parts, W.dyn5)) return XN_ERR_CUDA;
+    if (precision != XN_PREC_FP32 && (to_bf16(W.dyn5) || to_bf16(W.wq) || to_bf16(W.wo) || to_bf16(W.ff1) || to_bf16(W.ff2))) return XN_ERR_CUDA;
     h->dec.push_back(W);
   }
   h->input_linear = lin("input_linear", d, c.feat_dim);
@@ -868,6 +916,7 @@ int xn_finalize_weights(xn_handle* h, int precision) {
   h->pos = P("pos_encoder.weight", {c.max_seq_len, d});
   if (rc) return rc;
   if (concat(kvparts, h->kv_all)) return XN_ERR_CUDA;
+  if (precision != XN_PREC_FP32 && (to_bf16(h->kv_all) || to_bf16(h->vocab) || to_bf16(h->dec_reduce))) return XN_ERR_CUDA;
   CU(cudaDeviceSynchronize());
   h->precision = precision;
   return XN_OK;
@@ -933,7 +982,7 @@ int xn_forward_dec(xn_handle* h, const float* cross, int R, const int32_t* enc_p
     for (int i = 0; i < R; ++i) { v[i] = t - dec_pads_host[i]; any |= dec_pads_host[i] != 0; }
     if (any) if (int r = upload_ints(h, v, &rl, st)) return r;
   }
-  if (int r = lin_f32(h, cross, c.d_model, h->kv_all, nullptr, 0, D.kv, h->kv_all.N, R * c.enc_len, 0, st)) return r;
+  if (int r = dec_project(h, D, cross, R, st)) return r;
   const long ldl = (long)t * c.vocab;
   for (int p = 0; p < t; ++p) {
     float* lg = out + (size_t)p * c.vocab;

@@ -97,8 +97,9 @@ cudaError_t launch_dyn_exp_step(const DecState& s, int layer, int p, const float
                                 int n_exp, const int* row_len, const float* x_in, long ldxi, float* x_out,
                                 long ldxo, int d, int beam, cudaStream_t st);
 // cross attention of one query position per row against per-image K/V (shared by the beams)
-cudaError_t launch_cross_attn_step(const float* q, long ldq, const float* kv, long ldkv, int k_off, int v_off,
-                                   float* out, long ldo, int R, int rows_per_image, int n_keys, int heads, int dk,
+template <typename KvT, typename OutT>
+cudaError_t launch_cross_attn_step(const float* q, long ldq, const KvT* kv, long ldkv, int k_off, int v_off,
+                                   OutT* out, long ldo, int R, int rows_per_image, int n_keys, int heads, int dk,
                                    const int* n_valid, const int* row_len, int p, cudaStream_t st);
 cudaError_t launch_logsoftmax_topk(const float* logits, long ld, int rows, int V, int k, float* top_val,
                                    int* top_idx, float* logprob, long ldlp, int write_mode, cudaStream_t st);

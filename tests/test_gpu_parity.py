@@ -58,7 +58,21 @@ def test_beam_search_fp32_bit_exact_captions(name):
     _assert(G.check_beam(name, "fp32"))
 
 
+@pytest.mark.parametrize("precision", ["fp16", "bf16"])
 @pytest.mark.parametrize("name", ["tiny_e2e_peaky", "full_e2e_xavier", "full_e2e_peaky"])
-def test_encoder_bf16(name):
+def test_encoder_16bit(name, precision):
     import gpu_checks as G
-    _assert(G.check_encoder(name, "bf16"))
+    _assert(G.check_encoder(name, precision))
+
+
+@pytest.mark.parametrize("precision", ["fp16", "bf16"])
+@pytest.mark.parametrize("name", ["tiny_e2e_peaky", "feat_peaky_b5", "full_e2e_peaky"])
+def test_decoder_16bit(name, precision):
+    import gpu_checks as G
+    _assert(G.check_decoder(name, precision))
+
+
+@pytest.mark.parametrize("name", ["tiny_e2e_peaky", "feat_peaky_b5"])
+def test_beam_search_fp16_runs(name):
+    import gpu_checks as G
+    _assert(G.check_beam(name, "fp16"))

@@ -26,7 +26,10 @@ def main():
                  (f"beam:{c}", lambda c=c: G.check_beam(c, "fp32"))]
     for c in ["tiny_e2e_peaky"] + ([] if quick else ["full_e2e_xavier"]):
         jobs += [(f"enc_bf16:{c}", lambda c=c: G.check_encoder(c, "bf16")), (f"beam_bf16:{c}", lambda c=c: G.check_beam(c, "bf16"))]
-        jobs += [(f"enc_fp16:{c}", lambda c=c: G.check_encoder(c, "fp16")), (f"beam_fp16:{c}", lambda c=c: G.check_beam(c, "fp16"))]
+        jobs += [(f"enc_fp16:{c}", lambda c=c: G.check_encoder(c, "fp16")), (f"dec_fp16:{c}", lambda c=c: G.check_decoder(c, "fp16")),
+                 (f"dec_bf16:{c}", lambda c=c: G.check_decoder(c, "bf16")), (f"beam_fp16:{c}", lambda c=c: G.check_beam(c, "fp16"))]
+    jobs += [("dec_fp16:feat_peaky_b5", lambda: G.check_decoder("feat_peaky_b5", "fp16")),
+             ("beam_fp16:feat_peaky_b5", lambda: G.check_beam("feat_peaky_b5", "fp16"))]
     results, nbad = [], 0
     for name, fn in jobs:
         if only and not any(o in name for o in only):
