@@ -83,7 +83,7 @@ class _CaptioningBase(nn.Module):
         super().__init__()
         self.cfg = cfg
         self.rank = rank
-        self.precision = precision or os.environ.get("XNV2_PRECISION", "bf16")
+        self.precision = precision or os.environ.get("XNV2_PRECISION", "fp16")
         self._engine: Optional[Engine] = None
         self._engine_key = None
         self.trained_steps = 0

@@ -76,3 +76,60 @@ def test_decoder_16bit(name, precision):
 def test_beam_search_fp16_runs(name):
     import gpu_checks as G
     _assert(G.check_beam(name, "fp16"))
+
+
+def _shim_model(cfg, sd, precision):
+    import torch
+    from argparse import Namespace
+    from on_device_image_captioning_b200 import End_ExpansionNet_v2, ExpansionNet_v2
+    words = [f"w{i}" for i in range(cfg.vocab)]
+    w2i = {w: i for i, w in enumerate(words)}
+    da = Namespace(enc=0.0, dec=0.0, enc_input=0.0, dec_input=0.0, other=0.0)
+    if cfg.has_swin:
+        m = End_ExpansionNet_v2(
+            swin_img_size=cfg.img_size, swin_patch_size=cfg.patch_size, swin_in_chans=cfg.in_chans, swin_embed_dim=cfg.embed_dim,
+            swin_depths=cfg.depths, swin_num_heads=cfg.swin_heads, swin_window_size=cfg.window_size, swin_mlp_ratio=cfg.mlp_ratio,
+            swin_qkv_bias=True, swin_qk_scale=None, swin_drop_rate=0.0, swin_attn_drop_rate=0.0, swin_drop_path_rate=0.0,
+            swin_norm_layer=torch.nn.LayerNorm, swin_ape=False, swin_patch_norm=True, swin_use_checkpoint=False,
+            final_swin_dim=cfg.feat_dim, d_model=cfg.d_model, N_enc=cfg.n_enc, N_dec=cfg.n_dec, ff=cfg.ff, num_heads=cfg.num_heads,
+            num_exp_enc_list=cfg.num_exp_enc_list, num_exp_dec=cfg.num_exp_dec, output_word2idx=w2i, output_idx2word=words,
+            max_seq_len=cfg.max_seq_len, drop_args=da, rank=0, precision=precision)
+    else:
+        m = ExpansionNet_v2(d_model=cfg.d_model, N_enc=cfg.n_enc, N_dec=cfg.n_dec, ff=cfg.ff, num_heads=cfg.num_heads,
+                            num_exp_enc_list=cfg.num_exp_enc_list, num_exp_dec=cfg.num_exp_dec, output_word2idx=w2i,
+                            output_idx2word=words, max_seq_len=cfg.max_seq_len, drop_args=da, img_feature_dim=cfg.feat_dim,
+                            rank=0, precision=precision)
+    m.load_state_dict(sd)
+    return m.to("cuda:0").eval()
+
+
+@pytest.mark.parametrize("name", ["tiny_e2e_peaky", "feat_peaky_b5"])
+def test_drop_in_classes_both_call_styles(name):
+    """The reference's two call styles (demo.py:124 upstream style; quantization.py:133 Captioner style) and the
+    teacher-forced forward (test.py:119) through the shim classes, against the reference's golden outputs."""
+    import numpy as np
+    import torch
+    from conftest import golden_setup
+    from on_device_image_captioning_b200 import E2E_ExpansionNet_Captioner
+    g, cfg, sd, x, pads = golden_setup(name)
+    meta = g["meta"]
+    m = _shim_model(cfg, sd, "fp32")
+    kw = dict(beam_size=meta["beam"], beam_max_seq_len=meta["max_len"], sample_or_max="max", how_many_outputs=meta["how_many"],
+              sos_idx=meta["sos"], eos_idx=meta["eos"])
+    with torch.no_grad():
+        pred, lp = m(enc_x=x.cuda(), enc_x_num_pads=pads, mode="beam_search", **kw)
+        cap = E2E_ExpansionNet_Captioner(kw, model=m, rank=0)
+        pred2, lp2 = cap(x.cuda(), enc_x_num_pads=pads, mode="beam_search")
+        tok = torch.from_numpy(g["dec_tokens"])
+        logits = m(enc_x=x.cuda(), dec_x=tok.cuda(), enc_x_num_pads=pads, dec_x_num_pads=g["dec_pads"].tolist(),
+                   apply_log_softmax=False)
+    assert pred == pred2
+    for b in range(meta["B"]):
+        for j in range(meta["how_many"]):
+            n = int(g["beam_len"][b, j])
+            assert pred[b][j] == g["beam_tokens"][b, j, :n].tolist()
+    assert lp.shape == tuple(g["beam_logprobs"].shape)
+    np.testing.assert_allclose(lp.cpu().numpy(), g["beam_logprobs"], rtol=0, atol=3e-4)
+    from conftest import sub
+    err = np.abs(sub(logits.cpu()).numpy() - g["dec_logits_sub"]).max()
+    assert err < 5e-5, err
