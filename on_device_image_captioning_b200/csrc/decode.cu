@@ -215,6 +215,22 @@ cudaError_t launch_dyn_exp_step(const DecState& s, int layer, int p, const float
 // K/V of the encoder output are projected once per image and shared by its beams; one CTA
 // per (image, head) stages that head's K and V in shared memory and serves all rows of the image.
 // ------------------------------------------------------------------------------------------
+template <typename T> __device__ __forceinline__ void load4(const T* p, float (&o)[4]);
+template <> __device__ __forceinline__ void load4<float>(const float* p, float (&o)[4]) {
+  const float4 v = *reinterpret_cast<const float4*>(p);
+  o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
+}
+template <> __device__ __forceinline__ void load4<bf16>(const bf16* p, float (&o)[4]) {
+  const uint2 u = *reinterpret_cast<const uint2*>(p);
+  const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&u.x), b = *reinterpret_cast<const __nv_bfloat162*>(&u.y);
+  o[0] = __bfloat162float(a.x); o[1] = __bfloat162float(a.y); o[2] = __bfloat162float(b.x); o[3] = __bfloat162float(b.y);
+}
+template <> __device__ __forceinline__ void load4<f16>(const f16* p, float (&o)[4]) {
+  const uint2 u = *reinterpret_cast<const uint2*>(p);
+  const __half2 a = *reinterpret_cast<const __half2*>(&u.x), b = *reinterpret_cast<const __half2*>(&u.y);
+  o[0] = __half2float(a.x); o[1] = __half2float(a.y); o[2] = __half2float(b.x); o[3] = __half2float(b.y);
+}
+
 template <typename KvT, typename OutT>
 __global__ void __launch_bounds__(256) cross_attn_step_kernel(const float* __restrict__ q, long ldq,
                                                               const KvT* __restrict__ kv, long ldkv, int k_off,
@@ -236,8 +252,8 @@ __global__ void __launch_bounds__(256) cross_attn_step_kernel(const float* __res
     const int j = i / dk4, c = (i % dk4) * 4;
     const KvT* row = kv + ((long)b * n + j) * ldkv + h * dk + c;
     float kk[4], vv[4];
-#pragma unroll
-    for (int e = 0; e < 4; ++e) { kk[e] = to_f32<KvT>(row[k_off + e]); vv[e] = to_f32<KvT>(row[v_off + e]); }
+    load4<KvT>(row + k_off, kk);       // one 8- or 16-byte load per operand (offsets are multiples of 4 elements)
+    load4<KvT>(row + v_off, vv);
 #pragma unroll
     for (int e = 0; e < 4; ++e) { Kt[(c + e) * kt + j] = kk[e]; Vs[j * dk + c + e] = vv[e]; }
   }

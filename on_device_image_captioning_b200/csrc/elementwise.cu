@@ -122,56 +122,71 @@ template cudaError_t launch_merge_layernorm<f16>(const float*, const float*, con
 // One CTA per (image, patch row): the Cin*P input rows of that patch row are staged in smem
 // (coalesced), the (E x Cin*P*P) filter bank is staged transposed, one warp per patch.
 // ------------------------------------------------------------------------------------------
+constexpr int kPeRows = 4;     // patch rows per CTA (amortises staging the filter bank)
+
 __global__ void __launch_bounds__(256) patch_embed_kernel(const float* __restrict__ img, const float* __restrict__ w,
                                                           const float* __restrict__ bias, const float* __restrict__ g,
                                                           const float* __restrict__ be, float* __restrict__ out,
                                                           int Cin, int S, int P, int E) {
   extern __shared__ float sm[];
   const int G = S / P, K = Cin * P * P;
-  float* slab = sm;                       // [Cin*P][S]
-  float* wt = slab + Cin * P * S;         // [K][E]
-  const int b = blockIdx.x / G, py = blockIdx.x % G;
-  for (int i = threadIdx.x; i < Cin * P * S; i += blockDim.x) {
-    const int r = i / S, xcol = i % S, c = r / P, dy = r % P;
-    slab[i] = img[(((long)b * Cin + c) * S + (py * P + dy)) * S + xcol];
-  }
+  float* slab = sm;                       // [Cin*P][S]   one patch row of input pixels
+  float* wt = slab + Cin * P * S;         // [K][E]       filter bank, transposed
+  const int groups = (G + kPeRows - 1) / kPeRows;
+  const int b = blockIdx.x / groups, py0 = (blockIdx.x % groups) * kPeRows;
+  // w is (E, Cin, P, P) = [e][k]; smem writes are contiguous in e (conflict-free), the strided reads hit L2
   for (int i = threadIdx.x; i < K * E; i += blockDim.x) {
-    const int e = i / K, k = i % K;      // w is (E, Cin, P, P) -> k = c*P*P + dy*P + dx
-    wt[k * E + e] = w[i];
+    const int k = i / E, e = i % E;
+    wt[i] = w[e * K + k];
   }
-  __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
   const int EP = E / 32;                  // channels per lane (E % 32 == 0, E <= 256)
-  for (int px = warp; px < G; px += nw) {
-    float acc[8];
+  float gam[8], bet[8], bia[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = (j < EP) ? bias[lane + 32 * j] : 0.f;
-    for (int k = 0; k < K; ++k) {
-      const int c = k / (P * P), r = k % (P * P), dy = r / P, dx = r % P;
-      const float v = slab[(c * P + dy) * S + px * P + dx];
+  for (int j = 0; j < 8; ++j) {
+    const int e = lane + 32 * j;
+    gam[j] = (j < EP) ? g[e] : 0.f; bet[j] = (j < EP) ? be[e] : 0.f; bia[j] = (j < EP) ? bias[e] : 0.f;
+  }
+  for (int pr = 0; pr < kPeRows && py0 + pr < G; ++pr) {
+    const int py = py0 + pr;
+    __syncthreads();
+    for (int i = threadIdx.x; i < Cin * P * (S / 4); i += blockDim.x) {
+      const int r = i / (S / 4), x4 = (i % (S / 4)) * 4, c = r / P, dy = r % P;
+      *reinterpret_cast<float4*>(&slab[r * S + x4]) =
+          *reinterpret_cast<const float4*>(&img[(((long)b * Cin + c) * S + (py * P + dy)) * S + x4]);
+    }
+    __syncthreads();
+    for (int px = warp; px < G; px += nw) {
+      float acc[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = bia[j];
+      for (int k = 0; k < K; ++k) {
+        const int c = k / (P * P), r = k % (P * P), dy = r / P, dx = r % P;
+        const float v = slab[(c * P + dy) * S + px * P + dx];
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (j < EP) acc[j] = fmaf(v, wt[k * E + lane + 32 * j], acc[j]);
+      }
+      float s = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) if (j < EP) s += acc[j];
+      const float mean = warp_sum(s) / (float)E;
+      float q = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) if (j < EP) { const float d = acc[j] - mean; q += d * d; }
+      const float rstd = 1.0f / sqrtf(warp_sum(q) / (float)E + kLnEps);
+      float* o = out + (((long)b * G + py) * G + px) * E;
 #pragma unroll
       for (int j = 0; j < 8; ++j)
-        if (j < EP) acc[j] = fmaf(v, wt[k * E + lane + 32 * j], acc[j]);
+        if (j < EP) o[lane + 32 * j] = (acc[j] - mean) * rstd * gam[j] + bet[j];
     }
-    float s = 0.f;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) if (j < EP) s += acc[j];
-    const float mean = warp_sum(s) / (float)E;
-    float q = 0.f;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) if (j < EP) { const float d = acc[j] - mean; q += d * d; }
-    const float rstd = 1.0f / sqrtf(warp_sum(q) / (float)E + kLnEps);
-    float* o = out + (((long)b * G + py) * G + px) * E;
-#pragma unroll
-    for (int j = 0; j < 8; ++j)
-      if (j < EP) { const int e = lane + 32 * j; o[e] = (acc[j] - mean) * rstd * g[e] + be[e]; }
   }
 }
 
 cudaError_t launch_patch_embed(const float* img, const float* w, const float* b, const float* gamma,
                                const float* beta, float* out, int B, int Cin, int S, int P, int E,
                                cudaStream_t st) {
-  if (E % 32 || E > 256 || S % P) return cudaErrorInvalidValue;
+  if (E % 32 || E > 256 || S % P || S % 4) return cudaErrorInvalidValue;
   const size_t smem = ((size_t)Cin * P * S + (size_t)Cin * P * P * E) * sizeof(float);
   static size_t configured = 0;
   if (smem > configured) {
@@ -179,7 +194,8 @@ cudaError_t launch_patch_embed(const float* img, const float* w, const float* b,
     if (e != cudaSuccess) return e;
     configured = smem;
   }
-  patch_embed_kernel<<<B * (S / P), 256, smem, st>>>(img, w, b, gamma, beta, out, Cin, S, P, E);
+  const int G = S / P, groups = (G + kPeRows - 1) / kPeRows;
+  patch_embed_kernel<<<B * groups, 256, smem, st>>>(img, w, b, gamma, beta, out, Cin, S, P, E);
   return cudaGetLastError();
 }
 

@@ -8,10 +8,11 @@
 // (reference models/swin_transformer_mod.py:214-216,229-233,270 qkv/proj; :109-119 fc1/fc2;
 // :479,499 patch-merging reduction).
 //
-// CTA = 6 warps:  warp 0  TMA producer (one elected lane)
+// CTA = 10 warps: warp 0  TMA producer (one elected lane)
 //                 warp 1  TMEM allocator + MMA issuer (one elected lane)
-//                 warps 2-5  epilogue: tcgen05.ld -> smem transpose -> fused bias/GELU/residual
-//                            -> coalesced global stores
+//                 warps 2-9  epilogue (two per TMEM lane quarter, half of the columns each):
+//                            tcgen05.ld (16 columns, double-buffered) -> smem transpose -> fused
+//                            bias/GELU/residual (residual prefetched one step ahead) -> coalesced stores
 // Pipelines: a kStages-deep smem ring (full/empty mbarriers, TMA <-> MMA) and a 2-deep TMEM
 // accumulator ring (tmem_full/tmem_empty, MMA <-> epilogue) so the epilogue of tile i overlaps
 // the MMAs of tile i+1.  Tiles are 128 x BN (BN in {128,192,256}), K step 64 (one 128-byte
@@ -27,7 +28,8 @@ namespace xn {
 constexpr int kBM = 128;
 constexpr int kBK = 64;                       // bf16 elements = 128 bytes = swizzle span
 constexpr int kUmmaK = 16;
-constexpr int kTcThreads = 192;
+constexpr int kEpiWarps = 8;                  // 2 per TMEM lane quarter, each draining half of the tile's columns
+constexpr int kTcThreads = 64 + 32 * kEpiWarps;
 constexpr uint32_t kABytes = kBM * kBK * 2;   // 16 KB
 
 template <int BN> struct TcCfg {
@@ -36,7 +38,7 @@ template <int BN> struct TcCfg {
   static constexpr int kStages = (BN == 256) ? 4 : (BN == 192 ? 5 : 6);
   static constexpr uint32_t kAccCols = 256;                 // column stride between the two accumulators
   static constexpr uint32_t kTmemCols = 512;
-  static constexpr uint32_t kStagingBytes = 4 * 32 * 36 * 4;   // per epilogue warp: 32 rows x 36 floats (16-B aligned rows)
+  static constexpr uint32_t kStagingBytes = kEpiWarps * 32 * 20 * 4;   // per epilogue warp: 32 rows x (16 + 4 pad) floats
   static constexpr uint32_t kSmemBytes = kStages * kStageBytes + kStagingBytes + 256 + 1024;
 };
 
@@ -107,6 +109,30 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// GELU(erf) with erf from Abramowitz-Stegun 7.1.26 (|abs err| <= 1.5e-7), MUFU rcp/ex2: used when the output is
+// rounded to 16 bits anyway; the fp32 parity mode keeps erff().
+__device__ __forceinline__ float gelu_fast(float x) {
+  const float z = fabsf(x) * 0.70710678118654752440f;
+  const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
+  float pl = fmaf(t, 1.061405429f, -1.453152027f);
+  pl = fmaf(pl, t, 1.421413741f);
+  pl = fmaf(pl, t, -0.284496736f);
+  pl = fmaf(pl, t, 0.254829592f);
+  const float e = 1.0f - pl * t * __expf(-z * z);          // erf(|x|/sqrt2)
+  return 0.5f * x * (1.0f + copysignf(e, x));
+}
+
 // UMMA shared-memory descriptor, K-major operand, 128-byte swizzle (cute::UMMA::SmemDescriptor):
 //   [0,14) start address >> 4   [16,30) leading byte offset >> 4 (unused for swizzled K-major)
 //   [32,46) stride byte offset >> 4 (8 rows x 128 B = 1024)   [46,48) version = 1
@@ -149,7 +175,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < S; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), 4); }
+    for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), kEpiWarps); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -210,9 +236,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       }
     }
   } else {
-    const int q = warp & 3;                        // TMEM lane quarter this warp may access
-    float* tile_s = staging_gen + (warp - 2) * (32 * 36);
-    const int sub_r = lane >> 3, c4 = (lane & 7) * 4;   // coalesced phase: 4 rows x 8 lanes x float4 per instruction
+    const int q = warp & 3;                        // TMEM lane quarter this warp may access (hardware: warp id % 4)
+    const int hf = (warp - 2) >> 2;                // which half of the tile's columns this warp drains
+    float* tile_s = staging_gen + (warp - 2) * (32 * 20);
+    const int sub_r = lane >> 2, c4 = (lane & 3) * 4;   // coalesced phase: 8 rows x 4 lanes x float4 per instruction
+    constexpr int kSteps = BN / 32;                // 16-column steps per warp
+    const bool ld_vec = ((ep.ldc & 3) == 0) && (!ep.res || (ep.ldr & 3) == 0);
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       const int buf = it & 1;
@@ -221,78 +250,89 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       mbar_wait(tfull_bar(buf), acc_phase);
       tc_fence_after();
       const int row_base = m0 + q * 32;
-#pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        if (n0 + c0 >= N) break;
-        uint32_t v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * Cfg::kAccCols + c0, v);
-        // transpose through smem: lane == accumulator row; conflict-free 16-byte stores
+      const int col_base = n0 + hf * (BN / 2);
+      const uint32_t t_base = tmem_base + ((uint32_t)(q * 32) << 16) + buf * Cfg::kAccCols + hf * (BN / 2);
+      uint32_t v[2][16];
+      float4 rres[2][4];
+      auto load_res = [&](int step, float4 (&r)[4]) {
+        const int col = col_base + step * 16 + c4;
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-          *reinterpret_cast<uint4*>(&tile_s[lane * 36 + 4 * j]) = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-        __syncwarp();
-        if (ep.dbg & 1) { __syncwarp(); continue; }
-        const int col = n0 + c0 + c4;
-        const bool vec_ok = (col + 3 < N) && ((ep.ldc & 3) == 0) && (!ep.res || (ep.ldr & 3) == 0);
-        float4 bcol = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (ep.bias) {
-          if (col + 3 < N) bcol = *reinterpret_cast<const float4*>(ep.bias + col);
-          else {
-            if (col < N) bcol.x = ep.bias[col];
-            if (col + 1 < N) bcol.y = ep.bias[col + 1];
-            if (col + 2 < N) bcol.z = ep.bias[col + 2];
-          }
-        }
-        float4 acc[8], rres[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int r = i * 4 + sub_r;
-          acc[i] = *reinterpret_cast<const float4*>(&tile_s[r * 36 + c4]);
-          rres[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-          const int row = row_base + r;
-          if (ep.res && row < M) {
-            if (vec_ok) rres[i] = *reinterpret_cast<const float4*>(ep.res + (long)row * ep.ldr + col);
+        for (int i = 0; i < 4; ++i) {
+          r[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          const int row = row_base + i * 8 + sub_r;
+          if (ep.res && row < M && col < N) {
+            const float* src = ep.res + (long)row * ep.ldr + col;
+            if (ld_vec && col + 3 < N) r[i] = *reinterpret_cast<const float4*>(src);
             else {
-              if (col < N) rres[i].x = ep.res[(long)row * ep.ldr + col];
-              if (col + 1 < N) rres[i].y = ep.res[(long)row * ep.ldr + col + 1];
-              if (col + 2 < N) rres[i].z = ep.res[(long)row * ep.ldr + col + 2];
-              if (col + 3 < N) rres[i].w = ep.res[(long)row * ep.ldr + col + 3];
+              r[i].x = src[0];
+              if (col + 1 < N) r[i].y = src[1];
+              if (col + 2 < N) r[i].z = src[2];
+              if (col + 3 < N) r[i].w = src[3];
             }
           }
         }
+      };
+      tmem_ld16_nowait(t_base, v[0]);
+      load_res(0, rres[0]);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int row = row_base + i * 4 + sub_r;
-          float x[4] = {acc[i].x, acc[i].y, acc[i].z, acc[i].w};
-          const float bb[4] = {bcol.x, bcol.y, bcol.z, bcol.w};
-          const float rr[4] = {rres[i].x, rres[i].y, rres[i].z, rres[i].w};
+      for (int sidx = 0; sidx < kSteps; ++sidx) {
+        const int cur = sidx & 1;
+        tmem_ld_wait();
+        // transpose through smem: lane == accumulator row; conflict-free 16-byte stores (row stride 20 floats)
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            float t = fmaf(x[e], ep.scale, bb[e]);
-            if (ACT == 1) t = gelu_erf(t);
-            else if (ACT == 2) t = fmaxf(t, 0.f);
-            x[e] = t + rr[e];
+        for (int j = 0; j < 4; ++j)
+          *reinterpret_cast<uint4*>(&tile_s[lane * 20 + 4 * j]) = make_uint4(v[cur][4 * j], v[cur][4 * j + 1], v[cur][4 * j + 2], v[cur][4 * j + 3]);
+        __syncwarp();
+        if (sidx + 1 < kSteps) {                   // next step's accumulator slice and residual are in flight during this step's math
+          tmem_ld16_nowait(t_base + (sidx + 1) * 16, v[cur ^ 1]);
+          load_res(sidx + 1, rres[cur ^ 1]);
+        }
+        const int col = col_base + sidx * 16 + c4;
+        if (!(ep.dbg & 1) && col < N) {
+          const bool vec_ok = ld_vec && (col + 3 < N);
+          float4 bcol = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (ep.bias) {
+            if (col + 3 < N) bcol = *reinterpret_cast<const float4*>(ep.bias + col);
+            else {
+              bcol.x = ep.bias[col];
+              if (col + 1 < N) bcol.y = ep.bias[col + 1];
+              if (col + 2 < N) bcol.z = ep.bias[col + 2];
+            }
           }
-          if ((ep.dbg & 8) && x[0] != 1234567.f) continue;   // timing experiment: all the math, no global stores
-          if (row < M && col < N) {
-            if (OUT == 0) {
-              float* dst = ep.Cf + (long)row * ep.ldc + col;
-              if (vec_ok) *reinterpret_cast<float4*>(dst) = make_float4(x[0], x[1], x[2], x[3]);
-              else for (int e = 0; e < 4; ++e) if (col + e < N) dst[e] = x[e];
-            } else if (ep.fp16) {
-              f16* dst = reinterpret_cast<f16*>(ep.Cb) + (long)row * ep.ldc + col;
-              if (vec_ok) {
-                __half2 lo = __floats2half2_rn(x[0], x[1]), hi = __floats2half2_rn(x[2], x[3]);
-                uint2 u; u.x = *reinterpret_cast<uint32_t*>(&lo); u.y = *reinterpret_cast<uint32_t*>(&hi);
-                *reinterpret_cast<uint2*>(dst) = u;
-              } else for (int e = 0; e < 4; ++e) if (col + e < N) dst[e] = __float2half_rn(x[e]);
-            } else {
-              bf16* dst = reinterpret_cast<bf16*>(ep.Cb) + (long)row * ep.ldc + col;
-              if (vec_ok) {
-                __nv_bfloat162 lo = __floats2bfloat162_rn(x[0], x[1]), hi = __floats2bfloat162_rn(x[2], x[3]);
-                uint2 u; u.x = *reinterpret_cast<uint32_t*>(&lo); u.y = *reinterpret_cast<uint32_t*>(&hi);
-                *reinterpret_cast<uint2*>(dst) = u;
-              } else for (int e = 0; e < 4; ++e) if (col + e < N) dst[e] = __float2bfloat16_rn(x[e]);
+          const float bb[4] = {bcol.x, bcol.y, bcol.z, bcol.w};
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int row = row_base + i * 8 + sub_r;
+            const float4 a = *reinterpret_cast<const float4*>(&tile_s[(i * 8 + sub_r) * 20 + c4]);
+            float x[4] = {a.x, a.y, a.z, a.w};
+            const float rr[4] = {rres[cur][i].x, rres[cur][i].y, rres[cur][i].z, rres[cur][i].w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              float t = fmaf(x[e], ep.scale, bb[e]);
+              if (ACT == 1) t = (OUT == 1) ? gelu_fast(t) : gelu_erf(t);
+              else if (ACT == 2) t = fmaxf(t, 0.f);
+              x[e] = t + rr[e];
+            }
+            if (row < M) {
+              if (OUT == 0) {
+                float* dst = ep.Cf + (long)row * ep.ldc + col;
+                if (vec_ok) *reinterpret_cast<float4*>(dst) = make_float4(x[0], x[1], x[2], x[3]);
+                else for (int e = 0; e < 4; ++e) if (col + e < N) dst[e] = x[e];
+              } else if (ep.fp16) {
+                f16* dst = reinterpret_cast<f16*>(ep.Cb) + (long)row * ep.ldc + col;
+                if (vec_ok) {
+                  __half2 lo = __floats2half2_rn(x[0], x[1]), hi = __floats2half2_rn(x[2], x[3]);
+                  uint2 u; u.x = *reinterpret_cast<uint32_t*>(&lo); u.y = *reinterpret_cast<uint32_t*>(&hi);
+                  *reinterpret_cast<uint2*>(dst) = u;
+                } else for (int e = 0; e < 4; ++e) if (col + e < N) dst[e] = __float2half_rn(x[e]);
+              } else {
+                bf16* dst = reinterpret_cast<bf16*>(ep.Cb) + (long)row * ep.ldc + col;
+                if (vec_ok) {
+                  __nv_bfloat162 lo = __floats2bfloat162_rn(x[0], x[1]), hi = __floats2bfloat162_rn(x[2], x[3]);
+                  uint2 u; u.x = *reinterpret_cast<uint32_t*>(&lo); u.y = *reinterpret_cast<uint32_t*>(&hi);
+                  *reinterpret_cast<uint2*>(dst) = u;
+                } else for (int e = 0; e < 4; ++e) if (col + e < N) dst[e] = __float2bfloat16_rn(x[e]);
+              }
             }
           }
         }

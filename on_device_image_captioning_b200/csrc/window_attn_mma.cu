@@ -63,7 +63,7 @@ __global__ void __launch_bounds__(kMmaThreads, 2) window_attention_mma_kernel(co
   __shared__ __align__(16) T Vs[kWinTok * kRowPad];
   __shared__ float bt[532];
   __shared__ int tok[kWinTok];
-  __shared__ unsigned char lab[kWinTok];
+  __shared__ __align__(8) int jinfo[kWinTok];     // (yj*23 + xj) | region label << 16, per key token
 
   const int nWs = H / kWin;
   const int wid = blockIdx.x, head = blockIdx.y;
@@ -81,7 +81,7 @@ __global__ void __launch_bounds__(kMmaThreads, 2) window_attention_mma_kernel(co
       lh = hs < H - kWin ? 0 : (hs < H - shift ? 1 : 2);
       lw = ws_ < H - kWin ? 0 : (ws_ < H - shift ? 1 : 2);
     }
-    lab[tid] = (unsigned char)(lh * 3 + lw);
+    jinfo[tid] = (ty * (2 * kWin - 1) + tx) | ((lh * 3 + lw) << 16);
   }
   for (int i = tid; i < 529; i += kMmaThreads) bt[i] = bias_table[(long)i * heads + head];
   __syncthreads();
@@ -122,22 +122,27 @@ __global__ void __launch_bounds__(kMmaThreads, 2) window_attention_mma_kernel(co
   // scale + relative-position bias + shift mask, then the row softmax (rows r0 = m0 + lane/4, r1 = r0 + 8)
   const float scale = 0.17677669529663687f;
   const int r0 = m0 + (lane >> 2), r1 = r0 + 8;
-  const int y0 = r0 / kWin, x0 = r0 % kWin, y1 = r1 / kWin, x1 = r1 % kWin;
-  const int l0 = lab[r0], l1 = lab[r1];
+  // bias index = (yi - yj + 11)*23 + (xi - xj + 11) = rowbase_i - (yj*23 + xj)
+  const int i0 = jinfo[r0], i1 = jinfo[r1];
+  const float* bt0 = bt + (i0 & 0xffff) + (kWin - 1) * (2 * kWin - 1) + (kWin - 1);
+  const float* bt1 = bt + (i1 & 0xffff) + (kWin - 1) * (2 * kWin - 1) + (kWin - 1);
+  const int l0 = i0 >> 16, l1 = i1 >> 16;
   float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
   for (int nt = 0; nt < 18; ++nt) {
-#pragma unroll
-    for (int e = 0; e < 2; ++e) {
-      const int j = nt * 8 + (lane & 3) * 2 + e;
-      const int yj = j / kWin, xj = j % kWin, lj = lab[j];
-      float a = s[nt][e] * scale + bt[(y0 - yj + kWin - 1) * (2 * kWin - 1) + (x0 - xj + kWin - 1)];
-      float c = s[nt][2 + e] * scale + bt[(y1 - yj + kWin - 1) * (2 * kWin - 1) + (x1 - xj + kWin - 1)];
-      if (lj != l0) a += -100.0f;
-      if (lj != l1) c += -100.0f;
-      s[nt][e] = a; s[nt][2 + e] = c;
-      mx0 = fmaxf(mx0, a); mx1 = fmaxf(mx1, c);
-    }
+    const int2 jj = *reinterpret_cast<const int2*>(&jinfo[nt * 8 + (lane & 3) * 2]);
+    const int ja = jj.x & 0xffff, jb = jj.y & 0xffff, la = jj.x >> 16, lb = jj.y >> 16;
+    float a0 = fmaf(s[nt][0], scale, bt0[-ja]);
+    float a1 = fmaf(s[nt][1], scale, bt0[-jb]);
+    float c0 = fmaf(s[nt][2], scale, bt1[-ja]);
+    float c1 = fmaf(s[nt][3], scale, bt1[-jb]);
+    if (la != l0) a0 += -100.0f;
+    if (lb != l0) a1 += -100.0f;
+    if (la != l1) c0 += -100.0f;
+    if (lb != l1) c1 += -100.0f;
+    s[nt][0] = a0; s[nt][1] = a1; s[nt][2] = c0; s[nt][3] = c1;
+    mx0 = fmaxf(mx0, fmaxf(a0, a1));
+    mx1 = fmaxf(mx1, fmaxf(c0, c1));
   }
   mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
   mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
