@@ -36,7 +36,7 @@ struct LinW {
   int N = 0, K = 0;
 };
 
-struct SwinBlockW { const float *n1g, *n1b, *n2g, *n2b, *rpb; LinW qkv, proj, fc1, fc2; };
+struct SwinBlockW { const float *n1g, *n1b, *n2g, *n2b, *rpb, *rpb_t; LinW qkv, proj, fc1, fc2; };
 struct SwinStageW {
   int C, H, heads;
   std::vector<SwinBlockW> blocks;
@@ -254,7 +254,7 @@ int swin_forward_chunk(xn_handle* h, const float* img, int Bc, float* out, cudaS
       const int shift = (bi % 2 == 1 && H > c.window_size) ? c.window_size / 2 : 0;
       KL(1, launch_layernorm<T>(x, C, W.n1g, W.n1b, xn, C, M, C, st));
       if (int r = ActOps<T>::lin_act(h, xn, C, W.qkv, qkv, 3 * C, M, 0, st)) return r;
-      KL(1, ActOps<T>::attn(qkv, W.rpb, ao, Bc, H, C, S.heads, shift, st));
+      KL(1, ActOps<T>::attn(qkv, std::is_same<T, float>::value ? W.rpb : W.rpb_t, ao, Bc, H, C, S.heads, shift, st));
       if (int r = ActOps<T>::lin_res(h, ao, C, W.proj, x, C, x, C, M, st)) return r;
       KL(1, launch_layernorm<T>(x, C, W.n2g, W.n2b, xn, C, M, C, st));
       if (int r = ActOps<T>::lin_act(h, xn, C, W.fc1, hid, W.fc1.N, M, 1, st)) return r;
@@ -841,8 +841,16 @@ int xn_finalize_weights(xn_handle* h, int precision) {
         W.rpb = P(q + "attn.relative_position_bias_table", {23 * 23, S.heads});
         W.qkv = lin(q + "attn.qkv", 3 * C, C); W.proj = lin(q + "attn.proj", C, C);
         W.fc1 = lin(q + "mlp.fc1", hid, C); W.fc2 = lin(q + "mlp.fc2", C, hid);
+        W.rpb_t = nullptr;
         if (precision != XN_PREC_FP32) {
           if (to_bf16(W.qkv) || to_bf16(W.proj) || to_bf16(W.fc1) || to_bf16(W.fc2)) return XN_ERR_CUDA;
+          if (!rc) {
+            float* bt = nullptr;
+            CU(cudaMalloc(&bt, (size_t)23 * 23 * S.heads * sizeof(float)));
+            h->owned.push_back(bt);
+            KL(1, launch_transpose_bias(W.rpb, bt, S.heads, 0));
+            W.rpb_t = bt;
+          }
         }
         S.blocks.push_back(W);
       }
@@ -1139,9 +1147,12 @@ int xn_op_window_attention(xn_handle* h, const float* qkv, const float* bias_tab
     return XN_OK;
   }
   const size_t n = (size_t)B * H * H * C;
-  if (int r = ensure_ws(h, n * 4 * 2 + 8192, st)) return r;
+  if (int r = ensure_ws(h, n * 4 * 2 + 8192 + (size_t)529 * heads * 4, st)) return r;
   bf16* qb = h->ws.get<bf16>(3 * n);
   bf16* ob = h->ws.get<bf16>(n);
+  float* bias_t = h->ws.get<float>((size_t)529 * heads);
+  KL(1, launch_transpose_bias(bias_table, bias_t, heads, st));
+  bias_table = bias_t;
   if (precision == XN_PREC_FP16) {
     KL(1, launch_cast<f16>(qkv, reinterpret_cast<f16*>(qb), (long)(3 * n), st));
     KL(1, launch_window_attention_mma<f16>(reinterpret_cast<f16*>(qb), bias_table, reinterpret_cast<f16*>(ob), B, H, C, heads, shift, st));

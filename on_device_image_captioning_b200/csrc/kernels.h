@@ -65,10 +65,11 @@ cudaError_t launch_cast(const float* x, T* y, long n, cudaStream_t st);
 template <typename T>
 cudaError_t launch_window_attention(const T* qkv, const float* bias_table, T* out, int B, int H, int C,
                                     int heads, int shift, cudaStream_t st);
-// tensor-core (mma.sync) variant for the 16-bit modes
+// tensor-core (mma.sync) variant for the 16-bit modes; takes the bias table transposed to (heads, 529)
 template <typename T>
-cudaError_t launch_window_attention_mma(const T* qkv, const float* bias_table, T* out, int B, int H, int C,
+cudaError_t launch_window_attention_mma(const T* qkv, const float* bias_t, T* out, int B, int H, int C,
                                         int heads, int shift, cudaStream_t st);
+cudaError_t launch_transpose_bias(const float* table, float* out, int heads, cudaStream_t st);
 
 // ---------------------------------------------------------------- static expansion (encoder)
 // z (B, E, N) raw scores (already / sqrt(d)).  Produces forward weights (B,E,N) normalised over
