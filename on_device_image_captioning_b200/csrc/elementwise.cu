@@ -132,6 +132,11 @@ __global__ void __launch_bounds__(256) patch_embed_kernel(const float* __restric
   const int G = S / P, K = Cin * P * P;
   float* slab = sm;                       // [Cin*P][S]   one patch row of input pixels
   float* wt = slab + Cin * P * S;         // [K][E]       filter bank, transposed
+  int* koff = reinterpret_cast<int*>(wt + K * E);   // [K] slab offset of tap k = (c, dy, dx)
+  for (int k = threadIdx.x; k < K; k += blockDim.x) {
+    const int c = k / (P * P), r = k % (P * P);
+    koff[k] = (c * P + r / P) * S + r % P;
+  }
   const int groups = (G + kPeRows - 1) / kPeRows;
   const int b = blockIdx.x / groups, py0 = (blockIdx.x % groups) * kPeRows;
   // w is (E, Cin, P, P) = [e][k]; smem writes are contiguous in e (conflict-free), the strided reads hit L2
@@ -160,12 +165,13 @@ __global__ void __launch_bounds__(256) patch_embed_kernel(const float* __restric
       float acc[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) acc[j] = bia[j];
+      const float* sp = slab + px * P;
       for (int k = 0; k < K; ++k) {
-        const int c = k / (P * P), r = k % (P * P), dy = r / P, dx = r % P;
-        const float v = slab[(c * P + dy) * S + px * P + dx];
+        const float v = sp[koff[k]];
+        const float* wk = wt + k * E + lane;
 #pragma unroll
         for (int j = 0; j < 8; ++j)
-          if (j < EP) acc[j] = fmaf(v, wt[k * E + lane + 32 * j], acc[j]);
+          if (j < EP) acc[j] = fmaf(v, wk[32 * j], acc[j]);
       }
       float s = 0.f;
 #pragma unroll
@@ -187,7 +193,7 @@ cudaError_t launch_patch_embed(const float* img, const float* w, const float* b,
                                const float* beta, float* out, int B, int Cin, int S, int P, int E,
                                cudaStream_t st) {
   if (E % 32 || E > 256 || S % P || S % 4) return cudaErrorInvalidValue;
-  const size_t smem = ((size_t)Cin * P * S + (size_t)Cin * P * P * E) * sizeof(float);
+  const size_t smem = ((size_t)Cin * P * S + (size_t)Cin * P * P * E + (size_t)Cin * P * P) * sizeof(float);
   static size_t configured = 0;
   if (smem > configured) {
     cudaError_t e = cudaFuncSetAttribute(patch_embed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

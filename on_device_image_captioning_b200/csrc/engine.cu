@@ -89,6 +89,7 @@ struct xn_handle {
   };
   std::vector<DecodeGraph> graphs;
   int64_t use_graph = 1;
+  int64_t op_out16 = 0;
   cudaStream_t gstream = nullptr;      // graphs are captured/replayed here (the caller's stream may be the legacy
   cudaEvent_t g_in = nullptr, g_out = nullptr;   // default stream, which cannot be captured); ordered with events
   void drop_graphs() {
@@ -1079,6 +1080,7 @@ int xn_set_option(xn_handle* h, const char* name, int64_t value) {
   if (!h || !name) return XN_ERR_ARG;
   std::string n(name);
   if (n == "use_graph") { h->use_graph = value; h->drop_graphs(); return XN_OK; }
+  if (n == "op_out16") { h->op_out16 = value; return XN_OK; }
   if (n == "tc_debug") { set_tc_debug((int)value); return XN_OK; }
   if (n == "profile") { h->profile = value; h->prof_used = 0; h->prof_flops.clear(); }
   else if (n == "swin_chunk") h->swin_chunk = std::max<int64_t>(1, value);
@@ -1124,7 +1126,7 @@ int xn_op_linear(xn_handle* h, const float* x, const float* w, const float* bias
     return lin_f32(h, x, K, l, residual, N, y, N, M, act, st);
   }
   if (!tc_gemm_supported(M, N, K)) return h->fail(XN_ERR_UNSUPPORTED, "tcgen05 GEMM needs K %% 64 == 0 and N %% 8 == 0 (M=%d N=%d K=%d)", M, N, K);
-  if (int r = ensure_ws(h, ((size_t)M * K + (size_t)N * K) * 2 + 8192, st)) return r;
+  if (int r = ensure_ws(h, ((size_t)M * K + (size_t)N * K + (size_t)M * N) * 2 + 8192, st)) return r;
   bf16* xb = h->ws.get<bf16>((size_t)M * K);
   bf16* wb = h->ws.get<bf16>((size_t)N * K);
   const int fp16 = precision == XN_PREC_FP16;
@@ -1136,6 +1138,13 @@ int xn_op_linear(xn_handle* h, const float* x, const float* w, const float* bias
     KL(1, launch_cast<bf16>(w, wb, (long)N * K, st));
   }
   LinW l; l.wb = wb; l.b = bias; l.N = N; l.K = K;
+  if (h->op_out16) {            // exercise the 16-bit-output epilogue, then widen for the caller
+    if (h->ws.off + (size_t)M * N * 2 + 512 > h->ws.cap) return h->fail(XN_ERR_STATE, "op_out16: workspace too small");
+    bf16* y16 = h->ws.get<bf16>((size_t)M * N);
+    if (int r = lin_tc(h, xb, K, l, residual, N, nullptr, y16, N, M, act, fp16, st)) return r;
+    KL(1, launch_widen_16(y16, y, (long)M * N, fp16, st));
+    return XN_OK;
+  }
   return lin_tc(h, xb, K, l, residual, N, y, nullptr, N, M, act, fp16, st);
 }
 

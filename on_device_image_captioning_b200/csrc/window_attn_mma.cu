@@ -21,7 +21,6 @@ namespace xn {
 
 constexpr int kMmaThreads = 288;
 constexpr int kRowPad = 40;                      // 16-bit elements per smem row (80 B): conflict-free ldmatrix
-constexpr int kHeadsPerCta = 3;                  // 6, 12, 24, 48 heads are all multiples of 3
 constexpr int kBiasN = (2 * kWin - 1) * (2 * kWin - 1);   // 529
 
 template <typename T> struct Mma16;
@@ -63,7 +62,8 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 // bias_t is the relative-position table transposed to (heads, 529) so a head's column is contiguous
-template <typename T>
+// kHeadsPerCta: 3 for Swin-L (6/12/24/48 heads), 2 or 1 for other head counts
+template <typename T, int kHeadsPerCta>
 __global__ void __launch_bounds__(kMmaThreads, 2) window_attention_mma_kernel(const T* __restrict__ qkv,
                                                                               const float* __restrict__ bias_t,
                                                                               T* __restrict__ out, int H, int C, int heads,
@@ -231,20 +231,28 @@ __global__ void __launch_bounds__(kMmaThreads, 2) window_attention_mma_kernel(co
   }
 }
 
-template <typename T>
-cudaError_t launch_window_attention_mma(const T* qkv, const float* bias_t, T* out, int B, int H, int C, int heads,
-                                        int shift, cudaStream_t st) {
-  if (H % kWin || C != heads * kHeadDim || heads % kHeadsPerCta) return cudaErrorInvalidValue;
-  const size_t smem = 2 * 3 * kWinTok * kRowPad * sizeof(T) + kHeadsPerCta * 532 * sizeof(float) + 2 * kWinTok * sizeof(int);
+template <typename T, int HPC>
+static cudaError_t launch_wa_hpc(const T* qkv, const float* bias_t, T* out, int B, int H, int C, int heads, int shift,
+                                 cudaStream_t st) {
+  const size_t smem = 2 * 3 * kWinTok * kRowPad * sizeof(T) + HPC * 532 * sizeof(float) + 2 * kWinTok * sizeof(int);
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(window_attention_mma_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(window_attention_mma_kernel<T, HPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     configured = true;
   }
   const int nW = (H / kWin) * (H / kWin);
-  window_attention_mma_kernel<T><<<dim3(B * nW, heads / kHeadsPerCta), kMmaThreads, smem, st>>>(qkv, bias_t, out, H, C, heads, shift);
+  window_attention_mma_kernel<T, HPC><<<dim3(B * nW, heads / HPC), kMmaThreads, smem, st>>>(qkv, bias_t, out, H, C, heads, shift);
   return cudaGetLastError();
+}
+
+template <typename T>
+cudaError_t launch_window_attention_mma(const T* qkv, const float* bias_t, T* out, int B, int H, int C, int heads,
+                                        int shift, cudaStream_t st) {
+  if (H % kWin || C != heads * kHeadDim) return cudaErrorInvalidValue;
+  if (heads % 3 == 0) return launch_wa_hpc<T, 3>(qkv, bias_t, out, B, H, C, heads, shift, st);
+  if (heads % 2 == 0) return launch_wa_hpc<T, 2>(qkv, bias_t, out, B, H, C, heads, shift, st);
+  return launch_wa_hpc<T, 1>(qkv, bias_t, out, B, H, C, heads, shift, st);
 }
 template cudaError_t launch_window_attention_mma<bf16>(const bf16*, const float*, bf16*, int, int, int, int, int, cudaStream_t);
 template cudaError_t launch_window_attention_mma<__half>(const __half*, const float*, __half*, int, int, int, int, int, cudaStream_t);

@@ -17,7 +17,9 @@ def main():
               ("s3.qkv", Bc * 576, 2304, 768, 0, False), ("s3.proj", Bc * 576, 768, 768, 0, True),
               ("s3.fc1", Bc * 576, 3072, 768, 1, False), ("s3.fc2", Bc * 576, 768, 3072, 0, True),
               ("s4.fc1", Bc * 144, 6144, 1536, 1, False), ("big", 8192, 8192, 8192, 0, False)]
-    only = sys.argv[3].split(",") if len(sys.argv) > 3 else None
+    only = sys.argv[3].split(",") if len(sys.argv) > 3 and sys.argv[3] != "all" else None
+    out16 = len(sys.argv) > 4 and sys.argv[4] == "out16"
+    prec = "fp16" if out16 else "bf16"
     g = torch.Generator().manual_seed(0)
     for name, M, N, K, act, res in shapes:
         if only and name not in only:
@@ -26,13 +28,16 @@ def main():
         w = (torch.randn(N, K, generator=g) / K ** 0.5).cuda()
         b = torch.randn(N, generator=g).cuda()
         r = torch.randn(M, N, generator=g).cuda() if res else None
-        line = f"{name:8s} M={M:7d} N={N:5d} K={K:5d} act{act} res{int(res)}:"
+        if out16 and res:
+            continue          # 16-bit outputs never carry the fp32 residual in the engine
+        e.set_option("op_out16", 1 if out16 else 0)
+        line = f"{name:8s} M={M:7d} N={N:5d} K={K:5d} act{act} res{int(res)} {'out16' if out16 else 'out32'}:"
         for mode in modes:
             e.set_option("tc_debug", mode)
-            e.op_linear(x, w, b, r, act, "bf16")
+            e.op_linear(x, w, b, r, act, prec)
             e.set_option("profile", 1)
             for _ in range(3):
-                e.op_linear(x, w, b, r, act, "bf16")
+                e.op_linear(x, w, b, r, act, prec)
             ms, fl, n = e.profile_read()
             e.set_option("profile", 0)
             line += f"  dbg{mode}: {ms / n * 1e3:8.1f} us {fl / ms / 1e9:7.1f} TF/s |"
