@@ -38,7 +38,7 @@ template <int BN> struct TcCfg {
   static constexpr int kStages = (BN == 256) ? 4 : (BN == 192 ? 5 : 6);
   static constexpr uint32_t kAccCols = 256;                 // column stride between the two accumulators
   static constexpr uint32_t kTmemCols = 512;
-  static constexpr uint32_t kStagingBytes = kEpiWarps * 32 * 20 * 4;   // per epilogue warp: 32 rows x (16 + 4 pad) floats
+  static constexpr uint32_t kStagingBytes = kEpiWarps * 32 * 16 * 4;   // per epilogue warp: 32 rows x 16 floats, XOR-swizzled 16-B slots
   static constexpr uint32_t kSmemBytes = kStages * kStageBytes + kStagingBytes + 256 + 1024;
 };
 
@@ -115,6 +115,18 @@ __device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&v)[1
       "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
       : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
         "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
       : "r"(taddr)
       : "memory");
 }
@@ -238,11 +250,69 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   } else {
     const int q = warp & 3;                        // TMEM lane quarter this warp may access (hardware: warp id % 4)
     const int hf = (warp - 2) >> 2;                // which half of the tile's columns this warp drains
-    float* tile_s = staging_gen + (warp - 2) * (32 * 20);
+    int it = 0;
+    if (OUT == 1) {
+      // ---- 16-bit output: straight from the accumulator registers.  Lane == row; every step a lane owns 32
+      // consecutive columns = 64 contiguous bytes (two full 32-B sectors), so no smem transpose is needed.
+      constexpr int kSteps = BN / 64;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        const int buf = it & 1;
+        const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
+        const int m0 = (tile / n_tiles) * kBM, n0 = (tile % n_tiles) * BN;
+        mbar_wait(tfull_bar(buf), acc_phase);
+        tc_fence_after();
+        const int row = m0 + q * 32 + lane;
+        const int col_base = n0 + hf * (BN / 2);
+        const uint32_t t_base = tmem_base + ((uint32_t)(q * 32) << 16) + buf * Cfg::kAccCols + hf * (BN / 2);
+        uint32_t v[2][32];
+        tmem_ld32_nowait(t_base, v[0]);
+#pragma unroll
+        for (int sidx = 0; sidx < kSteps; ++sidx) {
+          const int cur = sidx & 1;
+          tmem_ld_wait();
+          if (sidx + 1 < kSteps) tmem_ld32_nowait(t_base + (sidx + 1) * 32, v[cur ^ 1]);
+          const int col = col_base + sidx * 32;
+          if ((ep.dbg & 1) || col >= N) continue;
+          const bool full = (col + 31 < N) && ((ep.ldc & 7) == 0);
+          uint32_t pk[16];
+#pragma unroll
+          for (int c = 0; c < 32; c += 2) {
+            float t0 = __uint_as_float(v[cur][c]) * ep.scale, t1 = __uint_as_float(v[cur][c + 1]) * ep.scale;
+            if (ep.bias) {
+              if (col + c < N) t0 += __ldg(ep.bias + col + c);
+              if (col + c + 1 < N) t1 += __ldg(ep.bias + col + c + 1);
+            }
+            if (ACT == 1) { t0 = gelu_fast(t0); t1 = gelu_fast(t1); }
+            else if (ACT == 2) { t0 = fmaxf(t0, 0.f); t1 = fmaxf(t1, 0.f); }
+            if (ep.res && row < M) {
+              if (col + c < N) t0 += ep.res[(long)row * ep.ldr + col + c];
+              if (col + c + 1 < N) t1 += ep.res[(long)row * ep.ldr + col + c + 1];
+            }
+            if (ep.fp16) { __half2 hh = __floats2half2_rn(t0, t1); pk[c >> 1] = *reinterpret_cast<uint32_t*>(&hh); }
+            else { __nv_bfloat162 hh = __floats2bfloat162_rn(t0, t1); pk[c >> 1] = *reinterpret_cast<uint32_t*>(&hh); }
+          }
+          if (row < M) {
+            uint16_t* dst = reinterpret_cast<uint16_t*>(ep.Cb) + (long)row * ep.ldc + col;
+            if (full) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                *reinterpret_cast<uint4*>(dst + 8 * j) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+            } else {
+              for (int c = 0; c < 32; ++c)
+                if (col + c < N) dst[c] = (uint16_t)((c & 1) ? (pk[c >> 1] >> 16) : (pk[c >> 1] & 0xffffu));
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty_bar(buf));
+      }
+    } else {
+    // ---- fp32 output (+ fp32 residual): transpose 16-column slices through smem for coalesced row segments
+    float* tile_s = staging_gen + (warp - 2) * (32 * 16);
     const int sub_r = lane >> 2, c4 = (lane & 3) * 4;   // coalesced phase: 8 rows x 4 lanes x float4 per instruction
     constexpr int kSteps = BN / 32;                // 16-column steps per warp
     const bool ld_vec = ((ep.ldc & 3) == 0) && (!ep.res || (ep.ldr & 3) == 0);
-    int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       const int buf = it & 1;
       const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
@@ -278,10 +348,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       for (int sidx = 0; sidx < kSteps; ++sidx) {
         const int cur = sidx & 1;
         tmem_ld_wait();
-        // transpose through smem: lane == accumulator row; conflict-free 16-byte stores (row stride 20 floats)
+        // lane == accumulator row.  Row stride 16 floats, 16-byte slot j stored at j ^ ((row >> 1) & 3): both the
+        // row-wise stores and the 8-rows-x-4-slots loads below are bank-conflict free.
 #pragma unroll
         for (int j = 0; j < 4; ++j)
-          *reinterpret_cast<uint4*>(&tile_s[lane * 20 + 4 * j]) = make_uint4(v[cur][4 * j], v[cur][4 * j + 1], v[cur][4 * j + 2], v[cur][4 * j + 3]);
+          *reinterpret_cast<uint4*>(&tile_s[lane * 16 + 4 * (j ^ ((lane >> 1) & 3))]) =
+              make_uint4(v[cur][4 * j], v[cur][4 * j + 1], v[cur][4 * j + 2], v[cur][4 * j + 3]);
         __syncwarp();
         if (sidx + 1 < kSteps) {                   // next step's accumulator slice and residual are in flight during this step's math
           tmem_ld16_nowait(t_base + (sidx + 1) * 16, v[cur ^ 1]);
@@ -302,37 +374,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
           const float bb[4] = {bcol.x, bcol.y, bcol.z, bcol.w};
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            const int row = row_base + i * 8 + sub_r;
-            const float4 a = *reinterpret_cast<const float4*>(&tile_s[(i * 8 + sub_r) * 20 + c4]);
+            const int rl = i * 8 + sub_r;
+            const int row = row_base + rl;
+            const float4 a = *reinterpret_cast<const float4*>(&tile_s[rl * 16 + 4 * ((lane & 3) ^ ((rl >> 1) & 3))]);
             float x[4] = {a.x, a.y, a.z, a.w};
             const float rr[4] = {rres[cur][i].x, rres[cur][i].y, rres[cur][i].z, rres[cur][i].w};
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               float t = fmaf(x[e], ep.scale, bb[e]);
-              if (ACT == 1) t = (OUT == 1) ? gelu_fast(t) : gelu_erf(t);
+              if (ACT == 1) t = gelu_erf(t);
               else if (ACT == 2) t = fmaxf(t, 0.f);
               x[e] = t + rr[e];
             }
             if (row < M) {
-              if (OUT == 0) {
-                float* dst = ep.Cf + (long)row * ep.ldc + col;
-                if (vec_ok) *reinterpret_cast<float4*>(dst) = make_float4(x[0], x[1], x[2], x[3]);
-                else for (int e = 0; e < 4; ++e) if (col + e < N) dst[e] = x[e];
-              } else if (ep.fp16) {
-                f16* dst = reinterpret_cast<f16*>(ep.Cb) + (long)row * ep.ldc + col;
-                if (vec_ok) {
-                  __half2 lo = __floats2half2_rn(x[0], x[1]), hi = __floats2half2_rn(x[2], x[3]);
-                  uint2 u; u.x = *reinterpret_cast<uint32_t*>(&lo); u.y = *reinterpret_cast<uint32_t*>(&hi);
-                  *reinterpret_cast<uint2*>(dst) = u;
-                } else for (int e = 0; e < 4; ++e) if (col + e < N) dst[e] = __float2half_rn(x[e]);
-              } else {
-                bf16* dst = reinterpret_cast<bf16*>(ep.Cb) + (long)row * ep.ldc + col;
-                if (vec_ok) {
-                  __nv_bfloat162 lo = __floats2bfloat162_rn(x[0], x[1]), hi = __floats2bfloat162_rn(x[2], x[3]);
-                  uint2 u; u.x = *reinterpret_cast<uint32_t*>(&lo); u.y = *reinterpret_cast<uint32_t*>(&hi);
-                  *reinterpret_cast<uint2*>(dst) = u;
-                } else for (int e = 0; e < 4; ++e) if (col + e < N) dst[e] = __float2bfloat16_rn(x[e]);
-              }
+              float* dst = ep.Cf + (long)row * ep.ldc + col;
+              if (vec_ok) *reinterpret_cast<float4*>(dst) = make_float4(x[0], x[1], x[2], x[3]);
+              else for (int e = 0; e < 4; ++e) if (col + e < N) dst[e] = x[e];
             }
           }
         }
@@ -340,6 +397,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       }
       tc_fence_before();
       if (lane == 0) mbar_arrive(tempty_bar(buf));
+    }
     }
   }
 
