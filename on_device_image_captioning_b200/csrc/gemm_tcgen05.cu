@@ -251,78 +251,34 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     const int q = warp & 3;                        // TMEM lane quarter this warp may access (hardware: warp id % 4)
     const int hf = (warp - 2) >> 2;                // which half of the tile's columns this warp drains
     int it = 0;
-    if (OUT == 1) {
-      // ---- 16-bit output: straight from the accumulator registers.  Lane == row; every step a lane owns 32
-      // consecutive columns = 64 contiguous bytes (two full 32-B sectors), so no smem transpose is needed.
-      constexpr int kSteps = BN / 64;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-        const int buf = it & 1;
-        const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
-        const int m0 = (tile / n_tiles) * kBM, n0 = (tile % n_tiles) * BN;
-        mbar_wait(tfull_bar(buf), acc_phase);
-        tc_fence_after();
-        const int row = m0 + q * 32 + lane;
-        const int col_base = n0 + hf * (BN / 2);
-        const uint32_t t_base = tmem_base + ((uint32_t)(q * 32) << 16) + buf * Cfg::kAccCols + hf * (BN / 2);
-        uint32_t v[2][32];
-        tmem_ld32_nowait(t_base, v[0]);
-#pragma unroll
-        for (int sidx = 0; sidx < kSteps; ++sidx) {
-          const int cur = sidx & 1;
-          tmem_ld_wait();
-          if (sidx + 1 < kSteps) tmem_ld32_nowait(t_base + (sidx + 1) * 32, v[cur ^ 1]);
-          const int col = col_base + sidx * 32;
-          if ((ep.dbg & 1) || col >= N) continue;
-          const bool full = (col + 31 < N) && ((ep.ldc & 7) == 0);
-          uint32_t pk[16];
-#pragma unroll
-          for (int c = 0; c < 32; c += 2) {
-            float t0 = __uint_as_float(v[cur][c]) * ep.scale, t1 = __uint_as_float(v[cur][c + 1]) * ep.scale;
-            if (ep.bias) {
-              if (col + c < N) t0 += __ldg(ep.bias + col + c);
-              if (col + c + 1 < N) t1 += __ldg(ep.bias + col + c + 1);
-            }
-            if (ACT == 1) { t0 = gelu_fast(t0); t1 = gelu_fast(t1); }
-            else if (ACT == 2) { t0 = fmaxf(t0, 0.f); t1 = fmaxf(t1, 0.f); }
-            if (ep.res && row < M) {
-              if (col + c < N) t0 += ep.res[(long)row * ep.ldr + col + c];
-              if (col + c + 1 < N) t1 += ep.res[(long)row * ep.ldr + col + c + 1];
-            }
-            if (ep.fp16) { __half2 hh = __floats2half2_rn(t0, t1); pk[c >> 1] = *reinterpret_cast<uint32_t*>(&hh); }
-            else { __nv_bfloat162 hh = __floats2bfloat162_rn(t0, t1); pk[c >> 1] = *reinterpret_cast<uint32_t*>(&hh); }
-          }
-          if (row < M) {
-            uint16_t* dst = reinterpret_cast<uint16_t*>(ep.Cb) + (long)row * ep.ldc + col;
-            if (full) {
-#pragma unroll
-              for (int j = 0; j < 4; ++j)
-                *reinterpret_cast<uint4*>(dst + 8 * j) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
-            } else {
-              for (int c = 0; c < 32; ++c)
-                if (col + c < N) dst[c] = (uint16_t)((c & 1) ? (pk[c >> 1] >> 16) : (pk[c >> 1] & 0xffffu));
-            }
-          }
-        }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(tempty_bar(buf));
-      }
-    } else {
-    // ---- fp32 output (+ fp32 residual): transpose 16-column slices through smem for coalesced row segments
+    // Transpose 16-column accumulator slices through smem so that global traffic is coalesced row segments
+    // (direct lane==row stores were measured 30% slower: 32 sectors per store instruction saturate the LSU).
     float* tile_s = staging_gen + (warp - 2) * (32 * 16);
-    const int sub_r = lane >> 2, c4 = (lane & 3) * 4;   // coalesced phase: 8 rows x 4 lanes x float4 per instruction
+    const int sub_r = lane >> 2, c4 = (lane & 3) * 4;   // coalesced phase: 8 rows x 4 lanes x 4 columns per instruction
     constexpr int kSteps = BN / 32;                // 16-column steps per warp
     const bool ld_vec = ((ep.ldc & 3) == 0) && (!ep.res || (ep.ldr & 3) == 0);
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       const int buf = it & 1;
       const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
       const int m0 = (tile / n_tiles) * kBM, n0 = (tile % n_tiles) * BN;
-      mbar_wait(tfull_bar(buf), acc_phase);
-      tc_fence_after();
       const int row_base = m0 + q * 32;
       const int col_base = n0 + hf * (BN / 2);
-      const uint32_t t_base = tmem_base + ((uint32_t)(q * 32) << 16) + buf * Cfg::kAccCols + hf * (BN / 2);
-      uint32_t v[2][16];
+      // this lane's bias values for all steps of the tile, fetched before waiting for the accumulator (the L1 is
+      // carved out for smem, so an in-loop bias load costs an exposed L2 round trip per step: measured 2.5k cycles/step)
+      float4 bcol[kSteps];
+#pragma unroll
+      for (int sidx = 0; sidx < kSteps; ++sidx) {
+        const int col = col_base + sidx * 16 + c4;
+        bcol[sidx] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (ep.bias && col < N) {
+          if (col + 3 < N) bcol[sidx] = *reinterpret_cast<const float4*>(ep.bias + col);
+          else {
+            bcol[sidx].x = ep.bias[col];
+            if (col + 1 < N) bcol[sidx].y = ep.bias[col + 1];
+            if (col + 2 < N) bcol[sidx].z = ep.bias[col + 2];
+          }
+        }
+      }
       float4 rres[2][4];
       auto load_res = [&](int step, float4 (&r)[4]) {
         const int col = col_base + step * 16 + c4;
@@ -342,8 +298,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
           }
         }
       };
+      load_res(0, rres[0]);                        // the residual does not depend on the accumulator either
+      mbar_wait(tfull_bar(buf), acc_phase);
+      tc_fence_after();
+      const uint32_t t_base = tmem_base + ((uint32_t)(q * 32) << 16) + buf * Cfg::kAccCols + hf * (BN / 2);
+      uint32_t v[2][16];
       tmem_ld16_nowait(t_base, v[0]);
-      load_res(0, rres[0]);
 #pragma unroll
       for (int sidx = 0; sidx < kSteps; ++sidx) {
         const int cur = sidx & 1;
@@ -362,16 +322,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         const int col = col_base + sidx * 16 + c4;
         if (!(ep.dbg & 1) && col < N) {
           const bool vec_ok = ld_vec && (col + 3 < N);
-          float4 bcol = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (ep.bias) {
-            if (col + 3 < N) bcol = *reinterpret_cast<const float4*>(ep.bias + col);
-            else {
-              bcol.x = ep.bias[col];
-              if (col + 1 < N) bcol.y = ep.bias[col + 1];
-              if (col + 2 < N) bcol.z = ep.bias[col + 2];
-            }
-          }
-          const float bb[4] = {bcol.x, bcol.y, bcol.z, bcol.w};
+          const float bb[4] = {bcol[sidx].x, bcol[sidx].y, bcol[sidx].z, bcol[sidx].w};
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const int rl = i * 8 + sub_r;
@@ -382,14 +333,31 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               float t = fmaf(x[e], ep.scale, bb[e]);
-              if (ACT == 1) t = gelu_erf(t);
+              if (ACT == 1) t = (OUT == 1) ? gelu_fast(t) : gelu_erf(t);
               else if (ACT == 2) t = fmaxf(t, 0.f);
               x[e] = t + rr[e];
             }
             if (row < M) {
-              float* dst = ep.Cf + (long)row * ep.ldc + col;
-              if (vec_ok) *reinterpret_cast<float4*>(dst) = make_float4(x[0], x[1], x[2], x[3]);
-              else for (int e = 0; e < 4; ++e) if (col + e < N) dst[e] = x[e];
+              if (OUT == 0) {
+                float* dst = ep.Cf + (long)row * ep.ldc + col;
+                if (vec_ok) *reinterpret_cast<float4*>(dst) = make_float4(x[0], x[1], x[2], x[3]);
+                else for (int e = 0; e < 4; ++e) if (col + e < N) dst[e] = x[e];
+              } else {
+                uint32_t lo, hi;
+                if (ep.fp16) {
+                  __half2 a2 = __floats2half2_rn(x[0], x[1]), b2 = __floats2half2_rn(x[2], x[3]);
+                  lo = *reinterpret_cast<uint32_t*>(&a2); hi = *reinterpret_cast<uint32_t*>(&b2);
+                } else {
+                  __nv_bfloat162 a2 = __floats2bfloat162_rn(x[0], x[1]), b2 = __floats2bfloat162_rn(x[2], x[3]);
+                  lo = *reinterpret_cast<uint32_t*>(&a2); hi = *reinterpret_cast<uint32_t*>(&b2);
+                }
+                uint16_t* dst = reinterpret_cast<uint16_t*>(ep.Cb) + (long)row * ep.ldc + col;
+                if (vec_ok) *reinterpret_cast<uint2*>(dst) = make_uint2(lo, hi);
+                else {
+                  const uint16_t h4[4] = {(uint16_t)(lo & 0xffffu), (uint16_t)(lo >> 16), (uint16_t)(hi & 0xffffu), (uint16_t)(hi >> 16)};
+                  for (int e = 0; e < 4; ++e) if (col + e < N) dst[e] = h4[e];
+                }
+              }
             }
           }
         }
@@ -397,7 +365,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       }
       tc_fence_before();
       if (lane == 0) mbar_arrive(tempty_bar(buf));
-    }
     }
   }
 
