@@ -67,6 +67,7 @@ __global__ void __launch_bounds__(256) dyn_exp_step_kernel(DecState s, int layer
   float* sA = tB + P;                          // [n_exp]
   float* sB = sA + n_exp;
   float* red = sB + n_exp;                     // [32]
+  float* part = red + 32;                      // [2][P][P] partial forward-backward products
 
   for (int i = tid; i < np; i += blockDim.x) slot[i] = (i == p || !s.anc) ? r : s.anc[(long)r * P + i];
   __syncthreads();
@@ -74,22 +75,28 @@ __global__ void __launch_bounds__(256) dyn_exp_step_kernel(DecState s, int layer
   const float* cp = crow(p);                   // [cond | key | A | B | sel] of the new position
   const float* Kp = cp + d;
 
-  // ---- phase A: the 2p+1+n_exp new dot products, one warp each
+  // ---- phase A: the 2p+1+n_exp new dot products, 8 lanes each (4 concurrent per warp, 32 per CTA round)
   const int ntask = np + p + n_exp;
-  for (int t = warp; t < ntask; t += (blockDim.x >> 5)) {
-    const float* u;
-    const float* v;
-    if (t < np) { u = cp; v = crow(t) + d; }                       // c_p . K_j
-    else if (t < np + p) { u = crow(t - np); v = Kp; }             // c_i . K_p
-    else { u = qexp + (long)(t - np - p) * d; v = Kp; }            // q_e . K_p
+  const int sub = lane & 7, grp = tid >> 3, ngrp = blockDim.x >> 3;
+  for (int t0 = 0; t0 < ntask; t0 += ngrp) {
+    const int t = t0 + grp;
     float a = 0.f;
-    for (int c = lane * 4; c < d; c += 128) {
-      const float4 x4 = *reinterpret_cast<const float4*>(u + c);
-      const float4 y4 = *reinterpret_cast<const float4*>(v + c);
-      a = fmaf(x4.x, y4.x, a); a = fmaf(x4.y, y4.y, a); a = fmaf(x4.z, y4.z, a); a = fmaf(x4.w, y4.w, a);
+    if (t < ntask) {
+      const float* u;
+      const float* v;
+      if (t < np) { u = cp; v = crow(t) + d; }                       // c_p . K_j
+      else if (t < np + p) { u = crow(t - np); v = Kp; }             // c_i . K_p
+      else { u = qexp + (long)(t - np - p) * d; v = Kp; }            // q_e . K_p
+      for (int c = sub * 4; c < d; c += 32) {
+        const float4 x4 = *reinterpret_cast<const float4*>(u + c);
+        const float4 y4 = *reinterpret_cast<const float4*>(v + c);
+        a = fmaf(x4.x, y4.x, a); a = fmaf(x4.y, y4.y, a); a = fmaf(x4.z, y4.z, a); a = fmaf(x4.w, y4.w, a);
+      }
     }
-    a = warp_sum(a);
-    if (lane == 0) {
+    a += __shfl_xor_sync(0xffffffffu, a, 4);
+    a += __shfl_xor_sync(0xffffffffu, a, 2);
+    a += __shfl_xor_sync(0xffffffffu, a, 1);
+    if (sub == 0 && t < ntask) {
       if (t < np) ck_row[t] = a;
       else if (t < np + p) ck_col[t - np] = a;
       else qkp[t - np - p] = a;
@@ -145,16 +152,22 @@ __global__ void __launch_bounds__(256) dyn_exp_step_kernel(DecState s, int layer
   __syncthreads();
   for (int i = tid; i < np * n_exp; i += blockDim.x) { ab[i] = ab[i] / ta; bb[i] = bb[i] / tb; }
   __syncthreads();
-  // wA[j], wB[j]: thread (j, which)
+  // wA[j] = sum_{i>=j} sum_e ab[(i,e)] * Af_i[e][j]: one task per (which, i, j<=i) pair, then a fixed-order sum over i
+  for (int t = tid; t < 2 * np * np; t += blockDim.x) {
+    const int which = t / (np * np), rem = t % (np * np), i = rem / np, j = rem % np;
+    if (j > i) continue;
+    const float* wsrc = which ? bb : ab;
+    const float* f = (i == p) ? (which ? bf : af)
+                              : s.fw + (((long)layer * P + i) * s.R + slot[i]) * (2L * n_exp * P) + (which ? (long)n_exp * P : 0);
+    float acc = 0.f;
+    for (int e = 0; e < n_exp; ++e) acc = fmaf(wsrc[i * n_exp + e], f[e * P + j], acc);
+    part[(which * P + i) * P + j] = acc;
+  }
+  __syncthreads();
   for (int t = tid; t < 2 * np; t += blockDim.x) {
     const int j = t >> 1, which = t & 1;
-    const float* wsrc = which ? bb : ab;
     float acc = 0.f;
-    for (int i = j; i < np; ++i) {
-      const float* f = (i == p) ? (which ? bf : af)
-                                : s.fw + (((long)layer * P + i) * s.R + slot[i]) * (2L * n_exp * P) + (which ? (long)n_exp * P : 0);
-      for (int e = 0; e < n_exp; ++e) acc = fmaf(wsrc[i * n_exp + e], f[e * P + j], acc);
-    }
+    for (int i = j; i < np; ++i) acc += part[(which * P + i) * P + j];
     (which ? wB : wA)[j] = acc;
   }
   for (int t = tid; t < 2 * np; t += blockDim.x) {       // tA[i] = sum_e ab[(i,e)]
@@ -197,7 +210,7 @@ cudaError_t launch_dyn_exp_step(const DecState& s, int layer, int p, const float
                                 int beam, cudaStream_t st) {
   (void)beam;
   if (s.P > 128 || (d & 3) || n_exp > 64) return cudaErrorInvalidValue;
-  const size_t smem = (size_t)(s.P * 7 + n_exp * 3 + 4 * n_exp * s.P + 32) * sizeof(float);
+  const size_t smem = (size_t)(s.P * 7 + n_exp * 3 + 4 * n_exp * s.P + 32 + 2 * s.P * s.P) * sizeof(float);
   if (smem > 48 * 1024) {
     static size_t configured = 0;
     if (smem > configured) {
@@ -231,6 +244,8 @@ template <> __device__ __forceinline__ void load4<f16>(const f16* p, float (&o)[
   o[0] = __half2float(a.x); o[1] = __half2float(a.y); o[2] = __half2float(b.x); o[3] = __half2float(b.y);
 }
 
+constexpr int kMaxRpi = 8;      // rows (beams) per image handled together
+
 template <typename KvT, typename OutT>
 __global__ void __launch_bounds__(256) cross_attn_step_kernel(const float* __restrict__ q, long ldq,
                                                               const KvT* __restrict__ kv, long ldkv, int k_off,
@@ -239,15 +254,19 @@ __global__ void __launch_bounds__(256) cross_attn_step_kernel(const float* __res
                                                               const int* __restrict__ n_valid,
                                                               const int* __restrict__ row_len, int p) {
   extern __shared__ float sm[];
-  const int b = blockIdx.x, h = blockIdx.y, tid = threadIdx.x;
+  const int b = blockIdx.x, h = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int kt = n + 1;           // K is staged transposed [dk][n+1]: the score loop reads it conflict-free
   float* Kt = sm;                 // [dk][n+1]
   float* Vs = Kt + dk * kt;       // [n][dk]
-  float* qs = Vs + n * dk;        // [dk]
-  float* pr = qs + dk;            // [n]
-  float* red = pr + n;            // [32]
-  float* po = red + 32;           // [blockDim.x] partial outputs
+  float* qs = Vs + n * dk;        // [rpi][dk]
+  float* pr = qs + kMaxRpi * dk;  // [rpi][n]   scores, then probabilities
+  float* po = pr + kMaxRpi * n;   // [parts][rpi][dk] partial outputs
+  const int rpi = rows_per_image;
   const int dk4 = dk >> 2;
+  for (int i = tid; i < rpi * dk; i += blockDim.x) {
+    const int r = b * rpi + i / dk;
+    qs[i] = q[(long)r * ldq + h * dk + (i % dk)];
+  }
   for (int i = tid; i < n * dk4; i += blockDim.x) {
     const int j = i / dk4, c = (i % dk4) * 4;
     const KvT* row = kv + ((long)b * n + j) * ldkv + h * dk + c;
@@ -259,46 +278,62 @@ __global__ void __launch_bounds__(256) cross_attn_step_kernel(const float* __res
   }
   const int nv = n_valid ? n_valid[b] : n;
   const float sq = sqrtf((float)dk);
-  for (int i = 0; i < rows_per_image; ++i) {
-    const int r = b * rows_per_image + i;
-    __syncthreads();
-    for (int c = tid; c < dk; c += blockDim.x) qs[c] = q[(long)r * ldq + h * dk + c];
-    __syncthreads();
-    const bool row_padded = row_len && p >= row_len[r];
-    float lmax = -INFINITY;
-    for (int j = tid; j < n; j += blockDim.x) {
-      float a = 0.f;
-      for (int c = 0; c < dk; ++c) a = fmaf(qs[c], Kt[c * kt + j], a);
-      a = a / sq;
-      if (row_padded || j >= nv) a = kCrossFill;
-      pr[j] = a;
-      lmax = fmaxf(lmax, a);
+  __syncthreads();
+  // scores of all rows in one pass over K (reference layers.py:279-284)
+  for (int j = tid; j < n; j += blockDim.x) {
+    float a[kMaxRpi];
+#pragma unroll
+    for (int i = 0; i < kMaxRpi; ++i) a[i] = 0.f;
+    for (int c = 0; c < dk; ++c) {
+      const float kvv = Kt[c * kt + j];
+#pragma unroll
+      for (int i = 0; i < kMaxRpi; ++i)
+        if (i < rpi) a[i] = fmaf(qs[i * dk + c], kvv, a[i]);
     }
-    const float mx = block_max(lmax, red);
-    float lsum = 0.f;
-    for (int j = tid; j < n; j += blockDim.x) {
-      const float e = expf(pr[j] - mx);
-      pr[j] = e;
-      lsum += e;
+#pragma unroll
+    for (int i = 0; i < kMaxRpi; ++i)
+      if (i < rpi) {
+        float v = a[i] / sq;
+        const bool row_padded = row_len && p >= row_len[b * rpi + i];
+        if (row_padded || j >= nv) v = kCrossFill;
+        pr[i * n + j] = v;
+      }
+  }
+  __syncthreads();
+  // softmax: one warp per row
+  for (int i = warp; i < rpi; i += (blockDim.x >> 5)) {
+    float mx = -INFINITY;
+    for (int j = lane; j < n; j += 32) mx = fmaxf(mx, pr[i * n + j]);
+    mx = warp_max(mx);
+    float sum = 0.f;
+    for (int j = lane; j < n; j += 32) { const float e = expf(pr[i * n + j] - mx); pr[i * n + j] = e; sum += e; }
+    sum = warp_sum(sum);
+    for (int j = lane; j < n; j += 32) pr[i * n + j] = pr[i * n + j] / sum;
+  }
+  __syncthreads();
+  // out[i][c] = sum_j p[i][j] V[j][c]: blockDim/dk partial sums per column, all rows in one pass over V
+  const int parts = blockDim.x / dk;
+  const int c = tid % dk, part = tid / dk;
+  if (part < parts) {
+    float o[kMaxRpi];
+#pragma unroll
+    for (int i = 0; i < kMaxRpi; ++i) o[i] = 0.f;
+    for (int j = part; j < n; j += parts) {
+      const float vv = Vs[j * dk + c];
+#pragma unroll
+      for (int i = 0; i < kMaxRpi; ++i)
+        if (i < rpi) o[i] = fmaf(pr[i * n + j], vv, o[i]);
     }
-    const float sum = block_sum(lsum, red);
-    __syncthreads();
-    for (int j = tid; j < n; j += blockDim.x) pr[j] = pr[j] / sum;
-    __syncthreads();
-    // out[c] = sum_j p_j V[j][c]: blockDim/dk partial sums per output column, combined in a fixed order
-    const int parts = blockDim.x / dk;
-    const int c = tid % dk, part = tid / dk;
-    if (part < parts) {
-      float o = 0.f;
-      for (int j = part; j < n; j += parts) o = fmaf(pr[j], Vs[j * dk + c], o);
-      po[part * dk + c] = o;
-    }
-    __syncthreads();
-    if (tid < dk) {
-      float o = 0.f;
-      for (int pp = 0; pp < parts; ++pp) o += po[pp * dk + tid];
-      out[(long)r * ldo + h * dk + tid] = from_f32<OutT>(o);
-    }
+#pragma unroll
+    for (int i = 0; i < kMaxRpi; ++i)
+      if (i < rpi) po[(part * kMaxRpi + i) * dk + c] = o[i];
+  }
+  __syncthreads();
+  for (int i = tid; i < rpi * dk; i += blockDim.x) {
+    const int ri = i / dk, cc = i % dk;
+    float o = 0.f;
+    for (int pp = 0; pp < parts; ++pp) o += po[(pp * kMaxRpi + ri) * dk + cc];   // fixed order: deterministic
+    out[(long)(b * rpi + ri) * ldo + h * dk + cc] = from_f32<OutT>(o);
   }
 }
 
@@ -306,8 +341,9 @@ template <typename KvT, typename OutT>
 cudaError_t launch_cross_attn_step(const float* q, long ldq, const KvT* kv, long ldkv, int k_off, int v_off,
                                    OutT* out, long ldo, int R, int rows_per_image, int n_keys, int heads, int dk,
                                    const int* n_valid, const int* row_len, int p, cudaStream_t st) {
-  if (R % rows_per_image || (dk & 3) || dk > 256 || (256 % dk)) return cudaErrorInvalidValue;
-  const size_t smem = ((size_t)dk * (n_keys + 1) + (size_t)n_keys * dk + dk + n_keys + 32 + 256) * sizeof(float);
+  if (R % rows_per_image || (dk & 3) || dk > 256 || (256 % dk) || rows_per_image > kMaxRpi) return cudaErrorInvalidValue;
+  const size_t smem = ((size_t)dk * (n_keys + 1) + (size_t)n_keys * dk + (size_t)kMaxRpi * dk + (size_t)kMaxRpi * n_keys +
+                       (size_t)(256 / dk) * kMaxRpi * dk) * sizeof(float);
   static size_t configured = 0;
   if (smem > 48 * 1024 && smem > configured) {
     cudaError_t e = cudaFuncSetAttribute(cross_attn_step_kernel<KvT, OutT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -132,17 +132,20 @@ __device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&v)[3
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-// GELU(erf) with erf from Abramowitz-Stegun 7.1.26 (|abs err| <= 1.5e-7), MUFU rcp/ex2: used when the output is
-// rounded to 16 bits anyway; the fp32 parity mode keeps erff().
+// GELU(erf) with erfc from Abramowitz-Stegun 7.1.26 (|abs err| <= 1.5e-7) arranged for 16 instructions with two
+// MUFU ops (rcp.approx, ex2.approx): used when the output is rounded to 16 bits anyway; the fp32 parity mode keeps
+// erff().   y = erfc(|x|/sqrt2) = poly(t) * exp(-x^2/2), t = 1/(1 + p|x|/sqrt2);   gelu(x) = max(x,0) - |x| * y / 2
 __device__ __forceinline__ float gelu_fast(float x) {
-  const float z = fabsf(x) * 0.70710678118654752440f;
-  const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
+  const float az = fabsf(x) * 0.70710678118654752440f;
+  float t, e;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, az, 1.0f)));
   float pl = fmaf(t, 1.061405429f, -1.453152027f);
   pl = fmaf(pl, t, 1.421413741f);
   pl = fmaf(pl, t, -0.284496736f);
   pl = fmaf(pl, t, 0.254829592f);
-  const float e = 1.0f - pl * t * __expf(-z * z);          // erf(|x|/sqrt2)
-  return 0.5f * x * (1.0f + copysignf(e, x));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(az * az * -1.4426950408889634f));
+  const float hy = (0.5f * x) * (pl * t * e);      // x * erfc(|x|/sqrt2) / 2, carries the sign of x
+  return fmaxf(x, 0.f) - fabsf(hy);
 }
 
 // UMMA shared-memory descriptor, K-major operand, 128-byte swizzle (cute::UMMA::SmemDescriptor):
