@@ -472,6 +472,10 @@ cudaError_t launch_gemm_tc(const TcGemmArgs& p, cudaStream_t st) {
     if (best_waste < 0 || waste < best_waste) { best = bn; best_waste = waste; }
   }
   if (p.act < 0 || p.act > 2) return cudaErrorInvalidValue;
+  // skinny problems (decoder steps, M = images x beam): few tiles, so prefer narrow tiles -- more CTAs in flight and
+  // a shorter serial epilogue per CTA
+  const long tiles256 = (long)((p.M + kBM - 1) / kBM) * ((p.N + 255) / 256);
+  if (tiles256 * 2 <= sm_count()) best = 128;
   if (best == 256) return launch_tc_bn<256>(p, st);
   if (best == 192) return launch_tc_bn<192>(p, st);
   return launch_tc_bn<128>(p, st);
