@@ -248,11 +248,12 @@ __global__ void __launch_bounds__(256) se_group_sum_kernel(const float* __restri
   }
 }
 
+template <typename WT>
 __global__ void __launch_bounds__(256) se_weights_kernel(const float* __restrict__ z, const int* __restrict__ n_valid,
                                                          const int* __restrict__ gstart, int n_groups,
-                                                         const float* __restrict__ gsum, float* __restrict__ a_fw,
-                                                         float* __restrict__ b_fw, float* __restrict__ a_bw,
-                                                         float* __restrict__ b_bw, int E, int N, int chunk) {
+                                                         const float* __restrict__ gsum, WT* __restrict__ a_fw,
+                                                         WT* __restrict__ b_fw, WT* __restrict__ a_bw,
+                                                         WT* __restrict__ b_bw, int E, int N, int chunk) {
   extern __shared__ float zt[];            // [chunk][N]
   const int b = blockIdx.x, e0 = blockIdx.y * chunk;
   const int nv = n_valid ? n_valid[b] : N;
@@ -271,13 +272,13 @@ __global__ void __launch_bounds__(256) se_weights_kernel(const float* __restrict
     }
     sa = warp_sum(sa) + kExpEps;
     sb = warp_sum(sb) + kExpEps;
-    float* ao = a_fw + ((long)b * E + e0 + e) * N;
-    float* bo = b_fw + ((long)b * E + e0 + e) * N;
+    WT* ao = a_fw + ((long)b * E + e0 + e) * N;
+    WT* bo = b_fw + ((long)b * E + e0 + e) * N;
     for (int n = lane; n < N; n += 32) {
       const float v = zt[e * N + n];
       const bool ok = n < nv;
-      ao[n] = ok ? fmaxf(v, 0.f) / sa : 0.f;
-      bo[n] = ok ? fmaxf(-v, 0.f) / sb : 0.f;
+      ao[n] = from_f32<WT>(ok ? fmaxf(v, 0.f) / sa : 0.f);
+      bo[n] = from_f32<WT>(ok ? fmaxf(-v, 0.f) / sb : 0.f);
     }
   }
   const float* ga = gsum + (((long)b * n_groups + g) * 2 + 0) * N;
@@ -286,42 +287,51 @@ __global__ void __launch_bounds__(256) se_weights_kernel(const float* __restrict
     const int e = i % chunk, n = i / chunk;
     const float v = zt[e * N + n];
     const long o = ((long)b * N + n) * E + e0 + e;
-    a_bw[o] = fmaxf(v, 0.f) / (ga[n] + kExpEps);
-    b_bw[o] = fmaxf(-v, 0.f) / (gb[n] + kExpEps);
+    a_bw[o] = from_f32<WT>(fmaxf(v, 0.f) / (ga[n] + kExpEps));
+    b_bw[o] = from_f32<WT>(fmaxf(-v, 0.f) / (gb[n] + kExpEps));
   }
 }
 
+template <typename WT>
 cudaError_t launch_static_exp_weights(const float* z, const int* n_valid, const int* group_start, int n_groups,
-                                      float* a_fw, float* b_fw, float* a_bw, float* b_bw, float* gsum_scratch,
+                                      WT* a_fw, WT* b_fw, WT* a_bw, WT* b_bw, float* gsum_scratch,
                                       int B, int E, int N, int chunk, cudaStream_t st) {
   // `chunk` rows of z per CTA; it must divide every group boundary (the engine picks the gcd, <= 32)
   if (chunk <= 0 || (E % chunk)) return cudaErrorInvalidValue;
   se_group_sum_kernel<<<dim3(B, n_groups), 160, 0, st>>>(z, group_start, gsum_scratch, E, N, n_groups);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
-  se_weights_kernel<<<dim3(B, E / chunk), 256, (size_t)chunk * N * sizeof(float), st>>>(
+  se_weights_kernel<WT><<<dim3(B, E / chunk), 256, (size_t)chunk * N * sizeof(float), st>>>(
       z, n_valid, group_start, n_groups, gsum_scratch, a_fw, b_fw, a_bw, b_bw, E, N, chunk);
   return cudaGetLastError();
 }
+template cudaError_t launch_static_exp_weights<float>(const float*, const int*, const int*, int, float*, float*, float*, float*, float*, int, int, int, int, cudaStream_t);
+template cudaError_t launch_static_exp_weights<bf16>(const float*, const int*, const int*, int, bf16*, bf16*, bf16*, bf16*, float*, int, int, int, int, cudaStream_t);
+template cudaError_t launch_static_exp_weights<f16>(const float*, const int*, const int*, int, f16*, f16*, f16*, f16*, float*, int, int, int, int, cudaStream_t);
 
 // x_out = x_in + sigmoid(sel)*a + (1-sigmoid(sel))*b     (reference layers.py:98-102,118-120)
-__global__ void selector_mix_kernel(const float* __restrict__ xi, long ldxi, const float* __restrict__ sel, long lds,
+template <typename ST>
+__global__ void selector_mix_kernel(const float* __restrict__ xi, long ldxi, const ST* __restrict__ sel, long lds,
                                     const float* __restrict__ a, const float* __restrict__ bb, long ldo,
                                     float* __restrict__ xo, long ldxo, long rows, int d) {
   const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= rows * d) return;
   const long r = i / d;
   const int c = (int)(i % d);
-  const float s = sigmoidf_(sel[r * lds + c]);
+  const float s = sigmoidf_(to_f32<ST>(sel[r * lds + c]));
   xo[r * ldxo + c] = xi[r * ldxi + c] + (s * a[r * ldo + c] + (1.0f - s) * bb[r * ldo + c]);
 }
-cudaError_t launch_selector_mix(const float* x_in, long ldxi, const float* sel, long lds, const float* out_a,
+template <typename ST>
+cudaError_t launch_selector_mix(const float* x_in, long ldxi, const ST* sel, long lds, const float* out_a,
                                 const float* out_b, long ldo, float* x_out, long ldxo, long rows, int d,
                                 cudaStream_t st) {
   const long n = rows * d;
-  selector_mix_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(x_in, ldxi, sel, lds, out_a, out_b, ldo, x_out,
-                                                                  ldxo, rows, d);
+  selector_mix_kernel<ST><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(x_in, ldxi, sel, lds, out_a, out_b, ldo, x_out,
+                                                                      ldxo, rows, d);
   return cudaGetLastError();
 }
+template cudaError_t launch_selector_mix<float>(const float*, long, const float*, long, const float*, const float*, long, float*, long, long, int, cudaStream_t);
+template cudaError_t launch_selector_mix<bf16>(const float*, long, const bf16*, long, const float*, const float*, long, float*, long, long, int, cudaStream_t);
+template cudaError_t launch_selector_mix<f16>(const float*, long, const f16*, long, const float*, const float*, long, float*, long, long, int, cudaStream_t);
 
 }  // namespace xn

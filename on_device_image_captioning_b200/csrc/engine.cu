@@ -44,7 +44,7 @@ struct SwinStageW {
   const float *mg = nullptr, *mb = nullptr;
   LinW red;
 };
-struct EncLayerW { const float *n1g, *n1b, *n2g, *n2b, *qexp, *bexp; LinW kabs, ff1, ff2; };
+struct EncLayerW { const float *n1g, *n1b, *n2g, *n2b, *qexp, *bexp; const void* qexp16; LinW kabs, ff1, ff2; };
 struct DecLayerW { const float *n1g, *n1b, *n2g, *n2b, *n3g, *n3b, *qexp, *bexp; LinW dyn5, wq, wo, ff1, ff2; };
 
 struct Arena {
@@ -312,9 +312,9 @@ size_t enc_ws_bytes(const xn_config& c, int Bc) {
   return f * 4 + Bc * 4 + 40 * 256;
 }
 
-// T = float: everything fp32 (parity mode).  T = bf16/f16: the plain Linear layers (input_linear, the fused
-// key|class_a|class_b|selector projection, FF, reduce group) run on tcgen05 with 16-bit operands; the per-image
-// expansion contractions (z, class, out) and all normalisations stay fp32.
+// T = float: everything fp32 (parity mode; CUDA-core GEMMs).  T = bf16/f16: the Linear layers run on tcgen05, the
+// per-image expansion contractions (z, class, out) on the batched mma.sync kernel, all with 16-bit operands and fp32
+// accumulation; normalisations, sums and the residual stream stay fp32.
 template <typename T>
 int enc_body_chunk(xn_handle* h, const float* feats, int Bc, const int* n_valid_dev, float* out, cudaStream_t st) {
   constexpr bool kF32 = std::is_same<T, float>::value;
@@ -324,14 +324,14 @@ int enc_body_chunk(xn_handle* h, const float* feats, int Bc, const int* n_valid_
   float* xcat = h->ws.get<float>((size_t)M * d * ne);
   T* xn = h->ws.get<T>((size_t)M * std::max(d, c.feat_dim));
   T* xcat16 = kF32 ? nullptr : h->ws.get<T>((size_t)M * d * ne);
-  float* kabs = h->ws.get<float>((size_t)M * 4 * d);
+  T* kabs = h->ws.get<T>((size_t)M * 4 * d);            // [key | class_a | class_b | selector] projections
   float* z = h->ws.get<float>((size_t)Bc * E * N);
-  float* afw = h->ws.get<float>((size_t)Bc * E * N);
-  float* bfw = h->ws.get<float>((size_t)Bc * E * N);
-  float* abw = h->ws.get<float>((size_t)Bc * E * N);
-  float* bbw = h->ws.get<float>((size_t)Bc * E * N);
-  float* CA = h->ws.get<float>((size_t)Bc * E * d);
-  float* CB = h->ws.get<float>((size_t)Bc * E * d);
+  T* afw = h->ws.get<T>((size_t)Bc * E * N);
+  T* bfw = h->ws.get<T>((size_t)Bc * E * N);
+  T* abw = h->ws.get<T>((size_t)Bc * E * N);
+  T* bbw = h->ws.get<T>((size_t)Bc * E * N);
+  T* CA = h->ws.get<T>((size_t)Bc * E * d);
+  T* CB = h->ws.get<T>((size_t)Bc * E * d);
   float* oA = h->ws.get<float>((size_t)M * d);
   float* oB = h->ws.get<float>((size_t)M * d);
   T* hid = h->ws.get<T>((size_t)M * c.ff);
@@ -340,17 +340,12 @@ int enc_body_chunk(xn_handle* h, const float* feats, int Bc, const int* n_valid_
   WS_CHECK();
   const long ldc = (long)d * ne;
   const int fp16 = std::is_same<T, f16>::value;
-  // y(fp32) = x W^T + b (+res)
-  auto lin_out32 = [&](const float* x32, const T* x16, long ldx, const LinW& w, const float* res, long ldr, float* y, long ldy) -> int {
-    if (kF32) return lin_f32(h, x32, ldx, w, res, ldr, y, ldy, M, 0, st);
-    return lin_tc(h, x16, ldx, w, res, ldr, y, nullptr, ldy, M, 0, fp16, st);
-  };
 
   if (kF32) {
-    if (int r = lin_out32(feats, nullptr, c.feat_dim, h->input_linear, nullptr, 0, x0, d)) return r;
+    if (int r = lin_f32(h, feats, c.feat_dim, h->input_linear, nullptr, 0, x0, d, M, 0, st)) return r;
   } else {
     KL(1, launch_cast<T>(feats, xn, (long)M * c.feat_dim, st));
-    if (int r = lin_out32(nullptr, xn, c.feat_dim, h->input_linear, nullptr, 0, x0, d)) return r;
+    if (int r = lin_tc(h, xn, c.feat_dim, h->input_linear, nullptr, 0, x0, nullptr, d, M, 0, fp16, st)) return r;
   }
   for (int l = 0; l < ne; ++l) {
     const EncLayerW& W = h->enc[l];
@@ -358,36 +353,71 @@ int enc_body_chunk(xn_handle* h, const float* feats, int Bc, const int* n_valid_
     const long ldi = l == 0 ? d : ldc;
     float* xout = xcat + (size_t)l * d;
     KL(1, launch_layernorm<T>(xin, ldi, W.n1g, W.n1b, xn, d, M, d, st));
-    if (int r = lin_out32(reinterpret_cast<const float*>(xn), xn, d, W.kabs, nullptr, 0, kabs, 4 * d)) return r;
-    GemmArgs g{};
-    // z[b] = Q (E x d) . key[b]^T / sqrt(d)            reference layers.py:52
-    g.A = W.qexp; g.lda = d; g.sA = 0;
-    g.W = kabs; g.ldw = 4 * d; g.sW = (long)N * 4 * d; g.w_kn = 0;
-    g.C = z; g.ldc = N; g.sC = (long)E * N;
-    g.M = E; g.N = N; g.K = d; g.batch = Bc; g.div = sqrtf((float)d); g.act = 0;
-    KL(1, launch_gemm_f32(g, st));
-    KL(2, launch_static_exp_weights(z, n_valid_dev, h->group_start_dev, c.n_exp_groups, afw, bfw, abw, bbw, gs, Bc, E, N,
-                                    h->exp_chunk, st));
-    // class_a = a_fw . A + bias_exp ; class_b = b_fw . B + bias_exp      layers.py:62-63
-    for (int ab = 0; ab < 2; ++ab) {
-      GemmArgs q{};
-      q.A = ab ? bfw : afw; q.lda = N; q.sA = (long)E * N;
-      q.W = kabs + (size_t)(1 + ab) * d; q.ldw = 4 * d; q.sW = (long)N * 4 * d; q.w_kn = 1;
-      q.C = ab ? CB : CA; q.ldc = d; q.sC = (long)E * d;
-      q.res = W.bexp; q.ldr = d; q.sR = 0;
-      q.M = E; q.N = d; q.K = N; q.batch = Bc;
-      KL(1, launch_gemm_f32(q, st));
+    if (kF32) {
+      const float* xn32 = reinterpret_cast<const float*>(xn);
+      float* k32 = reinterpret_cast<float*>(kabs);
+      float* afw32 = reinterpret_cast<float*>(afw); float* bfw32 = reinterpret_cast<float*>(bfw);
+      float* abw32 = reinterpret_cast<float*>(abw); float* bbw32 = reinterpret_cast<float*>(bbw);
+      float* CA32 = reinterpret_cast<float*>(CA); float* CB32 = reinterpret_cast<float*>(CB);
+      if (int r = lin_f32(h, xn32, d, W.kabs, nullptr, 0, k32, 4 * d, M, 0, st)) return r;
+      GemmArgs g{};
+      // z[b] = Q (E x d) . key[b]^T / sqrt(d)            reference layers.py:52
+      g.A = W.qexp; g.lda = d; g.sA = 0;
+      g.W = k32; g.ldw = 4 * d; g.sW = (long)N * 4 * d; g.w_kn = 0;
+      g.C = z; g.ldc = N; g.sC = (long)E * N;
+      g.M = E; g.N = N; g.K = d; g.batch = Bc; g.div = sqrtf((float)d); g.act = 0;
+      KL(1, launch_gemm_f32(g, st));
+      KL(2, launch_static_exp_weights<float>(z, n_valid_dev, h->group_start_dev, c.n_exp_groups, afw32, bfw32, abw32, bbw32, gs,
+                                             Bc, E, N, h->exp_chunk, st));
+      // class_a = a_fw . A + bias_exp ; class_b = b_fw . B + bias_exp      layers.py:62-63
+      for (int ab = 0; ab < 2; ++ab) {
+        GemmArgs q{};
+        q.A = ab ? bfw32 : afw32; q.lda = N; q.sA = (long)E * N;
+        q.W = k32 + (size_t)(1 + ab) * d; q.ldw = 4 * d; q.sW = (long)N * 4 * d; q.w_kn = 1;
+        q.C = ab ? CB32 : CA32; q.ldc = d; q.sC = (long)E * d;
+        q.res = W.bexp; q.ldr = d; q.sR = 0;
+        q.M = E; q.N = d; q.K = N; q.batch = Bc;
+        KL(1, launch_gemm_f32(q, st));
+      }
+      // out = bw . class / n_groups                                          layers.py:82-83
+      for (int ab = 0; ab < 2; ++ab) {
+        GemmArgs q{};
+        q.A = ab ? bbw32 : abw32; q.lda = E; q.sA = (long)N * E;
+        q.W = ab ? CB32 : CA32; q.ldw = d; q.sW = (long)E * d; q.w_kn = 1;
+        q.C = ab ? oB : oA; q.ldc = d; q.sC = (long)N * d;
+        q.M = N; q.N = d; q.K = E; q.batch = Bc; q.div = (float)c.n_exp_groups;
+        KL(1, launch_gemm_f32(q, st));
+      }
+      KL(1, launch_selector_mix<float>(xin, ldi, k32 + 3 * (size_t)d, 4 * d, oA, oB, d, xout, ldc, M, d, st));
+    } else {
+      if (int r = lin_tc(h, xn, d, W.kabs, nullptr, 0, nullptr, kabs, 4 * d, M, 0, fp16, st)) return r;
+      Mma16Args g{};
+      g.A = W.qexp16; g.lda = d; g.sA = 0;
+      g.B = kabs; g.ldb = 4 * d; g.sB = (long)N * 4 * d; g.b_kn = 0;
+      g.C = z; g.ldc = N; g.sC = (long)E * N;
+      g.M = E; g.N = N; g.K = d; g.batch = Bc; g.scale = 1.0f / sqrtf((float)d);
+      KL(1, (launch_gemm_mma16<T, float>(g, st)));
+      KL(2, launch_static_exp_weights<T>(z, n_valid_dev, h->group_start_dev, c.n_exp_groups, afw, bfw, abw, bbw, gs, Bc, E, N,
+                                         h->exp_chunk, st));
+      for (int ab = 0; ab < 2; ++ab) {
+        Mma16Args q{};
+        q.A = ab ? bfw : afw; q.lda = N; q.sA = (long)E * N;
+        q.B = kabs + (size_t)(1 + ab) * d; q.ldb = 4 * d; q.sB = (long)N * 4 * d; q.b_kn = 1;
+        q.C = ab ? CB : CA; q.ldc = d; q.sC = (long)E * d;
+        q.res = W.bexp; q.ldr = d; q.sR = 0;
+        q.M = E; q.N = d; q.K = N; q.batch = Bc; q.scale = 1.0f;
+        KL(1, (launch_gemm_mma16<T, T>(q, st)));
+      }
+      for (int ab = 0; ab < 2; ++ab) {
+        Mma16Args q{};
+        q.A = ab ? bbw : abw; q.lda = E; q.sA = (long)N * E;
+        q.B = ab ? CB : CA; q.ldb = d; q.sB = (long)E * d; q.b_kn = 1;
+        q.C = ab ? oB : oA; q.ldc = d; q.sC = (long)N * d;
+        q.M = N; q.N = d; q.K = E; q.batch = Bc; q.scale = 1.0f / (float)c.n_exp_groups;
+        KL(1, (launch_gemm_mma16<T, float>(q, st)));
+      }
+      KL(1, launch_selector_mix<T>(xin, ldi, kabs + 3 * (size_t)d, 4 * d, oA, oB, d, xout, ldc, M, d, st));
     }
-    // out = bw . class / n_groups                                          layers.py:82-83
-    for (int ab = 0; ab < 2; ++ab) {
-      GemmArgs q{};
-      q.A = ab ? bbw : abw; q.lda = E; q.sA = (long)N * E;
-      q.W = ab ? CB : CA; q.ldw = d; q.sW = (long)E * d; q.w_kn = 1;
-      q.C = ab ? oB : oA; q.ldc = d; q.sC = (long)N * d;
-      q.M = N; q.N = d; q.K = E; q.batch = Bc; q.div = (float)c.n_exp_groups;
-      KL(1, launch_gemm_f32(q, st));
-    }
-    KL(1, launch_selector_mix(xin, ldi, kabs + 3 * (size_t)d, 4 * d, oA, oB, d, xout, ldc, M, d, st));
     KL(1, launch_layernorm<T>(xout, ldc, W.n2g, W.n2b, xn, d, M, d, st));
     if (kF32) {
       if (int r = lin_f32(h, reinterpret_cast<const float*>(xn), d, W.ff1, nullptr, 0, reinterpret_cast<float*>(hid), c.ff, M, 2, st)) return r;
@@ -890,7 +920,13 @@ int xn_finalize_weights(xn_handle* h, int precision) {
     W.ff1 = lin(q + "ff.linear_1", ff, d); W.ff2 = lin(q + "ff.linear_2", d, ff);
     if (rc) return rc;
     if (concat(parts, W.kabs)) return XN_ERR_CUDA;
-    if (precision != XN_PREC_FP32 && (to_bf16(W.kabs) || to_bf16(W.ff1) || to_bf16(W.ff2))) return XN_ERR_CUDA;
+    W.qexp16 = nullptr;
+    if (precision != XN_PREC_FP32) {
+      if (to_bf16(W.kabs) || to_bf16(W.ff1) || to_bf16(W.ff2)) return XN_ERR_CUDA;
+      LinW qe; qe.w = W.qexp; qe.N = (int)E; qe.K = (int)d;       // 16-bit copy of the expansion queries (left operand of z)
+      if (to_bf16(qe)) return XN_ERR_CUDA;
+      W.qexp16 = qe.wb;
+    }
     h->enc.push_back(W);
   }
   std::vector<LinW> kvparts;

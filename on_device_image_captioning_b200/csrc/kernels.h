@@ -44,6 +44,20 @@ cudaError_t launch_gemm_tc(const TcGemmArgs& p, cudaStream_t st);
 bool tc_gemm_supported(int M, int N, int K);
 void set_tc_debug(int v);   // timing experiments (see TcEpilogue::dbg)
 
+// ---------------------------------------------------------------- batched 16-bit GEMM (mma.sync path)
+// C[b] = scale * A[b] . op(B[b]) + res[b];  A (M x K) K-contiguous;  B (N x K) K-contiguous [b_kn=0] or (K x N) [b_kn=1]
+struct Mma16Args {
+  const void* A; long lda, sA;
+  const void* B; long ldb, sB;
+  void* C; long ldc, sC;
+  const float* res; long ldr, sR;
+  int M, N, K, batch;
+  float scale;
+  int b_kn;
+};
+template <typename T, typename OutT>
+cudaError_t launch_gemm_mma16(const Mma16Args& p, cudaStream_t st);
+
 // ---------------------------------------------------------------- normalisation / embedding
 template <typename OutT>
 cudaError_t launch_layernorm(const float* x, long ldx, const float* gamma, const float* beta, OutT* y, long ldy,
@@ -74,11 +88,13 @@ cudaError_t launch_transpose_bias(const float* table, float* out, int heads, cud
 // ---------------------------------------------------------------- static expansion (encoder)
 // z (B, E, N) raw scores (already / sqrt(d)).  Produces forward weights (B,E,N) normalised over
 // the N keys (keys >= n_valid[b] masked) and backward weights (B,N,E) normalised per group.
+template <typename WT>
 cudaError_t launch_static_exp_weights(const float* z, const int* n_valid, const int* group_start, int n_groups,
-                                      float* a_fw, float* b_fw, float* a_bw, float* b_bw, float* gsum_scratch,
+                                      WT* a_fw, WT* b_fw, WT* a_bw, WT* b_bw, float* gsum_scratch,
                                       int B, int E, int N, int chunk, cudaStream_t st);
 // x_out = x_in + sigmoid(sel) * out_a + (1 - sigmoid(sel)) * out_b
-cudaError_t launch_selector_mix(const float* x_in, long ldxi, const float* sel, long lds, const float* out_a,
+template <typename ST>
+cudaError_t launch_selector_mix(const float* x_in, long ldxi, const ST* sel, long lds, const float* out_a,
                                 const float* out_b, long ldo, float* x_out, long ldxo, long rows, int d,
                                 cudaStream_t st);
 
