@@ -8,9 +8,10 @@
 // (reference models/swin_transformer_mod.py:214-216,229-233,270 qkv/proj; :109-119 fc1/fc2;
 // :479,499 patch-merging reduction).
 //
-// CTA = 10 warps: warp 0  TMA producer (one elected lane)
+// CTA = 18 warps: warp 0  TMA producer (one elected lane)
 //                 warp 1  TMEM allocator + MMA issuer (one elected lane)
-//                 warps 2-9  epilogue (two per TMEM lane quarter, half of the columns each):
+//                 warps 2-17 epilogue (four per TMEM lane quarter, a quarter of the columns each; the epilogue is
+//                            latency-bound per warp, so it wants many warps in flight):
 //                            tcgen05.ld (16 columns, double-buffered) -> smem transpose -> fused
 //                            bias/GELU/residual (residual prefetched one step ahead) -> coalesced stores
 // Pipelines: a kStages-deep smem ring (full/empty mbarriers, TMA <-> MMA) and a 2-deep TMEM
@@ -28,18 +29,19 @@ namespace xn {
 constexpr int kBM = 128;
 constexpr int kBK = 64;                       // bf16 elements = 128 bytes = swizzle span
 constexpr int kUmmaK = 16;
-constexpr int kEpiWarps = 8;                  // 2 per TMEM lane quarter, each draining half of the tile's columns
+constexpr int kEpiWarps = 16;                 // 4 per TMEM lane quarter, each draining a quarter of the tile's columns
 constexpr int kTcThreads = 64 + 32 * kEpiWarps;
 constexpr uint32_t kABytes = kBM * kBK * 2;   // 16 KB
 
 template <int BN> struct TcCfg {
   static constexpr uint32_t kBBytes = BN * kBK * 2;
   static constexpr uint32_t kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (BN == 256) ? 4 : (BN == 192 ? 5 : 6);
+  static constexpr int kStages = (BN == 128) ? 6 : 4;
   static constexpr uint32_t kAccCols = 256;                 // column stride between the two accumulators
   static constexpr uint32_t kTmemCols = 512;
   static constexpr uint32_t kStagingBytes = kEpiWarps * 32 * 16 * 4;   // per epilogue warp: 32 rows x 16 floats, XOR-swizzled 16-B slots
   static constexpr uint32_t kSmemBytes = kStages * kStageBytes + kStagingBytes + 256 + 1024;
+  static_assert(kSmemBytes <= 232448, "exceeds the 227 KB dynamic shared memory limit");
 };
 
 struct TcEpilogue {
@@ -252,20 +254,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     }
   } else {
     const int q = warp & 3;                        // TMEM lane quarter this warp may access (hardware: warp id % 4)
-    const int hf = (warp - 2) >> 2;                // which half of the tile's columns this warp drains
+    const int hf = (warp - 2) >> 2;                // which quarter of the tile's columns this warp drains
     int it = 0;
     // Transpose 16-column accumulator slices through smem so that global traffic is coalesced row segments
     // (direct lane==row stores were measured 30% slower: 32 sectors per store instruction saturate the LSU).
     float* tile_s = staging_gen + (warp - 2) * (32 * 16);
     const int sub_r = lane >> 2, c4 = (lane & 3) * 4;   // coalesced phase: 8 rows x 4 lanes x 4 columns per instruction
-    constexpr int kSteps = BN / 32;                // 16-column steps per warp
+    constexpr int kColsPerWarp = BN / (kEpiWarps / 4);
+    constexpr int kSteps = kColsPerWarp / 16;      // 16-column steps per warp
     const bool ld_vec = ((ep.ldc & 3) == 0) && (!ep.res || (ep.ldr & 3) == 0);
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       const int buf = it & 1;
       const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
       const int m0 = (tile / n_tiles) * kBM, n0 = (tile % n_tiles) * BN;
       const int row_base = m0 + q * 32;
-      const int col_base = n0 + hf * (BN / 2);
+      const int col_base = n0 + hf * kColsPerWarp;
       // this lane's bias values for all steps of the tile, fetched before waiting for the accumulator (the L1 is
       // carved out for smem, so an in-loop bias load costs an exposed L2 round trip per step: measured 2.5k cycles/step)
       float4 bcol[kSteps];
@@ -304,7 +307,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       load_res(0, rres[0]);                        // the residual does not depend on the accumulator either
       mbar_wait(tfull_bar(buf), acc_phase);
       tc_fence_after();
-      const uint32_t t_base = tmem_base + ((uint32_t)(q * 32) << 16) + buf * Cfg::kAccCols + hf * (BN / 2);
+      const uint32_t t_base = tmem_base + ((uint32_t)(q * 32) << 16) + buf * Cfg::kAccCols + hf * kColsPerWarp;
       uint32_t v[2][16];
       tmem_ld16_nowait(t_base, v[0]);
 #pragma unroll
@@ -340,6 +343,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
               else if (ACT == 2) t = fmaxf(t, 0.f);
               x[e] = t + rr[e];
             }
+            if ((ep.dbg & 8) && x[0] != 1234567.f) continue;     // timing experiment: all the math, no global stores
             if (row < M) {
               if (OUT == 0) {
                 float* dst = ep.Cf + (long)row * ep.ldc + col;
