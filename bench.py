@@ -140,8 +140,16 @@ def run_ours(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+
+    def note(msg):
+        if args.verbose:
+            print(f"[bench rank {rank}] {msg} (+{time.perf_counter() - t_begin:.1f}s)", file=sys.stderr, flush=True)
+
+    t_begin = time.perf_counter()
     if world > 1:
+        torch.set_num_threads(max(1, (os.cpu_count() or 8) // world))   # torchrun pins OMP_NUM_THREADS=1: weight synthesis is CPU work
         dist.init_process_group("nccl", device_id=dev)
+        note("process group up")
 
     cfg = C.swin_l_384()
     eng = Engine(cfg, local)
@@ -165,9 +173,12 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    note("weights loaded, inputs resident")
     for i in range(args.warmup):
         step(i)
+        note(f"warm-up step {i} enqueued")
     barrier()
+    note("warm-up done")
     sampler = ClockSampler(local)
     sampler.start()
     l0 = eng.kernel_launches
@@ -179,6 +190,7 @@ def run_ours(args):
     barrier()
     launches = eng.kernel_launches - l0
     ms = e0.elapsed_time(e1)
+    note(f"timed region done: {ms:.1f} ms")
     sampler.stop_flag.set()
     t = torch.tensor([ms], device=dev, dtype=torch.float64)
     if world > 1:
@@ -278,6 +290,7 @@ def main():
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--swin-chunk", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--verbose", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
