@@ -125,7 +125,7 @@ def run_reference(args):
                                   sample=f"{n} synthetic 384x384 images per step, oracle/xnv2_oracle.py (torch CPU fp32, "
                                          "reference algorithm: whole-prefix re-decode)"),
                 e2e=dict(value=val, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
@@ -273,14 +273,32 @@ def run_ours(args):
                                        sample="2 synthetic 384x384 images, beam 3, max_len 20, oracle/xnv2_oracle.py (torch CPU fp32, "
                                               f"{threads} threads), {cpu_dt:.1f} s") if cpu_v else None),
                     latency_batch1=lat, clocks=clocks)
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     return 0
 
 
+_REAL_STDOUT = None
+
+
+def _claim_stdout():
+    """Libraries (NCCL prints its version banner) may write to fd 1; the contract wants exactly one JSON line on
+    stdout, so fd 1 is pointed at stderr for the run and the JSON goes to the saved descriptor."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+
+def emit(line: dict):
+    _REAL_STDOUT.write(json.dumps(line) + "\n")
+    _REAL_STDOUT.flush()
+
+
 def main():
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
