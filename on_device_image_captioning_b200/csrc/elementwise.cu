@@ -36,9 +36,44 @@ __device__ __forceinline__ void store4<f16>(f16* p, float a, float b, float c, f
   *reinterpret_cast<uint2*>(p) = u;
 }
 
+// One warp per row.  The row is read from global memory once and held in registers (up to kLnMaxV float4 per lane,
+// i.e. C <= 128*kLnMaxV); wider rows fall back to re-reading (L1-resident).  Two-pass mean / variance in fp32.
+constexpr int kLnMaxV = 12;
+
 template <typename OutT, typename SrcFn>
 __device__ __forceinline__ void ln_row(SrcFn src, const float* __restrict__ g, const float* __restrict__ b,
                                        OutT* __restrict__ yr, int C, int lane) {
+  if (C <= 128 * kLnMaxV) {
+    float4 v[kLnMaxV];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < kLnMaxV; ++i) {
+      const int c = lane * 4 + i * 128;
+      if (c < C) { v[i] = src(c); s += (v[i].x + v[i].y) + (v[i].z + v[i].w); }
+    }
+    const float mean = warp_sum(s) / (float)C;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < kLnMaxV; ++i) {
+      const int c = lane * 4 + i * 128;
+      if (c < C) {
+        const float d0 = v[i].x - mean, d1 = v[i].y - mean, d2 = v[i].z - mean, d3 = v[i].w - mean;
+        q += (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
+      }
+    }
+    const float rstd = 1.0f / sqrtf(warp_sum(q) / (float)C + kLnEps);
+#pragma unroll
+    for (int i = 0; i < kLnMaxV; ++i) {
+      const int c = lane * 4 + i * 128;
+      if (c < C) {
+        const float4 gg = *reinterpret_cast<const float4*>(g + c);
+        const float4 bb = *reinterpret_cast<const float4*>(b + c);
+        store4<OutT>(yr + c, (v[i].x - mean) * rstd * gg.x + bb.x, (v[i].y - mean) * rstd * gg.y + bb.y,
+                     (v[i].z - mean) * rstd * gg.z + bb.z, (v[i].w - mean) * rstd * gg.w + bb.w);
+      }
+    }
+    return;
+  }
   float s = 0.f;
   for (int c = lane * 4; c < C; c += 128) {
     const float4 v = src(c);
@@ -161,30 +196,44 @@ __global__ void __launch_bounds__(256) patch_embed_kernel(const float* __restric
           *reinterpret_cast<const float4*>(&img[(((long)b * Cin + c) * S + (py * P + dy)) * S + x4]);
     }
     __syncthreads();
-    for (int px = warp; px < G; px += nw) {
-      float acc[8];
+    constexpr int PB = 4;                  // patches per warp pass: each filter tap is read from smem once for PB patches
+    for (int px0 = warp * PB; px0 < G; px0 += nw * PB) {
+      float acc[PB][8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) acc[j] = bia[j];
-      const float* sp = slab + px * P;
+      for (int q = 0; q < PB; ++q)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[q][j] = bia[j];
       for (int k = 0; k < K; ++k) {
-        const float v = sp[koff[k]];
+        const int ko = koff[k];
+        float v[PB];
+#pragma unroll
+        for (int q = 0; q < PB; ++q) v[q] = (px0 + q < G) ? slab[ko + (px0 + q) * P] : 0.f;
         const float* wk = wt + k * E + lane;
 #pragma unroll
         for (int j = 0; j < 8; ++j)
-          if (j < EP) acc[j] = fmaf(v, wk[32 * j], acc[j]);
+          if (j < EP) {
+            const float wv = wk[32 * j];
+#pragma unroll
+            for (int q = 0; q < PB; ++q) acc[q][j] = fmaf(v[q], wv, acc[q][j]);
+          }
       }
-      float s = 0.f;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) if (j < EP) s += acc[j];
-      const float mean = warp_sum(s) / (float)E;
-      float q = 0.f;
+      for (int q = 0; q < PB; ++q) {
+        const int px = px0 + q;
+        if (px >= G) break;
+        float s = 0.f;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) if (j < EP) { const float d = acc[j] - mean; q += d * d; }
-      const float rstd = 1.0f / sqrtf(warp_sum(q) / (float)E + kLnEps);
-      float* o = out + (((long)b * G + py) * G + px) * E;
+        for (int j = 0; j < 8; ++j) if (j < EP) s += acc[q][j];
+        const float mean = warp_sum(s) / (float)E;
+        float qv = 0.f;
 #pragma unroll
-      for (int j = 0; j < 8; ++j)
-        if (j < EP) o[lane + 32 * j] = (acc[j] - mean) * rstd * gam[j] + bet[j];
+        for (int j = 0; j < 8; ++j) if (j < EP) { const float dd = acc[q][j] - mean; qv += dd * dd; }
+        const float rstd = 1.0f / sqrtf(warp_sum(qv) / (float)E + kLnEps);
+        float* o = out + (((long)b * G + py) * G + px) * E;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (j < EP) o[lane + 32 * j] = (acc[q][j] - mean) * rstd * gam[j] + bet[j];
+      }
     }
   }
 }
