@@ -36,44 +36,11 @@ __device__ __forceinline__ void store4<f16>(f16* p, float a, float b, float c, f
   *reinterpret_cast<uint2*>(p) = u;
 }
 
-// One warp per row.  The row is read from global memory once and held in registers (up to kLnMaxV float4 per lane,
-// i.e. C <= 128*kLnMaxV); wider rows fall back to re-reading (L1-resident).  Two-pass mean / variance in fp32.
-constexpr int kLnMaxV = 12;
-
+// Generic row LayerNorm: one warp per row, three L1-resident passes (used for the gathered PatchMerging rows and
+// for widths without a specialised kernel).
 template <typename OutT, typename SrcFn>
 __device__ __forceinline__ void ln_row(SrcFn src, const float* __restrict__ g, const float* __restrict__ b,
                                        OutT* __restrict__ yr, int C, int lane) {
-  if (C <= 128 * kLnMaxV) {
-    float4 v[kLnMaxV];
-    float s = 0.f;
-#pragma unroll
-    for (int i = 0; i < kLnMaxV; ++i) {
-      const int c = lane * 4 + i * 128;
-      if (c < C) { v[i] = src(c); s += (v[i].x + v[i].y) + (v[i].z + v[i].w); }
-    }
-    const float mean = warp_sum(s) / (float)C;
-    float q = 0.f;
-#pragma unroll
-    for (int i = 0; i < kLnMaxV; ++i) {
-      const int c = lane * 4 + i * 128;
-      if (c < C) {
-        const float d0 = v[i].x - mean, d1 = v[i].y - mean, d2 = v[i].z - mean, d3 = v[i].w - mean;
-        q += (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
-      }
-    }
-    const float rstd = 1.0f / sqrtf(warp_sum(q) / (float)C + kLnEps);
-#pragma unroll
-    for (int i = 0; i < kLnMaxV; ++i) {
-      const int c = lane * 4 + i * 128;
-      if (c < C) {
-        const float4 gg = *reinterpret_cast<const float4*>(g + c);
-        const float4 bb = *reinterpret_cast<const float4*>(b + c);
-        store4<OutT>(yr + c, (v[i].x - mean) * rstd * gg.x + bb.x, (v[i].y - mean) * rstd * gg.y + bb.y,
-                     (v[i].z - mean) * rstd * gg.z + bb.z, (v[i].w - mean) * rstd * gg.w + bb.w);
-      }
-    }
-    return;
-  }
   float s = 0.f;
   for (int c = lane * 4; c < C; c += 128) {
     const float4 v = src(c);
@@ -107,11 +74,83 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
                threadIdx.x & 31);
 }
 
+// Specialised persistent LayerNorm for C = 128*VPL' widths: the row lives in exactly VPL float4 registers per lane,
+// gamma/beta are loaded once per warp, each warp strides over rows and keeps RIF rows in flight (memory-level
+// parallelism), so HBM latency is covered without relying on thousands of tiny CTAs.
+template <typename OutT, int VPL, int RIF>
+__global__ void __launch_bounds__(256) layernorm_rows_kernel(const float* __restrict__ x, long ldx,
+                                                             const float* __restrict__ g, const float* __restrict__ b,
+                                                             OutT* __restrict__ y, long ldy, long rows, int C) {
+  const int lane = threadIdx.x & 31;
+  const long warp_g = (long)blockIdx.x * 8 + (threadIdx.x >> 5), nwarps = (long)gridDim.x * 8;
+  constexpr bool kAffineInRegs = VPL <= 3;      // wide rows re-read gamma/beta (L1-resident) to keep occupancy up
+  float4 gg[kAffineInRegs ? VPL : 1], bb[kAffineInRegs ? VPL : 1];
+  if (kAffineInRegs) {
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const int c = lane * 4 + i * 128;
+      gg[i] = c < C ? *reinterpret_cast<const float4*>(g + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+      bb[i] = c < C ? *reinterpret_cast<const float4*>(b + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+  const float inv_c = 1.0f / (float)C;
+  for (long r0 = warp_g * RIF; r0 < rows; r0 += nwarps * RIF) {
+    float4 v[RIF][VPL];
+#pragma unroll
+    for (int k = 0; k < RIF; ++k)
+#pragma unroll
+      for (int i = 0; i < VPL; ++i) {
+        const int c = lane * 4 + i * 128;
+        v[k][i] = (r0 + k < rows && c < C) ? *reinterpret_cast<const float4*>(x + (r0 + k) * ldx + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+    for (int k = 0; k < RIF; ++k) {
+      if (r0 + k >= rows) break;
+      float s = 0.f;
+#pragma unroll
+      for (int i = 0; i < VPL; ++i) s += (v[k][i].x + v[k][i].y) + (v[k][i].z + v[k][i].w);   // padding lanes hold zeros
+      const float mean = warp_sum(s) * inv_c;
+      float q = 0.f;
+#pragma unroll
+      for (int i = 0; i < VPL; ++i) {
+        if (lane * 4 + i * 128 < C) {
+          const float d0 = v[k][i].x - mean, d1 = v[k][i].y - mean, d2 = v[k][i].z - mean, d3 = v[k][i].w - mean;
+          q += (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
+        }
+      }
+      const float rstd = 1.0f / sqrtf(warp_sum(q) * inv_c + kLnEps);
+      OutT* yr = y + (r0 + k) * ldy;
+#pragma unroll
+      for (int i = 0; i < VPL; ++i) {
+        const int c = lane * 4 + i * 128;
+        if (c < C) {
+          const float4 ga = kAffineInRegs ? gg[kAffineInRegs ? i : 0] : *reinterpret_cast<const float4*>(g + c);
+          const float4 be = kAffineInRegs ? bb[kAffineInRegs ? i : 0] : *reinterpret_cast<const float4*>(b + c);
+          store4<OutT>(yr + c, (v[k][i].x - mean) * rstd * ga.x + be.x, (v[k][i].y - mean) * rstd * ga.y + be.y,
+                       (v[k][i].z - mean) * rstd * ga.z + be.z, (v[k][i].w - mean) * rstd * ga.w + be.w);
+        }
+      }
+    }
+  }
+}
+
 template <typename OutT>
 cudaError_t launch_layernorm(const float* x, long ldx, const float* gamma, const float* beta, OutT* y, long ldy,
                              long rows, int C, cudaStream_t st) {
   if (rows <= 0) return cudaSuccess;
   if ((C & 3) || (ldx & 3) || (ldy & 3)) return cudaErrorInvalidValue;
+  const int vpl = (C + 127) / 128;
+  if (rows >= 4096 && vpl <= 12) {
+    const unsigned grid = 148 * 6;
+#define XN_LN(V, R) layernorm_rows_kernel<OutT, V, R><<<grid, 256, 0, st>>>(x, ldx, gamma, beta, y, ldy, rows, C)
+    if (vpl <= 2) XN_LN(2, 4);
+    else if (vpl <= 3) XN_LN(3, 4);
+    else if (vpl <= 4) XN_LN(4, 2);
+    else if (vpl <= 6) XN_LN(6, 2);
+    else XN_LN(12, 1);
+#undef XN_LN
+    return cudaGetLastError();
+  }
   layernorm_kernel<OutT><<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(x, ldx, gamma, beta, y, ldy, rows, C);
   return cudaGetLastError();
 }
