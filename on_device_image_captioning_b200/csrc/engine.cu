@@ -81,7 +81,7 @@ struct xn_handle {
   int n_exp_total = 0, exp_chunk = 8;
   Arena ws;
   int64_t launches = 0;
-  int64_t swin_chunk = 32, enc_chunk = 64;
+  int64_t swin_chunk = 64, enc_chunk = 64;
   // CUDA-graph cache of the decode loop (one entry per distinct call shape / buffer set)
   struct DecodeGraph {
     const void* enc; int B, beam, L, how_many, sos, eos; const char* ws_base; size_t ws_cap;

@@ -40,7 +40,10 @@ template <int BN> struct TcCfg {
   static constexpr uint32_t kAccCols = 256;                 // column stride between the two accumulators
   static constexpr uint32_t kTmemCols = 512;
   static constexpr uint32_t kStagingBytes = kEpiWarps * 32 * 16 * 4;   // per epilogue warp: 32 rows x 16 floats, XOR-swizzled 16-B slots
-  static constexpr uint32_t kSmemBytes = kStages * kStageBytes + kStagingBytes + 256 + 1024;
+  static constexpr uint32_t kBarBytes = 256;
+  static constexpr uint32_t kBiasBytes = 2 * BN * 4;          // the tile's bias row, double-buffered by accumulator parity
+  // no alignment slack: the kernel has no static smem, so the dynamic window starts 1024-aligned (checked on device)
+  static constexpr uint32_t kSmemBytes = kStages * kStageBytes + kStagingBytes + kBarBytes + kBiasBytes;
   static_assert(kSmemBytes <= 232448, "exceeds the 227 KB dynamic shared memory limit");
 };
 
@@ -50,6 +53,7 @@ struct TcEpilogue {
   const float* bias;
   const float* res; long ldr;
   float scale;  // accumulator multiplier (1 / div); a multiply, never a speculated division
+  int use_tma_store;   // 16-bit output without residual: write through TMA (needs ldc % 8 == 0)
   int dbg;     // timing experiments only: 1 = skip the epilogue's global traffic, 2 = skip MMA issue, 4 = skip TMA loads
 };
 
@@ -83,6 +87,14 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(bar)
       : "memory");
 }
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(src), "r"(c0), "r"(c1) : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -167,13 +179,14 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N, int ab_fmt) {
 // OUT: 0 = fp32 output, 1 = 16-bit output (bf16, or fp16 when ep.fp16).  ACT: 0 none, 1 GELU(erf), 2 ReLU.
 template <int BN, int OUT, int ACT>
 __global__ void __launch_bounds__(kTcThreads, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, TcEpilogue ep,
-               int M, int N, int K) {
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+               const __grid_constant__ CUtensorMap tma_c, TcEpilogue ep, int M, int N, int K) {
   using Cfg = TcCfg<BN>;
   constexpr int S = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
-  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;          // SWIZZLE_128B tiles need 1024-B alignment
-  uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t base = smem_u32(smem_raw);                             // SWIZZLE_128B tiles need 1024-B alignment
+  if (base & 1023u) __trap();
+  uint8_t* gen_base = smem_raw;
   const uint32_t staging = base + S * Cfg::kStageBytes;
   float* staging_gen = reinterpret_cast<float*>(gen_base + S * Cfg::kStageBytes);
   const uint32_t bars = staging + Cfg::kStagingBytes;
@@ -256,6 +269,77 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     const int q = warp & 3;                        // TMEM lane quarter this warp may access (hardware: warp id % 4)
     const int hf = (warp - 2) >> 2;                // which quarter of the tile's columns this warp drains
     int it = 0;
+    if (OUT == 1 && ep.use_tma_store) {
+      // ---- 16-bit output through TMA stores.  Lane == accumulator row: bias / activation / conversion happen in that
+      // layout, the 32 x 32 (rows x columns) 16-bit slab is written to smem in the 64-byte-swizzled box layout
+      // (conflict-free 16-byte stores) and one elected lane hands it to the TMA, which also clips at the M / N edges.
+      const int cq = hf;                                   // 64-column group of this warp
+      uint8_t* slab_gen = reinterpret_cast<uint8_t*>(staging_gen) + (warp - 2) * 2048;
+      const uint32_t slab_u32 = staging + (uint32_t)(warp - 2) * 2048u;
+      float* bias_all = reinterpret_cast<float*>(gen_base + S * Cfg::kStageBytes + Cfg::kStagingBytes + Cfg::kBarBytes);
+      const bool active = cq * 64 < BN;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        const int buf = it & 1;
+        const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
+        const int m0 = (tile / n_tiles) * kBM, n0 = (tile % n_tiles) * BN;
+        const int col_base = n0 + cq * 64;
+        // this warp's 64 bias values: fetched before the accumulator wait (latency hidden), published after it.  The
+        // buffer is shared by the four warps of a column group (they write identical values) and double-buffered by
+        // accumulator parity: once tile i's accumulator is full, every warp has left tile i-2.
+        float b_lo = 0.f, b_hi = 0.f;
+        if (active && ep.bias) {
+          if (col_base + lane < N) b_lo = ep.bias[col_base + lane];
+          if (col_base + lane + 32 < N) b_hi = ep.bias[col_base + lane + 32];
+        }
+        float* bias_s = bias_all + buf * BN + cq * 64;
+        mbar_wait(tfull_bar(buf), acc_phase);
+        tc_fence_after();
+        if (active) { bias_s[lane] = b_lo; bias_s[lane + 32] = b_hi; }
+        __syncwarp();
+        if (active && col_base < N) {
+          const uint32_t t_base = tmem_base + ((uint32_t)(q * 32) << 16) + buf * Cfg::kAccCols + cq * 64;
+          uint32_t v[2][32];
+          tmem_ld32_nowait(t_base, v[0]);
+          __syncwarp();
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            tmem_ld_wait();
+            if (half == 0) tmem_ld32_nowait(t_base + 32, v[1]);
+            if (ep.dbg & 1) continue;
+            uint32_t pk[16];
+#pragma unroll
+            for (int c = 0; c < 32; c += 4) {
+              const float4 b4 = *reinterpret_cast<const float4*>(bias_s + half * 32 + c);
+              float t0 = fmaf(__uint_as_float(v[half][c]), ep.scale, b4.x), t1 = fmaf(__uint_as_float(v[half][c + 1]), ep.scale, b4.y);
+              float t2 = fmaf(__uint_as_float(v[half][c + 2]), ep.scale, b4.z), t3 = fmaf(__uint_as_float(v[half][c + 3]), ep.scale, b4.w);
+              if (ACT == 1) { t0 = gelu_fast(t0); t1 = gelu_fast(t1); t2 = gelu_fast(t2); t3 = gelu_fast(t3); }
+              else if (ACT == 2) { t0 = fmaxf(t0, 0.f); t1 = fmaxf(t1, 0.f); t2 = fmaxf(t2, 0.f); t3 = fmaxf(t3, 0.f); }
+              if (ep.fp16) {
+                __half2 a2 = __floats2half2_rn(t0, t1), b2 = __floats2half2_rn(t2, t3);
+                pk[c >> 1] = *reinterpret_cast<uint32_t*>(&a2); pk[(c >> 1) + 1] = *reinterpret_cast<uint32_t*>(&b2);
+              } else {
+                __nv_bfloat162 a2 = __floats2bfloat162_rn(t0, t1), b2 = __floats2bfloat162_rn(t2, t3);
+                pk[c >> 1] = *reinterpret_cast<uint32_t*>(&a2); pk[(c >> 1) + 1] = *reinterpret_cast<uint32_t*>(&b2);
+              }
+            }
+            if (lane == 0) tma_store_wait_read();           // the previous slab has been read out of smem
+            __syncwarp();
+            // row = lane, 64 bytes per row; 16-byte chunk j lands at j ^ ((row >> 1) & 3)  (CU_TENSOR_MAP_SWIZZLE_64B)
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              *reinterpret_cast<uint4*>(slab_gen + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4)) =
+                  make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0 && col_base + half * 32 < N) tma_store_2d(&tma_c, slab_u32, col_base + half * 32, m0 + q * 32);
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty_bar(buf));
+      }
+      if (lane == 0) tma_store_wait_all();
+    } else {
     // Transpose 16-column accumulator slices through smem so that global traffic is coalesced row segments
     // (direct lane==row stores were measured 30% slower: 32 sectors per store instruction saturate the LSU).
     float* tile_s = staging_gen + (warp - 2) * (32 * 16);
@@ -373,6 +457,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       tc_fence_before();
       if (lane == 0) mbar_arrive(tempty_bar(buf));
     }
+    }
   }
 
   tc_fence_before();
@@ -402,15 +487,16 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-static bool make_map(CUtensorMap* map, const void* ptr, long rows, long cols, long ld, int box_rows, int fp16) {
+static bool make_map(CUtensorMap* map, const void* ptr, long rows, long cols, long ld, int box_rows, int fp16,
+                     int box_cols = kBK, CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return false;
   cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
   cuuint64_t gstride[1] = {(cuuint64_t)ld * 2};
-  cuuint32_t box[2] = {(cuuint32_t)kBK, (cuuint32_t)box_rows};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(map, fp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstride, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS;
 }
@@ -431,6 +517,8 @@ static int sm_count() {
   return n;
 }
 
+extern int g_tc_debug;
+
 template <int BN, int OUT, int ACT>
 static cudaError_t launch_tc(const TcGemmArgs& p, cudaStream_t st) {
   using Cfg = TcCfg<BN>;
@@ -442,10 +530,14 @@ static cudaError_t launch_tc(const TcGemmArgs& p, cudaStream_t st) {
   }
   CUtensorMap ma, mb;
   if (!make_map(&ma, p.A, p.M, p.K, p.lda, kBM, p.fp16) || !make_map(&mb, p.W, p.N, p.K, p.ldw, BN, p.fp16)) return cudaErrorInvalidValue;
-  TcEpilogue ep{p.Cf, p.Cb, p.ldc, p.fp16, p.bias, p.res, p.ldr, p.div != 0.f ? 1.0f / p.div : 1.0f, g_tc_debug};
+  // 16-bit outputs without a residual leave through TMA stores: 32 x 32 boxes, 64-byte swizzle
+  const bool tma_c_ok = OUT == 1 && !p.res && (p.ldc % 8) == 0 && (reinterpret_cast<uintptr_t>(p.Cb) & 15) == 0 && !(g_tc_debug & 16);
+  CUtensorMap mc = ma;
+  if (tma_c_ok && !make_map(&mc, p.Cb, p.M, p.N, p.ldc, 32, p.fp16, 32, CU_TENSOR_MAP_SWIZZLE_64B)) return cudaErrorInvalidValue;
+  TcEpilogue ep{p.Cf, p.Cb, p.ldc, p.fp16, p.bias, p.res, p.ldr, p.div != 0.f ? 1.0f / p.div : 1.0f, tma_c_ok ? 1 : 0, g_tc_debug};
   const int tiles = ((p.M + kBM - 1) / kBM) * ((p.N + BN - 1) / BN);
   const int grid = tiles < sm_count() ? tiles : sm_count();
-  gemm_tc_kernel<BN, OUT, ACT><<<grid, kTcThreads, Cfg::kSmemBytes, st>>>(ma, mb, ep, p.M, p.N, p.K);
+  gemm_tc_kernel<BN, OUT, ACT><<<grid, kTcThreads, Cfg::kSmemBytes, st>>>(ma, mb, mc, ep, p.M, p.N, p.K);
   return cudaGetLastError();
 }
 
