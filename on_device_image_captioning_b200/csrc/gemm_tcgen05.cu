@@ -40,7 +40,7 @@ template <int BN> struct TcCfg {
   static constexpr uint32_t kAccCols = 256;                 // column stride between the two accumulators
   static constexpr uint32_t kTmemCols = 512;
   static constexpr uint32_t kStagingBytes = kEpiWarps * 32 * 16 * 4;   // per epilogue warp: 32 rows x 16 floats, XOR-swizzled 16-B slots
-  static constexpr uint32_t kBarBytes = 256;
+  static constexpr uint32_t kBarBytes = 384;   // pipeline + accumulator barriers, TMEM pointer, 16 residual-slab barriers
   static constexpr uint32_t kBiasBytes = 2 * BN * 4;          // the tile's bias row, double-buffered by accumulator parity
   // no alignment slack: the kernel has no static smem, so the dynamic window starts 1024-aligned (checked on device)
   static constexpr uint32_t kSmemBytes = kStages * kStageBytes + kStagingBytes + kBarBytes + kBiasBytes;
@@ -180,7 +180,8 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N, int ab_fmt) {
 template <int BN, int OUT, int ACT>
 __global__ void __launch_bounds__(kTcThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
-               const __grid_constant__ CUtensorMap tma_c, TcEpilogue ep, int M, int N, int K) {
+               const __grid_constant__ CUtensorMap tma_c, const __grid_constant__ CUtensorMap tma_r, TcEpilogue ep,
+               int M, int N, int K) {
   using Cfg = TcCfg<BN>;
   constexpr int S = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
@@ -206,6 +207,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   if (threadIdx.x == 0) {
     for (int s = 0; s < S; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), kEpiWarps); }
+    for (int b = 0; b < 16; ++b) mbar_init(bars + 8u * (2 * S + 5 + b), 1);     // residual-slab barriers (fp32 TMA epilogue)
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -339,6 +341,92 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         if (lane == 0) mbar_arrive(tempty_bar(buf));
       }
       if (lane == 0) tma_store_wait_all();
+    } else if (OUT == 0 && ep.use_tma_store) {
+      // ---- fp32 output (+ fp32 residual) through the TMA.  Eight warps (two per TMEM lane quarter, half of the columns
+      // each) own two 2-KB slabs: the residual box (32 rows x 16 columns) of sub-step s+1 is TMA-loaded into one slab
+      // while sub-step s is computed in place in the other (lane == row, 64 swizzled bytes per row) and TMA-stored.
+      const int e = warp - 2;
+      const bool active = e < 8;
+      const int hf2 = (e >> 2) & 1;
+      constexpr int kSub = (BN / 2) / 16;
+      float* bias_all = reinterpret_cast<float*>(gen_base + S * Cfg::kStageBytes + Cfg::kStagingBytes + Cfg::kBarBytes);
+      uint8_t* slab_gen[2] = {reinterpret_cast<uint8_t*>(staging_gen) + (e & 7) * 2048, reinterpret_cast<uint8_t*>(staging_gen) + ((e & 7) + 8) * 2048};
+      const uint32_t slab_u32[2] = {staging + (uint32_t)(e & 7) * 2048u, staging + (uint32_t)((e & 7) + 8) * 2048u};
+      const uint32_t rbar[2] = {bars + 8u * (2 * S + 5 + 2 * (e & 7)), bars + 8u * (2 * S + 5 + 2 * (e & 7) + 1)};
+      uint32_t rphase[2] = {0u, 0u};
+      const bool has_res = ep.res != nullptr;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        const int buf = it & 1;
+        const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
+        const int m0 = (tile / n_tiles) * kBM, n0 = (tile % n_tiles) * BN;
+        const int col_base = n0 + hf2 * (BN / 2);
+        const int row0 = m0 + q * 32;
+        float bpre[4] = {0.f, 0.f, 0.f, 0.f};
+        if (active) {
+          if (ep.bias) {
+#pragma unroll
+            for (int j = 0; j < (BN / 2 + 31) / 32; ++j) {
+              const int cc = lane + 32 * j;
+              if (cc < BN / 2 && col_base + cc < N) bpre[j] = ep.bias[col_base + cc];
+            }
+          }
+          if (has_res && lane == 0 && col_base < N) {                   // residual of sub-step 0, before the accumulator wait
+            tma_store_wait_read();
+            mbar_expect_tx(rbar[0], 2048);
+            tma_load_2d(slab_u32[0], &tma_r, col_base, row0, rbar[0]);
+          }
+        }
+        mbar_wait(tfull_bar(buf), acc_phase);
+        tc_fence_after();
+        if (active) {
+          float* bias_s = bias_all + buf * BN + hf2 * (BN / 2);
+#pragma unroll
+          for (int j = 0; j < (BN / 2 + 31) / 32; ++j)
+            if (lane + 32 * j < BN / 2) bias_s[lane + 32 * j] = bpre[j];
+          __syncwarp();
+          const uint32_t t_base = tmem_base + ((uint32_t)(q * 32) << 16) + buf * Cfg::kAccCols + hf2 * (BN / 2);
+          uint32_t v[2][16];
+          tmem_ld16_nowait(t_base, v[0]);
+#pragma unroll
+          for (int sub = 0; sub < kSub; ++sub) {
+            const int cur = sub & 1;
+            const int col = col_base + sub * 16;
+            tmem_ld_wait();
+            if (sub + 1 < kSub) tmem_ld16_nowait(t_base + (sub + 1) * 16, v[cur ^ 1]);
+            if (col >= N) continue;                                       // warp-uniform
+            if (lane == 0) {
+              tma_store_wait_read();                                       // the other slab's last store has left smem
+              if (has_res && sub + 1 < kSub && col + 16 < N) {
+                mbar_expect_tx(rbar[cur ^ 1], 2048);
+                tma_load_2d(slab_u32[cur ^ 1], &tma_r, col + 16, row0, rbar[cur ^ 1]);
+              }
+            }
+            if (has_res) { mbar_wait(rbar[cur], rphase[cur]); rphase[cur] ^= 1u; }
+            __syncwarp();
+            if (!(ep.dbg & 1)) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                uint8_t* ptr = slab_gen[cur] + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4);
+                const float4 b4 = *reinterpret_cast<const float4*>(bias_s + sub * 16 + 4 * j);
+                float4 r4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (has_res) r4 = *reinterpret_cast<const float4*>(ptr);
+                float x0 = fmaf(__uint_as_float(v[cur][4 * j]), ep.scale, b4.x), x1 = fmaf(__uint_as_float(v[cur][4 * j + 1]), ep.scale, b4.y);
+                float x2 = fmaf(__uint_as_float(v[cur][4 * j + 2]), ep.scale, b4.z), x3 = fmaf(__uint_as_float(v[cur][4 * j + 3]), ep.scale, b4.w);
+                if (ACT == 1) { x0 = gelu_erf(x0); x1 = gelu_erf(x1); x2 = gelu_erf(x2); x3 = gelu_erf(x3); }
+                else if (ACT == 2) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); x2 = fmaxf(x2, 0.f); x3 = fmaxf(x3, 0.f); }
+                *reinterpret_cast<float4*>(ptr) = make_float4(x0 + r4.x, x1 + r4.y, x2 + r4.z, x3 + r4.w);
+              }
+              fence_async_smem();
+              __syncwarp();
+              if (lane == 0) tma_store_2d(&tma_c, slab_u32[cur], col, row0);
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty_bar(buf));
+      }
+      if (active && lane == 0) tma_store_wait_all();
     } else {
     // Transpose 16-column accumulator slices through smem so that global traffic is coalesced row segments
     // (direct lane==row stores were measured 30% slower: 32 sectors per store instruction saturate the LSU).
@@ -519,6 +607,17 @@ static int sm_count() {
 
 extern int g_tc_debug;
 
+static bool make_map32(CUtensorMap* map, const float* ptr, long rows, long cols, long ld) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return false;
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstride[1] = {(cuuint64_t)ld * 4};
+  cuuint32_t box[2] = {16u, 32u};
+  cuuint32_t estr[2] = {1, 1};
+  return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 template <int BN, int OUT, int ACT>
 static cudaError_t launch_tc(const TcGemmArgs& p, cudaStream_t st) {
   using Cfg = TcCfg<BN>;
@@ -531,13 +630,24 @@ static cudaError_t launch_tc(const TcGemmArgs& p, cudaStream_t st) {
   CUtensorMap ma, mb;
   if (!make_map(&ma, p.A, p.M, p.K, p.lda, kBM, p.fp16) || !make_map(&mb, p.W, p.N, p.K, p.ldw, BN, p.fp16)) return cudaErrorInvalidValue;
   // 16-bit outputs without a residual leave through TMA stores: 32 x 32 boxes, 64-byte swizzle
-  const bool tma_c_ok = OUT == 1 && !p.res && (p.ldc % 8) == 0 && (reinterpret_cast<uintptr_t>(p.Cb) & 15) == 0 && !(g_tc_debug & 16);
-  CUtensorMap mc = ma;
-  if (tma_c_ok && !make_map(&mc, p.Cb, p.M, p.N, p.ldc, 32, p.fp16, 32, CU_TENSOR_MAP_SWIZZLE_64B)) return cudaErrorInvalidValue;
+  bool tma_c_ok = false;
+  CUtensorMap mc = ma, mr = ma;
+  if (OUT == 1) {
+    tma_c_ok = !p.res && (p.ldc % 8) == 0 && (reinterpret_cast<uintptr_t>(p.Cb) & 15) == 0 && !(g_tc_debug & 16);
+    if (tma_c_ok && !make_map(&mc, p.Cb, p.M, p.N, p.ldc, 32, p.fp16, 32, CU_TENSOR_MAP_SWIZZLE_64B)) return cudaErrorInvalidValue;
+  } else {
+    // fp32 output (+ fp32 residual): 32-row x 16-column boxes (64 bytes per row), 64-byte swizzle
+    tma_c_ok = (p.ldc % 4) == 0 && (reinterpret_cast<uintptr_t>(p.Cf) & 15) == 0 && !(g_tc_debug & 32) &&
+               (!p.res || ((p.ldr % 4) == 0 && (reinterpret_cast<uintptr_t>(p.res) & 15) == 0));
+    if (tma_c_ok) {
+      if (!make_map32(&mc, p.Cf, p.M, p.N, p.ldc)) return cudaErrorInvalidValue;
+      if (p.res && !make_map32(&mr, p.res, p.M, p.N, p.ldr)) return cudaErrorInvalidValue;
+    }
+  }
   TcEpilogue ep{p.Cf, p.Cb, p.ldc, p.fp16, p.bias, p.res, p.ldr, p.div != 0.f ? 1.0f / p.div : 1.0f, tma_c_ok ? 1 : 0, g_tc_debug};
   const int tiles = ((p.M + kBM - 1) / kBM) * ((p.N + BN - 1) / BN);
   const int grid = tiles < sm_count() ? tiles : sm_count();
-  gemm_tc_kernel<BN, OUT, ACT><<<grid, kTcThreads, Cfg::kSmemBytes, st>>>(ma, mb, mc, ep, p.M, p.N, p.K);
+  gemm_tc_kernel<BN, OUT, ACT><<<grid, kTcThreads, Cfg::kSmemBytes, st>>>(ma, mb, mc, mr, ep, p.M, p.N, p.K);
   return cudaGetLastError();
 }
 
