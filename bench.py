@@ -174,6 +174,12 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     note("weights loaded, inputs resident")
+    # one-time setup, like a build step: the engine captures its whole-forward CUDA graph on the second call with a
+    # given (input buffer, shape), so every rotating input is seen twice before the W warm-up steps start
+    for i in range(2 * n_rot):
+        step(i)
+    barrier()
+    note("graphs captured")
     for i in range(args.warmup):
         step(i)
         note(f"warm-up step {i} enqueued")
@@ -201,7 +207,8 @@ def run_ours(args):
     # ---- end to end: host buffers in, host tokens out, through the C-ABI call a user makes
     outs = (torch.empty(B, 1, MAX_LEN, dtype=torch.int32).pin_memory(), torch.empty(B, 1, dtype=torch.int32).pin_memory(),
             torch.empty(B, 1, MAX_LEN, dtype=torch.float32).pin_memory())
-    eng.caption_host(host[0], SOS, EOS, BEAM, 1, MAX_LEN, out=outs)
+    for _ in range(3):
+        eng.caption_host(host[0], SOS, EOS, BEAM, 1, MAX_LEN, out=outs)
     barrier()
     e0.record()
     for i in range(args.steps):

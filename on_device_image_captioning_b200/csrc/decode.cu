@@ -337,11 +337,171 @@ __global__ void __launch_bounds__(256) cross_attn_step_kernel(const float* __res
   }
 }
 
+// 16-bit K/V variant, dk == 64: no smem staging of K/V.  Eight lanes cover one key's 128-byte head slice with one 16-byte
+// load each, a warp takes four keys per round and the CTA's eight warps 32; all K loads of a thread are issued before
+// the first dot product and the V loads before the softmax, so the kernel pays roughly one L2 round trip per phase
+// instead of a staged copy.  One CTA per (image, head) serves the image's RPI beam rows.
+template <typename T> __device__ __forceinline__ void unpack8(const uint4& u, float (&o)[8]);
+template <> __device__ __forceinline__ void unpack8<f16>(const uint4& u, float (&o)[8]) {
+  const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { const float2 f = __half22float2(h[i]); o[2 * i] = f.x; o[2 * i + 1] = f.y; }
+}
+template <> __device__ __forceinline__ void unpack8<bf16>(const uint4& u, float (&o)[8]) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { const float2 f = __bfloat1622float2(h[i]); o[2 * i] = f.x; o[2 * i + 1] = f.y; }
+}
+
+constexpr int kCaRounds = 5;            // key rounds per warp: 8 warps x 4 keys x 5 rounds >= 160 keys
+constexpr int kCaMaxKeys = 160;
+
+template <typename T, int RPI>
+__global__ void __launch_bounds__(256) cross_attn_step16_kernel(const float* __restrict__ q, long ldq,
+                                                                const T* __restrict__ kv, long ldkv, int k_off, int v_off,
+                                                                T* __restrict__ out, long ldo, int n,
+                                                                const int* __restrict__ n_valid,
+                                                                const int* __restrict__ row_len, int p) {
+  constexpr int dk = 64;
+  __shared__ float pr[RPI][kCaMaxKeys];            // scores, then probabilities
+  __shared__ float po[8][RPI][dk];                 // per-warp partial outputs
+  const int b = blockIdx.x, h = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int sub = lane & 7, kslot = lane >> 3;     // 8 dims per lane, 4 keys per warp round
+  const T* base = kv + (long)b * n * ldkv + h * dk + sub * 8;
+  uint4 kr[kCaRounds], vr[kCaRounds];
+#pragma unroll
+  for (int it = 0; it < kCaRounds; ++it) {
+    const int j = (it * 8 + warp) * 4 + kslot;
+    kr[it] = j < n ? *reinterpret_cast<const uint4*>(base + (long)j * ldkv + k_off) : make_uint4(0u, 0u, 0u, 0u);
+  }
+  float qv[RPI][8];
+#pragma unroll
+  for (int i = 0; i < RPI; ++i) {
+    const float* qp = q + (long)(b * RPI + i) * ldq + h * dk + sub * 8;
+    const float4 a = *reinterpret_cast<const float4*>(qp), c = *reinterpret_cast<const float4*>(qp + 4);
+    qv[i][0] = a.x; qv[i][1] = a.y; qv[i][2] = a.z; qv[i][3] = a.w; qv[i][4] = c.x; qv[i][5] = c.y; qv[i][6] = c.z; qv[i][7] = c.w;
+  }
+  const int nv = n_valid ? n_valid[b] : n;
+#pragma unroll
+  for (int it = 0; it < kCaRounds; ++it) {
+    const int j = (it * 8 + warp) * 4 + kslot;
+    float kf[8];
+    unpack8<T>(kr[it], kf);
+    // V of the same key: in flight while the scores and the softmax are computed
+    vr[it] = j < n ? *reinterpret_cast<const uint4*>(base + (long)j * ldkv + v_off) : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+    for (int i = 0; i < RPI; ++i) {
+      float a = 0.f;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) a = fmaf(qv[i][e], kf[e], a);
+      a += __shfl_xor_sync(0xffffffffu, a, 4);
+      a += __shfl_xor_sync(0xffffffffu, a, 2);
+      a += __shfl_xor_sync(0xffffffffu, a, 1);
+      if (sub == 0 && j < n) {
+        float v = a * 0.125f;                                        // / sqrt(64)
+        const bool row_padded = row_len && p >= row_len[b * RPI + i];
+        if (row_padded || j >= nv) v = kCrossFill;
+        pr[i][j] = v;
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = warp; i < RPI; i += 8) {              // softmax: one warp per row
+    float mx = -INFINITY;
+    for (int j = lane; j < n; j += 32) mx = fmaxf(mx, pr[i][j]);
+    mx = warp_max(mx);
+    float sum = 0.f;
+    for (int j = lane; j < n; j += 32) { const float e = expf(pr[i][j] - mx); pr[i][j] = e; sum += e; }
+    sum = warp_sum(sum);
+    const float inv = 1.0f / sum;
+    for (int j = lane; j < n; j += 32) pr[i][j] *= inv;
+  }
+  __syncthreads();
+  float acc[RPI][8];
+#pragma unroll
+  for (int i = 0; i < RPI; ++i)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[i][e] = 0.f;
+#pragma unroll
+  for (int it = 0; it < kCaRounds; ++it) {
+    const int j = (it * 8 + warp) * 4 + kslot;
+    if (j < n) {
+      float vf[8];
+      unpack8<T>(vr[it], vf);
+#pragma unroll
+      for (int i = 0; i < RPI; ++i) {
+        const float w = pr[i][j];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[i][e] = fmaf(w, vf[e], acc[i][e]);
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < RPI; ++i)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      float a = acc[i][e];
+      a += __shfl_xor_sync(0xffffffffu, a, 8);
+      a += __shfl_xor_sync(0xffffffffu, a, 16);
+      if (kslot == 0) po[warp][i][sub * 8 + e] = a;
+    }
+  __syncthreads();
+  for (int i = tid; i < RPI * dk; i += 256) {
+    const int ri = i / dk, cc = i % dk;
+    float o = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) o += po[w][ri][cc];               // fixed order: deterministic
+    out[(long)(b * RPI + ri) * ldo + h * dk + cc] = from_f32<T>(o);
+  }
+}
+
+template <typename T, int RPI>
+static cudaError_t launch_ca16(const float* q, long ldq, const T* kv, long ldkv, int k_off, int v_off, T* out, long ldo, int R,
+                               int n_keys, int heads, const int* n_valid, const int* row_len, int p, cudaStream_t st) {
+  cross_attn_step16_kernel<T, RPI><<<dim3(R / RPI, heads), 256, 0, st>>>(q, ldq, kv, ldkv, k_off, v_off, out, ldo, n_keys, n_valid, row_len, p);
+  return cudaGetLastError();
+}
+template <typename T>
+static bool try_ca16(cudaError_t* err, const float* q, long ldq, const T* kv, long ldkv, int k_off, int v_off, T* out, long ldo,
+                     int R, int rpi, int n_keys, int heads, int dk, const int* n_valid, const int* row_len, int p, cudaStream_t st) {
+  if (dk != 64 || n_keys > kCaMaxKeys || (ldkv & 7) || (k_off & 7) || (v_off & 7) || (ldq & 3) ||
+      (reinterpret_cast<uintptr_t>(kv) & 15) || (reinterpret_cast<uintptr_t>(q) & 15))
+    return false;
+  switch (rpi) {
+#define XN_CA16(N) case N: *err = launch_ca16<T, N>(q, ldq, kv, ldkv, k_off, v_off, out, ldo, R, n_keys, heads, n_valid, row_len, p, st); return true;
+    XN_CA16(1) XN_CA16(2) XN_CA16(3) XN_CA16(4) XN_CA16(5) XN_CA16(6) XN_CA16(7) XN_CA16(8)
+#undef XN_CA16
+  }
+  return false;
+}
+template <typename KvT, typename OutT> struct Ca16Dispatch {
+  static bool run(cudaError_t*, const float*, long, const KvT*, long, int, int, OutT*, long, int, int, int, int, int, const int*,
+                  const int*, int, cudaStream_t) { return false; }
+};
+template <> struct Ca16Dispatch<f16, f16> {
+  static bool run(cudaError_t* e, const float* q, long ldq, const f16* kv, long ldkv, int k_off, int v_off, f16* out, long ldo, int R,
+                  int rpi, int n, int heads, int dk, const int* nvp, const int* rl, int p, cudaStream_t st) {
+    return try_ca16<f16>(e, q, ldq, kv, ldkv, k_off, v_off, out, ldo, R, rpi, n, heads, dk, nvp, rl, p, st);
+  }
+};
+template <> struct Ca16Dispatch<bf16, bf16> {
+  static bool run(cudaError_t* e, const float* q, long ldq, const bf16* kv, long ldkv, int k_off, int v_off, bf16* out, long ldo, int R,
+                  int rpi, int n, int heads, int dk, const int* nvp, const int* rl, int p, cudaStream_t st) {
+    return try_ca16<bf16>(e, q, ldq, kv, ldkv, k_off, v_off, out, ldo, R, rpi, n, heads, dk, nvp, rl, p, st);
+  }
+};
+
 template <typename KvT, typename OutT>
 cudaError_t launch_cross_attn_step(const float* q, long ldq, const KvT* kv, long ldkv, int k_off, int v_off,
                                    OutT* out, long ldo, int R, int rows_per_image, int n_keys, int heads, int dk,
                                    const int* n_valid, const int* row_len, int p, cudaStream_t st) {
   if (R % rows_per_image || (dk & 3) || dk > 256 || (256 % dk) || rows_per_image > kMaxRpi) return cudaErrorInvalidValue;
+  {
+    cudaError_t e16 = cudaSuccess;
+    if (Ca16Dispatch<KvT, OutT>::run(&e16, q, ldq, kv, ldkv, k_off, v_off, out, ldo, R, rows_per_image, n_keys, heads, dk, n_valid,
+                                     row_len, p, st))
+      return e16;
+  }
   const size_t smem = ((size_t)dk * (n_keys + 1) + (size_t)n_keys * dk + (size_t)kMaxRpi * dk + (size_t)kMaxRpi * n_keys +
                        (size_t)(256 / dk) * kMaxRpi * dk) * sizeof(float);
   static size_t configured = 0;

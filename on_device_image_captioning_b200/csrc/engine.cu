@@ -82,12 +82,17 @@ struct xn_handle {
   Arena ws;
   int64_t launches = 0;
   int64_t swin_chunk = 64, enc_chunk = 64;
-  // CUDA-graph cache of the decode loop (one entry per distinct call shape / buffer set)
-  struct DecodeGraph {
-    const void* enc; int B, beam, L, how_many, sos, eos; const char* ws_base; size_t ws_cap;
-    cudaGraphExec_t exec; int64_t launches; int seen;
+  // CUDA-graph cache: the decode loop (kind 0, keyed by the encoder-output pointer) or the whole
+  // images -> token ids forward (kind 1, keyed by the input pointer); one entry per distinct call shape / buffer set
+  struct GraphKey {
+    int kind; const void* in; int B, beam, L, how_many, sos, eos; const char* ws_base; size_t ws_cap;
+    bool operator==(const GraphKey& o) const {
+      return kind == o.kind && in == o.in && B == o.B && beam == o.beam && L == o.L && how_many == o.how_many && sos == o.sos &&
+             eos == o.eos && ws_base == o.ws_base && ws_cap == o.ws_cap;
+    }
   };
-  std::vector<DecodeGraph> graphs;
+  struct CachedGraph { GraphKey key; cudaGraphExec_t exec; int64_t launches; };
+  std::vector<CachedGraph> graphs;
   int64_t use_graph = 1;
   int64_t op_out16 = 0;
   cudaStream_t gstream = nullptr;      // graphs are captured/replayed here (the caller's stream may be the legacy
@@ -590,115 +595,136 @@ int upload_ints(xn_handle* h, const std::vector<int>& v, int** dev, cudaStream_t
   return 0;
 }
 
-int beam_from_enc(xn_handle* h, const float* enc_out, int B, const int32_t* enc_pads_host, int beam, int L, int how_many,
-                  int sos, int eos, int32_t* out_tokens, int32_t* out_len, float* out_lp, cudaStream_t st, bool reset_ws) {
+// Runs `body(stream)` (kernel launches only: no allocation, no host sync) either directly on the caller's stream or,
+// from the second identical call on, as a CUDA graph captured once and replayed on an internal stream that is ordered
+// with the caller's stream by events.
+template <typename F>
+int run_graphed(xn_handle* h, const xn_handle::GraphKey& key, bool allow_graph, cudaStream_t user_st, F&& body) {
+  if (!(h->use_graph && allow_graph && !h->profile)) return body(user_st);
+  if (!h->gstream) {
+    CU(cudaStreamCreateWithFlags(&h->gstream, cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&h->g_in, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&h->g_out, cudaEventDisableTiming));
+  }
+  xn_handle::CachedGraph* g = nullptr;
+  for (auto& e : h->graphs)
+    if (e.key == key) { g = &e; break; }
+  if (!g) {                                         // first sight: run eagerly, remember the shape
+    if (h->graphs.size() > 16) h->drop_graphs();
+    h->graphs.push_back({key, nullptr, 0});
+    return body(user_st);
+  }
+  cudaStream_t st = h->gstream;                     // hand over from the caller's stream to the graph stream
+  CU(cudaEventRecord(h->g_in, user_st));
+  CU(cudaStreamWaitEvent(st, h->g_in, 0));
+  if (!g->exec) {                                   // second identical call: capture once, then replay from now on
+    const int64_t l0 = h->launches;
+    CU(cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed));
+    const int rr = body(st);
+    cudaGraph_t graph = nullptr;
+    cudaError_t ce = cudaStreamEndCapture(st, &graph);
+    if (rr) { if (graph) cudaGraphDestroy(graph); return rr; }
+    if (ce != cudaSuccess) return h->fail(XN_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(ce));
+    g->launches = h->launches - l0;
+    h->launches = l0;
+    cudaError_t ie = cudaGraphInstantiate(&g->exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ie != cudaSuccess) { g->exec = nullptr; return h->fail(XN_ERR_CUDA, "graph instantiate failed: %s", cudaGetErrorString(ie)); }
+  }
+  CU(cudaGraphLaunch(g->exec, st));
+  h->launches += g->launches;
+  CU(cudaEventRecord(h->g_out, st));                // and back
+  CU(cudaStreamWaitEvent(user_st, h->g_out, 0));
+  return 0;
+}
+
+// beam search over an encoder output: arena plan (host arithmetic only), kernel sequence, result copies
+struct BeamPlan {
+  DecBufs D;
+  float *logits, *topv; int* topi;
+  BeamBufs bb;
+  int* nv = nullptr;
+  int32_t *r_tok, *r_len; float* r_lp;
+};
+
+int beam_plan(xn_handle* h, BeamPlan& P, int B, const int32_t* enc_pads_host, int beam, int L, int how_many, cudaStream_t st,
+              bool reset_ws) {
   const xn_config& c = h->cfg;
   if (beam < 1 || beam > 8 || how_many > beam || how_many < 1) return h->fail(XN_ERR_ARG, "requested output per sequence must be lower than beam width (beam<=8)");
   if (L < 2 || L > c.max_seq_len || L > 128) return h->fail(XN_ERR_ARG, "max_seq_len %d outside [2, %d]", L, std::min(c.max_seq_len, 128));
   if (beam > c.vocab) return h->fail(XN_ERR_ARG, "beam > vocab");
-  const int R = B * beam, d = c.d_model;
+  const int R = B * beam;
   if (reset_ws) h->ws.reset();
-  DecBufs D;
-  dec_alloc(h, D, R, L, B);
-  float* logits = h->ws.get<float>((size_t)R * c.vocab);
-  float* topv = h->ws.get<float>((size_t)R * beam);
-  int* topi = h->ws.get<int>((size_t)R * beam);
-  BeamBufs bb;
+  dec_alloc(h, P.D, R, L, B);
+  P.logits = h->ws.get<float>((size_t)R * c.vocab);
+  P.topv = h->ws.get<float>((size_t)R * beam);
+  P.topi = h->ws.get<int>((size_t)R * beam);
   for (int s = 0; s < 2; ++s) {
-    bb.tokens[s] = h->ws.get<int>((size_t)R * L);
-    bb.lps[s] = h->ws.get<float>((size_t)R * L);
-    bb.len[s] = h->ws.get<int>(R);
-    bb.anc[s] = h->ws.get<int>((size_t)R * L);
+    P.bb.tokens[s] = h->ws.get<int>((size_t)R * L);
+    P.bb.lps[s] = h->ws.get<float>((size_t)R * L);
+    P.bb.len[s] = h->ws.get<int>(R);
+    P.bb.anc[s] = h->ws.get<int>((size_t)R * L);
   }
-  bb.all_done = h->ws.get<int>(1);
-  int* nv = nullptr;
+  P.bb.all_done = h->ws.get<int>(1);
+  // results land in arena buffers (stable addresses -> graph-capturable), then are copied to the caller
+  P.r_tok = h->ws.get<int32_t>((size_t)B * how_many * L);
+  P.r_len = h->ws.get<int32_t>((size_t)B * how_many);
+  P.r_lp = h->ws.get<float>((size_t)B * how_many * L);
+  P.nv = nullptr;
   if (enc_pads_host) {
     std::vector<int> v(B);
     bool any = false;
     for (int i = 0; i < B; ++i) { v[i] = c.enc_len - enc_pads_host[i]; any |= enc_pads_host[i] != 0; }
-    if (any) if (int r = upload_ints(h, v, &nv, st)) return r;
+    if (any) if (int r = upload_ints(h, v, &P.nv, st)) return r;
   }
   WS_CHECK();
-  // results land in arena buffers (stable addresses -> graph-capturable), then are copied to the caller
-  int32_t* r_tok = h->ws.get<int32_t>((size_t)B * how_many * L);
-  int32_t* r_len = h->ws.get<int32_t>((size_t)B * how_many);
-  float* r_lp = h->ws.get<float>((size_t)B * how_many * L);
-  WS_CHECK();
-  cudaStream_t user_st = st;
-  auto run = [&]() -> int {
-    // cross K/V of all decoder layers, once per image (shared by the beams)
-    if (int r = dec_project(h, D, enc_out, B, st)) return r;
-    KL(1, launch_beam_init(bb, B, beam, L, sos, st));
-    int src = 0;
-    // step 0: every beam row decodes [SOS]
-    D.s.anc = bb.anc[0];
-    if (int r = dec_step(h, D, 0, nullptr, bb.tokens[0], L, beam, nv, nullptr, logits, c.vocab, st)) return r;
-    KL(1, launch_logsoftmax_topk(logits, c.vocab, R, c.vocab, beam, topv, topi, nullptr, 0, 0, st));
-    KL(1, launch_beam_first(bb, topv, topi, B, beam, L, st));
-    int t_final = 2;
-    for (int t = 2; t < L; ++t) {
-      D.s.anc = bb.anc[src];
-      if (int r = dec_step(h, D, t - 1, nullptr, bb.tokens[src], L, beam, nv, nullptr, logits, c.vocab, st)) return r;
-      KL(1, launch_logsoftmax_topk(logits, c.vocab, R, c.vocab, beam, topv, topi, nullptr, 0, 0, st));
-      KL(1, launch_beam_step(bb, src, topv, topi, B, beam, L, t, eos, st));
-      src ^= 1;
-      t_final = t + 1;
-    }
-    KL(1, launch_beam_finalize(bb, src, B, beam, L, t_final, how_many, r_tok, r_len, r_lp, st));
-    return 0;
-  };
-  bool done = false;
-  if (h->use_graph && !nv && !h->profile) {
-    if (!h->gstream) {
-      CU(cudaStreamCreateWithFlags(&h->gstream, cudaStreamNonBlocking));
-      CU(cudaEventCreateWithFlags(&h->g_in, cudaEventDisableTiming));
-      CU(cudaEventCreateWithFlags(&h->g_out, cudaEventDisableTiming));
-    }
-    xn_handle::DecodeGraph* g = nullptr;
-    for (auto& e : h->graphs)
-      if (e.enc == enc_out && e.B == B && e.beam == beam && e.L == L && e.how_many == how_many && e.sos == sos && e.eos == eos &&
-          e.ws_base == h->ws.base && e.ws_cap == h->ws.cap) { g = &e; break; }
-    if (g) {          // hand over from the caller's stream to the graph stream
-      CU(cudaEventRecord(h->g_in, user_st));
-      CU(cudaStreamWaitEvent(h->gstream, h->g_in, 0));
-      st = h->gstream;
-    }
-    if (g && g->exec) {
-      CU(cudaGraphLaunch(g->exec, st));
-      h->launches += g->launches;
-      done = true;
-    } else if (g) {
-      // second identical call: capture the whole decode loop once, then replay it from now on
-      const int64_t l0 = h->launches;
-      CU(cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed));
-      const int rr = run();
-      cudaGraph_t graph = nullptr;
-      cudaError_t ce = cudaStreamEndCapture(st, &graph);
-      if (rr) { if (graph) cudaGraphDestroy(graph); return rr; }
-      if (ce != cudaSuccess) return h->fail(XN_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(ce));
-      g->launches = h->launches - l0;
-      h->launches = l0;
-      cudaError_t ie = cudaGraphInstantiate(&g->exec, graph, 0);
-      cudaGraphDestroy(graph);
-      if (ie != cudaSuccess) { g->exec = nullptr; return h->fail(XN_ERR_CUDA, "graph instantiate failed: %s", cudaGetErrorString(ie)); }
-      CU(cudaGraphLaunch(g->exec, st));
-      h->launches += g->launches;
-      done = true;
-    } else {
-      if (h->graphs.size() > 16) h->drop_graphs();
-      h->graphs.push_back({enc_out, B, beam, L, how_many, sos, eos, h->ws.base, h->ws.cap, nullptr, 0, 1});
-    }
-  }
-  if (done) {         // and back
-    CU(cudaEventRecord(h->g_out, h->gstream));
-    CU(cudaStreamWaitEvent(user_st, h->g_out, 0));
-    st = user_st;
-  }
-  if (!done) if (int r = run()) return r;
-  CU(cudaMemcpyAsync(out_tokens, r_tok, (size_t)B * how_many * L * 4, cudaMemcpyDeviceToDevice, st));
-  CU(cudaMemcpyAsync(out_len, r_len, (size_t)B * how_many * 4, cudaMemcpyDeviceToDevice, st));
-  CU(cudaMemcpyAsync(out_lp, r_lp, (size_t)B * how_many * L * 4, cudaMemcpyDeviceToDevice, st));
   return 0;
+}
+
+int beam_run(xn_handle* h, BeamPlan& P, const float* enc_out, int B, int beam, int L, int how_many, int sos, int eos,
+             cudaStream_t st) {
+  const xn_config& c = h->cfg;
+  const int R = B * beam;
+  DecBufs& D = P.D;
+  BeamBufs& bb = P.bb;
+  // cross K/V of all decoder layers, once per image (shared by the beams)
+  if (int r = dec_project(h, D, enc_out, B, st)) return r;
+  KL(1, launch_beam_init(bb, B, beam, L, sos, st));
+  int src = 0;
+  // step 0: every beam row decodes [SOS]
+  D.s.anc = bb.anc[0];
+  if (int r = dec_step(h, D, 0, nullptr, bb.tokens[0], L, beam, P.nv, nullptr, P.logits, c.vocab, st)) return r;
+  KL(1, launch_logsoftmax_topk(P.logits, c.vocab, R, c.vocab, beam, P.topv, P.topi, nullptr, 0, 0, st));
+  KL(1, launch_beam_first(bb, P.topv, P.topi, B, beam, L, st));
+  int t_final = 2;
+  for (int t = 2; t < L; ++t) {
+    D.s.anc = bb.anc[src];
+    if (int r = dec_step(h, D, t - 1, nullptr, bb.tokens[src], L, beam, P.nv, nullptr, P.logits, c.vocab, st)) return r;
+    KL(1, launch_logsoftmax_topk(P.logits, c.vocab, R, c.vocab, beam, P.topv, P.topi, nullptr, 0, 0, st));
+    KL(1, launch_beam_step(bb, src, P.topv, P.topi, B, beam, L, t, eos, st));
+    src ^= 1;
+    t_final = t + 1;
+  }
+  KL(1, launch_beam_finalize(bb, src, B, beam, L, t_final, how_many, P.r_tok, P.r_len, P.r_lp, st));
+  return 0;
+}
+
+int beam_copy_out(xn_handle* h, const BeamPlan& P, int B, int L, int how_many, int32_t* out_tokens, int32_t* out_len,
+                  float* out_lp, cudaStream_t st) {
+  CU(cudaMemcpyAsync(out_tokens, P.r_tok, (size_t)B * how_many * L * 4, cudaMemcpyDeviceToDevice, st));
+  CU(cudaMemcpyAsync(out_len, P.r_len, (size_t)B * how_many * 4, cudaMemcpyDeviceToDevice, st));
+  CU(cudaMemcpyAsync(out_lp, P.r_lp, (size_t)B * how_many * L * 4, cudaMemcpyDeviceToDevice, st));
+  return 0;
+}
+
+int beam_from_enc(xn_handle* h, const float* enc_out, int B, const int32_t* enc_pads_host, int beam, int L, int how_many,
+                  int sos, int eos, int32_t* out_tokens, int32_t* out_len, float* out_lp, cudaStream_t st, bool reset_ws) {
+  BeamPlan P;
+  if (int r = beam_plan(h, P, B, enc_pads_host, beam, L, how_many, st, reset_ws)) return r;
+  const xn_handle::GraphKey key{0, enc_out, B, beam, L, how_many, sos, eos, h->ws.base, h->ws.cap};
+  if (int r = run_graphed(h, key, P.nv == nullptr, st, [&](cudaStream_t s2) { return beam_run(h, P, enc_out, B, beam, L, how_many, sos, eos, s2); }))
+    return r;
+  return beam_copy_out(h, P, B, L, how_many, out_tokens, out_len, out_lp, st);
 }
 
 size_t beam_ws_bytes(const xn_config& c, int B, int beam, int L) {
@@ -877,7 +903,7 @@ int xn_finalize_weights(xn_handle* h, int precision) {
           if (to_bf16(W.qkv) || to_bf16(W.proj) || to_bf16(W.fc1) || to_bf16(W.fc2)) return XN_ERR_CUDA;
           if (!rc) {
             float* bt = nullptr;
-            CU(cudaMalloc(&bt, (size_t)23 * 23 * S.heads * sizeof(float)));
+            CU(cudaMalloc(&bt, (size_t)532 * S.heads * sizeof(float)));
             h->owned.push_back(bt);
             KL(1, launch_transpose_bias(W.rpb, bt, S.heads, 0));
             W.rpb_t = bt;
@@ -1063,17 +1089,35 @@ int xn_beam_search(xn_handle* h, const float* input, int B, const int32_t* enc_p
   float* fb = reinterpret_cast<float*>(top - enc_bytes - feat_bytes);
   h->ws.cap = (size_t)((top - enc_bytes - feat_bytes) - h->ws.base);
   int r = 0;
-  if (c.has_swin) {
-    if (enc_pads_host)
-      for (int i = 0; i < B && !r; ++i)
-        if (enc_pads_host[i] != 0) r = h->fail(XN_ERR_ARG, "End to End case have no padding");
-    if (!r) r = swin_forward(h, input, B, fb, st);
-    if (!r) r = enc_body(h, fb, B, nullptr, enc_out, st);
-  } else {
+  bool pads = false;
+  if (enc_pads_host)
+    for (int i = 0; i < B; ++i) pads |= enc_pads_host[i] != 0;
+  if (c.has_swin && pads) r = h->fail(XN_ERR_ARG, "End to End case have no padding");
+  if (!r && pads) {
+    // encoder padding (features-in model): per-image valid lengths are uploaded with a host sync -> plain stream order
     r = enc_body(h, input, B, enc_pads_host, enc_out, st);
+    if (!r) r = beam_from_enc(h, enc_out, B, enc_pads_host, beam, max_len, how_many, sos_idx, eos_idx, out_tokens, out_len,
+                              out_logprob, st, true);
+    h->ws.cap = keep;
+    return r;
   }
-  if (!r) r = beam_from_enc(h, enc_out, B, c.has_swin ? nullptr : enc_pads_host, beam, max_len, how_many, sos_idx, eos_idx,
-                            out_tokens, out_len, out_logprob, st, true);
+  BeamPlan P;
+  // the beam buffers are carved from the bottom of the arena, where the Swin / encoder chunks also put their scratch:
+  // both run strictly before the decoder, in stream order
+  if (!r) r = beam_plan(h, P, B, nullptr, beam, max_len, how_many, st, true);
+  if (!r) {
+    const xn_handle::GraphKey key{1, input, B, beam, max_len, how_many, sos_idx, eos_idx, h->ws.base, keep};
+    r = run_graphed(h, key, true, st, [&](cudaStream_t s2) -> int {
+      if (c.has_swin) {
+        if (int rr = swin_forward(h, input, B, fb, s2)) return rr;
+        if (int rr = enc_body(h, fb, B, nullptr, enc_out, s2)) return rr;
+      } else {
+        if (int rr = enc_body(h, input, B, nullptr, enc_out, s2)) return rr;
+      }
+      return beam_run(h, P, enc_out, B, beam, max_len, how_many, sos_idx, eos_idx, s2);
+    });
+  }
+  if (!r) r = beam_copy_out(h, P, B, max_len, how_many, out_tokens, out_len, out_logprob, st);
   h->ws.cap = keep;
   return r;
 }
@@ -1192,10 +1236,10 @@ int xn_op_window_attention(xn_handle* h, const float* qkv, const float* bias_tab
     return XN_OK;
   }
   const size_t n = (size_t)B * H * H * C;
-  if (int r = ensure_ws(h, n * 4 * 2 + 8192 + (size_t)529 * heads * 4, st)) return r;
+  if (int r = ensure_ws(h, n * 4 * 2 + 8192 + (size_t)532 * heads * 4, st)) return r;
   bf16* qb = h->ws.get<bf16>(3 * n);
   bf16* ob = h->ws.get<bf16>(n);
-  float* bias_t = h->ws.get<float>((size_t)529 * heads);
+  float* bias_t = h->ws.get<float>((size_t)532 * heads);
   KL(1, launch_transpose_bias(bias_table, bias_t, heads, st));
   bias_table = bias_t;
   if (precision == XN_PREC_FP16) {

@@ -79,7 +79,7 @@ cudaError_t launch_cast(const float* x, T* y, long n, cudaStream_t st);
 template <typename T>
 cudaError_t launch_window_attention(const T* qkv, const float* bias_table, T* out, int B, int H, int C,
                                     int heads, int shift, cudaStream_t st);
-// tensor-core (mma.sync) variant for the 16-bit modes; takes the bias table transposed to (heads, 529)
+// tensor-core (mma.sync) variant for the 16-bit modes; takes the derived bias table (heads, 532) x log2(e) built by launch_transpose_bias
 template <typename T>
 cudaError_t launch_window_attention_mma(const T* qkv, const float* bias_t, T* out, int B, int H, int C,
                                         int heads, int shift, cudaStream_t st);

@@ -14,6 +14,7 @@
 // 144-row window does not map onto 128-row UMMA tiles without 44% padding, and the kernel is
 // bounded by its Q/K/V reads, not by the MMA rate.)
 #include <cuda_fp16.h>
+#include <algorithm>
 #include "kernels.h"
 #include "common.cuh"
 
@@ -61,180 +62,252 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-// bias_t is the relative-position table transposed to (heads, 529) so a head's column is contiguous
-// kHeadsPerCta: 3 for Swin-L (6/12/24/48 heads), 2 or 1 for other head counts
+__device__ __forceinline__ void ldsm_x2(uint32_t (&r)[2], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0,%1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(addr));
+}
+__device__ __forceinline__ float ex2_ftz(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+constexpr int kBiasPitch = 532;                  // floats per head in the derived table (16-byte multiple)
+constexpr int kLPitch = 24;                      // 16-bit elements per row of the label tile (48 B: conflict-free ldmatrix)
+constexpr float kLabelVal = 24.0f;               // label one-hot magnitude: 24*24 = 576 -> mask = -576 * scale = -101.8 per mismatching axis
+constexpr float kLog2e = 1.4426950408889634f;
+
+// bias_l2 is the relative-position table transposed to (heads, 532) and multiplied by log2(e) (derived once per
+// weight load), so the softmax runs in the exp2 domain.
+//
+// Persistent CTAs loop over items = (window, group of kHeadsPerCta heads), head group fastest so that CTAs running
+// side by side share the 128-byte lines of a token's QKV row.  Q/K/V of the next head -- or of the next item's first
+// head -- stream into the other smem buffer with cp.async while the current head is computed; the per-item metadata
+// (token rows, label tile, bias tables) is double-buffered by item parity.
+//
+// The shift mask costs no ALU work: every token carries a 4-wide "label" row  24 * [y<6, y>=6, x<6, x>=6]  (only on
+// the axes where the window straddles the cyclic seam; [1,0] otherwise), the score accumulators start at -2*576 and
+// one extra k16 MMA step adds 576 per matching axis: same region -> 0, different region -> <= -576 (x scale = -101.8,
+// where the reference adds -100; both vanish in the softmax).  The row sum comes out of the P.V MMA through an
+// all-ones B fragment, i.e. it is the sum of the rounded probabilities that are actually multiplied with V.
 template <typename T, int kHeadsPerCta>
 __global__ void __launch_bounds__(kMmaThreads, 2) window_attention_mma_kernel(const T* __restrict__ qkv,
-                                                                              const float* __restrict__ bias_t,
+                                                                              const float* __restrict__ bias_l2,
                                                                               T* __restrict__ out, int H, int C, int heads,
-                                                                              int shift) {
+                                                                              int shift, int n_items) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  // layout: stage[2] x {Q,K,V} x [144][40] 16-bit | bias[kHeadsPerCta][532] f32 | jinfo[144] | tok[144]
+  // layout: stage[2] x {Q,K,V} x [144][40] 16-bit | bias[2][kHeadsPerCta][532] f32 | label[2][144][24] 16-bit | tok[2][144] | jneg[144]
   constexpr int kMatElems = kWinTok * kRowPad;
   T* stage = reinterpret_cast<T*>(smem_raw);
   float* bt_all = reinterpret_cast<float*>(smem_raw + 2 * 3 * kMatElems * sizeof(T));
-  int* jinfo = reinterpret_cast<int*>(bt_all + kHeadsPerCta * 532);   // (yj*23 + xj) | region label << 16, per key token
-  int* tok = jinfo + kWinTok;
+  T* lab_all = reinterpret_cast<T*>(bt_all + 2 * kHeadsPerCta * kBiasPitch);
+  int* tok_all = reinterpret_cast<int*>(lab_all + 2 * kWinTok * kLPitch);
+  int* jneg = tok_all + 2 * kWinTok;             // byte offset -4 * (yj*23 + xj) per key token
 
-  const int nWs = H / kWin;
-  const int wid = blockIdx.x, head0 = blockIdx.y * kHeadsPerCta;
-  const int b = wid / (nWs * nWs), wrem = wid % (nWs * nWs);
-  const int wy = wrem / nWs, wx = wrem % nWs;
+  const int nWs = H / kWin, nW = nWs * nWs, ngroups = heads / kHeadsPerCta;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-
-  auto token_row = [&](int t) {              // global token row of window token t (roll(-shift): shifted[h] = x[h+shift])
-    const int ty = t / kWin, tx = t % kWin;
-    const int h = (wy * kWin + ty + shift) % H, w = (wx * kWin + tx + shift) % H;
-    return (b * H + h) * H + w;
-  };
-  // each thread stages 6 (token, q/k/v, 16-byte chunk) slots per head; offsets are recomputed per call
-  // (a few integer ops) rather than kept live across the MMA section
+  const int my_ty = tid / kWin, my_tx = tid % kWin;          // token handled in the metadata phase (tid < 144)
   const uint32_t stage_u32 = (uint32_t)__cvta_generic_to_shared(stage);
-  auto issue_loads = [&](int hh, int bufi) {
+  const uint32_t lab_u32 = (uint32_t)__cvta_generic_to_shared(lab_all);
+  const uint32_t bt_u32 = (uint32_t)__cvta_generic_to_shared(bt_all);
+
+  // per-item metadata into buffer mb; returns nothing (the mask flag is recomputed from the item where needed)
+  auto item_masked = [&](int item) {
+    const int wid = item / ngroups, wrem = wid % nW;
+    return shift > 0 && (wrem / nWs == nWs - 1 || wrem % nWs == nWs - 1);
+  };
+  auto compute_meta = [&](int item, int mb) {
+    const int g = item % ngroups, wid = item / ngroups;
+    const int b = wid / nW, wrem = wid - b * nW;
+    const int wy = wrem / nWs, wx = wrem - wy * nWs;
+    if (tid < kWinTok) {
+      int h = wy * kWin + my_ty + shift, w = wx * kWin + my_tx + shift;   // roll(-shift): shifted[h] = x[h + shift]
+      if (h >= H) h -= H;
+      if (w >= H) w -= H;
+      tok_all[mb * kWinTok + tid] = (b * H + h) * H + w;
+      const bool ey = shift > 0 && wy == nWs - 1, ex = shift > 0 && wx == nWs - 1;
+      const float ya = ey ? (my_ty < kWin - shift ? kLabelVal : 0.f) : kLabelVal, yb = ey ? (my_ty < kWin - shift ? 0.f : kLabelVal) : 0.f;
+      const float xa = ex ? (my_tx < kWin - shift ? kLabelVal : 0.f) : kLabelVal, xb = ex ? (my_tx < kWin - shift ? 0.f : kLabelVal) : 0.f;
+      uint2 v;
+      v.x = Mma16<T>::pack(ya, yb);
+      v.y = Mma16<T>::pack(xa, xb);
+      *reinterpret_cast<uint2*>(lab_all + (mb * kWinTok + tid) * kLPitch) = v;
+    }
+    const float* src = bias_l2 + (long)g * kHeadsPerCta * kBiasPitch;
+    for (int i = tid; i < kHeadsPerCta * (kBiasPitch / 4); i += kMmaThreads)
+      cp_async16(bt_u32 + (uint32_t)((mb * kHeadsPerCta * kBiasPitch + i * 4) * sizeof(float)), src + i * 4);
+  };
+  auto issue_loads = [&](int item, int hh, int mb, int bufi) {
     const uint32_t base = stage_u32 + (uint32_t)(bufi * 3 * kMatElems * sizeof(T));
-    const T* src = qkv + (head0 + hh) * kHeadDim;
+    const T* src = qkv + ((item % ngroups) * kHeadsPerCta + hh) * kHeadDim;
+    const int* tk = tok_all + mb * kWinTok;
 #pragma unroll
     for (int k = 0; k < 6; ++k) {
       const int i = tid + k * kMmaThreads;
       const int t = i / 12, r = i % 12, which = r >> 2, ch = r & 3;
       cp_async16(base + (uint32_t)((which * kMatElems + t * kRowPad + ch * 8) * sizeof(T)),
-                 src + (long)token_row(t) * 3 * C + which * C + ch * 8);
+                 src + (long)tk[t] * 3 * C + which * C + ch * 8);
     }
     cp_async_commit();
   };
-  issue_loads(0, 0);
 
-  if (tid < kWinTok) {
-    const int ty = tid / kWin, tx = tid % kWin;
-    const int hs = wy * kWin + ty, ws_ = wx * kWin + tx;
-    int lh = 0, lw = 0;
-    if (shift > 0) {
-      lh = hs < H - kWin ? 0 : (hs < H - shift ? 1 : 2);
-      lw = ws_ < H - kWin ? 0 : (ws_ < H - shift ? 1 : 2);
-    }
-    jinfo[tid] = (ty * (2 * kWin - 1) + tx) | ((lh * 3 + lw) << 16);
-    tok[tid] = token_row(tid);
-  }
-  for (int i = tid; i < kHeadsPerCta * kBiasN; i += kMmaThreads) {
-    const int hh = i / kBiasN, e = i % kBiasN;
-    bt_all[hh * 532 + e] = bias_t[(long)(head0 + hh) * kBiasN + e];
-  }
+  // one-time: zero the label tiles (columns 4..23 stay zero for ever) and the key offsets
+  for (int i = tid; i < 2 * kWinTok * kLPitch / 2; i += kMmaThreads) reinterpret_cast<uint32_t*>(lab_all)[i] = 0u;
+  if (tid < kWinTok) jneg[tid] = -4 * (my_ty * (2 * kWin - 1) + my_tx);
+  __syncthreads();
+  int item = blockIdx.x;
+  if (item >= n_items) return;
+  compute_meta(item, 0);
+  __syncthreads();
+  issue_loads(item, 0, 0, 0);
 
   const int m0 = warp * 16;
   const int r0 = m0 + (lane >> 2), r1 = r0 + 8;
-  const float scale = 0.17677669529663687f;      // 32^-0.5
+  const float sl = 0.17677669529663687f * kLog2e;      // 32^-0.5 * log2(e)
+  // byte offset of (row token) + centre of the 23 x 23 table; the key offset jneg is added per column
+  const int rowoff0 = 4 * ((r0 / kWin) * (2 * kWin - 1) + (r0 % kWin) + (kWin - 1) * (2 * kWin - 1) + (kWin - 1));
+  const int rowoff1 = 4 * ((r1 / kWin) * (2 * kWin - 1) + (r1 % kWin) + (kWin - 1) * (2 * kWin - 1) + (kWin - 1));
+  const uint32_t ones = Mma16<T>::pack(1.0f, 1.0f);
 
-  for (int hh = 0; hh < kHeadsPerCta; ++hh) {
-    const int bufi = hh & 1;
-    cp_async_wait<0>();
-    __syncthreads();                              // head hh landed; everyone is done with the other buffer
-    if (hh + 1 < kHeadsPerCta) issue_loads(hh + 1, bufi ^ 1);
+  int unit = 0;
+  for (int k = 0; item < n_items; item += gridDim.x, ++k) {
+    const int mb = k & 1;
+    const int next_item = item + gridDim.x;
+    const bool has_next = next_item < n_items;
+    const bool masked = item_masked(item);
+    const int* tok = tok_all + mb * kWinTok;
+    const int head0 = (item % ngroups) * kHeadsPerCta;
+#pragma unroll 1
+    for (int hh = 0; hh < kHeadsPerCta; ++hh, ++unit) {
+      const int bufi = unit & 1;
+      cp_async_wait<0>();
+      __syncthreads();                              // this unit landed; everyone is done with the other buffer
+      if (hh == 0 && has_next) {
+        compute_meta(next_item, mb ^ 1);            // its cp.async traffic joins the next commit group
+        if (kHeadsPerCta == 1) __syncthreads();
+      }
+      if (hh + 1 < kHeadsPerCta) issue_loads(item, hh + 1, mb, bufi ^ 1);
+      else if (has_next) issue_loads(next_item, 0, mb ^ 1, bufi ^ 1);
 
-    const uint32_t q_base = stage_u32 + (uint32_t)(bufi * 3 * kMatElems * sizeof(T));
-    const uint32_t k_base = q_base + (uint32_t)(kMatElems * sizeof(T));
-    const uint32_t v_base = k_base + (uint32_t)(kMatElems * sizeof(T));
-    T* Qs = stage + bufi * 3 * kMatElems;
-    const float* bt = bt_all + hh * 532;
+      const uint32_t q_base = stage_u32 + (uint32_t)(bufi * 3 * kMatElems * sizeof(T));
+      const uint32_t k_base = q_base + (uint32_t)(kMatElems * sizeof(T));
+      const uint32_t v_base = k_base + (uint32_t)(kMatElems * sizeof(T));
+      T* Qs = stage + bufi * 3 * kMatElems;
 
-    // A fragments of Q for the two k16 steps (d 0-15, 16-31)
-    uint32_t qa[2][4];
-    {
-      const int row = m0 + (lane & 7) + ((lane >> 3) & 1) * 8;
-      const int col = (lane >> 4) * 8;
-      ldsm_x4(qa[0], q_base + (row * kRowPad + col) * 2);
-      ldsm_x4(qa[1], q_base + (row * kRowPad + col + 16) * 2);
-    }
-    float s[18][4];
+      float s[18][4];
+      {
+        const int row = m0 + (lane & 7) + ((lane >> 3) & 1) * 8;
+        const int col = (lane >> 4) * 8;
+        if (masked) {
+          const uint32_t l_base = lab_u32 + (uint32_t)(mb * kWinTok * kLPitch * sizeof(T));
+          uint32_t la[4];
+          ldsm_x4(la, l_base + (row * kLPitch + col) * 2);
 #pragma unroll
-    for (int nt = 0; nt < 18; ++nt) {
-      s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
-      uint32_t kb[4];     // {b0,b1} for d 0-15 and {b0,b1} for d 16-31 of keys nt*8 .. nt*8+7
-      const int krow = nt * 8 + (lane & 7), kcol = (lane >> 3) * 8;
-      ldsm_x4(kb, k_base + (krow * kRowPad + kcol) * 2);
-      Mma16<T>::mma(s[nt], qa[0], kb[0], kb[1]);
-      Mma16<T>::mma(s[nt], qa[1], kb[2], kb[3]);
-    }
+          for (int nt = 0; nt < 18; ++nt) {
+            s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = -2.0f * kLabelVal * kLabelVal;
+            uint32_t lb[2];
+            ldsm_x2(lb, l_base + ((nt * 8 + (lane & 7)) * kLPitch + ((lane >> 3) & 1) * 8) * 2);
+            Mma16<T>::mma(s[nt], la, lb[0], lb[1]);
+          }
+        } else {
+#pragma unroll
+          for (int nt = 0; nt < 18; ++nt) s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+        }
+        // A fragments of Q for the two k16 steps (d 0-15, 16-31)
+        uint32_t qa[2][4];
+        ldsm_x4(qa[0], q_base + (row * kRowPad + col) * 2);
+        ldsm_x4(qa[1], q_base + (row * kRowPad + col + 16) * 2);
+#pragma unroll
+        for (int nt = 0; nt < 18; ++nt) {
+          uint32_t kb[4];     // {b0,b1} for d 0-15 and {b0,b1} for d 16-31 of keys nt*8 .. nt*8+7
+          const int krow = nt * 8 + (lane & 7), kcol = (lane >> 3) * 8;
+          ldsm_x4(kb, k_base + (krow * kRowPad + kcol) * 2);
+          Mma16<T>::mma(s[nt], qa[0], kb[0], kb[1]);
+          Mma16<T>::mma(s[nt], qa[1], kb[2], kb[3]);
+        }
+      }
 
-    // scale + relative-position bias + shift mask, then the row softmax (rows r0, r1 = r0 + 8)
-    // bias index = (yi - yj + 11)*23 + (xi - xj + 11) = rowbase_i - (yj*23 + xj)
-    const int i0 = jinfo[r0], i1 = jinfo[r1];
-    const float* bt0 = bt + (i0 & 0xffff) + (kWin - 1) * (2 * kWin - 1) + (kWin - 1);
-    const float* bt1 = bt + (i1 & 0xffff) + (kWin - 1) * (2 * kWin - 1) + (kWin - 1);
-    const int l0 = i0 >> 16, l1 = i1 >> 16;
-    float mx0 = -INFINITY, mx1 = -INFINITY;
+      // scale + relative-position bias (exp2 domain), then the row softmax (rows r0, r1 = r0 + 8)
+      // bias index = (yi - yj + 11)*23 + (xi - xj + 11) = rowoff_i + jneg_j
+      const unsigned char* bt = reinterpret_cast<const unsigned char*>(bt_all + (mb * kHeadsPerCta + hh) * kBiasPitch);
+      const unsigned char* bt0 = bt + rowoff0;
+      const unsigned char* bt1 = bt + rowoff1;
+      float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
-    for (int nt = 0; nt < 18; ++nt) {
-      const int2 jj = *reinterpret_cast<const int2*>(&jinfo[nt * 8 + (lane & 3) * 2]);
-      const int ja = jj.x & 0xffff, jb = jj.y & 0xffff, la = jj.x >> 16, lb = jj.y >> 16;
-      float a0 = fmaf(s[nt][0], scale, bt0[-ja]);
-      float a1 = fmaf(s[nt][1], scale, bt0[-jb]);
-      float c0 = fmaf(s[nt][2], scale, bt1[-ja]);
-      float c1 = fmaf(s[nt][3], scale, bt1[-jb]);
-      if (la != l0) a0 += -100.0f;
-      if (lb != l0) a1 += -100.0f;
-      if (la != l1) c0 += -100.0f;
-      if (lb != l1) c1 += -100.0f;
-      s[nt][0] = a0; s[nt][1] = a1; s[nt][2] = c0; s[nt][3] = c1;
-      mx0 = fmaxf(mx0, fmaxf(a0, a1));
-      mx1 = fmaxf(mx1, fmaxf(c0, c1));
-    }
-    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
-    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
-    float sum0 = 0.f, sum1 = 0.f;
-    uint32_t pa[18][2];   // packed probabilities: [nt][0] = row r0 (cols 2q,2q+1), [nt][1] = row r1
+      for (int nt = 0; nt < 18; ++nt) {
+        const int jo = jneg[nt * 8 + (lane & 3) * 2];          // key 2q; key 2q+1 sits 4 bytes lower (same window row)
+        const float a0 = fmaf(s[nt][0], sl, *reinterpret_cast<const float*>(bt0 + jo));
+        const float a1 = fmaf(s[nt][1], sl, *reinterpret_cast<const float*>(bt0 + jo - 4));
+        const float c0 = fmaf(s[nt][2], sl, *reinterpret_cast<const float*>(bt1 + jo));
+        const float c1 = fmaf(s[nt][3], sl, *reinterpret_cast<const float*>(bt1 + jo - 4));
+        s[nt][0] = a0; s[nt][1] = a1; s[nt][2] = c0; s[nt][3] = c1;
+        mx0 = fmaxf(mx0, fmaxf(a0, a1));
+        mx1 = fmaxf(mx1, fmaxf(c0, c1));
+      }
+      mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+      mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+      uint32_t pa[18][2];   // packed probabilities: [nt][0] = row r0 (cols 2q,2q+1), [nt][1] = row r1
 #pragma unroll
-    for (int nt = 0; nt < 18; ++nt) {
-      const float e0 = __expf(s[nt][0] - mx0), e1 = __expf(s[nt][1] - mx0);
-      const float e2 = __expf(s[nt][2] - mx1), e3 = __expf(s[nt][3] - mx1);
-      sum0 += e0 + e1; sum1 += e2 + e3;
-      pa[nt][0] = Mma16<T>::pack(e0, e1);
-      pa[nt][1] = Mma16<T>::pack(e2, e3);
-    }
-    sum0 += __shfl_xor_sync(0xffffffffu, sum0, 1); sum0 += __shfl_xor_sync(0xffffffffu, sum0, 2);
-    sum1 += __shfl_xor_sync(0xffffffffu, sum1, 1); sum1 += __shfl_xor_sync(0xffffffffu, sum1, 2);
+      for (int nt = 0; nt < 18; ++nt) {
+        pa[nt][0] = Mma16<T>::pack(ex2_ftz(s[nt][0] - mx0), ex2_ftz(s[nt][1] - mx0));
+        pa[nt][1] = Mma16<T>::pack(ex2_ftz(s[nt][2] - mx1), ex2_ftz(s[nt][3] - mx1));
+      }
 
-    // O = P V : 9 k16 steps over the keys, 4 n8 tiles over head_dim
-    float o[4][4];
+      // O = P V : 9 k16 steps over the keys, 4 n8 tiles over head_dim + one all-ones tile for the row sums
+      float o[5][4];
 #pragma unroll
-    for (int n = 0; n < 4; ++n) o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.f;
+      for (int n = 0; n < 5; ++n) o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.f;
 #pragma unroll
-    for (int ks = 0; ks < 9; ++ks) {
-      uint32_t a[4] = {pa[2 * ks][0], pa[2 * ks][1], pa[2 * ks + 1][0], pa[2 * ks + 1][1]};
-      const int vrow = ks * 16 + ((lane >> 3) & 1) * 8 + (lane & 7);
-      const int vcol = (lane >> 4) * 8;
-      uint32_t vb0[4], vb1[4];                     // d 0-15 and d 16-31
-      ldsm_x4_trans(vb0, v_base + (vrow * kRowPad + vcol) * 2);
-      ldsm_x4_trans(vb1, v_base + (vrow * kRowPad + vcol + 16) * 2);
-      Mma16<T>::mma(o[0], a, vb0[0], vb0[1]);
-      Mma16<T>::mma(o[1], a, vb0[2], vb0[3]);
-      Mma16<T>::mma(o[2], a, vb1[0], vb1[1]);
-      Mma16<T>::mma(o[3], a, vb1[2], vb1[3]);
-    }
-    const float inv0 = 1.0f / sum0, inv1 = 1.0f / sum1;
+      for (int ks = 0; ks < 9; ++ks) {
+        uint32_t a[4] = {pa[2 * ks][0], pa[2 * ks][1], pa[2 * ks + 1][0], pa[2 * ks + 1][1]};
+        const int vrow = ks * 16 + ((lane >> 3) & 1) * 8 + (lane & 7);
+        const int vcol = (lane >> 4) * 8;
+        uint32_t vb0[4], vb1[4];                     // d 0-15 and d 16-31
+        ldsm_x4_trans(vb0, v_base + (vrow * kRowPad + vcol) * 2);
+        ldsm_x4_trans(vb1, v_base + (vrow * kRowPad + vcol + 16) * 2);
+        Mma16<T>::mma(o[0], a, vb0[0], vb0[1]);
+        Mma16<T>::mma(o[1], a, vb0[2], vb0[3]);
+        Mma16<T>::mma(o[2], a, vb1[0], vb1[1]);
+        Mma16<T>::mma(o[3], a, vb1[2], vb1[3]);
+        Mma16<T>::mma(o[4], a, ones, ones);
+      }
+      const float inv0 = 1.0f / o[4][0], inv1 = 1.0f / o[4][2];
 
-    // stage the warp's 16 x 32 output tile in its own (now dead) Q rows, then 64-byte row stores
-    __syncwarp();
-    uint32_t* qw = reinterpret_cast<uint32_t*>(Qs);
+      // stage the warp's 16 x 32 output tile in its own (now dead) Q rows, then 64-byte row stores
+      __syncwarp();
+      uint32_t* qw = reinterpret_cast<uint32_t*>(Qs);
 #pragma unroll
-    for (int n = 0; n < 4; ++n) {
-      const int col = n * 8 + (lane & 3) * 2;
-      qw[(r0 * kRowPad + col) >> 1] = Mma16<T>::pack(o[n][0] * inv0, o[n][1] * inv0);
-      qw[(r1 * kRowPad + col) >> 1] = Mma16<T>::pack(o[n][2] * inv1, o[n][3] * inv1);
-    }
-    __syncwarp();
+      for (int n = 0; n < 4; ++n) {
+        const int col = n * 8 + (lane & 3) * 2;
+        qw[(r0 * kRowPad + col) >> 1] = Mma16<T>::pack(o[n][0] * inv0, o[n][1] * inv0);
+        qw[(r1 * kRowPad + col) >> 1] = Mma16<T>::pack(o[n][2] * inv1, o[n][3] * inv1);
+      }
+      __syncwarp();
 #pragma unroll
-    for (int it = 0; it < 2; ++it) {
-      const int row = m0 + it * 8 + (lane >> 2), ch = lane & 3;
-      const uint4 v = *reinterpret_cast<const uint4*>(Qs + row * kRowPad + ch * 8);
-      *reinterpret_cast<uint4*>(out + (long)tok[row] * C + (head0 + hh) * kHeadDim + ch * 8) = v;
+      for (int it = 0; it < 2; ++it) {
+        const int row = m0 + it * 8 + (lane >> 2), ch = lane & 3;
+        const uint4 v = *reinterpret_cast<const uint4*>(Qs + row * kRowPad + ch * 8);
+        *reinterpret_cast<uint4*>(out + (long)tok[row] * C + (head0 + hh) * kHeadDim + ch * 8) = v;
+      }
     }
   }
 }
 
+static int wa_sm_count() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
 template <typename T, int HPC>
-static cudaError_t launch_wa_hpc(const T* qkv, const float* bias_t, T* out, int B, int H, int C, int heads, int shift,
+static cudaError_t launch_wa_hpc(const T* qkv, const float* bias_l2, T* out, int B, int H, int C, int heads, int shift,
                                  cudaStream_t st) {
-  const size_t smem = 2 * 3 * kWinTok * kRowPad * sizeof(T) + HPC * 532 * sizeof(float) + 2 * kWinTok * sizeof(int);
+  const size_t smem = 2 * 3 * kWinTok * kRowPad * sizeof(T) + 2 * HPC * kBiasPitch * sizeof(float) +
+                      2 * kWinTok * kLPitch * sizeof(T) + 3 * kWinTok * sizeof(int);
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(window_attention_mma_kernel<T, HPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -242,17 +315,23 @@ static cudaError_t launch_wa_hpc(const T* qkv, const float* bias_t, T* out, int 
     configured = true;
   }
   const int nW = (H / kWin) * (H / kWin);
-  window_attention_mma_kernel<T, HPC><<<dim3(B * nW, heads / HPC), kMmaThreads, smem, st>>>(qkv, bias_t, out, H, C, heads, shift);
+  const int n_items = B * nW * (heads / HPC);
+  const int grid = std::min(n_items, 2 * wa_sm_count());
+  window_attention_mma_kernel<T, HPC><<<grid, kMmaThreads, smem, st>>>(qkv, bias_l2, out, H, C, heads, shift, n_items);
   return cudaGetLastError();
 }
 
 template <typename T>
-cudaError_t launch_window_attention_mma(const T* qkv, const float* bias_t, T* out, int B, int H, int C, int heads,
+cudaError_t launch_window_attention_mma(const T* qkv, const float* bias_l2, T* out, int B, int H, int C, int heads,
                                         int shift, cudaStream_t st) {
-  if (H % kWin || C != heads * kHeadDim) return cudaErrorInvalidValue;
-  if (heads % 3 == 0) return launch_wa_hpc<T, 3>(qkv, bias_t, out, B, H, C, heads, shift, st);
-  if (heads % 2 == 0) return launch_wa_hpc<T, 2>(qkv, bias_t, out, B, H, C, heads, shift, st);
-  return launch_wa_hpc<T, 1>(qkv, bias_t, out, B, H, C, heads, shift, st);
+  if (H % kWin || C != heads * kHeadDim || (shift != 0 && shift != kWin / 2)) return cudaErrorInvalidValue;
+  const int nW = (H / kWin) * (H / kWin);
+  // three heads per item amortise the per-window metadata; small problems (batch-1 latency) take one head per item
+  // so that there are enough items to fill the machine
+  const bool wide = (long)B * nW * (heads / 3) >= 2L * wa_sm_count();
+  if (heads % 3 == 0 && wide) return launch_wa_hpc<T, 3>(qkv, bias_l2, out, B, H, C, heads, shift, st);
+  if (heads % 2 == 0 && (long)B * nW * (heads / 2) >= 2L * wa_sm_count()) return launch_wa_hpc<T, 2>(qkv, bias_l2, out, B, H, C, heads, shift, st);
+  return launch_wa_hpc<T, 1>(qkv, bias_l2, out, B, H, C, heads, shift, st);
 }
 template cudaError_t launch_window_attention_mma<bf16>(const bf16*, const float*, bf16*, int, int, int, int, int, cudaStream_t);
 template cudaError_t launch_window_attention_mma<__half>(const __half*, const float*, __half*, int, int, int, int, int, cudaStream_t);
@@ -260,13 +339,16 @@ template cudaError_t launch_window_attention_mma<__half>(const __half*, const fl
 }  // namespace xn
 
 namespace xn {
-// (529, heads) relative-position table -> (heads, 529), once per weight load
+// (529, heads) relative-position table -> (heads, 532) * log2(e), once per weight load
 __global__ void transpose_bias_kernel(const float* __restrict__ t, float* __restrict__ o, int heads) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < kBiasN * heads) { const int e = i / heads, h = i % heads; o[h * kBiasN + e] = t[i]; }
+  if (i < kBiasPitch * heads) {
+    const int h = i / kBiasPitch, e = i % kBiasPitch;
+    o[i] = e < kBiasN ? t[e * heads + h] * kLog2e : 0.f;
+  }
 }
 cudaError_t launch_transpose_bias(const float* table, float* out, int heads, cudaStream_t st) {
-  transpose_bias_kernel<<<(kBiasN * heads + 255) / 256, 256, 0, st>>>(table, out, heads);
+  transpose_bias_kernel<<<(kBiasPitch * heads + 255) / 256, 256, 0, st>>>(table, out, heads);
   return cudaGetLastError();
 }
 }  // namespace xn

@@ -16,7 +16,12 @@ def main():
               ("s2.qkv", Bc * 2304, 1152, 384, 0, False), ("s2.fc1", Bc * 2304, 1536, 384, 1, False),
               ("s3.qkv", Bc * 576, 2304, 768, 0, False), ("s3.proj", Bc * 576, 768, 768, 0, True),
               ("s3.fc1", Bc * 576, 3072, 768, 1, False), ("s3.fc2", Bc * 576, 768, 3072, 0, True),
-              ("s4.fc1", Bc * 144, 6144, 1536, 1, False), ("big", 8192, 8192, 8192, 0, False)]
+              ("s4.fc1", Bc * 144, 6144, 1536, 1, False), ("big", 8192, 8192, 8192, 0, False),
+              # decoder-step shapes (rows = images x beam)
+              ("dec.dyn5", 6 * Bc, 2560, 512, 0, False), ("dec.wq", 6 * Bc, 512, 512, 0, False),
+              ("dec.wo", 6 * Bc, 512, 512, 0, True), ("dec.ff1", 6 * Bc, 2048, 512, 2, False),
+              ("dec.ff2", 6 * Bc, 512, 2048, 0, True), ("dec.red", 6 * Bc, 512, 1536, 0, True),
+              ("dec.vocab", 6 * Bc, 10000, 512, 0, False)]
     only = sys.argv[3].split(",") if len(sys.argv) > 3 and sys.argv[3] != "all" else None
     out16 = len(sys.argv) > 4 and sys.argv[4] == "out16"
     prec = "fp16" if out16 else "bf16"
@@ -36,7 +41,7 @@ def main():
             e.set_option("tc_debug", mode)
             e.op_linear(x, w, b, r, act, prec)
             e.set_option("profile", 1)
-            for _ in range(3):
+            for _ in range(10 if name.startswith("dec") else 3):
                 e.op_linear(x, w, b, r, act, prec)
             ms, fl, n = e.profile_read()
             e.set_option("profile", 0)
