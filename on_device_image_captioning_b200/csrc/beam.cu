@@ -22,13 +22,15 @@ __global__ void beam_init_kernel(BeamBufs bb, int B, int beam, int L, int sos) {
       bb.anc[s][(long)r * L + i] = r;
     }
     bb.len[s][r] = 1;
+    bb.cum[s][r] = 0.f;
+    bb.eos[s][r] = 0;
   }
   if (r == 0) *bb.all_done = 0;
 }
 
 // step 0 (:242-271): all beams of an image hold [SOS]; beam k takes the k-th best first word of row (b,0).
 __global__ void beam_first_kernel(BeamBufs bb, const float* __restrict__ top_val, const int* __restrict__ top_idx,
-                                  int B, int beam, int L) {
+                                  int B, int beam, int L, int eos) {
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= B * beam) return;
   const int b = r / beam, k = r % beam;
@@ -36,70 +38,82 @@ __global__ void beam_first_kernel(BeamBufs bb, const float* __restrict__ top_val
   bb.tokens[0][(long)r * L + 1] = top_idx[src];
   bb.lps[0][(long)r * L + 1] = top_val[src];
   bb.len[0][r] = 2;
+  bb.cum[0][r] = 0.f + top_val[src];                         // running history sum, same order as history.sum(-1)
+  bb.eos[0][r] = top_idx[src] == eos;
   bb.anc[0][(long)r * L + 0] = r;                            // every slot computed identical position-0 state
   bb.anc[0][(long)r * L + 1] = r;
 }
 
-// One loop iteration for time_step t (tokens 0..t-1 known, choosing token t)  (:295-397)
-__global__ void beam_step_kernel(BeamBufs bb, int src, const float* __restrict__ top_val,
-                                 const int* __restrict__ top_idx, int B, int beam, int L, int t, int eos) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+// One loop iteration for time_step t (tokens 0..t-1 known, choosing token t)  (:295-397).  One warp per image: the
+// beam^2 candidates live in lanes (two per lane for beam > 5), the sorted top-k is `beam` rounds of a warp arg-max
+// (descending, ties to the lower flat index, as torch.topk on the flattened (beam, beam) candidates), the histories are
+// copied lane-parallel.  cum / eos are the running history sum and "prefix contains EOS" flag of every beam: the running
+// sum performs exactly the additions of history.sum(-1) in the same order.
+__global__ void __launch_bounds__(128) beam_step_kernel(BeamBufs bb, int src, const float* __restrict__ top_val,
+                                                        const int* __restrict__ top_idx, int B, int beam, int L, int t, int eos) {
+  const int b = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (b >= B) return;
-  const int dst = src ^ 1;
+  const int dst = src ^ 1, nc = beam * beam;
   const int* tk = bb.tokens[src] + (long)b * beam * L;
   const float* lp = bb.lps[src] + (long)b * beam * L;
-  const int* ln = bb.len[src] + b * beam;
   const int* an = bb.anc[src] + (long)b * beam * L;
-  float cand[kMaxBeam * kMaxBeam];
-  float word_lp[kMaxBeam * kMaxBeam];
-  bool has_eos[kMaxBeam];
-  for (int k = 0; k < beam; ++k) {
-    bool e = false;
-    float cum = 0.f;
-    for (int i = 0; i < t; ++i) {
-      e = e || (tk[k * L + i] == eos);
-      cum += lp[k * L + i];                                  // cumul = history.sum(-1)  (:381)
-    }
-    has_eos[k] = e;
-    for (int w = 0; w < beam; ++w) {
+  float cand[2], wlp[2];
+  bool used[2];
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int c = lane + 32 * h;
+    cand[h] = -INFINITY; wlp[h] = 0.f; used[h] = c >= nc;
+    if (c < nc) {
+      const int k = c / beam, w = c % beam;
       float v = top_val[((long)(b * beam + k)) * beam + w];
-      if (e) v = (w == 0) ? 0.0f : -999.0f;                  // (:322-335)
-      word_lp[k * beam + w] = v;
-      cand[k * beam + w] = cum + v;
+      if (bb.eos[src][b * beam + k]) v = (w == 0) ? 0.0f : -999.0f;      // (:322-335)
+      wlp[h] = v;
+      cand[h] = bb.cum[src][b * beam + k] + v;                            // cumul = history.sum(-1)  (:381)
     }
   }
-  int pick[kMaxBeam];
-  unsigned long long used = 0ull;
+  int mypick = 0;
   for (int j = 0; j < beam; ++j) {                           // top-k of beam^2, sorted
-    int best = -1;
     float bv = 0.f;
-    for (int c = 0; c < beam * beam; ++c) {
-      if ((used >> c) & 1ull) continue;
-      if (best < 0 || cand[c] > bv) { best = c; bv = cand[c]; }
+    int bi = 0x7fffffff;
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+      if (!used[h] && (bi == 0x7fffffff || cand[h] > bv)) { bv = cand[h]; bi = lane + 32 * h; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (oi != 0x7fffffff && (bi == 0x7fffffff || ov > bv || (ov == bv && oi < bi))) { bv = ov; bi = oi; }
     }
-    used |= 1ull << best;
-    pick[j] = best;
+    if ((bi & 31) == lane) used[bi >> 5] = true;
+    if (lane == j) mypick = bi;
   }
   int* tko = bb.tokens[dst] + (long)b * beam * L;
   float* lpo = bb.lps[dst] + (long)b * beam * L;
-  int* lno = bb.len[dst] + b * beam;
   int* ano = bb.anc[dst] + (long)b * beam * L;
-  bool any_grew = false;
   for (int j = 0; j < beam; ++j) {
-    const int parent = pick[j] / beam, w = pick[j] % beam;
-    for (int i = 0; i < t; ++i) {
+    const int pick = __shfl_sync(0xffffffffu, mypick, j);
+    const int parent = pick / beam;
+    const float w0 = __shfl_sync(0xffffffffu, wlp[0], pick & 31), w1 = __shfl_sync(0xffffffffu, wlp[1], pick & 31);
+    const float c0 = __shfl_sync(0xffffffffu, cand[0], pick & 31), c1 = __shfl_sync(0xffffffffu, cand[1], pick & 31);
+    for (int i = lane; i < t; i += 32) {
       tko[j * L + i] = tk[parent * L + i];
       lpo[j * L + i] = lp[parent * L + i];
       ano[j * L + i] = an[parent * L + i];
     }
-    tko[j * L + t] = top_idx[((long)(b * beam + parent)) * beam + w];
-    lpo[j * L + t] = word_lp[parent * beam + w];
-    if (t < L) ano[j * L + t] = b * beam + j;               // the next step writes position t into slot j
-    const int nl = ln[parent] + (has_eos[parent] ? 0 : 1);  // (:384-395)
-    lno[j] = nl;
-    any_grew = any_grew || (nl == t + 1);
+    if (lane == 0) {
+      const int w = pick % beam;
+      const int tokn = top_idx[((long)(b * beam + parent)) * beam + w];
+      const bool pe = bb.eos[src][b * beam + parent] != 0;
+      tko[j * L + t] = tokn;
+      lpo[j * L + t] = pick < 32 ? w0 : w1;
+      if (t < L) ano[j * L + t] = b * beam + j;               // the next step writes position t into slot j
+      const int nl = bb.len[src][b * beam + parent] + (pe ? 0 : 1);   // (:384-395)
+      bb.len[dst][b * beam + j] = nl;
+      bb.cum[dst][b * beam + j] = pick < 32 ? c0 : c1;       // = cum[parent] + word log-prob
+      bb.eos[dst][b * beam + j] = pe || tokn == eos;
+      if (nl == t + 1) atomicExch(bb.all_done, 0);           // informational; the host does not poll it
+    }
   }
-  if (any_grew) atomicExch(bb.all_done, 0);                  // informational; the host does not poll it
 }
 
 // (:401-425)  score = cumul / len, best `how_many` beams, tokens [:len], log-probs zero padded.
@@ -141,13 +155,13 @@ cudaError_t launch_beam_init(const BeamBufs& bb, int B, int beam, int L, int sos
   return cudaGetLastError();
 }
 cudaError_t launch_beam_first(const BeamBufs& bb, const float* top_val, const int* top_idx, int B, int beam, int L,
-                              cudaStream_t st) {
-  beam_first_kernel<<<(B * beam + 127) / 128, 128, 0, st>>>(bb, top_val, top_idx, B, beam, L);
+                              int eos, cudaStream_t st) {
+  beam_first_kernel<<<(B * beam + 127) / 128, 128, 0, st>>>(bb, top_val, top_idx, B, beam, L, eos);
   return cudaGetLastError();
 }
 cudaError_t launch_beam_step(const BeamBufs& bb, int src, const float* top_val, const int* top_idx, int B, int beam,
                              int L, int t, int eos, cudaStream_t st) {
-  beam_step_kernel<<<(B + 63) / 64, 64, 0, st>>>(bb, src, top_val, top_idx, B, beam, L, t, eos);
+  beam_step_kernel<<<(B + 3) / 4, 128, 0, st>>>(bb, src, top_val, top_idx, B, beam, L, t, eos);
   return cudaGetLastError();
 }
 cudaError_t launch_beam_finalize(const BeamBufs& bb, int src, int B, int beam, int L, int t_final, int how_many,

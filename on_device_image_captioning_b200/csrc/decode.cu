@@ -30,6 +30,55 @@ cudaError_t launch_embed(const int64_t* tokens64, const int* tokens32, long tok_
   return cudaGetLastError();
 }
 
+// Row LayerNorm tail shared by the fused decoder kernels: every thread holds NV values of the row (any column
+// assignment), statistics over the whole CTA.  Same formula as layernorm_kernel (two-pass mean / variance, eps 1e-5).
+template <int NV>
+__device__ __forceinline__ void block_ln_stats(const float (&v)[NV], int d, float* red, float& mean, float& rstd) {
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) s += v[i];
+  mean = block_sum(s, red) / (float)d;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) { const float dd = v[i] - mean; q += dd * dd; }
+  rstd = 1.0f / sqrtf(block_sum(q, red) / (float)d + 1e-5f);
+}
+
+// embedding + LayerNorm of the first decoder layer in one pass (d == 4 * blockDim.x)
+template <typename T>
+__global__ void __launch_bounds__(128) embed_ln_kernel(const int64_t* __restrict__ t64, const int* __restrict__ t32, long tok_stride,
+                                                       int p, const float* __restrict__ emb, const float* __restrict__ pos,
+                                                       float* __restrict__ x, long ldx, const float* __restrict__ g,
+                                                       const float* __restrict__ be, T* __restrict__ xn, long ldn, int d) {
+  __shared__ float red[32];
+  const int r = blockIdx.x, c = threadIdx.x * 4;
+  const long tok = t64 ? (long)t64[r * tok_stride + p] : (long)t32[r * tok_stride + p];
+  const float sc = sqrtf((float)d);
+  const float4 e4 = *reinterpret_cast<const float4*>(emb + tok * d + c);
+  const float4 p4 = *reinterpret_cast<const float4*>(pos + (long)p * d + c);
+  float v[4] = {e4.x * sc + p4.x, e4.y * sc + p4.y, e4.z * sc + p4.z, e4.w * sc + p4.w};
+  *reinterpret_cast<float4*>(x + (long)r * ldx + c) = make_float4(v[0], v[1], v[2], v[3]);
+  float mean, rstd;
+  block_ln_stats<4>(v, d, red, mean, rstd);
+  const float4 g4 = *reinterpret_cast<const float4*>(g + c), b4 = *reinterpret_cast<const float4*>(be + c);
+  T* o = xn + (long)r * ldn + c;
+  o[0] = from_f32<T>((v[0] - mean) * rstd * g4.x + b4.x);
+  o[1] = from_f32<T>((v[1] - mean) * rstd * g4.y + b4.y);
+  o[2] = from_f32<T>((v[2] - mean) * rstd * g4.z + b4.z);
+  o[3] = from_f32<T>((v[3] - mean) * rstd * g4.w + b4.w);
+}
+template <typename T>
+cudaError_t launch_embed_ln(const int64_t* tokens64, const int* tokens32, long tok_stride, int p, const float* emb,
+                            const float* pos, float* x, long ldx, const float* gamma, const float* beta, T* xn, long ldn, int R,
+                            int d, cudaStream_t st) {
+  if (d != 512 || (ldx & 3)) return cudaErrorInvalidValue;
+  embed_ln_kernel<T><<<R, 128, 0, st>>>(tokens64, tokens32, tok_stride, p, emb, pos, x, ldx, gamma, beta, xn, ldn, d);
+  return cudaGetLastError();
+}
+template cudaError_t launch_embed_ln<float>(const int64_t*, const int*, long, int, const float*, const float*, float*, long, const float*, const float*, float*, long, int, int, cudaStream_t);
+template cudaError_t launch_embed_ln<bf16>(const int64_t*, const int*, long, int, const float*, const float*, float*, long, const float*, const float*, bf16*, long, int, int, cudaStream_t);
+template cudaError_t launch_embed_ln<f16>(const int64_t*, const int*, long, int, const float*, const float*, float*, long, const float*, const float*, f16*, long, int, int, cudaStream_t);
+
 // ------------------------------------------------------------------------------------------
 // Dynamic expansion, incremental (reference models/layers.py:152-204, restated per position):
 //   z[(i,e),j] = (q_e + c_i).K_j / sqrt(d)
@@ -40,16 +89,29 @@ cudaError_t launch_embed(const int64_t* tokens64, const int* tokens32, long tok_
 //   with wA[j] = sum_{i>=j,e} ab[(i,e)] Af[(i,e),j],  sA[e] = sum_i ab[(i,e)],  tA[i] = sum_e ab[(i,e)]
 // One CTA per row.
 // ------------------------------------------------------------------------------------------
+// When ln_out != nullptr (d == 2 * blockDim.x) the kernel also emits LayerNorm(x_out) in the operand type: the
+// decoder layer's norm_2 (reference layers.py:238-241), fused because this CTA already holds the whole row.
+template <typename T>
 __global__ void __launch_bounds__(256) dyn_exp_step_kernel(DecState s, int layer, int p, const float* __restrict__ qexp,
                                                            const float* __restrict__ bexp, int n_exp,
                                                            const int* __restrict__ row_len,
                                                            const float* __restrict__ x_in, long ldxi,
-                                                           float* __restrict__ x_out, long ldxo, int d) {
+                                                           float* __restrict__ x_out, long ldxo, int d,
+                                                           const float* __restrict__ ln_g, const float* __restrict__ ln_b,
+                                                           T* __restrict__ ln_out, long ldn) {
   extern __shared__ float sm[];
   const int r = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int P = s.P, np = p + 1;
+  auto ln_tail = [&](float v0, float v1, float* red) {       // columns tid and tid + 256
+    float v[2] = {v0, v1};
+    float mean, rstd;
+    block_ln_stats<2>(v, d, red, mean, rstd);
+    ln_out[(long)r * ldn + tid] = from_f32<T>((v0 - mean) * rstd * ln_g[tid] + ln_b[tid]);
+    ln_out[(long)r * ldn + tid + 256] = from_f32<T>((v1 - mean) * rstd * ln_g[tid + 256] + ln_b[tid + 256]);
+  };
   if (row_len && p >= row_len[r]) {            // padded position: the block contributes 0 (all-zero mask rows)
     for (int c = tid; c < d; c += blockDim.x) x_out[(long)r * ldxo + c] = x_in[(long)r * ldxi + c];
+    if (ln_out) ln_tail(x_in[(long)r * ldxi + tid], x_in[(long)r * ldxi + tid + 256], sm);
     return;
   }
   int* slot = reinterpret_cast<int*>(sm);      // [P]
@@ -187,6 +249,7 @@ __global__ void __launch_bounds__(256) dyn_exp_step_kernel(DecState s, int layer
   __syncthreads();
 
   // ---- phase C: the d-wide mixes
+  float keep[2] = {0.f, 0.f};
   for (int c = tid; c < d; c += blockDim.x) {
     float oa = 0.f, ob = 0.f;
     for (int j = 0; j < np; ++j) {
@@ -201,27 +264,35 @@ __global__ void __launch_bounds__(256) dyn_exp_step_kernel(DecState s, int layer
       ob = fmaf(sB[e], be, ob);
     }
     const float sg = sigmoidf_(cp[4 * d + c]);
-    x_out[(long)r * ldxo + c] = x_in[(long)r * ldxi + c] + (sg * oa + (1.0f - sg) * ob);
+    const float xo = x_in[(long)r * ldxi + c] + (sg * oa + (1.0f - sg) * ob);
+    x_out[(long)r * ldxo + c] = xo;
+    if (c == tid) keep[0] = xo; else if (c == tid + 256) keep[1] = xo;
   }
+  if (ln_out) ln_tail(keep[0], keep[1], red);
 }
 
+template <typename T>
 cudaError_t launch_dyn_exp_step(const DecState& s, int layer, int p, const float* qexp, const float* bexp, int n_exp,
                                 const int* row_len, const float* x_in, long ldxi, float* x_out, long ldxo, int d,
-                                int beam, cudaStream_t st) {
-  (void)beam;
+                                const float* ln_g, const float* ln_b, T* ln_out, long ldn, cudaStream_t st) {
   if (s.P > 128 || (d & 3) || n_exp > 64) return cudaErrorInvalidValue;
+  if (ln_out && d != 512) return cudaErrorInvalidValue;
   const size_t smem = (size_t)(s.P * 7 + n_exp * 3 + 4 * n_exp * s.P + 32 + 2 * s.P * s.P) * sizeof(float);
   if (smem > 48 * 1024) {
     static size_t configured = 0;
     if (smem > configured) {
-      cudaError_t e = cudaFuncSetAttribute(dyn_exp_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      cudaError_t e = cudaFuncSetAttribute(dyn_exp_step_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) return e;
       configured = smem;
     }
   }
-  dyn_exp_step_kernel<<<s.R, 256, smem, st>>>(s, layer, p, qexp, bexp, n_exp, row_len, x_in, ldxi, x_out, ldxo, d);
+  dyn_exp_step_kernel<T><<<s.R, 256, smem, st>>>(s, layer, p, qexp, bexp, n_exp, row_len, x_in, ldxi, x_out, ldxo, d, ln_g, ln_b,
+                                                 ln_out, ldn);
   return cudaGetLastError();
 }
+template cudaError_t launch_dyn_exp_step<float>(const DecState&, int, int, const float*, const float*, int, const int*, const float*, long, float*, long, int, const float*, const float*, float*, long, cudaStream_t);
+template cudaError_t launch_dyn_exp_step<bf16>(const DecState&, int, int, const float*, const float*, int, const int*, const float*, long, float*, long, int, const float*, const float*, bf16*, long, cudaStream_t);
+template cudaError_t launch_dyn_exp_step<f16>(const DecState&, int, int, const float*, const float*, int, const int*, const float*, long, float*, long, int, const float*, const float*, f16*, long, cudaStream_t);
 
 // ------------------------------------------------------------------------------------------
 // Cross attention for one query position per row (reference models/layers.py:266-295).
@@ -591,9 +662,97 @@ __global__ void __launch_bounds__(256) logsoftmax_topk_kernel(const float* __res
   }
 }
 
+// Register-resident variant for V <= 256 * 4 * kLsVec: the row is read from memory exactly once (float4 loads, all in
+// flight together), max / sum / top-k run on registers.  Same arithmetic as above: lp = (x - max) - log(sum exp(x - max)).
+constexpr int kLsVec = 10;             // float4 per thread: 256 * 40 = 10240 logits
+
+__global__ void __launch_bounds__(256) logsoftmax_topk_reg_kernel(const float* __restrict__ logits, long ld, int V, int k,
+                                                                  float* __restrict__ top_val, int* __restrict__ top_idx,
+                                                                  float* __restrict__ logprob, long ldlp, int write_mode) {
+  __shared__ float red[32];
+  __shared__ float wv[8];
+  __shared__ int wi[8];
+  __shared__ int win_idx;
+  const int r = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float* x = logits + (long)r * ld;
+  float v[kLsVec][4];
+#pragma unroll
+  for (int j = 0; j < kLsVec; ++j) {
+    const int i = (j * 256 + tid) * 4;
+    if (i + 3 < V) {
+      const float4 f = *reinterpret_cast<const float4*>(x + i);
+      v[j][0] = f.x; v[j][1] = f.y; v[j][2] = f.z; v[j][3] = f.w;
+    } else {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) v[j][e] = (i + e < V) ? x[i + e] : -INFINITY;
+    }
+  }
+  float lmax = -INFINITY;
+#pragma unroll
+  for (int j = 0; j < kLsVec; ++j) lmax = fmaxf(lmax, fmaxf(fmaxf(v[j][0], v[j][1]), fmaxf(v[j][2], v[j][3])));
+  const float mx = block_max(lmax, red);
+  float ls = 0.f;
+#pragma unroll
+  for (int j = 0; j < kLsVec; ++j)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) ls += expf(v[j][e] - mx);            // exp(-inf) = 0 for the padding slots
+  const float lse = logf(block_sum(ls, red));
+#pragma unroll
+  for (int j = 0; j < kLsVec; ++j) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) v[j][e] = (v[j][e] - mx) - lse;
+    const int i = (j * 256 + tid) * 4;
+    if (write_mode == 1) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+        if (i + e < V) logprob[(long)r * ldlp + i + e] = v[j][e];
+    }
+  }
+  for (int round = 0; round < k; ++round) {
+    float bv = -INFINITY;
+    int bi = 0x7fffffff;
+#pragma unroll
+    for (int j = 0; j < kLsVec; ++j)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int i = (j * 256 + tid) * 4 + e;
+        if (i < V && better(v[j][e], i, bv, bi)) { bv = v[j][e]; bi = i; }
+      }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (better(ov, oi, bv, bi)) { bv = ov; bi = oi; }
+    }
+    __syncthreads();                       // previous round's win_idx has been consumed
+    if (lane == 0) { wv[warp] = bv; wi[warp] = bi; }
+    __syncthreads();
+    if (tid == 0) {
+      float fv = wv[0];
+      int fi = wi[0];
+      for (int w = 1; w < 8; ++w)
+        if (better(wv[w], wi[w], fv, fi)) { fv = wv[w]; fi = wi[w]; }
+      top_val[(long)r * k + round] = fv;
+      top_idx[(long)r * k + round] = fi;
+      win_idx = fi;
+    }
+    __syncthreads();
+    const int w = win_idx;                 // the owner retires the winner
+#pragma unroll
+    for (int j = 0; j < kLsVec; ++j)
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+        if ((j * 256 + tid) * 4 + e == w) v[j][e] = -INFINITY;
+  }
+}
+
 cudaError_t launch_logsoftmax_topk(const float* logits, long ld, int rows, int V, int k, float* top_val, int* top_idx,
                                    float* logprob, long ldlp, int write_mode, cudaStream_t st) {
   if (k > kMaxTopK) return cudaErrorInvalidValue;
+  if (V <= 256 * 4 * kLsVec && (ld & 3) == 0 && (reinterpret_cast<uintptr_t>(logits) & 15) == 0) {
+    logsoftmax_topk_reg_kernel<<<rows, 256, 0, st>>>(logits, ld, V, k, top_val, top_idx, logprob, ldlp, write_mode);
+    return cudaGetLastError();
+  }
   logsoftmax_topk_kernel<<<rows, 256, 0, st>>>(logits, ld, V, k, top_val, top_idx, logprob, ldlp, write_mode);
   return cudaGetLastError();
 }

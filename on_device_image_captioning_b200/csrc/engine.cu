@@ -546,17 +546,23 @@ int dec_step_t(xn_handle* h, DecBufs& D, int p, const int64_t* tok64, const int*
   T* att = reinterpret_cast<T*>(D.att);
   T* hid = reinterpret_cast<T*>(D.hid);
   T* yn = reinterpret_cast<T*>(D.yn);
-  KL(1, launch_embed(tok64, tok32, tok_stride, p, h->emb, h->pos, D.x0, d, R, d, st));
+  const bool fuse_ln = d == 512;            // embedding + norm_1 of layer 0, dynamic expansion + norm_2: one kernel each
+  if (fuse_ln) KL(1, launch_embed_ln<T>(tok64, tok32, tok_stride, p, h->emb, h->pos, D.x0, d, h->dec[0].n1g, h->dec[0].n1b, xn, d, R, d, st));
+  else KL(1, launch_embed(tok64, tok32, tok_stride, p, h->emb, h->pos, D.x0, d, R, d, st));
   for (int l = 0; l < nd; ++l) {
     const DecLayerW& W = h->dec[l];
     const float* xin = l == 0 ? D.x0 : D.ycat + (size_t)(l - 1) * d;
     const long ldi = l == 0 ? d : ldc;
     float* xout = D.ycat + (size_t)l * d;
-    KL(1, launch_layernorm<T>(xin, ldi, W.n1g, W.n1b, xn, d, R, d, st));
+    if (!(fuse_ln && l == 0)) KL(1, launch_layernorm<T>(xin, ldi, W.n1g, W.n1b, xn, d, R, d, st));
     float* crow = D.s.cache + (((size_t)l * D.P + p) * R) * D.s.cw;
     if (int r = dec_lin<T>(h, xn, d, W.dyn5, nullptr, 0, crow, nullptr, D.s.cw, R, 0, st)) return r;
-    KL(1, launch_dyn_exp_step(D.s, l, p, W.qexp, W.bexp, c.num_exp_dec, row_len, xin, ldi, xout, ldc, d, rows_per_image, st));
-    KL(1, launch_layernorm<T>(xout, ldc, W.n2g, W.n2b, xn, d, R, d, st));
+    if (fuse_ln) {
+      KL(1, launch_dyn_exp_step<T>(D.s, l, p, W.qexp, W.bexp, c.num_exp_dec, row_len, xin, ldi, xout, ldc, d, W.n2g, W.n2b, xn, d, st));
+    } else {
+      KL(1, launch_dyn_exp_step<T>(D.s, l, p, W.qexp, W.bexp, c.num_exp_dec, row_len, xin, ldi, xout, ldc, d, nullptr, nullptr, (T*)nullptr, 0, st));
+      KL(1, launch_layernorm<T>(xout, ldc, W.n2g, W.n2b, xn, d, R, d, st));
+    }
     if (int r = dec_lin<T>(h, xn, d, W.wq, nullptr, 0, D.q, nullptr, d, R, 0, st)) return r;
     KL(1, (launch_cross_attn_step<T, T>(D.q, d, reinterpret_cast<const T*>(D.kv), ldkv, l * 2 * d, l * 2 * d + d, att, d, R,
                                         rows_per_image, c.enc_len, c.num_heads, d / c.num_heads, n_valid, row_len, p, st)));
@@ -664,6 +670,8 @@ int beam_plan(xn_handle* h, BeamPlan& P, int B, const int32_t* enc_pads_host, in
     P.bb.lps[s] = h->ws.get<float>((size_t)R * L);
     P.bb.len[s] = h->ws.get<int>(R);
     P.bb.anc[s] = h->ws.get<int>((size_t)R * L);
+    P.bb.cum[s] = h->ws.get<float>(R);
+    P.bb.eos[s] = h->ws.get<int>(R);
   }
   P.bb.all_done = h->ws.get<int>(1);
   // results land in arena buffers (stable addresses -> graph-capturable), then are copied to the caller
@@ -695,7 +703,7 @@ int beam_run(xn_handle* h, BeamPlan& P, const float* enc_out, int B, int beam, i
   D.s.anc = bb.anc[0];
   if (int r = dec_step(h, D, 0, nullptr, bb.tokens[0], L, beam, P.nv, nullptr, P.logits, c.vocab, st)) return r;
   KL(1, launch_logsoftmax_topk(P.logits, c.vocab, R, c.vocab, beam, P.topv, P.topi, nullptr, 0, 0, st));
-  KL(1, launch_beam_first(bb, P.topv, P.topi, B, beam, L, st));
+  KL(1, launch_beam_first(bb, P.topv, P.topi, B, beam, L, eos, st));
   int t_final = 2;
   for (int t = 2; t < L; ++t) {
     D.s.anc = bb.anc[src];
@@ -729,7 +737,7 @@ int beam_from_enc(xn_handle* h, const float* enc_out, int B, const int32_t* enc_
 
 size_t beam_ws_bytes(const xn_config& c, int B, int beam, int L) {
   const int R = B * beam;
-  return dec_ws_bytes(c, R, L, B, true) + (size_t)R * beam * 8 + (size_t)R * L * 24 + R * 8 + B * 4 + (size_t)R * L * 8 + R * 4 + 64 * 256;
+  return dec_ws_bytes(c, R, L, B, true) + (size_t)R * beam * 8 + (size_t)R * L * 24 + R * 8 + B * 4 + (size_t)R * L * 8 + R * 4 + R * 16 + 80 * 256;
 }
 
 const float* rawp(xn_handle* h, const std::string& k, std::vector<int64_t> shape, int* rc) {

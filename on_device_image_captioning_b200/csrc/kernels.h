@@ -79,7 +79,7 @@ cudaError_t launch_cast(const float* x, T* y, long n, cudaStream_t st);
 template <typename T>
 cudaError_t launch_window_attention(const T* qkv, const float* bias_table, T* out, int B, int H, int C,
                                     int heads, int shift, cudaStream_t st);
-// tensor-core (mma.sync) variant for the 16-bit modes; takes the derived bias table (heads, 532) x log2(e) built by launch_transpose_bias
+// tensor-core (mma.sync) variant for the 16-bit modes; takes the derived bias table (heads, 532) / scale built by launch_transpose_bias
 template <typename T>
 cudaError_t launch_window_attention_mma(const T* qkv, const float* bias_t, T* out, int B, int H, int C,
                                         int heads, int shift, cudaStream_t st);
@@ -110,9 +110,16 @@ struct DecState {
 };
 cudaError_t launch_embed(const int64_t* tokens64, const int* tokens32, long tok_stride, int p, const float* emb,
                          const float* pos, float* x, long ldx, int R, int d, cudaStream_t st);
+// embedding + LayerNorm (first decoder layer's norm_1) in one pass; d == 512
+template <typename T>
+cudaError_t launch_embed_ln(const int64_t* tokens64, const int* tokens32, long tok_stride, int p, const float* emb,
+                            const float* pos, float* x, long ldx, const float* gamma, const float* beta, T* xn, long ldn, int R,
+                            int d, cudaStream_t st);
+// ln_out != nullptr (d == 512): also writes LayerNorm(x_out) in the operand type (the layer's norm_2)
+template <typename T>
 cudaError_t launch_dyn_exp_step(const DecState& s, int layer, int p, const float* qexp, const float* bexp,
                                 int n_exp, const int* row_len, const float* x_in, long ldxi, float* x_out,
-                                long ldxo, int d, int beam, cudaStream_t st);
+                                long ldxo, int d, const float* ln_g, const float* ln_b, T* ln_out, long ldn, cudaStream_t st);
 // cross attention of one query position per row against per-image K/V (shared by the beams)
 template <typename KvT, typename OutT>
 cudaError_t launch_cross_attn_step(const float* q, long ldq, const KvT* kv, long ldkv, int k_off, int v_off,
@@ -127,11 +134,13 @@ struct BeamBufs {
   float* lps[2];      // (B, beam, L)
   int* len[2];        // (B, beam)
   int* anc[2];        // (B*beam, L)   slot is local (0..beam-1) + b*beam
+  float* cum[2];      // (B, beam)     running sum of the history log-probs
+  int* eos[2];        // (B, beam)     history contains EOS
   int* all_done;      // [1]
 };
 cudaError_t launch_beam_init(const BeamBufs& bb, int B, int beam, int L, int sos, cudaStream_t st);
 cudaError_t launch_beam_first(const BeamBufs& bb, const float* top_val, const int* top_idx, int B, int beam,
-                              int L, cudaStream_t st);
+                              int L, int eos, cudaStream_t st);
 cudaError_t launch_beam_step(const BeamBufs& bb, int src, const float* top_val, const int* top_idx, int B,
                              int beam, int L, int t, int eos, cudaStream_t st);
 cudaError_t launch_beam_finalize(const BeamBufs& bb, int src, int B, int beam, int L, int t_final, int how_many,

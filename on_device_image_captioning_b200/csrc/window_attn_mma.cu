@@ -15,6 +15,7 @@
 // bounded by its Q/K/V reads, not by the MMA rate.)
 #include <cuda_fp16.h>
 #include <algorithm>
+#include <type_traits>
 #include "kernels.h"
 #include "common.cuh"
 
@@ -56,6 +57,21 @@ __device__ __forceinline__ void ldsm_x4_trans(uint32_t (&r)[4], uint32_t addr) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
 }
+// base register + compile-time byte offset: keeps the per-tile address arithmetic out of the instruction stream
+template <int kOff> __device__ __forceinline__ void ldsm_x4_o(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4+%5];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr), "n"(kOff));
+}
+template <int kOff> __device__ __forceinline__ void ldsm_x4_trans_o(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4+%5];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr), "n"(kOff));
+}
+template <int kOff> __device__ __forceinline__ void ldsm_x2_o(uint32_t (&r)[2], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0,%1}, [%2+%3];" : "=r"(r[0]), "=r"(r[1]) : "r"(addr), "n"(kOff));
+}
+template <int N, typename F> __device__ __forceinline__ void static_for(F&& f) {
+  if constexpr (N > 0) { static_for<N - 1>(f); f(std::integral_constant<int, N - 1>{}); }
+}
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
 }
@@ -76,8 +92,9 @@ constexpr int kLPitch = 24;                      // 16-bit elements per row of t
 constexpr float kLabelVal = 24.0f;               // label one-hot magnitude: 24*24 = 576 -> mask = -576 * scale = -101.8 per mismatching axis
 constexpr float kLog2e = 1.4426950408889634f;
 
-// bias_l2 is the relative-position table transposed to (heads, 532) and multiplied by log2(e) (derived once per
-// weight load), so the softmax runs in the exp2 domain.
+// bias_l2 is the relative-position table transposed to (heads, 532) and divided by the score scale (derived once per
+// weight load): the score accumulators are initialised with it, so s = q.k + bias/scale comes straight out of the MMAs
+// and the softmax is p = 2^((s - max) * scale * log2 e)  (ex2.f16x2 was tried: it issues two MUFU ops plus a PRMT, no gain).
 //
 // Persistent CTAs loop over items = (window, group of kHeadsPerCta heads), head group fastest so that CTAs running
 // side by side share the 128-byte lines of a token's QKV row.  Q/K/V of the next head -- or of the next item's first
@@ -110,21 +127,27 @@ __global__ void __launch_bounds__(kMmaThreads, 2) window_attention_mma_kernel(co
   const uint32_t lab_u32 = (uint32_t)__cvta_generic_to_shared(lab_all);
   const uint32_t bt_u32 = (uint32_t)__cvta_generic_to_shared(bt_all);
 
-  // per-item metadata into buffer mb; returns nothing (the mask flag is recomputed from the item where needed)
-  auto item_masked = [&](int item) {
-    const int wid = item / ngroups, wrem = wid % nW;
-    return shift > 0 && (wrem / nWs == nWs - 1 || wrem % nWs == nWs - 1);
+  // item -> (head group g, batch b, window wy/wx): decoded once per item (runtime divisions)
+  struct ItemPos { int g, b, wy, wx; bool masked; };
+  auto decode_item = [&](int item) {
+    ItemPos p;
+    p.g = item % ngroups;
+    const int wid = item / ngroups;
+    p.b = wid / nW;
+    const int wrem = wid - p.b * nW;
+    p.wy = wrem / nWs;
+    p.wx = wrem - p.wy * nWs;
+    p.masked = shift > 0 && (p.wy == nWs - 1 || p.wx == nWs - 1);
+    return p;
   };
-  auto compute_meta = [&](int item, int mb) {
-    const int g = item % ngroups, wid = item / ngroups;
-    const int b = wid / nW, wrem = wid - b * nW;
-    const int wy = wrem / nWs, wx = wrem - wy * nWs;
+  // per-item metadata (token rows, label rows, bias tables) into buffer mb
+  auto compute_meta = [&](const ItemPos& ip, int mb) {
     if (tid < kWinTok) {
-      int h = wy * kWin + my_ty + shift, w = wx * kWin + my_tx + shift;   // roll(-shift): shifted[h] = x[h + shift]
+      int h = ip.wy * kWin + my_ty + shift, w = ip.wx * kWin + my_tx + shift;   // roll(-shift): shifted[h] = x[h + shift]
       if (h >= H) h -= H;
       if (w >= H) w -= H;
-      tok_all[mb * kWinTok + tid] = (b * H + h) * H + w;
-      const bool ey = shift > 0 && wy == nWs - 1, ex = shift > 0 && wx == nWs - 1;
+      tok_all[mb * kWinTok + tid] = (ip.b * H + h) * H + w;
+      const bool ey = shift > 0 && ip.wy == nWs - 1, ex = shift > 0 && ip.wx == nWs - 1;
       const float ya = ey ? (my_ty < kWin - shift ? kLabelVal : 0.f) : kLabelVal, yb = ey ? (my_ty < kWin - shift ? 0.f : kLabelVal) : 0.f;
       const float xa = ex ? (my_tx < kWin - shift ? kLabelVal : 0.f) : kLabelVal, xb = ex ? (my_tx < kWin - shift ? 0.f : kLabelVal) : 0.f;
       uint2 v;
@@ -132,21 +155,27 @@ __global__ void __launch_bounds__(kMmaThreads, 2) window_attention_mma_kernel(co
       v.y = Mma16<T>::pack(xa, xb);
       *reinterpret_cast<uint2*>(lab_all + (mb * kWinTok + tid) * kLPitch) = v;
     }
-    const float* src = bias_l2 + (long)g * kHeadsPerCta * kBiasPitch;
+    const float* src = bias_l2 + (long)ip.g * kHeadsPerCta * kBiasPitch;
     for (int i = tid; i < kHeadsPerCta * (kBiasPitch / 4); i += kMmaThreads)
       cp_async16(bt_u32 + (uint32_t)((mb * kHeadsPerCta * kBiasPitch + i * 4) * sizeof(float)), src + i * 4);
   };
-  auto issue_loads = [&](int item, int hh, int mb, int bufi) {
+  // this thread's six (token, q/k/v, 16-byte chunk) slots of a head: smem byte offset and source column, fixed for the kernel
+  uint32_t ld_dst[6];
+  int ld_tok[6], ld_col[6];
+#pragma unroll
+  for (int k = 0; k < 6; ++k) {
+    const int i = tid + k * kMmaThreads;
+    const int t = i / 12, r = i % 12, which = r >> 2, ch = r & 3;
+    ld_dst[k] = (uint32_t)((which * kMatElems + t * kRowPad + ch * 8) * sizeof(T));
+    ld_tok[k] = t;
+    ld_col[k] = which * C + ch * 8;
+  }
+  auto issue_loads = [&](int head, int mb, int bufi) {
     const uint32_t base = stage_u32 + (uint32_t)(bufi * 3 * kMatElems * sizeof(T));
-    const T* src = qkv + ((item % ngroups) * kHeadsPerCta + hh) * kHeadDim;
+    const T* src = qkv + head * kHeadDim;
     const int* tk = tok_all + mb * kWinTok;
 #pragma unroll
-    for (int k = 0; k < 6; ++k) {
-      const int i = tid + k * kMmaThreads;
-      const int t = i / 12, r = i % 12, which = r >> 2, ch = r & 3;
-      cp_async16(base + (uint32_t)((which * kMatElems + t * kRowPad + ch * 8) * sizeof(T)),
-                 src + (long)tk[t] * 3 * C + which * C + ch * 8);
-    }
+    for (int k = 0; k < 6; ++k) cp_async16(base + ld_dst[k], src + (long)tk[ld_tok[k]] * 3 * C + ld_col[k]);
     cp_async_commit();
   };
 
@@ -156,9 +185,10 @@ __global__ void __launch_bounds__(kMmaThreads, 2) window_attention_mma_kernel(co
   __syncthreads();
   int item = blockIdx.x;
   if (item >= n_items) return;
-  compute_meta(item, 0);
+  ItemPos cur = decode_item(item);
+  compute_meta(cur, 0);
   __syncthreads();
-  issue_loads(item, 0, 0, 0);
+  issue_loads(cur.g * kHeadsPerCta, 0, 0);
 
   const int m0 = warp * 16;
   const int r0 = m0 + (lane >> 2), r1 = r0 + 8;
@@ -173,27 +203,44 @@ __global__ void __launch_bounds__(kMmaThreads, 2) window_attention_mma_kernel(co
     const int mb = k & 1;
     const int next_item = item + gridDim.x;
     const bool has_next = next_item < n_items;
-    const bool masked = item_masked(item);
+    ItemPos nxt = cur;
+    if (has_next) nxt = decode_item(next_item);
+    const bool masked = cur.masked;
     const int* tok = tok_all + mb * kWinTok;
-    const int head0 = (item % ngroups) * kHeadsPerCta;
+    const int head0 = cur.g * kHeadsPerCta;
 #pragma unroll 1
     for (int hh = 0; hh < kHeadsPerCta; ++hh, ++unit) {
       const int bufi = unit & 1;
       cp_async_wait<0>();
       __syncthreads();                              // this unit landed; everyone is done with the other buffer
       if (hh == 0 && has_next) {
-        compute_meta(next_item, mb ^ 1);            // its cp.async traffic joins the next commit group
+        compute_meta(nxt, mb ^ 1);                  // its cp.async traffic joins the next commit group
         if (kHeadsPerCta == 1) __syncthreads();
       }
-      if (hh + 1 < kHeadsPerCta) issue_loads(item, hh + 1, mb, bufi ^ 1);
-      else if (has_next) issue_loads(next_item, 0, mb ^ 1, bufi ^ 1);
+      if (hh + 1 < kHeadsPerCta) issue_loads(head0 + hh + 1, mb, bufi ^ 1);
+      else if (has_next) issue_loads(nxt.g * kHeadsPerCta, mb ^ 1, bufi ^ 1);
 
       const uint32_t q_base = stage_u32 + (uint32_t)(bufi * 3 * kMatElems * sizeof(T));
       const uint32_t k_base = q_base + (uint32_t)(kMatElems * sizeof(T));
       const uint32_t v_base = k_base + (uint32_t)(kMatElems * sizeof(T));
       T* Qs = stage + bufi * 3 * kMatElems;
 
+      // The accumulators start at bias / scale (the derived table), so after the MMAs s = q.k + bias/scale and
+      // p = 2^((s - max s) * scale * log2 e): no separate bias pass, no zero fill.
+      // bias index = (yi - yj + 11)*23 + (xi - xj + 11) = rowoff_i + jneg_j
+      const unsigned char* bt = reinterpret_cast<const unsigned char*>(bt_all + (mb * kHeadsPerCta + hh) * kBiasPitch);
+      const unsigned char* bt0 = bt + rowoff0;
+      const unsigned char* bt1 = bt + rowoff1;
+      const int* jq = jneg + (lane & 3) * 2;
       float s[18][4];
+#pragma unroll
+      for (int nt = 0; nt < 18; ++nt) {
+        const int jo = jq[nt * 8];                             // key 2q; key 2q+1 sits 4 bytes lower (same window row)
+        s[nt][0] = *reinterpret_cast<const float*>(bt0 + jo);
+        s[nt][1] = *reinterpret_cast<const float*>(bt0 + jo - 4);
+        s[nt][2] = *reinterpret_cast<const float*>(bt1 + jo);
+        s[nt][3] = *reinterpret_cast<const float*>(bt1 + jo - 4);
+      }
       {
         const int row = m0 + (lane & 7) + ((lane >> 3) & 1) * 8;
         const int col = (lane >> 4) * 8;
@@ -201,74 +248,66 @@ __global__ void __launch_bounds__(kMmaThreads, 2) window_attention_mma_kernel(co
           const uint32_t l_base = lab_u32 + (uint32_t)(mb * kWinTok * kLPitch * sizeof(T));
           uint32_t la[4];
           ldsm_x4(la, l_base + (row * kLPitch + col) * 2);
-#pragma unroll
-          for (int nt = 0; nt < 18; ++nt) {
-            s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = -2.0f * kLabelVal * kLabelVal;
+          const uint32_t lb_base = l_base + (uint32_t)(((lane & 7) * kLPitch + ((lane >> 3) & 1) * 8) * 2);
+          static_for<18>([&](auto nt_c) {
+            constexpr int nt = decltype(nt_c)::value;
+            s[nt][0] -= 2.0f * kLabelVal * kLabelVal; s[nt][1] -= 2.0f * kLabelVal * kLabelVal;
+            s[nt][2] -= 2.0f * kLabelVal * kLabelVal; s[nt][3] -= 2.0f * kLabelVal * kLabelVal;
             uint32_t lb[2];
-            ldsm_x2(lb, l_base + ((nt * 8 + (lane & 7)) * kLPitch + ((lane >> 3) & 1) * 8) * 2);
+            ldsm_x2_o<nt * 8 * kLPitch * 2>(lb, lb_base);
             Mma16<T>::mma(s[nt], la, lb[0], lb[1]);
-          }
-        } else {
-#pragma unroll
-          for (int nt = 0; nt < 18; ++nt) s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+          });
         }
         // A fragments of Q for the two k16 steps (d 0-15, 16-31)
         uint32_t qa[2][4];
-        ldsm_x4(qa[0], q_base + (row * kRowPad + col) * 2);
-        ldsm_x4(qa[1], q_base + (row * kRowPad + col + 16) * 2);
-#pragma unroll
-        for (int nt = 0; nt < 18; ++nt) {
+        const uint32_t qaddr = q_base + (uint32_t)((row * kRowPad + col) * 2);
+        ldsm_x4_o<0>(qa[0], qaddr);
+        ldsm_x4_o<32>(qa[1], qaddr);
+        const uint32_t kaddr = k_base + (uint32_t)(((lane & 7) * kRowPad + (lane >> 3) * 8) * 2);
+        static_for<18>([&](auto nt_c) {
+          constexpr int nt = decltype(nt_c)::value;
           uint32_t kb[4];     // {b0,b1} for d 0-15 and {b0,b1} for d 16-31 of keys nt*8 .. nt*8+7
-          const int krow = nt * 8 + (lane & 7), kcol = (lane >> 3) * 8;
-          ldsm_x4(kb, k_base + (krow * kRowPad + kcol) * 2);
+          ldsm_x4_o<nt * 8 * kRowPad * 2>(kb, kaddr);
           Mma16<T>::mma(s[nt], qa[0], kb[0], kb[1]);
           Mma16<T>::mma(s[nt], qa[1], kb[2], kb[3]);
-        }
+        });
       }
 
-      // scale + relative-position bias (exp2 domain), then the row softmax (rows r0, r1 = r0 + 8)
-      // bias index = (yi - yj + 11)*23 + (xi - xj + 11) = rowoff_i + jneg_j
-      const unsigned char* bt = reinterpret_cast<const unsigned char*>(bt_all + (mb * kHeadsPerCta + hh) * kBiasPitch);
-      const unsigned char* bt0 = bt + rowoff0;
-      const unsigned char* bt1 = bt + rowoff1;
+      // row softmax (rows r0, r1 = r0 + 8) straight into packed 16-bit probabilities
       float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
       for (int nt = 0; nt < 18; ++nt) {
-        const int jo = jneg[nt * 8 + (lane & 3) * 2];          // key 2q; key 2q+1 sits 4 bytes lower (same window row)
-        const float a0 = fmaf(s[nt][0], sl, *reinterpret_cast<const float*>(bt0 + jo));
-        const float a1 = fmaf(s[nt][1], sl, *reinterpret_cast<const float*>(bt0 + jo - 4));
-        const float c0 = fmaf(s[nt][2], sl, *reinterpret_cast<const float*>(bt1 + jo));
-        const float c1 = fmaf(s[nt][3], sl, *reinterpret_cast<const float*>(bt1 + jo - 4));
-        s[nt][0] = a0; s[nt][1] = a1; s[nt][2] = c0; s[nt][3] = c1;
-        mx0 = fmaxf(mx0, fmaxf(a0, a1));
-        mx1 = fmaxf(mx1, fmaxf(c0, c1));
+        mx0 = fmaxf(mx0, fmaxf(s[nt][0], s[nt][1]));
+        mx1 = fmaxf(mx1, fmaxf(s[nt][2], s[nt][3]));
       }
       mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
       mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+      const float nm0 = -mx0 * sl, nm1 = -mx1 * sl;
       uint32_t pa[18][2];   // packed probabilities: [nt][0] = row r0 (cols 2q,2q+1), [nt][1] = row r1
 #pragma unroll
       for (int nt = 0; nt < 18; ++nt) {
-        pa[nt][0] = Mma16<T>::pack(ex2_ftz(s[nt][0] - mx0), ex2_ftz(s[nt][1] - mx0));
-        pa[nt][1] = Mma16<T>::pack(ex2_ftz(s[nt][2] - mx1), ex2_ftz(s[nt][3] - mx1));
+        pa[nt][0] = Mma16<T>::pack(ex2_ftz(fmaf(s[nt][0], sl, nm0)), ex2_ftz(fmaf(s[nt][1], sl, nm0)));
+        pa[nt][1] = Mma16<T>::pack(ex2_ftz(fmaf(s[nt][2], sl, nm1)), ex2_ftz(fmaf(s[nt][3], sl, nm1)));
       }
 
       // O = P V : 9 k16 steps over the keys, 4 n8 tiles over head_dim + one all-ones tile for the row sums
       float o[5][4];
 #pragma unroll
       for (int n = 0; n < 5; ++n) o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.f;
-#pragma unroll
-      for (int ks = 0; ks < 9; ++ks) {
-        uint32_t a[4] = {pa[2 * ks][0], pa[2 * ks][1], pa[2 * ks + 1][0], pa[2 * ks + 1][1]};
-        const int vrow = ks * 16 + ((lane >> 3) & 1) * 8 + (lane & 7);
-        const int vcol = (lane >> 4) * 8;
-        uint32_t vb0[4], vb1[4];                     // d 0-15 and d 16-31
-        ldsm_x4_trans(vb0, v_base + (vrow * kRowPad + vcol) * 2);
-        ldsm_x4_trans(vb1, v_base + (vrow * kRowPad + vcol + 16) * 2);
-        Mma16<T>::mma(o[0], a, vb0[0], vb0[1]);
-        Mma16<T>::mma(o[1], a, vb0[2], vb0[3]);
-        Mma16<T>::mma(o[2], a, vb1[0], vb1[1]);
-        Mma16<T>::mma(o[3], a, vb1[2], vb1[3]);
-        Mma16<T>::mma(o[4], a, ones, ones);
+      {
+        const uint32_t vaddr = v_base + (uint32_t)(((((lane >> 3) & 1) * 8 + (lane & 7)) * kRowPad + (lane >> 4) * 8) * 2);
+        static_for<9>([&](auto ks_c) {
+          constexpr int ks = decltype(ks_c)::value;
+          uint32_t a[4] = {pa[2 * ks][0], pa[2 * ks][1], pa[2 * ks + 1][0], pa[2 * ks + 1][1]};
+          uint32_t vb0[4], vb1[4];                     // d 0-15 and d 16-31
+          ldsm_x4_trans_o<ks * 16 * kRowPad * 2>(vb0, vaddr);
+          ldsm_x4_trans_o<ks * 16 * kRowPad * 2 + 32>(vb1, vaddr);
+          Mma16<T>::mma(o[0], a, vb0[0], vb0[1]);
+          Mma16<T>::mma(o[1], a, vb0[2], vb0[3]);
+          Mma16<T>::mma(o[2], a, vb1[0], vb1[1]);
+          Mma16<T>::mma(o[3], a, vb1[2], vb1[3]);
+          Mma16<T>::mma(o[4], a, ones, ones);
+        });
       }
       const float inv0 = 1.0f / o[4][0], inv1 = 1.0f / o[4][2];
 
@@ -289,6 +328,7 @@ __global__ void __launch_bounds__(kMmaThreads, 2) window_attention_mma_kernel(co
         *reinterpret_cast<uint4*>(out + (long)tok[row] * C + (head0 + hh) * kHeadDim + ch * 8) = v;
       }
     }
+    cur = nxt;
   }
 }
 
@@ -339,12 +379,12 @@ template cudaError_t launch_window_attention_mma<__half>(const __half*, const fl
 }  // namespace xn
 
 namespace xn {
-// (529, heads) relative-position table -> (heads, 532) * log2(e), once per weight load
+// (529, heads) relative-position table -> (heads, 532) / scale (scale = 32^-0.5), once per weight load
 __global__ void transpose_bias_kernel(const float* __restrict__ t, float* __restrict__ o, int heads) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < kBiasPitch * heads) {
     const int h = i / kBiasPitch, e = i % kBiasPitch;
-    o[i] = e < kBiasN ? t[e * heads + h] * kLog2e : 0.f;
+    o[i] = e < kBiasN ? t[e * heads + h] * 5.656854249492380f : 0.f;     // / 32^-0.5
   }
 }
 cudaError_t launch_transpose_bias(const float* table, float* out, int heads, cudaStream_t st) {
