@@ -120,6 +120,17 @@ int xn_op_layernorm(xn_handle* h, const float* x, const float* gamma, const floa
                     int rows, int C, void* stream);
 int xn_op_linear(xn_handle* h, const float* x, const float* w, const float* bias, const float* residual,
                  float* y, int M, int N, int K, int act /*0 none,1 gelu,2 relu*/, int precision, void* stream);
+/* Decoder-step linear on the latency-oriented kernel (gemm_skinny.cu; 16-bit precisions, M <= 512):
+ * y = act(LN(x; gamma, beta) . w^T + bias) + residual, LayerNorm optional (gamma == NULL: plain conversion of the fp32
+ * rows; the fp32 path takes K slices <= 512).  x_is_16bit != 0 rounds x to the operand type first (the cp.async A path); 0 feeds the fp32 rows to the kernel.
+ * Replaces nn.LayerNorm + nn.Linear pairs of reference models/layers.py:222-248 at one new position per row. */
+int xn_op_linear_skinny(xn_handle* h, const float* x, const float* gamma, const float* beta, const float* w,
+                        const float* bias, const float* residual, float* y, int M, int N, int K, int act,
+                        int x_is_16bit, int precision, void* stream);
+/* Measurement hook: one GEMM launch on operands that are already 16-bit on the device (no conversions), y fp32.
+ * which = 0: tcgen05 kernel, 1: skinny kernel with a 16-bit A, 2: skinny kernel with fp32 A (+ LayerNorm if gamma). */
+int xn_op_gemm_raw(xn_handle* h, int which, const void* a, const float* gamma, const float* beta, const void* w16,
+                   const float* bias, const float* residual, float* y, int M, int N, int K, int act, int precision, void* stream);
 int xn_op_window_attention(xn_handle* h, const float* qkv, const float* bias_table, float* out,
                            int B, int H, int C, int heads, int shift, int precision, void* stream);
 int xn_op_logsoftmax_topk(xn_handle* h, const float* logits, int rows, int V, int k,

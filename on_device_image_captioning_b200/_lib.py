@@ -47,6 +47,8 @@ _SIGNATURES = {
     "xn_profile_read": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "xn_op_layernorm": (C.c_int, [_P, _P, _P, _P, _P, _I, _I, _P]),
     "xn_op_linear": (C.c_int, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
+    "xn_op_linear_skinny": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
+    "xn_op_gemm_raw": (C.c_int, [_P, _I, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "xn_op_window_attention": (C.c_int, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
     "xn_op_logsoftmax_topk": (C.c_int, [_P, _P, _I, _I, _I, _P, _P, _P, _P]),
 }

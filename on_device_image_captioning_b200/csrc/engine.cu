@@ -95,6 +95,7 @@ struct xn_handle {
   std::vector<CachedGraph> graphs;
   int64_t use_graph = 1;
   int64_t op_out16 = 0;
+  int64_t use_skinny = 1;            // decoder-step linears on gemm_skinny.cu when rows <= 512 (16-bit modes)
   cudaStream_t gstream = nullptr;      // graphs are captured/replayed here (the caller's stream may be the legacy
   cudaEvent_t g_in = nullptr, g_out = nullptr;   // default stream, which cannot be captured); ordered with events
   void drop_graphs() {
@@ -522,6 +523,33 @@ int dec_lin(xn_handle* h, const T* x, long ldx, const LinW& w, const float* res,
   return lin_tc(h, x, ldx, w, res, ldr, yf, yf ? nullptr : y16, ldy, M, act, std::is_same<T, f16>::value, st);
 }
 
+// decoder-step linear on the latency-oriented kernel (16-bit modes, M <= 512): optional LayerNorm / conversion of an
+// fp32 A on load.  Returns 1 when the shape is not covered (the caller falls back to the tcgen05 path).
+template <typename T>
+int dec_lin_skinny(xn_handle* h, const T* a16, const float* a32, long lda, const float* ln_g, const float* ln_b, const LinW& w,
+                   const float* res, long ldr, float* yf, T* y16, long ldy, int M, int act, cudaStream_t st) {
+  SkinnyArgs g{};
+  g.A16 = a16; g.A32 = a32; g.lda = lda; g.ln_g = ln_g; g.ln_b = ln_b;
+  g.W = w.wb; g.ldw = w.K; g.bias = w.b; g.res = res; g.ldr = ldr; g.Cf = yf; g.Cb = yf ? nullptr : y16; g.ldc = ldy;
+  g.M = M; g.N = w.N; g.K = w.K; g.act = act;
+  // selected where it measured faster in-graph than the 128-row tcgen05 tiles: few rows, narrow outputs, no LayerNorm on load
+  if (!h->use_skinny || M > 64 || w.N > 2048 || ln_g || !skinny_gemm_supported(g)) return 1;
+  if (a32 && (w.K % 512)) return 1;
+  if (h->profile) {
+    if (h->prof_used + 2 > h->prof_ev.size()) {
+      for (int i = 0; i < 2; ++i) { cudaEvent_t e; CU(cudaEventCreate(&e)); h->prof_ev.push_back(e); }
+    }
+    CU(cudaEventRecord(h->prof_ev[h->prof_used], st));
+    KL(1, launch_gemm_skinny<T>(g, st));
+    CU(cudaEventRecord(h->prof_ev[h->prof_used + 1], st));
+    h->prof_used += 2;
+    h->prof_flops.push_back(-2.0 * M * (double)w.N * w.K);      // negative: counted separately from the tcgen05 launches
+    return 0;
+  }
+  KL(1, launch_gemm_skinny<T>(g, st));
+  return 0;
+}
+
 // cross K/V of all decoder layers, once per image (shared by the beams)
 template <typename T>
 int dec_project_kv(xn_handle* h, DecBufs& D, const float* enc_out, int n_images, cudaStream_t st) {
@@ -546,6 +574,13 @@ int dec_step_t(xn_handle* h, DecBufs& D, int p, const int64_t* tok64, const int*
   T* att = reinterpret_cast<T*>(D.att);
   T* hid = reinterpret_cast<T*>(D.hid);
   T* yn = reinterpret_cast<T*>(D.yn);
+  constexpr bool k16 = !std::is_same<T, float>::value;
+  // 16-bit modes with a few hundred rows: the latency-oriented kernel (LayerNorm / conversion of A fused into its load)
+  auto skinny = [&](const T* a16, const float* a32, long lda, const float* g, const float* b, const LinW& w, const float* res,
+                    long ldr, float* yf, T* y16, long ldy, int act) -> int {
+    if constexpr (k16) return dec_lin_skinny<T>(h, a16, a32, lda, g, b, w, res, ldr, yf, y16, ldy, R, act, st);
+    else return 1;
+  };
   const bool fuse_ln = d == 512;            // embedding + norm_1 of layer 0, dynamic expansion + norm_2: one kernel each
   if (fuse_ln) KL(1, launch_embed_ln<T>(tok64, tok32, tok_stride, p, h->emb, h->pos, D.x0, d, h->dec[0].n1g, h->dec[0].n1b, xn, d, R, d, st));
   else KL(1, launch_embed(tok64, tok32, tok_stride, p, h->emb, h->pos, D.x0, d, R, d, st));
@@ -554,29 +589,40 @@ int dec_step_t(xn_handle* h, DecBufs& D, int p, const int64_t* tok64, const int*
     const float* xin = l == 0 ? D.x0 : D.ycat + (size_t)(l - 1) * d;
     const long ldi = l == 0 ? d : ldc;
     float* xout = D.ycat + (size_t)l * d;
-    if (!(fuse_ln && l == 0)) KL(1, launch_layernorm<T>(xin, ldi, W.n1g, W.n1b, xn, d, R, d, st));
     float* crow = D.s.cache + (((size_t)l * D.P + p) * R) * D.s.cw;
-    if (int r = dec_lin<T>(h, xn, d, W.dyn5, nullptr, 0, crow, nullptr, D.s.cw, R, 0, st)) return r;
+    // 16-bit A: the skinny kernel where selected (few rows), else the tcgen05 kernel
+    auto lin16 = [&](const T* a, long lda, const LinW& w, const float* res, long ldr, float* yf, T* y16, long ldy, int act) -> int {
+      const int rs = skinny(a, nullptr, lda, nullptr, nullptr, w, res, ldr, yf, y16, ldy, act);
+      if (rs <= 0) return rs;
+      return dec_lin<T>(h, a, lda, w, res, ldr, yf, y16, ldy, R, act, st);
+    };
+    if (!(fuse_ln && l == 0)) KL(1, launch_layernorm<T>(xin, ldi, W.n1g, W.n1b, xn, d, R, d, st));
+    if (int r = lin16(xn, d, W.dyn5, nullptr, 0, crow, nullptr, D.s.cw, 0)) return r;
     if (fuse_ln) {
       KL(1, launch_dyn_exp_step<T>(D.s, l, p, W.qexp, W.bexp, c.num_exp_dec, row_len, xin, ldi, xout, ldc, d, W.n2g, W.n2b, xn, d, st));
     } else {
       KL(1, launch_dyn_exp_step<T>(D.s, l, p, W.qexp, W.bexp, c.num_exp_dec, row_len, xin, ldi, xout, ldc, d, nullptr, nullptr, (T*)nullptr, 0, st));
       KL(1, launch_layernorm<T>(xout, ldc, W.n2g, W.n2b, xn, d, R, d, st));
     }
-    if (int r = dec_lin<T>(h, xn, d, W.wq, nullptr, 0, D.q, nullptr, d, R, 0, st)) return r;
+    if (int r = lin16(xn, d, W.wq, nullptr, 0, D.q, nullptr, d, 0)) return r;
     KL(1, (launch_cross_attn_step<T, T>(D.q, d, reinterpret_cast<const T*>(D.kv), ldkv, l * 2 * d, l * 2 * d + d, att, d, R,
                                         rows_per_image, c.enc_len, c.num_heads, d / c.num_heads, n_valid, row_len, p, st)));
-    if (int r = dec_lin<T>(h, att, d, W.wo, xout, ldc, xout, nullptr, ldc, R, 0, st)) return r;
+    if (int r = lin16(att, d, W.wo, xout, ldc, xout, nullptr, ldc, 0)) return r;
     KL(1, launch_layernorm<T>(xout, ldc, W.n3g, W.n3b, xn, d, R, d, st));
-    if (int r = dec_lin<T>(h, xn, d, W.ff1, nullptr, 0, nullptr, hid, c.ff, R, 2, st)) return r;
-    if (int r = dec_lin<T>(h, hid, c.ff, W.ff2, xout, ldc, xout, nullptr, ldc, R, 0, st)) return r;
+    if (int r = lin16(xn, d, W.ff1, nullptr, 0, nullptr, hid, c.ff, 2)) return r;
+    if (int r = lin16(hid, c.ff, W.ff2, xout, ldc, xout, nullptr, ldc, 0)) return r;
   }
-  const T* ycat_in = reinterpret_cast<const T*>(D.ycat);
-  if (!std::is_same<T, float>::value) {
-    KL(1, launch_cast<T>(D.ycat, reinterpret_cast<T*>(D.ycat16), (long)R * ldc, st));
-    ycat_in = reinterpret_cast<const T*>(D.ycat16);
+  // reduce group: fp32 concatenation, converted on load by the skinny kernel where selected
+  int rs = skinny(nullptr, D.ycat, ldc, nullptr, nullptr, h->dec_reduce, D.ycat + (size_t)(nd - 1) * d, ldc, D.pre, nullptr, d, 0);
+  if (rs < 0) return rs;
+  if (rs > 0) {
+    const T* ycat_in = reinterpret_cast<const T*>(D.ycat);
+    if (k16) {
+      KL(1, launch_cast<T>(D.ycat, reinterpret_cast<T*>(D.ycat16), (long)R * ldc, st));
+      ycat_in = reinterpret_cast<const T*>(D.ycat16);
+    }
+    if (int r = dec_lin<T>(h, ycat_in, ldc, h->dec_reduce, D.ycat + (size_t)(nd - 1) * d, ldc, D.pre, nullptr, d, R, 0, st)) return r;
   }
-  if (int r = dec_lin<T>(h, ycat_in, ldc, h->dec_reduce, D.ycat + (size_t)(nd - 1) * d, ldc, D.pre, nullptr, d, R, 0, st)) return r;
   KL(1, launch_layernorm<T>(D.pre, d, h->dec_ng, h->dec_nb, yn, d, R, d, st));
   if (int r = dec_lin<T>(h, yn, d, h->vocab, nullptr, 0, logits, nullptr, ldl, R, 0, st)) return r;
   return 0;
@@ -1169,6 +1215,7 @@ int xn_set_option(xn_handle* h, const char* name, int64_t value) {
   std::string n(name);
   if (n == "use_graph") { h->use_graph = value; h->drop_graphs(); return XN_OK; }
   if (n == "op_out16") { h->op_out16 = value; return XN_OK; }
+  if (n == "use_skinny") { h->use_skinny = value; h->drop_graphs(); return XN_OK; }
   if (n == "tc_debug") { set_tc_debug((int)value); return XN_OK; }
   if (n == "profile") { h->profile = value; h->prof_used = 0; h->prof_flops.clear(); }
   else if (n == "swin_chunk") h->swin_chunk = std::max<int64_t>(1, value);
@@ -1182,15 +1229,18 @@ int xn_profile_read(xn_handle* h, double* ms_total, double* flops_total, int64_t
   cudaSetDevice(h->device);
   CU(cudaDeviceSynchronize());
   double ms = 0, fl = 0;
+  int64_t n_tc = 0;
   for (size_t i = 0; i + 1 < h->prof_used; i += 2) {
+    if (h->prof_flops[i / 2] < 0) continue;          // skinny mma.sync launches are not part of the tcgen05 roofline
     float t = 0.f;
     CU(cudaEventElapsedTime(&t, h->prof_ev[i], h->prof_ev[i + 1]));
     ms += t;
+    fl += h->prof_flops[i / 2];
+    ++n_tc;
   }
-  for (double f : h->prof_flops) fl += f;
   if (ms_total) *ms_total = ms;
   if (flops_total) *flops_total = fl;
-  if (count) *count = (int64_t)h->prof_flops.size();
+  if (count) *count = n_tc;
   return XN_OK;
 }
 
@@ -1234,6 +1284,50 @@ int xn_op_linear(xn_handle* h, const float* x, const float* w, const float* bias
     return XN_OK;
   }
   return lin_tc(h, xb, K, l, residual, N, y, nullptr, N, M, act, fp16, st);
+}
+
+int xn_op_linear_skinny(xn_handle* h, const float* x, const float* gamma, const float* beta, const float* w, const float* bias,
+                        const float* residual, float* y, int M, int N, int K, int act, int x_is_16bit, int precision, void* stream) {
+  OP_READY();
+  if (precision != XN_PREC_FP16 && precision != XN_PREC_BF16) return h->fail(XN_ERR_ARG, "skinny GEMM is a 16-bit-operand kernel");
+  if (x_is_16bit && gamma) return h->fail(XN_ERR_ARG, "LayerNorm fusion takes the fp32 rows");
+  if (int r = ensure_ws(h, ((size_t)M * K + (size_t)N * K) * 2 + 8192, st)) return r;
+  bf16* xb = h->ws.get<bf16>((size_t)M * K);
+  bf16* wb = h->ws.get<bf16>((size_t)N * K);
+  const bool fp16 = precision == XN_PREC_FP16;
+  if (fp16) KL(1, launch_cast<f16>(w, reinterpret_cast<f16*>(wb), (long)N * K, st));
+  else KL(1, launch_cast<bf16>(w, wb, (long)N * K, st));
+  if (x_is_16bit) {
+    if (fp16) KL(1, launch_cast<f16>(x, reinterpret_cast<f16*>(xb), (long)M * K, st));
+    else KL(1, launch_cast<bf16>(x, xb, (long)M * K, st));
+  }
+  SkinnyArgs g{};
+  g.A16 = x_is_16bit ? xb : nullptr; g.A32 = x_is_16bit ? nullptr : x; g.lda = K; g.ln_g = gamma; g.ln_b = beta;
+  g.W = wb; g.ldw = K; g.bias = bias; g.res = residual; g.ldr = N; g.Cf = y; g.Cb = nullptr; g.ldc = N;
+  g.M = M; g.N = N; g.K = K; g.act = act;
+  if (!skinny_gemm_supported(g)) return h->fail(XN_ERR_UNSUPPORTED, "skinny GEMM does not cover M=%d N=%d K=%d", M, N, K);
+  if (fp16) KL(1, launch_gemm_skinny<f16>(g, st));
+  else KL(1, launch_gemm_skinny<bf16>(g, st));
+  return XN_OK;
+}
+
+int xn_op_gemm_raw(xn_handle* h, int which, const void* a, const float* gamma, const float* beta, const void* w16, const float* bias,
+                   const float* residual, float* y, int M, int N, int K, int act, int precision, void* stream) {
+  OP_READY();
+  const bool fp16 = precision == XN_PREC_FP16;
+  if (which == 0) {
+    LinW l; l.wb = w16; l.b = bias; l.N = N; l.K = K;
+    return lin_tc(h, a, K, l, residual, N, y, nullptr, N, M, act, fp16, st);
+  }
+  SkinnyArgs g{};
+  g.A16 = which == 1 ? a : nullptr; g.A32 = which == 2 ? reinterpret_cast<const float*>(a) : nullptr; g.lda = K;
+  g.ln_g = which == 2 ? gamma : nullptr; g.ln_b = which == 2 ? beta : nullptr;
+  g.W = w16; g.ldw = K; g.bias = bias; g.res = residual; g.ldr = N; g.Cf = y; g.Cb = nullptr; g.ldc = N;
+  g.M = M; g.N = N; g.K = K; g.act = act;
+  if (!skinny_gemm_supported(g)) return h->fail(XN_ERR_UNSUPPORTED, "skinny GEMM does not cover M=%d N=%d K=%d", M, N, K);
+  if (fp16) KL(1, launch_gemm_skinny<f16>(g, st));
+  else KL(1, launch_gemm_skinny<bf16>(g, st));
+  return XN_OK;
 }
 
 int xn_op_window_attention(xn_handle* h, const float* qkv, const float* bias_table, float* out, int B, int H, int C, int heads,

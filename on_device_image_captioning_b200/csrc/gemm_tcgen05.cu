@@ -669,13 +669,17 @@ cudaError_t launch_gemm_tc(const TcGemmArgs& p, cudaStream_t st) {
   if (!tc_gemm_supported(p.M, p.N, p.K) || (p.lda % 8) || (p.ldw % 8) || ((p.Cf != nullptr) == (p.Cb != nullptr)))
     return cudaErrorInvalidValue;
   if ((reinterpret_cast<uintptr_t>(p.A) & 15) || (reinterpret_cast<uintptr_t>(p.W) & 15)) return cudaErrorInvalidValue;
-  // pick the tile width with the least padded work; ties go to the wider tile
+  // pick the tile width with the least padded work; ties go to the wider tile.  With only a few waves of tiles over the
+  // persistent grid the wave count decides instead (a nearly empty second wave doubles the time): cost = waves x width.
   const int cands[3] = {256, 192, 128};
   int best = 256;
-  long best_waste = -1;
+  long best_cost = -1;
+  const long m_tiles = (p.M + kBM - 1) / kBM;
+  const bool few = m_tiles * ((p.N + 255) / 256) < 2L * sm_count();
   for (int bn : cands) {
-    const long waste = (long)((p.N + bn - 1) / bn) * bn - p.N;
-    if (best_waste < 0 || waste < best_waste) { best = bn; best_waste = waste; }
+    const long n_tiles = (p.N + bn - 1) / bn;
+    const long cost = few ? ((m_tiles * n_tiles + sm_count() - 1) / sm_count()) * bn : n_tiles * bn - p.N;
+    if (best_cost < 0 || cost < best_cost) { best = bn; best_cost = cost; }
   }
   if (p.act < 0 || p.act > 2) return cudaErrorInvalidValue;
   // skinny problems (decoder steps, M = images x beam): few tiles, so prefer narrow tiles -- more CTAs in flight and

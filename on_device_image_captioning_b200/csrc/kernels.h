@@ -58,6 +58,25 @@ struct Mma16Args {
 template <typename T, typename OutT>
 cudaError_t launch_gemm_mma16(const Mma16Args& p, cudaStream_t st);
 
+// ---------------------------------------------------------------- skinny 16-bit GEMM (decoder-step linears)
+// C = act(LN?(A) . W^T + bias) + res for M <= 512 rows: small tiles, operands resident in smem, optional LayerNorm /
+// fp32->16-bit conversion of A on load, split-K over a thread-block cluster (gemm_skinny.cu).
+struct SkinnyArgs {
+  const void* A16;                   // (M x K) 16-bit operand, or
+  const float* A32;                  // (M x K) fp32 rows, converted on load (exactly one of A16 / A32)
+  long lda;
+  const float *ln_g, *ln_b;          // LayerNorm over the K columns of A32 (needs K <= 1024), or null
+  const void* W; long ldw;           // (N x K) 16-bit
+  const float* bias;
+  const float* res; long ldr;        // fp32 residual (may alias Cf)
+  float* Cf; void* Cb; long ldc;     // fp32 or 16-bit output, exactly one non-null
+  int M, N, K;
+  int act;                           // 0 none, 1 GELU(erf), 2 ReLU
+};
+bool skinny_gemm_supported(const SkinnyArgs& p);
+template <typename T>
+cudaError_t launch_gemm_skinny(const SkinnyArgs& p, cudaStream_t st);
+
 // ---------------------------------------------------------------- normalisation / embedding
 template <typename OutT>
 cudaError_t launch_layernorm(const float* x, long ldx, const float* gamma, const float* beta, OutT* y, long ldy,

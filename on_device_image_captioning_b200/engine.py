@@ -193,6 +193,28 @@ class Engine:
                                           PRECISIONS[precision], self._stream()), "xn_op_linear")
         return y
 
+    def op_linear_skinny(self, x, w, bias=None, residual=None, act: int = 0, precision: str = "fp16", gamma=None, beta=None,
+                         x_is_16bit: bool = False):
+        x = self._f32(x); w = self._f32(w)
+        M, K = x.shape
+        N = w.shape[0]
+        b = self._f32(bias) if bias is not None else None
+        r = self._f32(residual) if residual is not None else None
+        g = self._f32(gamma) if gamma is not None else None
+        be = self._f32(beta) if beta is not None else None
+        y = torch.empty(M, N, device=self.device, dtype=torch.float32)
+        self._check(self.lib.xn_op_linear_skinny(self._h, _ptr(x), _ptr(g), _ptr(be), _ptr(w), _ptr(b), _ptr(r), _ptr(y), M, N, K,
+                                                 act, int(x_is_16bit), PRECISIONS[precision], self._stream()), "xn_op_linear_skinny")
+        return y
+
+    def op_gemm_raw(self, which: int, a, w16, bias, residual, y, act: int = 0, precision: str = "fp16", gamma=None, beta=None):
+        """Measurement hook: one GEMM launch on device operands as they are (a: 16-bit for which 0/1, fp32 for which 2)."""
+        M, K = a.shape
+        N = w16.shape[0]
+        self._check(self.lib.xn_op_gemm_raw(self._h, which, _ptr(a), _ptr(gamma), _ptr(beta), _ptr(w16), _ptr(bias), _ptr(residual),
+                                            _ptr(y), M, N, K, act, PRECISIONS[precision], self._stream()), "xn_op_gemm_raw")
+        return y
+
     def op_window_attention(self, qkv, bias_table, B, H, C_, heads, shift, precision: str = "fp32"):
         qkv = self._f32(qkv); bt = self._f32(bias_table)
         out = torch.empty(B * H * H, C_, device=self.device, dtype=torch.float32)

@@ -118,6 +118,40 @@ def check_linear_bf16(precision: str = "bf16") -> List[Triple]:
     return out
 
 
+def check_linear_skinny(precision: str = "fp16") -> List[Triple]:
+    """Decoder-step GEMM (mma.sync, resident operands, cluster split-K, LayerNorm fused into the A load) vs an fp64
+    product of the same 16-bit-rounded operands."""
+    e = bare_engine()
+    rnd = (lambda t: t.bfloat16()) if precision == "bf16" else (lambda t: t.half())
+    out = []
+    g = torch.Generator().manual_seed(12)
+    # (M, N, K, act, res, ln, x16): the decoder's shapes at batch 64 x beam 3, ragged rows / columns, batch 1
+    cases = [(192, 2560, 512, 0, False, True, False), (192, 512, 512, 0, False, False, True), (192, 512, 512, 0, True, False, True),
+             (192, 2048, 512, 2, False, True, False), (192, 512, 2048, 0, True, False, True), (192, 512, 1536, 0, True, False, False),
+             (3, 512, 512, 0, True, False, True), (5, 2048, 512, 2, False, True, False), (100, 130, 256, 1, True, False, True),
+             (320, 10000, 512, 0, False, True, False), (65, 64, 512, 0, False, True, False), (40, 512, 1536, 0, True, False, False)]
+    for (M, N, K, act, res, ln, x16) in cases:
+        x = torch.randn(M, K, generator=g) * 1.5 + 0.3
+        w = torch.randn(N, K, generator=g) / math.sqrt(K)
+        b = torch.randn(N, generator=g)
+        r = torch.randn(M, N, generator=g) if res else None
+        ga = (1.0 + 0.2 * torch.randn(K, generator=g)) if ln else None
+        be = (0.1 * torch.randn(K, generator=g)) if ln else None
+        y = e.op_linear_skinny(x, w, b, r, act, precision, ga, be, x16)
+        xa = torch.nn.functional.layer_norm(x, (K,), ga, be, 1e-5) if ln else x
+        ref = torch.nn.functional.linear(rnd(xa).double(), rnd(w).double(), b.double())
+        if act == 1:
+            ref = torch.nn.functional.gelu(ref)
+        elif act == 2:
+            ref = torch.relu(ref)
+        if res:
+            ref = ref + r.double()
+        # the fused LayerNorm rounds to 16 bits from a slightly different fp32 value than torch's: allow 1 operand ulp
+        tol = 2e-5 if not ln else (3e-3 if precision == "fp16" else 2e-2)
+        out.append((f"linear_{precision}_skinny[{M}x{N}x{K} act{act} res{int(res)} ln{int(ln)} x16={int(x16)}] rel-max", rel_max(y, ref), tol))
+    return out
+
+
 def check_window_attention(precision: str = "fp32") -> List[Triple]:
     e = bare_engine()
     out = []
