@@ -13,6 +13,8 @@ namespace xn {
 constexpr int kMaxBeam = 8;
 
 __global__ void beam_init_kernel(BeamBufs bb, int B, int beam, int L, int sos) {
+  pdl_wait();
+  pdl_trigger();
   const int r = blockIdx.x * blockDim.x + threadIdx.x;      // row = b*beam + k
   if (r >= B * beam) return;
   for (int s = 0; s < 2; ++s) {
@@ -31,6 +33,8 @@ __global__ void beam_init_kernel(BeamBufs bb, int B, int beam, int L, int sos) {
 // step 0 (:242-271): all beams of an image hold [SOS]; beam k takes the k-th best first word of row (b,0).
 __global__ void beam_first_kernel(BeamBufs bb, const float* __restrict__ top_val, const int* __restrict__ top_idx,
                                   int B, int beam, int L, int eos) {
+  pdl_wait();
+  pdl_trigger();
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= B * beam) return;
   const int b = r / beam, k = r % beam;
@@ -51,6 +55,8 @@ __global__ void beam_first_kernel(BeamBufs bb, const float* __restrict__ top_val
 // sum performs exactly the additions of history.sum(-1) in the same order.
 __global__ void __launch_bounds__(128) beam_step_kernel(BeamBufs bb, int src, const float* __restrict__ top_val,
                                                         const int* __restrict__ top_idx, int B, int beam, int L, int t, int eos) {
+  pdl_wait();
+  pdl_trigger();
   const int b = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (b >= B) return;
   const int dst = src ^ 1, nc = beam * beam;
@@ -120,6 +126,8 @@ __global__ void __launch_bounds__(128) beam_step_kernel(BeamBufs bb, int src, co
 __global__ void beam_finalize_kernel(BeamBufs bb, int src, int B, int beam, int L, int t_final, int how_many,
                                      int* __restrict__ out_tokens, int* __restrict__ out_len,
                                      float* __restrict__ out_lp) {
+  pdl_wait();
+  pdl_trigger();
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
   const int* tk = bb.tokens[src] + (long)b * beam * L;
@@ -151,22 +159,22 @@ __global__ void beam_finalize_kernel(BeamBufs bb, int src, int B, int beam, int 
 
 cudaError_t launch_beam_init(const BeamBufs& bb, int B, int beam, int L, int sos, cudaStream_t st) {
   if (beam > kMaxBeam) return cudaErrorInvalidValue;
-  beam_init_kernel<<<(B * beam + 127) / 128, 128, 0, st>>>(bb, B, beam, L, sos);
+  launch_k(beam_init_kernel, dim3((B * beam + 127) / 128), dim3(128), 0, st, bb, B, beam, L, sos);
   return cudaGetLastError();
 }
 cudaError_t launch_beam_first(const BeamBufs& bb, const float* top_val, const int* top_idx, int B, int beam, int L,
                               int eos, cudaStream_t st) {
-  beam_first_kernel<<<(B * beam + 127) / 128, 128, 0, st>>>(bb, top_val, top_idx, B, beam, L, eos);
+  launch_k(beam_first_kernel, dim3((B * beam + 127) / 128), dim3(128), 0, st, bb, top_val, top_idx, B, beam, L, eos);
   return cudaGetLastError();
 }
 cudaError_t launch_beam_step(const BeamBufs& bb, int src, const float* top_val, const int* top_idx, int B, int beam,
                              int L, int t, int eos, cudaStream_t st) {
-  beam_step_kernel<<<(B + 3) / 4, 128, 0, st>>>(bb, src, top_val, top_idx, B, beam, L, t, eos);
+  launch_k(beam_step_kernel, dim3((B + 3) / 4), dim3(128), 0, st, bb, src, top_val, top_idx, B, beam, L, t, eos);
   return cudaGetLastError();
 }
 cudaError_t launch_beam_finalize(const BeamBufs& bb, int src, int B, int beam, int L, int t_final, int how_many,
                                  int* out_tokens, int* out_len, float* out_lp, cudaStream_t st) {
-  beam_finalize_kernel<<<(B + 63) / 64, 64, 0, st>>>(bb, src, B, beam, L, t_final, how_many, out_tokens, out_len,
+  launch_k(beam_finalize_kernel, dim3((B + 63) / 64), dim3(64), 0, st, bb, src, B, beam, L, t_final, how_many, out_tokens, out_len,
                                                      out_lp);
   return cudaGetLastError();
 }

@@ -4,12 +4,38 @@
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include <stdint.h>
+#include <utility>
 
 namespace xn {
 
 constexpr int kWin = 12;            // Swin window edge (swin_window_size=12 at every reference call site)
 constexpr int kWinTok = kWin * kWin; // 144 tokens per window
 constexpr int kHeadDim = 32;        // C / heads == 32 in every Swin-L stage (reference swin:189-190)
+
+// ---- programmatic dependent launch (PDL).  Every kernel of the 16-bit production path is launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization and starts with pdl_wait() (griddepcontrol.wait: blocks until the
+// preceding kernels in the stream have completed and flushed) followed by pdl_trigger() (lets the next kernel's CTAs
+// be scheduled as soon as every CTA of this one is running).  Launch latency, block scheduling and the per-kernel
+// prologue then overlap the tail of the previous kernel instead of following it -- the decode loop is ~700 dependent
+// launches of a few microseconds each.  Nothing before pdl_wait() may touch global memory written by earlier kernels.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+extern int g_pdl_enabled;
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = g_pdl_enabled ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

@@ -18,6 +18,8 @@ constexpr float kCrossFill = -1e4f;  // reference models/layers.py:284
 __global__ void embed_kernel(const int64_t* __restrict__ t64, const int* __restrict__ t32, long tok_stride, int p,
                              const float* __restrict__ emb, const float* __restrict__ pos, float* __restrict__ x,
                              long ldx, int R, int d) {
+  pdl_wait();
+  pdl_trigger();
   const int r = blockIdx.x;
   const long tok = t64 ? (long)t64[r * tok_stride + p] : (long)t32[r * tok_stride + p];
   const float sc = sqrtf((float)d);
@@ -26,7 +28,7 @@ __global__ void embed_kernel(const int64_t* __restrict__ t64, const int* __restr
 }
 cudaError_t launch_embed(const int64_t* tokens64, const int* tokens32, long tok_stride, int p, const float* emb,
                          const float* pos, float* x, long ldx, int R, int d, cudaStream_t st) {
-  embed_kernel<<<R, 128, 0, st>>>(tokens64, tokens32, tok_stride, p, emb, pos, x, ldx, R, d);
+  launch_k(embed_kernel, dim3(R), dim3(128), 0, st, tokens64, tokens32, tok_stride, p, emb, pos, x, ldx, R, d);
   return cudaGetLastError();
 }
 
@@ -50,6 +52,8 @@ __global__ void __launch_bounds__(128) embed_ln_kernel(const int64_t* __restrict
                                                        int p, const float* __restrict__ emb, const float* __restrict__ pos,
                                                        float* __restrict__ x, long ldx, const float* __restrict__ g,
                                                        const float* __restrict__ be, T* __restrict__ xn, long ldn, int d) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ float red[32];
   const int r = blockIdx.x, c = threadIdx.x * 4;
   const long tok = t64 ? (long)t64[r * tok_stride + p] : (long)t32[r * tok_stride + p];
@@ -72,7 +76,7 @@ cudaError_t launch_embed_ln(const int64_t* tokens64, const int* tokens32, long t
                             const float* pos, float* x, long ldx, const float* gamma, const float* beta, T* xn, long ldn, int R,
                             int d, cudaStream_t st) {
   if (d != 512 || (ldx & 3)) return cudaErrorInvalidValue;
-  embed_ln_kernel<T><<<R, 128, 0, st>>>(tokens64, tokens32, tok_stride, p, emb, pos, x, ldx, gamma, beta, xn, ldn, d);
+  launch_k(embed_ln_kernel<T>, dim3(R), dim3(128), 0, st, tokens64, tokens32, tok_stride, p, emb, pos, x, ldx, gamma, beta, xn, ldn, d);
   return cudaGetLastError();
 }
 template cudaError_t launch_embed_ln<float>(const int64_t*, const int*, long, int, const float*, const float*, float*, long, const float*, const float*, float*, long, int, int, cudaStream_t);
@@ -99,6 +103,8 @@ __global__ void __launch_bounds__(256) dyn_exp_step_kernel(DecState s, int layer
                                                            float* __restrict__ x_out, long ldxo, int d,
                                                            const float* __restrict__ ln_g, const float* __restrict__ ln_b,
                                                            T* __restrict__ ln_out, long ldn) {
+  pdl_wait();
+  pdl_trigger();
   extern __shared__ float sm[];
   const int r = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int P = s.P, np = p + 1;
@@ -286,7 +292,7 @@ cudaError_t launch_dyn_exp_step(const DecState& s, int layer, int p, const float
       configured = smem;
     }
   }
-  dyn_exp_step_kernel<T><<<s.R, 256, smem, st>>>(s, layer, p, qexp, bexp, n_exp, row_len, x_in, ldxi, x_out, ldxo, d, ln_g, ln_b,
+  launch_k(dyn_exp_step_kernel<T>, dim3(s.R), dim3(256), smem, st, s, layer, p, qexp, bexp, n_exp, row_len, x_in, ldxi, x_out, ldxo, d, ln_g, ln_b,
                                                  ln_out, ldn);
   return cudaGetLastError();
 }
@@ -324,6 +330,8 @@ __global__ void __launch_bounds__(256) cross_attn_step_kernel(const float* __res
                                                               int rows_per_image, int n, int dk,
                                                               const int* __restrict__ n_valid,
                                                               const int* __restrict__ row_len, int p) {
+  pdl_wait();
+  pdl_trigger();
   extern __shared__ float sm[];
   const int b = blockIdx.x, h = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int kt = n + 1;           // K is staged transposed [dk][n+1]: the score loop reads it conflict-free
@@ -433,6 +441,8 @@ __global__ void __launch_bounds__(256) cross_attn_step16_kernel(const float* __r
                                                                 T* __restrict__ out, long ldo, int n,
                                                                 const int* __restrict__ n_valid,
                                                                 const int* __restrict__ row_len, int p) {
+  pdl_wait();
+  pdl_trigger();
   constexpr int dk = 64;
   __shared__ float pr[RPI][kCaMaxKeys];            // scores, then probabilities
   __shared__ float po[8][RPI][dk];                 // per-warp partial outputs
@@ -529,7 +539,7 @@ __global__ void __launch_bounds__(256) cross_attn_step16_kernel(const float* __r
 template <typename T, int RPI>
 static cudaError_t launch_ca16(const float* q, long ldq, const T* kv, long ldkv, int k_off, int v_off, T* out, long ldo, int R,
                                int n_keys, int heads, const int* n_valid, const int* row_len, int p, cudaStream_t st) {
-  cross_attn_step16_kernel<T, RPI><<<dim3(R / RPI, heads), 256, 0, st>>>(q, ldq, kv, ldkv, k_off, v_off, out, ldo, n_keys, n_valid, row_len, p);
+  launch_k(cross_attn_step16_kernel<T, RPI>, dim3(dim3(R / RPI, heads)), dim3(256), 0, st, q, ldq, kv, ldkv, k_off, v_off, out, ldo, n_keys, n_valid, row_len, p);
   return cudaGetLastError();
 }
 template <typename T>
@@ -581,7 +591,7 @@ cudaError_t launch_cross_attn_step(const float* q, long ldq, const KvT* kv, long
     if (e != cudaSuccess) return e;
     configured = smem;
   }
-  cross_attn_step_kernel<KvT, OutT><<<dim3(R / rows_per_image, heads), 256, smem, st>>>(
+  launch_k(cross_attn_step_kernel<KvT, OutT>, dim3(dim3(R / rows_per_image, heads)), dim3(256), smem, st, 
       q, ldq, kv, ldkv, k_off, v_off, out, ldo, rows_per_image, n_keys, dk, n_valid, row_len, p);
   return cudaGetLastError();
 }
@@ -601,6 +611,8 @@ __device__ __forceinline__ bool better(float v, int i, float bv, int bi) { retur
 __global__ void __launch_bounds__(256) logsoftmax_topk_kernel(const float* __restrict__ logits, long ld, int V, int k,
                                                               float* __restrict__ top_val, int* __restrict__ top_idx,
                                                               float* __restrict__ logprob, long ldlp, int write_mode) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ float red[32];
   __shared__ float cv[256];
   __shared__ int ci[256];
@@ -669,6 +681,8 @@ constexpr int kLsVec = 10;             // float4 per thread: 256 * 40 = 10240 lo
 __global__ void __launch_bounds__(256) logsoftmax_topk_reg_kernel(const float* __restrict__ logits, long ld, int V, int k,
                                                                   float* __restrict__ top_val, int* __restrict__ top_idx,
                                                                   float* __restrict__ logprob, long ldlp, int write_mode) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ float red[32];
   __shared__ float wv[8];
   __shared__ int wi[8];
@@ -750,10 +764,10 @@ cudaError_t launch_logsoftmax_topk(const float* logits, long ld, int rows, int V
                                    float* logprob, long ldlp, int write_mode, cudaStream_t st) {
   if (k > kMaxTopK) return cudaErrorInvalidValue;
   if (V <= 256 * 4 * kLsVec && (ld & 3) == 0 && (reinterpret_cast<uintptr_t>(logits) & 15) == 0) {
-    logsoftmax_topk_reg_kernel<<<rows, 256, 0, st>>>(logits, ld, V, k, top_val, top_idx, logprob, ldlp, write_mode);
+    launch_k(logsoftmax_topk_reg_kernel, dim3(rows), dim3(256), 0, st, logits, ld, V, k, top_val, top_idx, logprob, ldlp, write_mode);
     return cudaGetLastError();
   }
-  logsoftmax_topk_kernel<<<rows, 256, 0, st>>>(logits, ld, V, k, top_val, top_idx, logprob, ldlp, write_mode);
+  launch_k(logsoftmax_topk_kernel, dim3(rows), dim3(256), 0, st, logits, ld, V, k, top_val, top_idx, logprob, ldlp, write_mode);
   return cudaGetLastError();
 }
 

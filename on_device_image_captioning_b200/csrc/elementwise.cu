@@ -67,6 +67,8 @@ template <typename OutT>
 __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, long ldx,
                                                         const float* __restrict__ g, const float* __restrict__ b,
                                                         OutT* __restrict__ y, long ldy, long rows, int C) {
+  pdl_wait();
+  pdl_trigger();
   const long row = (long)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= rows) return;
   const float* xr = x + row * ldx;
@@ -81,6 +83,8 @@ template <typename OutT, int VPL, int RIF>
 __global__ void __launch_bounds__(256) layernorm_rows_kernel(const float* __restrict__ x, long ldx,
                                                              const float* __restrict__ g, const float* __restrict__ b,
                                                              OutT* __restrict__ y, long ldy, long rows, int C) {
+  pdl_wait();
+  pdl_trigger();
   const int lane = threadIdx.x & 31;
   const long warp_g = (long)blockIdx.x * 8 + (threadIdx.x >> 5), nwarps = (long)gridDim.x * 8;
   constexpr bool kAffineInRegs = VPL <= 3;      // wide rows re-read gamma/beta (L1-resident) to keep occupancy up
@@ -142,7 +146,7 @@ cudaError_t launch_layernorm(const float* x, long ldx, const float* gamma, const
   const int vpl = (C + 127) / 128;
   if (rows >= 4096 && vpl <= 12) {
     const unsigned grid = 148 * 6;
-#define XN_LN(V, R) layernorm_rows_kernel<OutT, V, R><<<grid, 256, 0, st>>>(x, ldx, gamma, beta, y, ldy, rows, C)
+#define XN_LN(V, R) launch_k(layernorm_rows_kernel<OutT, V, R>, dim3(grid), dim3(256), 0, st, x, ldx, gamma, beta, y, ldy, rows, C)
     if (vpl <= 2) XN_LN(2, 4);
     else if (vpl <= 3) XN_LN(3, 4);
     else if (vpl <= 4) XN_LN(4, 2);
@@ -151,7 +155,7 @@ cudaError_t launch_layernorm(const float* x, long ldx, const float* gamma, const
 #undef XN_LN
     return cudaGetLastError();
   }
-  layernorm_kernel<OutT><<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(x, ldx, gamma, beta, y, ldy, rows, C);
+  launch_k(layernorm_kernel<OutT>, dim3((unsigned)((rows + 7) / 8)), dim3(256), 0, st, x, ldx, gamma, beta, y, ldy, rows, C);
   return cudaGetLastError();
 }
 template cudaError_t launch_layernorm<float>(const float*, long, const float*, const float*, float*, long, long, int, cudaStream_t);
@@ -164,6 +168,8 @@ template <typename OutT>
 __global__ void __launch_bounds__(256) merge_layernorm_kernel(const float* __restrict__ x, const float* __restrict__ g,
                                                               const float* __restrict__ b, OutT* __restrict__ y,
                                                               int B, int H, int C) {
+  pdl_wait();
+  pdl_trigger();
   const int H2 = H / 2;
   const long rows = (long)B * H2 * H2;
   const long row = (long)blockIdx.x * 8 + (threadIdx.x >> 5);
@@ -184,7 +190,7 @@ cudaError_t launch_merge_layernorm(const float* x, const float* gamma, const flo
                                    int C, cudaStream_t st) {
   if (C & 3) return cudaErrorInvalidValue;
   const long rows = (long)B * (H / 2) * (H / 2);
-  merge_layernorm_kernel<OutT><<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(x, gamma, beta, y, B, H, C);
+  launch_k(merge_layernorm_kernel<OutT>, dim3((unsigned)((rows + 7) / 8)), dim3(256), 0, st, x, gamma, beta, y, B, H, C);
   return cudaGetLastError();
 }
 template cudaError_t launch_merge_layernorm<float>(const float*, const float*, const float*, float*, int, int, int, cudaStream_t);
@@ -202,6 +208,8 @@ __global__ void __launch_bounds__(256) patch_embed_kernel(const float* __restric
                                                           const float* __restrict__ bias, const float* __restrict__ g,
                                                           const float* __restrict__ be, float* __restrict__ out,
                                                           int Cin, int S, int P, int E) {
+  pdl_wait();
+  pdl_trigger();
   extern __shared__ float sm[];
   const int G = S / P, K = Cin * P * P;
   float* slab = sm;                       // [Cin*P][S]   one patch row of input pixels
@@ -289,12 +297,14 @@ cudaError_t launch_patch_embed(const float* img, const float* w, const float* b,
     configured = smem;
   }
   const int G = S / P, groups = (G + kPeRows - 1) / kPeRows;
-  patch_embed_kernel<<<B * groups, 256, smem, st>>>(img, w, b, gamma, beta, out, Cin, S, P, E);
+  launch_k(patch_embed_kernel, dim3(B * groups), dim3(256), smem, st, img, w, b, gamma, beta, out, Cin, S, P, E);
   return cudaGetLastError();
 }
 
 template <typename T>
 __global__ void cast_kernel(const float* __restrict__ x, T* __restrict__ y, long n) {
+  pdl_wait();
+  pdl_trigger();
   const long i = ((long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
   if (i + 3 < n) {
     const float4 v = *reinterpret_cast<const float4*>(x + i);
@@ -306,7 +316,7 @@ __global__ void cast_kernel(const float* __restrict__ x, T* __restrict__ y, long
 template <typename T>
 cudaError_t launch_cast(const float* x, T* y, long n, cudaStream_t st) {
   if (n <= 0) return cudaSuccess;
-  cast_kernel<T><<<(unsigned)((n / 4 + 256) / 256), 256, 0, st>>>(x, y, n);
+  launch_k(cast_kernel<T>, dim3((unsigned)((n / 4 + 256) / 256)), dim3(256), 0, st, x, y, n);
   return cudaGetLastError();
 }
 template cudaError_t launch_cast<bf16>(const float*, bf16*, long, cudaStream_t);
@@ -321,6 +331,8 @@ template cudaError_t launch_cast<float>(const float*, float*, long, cudaStream_t
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) se_group_sum_kernel(const float* __restrict__ z, const int* __restrict__ gstart,
                                                            float* __restrict__ gsum, int E, int N, int n_groups) {
+  pdl_wait();
+  pdl_trigger();
   const int b = blockIdx.x, g = blockIdx.y;
   const int e0 = gstart[g], e1 = gstart[g + 1];
   for (int n = threadIdx.x; n < N; n += blockDim.x) {
@@ -342,6 +354,8 @@ __global__ void __launch_bounds__(256) se_weights_kernel(const float* __restrict
                                                          const float* __restrict__ gsum, WT* __restrict__ a_fw,
                                                          WT* __restrict__ b_fw, WT* __restrict__ a_bw,
                                                          WT* __restrict__ b_bw, int E, int N, int chunk) {
+  pdl_wait();
+  pdl_trigger();
   extern __shared__ float zt[];            // [chunk][N]
   const int b = blockIdx.x, e0 = blockIdx.y * chunk;
   const int nv = n_valid ? n_valid[b] : N;
@@ -386,10 +400,10 @@ cudaError_t launch_static_exp_weights(const float* z, const int* n_valid, const 
                                       int B, int E, int N, int chunk, cudaStream_t st) {
   // `chunk` rows of z per CTA; it must divide every group boundary (the engine picks the gcd, <= 32)
   if (chunk <= 0 || (E % chunk)) return cudaErrorInvalidValue;
-  se_group_sum_kernel<<<dim3(B, n_groups), 160, 0, st>>>(z, group_start, gsum_scratch, E, N, n_groups);
+  launch_k(se_group_sum_kernel, dim3(dim3(B, n_groups)), dim3(160), 0, st, z, group_start, gsum_scratch, E, N, n_groups);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
-  se_weights_kernel<WT><<<dim3(B, E / chunk), 256, (size_t)chunk * N * sizeof(float), st>>>(
+  launch_k(se_weights_kernel<WT>, dim3(dim3(B, E / chunk)), dim3(256), (size_t)chunk * N * sizeof(float), st, 
       z, n_valid, group_start, n_groups, gsum_scratch, a_fw, b_fw, a_bw, b_bw, E, N, chunk);
   return cudaGetLastError();
 }
@@ -402,6 +416,8 @@ template <typename ST>
 __global__ void selector_mix_kernel(const float* __restrict__ xi, long ldxi, const ST* __restrict__ sel, long lds,
                                     const float* __restrict__ a, const float* __restrict__ bb, long ldo,
                                     float* __restrict__ xo, long ldxo, long rows, int d) {
+  pdl_wait();
+  pdl_trigger();
   const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= rows * d) return;
   const long r = i / d;
@@ -414,7 +430,7 @@ cudaError_t launch_selector_mix(const float* x_in, long ldxi, const ST* sel, lon
                                 const float* out_b, long ldo, float* x_out, long ldxo, long rows, int d,
                                 cudaStream_t st) {
   const long n = rows * d;
-  selector_mix_kernel<ST><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(x_in, ldxi, sel, lds, out_a, out_b, ldo, x_out,
+  launch_k(selector_mix_kernel<ST>, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, st, x_in, ldxi, sel, lds, out_a, out_b, ldo, x_out,
                                                                       ldxo, rows, d);
   return cudaGetLastError();
 }

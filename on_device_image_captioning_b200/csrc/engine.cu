@@ -1216,6 +1216,7 @@ int xn_set_option(xn_handle* h, const char* name, int64_t value) {
   if (n == "use_graph") { h->use_graph = value; h->drop_graphs(); return XN_OK; }
   if (n == "op_out16") { h->op_out16 = value; return XN_OK; }
   if (n == "use_skinny") { h->use_skinny = value; h->drop_graphs(); return XN_OK; }
+  if (n == "pdl") { g_pdl_enabled = value != 0; h->drop_graphs(); return XN_OK; }
   if (n == "tc_debug") { set_tc_debug((int)value); return XN_OK; }
   if (n == "profile") { h->profile = value; h->prof_used = 0; h->prof_flops.clear(); }
   else if (n == "swin_chunk") h->swin_chunk = std::max<int64_t>(1, value);

@@ -60,6 +60,8 @@ template <> __device__ __forceinline__ void store2<f16>(f16* p, float a, float b
 // BM = 128: warps 2 (M) x 4 (N), warp tile 64 x 32.   BM = 64: warps 2 x 4, warp tile 32 x 32.
 template <typename T, typename OutT, int BM, bool BKN>
 __global__ void __launch_bounds__(256) gemm_mma16_kernel(Mma16Args p) {
+  pdl_wait();
+  pdl_trigger();
   extern __shared__ __align__(16) unsigned char smraw[];
   constexpr int kAStage = BM * kApad;
   constexpr int kBStage = BKN ? kBKm * kBpadKN : kBN * kApad;
@@ -181,7 +183,7 @@ cudaError_t launch_gemm_mma16(const Mma16Args& p, cudaStream_t st) {
       if (e != cudaSuccess) return e;                                                                                    \
       cfgd = true;                                                                                                       \
     }                                                                                                                    \
-    gemm_mma16_kernel<T, OutT, BMV, KNV><<<grid, 256, smem, st>>>(p);                                                   \
+    launch_k(gemm_mma16_kernel<T, OutT, BMV, KNV>, dim3(grid), dim3(256), smem, st, p);                                                   \
   } while (0)
   if (small_m) { if (p.b_kn) XN_LAUNCH_MMA(64, true); else XN_LAUNCH_MMA(64, false); }
   else         { if (p.b_kn) XN_LAUNCH_MMA(128, true); else XN_LAUNCH_MMA(128, false); }

@@ -141,6 +141,8 @@ __device__ __forceinline__ void skinny_ln_rows(const SkinnyArgs& p, T* As, int P
 // grid = (ceil(N / BN), ceil(M / 64), split); cluster = (1, 1, split).  Kc = K / split columns per CTA.
 template <typename T, int BN>
 __global__ void __launch_bounds__(kSkThreads) gemm_skinny_kernel(SkinnyArgs p, int Kc, int split) {
+  pdl_wait();
+  pdl_trigger();
   extern __shared__ __align__(16) unsigned char smraw[];
   const int PA = Kc + 8;                               // smem row pitch in elements: (2 Kc + 16) / 16 is odd -> conflict-free ldmatrix
   T* As = reinterpret_cast<T*>(smraw);                 // [64][PA]
@@ -283,13 +285,22 @@ static cudaError_t launch_skinny_bn(const SkinnyArgs& p, int split, cudaStream_t
   cfg.blockDim = dim3(kSkThreads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 1;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = split;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (split > 1) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = 1;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = split;
+    ++na;
+  }
+  if (g_pdl_enabled) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
   cfg.attrs = attr;
-  cfg.numAttrs = split > 1 ? 1 : 0;
+  cfg.numAttrs = na;
   return cudaLaunchKernelEx(&cfg, gemm_skinny_kernel<T, BN>, p, Kc, split);
 }
 

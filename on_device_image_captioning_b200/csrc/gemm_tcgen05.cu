@@ -220,6 +220,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_gen;
+  // barrier init and the TMEM allocation above overlap the previous kernel's tail (programmatic dependent launch)
+  pdl_wait();
+  pdl_trigger();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -590,6 +593,7 @@ static bool make_map(CUtensorMap* map, const void* ptr, long rows, long cols, lo
 }
 
 int g_tc_debug = 0;
+int g_pdl_enabled = 1;
 void set_tc_debug(int v) { g_tc_debug = v; }
 
 bool tc_gemm_supported(int M, int N, int K) { return M > 0 && N > 0 && K > 0 && (K % 8) == 0; }
@@ -647,7 +651,7 @@ static cudaError_t launch_tc(const TcGemmArgs& p, cudaStream_t st) {
   TcEpilogue ep{p.Cf, p.Cb, p.ldc, p.fp16, p.bias, p.res, p.ldr, p.div != 0.f ? 1.0f / p.div : 1.0f, tma_c_ok ? 1 : 0, g_tc_debug};
   const int tiles = ((p.M + kBM - 1) / kBM) * ((p.N + BN - 1) / BN);
   const int grid = tiles < sm_count() ? tiles : sm_count();
-  gemm_tc_kernel<BN, OUT, ACT><<<grid, kTcThreads, Cfg::kSmemBytes, st>>>(ma, mb, mc, mr, ep, p.M, p.N, p.K);
+  launch_k(gemm_tc_kernel<BN, OUT, ACT>, dim3(grid), dim3(kTcThreads), Cfg::kSmemBytes, st, ma, mb, mc, mr, ep, p.M, p.N, p.K);
   return cudaGetLastError();
 }
 

@@ -8,6 +8,8 @@
 
 namespace xn {
 
+extern int g_pdl_enabled;   // programmatic dependent launch for the kernels of the 16-bit path (common.cuh)
+
 typedef __nv_bfloat16 bf16;
 typedef __half f16;
 

@@ -183,6 +183,8 @@ __global__ void __launch_bounds__(kMmaThreads, 2) window_attention_mma_kernel(co
   for (int i = tid; i < 2 * kWinTok * kLPitch / 2; i += kMmaThreads) reinterpret_cast<uint32_t*>(lab_all)[i] = 0u;
   if (tid < kWinTok) jneg[tid] = -4 * (my_ty * (2 * kWin - 1) + my_tx);
   __syncthreads();
+  pdl_wait();
+  pdl_trigger();
   int item = blockIdx.x;
   if (item >= n_items) return;
   ItemPos cur = decode_item(item);
@@ -357,7 +359,7 @@ static cudaError_t launch_wa_hpc(const T* qkv, const float* bias_l2, T* out, int
   const int nW = (H / kWin) * (H / kWin);
   const int n_items = B * nW * (heads / HPC);
   const int grid = std::min(n_items, 2 * wa_sm_count());
-  window_attention_mma_kernel<T, HPC><<<grid, kMmaThreads, smem, st>>>(qkv, bias_l2, out, H, C, heads, shift, n_items);
+  launch_k(window_attention_mma_kernel<T, HPC>, dim3(grid), dim3(kMmaThreads), smem, st, qkv, bias_l2, out, H, C, heads, shift, n_items);
   return cudaGetLastError();
 }
 
