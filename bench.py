@@ -46,6 +46,18 @@ def _peaks():
     return dict(bf16_sustained=1400.0, bf16_burst=1590.0, hbm=6650.0, source="fallback (B200_PROFILING.md)")
 
 
+def _traffic():
+    """dram read+write bytes per launch of the dominant kernel, from the committed `ncu --set full` capture
+    (profiles/gemm_tc_traffic.json, written by tools/ncu_traffic.py); None when no capture is committed."""
+    p = os.path.join(ROOT, "profiles", "gemm_tc_traffic.json")
+    if not os.path.exists(p):
+        return None
+    try:
+        return json.load(open(p))
+    except Exception:
+        return None
+
+
 class ClockSampler(threading.Thread):
     """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md recipe)."""
 
@@ -237,9 +249,42 @@ def run_ours(args):
             achieved = g_fl / (g_ms * 1e-3) / 1e12 if g_ms > 0 else 0.0
             roofline = dict(bound="tensor", kernel="gemm_tc_kernel (tcgen05.mma, TMA, TMEM)", achieved=achieved,
                             peak=peaks["bf16_sustained"], unit="TFLOP/s", frac=achieved / peaks["bf16_sustained"],
-                            traffic=None, peak_source=peaks["source"] + ", sustained figure (kernel timed inside a long step)",
+                            traffic=(_traffic() or {}).get("dram_bytes_per_launch"),
+                            traffic_detail=_traffic(), peak_source=peaks["source"] + ", sustained figure (kernel timed inside a long step)",
                             launches_timed=g_n, gemm_ms_per_step=g_ms, gemm_share_of_step=g_ms / (ms / args.steps),
                             algorithmic_tflop_per_step=g_fl / 1e12)
+        # ---- bandwidth-bound kernels: one more instrumented step with EVERY launch event-timed (graphs off), attributed
+        # to its launcher; achieved = algorithmic bytes (tensors that must cross HBM once) / summed time
+        hbm_kernels = None
+        if args.precision != "fp32":
+            eng.set_option("profile", 2)
+            eng.beam_search(devin[0], None, SOS, EOS, BEAM, 1, MAX_LEN)
+            spans = eng.profile_kernels()
+            eng.set_option("profile", 0)
+            G = cfg.img_size // cfg.patch_size
+            lc = sum(cfg.depths[i] * (G >> i) ** 2 * (cfg.embed_dim << i) for i in range(len(cfg.depths)))   # sum over blocks of L*C
+            R = B * BEAM
+            algo = {   # launcher -> (what, algorithmic bytes per step)
+                "ActOps<T>::attn": ("window_attention_mma_kernel: read QKV + write O, 16-bit", 8.0 * lc * B),
+                "launch_layernorm<T>": ("layernorm kernels (Swin 2 per block: fp32 in, 16-bit out; + encoder/decoder rows)",
+                                        2 * 6.0 * lc * B + 7 * 6.0 * cfg.enc_len * cfg.d_model * B),
+                "launch_logsoftmax_topk": ("logsoftmax_topk_reg_kernel: read R x V logits once", 4.0 * R * cfg.vocab * (MAX_LEN - 1)),
+                "launch_cross_attn_step<T, T>": ("cross_attn_step16_kernel: K/V of one layer per launch (KV-cache read by beam rows)",
+                                                 2.0 * 2 * cfg.enc_len * cfg.d_model * B * cfg.n_dec * (MAX_LEN - 1)),
+                "launch_patch_embed": ("patch_embed_kernel: read image fp32, write tokens fp32",
+                                       4.0 * B * (cfg.in_chans * cfg.img_size ** 2 + G * G * cfg.embed_dim)),
+            }
+            hbm_kernels = []
+            for key, (what, nbytes) in algo.items():
+                if key in spans and spans[key][1] > 0:
+                    n, t_ms = spans[key]
+                    gbs = nbytes / (t_ms * 1e-3) / 1e9
+                    hbm_kernels.append(dict(kernel=what, launches=n, ms_per_step=t_ms, algorithmic_gb_per_step=nbytes / 1e9,
+                                            achieved_gbs=gbs, frac_of_hbm_peak=gbs / peaks["hbm"]))
+            step_ms = sum(v[1] for v in spans.values())
+            shares = {k: round(v[1] / step_ms, 4) for k, v in sorted(spans.items(), key=lambda kv: -kv[1][1])[:12]}
+            if roofline is not None:
+                roofline["launcher_time_shares_eager_step"] = shares
         # ---- batch-1 latency (BASELINE.json configs[4])
         lat = {}
         one = devin[0][:1].contiguous()
@@ -279,7 +324,7 @@ def run_ours(args):
                     cpu_baseline=(dict(value=cpu_v, unit=UNIT, cores=threads, kind="port",
                                        sample="2 synthetic 384x384 images, beam 3, max_len 20, oracle/xnv2_oracle.py (torch CPU fp32, "
                                               f"{threads} threads), {cpu_dt:.1f} s") if cpu_v else None),
-                    latency_batch1=lat, clocks=clocks)
+                    hbm_kernels=hbm_kernels, latency_batch1=lat, clocks=clocks)
         emit(line)
     if world > 1:
         dist.barrier()

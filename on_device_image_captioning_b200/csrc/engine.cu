@@ -107,6 +107,15 @@ struct xn_handle {
   std::vector<cudaEvent_t> prof_ev;
   std::vector<double> prof_flops;
   size_t prof_used = 0;
+  // "profile" = 2: every kernel launch of the library is bracketed by events and attributed to its launcher
+  struct KernelSpan { const char* label; cudaEvent_t e0, e1; };
+  std::vector<KernelSpan> spans;
+  std::vector<cudaEvent_t> span_pool;
+  cudaStream_t cur_st = nullptr;
+  cudaEvent_t span_event() {
+    if (span_pool.empty()) { cudaEvent_t e; cudaEventCreate(&e); return e; }
+    cudaEvent_t e = span_pool.back(); span_pool.pop_back(); return e;
+  }
   float* io_in = nullptr; size_t io_in_cap = 0;     // xn_caption_host staging
   char* io_out = nullptr; size_t io_out_cap = 0;
 
@@ -132,7 +141,10 @@ struct xn_handle {
   } while (0)
 #define KL(n, expr)                                                                                \
   do {                                                                                             \
+    cudaEvent_t pe0_ = nullptr, pe1_ = nullptr;                                                    \
+    if (h->profile == 2) { pe0_ = h->span_event(); pe1_ = h->span_event(); cudaEventRecord(pe0_, h->cur_st); } \
     cudaError_t e_ = (expr);                                                                       \
+    if (pe0_) { cudaEventRecord(pe1_, h->cur_st); h->spans.push_back({#expr, pe0_, pe1_}); }       \
     h->launches += (n);                                                                            \
     if (e_ != cudaSuccess) return h->fail(XN_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); \
   } while (0)
@@ -174,7 +186,7 @@ int lin_tc(xn_handle* h, const void* x, long ldx, const LinW& w, const float* re
   TcGemmArgs g{};
   g.A = x; g.lda = ldx; g.W = w.wb; g.ldw = w.K; g.Cf = yf; g.Cb = yb; g.ldc = ldy; g.fp16 = fp16;
   g.bias = w.b; g.res = res; g.ldr = ldr; g.M = M; g.N = w.N; g.K = w.K; g.div = 0.f; g.act = act;
-  if (h->profile) {
+  if (h->profile == 1) {
     if (h->prof_used + 2 > h->prof_ev.size()) {
       for (int i = 0; i < 2; ++i) { cudaEvent_t e; CU(cudaEventCreate(&e)); h->prof_ev.push_back(e); }
     }
@@ -535,7 +547,7 @@ int dec_lin_skinny(xn_handle* h, const T* a16, const float* a32, long lda, const
   // selected where it measured faster in-graph than the 128-row tcgen05 tiles: few rows, narrow outputs, no LayerNorm on load
   if (!h->use_skinny || M > 64 || w.N > 2048 || ln_g || !skinny_gemm_supported(g)) return 1;
   if (a32 && (w.K % 512)) return 1;
-  if (h->profile) {
+  if (h->profile == 1) {
     if (h->prof_used + 2 > h->prof_ev.size()) {
       for (int i = 0; i < 2; ++i) { cudaEvent_t e; CU(cudaEventCreate(&e)); h->prof_ev.push_back(e); }
     }
@@ -860,6 +872,8 @@ int xn_destroy(xn_handle* h) {
   h->drop_graphs();
   if (h->gstream) { cudaStreamDestroy(h->gstream); cudaEventDestroy(h->g_in); cudaEventDestroy(h->g_out); }
   for (cudaEvent_t e : h->prof_ev) cudaEventDestroy(e);
+  for (auto& sp : h->spans) { cudaEventDestroy(sp.e0); cudaEventDestroy(sp.e1); }
+  for (cudaEvent_t e : h->span_pool) cudaEventDestroy(e);
   delete h;
   return XN_OK;
 }
@@ -1051,7 +1065,8 @@ int xn_finalize_weights(xn_handle* h, int precision) {
   if (!h) return XN_ERR_ARG;                                                           \
   if (h->precision < 0) return h->fail(XN_ERR_STATE, "weights not finalised");         \
   cudaSetDevice(h->device);                                                            \
-  cudaStream_t st = (cudaStream_t)stream;
+  cudaStream_t st = (cudaStream_t)stream;                                              \
+  h->cur_st = st;
 
 int xn_forward_swin(xn_handle* h, const float* images, int B, float* out, void* stream) {
   NEED_READY();
@@ -1218,7 +1233,12 @@ int xn_set_option(xn_handle* h, const char* name, int64_t value) {
   if (n == "use_skinny") { h->use_skinny = value; h->drop_graphs(); return XN_OK; }
   if (n == "pdl") { g_pdl_enabled = value != 0; h->drop_graphs(); return XN_OK; }
   if (n == "tc_debug") { set_tc_debug((int)value); return XN_OK; }
-  if (n == "profile") { h->profile = value; h->prof_used = 0; h->prof_flops.clear(); }
+  if (n == "tc_pair") { set_tc_pair((int)value); h->drop_graphs(); return XN_OK; }
+  if (n == "profile") {
+    h->profile = value; h->prof_used = 0; h->prof_flops.clear();
+    for (auto& sp : h->spans) { h->span_pool.push_back(sp.e0); h->span_pool.push_back(sp.e1); }
+    h->spans.clear();
+  }
   else if (n == "swin_chunk") h->swin_chunk = std::max<int64_t>(1, value);
   else if (n == "enc_chunk") h->enc_chunk = std::max<int64_t>(1, value);
   else return h->fail(XN_ERR_ARG, "unknown option '%s'", name);
@@ -1245,11 +1265,43 @@ int xn_profile_read(xn_handle* h, double* ms_total, double* flops_total, int64_t
   return XN_OK;
 }
 
+int xn_profile_kernels(xn_handle* h, char* buf, int cap) {
+  if (!h || !buf || cap <= 0) return XN_ERR_ARG;
+  cudaSetDevice(h->device);
+  CU(cudaDeviceSynchronize());
+  // aggregate by launcher name: the text of the launch expression up to its argument list
+  std::vector<std::string> names;
+  std::vector<double> ms;
+  std::vector<int64_t> cnt;
+  for (auto& sp : h->spans) {
+    std::string n(sp.label);
+    size_t b = n.find_first_not_of("( ");
+    n = n.substr(b == std::string::npos ? 0 : b);
+    n = n.substr(0, n.find('('));
+    float t = 0.f;
+    CU(cudaEventElapsedTime(&t, sp.e0, sp.e1));
+    size_t i = 0;
+    for (; i < names.size(); ++i) if (names[i] == n) break;
+    if (i == names.size()) { names.push_back(n); ms.push_back(0); cnt.push_back(0); }
+    ms[i] += t; cnt[i] += 1;
+  }
+  std::string out;
+  for (size_t i = 0; i < names.size(); ++i) {
+    char line[256];
+    snprintf(line, sizeof line, "%s\t%lld\t%.6f\n", names[i].c_str(), (long long)cnt[i], ms[i]);
+    out += line;
+  }
+  if ((int)out.size() + 1 > cap) return h->fail(XN_ERR_ARG, "profile buffer too small: need %zu", out.size() + 1);
+  memcpy(buf, out.c_str(), out.size() + 1);
+  return XN_OK;
+}
+
 // ---- single-operator entry points ------------------------------------------------------------
 #define OP_READY()                                   \
   if (!h) return XN_ERR_ARG;                         \
   cudaSetDevice(h->device);                          \
-  cudaStream_t st = (cudaStream_t)stream;
+  cudaStream_t st = (cudaStream_t)stream;            \
+  h->cur_st = st;
 
 int xn_op_layernorm(xn_handle* h, const float* x, const float* gamma, const float* beta, float* y, int rows, int C, void* stream) {
   OP_READY();

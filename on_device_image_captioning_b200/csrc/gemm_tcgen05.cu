@@ -33,10 +33,13 @@ constexpr int kEpiWarps = 16;                 // 4 per TMEM lane quarter, each d
 constexpr int kTcThreads = 64 + 32 * kEpiWarps;
 constexpr uint32_t kABytes = kBM * kBK * 2;   // 16 KB
 
-template <int BN> struct TcCfg {
-  static constexpr uint32_t kBBytes = BN * kBK * 2;
+// CTAS = 2: a CTA pair (cluster of two, the two SMs of a TPC) shares one 256 x BN tile through tcgen05.mma.cta_group::2.
+// Each CTA stages its own 128 rows of A and only HALF of the W tile, which cuts the shared-memory traffic per MMA by a
+// third (the single-CTA kernel measured 66-71 % tensor-pipe utilisation with TMA writes + MMA reads at the smem limit).
+template <int BN, int CTAS> struct TcCfg {
+  static constexpr uint32_t kBBytes = (BN / CTAS) * kBK * 2;
   static constexpr uint32_t kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (BN == 128) ? 6 : 4;
+  static constexpr int kStages = (kStageBytes <= 32768) ? 6 : 4;
   static constexpr uint32_t kAccCols = 256;                 // column stride between the two accumulators
   static constexpr uint32_t kTmemCols = 512;
   static constexpr uint32_t kStagingBytes = kEpiWarps * 32 * 16 * 4;   // per epilogue warp: 32 rows x 16 floats, XOR-swizzled 16-B slots
@@ -86,6 +89,41 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(bar)
       : "memory");
+}
+// CTA-pair variants: the transaction bytes of both CTAs' loads land on the LEADER's barrier (shared::cluster address)
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t leader_bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(leader_bar)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t local_addr, uint32_t rank) {     // shared::cluster address of a peer's smem
+  uint32_t ra;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(local_addr), "r"(rank));
+  return ra;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void umma_f16_pair(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {     // arrives on the barrier at this offset in BOTH CTAs
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"((uint16_t)3) : "memory");
 }
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
@@ -177,13 +215,14 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N, int ab_fmt) {
 }
 
 // OUT: 0 = fp32 output, 1 = 16-bit output (bf16, or fp16 when ep.fp16).  ACT: 0 none, 1 GELU(erf), 2 ReLU.
-template <int BN, int OUT, int ACT>
+template <int BN, int OUT, int ACT, int CTAS>
 __global__ void __launch_bounds__(kTcThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                const __grid_constant__ CUtensorMap tma_c, const __grid_constant__ CUtensorMap tma_r, TcEpilogue ep,
                int M, int N, int K) {
-  using Cfg = TcCfg<BN>;
+  using Cfg = TcCfg<BN, CTAS>;
   constexpr int S = Cfg::kStages;
+  constexpr int kTileM = kBM * CTAS;               // rows of one (pair) tile
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = smem_u32(smem_raw);                             // SWIZZLE_128B tiles need 1024-B alignment
   if (base & 1023u) __trap();
@@ -200,24 +239,35 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       reinterpret_cast<volatile uint32_t*>(gen_base + S * Cfg::kStageBytes + Cfg::kStagingBytes + 8 * (2 * S + 4));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m_tiles = (M + kBM - 1) / kBM, n_tiles = (N + BN - 1) / BN;
+  const int m_tiles = (M + kTileM - 1) / kTileM, n_tiles = (N + BN - 1) / BN;
   const int total_tiles = m_tiles * n_tiles;
   const int nkb = (K + kBK - 1) / kBK;
+  const uint32_t rank = CTAS == 2 ? cluster_ctarank() : 0u;           // 0 = leader (issues the MMAs)
+  const int tile0 = blockIdx.x / CTAS, tile_step = gridDim.x / CTAS;   // persistent loop over (pair) tiles
+  const int row_off = (int)rank * kBM;                                 // this CTA's rows inside the pair tile
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < S; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), kEpiWarps); }
+    for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), kEpiWarps * CTAS); }
     for (int b = 0; b < 16; ++b) mbar_init(bars + 8u * (2 * S + 5 + b), 1);     // residual-slab barriers (fp32 TMA epilogue)
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)tmem_ptr_gen)),
-                 "r"(Cfg::kTmemCols)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (CTAS == 2) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)tmem_ptr_gen)),
+                   "r"(Cfg::kTmemCols)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)tmem_ptr_gen)),
+                   "r"(Cfg::kTmemCols)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if (CTAS == 2) cluster_sync_all();      // the peer's barriers are initialised before anything signals them
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_gen;
   // barrier init and the TMEM allocation above overlap the previous kernel's tail (programmatic dependent launch)
@@ -228,26 +278,35 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int m0 = (tile / n_tiles) * kBM, n0 = (tile % n_tiles) * BN;
+      for (int tile = tile0; tile < total_tiles; tile += tile_step) {
+        const int m0 = (tile / n_tiles) * kTileM + row_off, n0 = (tile % n_tiles) * BN + (int)rank * (BN / CTAS);
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
-          if (ep.dbg & 4) { mbar_arrive(full_bar(stage)); if (++stage == S) { stage = 0; phase ^= 1u; } continue; }
-          mbar_expect_tx(full_bar(stage), Cfg::kStageBytes);
           const uint32_t sa = base + stage * Cfg::kStageBytes;
-          tma_load_2d(sa, &tma_a, kb * kBK, m0, full_bar(stage));
-          tma_load_2d(sa + kABytes, &tma_b, kb * kBK, n0, full_bar(stage));
+          if (CTAS == 2) {
+            // both CTAs' bytes are expected by, and complete on, the leader's barrier
+            const uint32_t lbar = map_to_cta(full_bar(stage), 0u);
+            if (ep.dbg & 4) { if (rank == 0) mbar_arrive(full_bar(stage)); if (++stage == S) { stage = 0; phase ^= 1u; } continue; }
+            if (rank == 0) mbar_expect_tx(full_bar(stage), 2u * Cfg::kStageBytes);
+            tma_load_2d_pair(sa, &tma_a, kb * kBK, m0, lbar);
+            tma_load_2d_pair(sa + kABytes, &tma_b, kb * kBK, n0, lbar);
+          } else {
+            if (ep.dbg & 4) { mbar_arrive(full_bar(stage)); if (++stage == S) { stage = 0; phase ^= 1u; } continue; }
+            mbar_expect_tx(full_bar(stage), Cfg::kStageBytes);
+            tma_load_2d(sa, &tma_a, kb * kBK, m0, full_bar(stage));
+            tma_load_2d(sa + kABytes, &tma_b, kb * kBK, n0, full_bar(stage));
+          }
           if (++stage == S) { stage = 0; phase ^= 1u; }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc(kBM, BN, ep.fp16 ? 0 : 1);
+    if (lane == 0 && rank == 0) {
+      const uint32_t idesc = make_idesc(kTileM, BN, ep.fp16 ? 0 : 1);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      for (int tile = tile0; tile < total_tiles; tile += tile_step, ++it) {
         const int buf = it & 1;
         const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
         mbar_wait(tempty_bar(buf), acc_phase ^ 1u);
@@ -261,13 +320,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
           const uint64_t bdesc = make_sw128_desc(sa + kABytes);
           if (!(ep.dbg & 2)) {
 #pragma unroll
-            for (int k = 0; k < kBK / kUmmaK; ++k)   // +32 bytes (>>4 = 2) per UMMA_K step inside the swizzle atom
-              umma_bf16(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (uint32_t)((kb | k) != 0));
+            for (int k = 0; k < kBK / kUmmaK; ++k) {  // +32 bytes (>>4 = 2) per UMMA_K step inside the swizzle atom
+              if (CTAS == 2) umma_f16_pair(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (uint32_t)((kb | k) != 0));
+              else umma_bf16(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (uint32_t)((kb | k) != 0));
+            }
           }
-          umma_commit(empty_bar(stage));           // frees the smem slot when these MMAs retire
+          if (CTAS == 2) umma_commit_pair(empty_bar(stage));   // frees the smem slot in both CTAs when these MMAs retire
+          else umma_commit(empty_bar(stage));
           if (++stage == S) { stage = 0; phase ^= 1u; }
         }
-        umma_commit(tfull_bar(buf));               // accumulator complete -> epilogue
+        if (CTAS == 2) umma_commit_pair(tfull_bar(buf));       // accumulator complete -> both CTAs' epilogues
+        else umma_commit(tfull_bar(buf));
       }
     }
   } else {
@@ -283,10 +346,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       const uint32_t slab_u32 = staging + (uint32_t)(warp - 2) * 2048u;
       float* bias_all = reinterpret_cast<float*>(gen_base + S * Cfg::kStageBytes + Cfg::kStagingBytes + Cfg::kBarBytes);
       const bool active = cq * 64 < BN;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      for (int tile = tile0; tile < total_tiles; tile += tile_step, ++it) {
         const int buf = it & 1;
         const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
-        const int m0 = (tile / n_tiles) * kBM, n0 = (tile % n_tiles) * BN;
+        const int m0 = (tile / n_tiles) * kTileM + row_off, n0 = (tile % n_tiles) * BN;
         const int col_base = n0 + cq * 64;
         // this warp's 64 bias values: fetched before the accumulator wait (latency hidden), published after it.  The
         // buffer is shared by the four warps of a column group (they write identical values) and double-buffered by
@@ -341,7 +404,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(tempty_bar(buf));
+        if (lane == 0) { if (CTAS == 2) mbar_arrive_cluster(map_to_cta(tempty_bar(buf), 0u)); else mbar_arrive(tempty_bar(buf)); }
       }
       if (lane == 0) tma_store_wait_all();
     } else if (OUT == 0 && ep.use_tma_store) {
@@ -358,10 +421,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       const uint32_t rbar[2] = {bars + 8u * (2 * S + 5 + 2 * (e & 7)), bars + 8u * (2 * S + 5 + 2 * (e & 7) + 1)};
       uint32_t rphase[2] = {0u, 0u};
       const bool has_res = ep.res != nullptr;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      for (int tile = tile0; tile < total_tiles; tile += tile_step, ++it) {
         const int buf = it & 1;
         const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
-        const int m0 = (tile / n_tiles) * kBM, n0 = (tile % n_tiles) * BN;
+        const int m0 = (tile / n_tiles) * kTileM + row_off, n0 = (tile % n_tiles) * BN;
         const int col_base = n0 + hf2 * (BN / 2);
         const int row0 = m0 + q * 32;
         float bpre[4] = {0.f, 0.f, 0.f, 0.f};
@@ -427,7 +490,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(tempty_bar(buf));
+        if (lane == 0) { if (CTAS == 2) mbar_arrive_cluster(map_to_cta(tempty_bar(buf), 0u)); else mbar_arrive(tempty_bar(buf)); }
       }
       if (active && lane == 0) tma_store_wait_all();
     } else {
@@ -438,10 +501,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     constexpr int kColsPerWarp = BN / (kEpiWarps / 4);
     constexpr int kSteps = kColsPerWarp / 16;      // 16-column steps per warp
     const bool ld_vec = ((ep.ldc & 3) == 0) && (!ep.res || (ep.ldr & 3) == 0);
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+    for (int tile = tile0; tile < total_tiles; tile += tile_step, ++it) {
       const int buf = it & 1;
       const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
-      const int m0 = (tile / n_tiles) * kBM, n0 = (tile % n_tiles) * BN;
+      const int m0 = (tile / n_tiles) * kTileM + row_off, n0 = (tile % n_tiles) * BN;
       const int row_base = m0 + q * 32;
       const int col_base = n0 + hf * kColsPerWarp;
       // this lane's bias values for all steps of the tile, fetched before waiting for the accumulator (the L1 is
@@ -546,17 +609,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         __syncwarp();
       }
       tc_fence_before();
-      if (lane == 0) mbar_arrive(tempty_bar(buf));
+      if (lane == 0) { if (CTAS == 2) mbar_arrive_cluster(map_to_cta(tempty_bar(buf), 0u)); else mbar_arrive(tempty_bar(buf)); }
     }
     }
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (CTAS == 2) cluster_sync_all();      // neither CTA frees TMEM or exits while the pair still uses it
+  else __syncthreads();
   if (warp == 1) {
     __syncwarp();
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(Cfg::kTmemCols) : "memory");
+    if (CTAS == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(Cfg::kTmemCols) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(Cfg::kTmemCols) : "memory");
   }
 }
 
@@ -622,17 +687,20 @@ static bool make_map32(CUtensorMap* map, const float* ptr, long rows, long cols,
             CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <int BN, int OUT, int ACT>
+int g_tc_pair = 1;          // CTA-pair (cta_group::2) tiles for problems with at least a wave of 256-row tiles
+void set_tc_pair(int v) { g_tc_pair = v; }
+
+template <int BN, int OUT, int ACT, int CTAS>
 static cudaError_t launch_tc(const TcGemmArgs& p, cudaStream_t st) {
-  using Cfg = TcCfg<BN>;
+  using Cfg = TcCfg<BN, CTAS>;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, OUT, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, OUT, ACT, CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmemBytes);
     if (e != cudaSuccess) return e;
     configured = true;
   }
   CUtensorMap ma, mb;
-  if (!make_map(&ma, p.A, p.M, p.K, p.lda, kBM, p.fp16) || !make_map(&mb, p.W, p.N, p.K, p.ldw, BN, p.fp16)) return cudaErrorInvalidValue;
+  if (!make_map(&ma, p.A, p.M, p.K, p.lda, kBM, p.fp16) || !make_map(&mb, p.W, p.N, p.K, p.ldw, BN / CTAS, p.fp16)) return cudaErrorInvalidValue;
   // 16-bit outputs without a residual leave through TMA stores: 32 x 32 boxes, 64-byte swizzle
   bool tma_c_ok = false;
   CUtensorMap mc = ma, mr = ma;
@@ -649,22 +717,43 @@ static cudaError_t launch_tc(const TcGemmArgs& p, cudaStream_t st) {
     }
   }
   TcEpilogue ep{p.Cf, p.Cb, p.ldc, p.fp16, p.bias, p.res, p.ldr, p.div != 0.f ? 1.0f / p.div : 1.0f, tma_c_ok ? 1 : 0, g_tc_debug};
-  const int tiles = ((p.M + kBM - 1) / kBM) * ((p.N + BN - 1) / BN);
-  const int grid = tiles < sm_count() ? tiles : sm_count();
-  launch_k(gemm_tc_kernel<BN, OUT, ACT>, dim3(grid), dim3(kTcThreads), Cfg::kSmemBytes, st, ma, mb, mc, mr, ep, p.M, p.N, p.K);
-  return cudaGetLastError();
+  const int tiles = ((p.M + kBM * CTAS - 1) / (kBM * CTAS)) * ((p.N + BN - 1) / BN);
+  const int slots = sm_count() / CTAS;
+  const int grid = CTAS * (tiles < slots ? tiles : slots);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kTcThreads);
+  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (CTAS == 2) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = 2;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  if (g_pdl_enabled) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = na;
+  return cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, OUT, ACT, CTAS>, ma, mb, mc, mr, ep, p.M, p.N, p.K);
 }
 
-template <int BN>
+template <int BN, int CTAS>
 static cudaError_t launch_tc_bn(const TcGemmArgs& p, cudaStream_t st) {
   const int out = p.Cf ? 0 : 1;
   switch (out * 3 + p.act) {
-    case 0: return launch_tc<BN, 0, 0>(p, st);
-    case 1: return launch_tc<BN, 0, 1>(p, st);
-    case 2: return launch_tc<BN, 0, 2>(p, st);
-    case 3: return launch_tc<BN, 1, 0>(p, st);
-    case 4: return launch_tc<BN, 1, 1>(p, st);
-    case 5: return launch_tc<BN, 1, 2>(p, st);
+    case 0: return launch_tc<BN, 0, 0, CTAS>(p, st);
+    case 1: return launch_tc<BN, 0, 1, CTAS>(p, st);
+    case 2: return launch_tc<BN, 0, 2, CTAS>(p, st);
+    case 3: return launch_tc<BN, 1, 0, CTAS>(p, st);
+    case 4: return launch_tc<BN, 1, 1, CTAS>(p, st);
+    case 5: return launch_tc<BN, 1, 2, CTAS>(p, st);
   }
   return cudaErrorInvalidValue;
 }
@@ -690,9 +779,20 @@ cudaError_t launch_gemm_tc(const TcGemmArgs& p, cudaStream_t st) {
   // a shorter serial epilogue per CTA
   const long tiles256 = (long)((p.M + kBM - 1) / kBM) * ((p.N + 255) / 256);
   if (tiles256 * 2 <= sm_count()) best = 128;
-  if (best == 256) return launch_tc_bn<256>(p, st);
-  if (best == 192) return launch_tc_bn<192>(p, st);
-  return launch_tc_bn<128>(p, st);
+  // CTA pairs where the main loop is the limit: at least one full wave of 256-row pair tiles and a long contraction.
+  // Measured at 32 images per chunk (profiles/): K = 3072 +8 %, K = 768 with 16-bit output +8 %, 8192^3 +10 %;
+  // short-K / epilogue-bound shapes (stage 1-2, GELU or fp32+residual epilogues at K <= 768) lose 5-40 % to the pair's
+  // coupled epilogues, so they stay on single-CTA tiles.
+  const long pair_tiles = (long)((p.M + 2 * kBM - 1) / (2 * kBM)) * ((p.N + best - 1) / best);
+  const bool long_k = p.K >= 1536 || (p.K >= 768 && p.Cb != nullptr && p.act != 1);
+  if (g_tc_pair && long_k && pair_tiles >= sm_count() / 2) {
+    if (best == 256) return launch_tc_bn<256, 2>(p, st);
+    if (best == 192) return launch_tc_bn<192, 2>(p, st);
+    return launch_tc_bn<128, 2>(p, st);
+  }
+  if (best == 256) return launch_tc_bn<256, 1>(p, st);
+  if (best == 192) return launch_tc_bn<192, 1>(p, st);
+  return launch_tc_bn<128, 1>(p, st);
 }
 
 }  // namespace xn

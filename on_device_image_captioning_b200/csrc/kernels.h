@@ -44,7 +44,8 @@ struct TcGemmArgs {
 };
 cudaError_t launch_gemm_tc(const TcGemmArgs& p, cudaStream_t st);
 bool tc_gemm_supported(int M, int N, int K);
-void set_tc_debug(int v);   // timing experiments (see TcEpilogue::dbg)
+void set_tc_debug(int v);
+void set_tc_pair(int v);    // 0: never use CTA-pair (cta_group::2) tiles   // timing experiments (see TcEpilogue::dbg)
 
 // ---------------------------------------------------------------- batched 16-bit GEMM (mma.sync path)
 // C[b] = scale * A[b] . op(B[b]) + res[b];  A (M x K) K-contiguous;  B (N x K) K-contiguous [b_kn=0] or (K x N) [b_kn=1]

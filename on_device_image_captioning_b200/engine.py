@@ -83,6 +83,16 @@ class Engine:
     def set_option(self, name: str, value: int):
         self._check(self.lib.xn_set_option(self._h, name.encode(), int(value)), "xn_set_option")
 
+    def profile_kernels(self):
+        """{launcher: (launches, total_ms)} of every kernel launch since set_option('profile', 2)."""
+        buf = C.create_string_buffer(1 << 16)
+        self._check(self.lib.xn_profile_kernels(self._h, buf, len(buf)), "xn_profile_kernels")
+        out = {}
+        for line in buf.value.decode().splitlines():
+            name, n, ms = line.split("\t")
+            out[name.strip()] = (int(n), float(ms))
+        return out
+
     def profile_read(self):
         """(ms, flops, launches) of the event-timed tcgen05 GEMMs since set_option('profile', 1)."""
         ms, fl, n = C.c_double(), C.c_double(), C.c_int64()

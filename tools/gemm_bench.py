@@ -9,6 +9,8 @@ from on_device_image_captioning_b200.engine import Engine
 
 def main():
     e = Engine(C.swin_tiny_test(), 0)
+    if os.environ.get("XNV2_TC_PAIR") is not None:
+        e.set_option("tc_pair", int(os.environ["XNV2_TC_PAIR"]))
     Bc = int(sys.argv[1]) if len(sys.argv) > 1 else 32
     modes = [int(m) for m in sys.argv[2].split(",")] if len(sys.argv) > 2 else [0, 1, 2, 4, 7]
     shapes = [("s1.qkv", Bc * 9216, 576, 192, 0, False), ("s1.proj", Bc * 9216, 192, 192, 0, True),
