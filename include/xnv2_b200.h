@@ -106,6 +106,12 @@ int xn_caption_host(xn_handle* h, const float* input_host, int B, int beam, int 
                     float* out_logprob_host, void* stream);
 
 /* Counters / introspection. */
+/* Image preprocessing (replaces utils/image_utils.py:5-23 preprocess_image after the decode):
+ * RGB8 (H x W x 3, interleaved) -> float32 (3 x S x S) = Normalize(ToTensor(Resize((S,S))(image))), bit-identical to
+ * Pillow's antialiased bilinear resize + torchvision's float32 tail.  `rgb` is a host pointer (rgb_on_device = 0: copied
+ * inside the call, stream-ordered) or a device pointer; `out` is device memory.  Any H, W >= 1; S = out_size. */
+int xn_preprocess_rgb8(xn_handle* h, const uint8_t* rgb, int rgb_on_device, int H, int W, float* out, int out_size, void* stream);
+
 int64_t xn_kernel_launches(const xn_handle* h);      /* kernels of this library launched so far */
 int64_t xn_workspace_bytes(const xn_handle* h);
 int xn_set_option(xn_handle* h, const char* name, int64_t value);   /* "swin_chunk", "enc_chunk", "profile" */

@@ -41,6 +41,7 @@ _SIGNATURES = {
     "xn_beam_search": (C.c_int, [_P, _P, _I, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P]),
     "xn_beam_search_from_enc": (C.c_int, [_P, _P, _I, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P]),
     "xn_caption_host": (C.c_int, [_P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P]),
+    "xn_preprocess_rgb8": (C.c_int, [_P, _P, _I, _I, _I, _P, _I, _P]),
     "xn_kernel_launches": (C.c_int64, [_P]),
     "xn_workspace_bytes": (C.c_int64, [_P]),
     "xn_set_option": (C.c_int, [_P, C.c_char_p, C.c_int64]),

@@ -117,6 +117,10 @@ struct xn_handle {
     cudaEvent_t e = span_pool.back(); span_pool.pop_back(); return e;
   }
   float* io_in = nullptr; size_t io_in_cap = 0;     // xn_caption_host staging
+  // xn_preprocess_rgb8: coefficient tables per (input size, output size), staging for the image and the first pass
+  struct ResampleTable { int in_size, out_size, ksize; int* bounds; int* kk; };
+  std::vector<ResampleTable> rtables;
+  uint8_t* pp_buf = nullptr; size_t pp_cap = 0;
   char* io_out = nullptr; size_t io_out_cap = 0;
 
   int fail(int code, const char* fmt, ...) {
@@ -868,6 +872,8 @@ int xn_destroy(xn_handle* h) {
   if (h->group_start_dev) cudaFree(h->group_start_dev);
   if (h->ws.base) cudaFree(h->ws.base);
   if (h->io_in) cudaFree(h->io_in);
+  if (h->pp_buf) cudaFree(h->pp_buf);
+  for (auto& t : h->rtables) { cudaFree(t.bounds); cudaFree(t.kk); }
   if (h->io_out) cudaFree(h->io_out);
   h->drop_graphs();
   if (h->gstream) { cudaStreamDestroy(h->gstream); cudaEventDestroy(h->g_in); cudaEventDestroy(h->g_out); }
@@ -1219,6 +1225,53 @@ int xn_caption_host(xn_handle* h, const float* input_host, int B, int beam, int 
   CU(cudaMemcpyAsync(out_len_host, d_len, (size_t)B * how_many * 4, cudaMemcpyDeviceToHost, st));
   if (out_logprob_host) CU(cudaMemcpyAsync(out_logprob_host, d_lp, n_out * 4, cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));
+  return XN_OK;
+}
+
+static int resample_table(xn_handle* h, int in_size, int out_size, const xn_handle::ResampleTable** out) {
+  for (auto& t : h->rtables)
+    if (t.in_size == in_size && t.out_size == out_size) { *out = &t; return 0; }
+  std::vector<int> bounds, kk;
+  xn_handle::ResampleTable t{in_size, out_size, 0, nullptr, nullptr};
+  resample_coeffs(in_size, out_size, bounds, kk, &t.ksize);
+  CU(cudaMalloc(&t.bounds, bounds.size() * sizeof(int)));
+  CU(cudaMalloc(&t.kk, kk.size() * sizeof(int)));
+  CU(cudaMemcpy(t.bounds, bounds.data(), bounds.size() * sizeof(int), cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(t.kk, kk.data(), kk.size() * sizeof(int), cudaMemcpyHostToDevice));
+  if (h->rtables.size() >= 64) {            // bounded cache: drop the oldest entry
+    CU(cudaDeviceSynchronize());
+    cudaFree(h->rtables.front().bounds); cudaFree(h->rtables.front().kk);
+    h->rtables.erase(h->rtables.begin());
+  }
+  h->rtables.push_back(t);
+  *out = &h->rtables.back();
+  return 0;
+}
+
+int xn_preprocess_rgb8(xn_handle* h, const uint8_t* rgb, int rgb_on_device, int H, int W, float* out, int out_size, void* stream) {
+  if (!h || !rgb || !out) return XN_ERR_ARG;
+  cudaSetDevice(h->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  h->cur_st = st;
+  if (H < 1 || W < 1 || out_size < 1 || (long)H * W > (1L << 28)) return h->fail(XN_ERR_ARG, "bad image size %d x %d -> %d", H, W, out_size);
+  const xn_handle::ResampleTable *tx = nullptr, *ty = nullptr;
+  if (int r = resample_table(h, W, out_size, &tx)) return r;
+  const int ksx = tx->ksize; const int* bx = tx->bounds; const int* kx = tx->kk;      // (the vector may reallocate below)
+  if (int r = resample_table(h, H, out_size, &ty)) return r;
+  const size_t in_bytes = (size_t)H * W * 3, tmp_bytes = (size_t)H * out_size * 3;
+  const size_t need = ((in_bytes + 255) & ~size_t(255)) + tmp_bytes;
+  if (h->pp_cap < need) {
+    if (h->pp_buf) { CU(cudaDeviceSynchronize()); cudaFree(h->pp_buf); h->pp_buf = nullptr; h->pp_cap = 0; }
+    CU(cudaMalloc(&h->pp_buf, need));
+    h->pp_cap = need;
+  }
+  const uint8_t* src = rgb;
+  uint8_t* tmp = h->pp_buf + ((in_bytes + 255) & ~size_t(255));
+  if (!rgb_on_device) {
+    CU(cudaMemcpyAsync(h->pp_buf, rgb, in_bytes, cudaMemcpyHostToDevice, st));
+    src = h->pp_buf;
+  }
+  KL(2, launch_preprocess_rgb8(src, H, W, out_size, bx, kx, ksx, ty->bounds, ty->kk, ty->ksize, tmp, out, st));
   return XN_OK;
 }
 

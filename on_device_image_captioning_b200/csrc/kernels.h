@@ -5,6 +5,7 @@
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include <stdint.h>
+#include <vector>
 
 namespace xn {
 
@@ -149,6 +150,14 @@ cudaError_t launch_cross_attn_step(const float* q, long ldq, const KvT* kv, long
                                    const int* n_valid, const int* row_len, int p, cudaStream_t st);
 cudaError_t launch_logsoftmax_topk(const float* logits, long ld, int rows, int V, int k, float* top_val,
                                    int* top_idx, float* logprob, long ldlp, int write_mode, cudaStream_t st);
+
+// ---------------------------------------------------------------- image preprocessing (Pillow-exact resize + normalise)
+// Pillow precompute_coeffs + normalize_coeffs_8bpc for the bilinear filter: bounds (out_size x {first, count}) and
+// 22-bit fixed-point weights (out_size x ksize)
+void resample_coeffs(int in_size, int out_size, std::vector<int>& bounds, std::vector<int>& kk, int* ksize_out);
+cudaError_t launch_preprocess_rgb8(const uint8_t* rgb_dev, int H, int W, int S, const int* bounds_x, const int* kk_x, int ksize_x,
+                                   const int* bounds_y, const int* kk_y, int ksize_y, uint8_t* tmp_dev, float* out_dev,
+                                   cudaStream_t st);
 
 // ---------------------------------------------------------------- beam search bookkeeping
 struct BeamBufs {

@@ -80,6 +80,10 @@ class Engine:
     def kernel_launches(self) -> int:
         return int(self.lib.xn_kernel_launches(self._h))
 
+    @property
+    def workspace_bytes(self) -> int:
+        return int(self.lib.xn_workspace_bytes(self._h))
+
     def set_option(self, name: str, value: int):
         self._check(self.lib.xn_set_option(self._h, name.encode(), int(value)), "xn_set_option")
 
@@ -166,6 +170,25 @@ class Engine:
             self._check(fn(self._h, _ptr(x), B, _int_array(enc_pads), int(beam_size), int(max_len), int(how_many),
                            int(sos_idx), int(eos_idx), _ptr(tok), _ptr(ln), _ptr(lp), self._stream()), "xn_beam_search")
         return tok, ln, lp
+
+    def preprocess_rgb8(self, images, img_size: Optional[int] = None) -> torch.Tensor:
+        """Decoded RGB8 images (list of (H, W, 3) uint8 numpy arrays / CPU or CUDA tensors, any sizes) ->
+        (B, 3, S, S) float32 on the device: Resize((S, S)) + ToTensor + Normalize of the reference's
+        utils/image_utils.py:preprocess_image, bit-identical to Pillow/torchvision (csrc/preprocess.cu)."""
+        S = int(img_size or self.cfg.img_size)
+        out = torch.empty(len(images), 3, S, S, device=self.device, dtype=torch.float32)
+        keep = []
+        with torch.cuda.device(self.device):
+            for i, im in enumerate(images):
+                t = im if isinstance(im, torch.Tensor) else torch.from_numpy(im)
+                assert t.dtype == torch.uint8 and t.dim() == 3 and t.shape[2] == 3, "expected (H, W, 3) uint8 RGB"
+                t = t.contiguous()
+                keep.append(t)
+                self._check(self.lib.xn_preprocess_rgb8(self._h, _ptr(t), int(t.is_cuda), int(t.shape[0]), int(t.shape[1]),
+                                                        _ptr(out[i]), S, self._stream()), "xn_preprocess_rgb8")
+            if any(not t.is_cuda for t in keep):
+                torch.cuda.current_stream().synchronize()      # host buffers were read asynchronously
+        return out
 
     def caption_host(self, inputs_host: torch.Tensor, sos_idx: int, eos_idx: int, beam_size: int = 3, how_many: int = 1,
                      max_len: int = 20, out: Optional[Tuple[torch.Tensor, torch.Tensor, torch.Tensor]] = None):

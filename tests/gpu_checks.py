@@ -281,4 +281,86 @@ def check_beam(name: str, precision: str = "fp32") -> List[Triple]:
     return out
 
 
+def check_preprocess() -> List[Triple]:
+    """GPU preprocessing (Pillow-exact resize + ToTensor + Normalize) vs the CPU oracle: bit-exact float32 tensors,
+    host and device inputs, down- and up-scaling, extreme aspect ratios, 1-pixel images."""
+    from oracle import preprocess_oracle as P
+    from test_preprocess_oracle import synth_image
+    e = bare_engine()
+    out = []
+    for (H, W, S) in [(50, 70, 96), (500, 333, 384), (384, 384, 384), (640, 480, 384), (100, 1000, 384), (37, 41, 48),
+                      (1200, 800, 384), (383, 385, 384), (1, 1, 16), (2, 900, 32), (2160, 3840, 384)]:
+        img = synth_image(H, W, H * 1000 + W)
+        ref = P.preprocess_rgb8(img, S)
+        y_host = e.preprocess_rgb8([img], S)[0].cpu().numpy()
+        y_dev = e.preprocess_rgb8([torch.from_numpy(img).cuda()], S)[0].cpu().numpy()
+        out.append((f"preprocess[{H}x{W}->{S}] elements differing from the oracle (host input)", float((y_host != ref).sum()), 0.0))
+        out.append((f"preprocess[{H}x{W}->{S}] elements differing from the oracle (device input)", float((y_dev != ref).sum()), 0.0))
+    imgs = [synth_image(h, w, 7 * h + w) for (h, w) in [(300, 400), (480, 640), (200, 200)]]
+    yb = e.preprocess_rgb8(imgs, 96).cpu().numpy()
+    bad = sum(int((yb[i] != P.preprocess_rgb8(im, 96)).sum()) for i, im in enumerate(imgs))
+    out.append(("preprocess batch of mixed sizes: elements differing from the oracle", float(bad), 0.0))
+    return out
+
+
+# ------------------------------------------------------------------ BASELINE.json configurations at full size
+def _tokens_list(tok, ln):
+    tok, ln = tok.cpu(), ln.cpu()
+    return [tok[b, 0, : int(ln[b, 0])].tolist() for b in range(tok.shape[0])]
+
+
+def check_config3_features_beam5(B: int = 256) -> List[Triple]:
+    """BASELINE.json configs[2]: decoder-only ExpansionNet_v2 on precomputed (144 x 1536) features, batch 256, beam 5.
+    fp32: the first images are decoded by the CPU oracle (seconds) and must match token for token where the oracle's
+    own decision margins allow a parity claim; the rest of the batch is held to batch invariance (same captions whether
+    an image is decoded inside the batch of 256 or in a batch of 8).  fp16: invariance only."""
+    from on_device_image_captioning_b200 import synth
+    from on_device_image_captioning_b200.config import features_only
+    cfg = features_only(vocab=1000, max_seq_len=24)
+    sd = synth.make_state_dict(cfg, seed=0, profile="peaky", eos_idx=7)
+    x = synth.make_features(cfg, B, seed=3)
+    out = []
+    n_or = 3
+    with torch.no_grad():
+        tr = {}
+        ref_tok, ref_lp = O.beam_search(sd, cfg, x[:n_or], [0] * n_or, 5, 7, 5, 1, 20, trace=tr)
+        ref_m = torch.minimum(torch.minimum(tr["vocab_margin"], tr["merge_margin"]), tr["final_margin"]).tolist()
+    for precision in ("fp32", "fp16"):
+        e = Engine(cfg, 0)
+        e.load_state_dict(sd, precision)
+        tok, ln, lp = e.beam_search(x, [0] * B, 5, 7, 5, 1, 20)
+        full = _tokens_list(tok, ln)
+        diff = 0
+        for b0 in range(0, B, 64):                      # a few sub-batches spread over the batch
+            t8, l8, _ = e.beam_search(x[b0:b0 + 8].contiguous(), [0] * 8, 5, 7, 5, 1, 20)
+            diff += sum(1 for i, t in enumerate(_tokens_list(t8, l8)) if t != full[b0 + i])
+        out.append((f"config3/{precision} B={B} beam 5: captions that change with the batch they are decoded in", float(diff), 0.0))
+        if precision == "fp32":
+            bad = sum(1 for i in range(n_or) if ref_m[i] > 2e-5 and full[i] != ref_tok[i][0])
+            out.append((f"config3/fp32 captions differing from the CPU oracle (first {n_or} images)", float(bad), 0.0))
+        lens = ln.cpu().flatten().tolist()
+        out.append((f"config3/{precision} caption lengths outside [2, 20]", float(sum(1 for v in lens if v < 2 or v > 20)), 0.0))
+        e.close()
+    return out
+
+
+def check_config4_batch512_chunking() -> List[Triple]:
+    """BASELINE.json configs[3] per-GPU shape: 512 images in one call (8 Swin chunks of 64, 1536 decoder rows).  The
+    batch is 8 copies of 64 distinct images, so every chunk must reproduce the captions of a plain 64-image call."""
+    e, g, cfg, sd, x, pads = engine_for("full_e2e_peaky", "fp16")
+    from on_device_image_captioning_b200 import synth
+    m = g["meta"]
+    x64 = synth.make_images(cfg, 64, seed=11, kind="mixed")
+    t64, l64, _ = e.beam_search(x64, None, m["sos"], m["eos"], 3, 1, 20)
+    base = _tokens_list(t64, l64)
+    x512 = x64.repeat(8, 1, 1, 1).contiguous()
+    t, l, _ = e.beam_search(x512, None, m["sos"], m["eos"], 3, 1, 20)
+    big = _tokens_list(t, l)
+    diff = sum(1 for i in range(512) if big[i] != base[i % 64])
+    distinct = len({tuple(c) for c in base})
+    return [("config4/fp16 B=512: captions differing from the 64-image call they repeat", float(diff), 0.0),
+            ("config4/fp16 distinct captions among the 64 images (>= 8 expected, the check is not vacuous)", float(-distinct), -8.0),
+            ("config4/fp16 workspace GiB (of 180)", e.workspace_bytes / 2 ** 30, 60.0)]
+
+
 ALL_FP32_MODEL_CASES = ["tiny_e2e_peaky", "tiny_e2e_xavier", "feat_peaky_b5", "feat_xavier_b1", "full_e2e_xavier", "full_e2e_peaky"]

@@ -139,3 +139,21 @@ def test_drop_in_classes_both_call_styles(name):
     from conftest import sub
     err = np.abs(sub(logits.cpu()).numpy() - g["dec_logits_sub"]).max()
     assert err < 5e-5, err
+
+
+def test_config3_features_batch256_beam5():
+    """BASELINE.json configs[2] at full size: oracle parity on the first images, batch invariance on the rest."""
+    import gpu_checks as G
+    _assert(G.check_config3_features_beam5(256))
+
+
+def test_config4_batch512_per_gpu():
+    """BASELINE.json configs[3] per-GPU shape: 512 images per call through the chunked Swin / 1536-row decoder."""
+    import gpu_checks as G
+    _assert(G.check_config4_batch512_chunking())
+
+
+def test_preprocess_bit_exact():
+    """GPU resize/normalise vs the Pillow-pinned oracle, bit-exact."""
+    import gpu_checks as G
+    _assert(G.check_preprocess())

@@ -20,7 +20,7 @@ def main():
             ("skinny_fp16", lambda: G.check_linear_skinny("fp16")), ("skinny_bf16", lambda: G.check_linear_skinny("bf16")),
             ("wattn_fp32", lambda: G.check_window_attention("fp32")), ("wattn_bf16", lambda: G.check_window_attention("bf16")),
             ("wattn_fp16", lambda: G.check_window_attention("fp16")),
-            ("logsoftmax_topk", G.check_logsoftmax_topk)]
+            ("logsoftmax_topk", G.check_logsoftmax_topk), ("preprocess", G.check_preprocess)]
     cases = ["tiny_e2e_peaky", "tiny_e2e_xavier", "feat_peaky_b5", "feat_xavier_b1"] + ([] if quick else ["full_e2e_xavier", "full_e2e_peaky"])
     for c in cases:
         jobs += [(f"enc:{c}", lambda c=c: G.check_encoder(c, "fp32")), (f"dec:{c}", lambda c=c: G.check_decoder(c, "fp32")),
@@ -31,6 +31,8 @@ def main():
                  (f"dec_bf16:{c}", lambda c=c: G.check_decoder(c, "bf16")), (f"beam_fp16:{c}", lambda c=c: G.check_beam(c, "fp16"))]
     jobs += [("dec_fp16:feat_peaky_b5", lambda: G.check_decoder("feat_peaky_b5", "fp16")),
              ("beam_fp16:feat_peaky_b5", lambda: G.check_beam("feat_peaky_b5", "fp16"))]
+    if not quick:
+        jobs += [("config3", G.check_config3_features_beam5), ("config4", G.check_config4_batch512_chunking)]
     results, nbad = [], 0
     for name, fn in jobs:
         if only and not any(o in name for o in only):
