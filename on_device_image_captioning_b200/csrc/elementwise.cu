@@ -285,6 +285,115 @@ __global__ void __launch_bounds__(256) patch_embed_kernel(const float* __restric
   }
 }
 
+// Patch width 4 (every Swin-L/384 call site): the four dx taps of a (channel, dy) row segment are one float4 in the
+// slab, and the filter bank is pre-arranged as wq[(c*4+dy)][e] = float4 over dx (derived once per weight load), so four
+// taps cost one LDS.128 per patch plus one per channel: 12 FMAs per shared-memory load with 6 patches x 6 channels in
+// registers (the generic kernel above issues 10 loads per 24 FMAs and re-transposes the filter bank in every CTA).
+constexpr int kPe4Patches = 6;
+
+__global__ void __launch_bounds__(256) patch_embed4_kernel(const float* __restrict__ img, const float4* __restrict__ wq,
+                                                           const float* __restrict__ bias, const float* __restrict__ g,
+                                                           const float* __restrict__ be, float* __restrict__ out,
+                                                           int Cin, int S, int E) {
+  pdl_wait();
+  pdl_trigger();
+  extern __shared__ float4 sm4[];
+  const int G = S / 4, KG = Cin * 4;            // KG (channel, dy) groups of four dx taps
+  float4* slab = sm4;                           // [KG][G]   one patch row of input pixels, a float4 per patch
+  float4* wt = slab + KG * G;                   // [KG][E]
+  const int groups = (G + kPeRows - 1) / kPeRows;
+  const int b = blockIdx.x / groups, py0 = (blockIdx.x % groups) * kPeRows;
+  for (int i = threadIdx.x; i < KG * E; i += blockDim.x) wt[i] = wq[i];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int EP = E / 32;                        // channels per lane (E % 32 == 0, E <= 256)
+  float gam[8], bet[8], bia[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int e = lane + 32 * j;
+    gam[j] = (j < EP) ? g[e] : 0.f; bet[j] = (j < EP) ? be[e] : 0.f; bia[j] = (j < EP) ? bias[e] : 0.f;
+  }
+  for (int pr = 0; pr < kPeRows && py0 + pr < G; ++pr) {
+    const int py = py0 + pr;
+    __syncthreads();
+    for (int i = threadIdx.x; i < KG * G; i += blockDim.x) {
+      const int r = i / G, px = i % G, c = r >> 2, dy = r & 3;
+      slab[i] = *reinterpret_cast<const float4*>(&img[(((long)b * Cin + c) * S + (py * 4 + dy)) * S + px * 4]);
+    }
+    __syncthreads();
+    for (int px0 = warp * kPe4Patches; px0 < G; px0 += nw * kPe4Patches) {
+      float acc[kPe4Patches][8];
+#pragma unroll
+      for (int q = 0; q < kPe4Patches; ++q)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[q][j] = bia[j];
+      for (int r = 0; r < KG; ++r) {
+        float4 v[kPe4Patches];
+#pragma unroll
+        for (int q = 0; q < kPe4Patches; ++q) v[q] = (px0 + q < G) ? slab[r * G + px0 + q] : make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4* wr = wt + r * E + lane;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (j < EP) {
+            const float4 w4 = wr[32 * j];
+#pragma unroll
+            for (int q = 0; q < kPe4Patches; ++q) {
+              // same tap order as the generic kernel: k = (c, dy, dx) ascending
+              acc[q][j] = fmaf(v[q].x, w4.x, acc[q][j]);
+              acc[q][j] = fmaf(v[q].y, w4.y, acc[q][j]);
+              acc[q][j] = fmaf(v[q].z, w4.z, acc[q][j]);
+              acc[q][j] = fmaf(v[q].w, w4.w, acc[q][j]);
+            }
+          }
+      }
+#pragma unroll
+      for (int q = 0; q < kPe4Patches; ++q) {
+        const int px = px0 + q;
+        if (px >= G) break;
+        float s = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) if (j < EP) s += acc[q][j];
+        const float mean = warp_sum(s) / (float)E;
+        float qv = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) if (j < EP) { const float dd = acc[q][j] - mean; qv += dd * dd; }
+        const float rstd = 1.0f / sqrtf(warp_sum(qv) / (float)E + kLnEps);
+        float* o = out + (((long)b * G + py) * G + px) * E;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (j < EP) o[lane + 32 * j] = (acc[q][j] - mean) * rstd * gam[j] + bet[j];
+      }
+    }
+  }
+}
+
+// (E, Cin, 4, 4) conv filter -> wq[(c*4+dy)*E + e] = (w[e][c][dy][0..3])
+__global__ void patch_filter_pack4_kernel(const float* __restrict__ w, float4* __restrict__ wq, int Cin, int E) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= Cin * 4 * E) return;
+  const int r = i / E, e = i % E;
+  wq[i] = *reinterpret_cast<const float4*>(w + ((long)e * Cin * 4 + r) * 4);
+}
+cudaError_t launch_patch_filter_pack4(const float* w, float* wq, int Cin, int E, cudaStream_t st) {
+  patch_filter_pack4_kernel<<<(Cin * 4 * E + 255) / 256, 256, 0, st>>>(w, reinterpret_cast<float4*>(wq), Cin, E);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_patch_embed4(const float* img, const float* wq, const float* b, const float* gamma, const float* beta,
+                                float* out, int B, int Cin, int S, int E, cudaStream_t st) {
+  if (E % 32 || E > 256 || S % 16) return cudaErrorInvalidValue;
+  const int G = S / 4;
+  const size_t smem = ((size_t)Cin * 4 * G + (size_t)Cin * 4 * E) * sizeof(float4);
+  static size_t configured = 0;
+  if (smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(patch_embed4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    configured = smem;
+  }
+  const int groups = (G + kPeRows - 1) / kPeRows;
+  return launch_k(patch_embed4_kernel, dim3(B * groups), dim3(256), smem, st, img, reinterpret_cast<const float4*>(wq), b, gamma, beta,
+                  out, Cin, S, E);
+}
+
 cudaError_t launch_patch_embed(const float* img, const float* w, const float* b, const float* gamma,
                                const float* beta, float* out, int B, int Cin, int S, int P, int E,
                                cudaStream_t st) {

@@ -93,6 +93,10 @@ cudaError_t launch_merge_layernorm(const float* x, const float* gamma, const flo
 cudaError_t launch_patch_embed(const float* img, const float* w, const float* b, const float* gamma,
                                const float* beta, float* out, int B, int Cin, int S, int P, int E,
                                cudaStream_t st);
+// patch width 4: filter bank pre-packed by launch_patch_filter_pack4 into float4-over-dx rows
+cudaError_t launch_patch_filter_pack4(const float* w, float* wq, int Cin, int E, cudaStream_t st);
+cudaError_t launch_patch_embed4(const float* img, const float* wq, const float* b, const float* gamma, const float* beta,
+                                float* out, int B, int Cin, int S, int E, cudaStream_t st);
 template <typename T>
 cudaError_t launch_cast(const float* x, T* y, long n, cudaStream_t st);
 
