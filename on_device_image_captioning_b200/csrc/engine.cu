@@ -995,7 +995,7 @@ int xn_finalize_weights(xn_handle* h, int precision) {
           if (to_bf16(W.qkv) || to_bf16(W.proj) || to_bf16(W.fc1) || to_bf16(W.fc2)) return XN_ERR_CUDA;
           if (!rc) {
             float* bt = nullptr;
-            CU(cudaMalloc(&bt, (size_t)532 * S.heads * sizeof(float)));
+            CU(cudaMalloc(&bt, (size_t)2 * 532 * S.heads * sizeof(float)));
             h->owned.push_back(bt);
             KL(1, launch_transpose_bias(W.rpb, bt, S.heads, 0));
             W.rpb_t = bt;
@@ -1462,10 +1462,10 @@ int xn_op_window_attention(xn_handle* h, const float* qkv, const float* bias_tab
     return XN_OK;
   }
   const size_t n = (size_t)B * H * H * C;
-  if (int r = ensure_ws(h, n * 4 * 2 + 8192 + (size_t)532 * heads * 4, st)) return r;
+  if (int r = ensure_ws(h, n * 4 * 2 + 8192 + (size_t)2 * 532 * heads * 4, st)) return r;
   bf16* qb = h->ws.get<bf16>(3 * n);
   bf16* ob = h->ws.get<bf16>(n);
-  float* bias_t = h->ws.get<float>((size_t)532 * heads);
+  float* bias_t = h->ws.get<float>((size_t)2 * 532 * heads);
   KL(1, launch_transpose_bias(bias_table, bias_t, heads, st));
   bias_table = bias_t;
   if (precision == XN_PREC_FP16) {

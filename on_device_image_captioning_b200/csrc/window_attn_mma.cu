@@ -102,7 +102,7 @@ constexpr float kLog2e = 1.4426950408889634f;
 // (token rows, label tile, bias tables) is double-buffered by item parity.
 //
 // The shift mask costs no ALU work: every token carries a 4-wide "label" row  24 * [y<6, y>=6, x<6, x>=6]  (only on
-// the axes where the window straddles the cyclic seam; [1,0] otherwise), the score accumulators start at -2*576 and
+// the axes where the window straddles the cyclic seam; [1,0] otherwise), the score accumulators start at bias - 2*576 (second copy of the table) and
 // one extra k16 MMA step adds 576 per matching axis: same region -> 0, different region -> <= -576 (x scale = -101.8,
 // where the reference adds -100; both vanish in the softmax).  The row sum comes out of the P.V MMA through an
 // all-ones B fragment, i.e. it is the sum of the rounded probabilities that are actually multiplied with V.
@@ -155,27 +155,23 @@ __global__ void __launch_bounds__(kMmaThreads, 2) window_attention_mma_kernel(co
       v.y = Mma16<T>::pack(xa, xb);
       *reinterpret_cast<uint2*>(lab_all + (mb * kWinTok + tid) * kLPitch) = v;
     }
-    const float* src = bias_l2 + (long)ip.g * kHeadsPerCta * kBiasPitch;
+    // masked windows take the second copy of the table, which already carries the -2 * 576 accumulator offset
+    const float* src = bias_l2 + ((long)(ip.masked ? heads : 0) + (long)ip.g * kHeadsPerCta) * kBiasPitch;
     for (int i = tid; i < kHeadsPerCta * (kBiasPitch / 4); i += kMmaThreads)
       cp_async16(bt_u32 + (uint32_t)((mb * kHeadsPerCta * kBiasPitch + i * 4) * sizeof(float)), src + i * 4);
   };
-  // this thread's six (token, q/k/v, 16-byte chunk) slots of a head: smem byte offset and source column, fixed for the kernel
-  uint32_t ld_dst[6];
-  int ld_tok[6], ld_col[6];
-#pragma unroll
-  for (int k = 0; k < 6; ++k) {
-    const int i = tid + k * kMmaThreads;
-    const int t = i / 12, r = i % 12, which = r >> 2, ch = r & 3;
-    ld_dst[k] = (uint32_t)((which * kMatElems + t * kRowPad + ch * 8) * sizeof(T));
-    ld_tok[k] = t;
-    ld_col[k] = which * C + ch * 8;
-  }
+  // this thread's six (token, q/k/v, 16-byte chunk) slots of a head: slot i = tid + 288 k  ->  token tid/12 + 24 k and
+  // the same (q/k/v, chunk) = tid % 12 for every k, so two registers describe all six
+  const int ld_t0 = tid / 12, ld_r = tid % 12;
+  const int ld_col = (ld_r >> 2) * C + (ld_r & 3) * 8;
+  const uint32_t ld_dst0 = (uint32_t)(((ld_r >> 2) * kMatElems + ld_t0 * kRowPad + (ld_r & 3) * 8) * sizeof(T));
   auto issue_loads = [&](int head, int mb, int bufi) {
-    const uint32_t base = stage_u32 + (uint32_t)(bufi * 3 * kMatElems * sizeof(T));
-    const T* src = qkv + head * kHeadDim;
-    const int* tk = tok_all + mb * kWinTok;
+    const uint32_t base = stage_u32 + (uint32_t)(bufi * 3 * kMatElems * sizeof(T)) + ld_dst0;
+    const T* src = qkv + head * kHeadDim + ld_col;
+    const int* tk = tok_all + mb * kWinTok + ld_t0;
 #pragma unroll
-    for (int k = 0; k < 6; ++k) cp_async16(base + ld_dst[k], src + (long)tk[ld_tok[k]] * 3 * C + ld_col[k]);
+    for (int k = 0; k < 6; ++k)
+      cp_async16(base + (uint32_t)(k * 24 * kRowPad * sizeof(T)), src + (long)tk[k * 24] * 3 * C);
     cp_async_commit();
   };
 
@@ -187,10 +183,16 @@ __global__ void __launch_bounds__(kMmaThreads, 2) window_attention_mma_kernel(co
   pdl_trigger();
   int item = blockIdx.x;
   if (item >= n_items) return;
-  ItemPos cur = decode_item(item);
-  compute_meta(cur, 0);
+  int cur_g;
+  bool cur_masked;
+  {
+    const ItemPos first = decode_item(item);
+    cur_g = first.g;
+    cur_masked = first.masked;
+    compute_meta(first, 0);
+  }
   __syncthreads();
-  issue_loads(cur.g * kHeadsPerCta, 0, 0);
+  issue_loads(cur_g * kHeadsPerCta, 0, 0);
 
   const int m0 = warp * 16;
   const int r0 = m0 + (lane >> 2), r1 = r0 + 8;
@@ -205,22 +207,25 @@ __global__ void __launch_bounds__(kMmaThreads, 2) window_attention_mma_kernel(co
     const int mb = k & 1;
     const int next_item = item + gridDim.x;
     const bool has_next = next_item < n_items;
-    ItemPos nxt = cur;
-    if (has_next) nxt = decode_item(next_item);
-    const bool masked = cur.masked;
+    const bool masked = cur_masked;
     const int* tok = tok_all + mb * kWinTok;
-    const int head0 = cur.g * kHeadsPerCta;
+    const int head0 = cur_g * kHeadsPerCta;
+    int nxt_g = 0;
+    bool nxt_masked = false;
 #pragma unroll 1
     for (int hh = 0; hh < kHeadsPerCta; ++hh, ++unit) {
       const int bufi = unit & 1;
       cp_async_wait<0>();
       __syncthreads();                              // this unit landed; everyone is done with the other buffer
       if (hh == 0 && has_next) {
+        const ItemPos nxt = decode_item(next_item);  // only the head group and the mask flag stay live across the heads
+        nxt_g = nxt.g;
+        nxt_masked = nxt.masked;
         compute_meta(nxt, mb ^ 1);                  // its cp.async traffic joins the next commit group
         if (kHeadsPerCta == 1) __syncthreads();
       }
       if (hh + 1 < kHeadsPerCta) issue_loads(head0 + hh + 1, mb, bufi ^ 1);
-      else if (has_next) issue_loads(nxt.g * kHeadsPerCta, mb ^ 1, bufi ^ 1);
+      else if (has_next) issue_loads(nxt_g * kHeadsPerCta, mb ^ 1, bufi ^ 1);
 
       const uint32_t q_base = stage_u32 + (uint32_t)(bufi * 3 * kMatElems * sizeof(T));
       const uint32_t k_base = q_base + (uint32_t)(kMatElems * sizeof(T));
@@ -253,8 +258,6 @@ __global__ void __launch_bounds__(kMmaThreads, 2) window_attention_mma_kernel(co
           const uint32_t lb_base = l_base + (uint32_t)(((lane & 7) * kLPitch + ((lane >> 3) & 1) * 8) * 2);
           static_for<18>([&](auto nt_c) {
             constexpr int nt = decltype(nt_c)::value;
-            s[nt][0] -= 2.0f * kLabelVal * kLabelVal; s[nt][1] -= 2.0f * kLabelVal * kLabelVal;
-            s[nt][2] -= 2.0f * kLabelVal * kLabelVal; s[nt][3] -= 2.0f * kLabelVal * kLabelVal;
             uint32_t lb[2];
             ldsm_x2_o<nt * 8 * kLPitch * 2>(lb, lb_base);
             Mma16<T>::mma(s[nt], la, lb[0], lb[1]);
@@ -265,13 +268,20 @@ __global__ void __launch_bounds__(kMmaThreads, 2) window_attention_mma_kernel(co
         const uint32_t qaddr = q_base + (uint32_t)((row * kRowPad + col) * 2);
         ldsm_x4_o<0>(qa[0], qaddr);
         ldsm_x4_o<32>(qa[1], qaddr);
-        const uint32_t kaddr = k_base + (uint32_t)(((lane & 7) * kRowPad + (lane >> 3) * 8) * 2);
+        // two passes over the 18 key tiles (d 0-15, then d 16-31): the two MMAs that accumulate into the same score tile
+        // are 18 instructions apart instead of back to back, so neither waits for the other's result
+        const uint32_t kaddr = k_base + (uint32_t)(((lane & 7) * kRowPad + ((lane >> 3) & 1) * 8) * 2);
         static_for<18>([&](auto nt_c) {
           constexpr int nt = decltype(nt_c)::value;
-          uint32_t kb[4];     // {b0,b1} for d 0-15 and {b0,b1} for d 16-31 of keys nt*8 .. nt*8+7
-          ldsm_x4_o<nt * 8 * kRowPad * 2>(kb, kaddr);
+          uint32_t kb[2];
+          ldsm_x2_o<nt * 8 * kRowPad * 2>(kb, kaddr);
           Mma16<T>::mma(s[nt], qa[0], kb[0], kb[1]);
-          Mma16<T>::mma(s[nt], qa[1], kb[2], kb[3]);
+        });
+        static_for<18>([&](auto nt_c) {
+          constexpr int nt = decltype(nt_c)::value;
+          uint32_t kb[2];
+          ldsm_x2_o<nt * 8 * kRowPad * 2 + 32>(kb, kaddr);
+          Mma16<T>::mma(s[nt], qa[1], kb[0], kb[1]);
         });
       }
 
@@ -330,7 +340,8 @@ __global__ void __launch_bounds__(kMmaThreads, 2) window_attention_mma_kernel(co
         *reinterpret_cast<uint4*>(out + (long)tok[row] * C + (head0 + hh) * kHeadDim + ch * 8) = v;
       }
     }
-    cur = nxt;
+    cur_g = nxt_g;
+    cur_masked = nxt_masked;
   }
 }
 
@@ -381,12 +392,15 @@ template cudaError_t launch_window_attention_mma<__half>(const __half*, const fl
 }  // namespace xn
 
 namespace xn {
-// (529, heads) relative-position table -> (heads, 532) / scale (scale = 32^-0.5), once per weight load
+// (529, heads) relative-position table -> two (heads, 532) tables / scale (scale = 32^-0.5), once per weight load:
+// plain, and shifted by the mask offset that the label MMA cancels for same-region pairs
 __global__ void transpose_bias_kernel(const float* __restrict__ t, float* __restrict__ o, int heads) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < kBiasPitch * heads) {
     const int h = i / kBiasPitch, e = i % kBiasPitch;
-    o[i] = e < kBiasN ? t[e * heads + h] * 5.656854249492380f : 0.f;     // / 32^-0.5
+    const float v = e < kBiasN ? t[e * heads + h] * 5.656854249492380f : 0.f;     // / 32^-0.5
+    o[i] = v;
+    o[i + kBiasPitch * heads] = v - 2.0f * kLabelVal * kLabelVal;                   // copy for windows on the cyclic seam
   }
 }
 cudaError_t launch_transpose_bias(const float* table, float* out, int heads, cudaStream_t st) {
