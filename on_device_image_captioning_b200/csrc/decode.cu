@@ -6,6 +6,7 @@
 // changes once computed, so each step only adds the row-block and the column of position p.
 // Beam reordering never copies that state: `anc[r][i]` names the slot (row) that holds position
 // i of row r's history, and the kernels gather through it.
+#include <algorithm>
 #include "kernels.h"
 #include "common.cuh"
 
@@ -105,7 +106,7 @@ __global__ void __launch_bounds__(256) dyn_exp_step_kernel(DecState s, int layer
                                                            T* __restrict__ ln_out, long ldn) {
   pdl_wait();
   pdl_trigger();
-  extern __shared__ float sm[];
+  extern __shared__ __align__(16) float sm[];
   const int r = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int P = s.P, np = p + 1;
   auto ln_tail = [&](float v0, float v1, float* red) {       // columns tid and tid + 256
@@ -120,22 +121,24 @@ __global__ void __launch_bounds__(256) dyn_exp_step_kernel(DecState s, int layer
     if (ln_out) ln_tail(x_in[(long)r * ldxi + tid], x_in[(long)r * ldxi + tid + 256], sm);
     return;
   }
-  int* slot = reinterpret_cast<int*>(sm);      // [P]
-  float* ck_row = sm + P;                      // [P]   c_p . K_j
-  float* ck_col = ck_row + P;                  // [P]   c_i . K_p
-  float* qkp = ck_col + P;                     // [n_exp]
-  float* af = qkp + n_exp;                     // [n_exp][P] forward weights of the new row-block (A)
-  float* bf = af + n_exp * P;                  // [n_exp][P]
-  float* ab = bf + n_exp * P;                  // [P][n_exp] backward weights (A)
-  float* bb = ab + P * n_exp;                  // [P][n_exp]
-  float* wA = bb + P * n_exp;                  // [P]
-  float* wB = wA + P;
-  float* tA = wB + P;
-  float* tB = tA + P;
-  float* sA = tB + P;                          // [n_exp]
-  float* sB = sA + n_exp;
-  float* red = sB + n_exp;                     // [32]
-  float* part = red + 32;                      // [2][P][P] partial forward-backward products
+  // carve-up in floats; P4 = P rounded up to 4 keeps the float4-read arrays (af, bf, part) 16-byte aligned
+  const int P4 = (P + 3) & ~3, E4 = (n_exp + 3) & ~3;
+  int* slot = reinterpret_cast<int*>(sm);      // [P4]
+  float* ck_row = sm + P4;                     // [P4]  c_p . K_j
+  float* ck_col = ck_row + P4;                 // [P4]  c_i . K_p
+  float* qkp = ck_col + P4;                    // [E4]
+  float* af = qkp + E4;                        // [P][n_exp] forward weights of the new row-block (A), key-major
+  float* bf = af + P4 * E4;                    // [P][n_exp]
+  float* ab = bf + P4 * E4;                    // [P][n_exp] backward weights (A)
+  float* bb = ab + P4 * E4;                    // [P][n_exp]
+  float* wA = bb + P4 * E4;                    // [P4]
+  float* wB = wA + P4;
+  float* tA = wB + P4;
+  float* tB = tA + P4;
+  float* sA = tB + P4;                         // [E4]
+  float* sB = sA + E4;
+  float* red = sB + E4;                        // [32]
+  float* part = red + 32;                      // [2][P][P] partial forward-backward products; later >= 1536 floats of mix scratch
 
   for (int i = tid; i < np; i += blockDim.x) slot[i] = (i == p || !s.anc) ? r : s.anc[(long)r * P + i];
   __syncthreads();
@@ -155,7 +158,8 @@ __global__ void __launch_bounds__(256) dyn_exp_step_kernel(DecState s, int layer
       if (t < np) { u = cp; v = crow(t) + d; }                       // c_p . K_j
       else if (t < np + p) { u = crow(t - np); v = Kp; }             // c_i . K_p
       else { u = qexp + (long)(t - np - p) * d; v = Kp; }            // q_e . K_p
-      for (int c = sub * 4; c < d; c += 32) {
+#pragma unroll 4
+      for (int c = sub * 4; c < d; c += 32) {             // unrolled: 8 independent 16-byte loads in flight per lane
         const float4 x4 = *reinterpret_cast<const float4*>(u + c);
         const float4 y4 = *reinterpret_cast<const float4*>(v + c);
         a = fmaf(x4.x, y4.x, a); a = fmaf(x4.y, y4.y, a); a = fmaf(x4.z, y4.z, a); a = fmaf(x4.w, y4.w, a);
@@ -201,8 +205,8 @@ __global__ void __launch_bounds__(256) dyn_exp_step_kernel(DecState s, int layer
       const int j = lane + 32 * c;
       if (j < np) {
         const float a = fmaxf(za[c], 0.f) / sa, b = fmaxf(-za[c], 0.f) / sb;
-        af[e * P + j] = a; bf[e * P + j] = b;
-        fw_out[e * P + j] = a; fw_out[(long)n_exp * P + e * P + j] = b;
+        af[j * n_exp + e] = a; bf[j * n_exp + e] = b;            // [key j][expansion e]: the 16 e of a key are contiguous
+        fw_out[j * n_exp + e] = a; fw_out[(long)n_exp * P + j * n_exp + e] = b;
       }
     }
   }
@@ -228,7 +232,16 @@ __global__ void __launch_bounds__(256) dyn_exp_step_kernel(DecState s, int layer
     const float* f = (i == p) ? (which ? bf : af)
                               : s.fw + (((long)layer * P + i) * s.R + slot[i]) * (2L * n_exp * P) + (which ? (long)n_exp * P : 0);
     float acc = 0.f;
-    for (int e = 0; e < n_exp; ++e) acc = fmaf(wsrc[i * n_exp + e], f[e * P + j], acc);
+    const float* fj = f + j * n_exp;
+    const float* wi = wsrc + i * n_exp;
+    if ((n_exp & 3) == 0) {
+      for (int e = 0; e < n_exp; e += 4) {
+        const float4 f4 = *reinterpret_cast<const float4*>(fj + e);
+        acc = fmaf(wi[e], f4.x, acc); acc = fmaf(wi[e + 1], f4.y, acc); acc = fmaf(wi[e + 2], f4.z, acc); acc = fmaf(wi[e + 3], f4.w, acc);
+      }
+    } else {
+      for (int e = 0; e < n_exp; ++e) acc = fmaf(wi[e], fj[e], acc);
+    }
     part[(which * P + i) * P + j] = acc;
   }
   __syncthreads();
@@ -254,25 +267,76 @@ __global__ void __launch_bounds__(256) dyn_exp_step_kernel(DecState s, int layer
   }
   __syncthreads();
 
-  // ---- phase C: the d-wide mixes
+  // ---- phase C: the d-wide mixes.  Thread t owns the four columns 4*(t % 128) .. +3 and one half of the history
+  // (t / 128): three independent 16-byte loads per position, unrolled so that a dozen are in flight; the two halves
+  // meet in shared memory.  Needs d == 512 and 256 threads; other widths take the scalar loop.
   float keep[2] = {0.f, 0.f};
-  for (int c = tid; c < d; c += blockDim.x) {
-    float oa = 0.f, ob = 0.f;
-    for (int j = 0; j < np; ++j) {
+  if (d == 512 && blockDim.x == 256) {
+    float4* mix = reinterpret_cast<float4*>(part);          // [2 (a|b)][128] partial sums of the upper half (part is free now)
+    const int c4 = (tid & 127) * 4, half = tid >> 7;
+    float4 oa = make_float4(0.f, 0.f, 0.f, 0.f), ob = oa;
+    const int j0 = half ? (np + 1) / 2 : 0, j1 = half ? np : (np + 1) / 2;
+#pragma unroll 4
+    for (int j = j0; j < j1; ++j) {
       const float* cr = crow(j);
-      const float cj = cr[c];
-      oa = fmaf(wA[j], cr[2 * d + c], oa); oa = fmaf(tA[j], cj, oa);
-      ob = fmaf(wB[j], cr[3 * d + c], ob); ob = fmaf(tB[j], cj, ob);
+      const float4 cj = *reinterpret_cast<const float4*>(cr + c4);
+      const float4 aj = *reinterpret_cast<const float4*>(cr + 2 * d + c4);
+      const float4 bj = *reinterpret_cast<const float4*>(cr + 3 * d + c4);
+      const float wa = wA[j], wb = wB[j], ta = tA[j], tb = tB[j];
+      oa.x = fmaf(wa, aj.x, oa.x); oa.x = fmaf(ta, cj.x, oa.x); ob.x = fmaf(wb, bj.x, ob.x); ob.x = fmaf(tb, cj.x, ob.x);
+      oa.y = fmaf(wa, aj.y, oa.y); oa.y = fmaf(ta, cj.y, oa.y); ob.y = fmaf(wb, bj.y, ob.y); ob.y = fmaf(tb, cj.y, ob.y);
+      oa.z = fmaf(wa, aj.z, oa.z); oa.z = fmaf(ta, cj.z, oa.z); ob.z = fmaf(wb, bj.z, ob.z); ob.z = fmaf(tb, cj.z, ob.z);
+      oa.w = fmaf(wa, aj.w, oa.w); oa.w = fmaf(ta, cj.w, oa.w); ob.w = fmaf(wb, bj.w, ob.w); ob.w = fmaf(tb, cj.w, ob.w);
     }
-    for (int e = 0; e < n_exp; ++e) {
-      const float be = bexp[(long)e * d + c];
-      oa = fmaf(sA[e], be, oa);
-      ob = fmaf(sB[e], be, ob);
+    if (half) {                                                // + the expansion-bias term, split the same way
+      for (int e = 0; e < n_exp; ++e) {
+        const float4 be = *reinterpret_cast<const float4*>(bexp + (long)e * d + c4);
+        oa.x = fmaf(sA[e], be.x, oa.x); oa.y = fmaf(sA[e], be.y, oa.y); oa.z = fmaf(sA[e], be.z, oa.z); oa.w = fmaf(sA[e], be.w, oa.w);
+        ob.x = fmaf(sB[e], be.x, ob.x); ob.y = fmaf(sB[e], be.y, ob.y); ob.z = fmaf(sB[e], be.z, ob.z); ob.w = fmaf(sB[e], be.w, ob.w);
+      }
+      mix[tid & 127] = oa;
+      mix[128 + (tid & 127)] = ob;
     }
-    const float sg = sigmoidf_(cp[4 * d + c]);
-    const float xo = x_in[(long)r * ldxi + c] + (sg * oa + (1.0f - sg) * ob);
-    x_out[(long)r * ldxo + c] = xo;
-    if (c == tid) keep[0] = xo; else if (c == tid + 256) keep[1] = xo;
+    __syncthreads();
+    float* xo_s = reinterpret_cast<float*>(mix + 256);        // the row, for the LayerNorm tail's column assignment
+    if (!half) {
+      const float4 ua = mix[tid], ub = mix[128 + tid];
+      oa.x += ua.x; oa.y += ua.y; oa.z += ua.z; oa.w += ua.w;
+      ob.x += ub.x; ob.y += ub.y; ob.z += ub.z; ob.w += ub.w;
+      const float4 sl4 = *reinterpret_cast<const float4*>(cp + 4 * d + c4);
+      const float4 xi = *reinterpret_cast<const float4*>(x_in + (long)r * ldxi + c4);
+      const float s0 = sigmoidf_(sl4.x), s1 = sigmoidf_(sl4.y), s2 = sigmoidf_(sl4.z), s3 = sigmoidf_(sl4.w);
+      float4 xo;
+      xo.x = xi.x + (s0 * oa.x + (1.0f - s0) * ob.x);
+      xo.y = xi.y + (s1 * oa.y + (1.0f - s1) * ob.y);
+      xo.z = xi.z + (s2 * oa.z + (1.0f - s2) * ob.z);
+      xo.w = xi.w + (s3 * oa.w + (1.0f - s3) * ob.w);
+      *reinterpret_cast<float4*>(x_out + (long)r * ldxo + c4) = xo;
+      *reinterpret_cast<float4*>(xo_s + c4) = xo;
+    }
+    if (ln_out) {
+      __syncthreads();
+      keep[0] = xo_s[tid]; keep[1] = xo_s[tid + 256];
+    }
+  } else {
+    for (int c = tid; c < d; c += blockDim.x) {
+      float oa = 0.f, ob = 0.f;
+      for (int j = 0; j < np; ++j) {
+        const float* cr = crow(j);
+        const float cj = cr[c];
+        oa = fmaf(wA[j], cr[2 * d + c], oa); oa = fmaf(tA[j], cj, oa);
+        ob = fmaf(wB[j], cr[3 * d + c], ob); ob = fmaf(tB[j], cj, ob);
+      }
+      for (int e = 0; e < n_exp; ++e) {
+        const float be = bexp[(long)e * d + c];
+        oa = fmaf(sA[e], be, oa);
+        ob = fmaf(sB[e], be, ob);
+      }
+      const float sg = sigmoidf_(cp[4 * d + c]);
+      const float xo = x_in[(long)r * ldxi + c] + (sg * oa + (1.0f - sg) * ob);
+      x_out[(long)r * ldxo + c] = xo;
+      if (c == tid) keep[0] = xo; else if (c == tid + 256) keep[1] = xo;
+    }
   }
   if (ln_out) ln_tail(keep[0], keep[1], red);
 }
@@ -283,7 +347,8 @@ cudaError_t launch_dyn_exp_step(const DecState& s, int layer, int p, const float
                                 const float* ln_g, const float* ln_b, T* ln_out, long ldn, cudaStream_t st) {
   if (s.P > 128 || (d & 3) || n_exp > 64) return cudaErrorInvalidValue;
   if (ln_out && d != 512) return cudaErrorInvalidValue;
-  const size_t smem = (size_t)(s.P * 7 + n_exp * 3 + 4 * n_exp * s.P + 32 + 2 * s.P * s.P) * sizeof(float);
+  const size_t P4 = (s.P + 3) & ~3, E4 = (n_exp + 3) & ~3;
+  const size_t smem = (P4 * 7 + E4 * 3 + 4 * P4 * E4 + 32 + std::max<size_t>(2 * (size_t)s.P * s.P, 1536)) * sizeof(float);
   if (smem > 48 * 1024) {
     static size_t configured = 0;
     if (smem > configured) {
