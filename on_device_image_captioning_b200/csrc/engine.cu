@@ -187,8 +187,9 @@ int lin_f32(xn_handle* h, const float* x, long ldx, const LinW& w, const float* 
   return 0;
 }
 int lin_tc(xn_handle* h, const void* x, long ldx, const LinW& w, const float* res, long ldr, float* yf, void* yb,
-           long ldy, int M, int act, int fp16, cudaStream_t st) {
+           long ldy, int M, int act, int fp16, cudaStream_t st, int w_static = 1) {
   TcGemmArgs g{};
+  g.w_static = w_static;
   g.A = x; g.lda = ldx; g.W = w.wb; g.ldw = w.K; g.Cf = yf; g.Cb = yb; g.ldc = ldy; g.fp16 = fp16;
   g.bias = w.b; g.res = res; g.ldr = ldr; g.M = M; g.N = w.N; g.K = w.K; g.div = 0.f; g.act = act;
   if (h->profile == 1) {
@@ -1403,11 +1404,11 @@ int xn_op_linear(xn_handle* h, const float* x, const float* w, const float* bias
   if (h->op_out16) {            // exercise the 16-bit-output epilogue, then widen for the caller
     if (h->ws.off + (size_t)M * N * 2 + 512 > h->ws.cap) return h->fail(XN_ERR_STATE, "op_out16: workspace too small");
     bf16* y16 = h->ws.get<bf16>((size_t)M * N);
-    if (int r = lin_tc(h, xb, K, l, residual, N, nullptr, y16, N, M, act, fp16, st)) return r;
+    if (int r = lin_tc(h, xb, K, l, residual, N, nullptr, y16, N, M, act, fp16, st, 0)) return r;
     KL(1, launch_widen_16(y16, y, (long)M * N, fp16, st));
     return XN_OK;
   }
-  return lin_tc(h, xb, K, l, residual, N, y, nullptr, N, M, act, fp16, st);
+  return lin_tc(h, xb, K, l, residual, N, y, nullptr, N, M, act, fp16, st, 0);
 }
 
 int xn_op_linear_skinny(xn_handle* h, const float* x, const float* gamma, const float* beta, const float* w, const float* bias,

@@ -56,6 +56,7 @@ struct TcEpilogue {
   const float* bias;
   const float* res; long ldr;
   float scale;  // accumulator multiplier (1 / div); a multiply, never a speculated division
+  int w_static;        // weight tiles may be loaded before the dependency wait
   int use_tma_store;   // 16-bit output without residual: write through TMA (needs ldc % 8 == 0)
   int dbg;     // timing experiments only: 1 = skip the epilogue's global traffic, 2 = skip MMA issue, 4 = skip TMA loads
 };
@@ -247,6 +248,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   const int row_off = (int)rank * kBM;                                 // this CTA's rows inside the pair tile
 
   if (threadIdx.x == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tma_a)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tma_b)) : "memory");
+    if (ep.use_tma_store) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tma_c)) : "memory");
     for (int s = 0; s < S; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), kEpiWarps * CTAS); }
     for (int b = 0; b < 16; ++b) mbar_init(bars + 8u * (2 * S + 5 + b), 1);     // residual-slab barriers (fp32 TMA epilogue)
@@ -270,7 +274,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_gen;
-  // barrier init and the TMEM allocation above overlap the previous kernel's tail (programmatic dependent launch)
+  // Barrier init and the TMEM allocation above overlap the previous kernel's tail (programmatic dependent launch).
+  // The weight operand does not depend on the previous kernel either: the single-CTA producer streams the W tiles of
+  // its first pipeline stages BEFORE the dependency wait and adds the A tiles after it, so a latency-bound decoder-step
+  // GEMM starts its MMAs one L2 round trip after the previous kernel has drained.
+  int pre_stages = 0;
+  if (CTAS == 1 && ep.w_static && warp == 0 && lane == 0 && tile0 < total_tiles && !(ep.dbg & 4)) {
+    pre_stages = nkb < S ? nkb : S;
+    const int n0 = (tile0 % n_tiles) * BN;
+    for (int kb = 0; kb < pre_stages; ++kb) {
+      mbar_expect_tx(full_bar(kb), Cfg::kStageBytes);
+      tma_load_2d(base + kb * Cfg::kStageBytes + kABytes, &tma_b, kb * kBK, n0, full_bar(kb));
+    }
+  }
   pdl_wait();
   pdl_trigger();
 
@@ -292,9 +308,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             tma_load_2d_pair(sa + kABytes, &tma_b, kb * kBK, n0, lbar);
           } else {
             if (ep.dbg & 4) { mbar_arrive(full_bar(stage)); if (++stage == S) { stage = 0; phase ^= 1u; } continue; }
-            mbar_expect_tx(full_bar(stage), Cfg::kStageBytes);
-            tma_load_2d(sa, &tma_a, kb * kBK, m0, full_bar(stage));
-            tma_load_2d(sa + kABytes, &tma_b, kb * kBK, n0, full_bar(stage));
+            if (pre_stages > 0) {                       // W tile and byte count of this stage were issued before the wait
+              --pre_stages;
+              tma_load_2d(sa, &tma_a, kb * kBK, m0, full_bar(stage));
+            } else {
+              mbar_expect_tx(full_bar(stage), Cfg::kStageBytes);
+              tma_load_2d(sa, &tma_a, kb * kBK, m0, full_bar(stage));
+              tma_load_2d(sa + kABytes, &tma_b, kb * kBK, n0, full_bar(stage));
+            }
           }
           if (++stage == S) { stage = 0; phase ^= 1u; }
         }
@@ -716,7 +737,7 @@ static cudaError_t launch_tc(const TcGemmArgs& p, cudaStream_t st) {
       if (p.res && !make_map32(&mr, p.res, p.M, p.N, p.ldr)) return cudaErrorInvalidValue;
     }
   }
-  TcEpilogue ep{p.Cf, p.Cb, p.ldc, p.fp16, p.bias, p.res, p.ldr, p.div != 0.f ? 1.0f / p.div : 1.0f, tma_c_ok ? 1 : 0, g_tc_debug};
+  TcEpilogue ep{p.Cf, p.Cb, p.ldc, p.fp16, p.bias, p.res, p.ldr, p.div != 0.f ? 1.0f / p.div : 1.0f, p.w_static, tma_c_ok ? 1 : 0, g_tc_debug};
   const int tiles = ((p.M + kBM * CTAS - 1) / (kBM * CTAS)) * ((p.N + BN - 1) / BN);
   const int slots = sm_count() / CTAS;
   const int grid = CTAS * (tiles < slots ? tiles : slots);
@@ -792,6 +813,8 @@ cudaError_t launch_gemm_tc(const TcGemmArgs& p, cudaStream_t st) {
   }
   if (best == 256) return launch_tc_bn<256, 1>(p, st);
   if (best == 192) return launch_tc_bn<192, 1>(p, st);
+  // very few tiles (decoder-step projections onto d_model): 64-wide tiles double the CTAs that share the operand stream
+  if ((long)((p.M + kBM - 1) / kBM) * ((p.N + 127) / 128) * 8 <= sm_count()) return launch_tc_bn<64, 1>(p, st);
   return launch_tc_bn<128, 1>(p, st);
 }
 

@@ -42,6 +42,8 @@ struct TcGemmArgs {
   int M, N, K;
   float div;
   int act;
+  int w_static;                      // W was written before the previous kernel started (model weights): its tiles may
+                                     // be fetched ahead of the programmatic-dependent-launch wait
 };
 cudaError_t launch_gemm_tc(const TcGemmArgs& p, cudaStream_t st);
 bool tc_gemm_supported(int M, int N, int K);
