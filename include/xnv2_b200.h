@@ -106,6 +106,14 @@ int xn_caption_host(xn_handle* h, const float* input_host, int B, int beam, int 
                     float* out_logprob_host, void* stream);
 
 /* Counters / introspection. */
+/* Ensemble beam search (replaces EsembleCaptioningModel.forward(mode="beam_search"),
+ * legacy_models/ensemble_captioning_model.py:19-241, built at test.py:334): up to 8 handles on one device with the same
+ * vocabulary and input geometry decode in lock step; the step distribution is log(mean_m softmax(logits_m)), the
+ * search itself (EOS rules, beam^2 merge, length bookkeeping) is xn_beam_search's.  'max' branch only. */
+int xn_ensemble_beam_search(xn_handle* const* handles, int n_models, const float* input, int B, const int32_t* enc_pads_host,
+                            int beam, int max_len, int how_many, int sos_idx, int eos_idx, int32_t* out_tokens,
+                            int32_t* out_len, float* out_logprob, void* stream);
+
 /* Image preprocessing (replaces utils/image_utils.py:5-23 preprocess_image after the decode):
  * RGB8 (H x W x 3, interleaved) -> float32 (3 x S x S) = Normalize(ToTensor(Resize((S,S))(image))), bit-identical to
  * Pillow's antialiased bilinear resize + torchvision's float32 tail.  `rgb` is a host pointer (rgb_on_device = 0: copied

@@ -40,6 +40,7 @@ _SIGNATURES = {
     "xn_forward_dec": (C.c_int, [_P, _P, _I, _P, _P, _I, _P, _I, _P, _P]),
     "xn_beam_search": (C.c_int, [_P, _P, _I, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P]),
     "xn_beam_search_from_enc": (C.c_int, [_P, _P, _I, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P]),
+    "xn_ensemble_beam_search": (C.c_int, [C.POINTER(_P), _I, _P, _I, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P]),
     "xn_caption_host": (C.c_int, [_P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P]),
     "xn_preprocess_rgb8": (C.c_int, [_P, _P, _I, _I, _I, _P, _I, _P]),
     "xn_kernel_launches": (C.c_int64, [_P]),

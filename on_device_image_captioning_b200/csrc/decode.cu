@@ -769,19 +769,23 @@ __global__ void __launch_bounds__(256) logsoftmax_topk_reg_kernel(const float* _
   float lmax = -INFINITY;
 #pragma unroll
   for (int j = 0; j < kLsVec; ++j) lmax = fmaxf(lmax, fmaxf(fmaxf(v[j][0], v[j][1]), fmaxf(v[j][2], v[j][3])));
-  const float mx = block_max(lmax, red);
-  float ls = 0.f;
+  const bool raw = (write_mode & 2) != 0;            // input already holds log-probabilities (ensemble path): top-k only
+  float mx = 0.f, lse = 0.f;
+  if (!raw) {
+    mx = block_max(lmax, red);
+    float ls = 0.f;
 #pragma unroll
-  for (int j = 0; j < kLsVec; ++j)
+    for (int j = 0; j < kLsVec; ++j)
 #pragma unroll
-    for (int e = 0; e < 4; ++e) ls += expf(v[j][e] - mx);            // exp(-inf) = 0 for the padding slots
-  const float lse = logf(block_sum(ls, red));
+      for (int e = 0; e < 4; ++e) ls += expf(v[j][e] - mx);            // exp(-inf) = 0 for the padding slots
+    lse = logf(block_sum(ls, red));
+  }
 #pragma unroll
   for (int j = 0; j < kLsVec; ++j) {
 #pragma unroll
-    for (int e = 0; e < 4; ++e) v[j][e] = (v[j][e] - mx) - lse;
+    for (int e = 0; e < 4; ++e) if (!raw) v[j][e] = (v[j][e] - mx) - lse;
     const int i = (j * 256 + tid) * 4;
-    if (write_mode == 1) {
+    if (write_mode & 1) {
 #pragma unroll
       for (int e = 0; e < 4; ++e)
         if (i + e < V) logprob[(long)r * ldlp + i + e] = v[j][e];
@@ -825,9 +829,43 @@ __global__ void __launch_bounds__(256) logsoftmax_topk_reg_kernel(const float* _
   }
 }
 
+// Ensemble step distribution (reference legacy_models/ensemble_captioning_model.py:55-84):
+//   lp = log( mean_m softmax(logits_m) ),  softmax_m = exp(x - max_m) / sum_m,  mean = (p_0 + p_1 + ...) / n in model order.
+// One CTA per row; each model's row is read twice from L2 (statistics, then the combination).
+__global__ void __launch_bounds__(256) ensemble_logprob_kernel(EnsembleLogits in, long ld, int V, float* __restrict__ out, long ldo) {
+  pdl_wait();
+  pdl_trigger();
+  __shared__ float red[32];
+  __shared__ float s_mx[kMaxEnsemble], s_inv[kMaxEnsemble];
+  const int r = blockIdx.x, tid = threadIdx.x;
+  for (int m = 0; m < in.n; ++m) {
+    const float* x = in.p[m] + (long)r * ld;
+    float lmax = -INFINITY;
+    for (int i = tid; i < V; i += 256) lmax = fmaxf(lmax, x[i]);
+    const float mx = block_max(lmax, red);
+    float ls = 0.f;
+    for (int i = tid; i < V; i += 256) ls += expf(x[i] - mx);
+    const float sum = block_sum(ls, red);
+    if (tid == 0) { s_mx[m] = mx; s_inv[m] = sum; }
+  }
+  __syncthreads();
+  const float nf = (float)in.n;
+  for (int i = tid; i < V; i += 256) {
+    float acc = 0.f;
+    for (int m = 0; m < in.n; ++m) acc += expf(in.p[m][(long)r * ld + i] - s_mx[m]) / s_inv[m];
+    out[(long)r * ldo + i] = logf(acc / nf);
+  }
+}
+cudaError_t launch_ensemble_logprob(const EnsembleLogits& in, long ld, int rows, int V, float* out, long ldo, cudaStream_t st) {
+  if (in.n < 1 || in.n > kMaxEnsemble) return cudaErrorInvalidValue;
+  return launch_k(ensemble_logprob_kernel, dim3(rows), dim3(256), 0, st, in, ld, V, out, ldo);
+}
+
 cudaError_t launch_logsoftmax_topk(const float* logits, long ld, int rows, int V, int k, float* top_val, int* top_idx,
                                    float* logprob, long ldlp, int write_mode, cudaStream_t st) {
   if (k > kMaxTopK) return cudaErrorInvalidValue;
+  if ((write_mode & 2) && !(V <= 256 * 4 * kLsVec && (ld & 3) == 0 && (reinterpret_cast<uintptr_t>(logits) & 15) == 0))
+    return cudaErrorInvalidValue;            // top-k over ready log-probabilities is served by the register-resident kernel only
   if (V <= 256 * 4 * kLsVec && (ld & 3) == 0 && (reinterpret_cast<uintptr_t>(logits) & 15) == 0) {
     launch_k(logsoftmax_topk_reg_kernel, dim3(rows), dim3(256), 0, st, logits, ld, V, k, top_val, top_idx, logprob, ldlp, write_mode);
     return cudaGetLastError();

@@ -1216,6 +1216,122 @@ int xn_beam_search(xn_handle* h, const float* input, int B, const int32_t* enc_p
   return r;
 }
 
+int xn_ensemble_beam_search(xn_handle* const* hs, int n_models, const float* input, int B, const int32_t* enc_pads_host, int beam,
+                            int max_len, int how_many, int sos_idx, int eos_idx, int32_t* out_tokens, int32_t* out_len,
+                            float* out_logprob, void* stream) {
+  if (!hs || n_models < 1 || n_models > kMaxEnsemble || !hs[0]) return XN_ERR_ARG;
+  xn_handle* h = hs[0];                       // owner of the shared beam state; errors are reported on it
+  cudaStream_t st = (cudaStream_t)stream;
+  const xn_config& c = h->cfg;
+  for (int m = 0; m < n_models; ++m) {
+    if (!hs[m] || hs[m]->precision < 0) return h->fail(XN_ERR_STATE, "ensemble model %d: weights not finalised", m);
+    const xn_config& cm = hs[m]->cfg;
+    if (hs[m]->device != h->device || cm.vocab != c.vocab || cm.has_swin != c.has_swin || cm.enc_len != c.enc_len ||
+        cm.max_seq_len < max_len || (c.has_swin ? (cm.img_size != c.img_size || cm.in_chans != c.in_chans) : cm.feat_dim != c.feat_dim))
+      return h->fail(XN_ERR_ARG, "ensemble model %d is not compatible with model 0 (device, vocabulary or input geometry)", m);
+  }
+  cudaSetDevice(h->device);
+  if (how_many > beam) return h->fail(XN_ERR_ARG, "requested output per sequence must be lower than beam width");
+  bool pads = false;
+  if (enc_pads_host)
+    for (int i = 0; i < B; ++i) pads |= enc_pads_host[i] != 0;
+  if (c.has_swin && pads) return h->fail(XN_ERR_ARG, "End to End case have no padding");
+  const int R = B * beam;
+  std::vector<size_t> keep(n_models);
+  std::vector<float*> enc_out(n_models);
+  std::vector<DecBufs> D(n_models);
+  std::vector<float*> logits(n_models);
+  std::vector<int*> nv(n_models, nullptr);
+  BeamPlan P;
+  int rc = 0;
+  // ---- per model: arena, encoder (image / feature input is shared), decoder buffers
+  for (int m = 0; m < n_models && !rc; ++m) {
+    xn_handle* hm = hs[m];
+    hm->cur_st = st;
+    const xn_config& cm = hm->cfg;
+    const int Bs = (int)std::min<int64_t>(B, hm->swin_chunk), Be = (int)std::min<int64_t>(B, hm->enc_chunk);
+    const size_t enc_bytes = ((size_t)B * cm.enc_len * cm.d_model * 4 + 4095) & ~size_t(255);
+    const size_t feat_bytes = cm.has_swin ? (((size_t)B * cm.enc_len * cm.feat_dim * 4 + 4095) & ~size_t(255)) : 0;
+    const size_t scratch = std::max(std::max(cm.has_swin ? swin_ws_bytes(cm, Bs, hm->precision) : 0, enc_ws_bytes(cm, Be)),
+                                    beam_ws_bytes(cm, B, beam, max_len) + (size_t)B * beam * cm.vocab * 4 + 4096);   // + combined log-probs
+    if ((rc = ensure_ws(hm, scratch + enc_bytes + feat_bytes, st))) { if (hm != h) h->err = hm->err; break; }
+    keep[m] = hm->ws.cap;
+    char* top = hm->ws.base + (keep[m] & ~size_t(255));
+    enc_out[m] = reinterpret_cast<float*>(top - enc_bytes);
+    float* fb = reinterpret_cast<float*>(top - enc_bytes - feat_bytes);
+    hm->ws.cap = (size_t)((top - enc_bytes - feat_bytes) - hm->ws.base);
+    if (cm.has_swin) {
+      rc = swin_forward(hm, input, B, fb, st);
+      if (!rc) rc = enc_body(hm, fb, B, nullptr, enc_out[m], st);
+    } else {
+      rc = enc_body(hm, input, B, enc_pads_host, enc_out[m], st);
+    }
+    if (rc) { if (hm != h) h->err = hm->err; break; }
+    if (m == 0) {
+      rc = beam_plan(hm, P, B, cm.has_swin ? nullptr : enc_pads_host, beam, max_len, how_many, st, true);
+      D[0] = P.D; logits[0] = P.logits; nv[0] = P.nv;
+    } else {
+      hm->ws.reset();
+      dec_alloc(hm, D[m], R, max_len, B);
+      logits[m] = hm->ws.get<float>((size_t)R * cm.vocab);
+      if (!cm.has_swin && pads) {
+        std::vector<int> v(B);
+        for (int i = 0; i < B; ++i) v[i] = cm.enc_len - enc_pads_host[i];
+        rc = upload_ints(hm, v, &nv[m], st);
+      }
+      if (!rc && hm->ws.overflow) rc = hm->fail(XN_ERR_STATE, "workspace overflow in ensemble model %d", m);
+    }
+    if (rc && hm != h) h->err = hm->err;
+  }
+  // ---- the search of beam_run with the step distribution log(mean_m softmax(logits_m))  (ensemble_captioning_model.py:55-84)
+  float* lp_comb = nullptr;
+  if (!rc) {
+    lp_comb = h->ws.get<float>((size_t)R * c.vocab);
+    if (h->ws.overflow) rc = h->fail(XN_ERR_STATE, "workspace overflow (ensemble log-probabilities)");
+  }
+  auto step_all = [&](int p, const int* tok32, int src_anc) -> int {
+    EnsembleLogits el{};
+    el.n = n_models;
+    for (int m = 0; m < n_models; ++m) {
+      xn_handle* hm = hs[m];
+      D[m].s.anc = P.bb.anc[src_anc];
+      if (int r = dec_step(hm, D[m], p, nullptr, tok32, max_len, beam, nv[m], nullptr, logits[m], hm->cfg.vocab, st)) { if (hm != h) h->err = hm->err; return r; }
+      el.p[m] = logits[m];
+    }
+    KL(1, launch_ensemble_logprob(el, c.vocab, R, c.vocab, lp_comb, c.vocab, st));
+    KL(1, launch_logsoftmax_topk(lp_comb, c.vocab, R, c.vocab, beam, P.topv, P.topi, nullptr, 0, 2, st));
+    return 0;
+  };
+  if (!rc) {
+    for (int m = 0; m < n_models && !rc; ++m) {
+      rc = dec_project(hs[m], D[m], enc_out[m], B, st);
+      if (rc && hs[m] != h) h->err = hs[m]->err;
+    }
+  }
+  if (!rc) {
+    auto run = [&]() -> int {
+      KL(1, launch_beam_init(P.bb, B, beam, max_len, sos_idx, st));
+      int src = 0;
+      if (int r = step_all(0, P.bb.tokens[0], 0)) return r;
+      KL(1, launch_beam_first(P.bb, P.topv, P.topi, B, beam, max_len, eos_idx, st));
+      int t_final = 2;
+      for (int t = 2; t < max_len; ++t) {
+        if (int r = step_all(t - 1, P.bb.tokens[src], src)) return r;
+        KL(1, launch_beam_step(P.bb, src, P.topv, P.topi, B, beam, max_len, t, eos_idx, st));
+        src ^= 1;
+        t_final = t + 1;
+      }
+      KL(1, launch_beam_finalize(P.bb, src, B, beam, max_len, t_final, how_many, P.r_tok, P.r_len, P.r_lp, st));
+      return 0;
+    };
+    rc = run();
+  }
+  if (!rc) rc = beam_copy_out(h, P, B, max_len, how_many, out_tokens, out_len, out_logprob, st);
+  for (int m = 0; m < n_models; ++m)
+    if (keep[m]) hs[m]->ws.cap = keep[m];
+  return rc;
+}
+
 int xn_caption_host(xn_handle* h, const float* input_host, int B, int beam, int max_len, int how_many, int sos_idx,
                     int eos_idx, int32_t* out_tokens_host, int32_t* out_len_host, float* out_logprob_host, void* stream) {
   NEED_READY();

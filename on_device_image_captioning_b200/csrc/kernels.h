@@ -154,6 +154,11 @@ template <typename KvT, typename OutT>
 cudaError_t launch_cross_attn_step(const float* q, long ldq, const KvT* kv, long ldkv, int k_off, int v_off,
                                    OutT* out, long ldo, int R, int rows_per_image, int n_keys, int heads, int dk,
                                    const int* n_valid, const int* row_len, int p, cudaStream_t st);
+// ensemble of up to kMaxEnsemble models: out = log(mean_m softmax(logits_m)) per row
+constexpr int kMaxEnsemble = 8;
+struct EnsembleLogits { const float* p[kMaxEnsemble]; int n; };
+cudaError_t launch_ensemble_logprob(const EnsembleLogits& in, long ld, int rows, int V, float* out, long ldo, cudaStream_t st);
+// write_mode bit 0: also store the log-probabilities; bit 1: the input already holds log-probabilities (top-k only)
 cudaError_t launch_logsoftmax_topk(const float* logits, long ld, int rows, int V, int k, float* top_val,
                                    int* top_idx, float* logprob, long ldlp, int write_mode, cudaStream_t st);
 

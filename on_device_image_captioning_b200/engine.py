@@ -190,6 +190,23 @@ class Engine:
                 torch.cuda.current_stream().synchronize()      # host buffers were read asynchronously
         return out
 
+    @staticmethod
+    def ensemble_beam_search(engines: Sequence["Engine"], enc_input: torch.Tensor, enc_pads: Optional[Sequence[int]], sos_idx: int,
+                             eos_idx: int, beam_size: int = 3, how_many: int = 1, max_len: int = 20):
+        """Beam search over an ensemble (reference EsembleCaptioningModel, test.py:334): same returns as beam_search."""
+        e0 = engines[0]
+        x = e0._f32(enc_input)
+        B = x.shape[0]
+        tok = torch.empty(B, how_many, max_len, device=e0.device, dtype=torch.int32)
+        ln = torch.empty(B, how_many, device=e0.device, dtype=torch.int32)
+        lp = torch.empty(B, how_many, max_len, device=e0.device, dtype=torch.float32)
+        arr = (C.c_void_p * len(engines))(*[e._h.value for e in engines])
+        with torch.cuda.device(e0.device):
+            e0._check(e0.lib.xn_ensemble_beam_search(arr, len(engines), _ptr(x), B, _int_array(enc_pads), int(beam_size), int(max_len),
+                                                     int(how_many), int(sos_idx), int(eos_idx), _ptr(tok), _ptr(ln), _ptr(lp),
+                                                     e0._stream()), "xn_ensemble_beam_search")
+        return tok, ln, lp
+
     def caption_host(self, inputs_host: torch.Tensor, sos_idx: int, eos_idx: int, beam_size: int = 3, how_many: int = 1,
                      max_len: int = 20, out: Optional[Tuple[torch.Tensor, torch.Tensor, torch.Tensor]] = None):
         """Host buffers in, host buffers out (H2D/D2H inside the call).  `inputs_host` should be pinned."""

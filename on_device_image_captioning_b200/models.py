@@ -3,6 +3,7 @@
   End_ExpansionNet_v2          reference models/End_ExpansionNet_v2.py:10-209 (legacy_models/...:10-138)
   ExpansionNet_v2              reference models/ExpansionNet_v2.py:9-156
   E2E_ExpansionNet_Captioner   reference models/End_ExpansionNet_v2.py:311-354 + models/captioning_model.py:40-110
+  EsembleCaptioningModel       reference models/ensemble_captioning_model.py:6-241 (built at test.py:334)
 
 They are ``nn.Module``s holding the parameters under exactly the reference's names and
 shapes, so ``load_state_dict(torch.load(p)["model_state_dict"])``,
@@ -255,3 +256,43 @@ class E2E_ExpansionNet_Captioner:
     def forward_dec(self, cross_input, enc_input_num_pads, dec_input, dec_input_num_pads):
         return self.model.forward_dec(cross_input, enc_input_num_pads, dec_input, dec_input_num_pads,
                                       apply_log_softmax=self.apply_log_softmax)
+
+
+class EsembleCaptioningModel(nn.Module):
+    """reference models/ensemble_captioning_model.py:6-241 (the spelling is the reference's): beam search over several
+    models whose per-step distribution is log(mean_m softmax(logits_m)).  ``models_list`` holds drop-in models of this
+    package on one CUDA device; the search runs in the CUDA library (xn_ensemble_beam_search)."""
+
+    def __init__(self, models_list, rank):
+        super().__init__()
+        self.num_models = len(models_list)
+        self.models_list = models_list
+        self.rank = rank
+        self.dummy_linear = nn.Linear(1, 1)          # the reference keeps one so that DDP(model) has a parameter
+        for model in self.models_list:
+            model.eval()
+
+    def forward(self, enc_x, dec_x=None, enc_x_num_pads=[0], dec_x_num_pads=[0], apply_log_softmax=False,
+                mode="beam_search", **kwargs):
+        assert mode == "beam_search", "this class supports only beam search."
+        return self.ensemble_beam_search(enc_x, enc_x_num_pads, sos_idx=kwargs.get("sos_idx", -999),
+                                         eos_idx=kwargs.get("eos_idx", -999), beam_size=kwargs.get("beam_size", 5),
+                                         how_many_outputs=kwargs.get("how_many_outputs", 1),
+                                         max_seq_len=kwargs.get("beam_max_seq_len", 20),
+                                         sample_or_max=kwargs.get("sample_or_max", "max"))
+
+    def forward_enc(self, enc_input, enc_input_num_pads):
+        return [m.forward_enc(enc_input, enc_input_num_pads) for m in self.models_list]
+
+    def ensemble_beam_search(self, enc_input, enc_input_num_pads, sos_idx, eos_idx, beam_size=3, how_many_outputs=1,
+                             max_seq_len=20, sample_or_max="max"):
+        assert (how_many_outputs <= beam_size), "requested output per sequence must be lower than beam width"
+        assert (sample_or_max == "max" or sample_or_max == "sample"), "argument must be chosen between 'max' and 'sample'"
+        if sample_or_max != "max":
+            raise NotImplementedError("sample_or_max='sample' is not on the accelerated path")
+        B = enc_input.size(0)
+        m0 = self.models_list[0]
+        pads = None if m0.cfg.has_swin else _as_list(enc_input_num_pads, B)
+        tok, ln, lp = Engine.ensemble_beam_search([m.engine() for m in self.models_list], enc_input, pads, sos_idx, eos_idx,
+                                                  beam_size, how_many_outputs, max_seq_len)
+        return unpack_beam_results(tok, ln, lp)

@@ -344,14 +344,29 @@ def beam_search(sd: SD, cfg, enc_input: torch.Tensor, enc_pads: Sequence[int], s
     B = enc_input.shape[0]
     k = beam_size
     enc_pads = list(enc_pads)
-    cross = forward_enc(sd, cfg, enc_input, enc_pads)
+    # ``sd`` may be a list of state dicts: the ensemble of legacy_models/ensemble_captioning_model.py (test.py:334), whose
+    # step distribution is log(mean_m softmax(logits_m)) (:55-84) fed to exactly the same search (:86-241)
+    sds = list(sd) if isinstance(sd, (list, tuple)) else None
+    if sds is not None:
+        crosses = [forward_enc(s_, cfg, enc_input, enc_pads) for s_ in sds]
+        cross = crosses[0]
+        def _fd(_sd, _cfg, cross_in, pads_in, tok_in, dpads_in, _apply):
+            rep = cross_in.shape[0] // crosses[0].shape[0]
+            ps = []
+            for s_, c_ in zip(sds, crosses):
+                c_in = c_ if rep == 1 else c_.unsqueeze(1).expand(B, rep, c_.shape[1], c_.shape[2]).reshape(B * rep, c_.shape[1], c_.shape[2])
+                ps.append(torch.softmax(forward_dec(s_, _cfg, c_in, pads_in, tok_in, dpads_in, False).unsqueeze(0), dim=-1))
+            return torch.cat(ps, dim=0).mean(dim=0).log()
+    else:
+        cross = forward_enc(sd, cfg, enc_input, enc_pads)
+        _fd = forward_dec
     n, d = cross.shape[1], cross.shape[2]
     vocab_margin = torch.full((B,), float("inf"))
     merge_margin = torch.full((B,), float("inf"))
 
     # step 0 (:120-140): one row per image holding [SOS]
     tok0 = torch.full((B, 1), sos_idx, dtype=torch.long)
-    lp = forward_dec(sd, cfg, cross, enc_pads, tok0, [0] * B, True)          # (B,1,V)
+    lp = _fd(sd, cfg, cross, enc_pads, tok0, [0] * B, True)          # (B,1,V)
     top_v, top_i = torch.topk(lp, k=k, sorted=True)
     if lp.shape[-1] > k:
         mv = torch.topk(lp, k=k + 1, sorted=True).values
@@ -367,7 +382,7 @@ def beam_search(sd: SD, cfg, enc_input: torch.Tensor, enc_pads: Sequence[int], s
 
     for t in range(2, max_seq_len):                                          # :155
         flat = classes.reshape(B * k, t)
-        lp = forward_dec(sd, cfg, cross_rep, enc_pads_rep, flat, (t - num_elem).tolist(), True)[:, t - 1, :]
+        lp = _fd(sd, cfg, cross_rep, enc_pads_rep, flat, (t - num_elem).tolist(), True)[:, t - 1, :]
         tv, ti = torch.topk(lp, k=k, sorted=True)                              # :163
         if lp.shape[-1] > k:
             mv = torch.topk(lp, k=k + 1, sorted=True).values

@@ -303,6 +303,90 @@ def check_preprocess() -> List[Triple]:
     return out
 
 
+def check_feature_extraction() -> List[Triple]:
+    """the bulk extractor (decode -> GPU preprocess -> Swin, batched) writes, per image id, exactly the
+    features a one-image call produces, in the reference's "<img_id>_features" layout."""
+    import tempfile
+    from on_device_image_captioning_b200 import features as F
+    from test_preprocess_oracle import synth_image
+    e, g, cfg, sd, x, pads = engine_for("tiny_e2e_peaky", "fp32")
+    imgs = [synth_image(h, w, 3 * h + w) for (h, w) in [(120, 160), (96, 96), (300, 200), (64, 500), (97, 101)]]
+    ids = [11, 22, 33, 44, 55]
+    with tempfile.TemporaryDirectory() as td:
+        path = td + "/precalc_features.hdf5"
+        F.extract_features(e, imgs, ids, path, batch_size=2)
+        bad = 0.0
+        for im, i in zip(imgs, ids):
+            one = e.forward_swin(e.preprocess_rgb8([im]))[0].cpu().numpy()
+            got = F.read_features(path, i)
+            bad += float(got.shape != (cfg.enc_len, cfg.feat_dim)) + float(np.abs(got - one).max() > 1e-6)
+    return [("feature extractor: images whose stored features differ from the single-image call", bad, 0.0)]
+
+
+def check_ensemble() -> List[Triple]:
+    """ensemble beam search (two tiny end-to-end models) vs the fixture produced by the reference's
+    EsembleCaptioningModel: bit-exact captions in fp32, through the raw engine call and the drop-in class."""
+    from conftest import load_golden
+    from on_device_image_captioning_b200 import synth
+    from on_device_image_captioning_b200.models import End_ExpansionNet_v2, EsembleCaptioningModel
+    g = load_golden("ens_tiny_e2e")
+    m = g["meta"]
+    cfg = XNConfig(**m["cfg"])
+    sds = [synth.make_state_dict(cfg, seed=sd_, profile=m["profile"], eos_idx=m["eos"]) for sd_ in m["seeds"]]
+    x = synth.make_images(cfg, m["B"], seed=1, kind=m["kind"])
+    out = []
+    margin = np.minimum(np.minimum(g["vocab_margin"], g["merge_margin"]), g["final_margin"])
+    for precision in ("fp32", "fp16"):
+        engs = []
+        for sd_ in sds:
+            e = Engine(cfg, 0)
+            e.load_state_dict(sd_, precision)
+            engs.append(e)
+        tok, ln, lp = Engine.ensemble_beam_search(engs, x, None, m["sos"], m["eos"], m["beam"], m["how_many"], m["max_len"])
+        toks, lps = unpack_beam_results(tok, ln, lp)
+        bad = 0
+        for b in range(m["B"]):
+            if margin[b] <= 2e-5:
+                continue
+            for j in range(m["how_many"]):
+                bad += toks[b][j] != g["beam_tokens"][b, j, : int(g["beam_len"][b, j])].tolist()
+        if precision == "fp32":
+            out.append(("ensemble/fp32 caption token sequences differing from the reference class", float(bad), 0.0))
+            ref_lp = torch.from_numpy(g["beam_logprobs"])
+            if bad == 0 and tuple(lps.shape) == tuple(ref_lp.shape):
+                out.append(("ensemble/fp32 caption log-probs vs reference rel-max", rel_max(lps, ref_lp), 1e-5))
+        else:
+            out.append((f"ensemble/{precision} caption token sequences differing from the reference (informational)", float(bad), float("inf")))
+        for e in engs:
+            e.close()
+    # drop-in class surface (test.py:334 style)
+    import argparse
+    words = [f"w{i}" for i in range(cfg.vocab)]
+    da = argparse.Namespace(enc=0.0, dec=0.0, enc_input=0.0, dec_input=0.0, other=0.0)
+    models = []
+    for sd_ in sds:
+        mm = End_ExpansionNet_v2(swin_img_size=cfg.img_size, swin_patch_size=cfg.patch_size, swin_in_chans=cfg.in_chans,
+                                 swin_embed_dim=cfg.embed_dim, swin_depths=list(cfg.depths), swin_num_heads=list(cfg.swin_heads),
+                                 swin_window_size=cfg.window_size, swin_mlp_ratio=cfg.mlp_ratio, swin_qkv_bias=True, swin_qk_scale=None,
+                                 swin_drop_rate=0.0, swin_attn_drop_rate=0.0, swin_drop_path_rate=0.0, swin_norm_layer=torch.nn.LayerNorm,
+                                 swin_ape=False, swin_patch_norm=True, swin_use_checkpoint=False, final_swin_dim=cfg.feat_dim,
+                                 d_model=cfg.d_model, N_enc=cfg.n_enc, N_dec=cfg.n_dec, ff=cfg.ff, num_heads=cfg.num_heads,
+                                 num_exp_enc_list=list(cfg.num_exp_enc_list), num_exp_dec=cfg.num_exp_dec,
+                                 output_word2idx={w: i for i, w in enumerate(words)}, output_idx2word=words,
+                                 max_seq_len=cfg.max_seq_len, drop_args=da, rank=0, precision="fp32")
+        mm.load_state_dict(sd_)
+        models.append(mm.to(0).eval())
+    ens = EsembleCaptioningModel(models, 0)
+    with torch.no_grad():
+        pred, plp = ens(enc_x=x.cuda(), enc_x_num_pads=[0] * m["B"], mode="beam_search", beam_size=m["beam"],
+                        how_many_outputs=m["how_many"], beam_max_seq_len=m["max_len"], sample_or_max="max",
+                        sos_idx=m["sos"], eos_idx=m["eos"])
+    bad = sum(pred[b][j] != g["beam_tokens"][b, j, : int(g["beam_len"][b, j])].tolist()
+              for b in range(m["B"]) if margin[b] > 2e-5 for j in range(m["how_many"]))
+    out.append(("ensemble drop-in class: caption token sequences differing from the reference class", float(bad), 0.0))
+    return out
+
+
 # ------------------------------------------------------------------ BASELINE.json configurations at full size
 def _tokens_list(tok, ln):
     tok, ln = tok.cpu(), ln.cpu()

@@ -157,3 +157,15 @@ def test_preprocess_bit_exact():
     """GPU resize/normalise vs the Pillow-pinned oracle, bit-exact."""
     import gpu_checks as G
     _assert(G.check_preprocess())
+
+
+def test_feature_extraction_layout():
+    """bulk Swin feature extraction in the reference's storage layout."""
+    import gpu_checks as G
+    _assert(G.check_feature_extraction())
+
+
+def test_ensemble_beam_search():
+    """ensemble beam search vs the reference's EsembleCaptioningModel fixture."""
+    import gpu_checks as G
+    _assert(G.check_ensemble())

@@ -62,3 +62,23 @@ def test_geometry_tables():
     assert int(idx[0, 0]) == 11 * 23 + 11 and int(idx[0, 143]) == 0 and int(idx[143, 0]) == 528
     lab = O.shift_region_labels(24, 12, 6)
     assert lab[0, 0] == 0 and lab[12, 0] == 3 and lab[18, 18] == 8 and lab[0, 17] == 1
+
+
+def test_oracle_ensemble_equals_reference_class():
+    """the oracle's ensemble search vs the fixture made by the reference's EsembleCaptioningModel."""
+    import torch
+    from conftest import load_golden
+    from on_device_image_captioning_b200 import synth
+    from on_device_image_captioning_b200.config import XNConfig
+    from oracle import xnv2_oracle as O
+    g = load_golden("ens_tiny_e2e")
+    m = g["meta"]
+    cfg = XNConfig(**m["cfg"])
+    sds = [synth.make_state_dict(cfg, seed=s, profile=m["profile"], eos_idx=m["eos"]) for s in m["seeds"]]
+    x = synth.make_images(cfg, m["B"], seed=1, kind=m["kind"])
+    with torch.no_grad():
+        tok, lp = O.beam_search(sds, cfg, x, [0] * m["B"], m["sos"], m["eos"], m["beam"], m["how_many"], m["max_len"])
+    for b in range(m["B"]):
+        for j in range(m["how_many"]):
+            assert tok[b][j] == g["beam_tokens"][b, j, : g["beam_len"][b, j]].tolist()
+    assert float((lp - torch.from_numpy(g["beam_logprobs"])).abs().max()) <= 1e-6

@@ -51,3 +51,18 @@ def test_detokenisation_mirror():
     assert L.batch_tokens2description([[[4, 1, 2, 5, -1]], [[4, 2, 3, -1, -1]]], [[4], [3]], vocab, 4, 5) == ["A dog.", "Dog runs."]
     with pytest.raises(IndexError):
         L.tokens2description([4, 5], vocab, 4, 5)
+
+
+def test_feature_store_layout(tmp_path):
+    """"<img_id>_features" -> (144, 1536) float32, the keys coco_dataloader.py:446 reads."""
+    from on_device_image_captioning_b200 import features as F
+    path = str(tmp_path / "precalc_features.hdf5")
+    w = F.FeatureWriter(path)
+    rng = np.random.default_rng(0)
+    a, b = rng.standard_normal((144, 1536)).astype(np.float32), rng.standard_normal((144, 1536)).astype(np.float32)
+    w.add(391895, a)
+    w.add("42", b)
+    w.close()
+    assert F.feature_key(391895) == "391895_features"
+    assert np.array_equal(F.read_features(path, 391895), a) and np.array_equal(F.read_features(path, 42), b)
+    assert F.read_features(path, 42).dtype == np.float32

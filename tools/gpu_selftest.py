@@ -20,7 +20,8 @@ def main():
             ("skinny_fp16", lambda: G.check_linear_skinny("fp16")), ("skinny_bf16", lambda: G.check_linear_skinny("bf16")),
             ("wattn_fp32", lambda: G.check_window_attention("fp32")), ("wattn_bf16", lambda: G.check_window_attention("bf16")),
             ("wattn_fp16", lambda: G.check_window_attention("fp16")),
-            ("logsoftmax_topk", G.check_logsoftmax_topk), ("preprocess", G.check_preprocess)]
+            ("logsoftmax_topk", G.check_logsoftmax_topk), ("preprocess", G.check_preprocess),
+            ("features", G.check_feature_extraction), ("ensemble", G.check_ensemble)]
     cases = ["tiny_e2e_peaky", "tiny_e2e_xavier", "feat_peaky_b5", "feat_xavier_b1"] + ([] if quick else ["full_e2e_xavier", "full_e2e_peaky"])
     for c in cases:
         jobs += [(f"enc:{c}", lambda c=c: G.check_encoder(c, "fp32")), (f"dec:{c}", lambda c=c: G.check_decoder(c, "fp32")),
