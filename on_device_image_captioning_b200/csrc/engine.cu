@@ -96,7 +96,13 @@ struct xn_handle {
   std::vector<CachedGraph> graphs;
   int64_t use_graph = 1;
   int64_t op_out16 = 0;
-  int64_t use_skinny = 1;            // decoder-step linears on gemm_skinny.cu when rows <= 512 (16-bit modes)
+  int64_t use_skinny = 1;
+  // the decoder step is a chain of latency-bound kernels that fills a fraction of the machine: the batch is decoded as
+  // up to kMaxDecodeGroups independent image groups on concurrent streams (parallel branches of the captured graph)
+  static constexpr int kMaxDecodeGroups = 8;
+  int64_t decode_groups = 0;          // 0 = automatic (by batch size)
+  cudaStream_t dstream[kMaxDecodeGroups] = {};
+  cudaEvent_t d_fork = nullptr, d_join[kMaxDecodeGroups] = {};            // decoder-step linears on gemm_skinny.cu when rows <= 512 (16-bit modes)
   cudaStream_t gstream = nullptr;      // graphs are captured/replayed here (the caller's stream may be the legacy
   cudaEvent_t g_in = nullptr, g_out = nullptr;   // default stream, which cannot be captured); ordered with events
   void drop_graphs() {
@@ -887,6 +893,11 @@ int xn_destroy(xn_handle* h) {
   if (h->io_out) cudaFree(h->io_out);
   h->drop_graphs();
   if (h->gstream) { cudaStreamDestroy(h->gstream); cudaEventDestroy(h->g_in); cudaEventDestroy(h->g_out); }
+  for (int g = 0; g < xn_handle::kMaxDecodeGroups; ++g) {
+    if (h->dstream[g]) cudaStreamDestroy(h->dstream[g]);
+    if (h->d_join[g]) cudaEventDestroy(h->d_join[g]);
+  }
+  if (h->d_fork) cudaEventDestroy(h->d_fork);
   for (cudaEvent_t e : h->prof_ev) cudaEventDestroy(e);
   for (auto& sp : h->spans) { cudaEventDestroy(sp.e0); cudaEventDestroy(sp.e1); }
   for (cudaEvent_t e : h->span_pool) cudaEventDestroy(e);
@@ -1175,7 +1186,7 @@ int xn_beam_search(xn_handle* h, const float* input, int B, const int32_t* enc_p
   const size_t enc_bytes = ((size_t)B * c.enc_len * c.d_model * 4 + 4095) & ~size_t(255);
   const size_t feat_bytes = c.has_swin ? (((size_t)B * c.enc_len * c.feat_dim * 4 + 4095) & ~size_t(255)) : 0;
   size_t scratch = std::max(std::max(c.has_swin ? swin_ws_bytes(c, Bs, h->precision) : 0, enc_ws_bytes(c, Be)),
-                            beam_ws_bytes(c, B, beam, max_len));
+                            beam_ws_bytes(c, B, beam, max_len) + xn_handle::kMaxDecodeGroups * (size_t)(96 * 256));   // + per-group rounding
   if (int r = ensure_ws(h, scratch + enc_bytes + feat_bytes, st)) return r;
   const size_t keep = h->ws.cap;
   char* top = h->ws.base + (keep & ~size_t(255));
@@ -1195,12 +1206,28 @@ int xn_beam_search(xn_handle* h, const float* input, int B, const int32_t* enc_p
     h->ws.cap = keep;
     return r;
   }
-  BeamPlan P;
-  // the beam buffers are carved from the bottom of the arena, where the Swin / encoder chunks also put their scratch:
-  // both run strictly before the decoder, in stream order
-  if (!r) r = beam_plan(h, P, B, nullptr, beam, max_len, how_many, st, true);
+  // The beam buffers are carved from the bottom of the arena, where the Swin / encoder chunks also put their scratch:
+  // both run strictly before the decoder, in stream order.  The images are decoded in G independent groups (beam search
+  // never mixes images), each with its own buffers, on G streams forked from the encoder's stream.
+  int G = (int)h->decode_groups;
+  // measured at batch 64 (profiles/r2_quick_time_decode_groups.txt): 2 groups -0.6 ms, 4 groups +0.9 ms, 8 groups +3.8 ms --
+  // beyond two chains the graph's kernel-node dispatch rate, not kernel latency, is the limit
+  if (G <= 0) G = B >= 32 ? 2 : 1;
+  if (h->profile) G = 1;                                    // per-launch event timing wants one stream
+  G = std::max(1, std::min(G, std::min(B, (int)xn_handle::kMaxDecodeGroups)));
+  std::vector<BeamPlan> P(G);
+  std::vector<int> g0(G + 1, 0);
+  for (int g = 0; g < G; ++g) g0[g + 1] = g0[g] + B / G + (g < B % G ? 1 : 0);
+  for (int g = 0; g < G && !r; ++g) r = beam_plan(h, P[g], g0[g + 1] - g0[g], nullptr, beam, max_len, how_many, st, g == 0);
+  if (!r && G > 1 && !h->d_fork) {
+    CU(cudaEventCreateWithFlags(&h->d_fork, cudaEventDisableTiming));
+    for (int g = 0; g < xn_handle::kMaxDecodeGroups; ++g) {
+      CU(cudaStreamCreateWithFlags(&h->dstream[g], cudaStreamNonBlocking));
+      CU(cudaEventCreateWithFlags(&h->d_join[g], cudaEventDisableTiming));
+    }
+  }
   if (!r) {
-    const xn_handle::GraphKey key{1, input, B, beam, max_len, how_many, sos_idx, eos_idx, h->ws.base, keep};
+    const xn_handle::GraphKey key{1 + 16 * G, input, B, beam, max_len, how_many, sos_idx, eos_idx, h->ws.base, keep};
     r = run_graphed(h, key, true, st, [&](cudaStream_t s2) -> int {
       if (c.has_swin) {
         if (int rr = swin_forward(h, input, B, fb, s2)) return rr;
@@ -1208,10 +1235,24 @@ int xn_beam_search(xn_handle* h, const float* input, int B, const int32_t* enc_p
       } else {
         if (int rr = enc_body(h, input, B, nullptr, enc_out, s2)) return rr;
       }
-      return beam_run(h, P, enc_out, B, beam, max_len, how_many, sos_idx, eos_idx, s2);
+      if (G == 1) return beam_run(h, P[0], enc_out, B, beam, max_len, how_many, sos_idx, eos_idx, s2);
+      CU(cudaEventRecord(h->d_fork, s2));
+      int rr = 0;
+      for (int g = 0; g < G; ++g) {                         // issue order interleaves nothing: each group is one chain
+        cudaStream_t sg = h->dstream[g];
+        CU(cudaStreamWaitEvent(sg, h->d_fork, 0));
+        if (!rr) rr = beam_run(h, P[g], enc_out + (size_t)g0[g] * c.enc_len * c.d_model, g0[g + 1] - g0[g], beam, max_len, how_many,
+                               sos_idx, eos_idx, sg);
+        CU(cudaEventRecord(h->d_join[g], sg));
+        CU(cudaStreamWaitEvent(s2, h->d_join[g], 0));       // always joined, also on error: a capture must not end forked
+      }
+      return rr;
     });
   }
-  if (!r) r = beam_copy_out(h, P, B, max_len, how_many, out_tokens, out_len, out_logprob, st);
+  for (int g = 0; g < G && !r; ++g) {
+    const size_t o = (size_t)g0[g] * how_many;
+    r = beam_copy_out(h, P[g], g0[g + 1] - g0[g], max_len, how_many, out_tokens + o * max_len, out_len + o, out_logprob + o * max_len, st);
+  }
   h->ws.cap = keep;
   return r;
 }
@@ -1419,6 +1460,7 @@ int xn_set_option(xn_handle* h, const char* name, int64_t value) {
   if (n == "use_graph") { h->use_graph = value; h->drop_graphs(); return XN_OK; }
   if (n == "op_out16") { h->op_out16 = value; return XN_OK; }
   if (n == "use_skinny") { h->use_skinny = value; h->drop_graphs(); return XN_OK; }
+  if (n == "decode_groups") { h->decode_groups = std::max<int64_t>(0, std::min<int64_t>(value, xn_handle::kMaxDecodeGroups)); h->drop_graphs(); return XN_OK; }
   if (n == "pdl") { g_pdl_enabled = value != 0; h->drop_graphs(); return XN_OK; }
   if (n == "tc_debug") { set_tc_debug((int)value); return XN_OK; }
   if (n == "tc_pair") { set_tc_pair((int)value); h->drop_graphs(); return XN_OK; }
