@@ -508,6 +508,7 @@ struct DecBufs {
   DecState s;
   float *x0, *ycat, *q, *pre;
   void *xn, *att, *hid, *yn, *ycat16, *kv;      // fp32 in the parity mode, 16-bit operands otherwise
+  void* e16;                                    // 16-bit copy of the encoder output (operand of the cross K/V projection)
   int R, P;
 };
 
@@ -543,6 +544,8 @@ int dec_alloc(xn_handle* h, DecBufs& D, int R, int P, int n_images) {
   D.yn = h->ws.get<float>((size_t)R * d);
   D.ycat16 = h->ws.get<float>((size_t)R * d * c.n_dec);
   D.kv = h->ws.get<float>((size_t)n_images * c.enc_len * c.n_dec * 2 * d);
+  // planned here, not taken from the arena at run time: the Swin / encoder chunks reset the arena offset in between
+  D.e16 = h->ws.get<float>(((size_t)n_images * c.enc_len * d + 1) / 2);
   return 0;
 }
 
@@ -589,8 +592,7 @@ int dec_project_kv(xn_handle* h, DecBufs& D, const float* enc_out, int n_images,
   const int d = c.d_model, M = n_images * c.enc_len;
   if (std::is_same<T, float>::value)
     return lin_f32(h, enc_out, d, h->kv_all, nullptr, 0, reinterpret_cast<float*>(D.kv), h->kv_all.N, M, 0, st);
-  T* e16 = h->ws.get<T>((size_t)M * d);
-  WS_CHECK();
+  T* e16 = reinterpret_cast<T*>(D.e16);
   KL(1, launch_cast<T>(enc_out, e16, (long)M * d, st));
   return lin_tc(h, e16, d, h->kv_all, nullptr, 0, nullptr, D.kv, h->kv_all.N, M, 0, std::is_same<T, f16>::value, st);
 }
