@@ -300,7 +300,8 @@ def run_ours(args):
             lat[name + "_p50_ms"] = statistics.median(ts)
         # ---- CPU baseline: bounded sample on this host's cores
         threads = os.cpu_count() or 1
-        cpu_v, cpu_dt = CpuOracle(threads).captions_per_sec(2) if not args.no_cpu else (None, None)
+        # reported at N = 1 only (the other ranks' processes share these host cores at N > 1)
+        cpu_v, cpu_dt = CpuOracle(threads).captions_per_sec(2) if (not args.no_cpu and world == 1) else (None, None)
         clocks = sampler.summary()
         whole_tflops = value / world * FLOPS_PER_CAPTION / 1e12
         line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
