@@ -219,8 +219,8 @@ def run_ours(args):
     # ---- end to end: host buffers in, host tokens out, through the C-ABI call a user makes
     outs = (torch.empty(B, 1, MAX_LEN, dtype=torch.int32).pin_memory(), torch.empty(B, 1, dtype=torch.int32).pin_memory(),
             torch.empty(B, 1, MAX_LEN, dtype=torch.float32).pin_memory())
-    for _ in range(3):
-        eng.caption_host(host[0], SOS, EOS, BEAM, 1, MAX_LEN, out=outs)
+    for i in range(3 * n_rot):                          # every rotating host buffer is seen three times: eager, capture, replay
+        eng.caption_host(host[i % n_rot], SOS, EOS, BEAM, 1, MAX_LEN, out=outs)
     barrier()
     e0.record()
     for i in range(args.steps):

@@ -102,7 +102,12 @@ struct xn_handle {
   static constexpr int kMaxDecodeGroups = 8;
   int64_t decode_groups = 0;          // 0 = automatic (by batch size)
   cudaStream_t dstream[kMaxDecodeGroups] = {};
-  cudaEvent_t d_fork = nullptr, d_join[kMaxDecodeGroups] = {};            // decoder-step linears on gemm_skinny.cu when rows <= 512 (16-bit modes)
+  cudaEvent_t d_fork = nullptr, d_join[kMaxDecodeGroups] = {};
+  // xn_caption_host with pinned input: the images are copied chunk by chunk on a side stream inside the call's graph, so
+  // the copy of Swin chunk c+1 overlaps the compute of chunk c
+  static constexpr int kMaxCopyChunks = 64;
+  cudaStream_t cstream = nullptr;
+  cudaEvent_t c_fork = nullptr, c_ev[kMaxCopyChunks] = {};            // decoder-step linears on gemm_skinny.cu when rows <= 512 (16-bit modes)
   cudaStream_t gstream = nullptr;      // graphs are captured/replayed here (the caller's stream may be the legacy
   cudaEvent_t g_in = nullptr, g_out = nullptr;   // default stream, which cannot be captured); ordered with events
   void drop_graphs() {
@@ -311,14 +316,35 @@ int swin_forward_chunk(xn_handle* h, const float* img, int Bc, float* out, cudaS
   return 0;
 }
 
-int swin_forward(xn_handle* h, const float* img, int B, float* out, cudaStream_t st) {
+// host_img != nullptr: `img` is device staging that has NOT been filled yet; every chunk's images are copied from the
+// (pinned) host buffer on the handle's copy stream, all copies queued up front, and chunk c waits only for its own copy.
+int swin_forward(xn_handle* h, const float* img, int B, float* out, cudaStream_t st, const float* host_img = nullptr, int host_chunk = 0) {
   const xn_config& c = h->cfg;
   const SwinStageW& Sl = h->stages.back();
   const size_t img_elems = (size_t)c.in_chans * c.img_size * c.img_size;
   const size_t out_elems = (size_t)Sl.H * Sl.H * Sl.C;
-  const int chunk = (int)std::max<int64_t>(1, h->swin_chunk);
-  for (int b0 = 0; b0 < B; b0 += chunk) {
+  int chunk = (int)std::max<int64_t>(1, h->swin_chunk);
+  if (host_img && host_chunk > 0) chunk = std::min(chunk, host_chunk);
+  const int n_chunks = (B + chunk - 1) / chunk;
+  if (host_img) {
+    if (n_chunks > xn_handle::kMaxCopyChunks) return h->fail(XN_ERR_ARG, "too many copy chunks (%d)", n_chunks);
+    if (!h->cstream) {
+      CU(cudaStreamCreateWithFlags(&h->cstream, cudaStreamNonBlocking));
+      CU(cudaEventCreateWithFlags(&h->c_fork, cudaEventDisableTiming));
+    }
+    CU(cudaEventRecord(h->c_fork, st));
+    CU(cudaStreamWaitEvent(h->cstream, h->c_fork, 0));
+    for (int ci = 0; ci < n_chunks; ++ci) {
+      const int b0 = ci * chunk, Bc = std::min(chunk, B - b0);
+      if (!h->c_ev[ci]) CU(cudaEventCreateWithFlags(&h->c_ev[ci], cudaEventDisableTiming));
+      CU(cudaMemcpyAsync(const_cast<float*>(img) + b0 * img_elems, host_img + b0 * img_elems, (size_t)Bc * img_elems * 4,
+                         cudaMemcpyHostToDevice, h->cstream));
+      CU(cudaEventRecord(h->c_ev[ci], h->cstream));
+    }
+  }
+  for (int b0 = 0, ci = 0; b0 < B; b0 += chunk, ++ci) {
     const int Bc = std::min(chunk, B - b0);
+    if (host_img) CU(cudaStreamWaitEvent(st, h->c_ev[ci], 0));
     h->ws.reset();
     int r = (h->precision == XN_PREC_BF16)   ? swin_forward_chunk<bf16>(h, img + b0 * img_elems, Bc, out + b0 * out_elems, st)
             : (h->precision == XN_PREC_FP16) ? swin_forward_chunk<f16>(h, img + b0 * img_elems, Bc, out + b0 * out_elems, st)
@@ -900,6 +926,9 @@ int xn_destroy(xn_handle* h) {
     if (h->d_join[g]) cudaEventDestroy(h->d_join[g]);
   }
   if (h->d_fork) cudaEventDestroy(h->d_fork);
+  if (h->cstream) cudaStreamDestroy(h->cstream);
+  if (h->c_fork) cudaEventDestroy(h->c_fork);
+  for (int i = 0; i < xn_handle::kMaxCopyChunks; ++i) if (h->c_ev[i]) cudaEventDestroy(h->c_ev[i]);
   for (cudaEvent_t e : h->prof_ev) cudaEventDestroy(e);
   for (auto& sp : h->spans) { cudaEventDestroy(sp.e0); cudaEventDestroy(sp.e1); }
   for (cudaEvent_t e : h->span_pool) cudaEventDestroy(e);
@@ -1179,8 +1208,13 @@ int xn_beam_search_from_enc(xn_handle* h, const float* enc_out, int B, const int
                        out_tokens, out_len, out_logprob, st, true);
 }
 
-int xn_beam_search(xn_handle* h, const float* input, int B, const int32_t* enc_pads_host, int beam, int max_len, int how_many,
-                   int sos_idx, int eos_idx, int32_t* out_tokens, int32_t* out_len, float* out_logprob, void* stream) {
+}  // extern "C"
+
+// images -> captions; host_src != nullptr: `input` is unfilled device staging and the images come from that pinned host
+// buffer, copied chunk-wise inside the call (xn_caption_host)
+static int beam_search_impl(xn_handle* h, const float* input, const float* host_src, int B, const int32_t* enc_pads_host, int beam,
+                            int max_len, int how_many, int sos_idx, int eos_idx, int32_t* out_tokens, int32_t* out_len,
+                            float* out_logprob, void* stream) {
   NEED_READY();
   const xn_config& c = h->cfg;
   if (how_many > beam) return h->fail(XN_ERR_ARG, "requested output per sequence must be lower than beam width");
@@ -1229,10 +1263,12 @@ int xn_beam_search(xn_handle* h, const float* input, int B, const int32_t* enc_p
     }
   }
   if (!r) {
-    const xn_handle::GraphKey key{1 + 16 * G, input, B, beam, max_len, how_many, sos_idx, eos_idx, h->ws.base, keep};
+    const int host_chunk = 32;                              // copy granularity of the host path (chunk c+1 lands during chunk c)
+    const xn_handle::GraphKey key{1 + 16 * G + (host_src ? 4096 : 0), host_src ? host_src : input, B, beam, max_len, how_many,
+                                  sos_idx, eos_idx, h->ws.base, keep};
     r = run_graphed(h, key, true, st, [&](cudaStream_t s2) -> int {
       if (c.has_swin) {
-        if (int rr = swin_forward(h, input, B, fb, s2)) return rr;
+        if (int rr = swin_forward(h, input, B, fb, s2, host_src, host_chunk)) return rr;
         if (int rr = enc_body(h, fb, B, nullptr, enc_out, s2)) return rr;
       } else {
         if (int rr = enc_body(h, input, B, nullptr, enc_out, s2)) return rr;
@@ -1257,6 +1293,14 @@ int xn_beam_search(xn_handle* h, const float* input, int B, const int32_t* enc_p
   }
   h->ws.cap = keep;
   return r;
+}
+
+extern "C" {
+
+int xn_beam_search(xn_handle* h, const float* input, int B, const int32_t* enc_pads_host, int beam, int max_len, int how_many,
+                   int sos_idx, int eos_idx, int32_t* out_tokens, int32_t* out_len, float* out_logprob, void* stream) {
+  return beam_search_impl(h, input, nullptr, B, enc_pads_host, beam, max_len, how_many, sos_idx, eos_idx, out_tokens, out_len,
+                          out_logprob, stream);
 }
 
 int xn_ensemble_beam_search(xn_handle* const* hs, int n_models, const float* input, int B, const int32_t* enc_pads_host, int beam,
@@ -1397,8 +1441,17 @@ int xn_caption_host(xn_handle* h, const float* input_host, int B, int beam, int 
   int32_t* d_tok = reinterpret_cast<int32_t*>(dout);
   float* d_lp = reinterpret_cast<float*>(dout + n_out * 4);
   int32_t* d_len = reinterpret_cast<int32_t*>(dout + n_out * 8);
-  CU(cudaMemcpyAsync(din, input_host, in_elems * 4, cudaMemcpyHostToDevice, st));
-  if (int r = xn_beam_search(h, din, B, nullptr, beam, max_len, how_many, sos_idx, eos_idx, d_tok, d_len, d_lp, stream)) return r;
+  // pinned host images of an end-to-end model: copied chunk by chunk inside the call's graph, overlapping the Swin chunks;
+  // anything else (pageable memory, features-in model) is copied up front
+  cudaPointerAttributes pa{};
+  const bool pinned = cudaPointerGetAttributes(&pa, input_host) == cudaSuccess && pa.type == cudaMemoryTypeHost;
+  (void)cudaGetLastError();
+  if (pinned && c.has_swin && !h->profile) {
+    if (int r = beam_search_impl(h, din, input_host, B, nullptr, beam, max_len, how_many, sos_idx, eos_idx, d_tok, d_len, d_lp, stream)) return r;
+  } else {
+    CU(cudaMemcpyAsync(din, input_host, in_elems * 4, cudaMemcpyHostToDevice, st));
+    if (int r = xn_beam_search(h, din, B, nullptr, beam, max_len, how_many, sos_idx, eos_idx, d_tok, d_len, d_lp, stream)) return r;
+  }
   CU(cudaMemcpyAsync(out_tokens_host, d_tok, n_out * 4, cudaMemcpyDeviceToHost, st));
   CU(cudaMemcpyAsync(out_len_host, d_len, (size_t)B * how_many * 4, cudaMemcpyDeviceToHost, st));
   if (out_logprob_host) CU(cudaMemcpyAsync(out_logprob_host, d_lp, n_out * 4, cudaMemcpyDeviceToHost, st));

@@ -387,6 +387,28 @@ def check_ensemble() -> List[Triple]:
     return out
 
 
+def check_caption_host() -> List[Triple]:
+    """xn_caption_host (host buffers in, host tokens out -- the call bench.py's e2e times): pinned input takes the in-graph
+    chunked-copy path (Swin chunks of 32 overlapping the copies), pageable input the plain copy; both must return exactly
+    what the device-input beam search returns, on repeated calls (eager, capture, replay) and for a batch that is not a
+    multiple of the copy chunk."""
+    e, g, cfg, sd, x, pads = engine_for("full_e2e_peaky", "fp16")
+    from on_device_image_captioning_b200 import synth
+    m = g["meta"]
+    out = []
+    for B in (70, 3):
+        xs = synth.make_images(cfg, B, seed=21, kind="mixed")
+        t_ref, l_ref, _ = e.beam_search(xs, None, m["sos"], m["eos"], 3, 1, 20)
+        ref = _tokens_list(t_ref, l_ref)
+        for kind, host in (("pinned", xs.clone().pin_memory()), ("pageable", xs.clone())):
+            bad = 0
+            for _ in range(4):                      # first sight, capture, two replays
+                tok, ln, lp = e.caption_host(host, m["sos"], m["eos"], 3, 1, 20)
+                bad += sum(1 for i, t in enumerate(_tokens_list(tok, ln)) if t != ref[i])
+            out.append((f"caption_host[{kind} input, B={B}] captions differing from the device-input call (4 calls)", float(bad), 0.0))
+    return out
+
+
 # ------------------------------------------------------------------ BASELINE.json configurations at full size
 def _tokens_list(tok, ln):
     tok, ln = tok.cpu(), ln.cpu()

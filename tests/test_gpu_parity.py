@@ -169,3 +169,9 @@ def test_ensemble_beam_search():
     """ensemble beam search vs the reference's EsembleCaptioningModel fixture."""
     import gpu_checks as G
     _assert(G.check_ensemble())
+
+
+def test_caption_host_paths():
+    """The host-buffer C-ABI call (bench.py's e2e): pinned (in-graph chunked copies) and pageable inputs."""
+    import gpu_checks as G
+    _assert(G.check_caption_host())

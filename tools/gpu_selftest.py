@@ -33,7 +33,8 @@ def main():
     jobs += [("dec_fp16:feat_peaky_b5", lambda: G.check_decoder("feat_peaky_b5", "fp16")),
              ("beam_fp16:feat_peaky_b5", lambda: G.check_beam("feat_peaky_b5", "fp16"))]
     if not quick:
-        jobs += [("config3", G.check_config3_features_beam5), ("config4", G.check_config4_batch512_chunking)]
+        jobs += [("config3", G.check_config3_features_beam5), ("config4", G.check_config4_batch512_chunking),
+                 ("caption_host", G.check_caption_host)]
     results, nbad = [], 0
     for name, fn in jobs:
         if only and not any(o in name for o in only):
