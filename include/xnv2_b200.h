@@ -145,7 +145,8 @@ int xn_op_linear_skinny(xn_handle* h, const float* x, const float* gamma, const 
                         const float* bias, const float* residual, float* y, int M, int N, int K, int act,
                         int x_is_16bit, int precision, void* stream);
 /* Measurement hook: one GEMM launch on operands that are already 16-bit on the device (no conversions), y fp32.
- * which = 0: tcgen05 kernel, 1: skinny kernel with a 16-bit A, 2: skinny kernel with fp32 A (+ LayerNorm if gamma). */
+ * which = 0: tcgen05 kernel, 1: skinny kernel with a 16-bit A, 2: skinny kernel with fp32 A (+ LayerNorm if gamma),
+ * 3: tcgen05 kernel with LayerNorm-on-load (a = fp32 rows, K = 512; gamma may be NULL for a plain conversion). */
 int xn_op_gemm_raw(xn_handle* h, int which, const void* a, const float* gamma, const float* beta, const void* w16,
                    const float* bias, const float* residual, float* y, int M, int N, int K, int act, int precision, void* stream);
 int xn_op_window_attention(xn_handle* h, const float* qkv, const float* bias_table, float* out,

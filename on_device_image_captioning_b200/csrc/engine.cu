@@ -97,6 +97,11 @@ struct xn_handle {
   int64_t use_graph = 1;
   int64_t op_out16 = 0;
   int64_t use_skinny = 1;
+  // Decoder-step LayerNorms folded into the consuming tcgen05 GEMM's A path.  Implemented and bit-identical to the
+  // two-kernel path, but measured slower in the graph (14.4 us vs 6.5 us GEMM + 4.7 us LayerNorm kernel at M = 96: the
+  // in-kernel normalisation sits on the critical path in front of the first MMA; 64-image call 29.5 vs 28.8 ms), so it
+  // is off by default (profiles/r2_decoder_gemm_ln_on_load.txt).
+  int64_t ln_on_load = 0;
   // the decoder step is a chain of latency-bound kernels that fills a fraction of the machine: the batch is decoded as
   // up to kMaxDecodeGroups independent image groups on concurrent streams (parallel branches of the captured graph)
   static constexpr int kMaxDecodeGroups = 8;
@@ -198,9 +203,11 @@ int lin_f32(xn_handle* h, const float* x, long ldx, const LinW& w, const float* 
   return 0;
 }
 int lin_tc(xn_handle* h, const void* x, long ldx, const LinW& w, const float* res, long ldr, float* yf, void* yb,
-           long ldy, int M, int act, int fp16, cudaStream_t st, int w_static = 1) {
+           long ldy, int M, int act, int fp16, cudaStream_t st, int w_static = 1, const float* a32 = nullptr, long lda32 = 0,
+           const float* ln_g = nullptr, const float* ln_b = nullptr) {
   TcGemmArgs g{};
   g.w_static = w_static;
+  g.a32 = a32; g.lda32 = lda32; g.ln_g = ln_g; g.ln_b = ln_b;        // LayerNorm-on-load (x is then unused)
   g.A = x; g.lda = ldx; g.W = w.wb; g.ldw = w.K; g.Cf = yf; g.Cb = yb; g.ldc = ldy; g.fp16 = fp16;
   g.bias = w.b; g.res = res; g.ldr = ldr; g.M = M; g.N = w.N; g.K = w.K; g.div = 0.f; g.act = act;
   if (h->profile == 1) {
@@ -656,8 +663,17 @@ int dec_step_t(xn_handle* h, DecBufs& D, int p, const int64_t* tok64, const int*
       if (rs <= 0) return rs;
       return dec_lin<T>(h, a, lda, w, res, ldr, yf, y16, ldy, R, act, st);
     };
-    if (!(fuse_ln && l == 0)) KL(1, launch_layernorm<T>(xin, ldi, W.n1g, W.n1b, xn, d, R, d, st));
-    if (int r = lin16(xn, d, W.dyn5, nullptr, 0, crow, nullptr, D.s.cw, 0)) return r;
+    // LayerNorm + linear with the norm folded into the GEMM's A path (tcgen05, K = 512, one tile per CTA, more than 64 rows)
+    auto ln_lin = [&](const float* x32, long ldx32, const float* g_, const float* b_, const LinW& w, float* yf, T* y16, long ldy, int act) -> int {
+      if constexpr (k16) {
+        if (h->ln_on_load && R > 64 && tc_gemm_ln_supported(R, w.N, w.K))
+          return lin_tc(h, nullptr, 0, w, nullptr, 0, yf, yf ? nullptr : y16, ldy, R, act, std::is_same<T, f16>::value, st, 1, x32, ldx32, g_, b_);
+      }
+      KL(1, launch_layernorm<T>(x32, ldx32, g_, b_, xn, d, R, d, st));
+      return lin16(xn, d, w, nullptr, 0, yf, y16, ldy, act);
+    };
+    if (fuse_ln && l == 0) { if (int r = lin16(xn, d, W.dyn5, nullptr, 0, crow, nullptr, D.s.cw, 0)) return r; }
+    else if (int r = ln_lin(xin, ldi, W.n1g, W.n1b, W.dyn5, crow, nullptr, D.s.cw, 0)) return r;
     if (fuse_ln) {
       KL(1, launch_dyn_exp_step<T>(D.s, l, p, W.qexp, W.bexp, c.num_exp_dec, row_len, xin, ldi, xout, ldc, d, W.n2g, W.n2b, xn, d, st));
     } else {
@@ -668,8 +684,7 @@ int dec_step_t(xn_handle* h, DecBufs& D, int p, const int64_t* tok64, const int*
     KL(1, (launch_cross_attn_step<T, T>(D.q, d, reinterpret_cast<const T*>(D.kv), ldkv, l * 2 * d, l * 2 * d + d, att, d, R,
                                         rows_per_image, c.enc_len, c.num_heads, d / c.num_heads, n_valid, row_len, p, st)));
     if (int r = lin16(att, d, W.wo, xout, ldc, xout, nullptr, ldc, 0)) return r;
-    KL(1, launch_layernorm<T>(xout, ldc, W.n3g, W.n3b, xn, d, R, d, st));
-    if (int r = lin16(xn, d, W.ff1, nullptr, 0, nullptr, hid, c.ff, 2)) return r;
+    if (int r = ln_lin(xout, ldc, W.n3g, W.n3b, W.ff1, nullptr, hid, c.ff, 2)) return r;
     if (int r = lin16(hid, c.ff, W.ff2, xout, ldc, xout, nullptr, ldc, 0)) return r;
   }
   // reduce group: fp32 concatenation, converted on load by the skinny kernel where selected
@@ -682,6 +697,11 @@ int dec_step_t(xn_handle* h, DecBufs& D, int p, const int64_t* tok64, const int*
       ycat_in = reinterpret_cast<const T*>(D.ycat16);
     }
     if (int r = dec_lin<T>(h, ycat_in, ldc, h->dec_reduce, D.ycat + (size_t)(nd - 1) * d, ldc, D.pre, nullptr, d, R, 0, st)) return r;
+  }
+  if constexpr (k16) {
+    if (h->ln_on_load && R > 64 && d == 512 && tc_gemm_ln_supported(R, h->vocab.N, h->vocab.K))
+      return lin_tc(h, nullptr, 0, h->vocab, nullptr, 0, logits, nullptr, ldl, R, 0, std::is_same<T, f16>::value, st, 1, D.pre, d,
+                    h->dec_ng, h->dec_nb);
   }
   KL(1, launch_layernorm<T>(D.pre, d, h->dec_ng, h->dec_nb, yn, d, R, d, st));
   if (int r = dec_lin<T>(h, yn, d, h->vocab, nullptr, 0, logits, nullptr, ldl, R, 0, st)) return r;
@@ -1515,6 +1535,7 @@ int xn_set_option(xn_handle* h, const char* name, int64_t value) {
   if (n == "use_graph") { h->use_graph = value; h->drop_graphs(); return XN_OK; }
   if (n == "op_out16") { h->op_out16 = value; return XN_OK; }
   if (n == "use_skinny") { h->use_skinny = value; h->drop_graphs(); return XN_OK; }
+  if (n == "ln_on_load") { h->ln_on_load = value; h->drop_graphs(); return XN_OK; }
   if (n == "decode_groups") { h->decode_groups = std::max<int64_t>(0, std::min<int64_t>(value, xn_handle::kMaxDecodeGroups)); h->drop_graphs(); return XN_OK; }
   if (n == "pdl") { g_pdl_enabled = value != 0; h->drop_graphs(); return XN_OK; }
   if (n == "tc_debug") { set_tc_debug((int)value); return XN_OK; }
@@ -1653,8 +1674,12 @@ int xn_op_gemm_raw(xn_handle* h, int which, const void* a, const float* gamma, c
                    const float* residual, float* y, int M, int N, int K, int act, int precision, void* stream) {
   OP_READY();
   const bool fp16 = precision == XN_PREC_FP16;
-  if (which == 0) {
+  if (which == 0 || which == 3) {
     LinW l; l.wb = w16; l.b = bias; l.N = N; l.K = K;
+    if (which == 3) {            // LayerNorm-on-load: a = fp32 rows
+      if (!tc_gemm_ln_supported(M, N, K)) return h->fail(XN_ERR_UNSUPPORTED, "LayerNorm-on-load GEMM does not cover M=%d N=%d K=%d", M, N, K);
+      return lin_tc(h, nullptr, 0, l, residual, N, y, nullptr, N, M, act, fp16, st, 1, reinterpret_cast<const float*>(a), K, gamma, beta);
+    }
     return lin_tc(h, a, K, l, residual, N, y, nullptr, N, M, act, fp16, st);
   }
   SkinnyArgs g{};

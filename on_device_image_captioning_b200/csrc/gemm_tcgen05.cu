@@ -57,6 +57,7 @@ struct TcEpilogue {
   const float* res; long ldr;
   float scale;  // accumulator multiplier (1 / div); a multiply, never a speculated division
   int w_static;        // weight tiles may be loaded before the dependency wait
+  const float* a32; long lda32; const float* ln_g; const float* ln_b;   // LayerNorm-on-load source of A (or nullptr)
   int use_tma_store;   // 16-bit output without residual: write through TMA (needs ldc % 8 == 0)
   int dbg;     // timing experiments only: 1 = skip the epilogue's global traffic, 2 = skip MMA issue, 4 = skip TMA loads
 };
@@ -246,6 +247,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   const uint32_t rank = CTAS == 2 ? cluster_ctarank() : 0u;           // 0 = leader (issues the MMAs)
   const int tile0 = blockIdx.x / CTAS, tile_step = gridDim.x / CTAS;   // persistent loop over (pair) tiles
   const int row_off = (int)rank * kBM;                                 // this CTA's rows inside the pair tile
+  // LayerNorm-on-load mode (single CTA, one tile per CTA, K = 8 k-blocks): A lives in the first 8 x 16 KB of the ring
+  // area for the whole kernel, the remaining ring bytes form the B pipeline
+  constexpr int kAResBlocks = 8;
+  const bool a_res = CTAS == 1 && ep.a32 != nullptr;
+  constexpr uint32_t kBRingOff = kAResBlocks * kABytes;
+  constexpr int kSB = (int)((S * Cfg::kStageBytes - kBRingOff) / Cfg::kBBytes) > 0 ? (int)((S * Cfg::kStageBytes - kBRingOff) / Cfg::kBBytes) : 1;
+  const uint32_t afull_bar = bars + 8u * (2 * S + 21);
 
   if (threadIdx.x == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tma_a)) : "memory");
@@ -254,6 +262,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     for (int s = 0; s < S; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), kEpiWarps * CTAS); }
     for (int b = 0; b < 16; ++b) mbar_init(bars + 8u * (2 * S + 5 + b), 1);     // residual-slab barriers (fp32 TMA epilogue)
+    mbar_init(bars + 8u * (2 * S + 21), kEpiWarps);                              // A tile produced in-kernel (LayerNorm-on-load)
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -280,11 +289,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   // GEMM starts its MMAs one L2 round trip after the previous kernel has drained.
   int pre_stages = 0;
   if (CTAS == 1 && ep.w_static && warp == 0 && lane == 0 && tile0 < total_tiles && !(ep.dbg & 4)) {
-    pre_stages = nkb < S ? nkb : S;
+    const int ring = a_res ? kSB : S;
+    pre_stages = nkb < ring ? nkb : ring;
     const int n0 = (tile0 % n_tiles) * BN;
     for (int kb = 0; kb < pre_stages; ++kb) {
-      mbar_expect_tx(full_bar(kb), Cfg::kStageBytes);
-      tma_load_2d(base + kb * Cfg::kStageBytes + kABytes, &tma_b, kb * kBK, n0, full_bar(kb));
+      mbar_expect_tx(full_bar(kb), a_res ? Cfg::kBBytes : Cfg::kStageBytes);
+      tma_load_2d(a_res ? base + kBRingOff + kb * Cfg::kBBytes : base + kb * Cfg::kStageBytes + kABytes, &tma_b, kb * kBK, n0, full_bar(kb));
     }
   }
   pdl_wait();
@@ -308,7 +318,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             tma_load_2d_pair(sa + kABytes, &tma_b, kb * kBK, n0, lbar);
           } else {
             if (ep.dbg & 4) { mbar_arrive(full_bar(stage)); if (++stage == S) { stage = 0; phase ^= 1u; } continue; }
-            if (pre_stages > 0) {                       // W tile and byte count of this stage were issued before the wait
+            if (a_res) {                                // only W travels through the ring; A is written by the epilogue warps
+              if (pre_stages > 0) --pre_stages;
+              else {
+                mbar_expect_tx(full_bar(stage), Cfg::kBBytes);
+                tma_load_2d(base + kBRingOff + stage * Cfg::kBBytes, &tma_b, kb * kBK, n0, full_bar(stage));
+              }
+            } else if (pre_stages > 0) {                // W tile and byte count of this stage were issued before the wait
               --pre_stages;
               tma_load_2d(sa, &tma_a, kb * kBK, m0, full_bar(stage));
             } else {
@@ -317,7 +333,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
               tma_load_2d(sa + kABytes, &tma_b, kb * kBK, n0, full_bar(stage));
             }
           }
-          if (++stage == S) { stage = 0; phase ^= 1u; }
+          if (++stage == (a_res ? kSB : S)) { stage = 0; phase ^= 1u; }
         }
       }
     }
@@ -333,12 +349,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         mbar_wait(tempty_bar(buf), acc_phase ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + buf * Cfg::kAccCols;
+        if (a_res) { mbar_wait(afull_bar, 0u); tc_fence_after(); }      // the normalised A tile is in shared memory
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
           const uint32_t sa = base + stage * Cfg::kStageBytes;
-          const uint64_t adesc = make_sw128_desc(sa);
-          const uint64_t bdesc = make_sw128_desc(sa + kABytes);
+          const uint64_t adesc = make_sw128_desc(a_res ? base + kb * kABytes : sa);
+          const uint64_t bdesc = make_sw128_desc(a_res ? base + kBRingOff + stage * Cfg::kBBytes : sa + kABytes);
           if (!(ep.dbg & 2)) {
 #pragma unroll
             for (int k = 0; k < kBK / kUmmaK; ++k) {  // +32 bytes (>>4 = 2) per UMMA_K step inside the swizzle atom
@@ -348,13 +365,74 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
           }
           if (CTAS == 2) umma_commit_pair(empty_bar(stage));   // frees the smem slot in both CTAs when these MMAs retire
           else umma_commit(empty_bar(stage));
-          if (++stage == S) { stage = 0; phase ^= 1u; }
+          if (++stage == (a_res ? kSB : S)) { stage = 0; phase ^= 1u; }
         }
         if (CTAS == 2) umma_commit_pair(tfull_bar(buf));       // accumulator complete -> both CTAs' epilogues
         else umma_commit(tfull_bar(buf));
       }
     }
   } else {
+    if (a_res) {
+      // ---- LayerNorm-on-load: epilogue warp e normalises rows 8e .. 8e+7 of the tile (four at a time, all their loads in
+      // flight), rounds to the operand type and writes them into the resident A area in the 128-byte-swizzled K-major
+      // layout the UMMA descriptor expects: k-block kb at kb * 16 KB, row r at r * 128 B, 16-byte chunk c at c ^ (r & 7).
+      // Same per-lane column assignment and reduction order as layernorm_kernel, so the statistics are bit-identical.
+      const int e = warp - 2;
+      const int m0t = (tile0 / n_tiles) * kBM;
+      const float inv_k = 1.0f / (float)K;
+      for (int hb = 0; hb < 2; ++hb) {
+        float4 v[4][4];
+#pragma unroll
+        for (int qq = 0; qq < 4; ++qq) {
+          const int row = m0t + e * 8 + hb * 4 + qq;
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            v[qq][i] = row < M ? *reinterpret_cast<const float4*>(ep.a32 + (long)row * ep.lda32 + (i * 32 + lane) * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int qq = 0; qq < 4; ++qq) {
+          float mean = 0.f, rstd = 1.f;
+          if (ep.ln_g) {
+            float sm_ = 0.f;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) sm_ += (v[qq][i].x + v[qq][i].y) + (v[qq][i].z + v[qq][i].w);
+            mean = warp_sum(sm_) * inv_k;
+            float qv = 0.f;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float d0 = v[qq][i].x - mean, d1 = v[qq][i].y - mean, d2 = v[qq][i].z - mean, d3 = v[qq][i].w - mean;
+              qv += (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
+            }
+            rstd = 1.0f / sqrtf(warp_sum(qv) * inv_k + 1e-5f);
+          }
+          const int r = e * 8 + hb * 4 + qq;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            float4 o = v[qq][i];
+            if (ep.ln_g) {
+              const int c = (i * 32 + lane) * 4;
+              const float4 ga = *reinterpret_cast<const float4*>(ep.ln_g + c), be = *reinterpret_cast<const float4*>(ep.ln_b + c);
+              o.x = (o.x - mean) * rstd * ga.x + be.x; o.y = (o.y - mean) * rstd * ga.y + be.y;
+              o.z = (o.z - mean) * rstd * ga.z + be.z; o.w = (o.w - mean) * rstd * ga.w + be.w;
+            }
+            uint2 u;
+            if (ep.fp16) {
+              __half2 a2 = __floats2half2_rn(o.x, o.y), b2 = __floats2half2_rn(o.z, o.w);
+              u.x = *reinterpret_cast<uint32_t*>(&a2); u.y = *reinterpret_cast<uint32_t*>(&b2);
+            } else {
+              __nv_bfloat162 a2 = __floats2bfloat162_rn(o.x, o.y), b2 = __floats2bfloat162_rn(o.z, o.w);
+              u.x = *reinterpret_cast<uint32_t*>(&a2); u.y = *reinterpret_cast<uint32_t*>(&b2);
+            }
+            const int kb = i * 2 + (lane >> 4);                 // column (i*32+lane)*4 lies in k-block ((i*32+lane)*4) / 64
+            const int chunk = (lane & 15) >> 1;                 // 16-byte chunk inside the 128-byte row of that k-block
+            *reinterpret_cast<uint2*>(gen_base + kb * kABytes + r * 128 + ((chunk ^ (r & 7)) << 4) + (lane & 1) * 8) = u;
+          }
+        }
+      }
+      fence_async_smem();                                        // generic-proxy writes -> visible to the tensor core (async proxy)
+      __syncwarp();
+      if (lane == 0) mbar_arrive(afull_bar);
+    }
     const int q = warp & 3;                        // TMEM lane quarter this warp may access (hardware: warp id % 4)
     const int hf = (warp - 2) >> 2;                // which quarter of the tile's columns this warp drains
     int it = 0;
@@ -683,6 +761,13 @@ int g_pdl_enabled = 1;
 void set_tc_debug(int v) { g_tc_debug = v; }
 
 bool tc_gemm_supported(int M, int N, int K) { return M > 0 && N > 0 && K > 0 && (K % 8) == 0; }
+// LayerNorm-on-load: K = 512 (8 resident k-blocks), 128-wide tiles, one tile per CTA
+bool tc_gemm_ln_supported(int M, int N, int K) {
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  return M > 0 && N > 0 && K == 512 && (long)((M + kBM - 1) / kBM) * ((N + 127) / 128) <= sms;
+}
 
 static int sm_count() {
   static int n = 0;
@@ -737,7 +822,8 @@ static cudaError_t launch_tc(const TcGemmArgs& p, cudaStream_t st) {
       if (p.res && !make_map32(&mr, p.res, p.M, p.N, p.ldr)) return cudaErrorInvalidValue;
     }
   }
-  TcEpilogue ep{p.Cf, p.Cb, p.ldc, p.fp16, p.bias, p.res, p.ldr, p.div != 0.f ? 1.0f / p.div : 1.0f, p.w_static, tma_c_ok ? 1 : 0, g_tc_debug};
+  TcEpilogue ep{p.Cf, p.Cb, p.ldc, p.fp16, p.bias, p.res, p.ldr, p.div != 0.f ? 1.0f / p.div : 1.0f, p.w_static, p.a32, p.lda32, p.ln_g, p.ln_b,
+                tma_c_ok ? 1 : 0, g_tc_debug};
   const int tiles = ((p.M + kBM * CTAS - 1) / (kBM * CTAS)) * ((p.N + BN - 1) / BN);
   const int slots = sm_count() / CTAS;
   const int grid = CTAS * (tiles < slots ? tiles : slots);
@@ -780,6 +866,14 @@ static cudaError_t launch_tc_bn(const TcGemmArgs& p, cudaStream_t st) {
 }
 
 cudaError_t launch_gemm_tc(const TcGemmArgs& p, cudaStream_t st) {
+  if (p.a32) {          // LayerNorm-on-load: fixed configuration (128-wide single-CTA tiles, one per CTA)
+    if (!tc_gemm_ln_supported(p.M, p.N, p.K) || (p.ldw % 8) || (p.lda32 % 4) || ((p.Cf != nullptr) == (p.Cb != nullptr)) ||
+        (reinterpret_cast<uintptr_t>(p.a32) & 15) || (reinterpret_cast<uintptr_t>(p.W) & 15) || p.act < 0 || p.act > 2)
+      return cudaErrorInvalidValue;
+    TcGemmArgs q = p;
+    q.A = p.W; q.lda = p.ldw;                      // a valid tensor map is still built for the unused A operand
+    return launch_tc_bn<128, 1>(q, st);
+  }
   if (!tc_gemm_supported(p.M, p.N, p.K) || (p.lda % 8) || (p.ldw % 8) || ((p.Cf != nullptr) == (p.Cb != nullptr)))
     return cudaErrorInvalidValue;
   if ((reinterpret_cast<uintptr_t>(p.A) & 15) || (reinterpret_cast<uintptr_t>(p.W) & 15)) return cudaErrorInvalidValue;

@@ -44,7 +44,13 @@ struct TcGemmArgs {
   int act;
   int w_static;                      // W was written before the previous kernel started (model weights): its tiles may
                                      // be fetched ahead of the programmatic-dependent-launch wait
+  // LayerNorm-on-load (decoder-step linears, K == 512, one tile per CTA): A is produced inside the kernel from these fp32
+  // rows -- LayerNorm(gamma, beta) (or a plain conversion when ln_g == nullptr), rounded to the operand type and written
+  // into shared memory in the UMMA layout by the epilogue warps before their epilogue role.  `A` is then unused.
+  const float* a32; long lda32;
+  const float *ln_g, *ln_b;
 };
+bool tc_gemm_ln_supported(int M, int N, int K);
 cudaError_t launch_gemm_tc(const TcGemmArgs& p, cudaStream_t st);
 bool tc_gemm_supported(int M, int N, int K);
 void set_tc_debug(int v);

@@ -152,6 +152,39 @@ def check_linear_skinny(precision: str = "fp16") -> List[Triple]:
     return out
 
 
+def check_linear_ln_on_load(precision: str = "fp16") -> List[Triple]:
+    """tcgen05 GEMM with LayerNorm-on-load (the epilogue warps normalise the fp32 rows into the UMMA shared-memory layout)
+    vs the two-kernel path it replaces (LayerNorm kernel -> 16-bit operand -> the same GEMM): bit-identical outputs, plus
+    the fp64 reference of the rounded operands."""
+    e = bare_engine()
+    cast = (lambda t: t.bfloat16()) if precision == "bf16" else (lambda t: t.half())
+    out = []
+    g = torch.Generator().manual_seed(31)
+    for (M, N, act, res, ln) in [(96, 2560, 0, False, True), (192, 2048, 2, False, True), (96, 10000, 0, False, True),
+                                 (100, 512, 0, True, True), (1, 512, 0, False, True), (128, 640, 1, True, False), (77, 130, 0, False, True)]:
+        K = 512
+        x = (torch.randn(M, K, generator=g) * 1.7 + 0.4).cuda()
+        w16 = cast((torch.randn(N, K, generator=g) / math.sqrt(K)).cuda())
+        b = torch.randn(N, generator=g).cuda()
+        r = torch.randn(M, N, generator=g).cuda() if res else None
+        ga = (1.0 + 0.2 * torch.randn(K, generator=g)).cuda() if ln else None
+        be = (0.1 * torch.randn(K, generator=g)).cuda() if ln else None
+        y_fused = e.op_gemm_raw(3, x, w16, b, r, torch.empty(M, N, device="cuda"), act, precision, ga, be)
+        a16 = cast(e.op_layernorm(x, ga, be)) if ln else cast(x)
+        y_two = e.op_gemm_raw(0, a16, w16, b, r, torch.empty(M, N, device="cuda"), act, precision)
+        out.append((f"ln_on_load_{precision}[{M}x{N}x{K} act{act} res{int(res)} ln{int(ln)}] max |fused - (LN kernel, GEMM)|",
+                    float((y_fused - y_two).abs().max()), 0.0))
+        ref = torch.nn.functional.linear(a16.double(), w16.double(), b.double())
+        if act == 1:
+            ref = torch.nn.functional.gelu(ref)
+        elif act == 2:
+            ref = torch.relu(ref)
+        if res:
+            ref = ref + r.double()
+        out.append((f"ln_on_load_{precision}[{M}x{N}x{K}] vs fp64 product of the rounded operands rel-max", rel_max(y_fused, ref), 2e-5))
+    return out
+
+
 def check_window_attention(precision: str = "fp32") -> List[Triple]:
     e = bare_engine()
     out = []

@@ -32,6 +32,12 @@ def test_linear_16bit_skinny_decoder_step(precision):
     _assert(G.check_linear_skinny(precision))
 
 
+@pytest.mark.parametrize("precision", ["bf16", "fp16"])
+def test_linear_16bit_layernorm_on_load(precision):
+    import gpu_checks as G
+    _assert(G.check_linear_ln_on_load(precision))
+
+
 @pytest.mark.parametrize("precision", ["fp32", "bf16", "fp16"])
 def test_window_attention(precision):
     import gpu_checks as G

@@ -27,6 +27,8 @@ def main():
         variants = [("tcgen05", 0, x16, None), ("skinny16", 1, x16, None)]
         if a32ok:
             variants.append(("skinny32" + ("+ln" if K <= 1024 else ""), 2, x32, ga if K <= 1024 else None))
+        if K == 512:
+            variants.append(("tcgen05+ln-on-load", 3, x32, ga))
         for label, which, a, gam in variants:
             try:
                 fn = lambda: e.op_gemm_raw(which, a, w16, b, r, y, act, "fp16", gam, be if gam is not None else None)

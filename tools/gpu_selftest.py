@@ -17,6 +17,7 @@ def main():
     only = [a for a in sys.argv[1:] if not a.startswith("--")]
     jobs = [("layernorm", G.check_layernorm), ("linear_fp32", G.check_linear_fp32), ("linear_bf16", G.check_linear_bf16),
             ("linear_fp16", lambda: G.check_linear_bf16("fp16")),
+            ("lnload_fp16", lambda: G.check_linear_ln_on_load("fp16")), ("lnload_bf16", lambda: G.check_linear_ln_on_load("bf16")),
             ("skinny_fp16", lambda: G.check_linear_skinny("fp16")), ("skinny_bf16", lambda: G.check_linear_skinny("bf16")),
             ("wattn_fp32", lambda: G.check_window_attention("fp32")), ("wattn_bf16", lambda: G.check_window_attention("bf16")),
             ("wattn_fp16", lambda: G.check_window_attention("fp16")),
