@@ -600,7 +600,9 @@ int dec_lin_skinny(xn_handle* h, const T* a16, const float* a32, long lda, const
   g.A16 = a16; g.A32 = a32; g.lda = lda; g.ln_g = ln_g; g.ln_b = ln_b;
   g.W = w.wb; g.ldw = w.K; g.bias = w.b; g.res = res; g.ldr = ldr; g.Cf = yf; g.Cb = yf ? nullptr : y16; g.ldc = ldy;
   g.M = M; g.N = w.N; g.K = w.K; g.act = act;
-  // selected where it measured faster in-graph than the 128-row tcgen05 tiles: few rows, narrow outputs, no LayerNorm on load
+  // selected where it measured faster in-graph than the 128-row tcgen05 tiles: few rows, narrow outputs, no LayerNorm on
+  // load.  (Extending it to one 128-row tile for the long-K projections -- 8.8 vs 12.8 us in isolation at M = 96 -- made
+  // the two-group decode slower, 28.4 vs 27.9 ms per call: its 192 cluster CTAs crowd the other chain's kernels.)
   if (!h->use_skinny || M > 64 || w.N > 2048 || ln_g || !skinny_gemm_supported(g)) return 1;
   if (a32 && (w.K % 512)) return 1;
   if (h->profile == 1) {
