@@ -242,10 +242,13 @@ def run_ours(args):
         roofline = None
         if args.precision != "fp32":
             # ---- roofline of the dominant kernel: every tcgen05 GEMM launch of one more step, event-timed
-            eng.set_option("profile", 1)
-            eng.beam_search(devin[0], None, SOS, EOS, BEAM, 1, MAX_LEN)     # rank-local: no collective outside the lock-step region
-            g_ms, g_fl, g_n = eng.profile_read()
-            eng.set_option("profile", 0)
+            runs = []
+            for _ in range(3):                                  # median of three instrumented steps (one eager pass is noisy)
+                eng.set_option("profile", 1)
+                eng.beam_search(devin[0], None, SOS, EOS, BEAM, 1, MAX_LEN)     # rank-local: no collective outside the lock-step region
+                runs.append(eng.profile_read())
+                eng.set_option("profile", 0)
+            g_ms, g_fl, g_n = sorted(runs)[1]
             achieved = g_fl / (g_ms * 1e-3) / 1e12 if g_ms > 0 else 0.0
             roofline = dict(bound="tensor", kernel="gemm_tc_kernel (tcgen05.mma, TMA, TMEM)", achieved=achieved,
                             peak=peaks["bf16_sustained"], unit="TFLOP/s", frac=achieved / peaks["bf16_sustained"],
