@@ -21,6 +21,20 @@ constexpr int kHeadDim = 32;        // C / heads == 32 in every Swin-L stage (re
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device property of a kernel: remember the largest size configured
+// on each device (call sites keep one `static DynSmemState` per kernel instantiation)
+struct DynSmemState { size_t bytes[32] = {}; };
+template <typename F>
+inline cudaError_t ensure_dyn_smem(F func, size_t bytes, DynSmemState& st) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 32) dev = 0;
+  if (bytes <= st.bytes[dev] || bytes <= 48 * 1024) return cudaSuccess;
+  cudaError_t e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (e == cudaSuccess) st.bytes[dev] = bytes;
+  return e;
+}
+
 extern int g_pdl_enabled;
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {

@@ -349,14 +349,8 @@ cudaError_t launch_dyn_exp_step(const DecState& s, int layer, int p, const float
   if (ln_out && d != 512) return cudaErrorInvalidValue;
   const size_t P4 = (s.P + 3) & ~3, E4 = (n_exp + 3) & ~3;
   const size_t smem = (P4 * 7 + E4 * 3 + 4 * P4 * E4 + 32 + std::max<size_t>(2 * (size_t)s.P * s.P, 1536)) * sizeof(float);
-  if (smem > 48 * 1024) {
-    static size_t configured = 0;
-    if (smem > configured) {
-      cudaError_t e = cudaFuncSetAttribute(dyn_exp_step_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      if (e != cudaSuccess) return e;
-      configured = smem;
-    }
-  }
+  static DynSmemState smem_state;
+  if (cudaError_t e = ensure_dyn_smem(dyn_exp_step_kernel<T>, smem, smem_state)) return e;
   launch_k(dyn_exp_step_kernel<T>, dim3(s.R), dim3(256), smem, st, s, layer, p, qexp, bexp, n_exp, row_len, x_in, ldxi, x_out, ldxo, d, ln_g, ln_b,
                                                  ln_out, ldn);
   return cudaGetLastError();
@@ -650,12 +644,8 @@ cudaError_t launch_cross_attn_step(const float* q, long ldq, const KvT* kv, long
   }
   const size_t smem = ((size_t)dk * (n_keys + 1) + (size_t)n_keys * dk + (size_t)kMaxRpi * dk + (size_t)kMaxRpi * n_keys +
                        (size_t)(256 / dk) * kMaxRpi * dk) * sizeof(float);
-  static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(cross_attn_step_kernel<KvT, OutT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    configured = smem;
-  }
+  static DynSmemState smem_state;
+  if (cudaError_t e = ensure_dyn_smem(cross_attn_step_kernel<KvT, OutT>, smem, smem_state)) return e;
   launch_k(cross_attn_step_kernel<KvT, OutT>, dim3(dim3(R / rows_per_image, heads)), dim3(256), smem, st, 
       q, ldq, kv, ldkv, k_off, v_off, out, ldo, rows_per_image, n_keys, dk, n_valid, row_len, p);
   return cudaGetLastError();

@@ -383,12 +383,8 @@ cudaError_t launch_patch_embed4(const float* img, const float* wq, const float* 
   if (E % 32 || E > 256 || S % 16) return cudaErrorInvalidValue;
   const int G = S / 4;
   const size_t smem = ((size_t)Cin * 4 * G + (size_t)Cin * 4 * E) * sizeof(float4);
-  static size_t configured = 0;
-  if (smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(patch_embed4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    configured = smem;
-  }
+  static DynSmemState smem_state;
+  if (cudaError_t e = ensure_dyn_smem(patch_embed4_kernel, smem, smem_state)) return e;
   const int groups = (G + kPeRows - 1) / kPeRows;
   return launch_k(patch_embed4_kernel, dim3(B * groups), dim3(256), smem, st, img, reinterpret_cast<const float4*>(wq), b, gamma, beta,
                   out, Cin, S, E);
@@ -399,12 +395,8 @@ cudaError_t launch_patch_embed(const float* img, const float* w, const float* b,
                                cudaStream_t st) {
   if (E % 32 || E > 256 || S % P || S % 4) return cudaErrorInvalidValue;
   const size_t smem = ((size_t)Cin * P * S + (size_t)Cin * P * P * E + (size_t)Cin * P * P) * sizeof(float);
-  static size_t configured = 0;
-  if (smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(patch_embed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    configured = smem;
-  }
+  static DynSmemState smem_state;
+  if (cudaError_t e = ensure_dyn_smem(patch_embed_kernel, smem, smem_state)) return e;
   const int G = S / P, groups = (G + kPeRows - 1) / kPeRows;
   launch_k(patch_embed_kernel, dim3(B * groups), dim3(256), smem, st, img, w, b, gamma, beta, out, Cin, S, P, E);
   return cudaGetLastError();

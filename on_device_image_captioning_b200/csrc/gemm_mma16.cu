@@ -177,12 +177,8 @@ cudaError_t launch_gemm_mma16(const Mma16Args& p, cudaStream_t st) {
   dim3 grid((p.N + kBN - 1) / kBN, (p.M + BM - 1) / BM, p.batch);
 #define XN_LAUNCH_MMA(BMV, KNV)                                                                                         \
   do {                                                                                                                   \
-    static bool cfgd = false;                                                                                            \
-    if (!cfgd) {                                                                                                         \
-      cudaError_t e = cudaFuncSetAttribute(gemm_mma16_kernel<T, OutT, BMV, KNV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-      if (e != cudaSuccess) return e;                                                                                    \
-      cfgd = true;                                                                                                       \
-    }                                                                                                                    \
+    static DynSmemState smem_state;                                                                                      \
+    if (cudaError_t e = ensure_dyn_smem(gemm_mma16_kernel<T, OutT, BMV, KNV>, smem, smem_state)) return e;               \
     launch_k(gemm_mma16_kernel<T, OutT, BMV, KNV>, dim3(grid), dim3(256), smem, st, p);                                                   \
   } while (0)
   if (small_m) { if (p.b_kn) XN_LAUNCH_MMA(64, true); else XN_LAUNCH_MMA(64, false); }

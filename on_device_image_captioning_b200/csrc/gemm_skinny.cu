@@ -274,12 +274,8 @@ template <typename T, int BN>
 static cudaError_t launch_skinny_bn(const SkinnyArgs& p, int split, cudaStream_t st) {
   const int Kc = p.K / split;
   const size_t smem = (size_t)(kSkBM + BN) * (Kc + 8) * 2 + (split > 1 ? (size_t)(split - 1) * kSkBM * BN * 4 : 0);
-  static size_t configured = 0;
-  if (smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_skinny_kernel<T, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    configured = smem;
-  }
+  static DynSmemState smem_state;
+  if (cudaError_t e = ensure_dyn_smem(gemm_skinny_kernel<T, BN>, smem, smem_state)) return e;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((p.N + BN - 1) / BN, (p.M + kSkBM - 1) / kSkBM, split);
   cfg.blockDim = dim3(kSkThreads);

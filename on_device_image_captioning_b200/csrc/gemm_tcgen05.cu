@@ -799,12 +799,8 @@ void set_tc_pair(int v) { g_tc_pair = v; }
 template <int BN, int OUT, int ACT, int CTAS>
 static cudaError_t launch_tc(const TcGemmArgs& p, cudaStream_t st) {
   using Cfg = TcCfg<BN, CTAS>;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, OUT, ACT, CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmemBytes);
-    if (e != cudaSuccess) return e;
-    configured = true;
-  }
+  static DynSmemState smem_state;
+  if (cudaError_t e = ensure_dyn_smem(gemm_tc_kernel<BN, OUT, ACT, CTAS>, Cfg::kSmemBytes, smem_state)) return e;
   CUtensorMap ma, mb;
   if (!make_map(&ma, p.A, p.M, p.K, p.lda, kBM, p.fp16) || !make_map(&mb, p.W, p.N, p.K, p.ldw, BN / CTAS, p.fp16)) return cudaErrorInvalidValue;
   // 16-bit outputs without a residual leave through TMA stores: 32 x 32 boxes, 64-byte swizzle

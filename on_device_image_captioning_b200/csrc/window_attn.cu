@@ -113,13 +113,8 @@ cudaError_t launch_window_attention(const T* qkv, const float* bias_table, T* ou
                                     int shift, cudaStream_t st) {
   if (H % kWin || C != heads * kHeadDim) return cudaErrorInvalidValue;
   const size_t smem = (3 * kWinTok * kKs + 9 * kWinTok + 532) * sizeof(float) + 2 * kWinTok * sizeof(int);
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(window_attention_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)smem);
-    if (e != cudaSuccess) return e;
-    configured = true;
-  }
+  static DynSmemState smem_state;
+  if (cudaError_t e = ensure_dyn_smem(window_attention_kernel<T>, smem, smem_state)) return e;
   const int nW = (H / kWin) * (H / kWin);
   window_attention_kernel<T><<<dim3(B * nW, heads), kWaThreads, smem, st>>>(qkv, bias_table, out, H, C, heads, shift);
   return cudaGetLastError();

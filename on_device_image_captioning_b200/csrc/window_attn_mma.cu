@@ -361,12 +361,8 @@ static cudaError_t launch_wa_hpc(const T* qkv, const float* bias_l2, T* out, int
                                  cudaStream_t st) {
   const size_t smem = 2 * 3 * kWinTok * kRowPad * sizeof(T) + 2 * HPC * kBiasPitch * sizeof(float) +
                       2 * kWinTok * kLPitch * sizeof(T) + 3 * kWinTok * sizeof(int);
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(window_attention_mma_kernel<T, HPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    configured = true;
-  }
+  static DynSmemState smem_state;
+  if (cudaError_t e = ensure_dyn_smem(window_attention_mma_kernel<T, HPC>, smem, smem_state)) return e;
   const int nW = (H / kWin) * (H / kWin);
   const int n_items = B * nW * (heads / HPC);
   const int grid = std::min(n_items, 2 * wa_sm_count());
