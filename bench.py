@@ -201,11 +201,15 @@ def run_ours(args):
     sampler.start()
     l0 = eng.kernel_launches
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if args.profile_region:                             # ncu --profile-from-start off: launch list of exactly the timed steps
+        torch.cuda.cudart().cudaProfilerStart()
     e0.record()
     for i in range(args.steps):
         step(i)
     e1.record()
     barrier()
+    if args.profile_region:
+        torch.cuda.cudart().cudaProfilerStop()
     launches = eng.kernel_launches - l0
     ms = e0.elapsed_time(e1)
     note(f"timed region done: {ms:.1f} ms")
@@ -363,6 +367,7 @@ def main():
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--swin-chunk", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--profile-region", action="store_true", help="cudaProfilerStart/Stop around the timed steps (for ncu launch lists)")
     ap.add_argument("--verbose", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

@@ -145,6 +145,15 @@ __global__ void __launch_bounds__(256) dyn_exp_step_kernel(DecState s, int layer
   auto crow = [&](int i) { return s.cache + (((long)layer * P + i) * s.R + slot[i]) * s.cw; };
   const float* cp = crow(p);                   // [cond | key | A | B | sel] of the new position
   const float* Kp = cp + d;
+  // The history rows this CTA will touch -- cond, key, A, B of every position -- are pulled towards L1 now, 128 bytes per
+  // request, so the three phases below (each a dependent round of reads) hit L1 instead of paying an L2 trip apiece.
+  if (s.cw == 5 * d) {
+    const int lines_per_row = (4 * d * (int)sizeof(float)) / 128;
+    for (int i = tid; i < np * lines_per_row; i += blockDim.x) {
+      const float* a = crow(i / lines_per_row) + (i % lines_per_row) * 32;
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(a));
+    }
+  }
 
   // ---- phase A: the 2p+1+n_exp new dot products, 8 lanes each (4 concurrent per warp, 32 per CTA round)
   const int ntask = np + p + n_exp;
