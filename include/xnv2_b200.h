@@ -127,6 +127,9 @@ int xn_set_option(xn_handle* h, const char* name, int64_t value);   /* "swin_chu
  * this returns the summed device time, the summed algorithmic FLOPs and the launch count since
  * the option was set (synchronises the device). */
 int xn_profile_read(xn_handle* h, double* ms_total, double* flops_total, int64_t* count);
+/* Same, restricted to launches of at least min_flops floating-point operations (separates the Swin / encoder GEMMs from
+ * the latency-bound decoder-step GEMMs in the roofline report). */
+int xn_profile_read_min(xn_handle* h, double min_flops, double* ms_total, double* flops_total, int64_t* count);
 /* With option "profile"=2 EVERY kernel launch of the library is bracketed by CUDA events (graphs off) and attributed to
  * its launcher; this writes "launcher<TAB>launches<TAB>total_ms" lines into buf (bench.py's bandwidth-roofline leg). */
 int xn_profile_kernels(xn_handle* h, char* buf, int cap);

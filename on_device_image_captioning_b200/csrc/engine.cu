@@ -1554,6 +1554,10 @@ int xn_set_option(xn_handle* h, const char* name, int64_t value) {
 }
 
 int xn_profile_read(xn_handle* h, double* ms_total, double* flops_total, int64_t* count) {
+  return xn_profile_read_min(h, 0.0, ms_total, flops_total, count);
+}
+
+int xn_profile_read_min(xn_handle* h, double min_flops, double* ms_total, double* flops_total, int64_t* count) {
   if (!h) return XN_ERR_ARG;
   cudaSetDevice(h->device);
   CU(cudaDeviceSynchronize());
@@ -1561,6 +1565,7 @@ int xn_profile_read(xn_handle* h, double* ms_total, double* flops_total, int64_t
   int64_t n_tc = 0;
   for (size_t i = 0; i + 1 < h->prof_used; i += 2) {
     if (h->prof_flops[i / 2] < 0) continue;          // skinny mma.sync launches are not part of the tcgen05 roofline
+    if (h->prof_flops[i / 2] < min_flops) continue;
     float t = 0.f;
     CU(cudaEventElapsedTime(&t, h->prof_ev[i], h->prof_ev[i + 1]));
     ms += t;

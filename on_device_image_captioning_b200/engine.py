@@ -87,6 +87,12 @@ class Engine:
     def set_option(self, name: str, value: int):
         self._check(self.lib.xn_set_option(self._h, name.encode(), int(value)), "xn_set_option")
 
+    def profile_read_min(self, min_flops: float):
+        """(ms, flops, launches) of the event-timed tcgen05 GEMMs of at least `min_flops` FLOP each."""
+        ms, fl, n = C.c_double(), C.c_double(), C.c_int64()
+        self._check(self.lib.xn_profile_read_min(self._h, float(min_flops), C.byref(ms), C.byref(fl), C.byref(n)), "xn_profile_read_min")
+        return ms.value, fl.value, n.value
+
     def profile_kernels(self):
         """{launcher: (launches, total_ms)} of every kernel launch since set_option('profile', 2)."""
         buf = C.create_string_buffer(1 << 16)
