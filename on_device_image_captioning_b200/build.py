@@ -36,6 +36,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(objdir, exist_ok=True)
     nvcc = _nvcc()
     flags = [f for f in NVCC_FLAGS if not f.startswith("--use_fast_math")]
+    flags += os.environ.get("XNV2_NVCC_EXTRA", "").split()
     procs = []
     objs = []
     for src in SOURCES:

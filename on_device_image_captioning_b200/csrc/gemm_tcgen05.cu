@@ -186,20 +186,21 @@ __device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&v)[3
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-// GELU(erf) for outputs that are rounded to 16 bits anyway:  gelu(x) = x * Phi(x) = x / (1 + exp(-logit(Phi(x)))),
-// with the odd function logit(Phi(x)) fitted by x * (a0 + a1 x^2 + a2 x^4) on |x| <= 5 (x^2 clamped beyond, where the
-// sigmoid is saturated): max |error| 3.0e-5 absolute (fit in tools/fit_gelu.py), an order of magnitude below the
-// output rounding, for 7 FP32 instructions + 2 MUFU ops (ex2, rcp) instead of 16 + 2 for the Abramowitz-Stegun erfc.
-// The epilogue of the GELU GEMMs is issue/power-bound, so the instruction count is what matters.  The fp32 parity
-// mode keeps erff().
+// GELU(erf) for outputs that are rounded to 16 bits anyway:  gelu(x) = x * Phi(x) = x * sigmoid(u) = 0.5 x (1 + tanh(u / 2))
+// with u = logit(Phi(x)), an odd function fitted by x * (a0 + a1 x^2 + a2 x^4) on |x| <= 5 (x^2 clamped beyond, where the
+// sigmoid is saturated): max |error| of the fit 3.0e-5 absolute (tools/fit_gelu.py), an order of magnitude below the
+// output rounding; tanh.approx.f32 adds 2^-11 relative.  7 FP32 instructions + 1 MUFU op per element, against 16 + 2
+// for the Abramowitz-Stegun erfc it replaced (and 7 + 2 for the ex2/rcp form of the same sigmoid): the epilogue of the
+// GELU GEMMs is issue/MUFU/power-bound, so the instruction count is what matters.  Measured: fc1 launches -8..-27 %,
+// fp16 Swin features 8.2e-4 rel-fro before and after (profiles/).  The fp32 parity mode keeps erff().
 __device__ __forceinline__ float gelu_fast(float x) {
   const float x2 = fminf(x * x, 25.0f);
-  float q = fmaf(-0.000717442621f * -1.4426950408889634f, x2, 0.0741005620f * -1.4426950408889634f);
-  q = fmaf(q, x2, 1.59491707f * -1.4426950408889634f);
-  float e, r;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(q * x));        // exp(-logit Phi(x))
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
-  return x * r;
+  float q = fmaf(-0.000717442621f * 0.5f, x2, 0.0741005620f * 0.5f);
+  q = fmaf(q, x2, 1.59491707f * 0.5f);
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(q * x));
+  const float hx = 0.5f * x;
+  return fmaf(hx, t, hx);
 }
 
 // UMMA shared-memory descriptor, K-major operand, 128-byte swizzle (cute::UMMA::SmemDescriptor):
