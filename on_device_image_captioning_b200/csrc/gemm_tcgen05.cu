@@ -892,11 +892,11 @@ cudaError_t launch_gemm_tc(const TcGemmArgs& p, cudaStream_t st) {
   const long tiles256 = (long)((p.M + kBM - 1) / kBM) * ((p.N + 255) / 256);
   if (tiles256 * 2 <= sm_count()) best = 128;
   // CTA pairs where the main loop is the limit: at least one full wave of 256-row pair tiles and a long contraction.
-  // Measured at 32 images per chunk (profiles/): K = 3072 +8 %, K = 768 with 16-bit output +8 %, 8192^3 +10 %;
-  // short-K / epilogue-bound shapes (stage 1-2, GELU or fp32+residual epilogues at K <= 768) lose 5-40 % to the pair's
-  // coupled epilogues, so they stay on single-CTA tiles.
+  // Measured (profiles/): K = 3072 +8 %, K = 768 with 16-bit output +8 % (+6 % with the GELU epilogue once that became
+  // cheap), 8192^3 +10 %; short-K / epilogue-bound shapes (stage 1-2, fp32+residual epilogues at K <= 768) lose 5-40 % to
+  // the pair's coupled epilogues, so they stay on single-CTA tiles.
   const long pair_tiles = (long)((p.M + 2 * kBM - 1) / (2 * kBM)) * ((p.N + best - 1) / best);
-  const bool long_k = p.K >= 1536 || (p.K >= 768 && p.Cb != nullptr && p.act != 1);
+  const bool long_k = p.K >= 1536 || (p.K >= 768 && p.Cb != nullptr);
   if (g_tc_pair && long_k && pair_tiles >= sm_count() / 2) {
     if (best == 256) return launch_tc_bn<256, 2>(p, st);
     if (best == 192) return launch_tc_bn<192, 2>(p, st);
