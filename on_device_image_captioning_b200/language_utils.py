@@ -1,40 +1,38 @@
-"""Mirror of the detokenisation helpers of the reference's utils/language_utils.py:60-93 (same names, same results),
-plus the batched form the accelerated path returns its captions in.  Host-side string work: there is nothing to
-accelerate, it only has to keep the reference's exact rules (skip SOS, stop at EOS, final full stop, capitalise)."""
+"""Detokenisation helpers with the names and results of the reference's utils/language_utils.py:60-93, plus the batched
+form the accelerated path returns its captions in.  Host-side string work -- nothing to accelerate; it only has to keep
+the reference's rules: SOS tokens are dropped wherever they occur, the caption ends at the first EOS, the last word gets
+a full stop, and the sentence is capitalised with str.capitalize() (which also lower-cases the rest)."""
 from __future__ import annotations
 
-from typing import List, Sequence
+from itertools import takewhile
+from typing import Dict, List, Sequence
 
 
-def convert_vector_word2idx(sentence, word2idx_dict):
-    return [word2idx_dict[word] for word in sentence]
+def convert_vector_word2idx(sentence: Sequence[str], word2idx_dict: Dict[str, int]) -> List[int]:
+    return list(map(word2idx_dict.__getitem__, sentence))
 
 
 def convert_allsentences_word2idx(sentences, word2idx_dict):
-    return [convert_vector_word2idx(s, word2idx_dict) for s in sentences]
+    return [convert_vector_word2idx(one, word2idx_dict) for one in sentences]
 
 
-def convert_vector_idx2word(sentence, idx2word_list):
-    return [idx2word_list[idx] for idx in sentence]
+def convert_vector_idx2word(sentence: Sequence[int], idx2word_list: Sequence[str]) -> List[str]:
+    return list(map(idx2word_list.__getitem__, sentence))
 
 
 def convert_allsentences_idx2word(sentences, idx2word_list):
-    return [convert_vector_idx2word(s, idx2word_list) for s in sentences]
+    return [convert_vector_idx2word(one, idx2word_list) for one in sentences]
 
 
-def tokens2description(tokens, idx2word_list, sos_idx, eos_idx):
-    """reference utils/language_utils.py:82-93 (raises IndexError on a caption without words, like the reference)."""
-    desc = []
-    for tok in tokens:
-        if tok == sos_idx:
-            continue
-        if tok == eos_idx:
-            break
-        desc.append(tok)
-    desc = convert_vector_idx2word(desc, idx2word_list)
-    desc[-1] = desc[-1] + "."
-    pred = " ".join(desc).capitalize()
-    return pred
+def tokens2description(tokens, idx2word_list, sos_idx, eos_idx) -> str:
+    """Token ids -> caption string.  A caption without any word raises IndexError, as the reference does (its
+    ``desc[-1]`` on an empty list)."""
+    body = [t for t in takewhile(lambda t: t != eos_idx, tokens) if t != sos_idx]
+    words = convert_vector_idx2word(body, idx2word_list)
+    if not words:
+        raise IndexError("list index out of range")
+    words[-1] += "."
+    return " ".join(words).capitalize()
 
 
 def batch_tokens2description(tokens, lengths, idx2word_list, sos_idx, eos_idx) -> List[str]:
@@ -42,4 +40,4 @@ def batch_tokens2description(tokens, lengths, idx2word_list, sos_idx, eos_idx) -
     best caption string of every image (one device->host copy for the whole batch)."""
     tok = tokens.cpu().tolist() if hasattr(tokens, "cpu") else tokens
     ln = lengths.cpu().tolist() if hasattr(lengths, "cpu") else lengths
-    return [tokens2description(tok[b][0][: ln[b][0]], idx2word_list, sos_idx, eos_idx) for b in range(len(tok))]
+    return [tokens2description(row[0][: n[0]], idx2word_list, sos_idx, eos_idx) for row, n in zip(tok, ln)]
