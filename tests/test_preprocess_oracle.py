@@ -66,3 +66,15 @@ def test_feature_store_layout(tmp_path):
     assert F.feature_key(391895) == "391895_features"
     assert np.array_equal(F.read_features(path, 391895), a) and np.array_equal(F.read_features(path, 42), b)
     assert F.read_features(path, 42).dtype == np.float32
+
+
+def test_detokenisation_matches_reference_known_answers():
+    """tests/golden/detok_cases.json: outputs of the reference's tokens2description (made by make_detok_golden.py)."""
+    from on_device_image_captioning_b200 import language_utils as L
+    g = json.load(open(os.path.join(GOLDEN_DIR, "detok_cases.json")))
+    for c in g["cases"]:
+        if c["caption"] is None:
+            with pytest.raises(IndexError):
+                L.tokens2description(c["tokens"], g["vocab"], g["sos"], g["eos"])
+        else:
+            assert L.tokens2description(c["tokens"], g["vocab"], g["sos"], g["eos"]) == c["caption"]
