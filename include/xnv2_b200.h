@@ -11,6 +11,9 @@
  * on_device_image_captioning_b200/ binds these symbols with ctypes and re-exposes the
  * reference's class/method signatures.
  *
+ * Beyond the hot path: xn_preprocess_rgb8 (utils/image_utils.py), xn_ensemble_beam_search
+ * (models/ensemble_captioning_model.py).
+ *
  * Conventions: every call returns 0 on success and a negative code on failure (never
  * throws); xn_last_error() gives the message.  All tensor arguments are caller-owned
  * DEVICE pointers unless the name says host; work is enqueued on the given CUDA stream
@@ -122,7 +125,17 @@ int xn_preprocess_rgb8(xn_handle* h, const uint8_t* rgb, int rgb_on_device, int 
 
 int64_t xn_kernel_launches(const xn_handle* h);      /* kernels of this library launched so far */
 int64_t xn_workspace_bytes(const xn_handle* h);
-int xn_set_option(xn_handle* h, const char* name, int64_t value);   /* "swin_chunk", "enc_chunk", "profile" */
+/* Tuning / measurement switches (defaults are the measured best; see DESIGN.md and profiles/README.md):
+ *   "swin_chunk", "enc_chunk"  images per Swin / encoder chunk (64)
+ *   "use_graph"                1: calls are captured into a CUDA graph on their second occurrence and replayed
+ *   "decode_groups"            image groups decoded on concurrent graph branches (0 = automatic: 2 from 32 images)
+ *   "pdl"                      programmatic dependent launch (process-wide)
+ *   "tc_pair"                  CTA-pair (cta_group::2) GEMM tiles for long-K shapes (process-wide)
+ *   "use_skinny"               skinny mma.sync GEMM for decoder-step linears with <= 64 rows
+ *   "ln_on_load"               LayerNorm folded into the consuming tcgen05 GEMM (off: measured slower)
+ *   "profile"                  1: event-time every tcgen05 GEMM; 2: event-time every kernel launch (both disable graphs)
+ *   "tc_debug", "op_out16"     kernel timing experiments / test hooks */
+int xn_set_option(xn_handle* h, const char* name, int64_t value);
 /* With option "profile"=1 every tcgen05 GEMM launch is bracketed by CUDA events on its stream;
  * this returns the summed device time, the summed algorithmic FLOPs and the launch count since
  * the option was set (synchronises the device). */
