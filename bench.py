@@ -309,6 +309,29 @@ def run_ours(args):
                 if i >= 3:
                     ts.append(a.elapsed_time(b))
             lat[name + "_p50_ms"] = statistics.median(ts)
+        # ---- config-5 comparator (no TensorRT / ONNX runtime on this image, so the substitute is the
+        # reference ALGORITHM in eager PyTorch ops on this B200, fp32): the oracle port run with CUDA tensors -- whole-prefix
+        # re-decode, dense masks, one stream of small torch kernels.  A baseline next to latency_batch1, not a product path.
+        if not args.no_cpu and world == 1:
+            try:
+                from oracle import xnv2_oracle as O
+                sd_dev = {k: v.to(dev) for k, v in synth.make_state_dict(cfg, 0, "xavier").items()}
+                torch.backends.cuda.matmul.allow_tf32 = False
+                torch.backends.cudnn.allow_tf32 = False
+                ts = []
+                with torch.no_grad(), torch.device(dev):
+                    for i in range(3):
+                        torch.cuda.synchronize()
+                        t0 = time.perf_counter()
+                        O.beam_search(sd_dev, cfg, one, [0], SOS, EOS, BEAM, 1, MAX_LEN)
+                        torch.cuda.synchronize()
+                        if i:
+                            ts.append((time.perf_counter() - t0) * 1e3)
+                lat["reference_algorithm_torch_eager_on_this_gpu_beam3_ms"] = statistics.median(ts)
+                del sd_dev
+            except Exception as ex:            # a comparator must never take the bench line down
+                lat["reference_algorithm_torch_eager_on_this_gpu_beam3_ms"] = None
+                note(f"torch-eager comparator skipped: {ex}")
         # ---- CPU baseline: bounded sample on this host's cores
         threads = os.cpu_count() or 1
         # reported at N = 1 only (the other ranks' processes share these host cores at N > 1)
