@@ -328,7 +328,17 @@ def run_ours(args):
                         if i:
                             ts.append((time.perf_counter() - t0) * 1e3)
                 lat["reference_algorithm_torch_eager_on_this_gpu_beam3_ms"] = statistics.median(ts)
+                # and the bench workload itself (one batch of B images) through the same eager path
+                with torch.no_grad(), torch.device(dev):
+                    for i in range(2):
+                        torch.cuda.synchronize()
+                        t0 = time.perf_counter()
+                        O.beam_search(sd_dev, cfg, devin[0], [0] * B, SOS, EOS, BEAM, 1, MAX_LEN)
+                        torch.cuda.synchronize()
+                        eager_dt = time.perf_counter() - t0
+                lat["reference_algorithm_torch_eager_on_this_gpu_captions_per_s_batch%d" % B] = B / eager_dt
                 del sd_dev
+                torch.cuda.empty_cache()
             except Exception as ex:            # a comparator must never take the bench line down
                 lat["reference_algorithm_torch_eager_on_this_gpu_beam3_ms"] = None
                 note(f"torch-eager comparator skipped: {ex}")
