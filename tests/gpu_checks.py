@@ -329,6 +329,21 @@ def check_preprocess() -> List[Triple]:
         y_dev = e.preprocess_rgb8([torch.from_numpy(img).cuda()], S)[0].cpu().numpy()
         out.append((f"preprocess[{H}x{W}->{S}] elements differing from the oracle (host input)", float((y_host != ref).sum()), 0.0))
         out.append((f"preprocess[{H}x{W}->{S}] elements differing from the oracle (device input)", float((y_dev != ref).sum()), 0.0))
+    # the file-level mirror of utils/image_utils.py:preprocess_image: PNG files (lossless), including the reference's rule
+    # that a non-RGB file is replaced by a blank RGB canvas of the same size (:18-19)
+    import tempfile
+    from PIL import Image
+    from on_device_image_captioning_b200.image_utils import preprocess_image
+    from test_preprocess_oracle import reference_preprocess
+    with tempfile.TemporaryDirectory() as td:
+        rgb = synth_image(211, 333, 5)
+        Image.fromarray(rgb, "RGB").save(td + "/a.png")
+        Image.fromarray(rgb[..., 0], "L").save(td + "/gray.png")
+        y = preprocess_image(td + "/a.png", 96, e)[0].cpu().numpy()
+        out.append(("preprocess_image(RGB png) elements differing from Pillow + torchvision", float((y != reference_preprocess(rgb, 96)).sum()), 0.0))
+        yg = preprocess_image(td + "/gray.png", 96, e)[0].cpu().numpy()
+        blank = reference_preprocess(np.zeros((211, 333, 3), dtype=np.uint8), 96)
+        out.append(("preprocess_image(grayscale png -> blank canvas rule) elements differing", float((yg != blank).sum()), 0.0))
     imgs = [synth_image(h, w, 7 * h + w) for (h, w) in [(300, 400), (480, 640), (200, 200)]]
     yb = e.preprocess_rgb8(imgs, 96).cpu().numpy()
     bad = sum(int((yb[i] != P.preprocess_rgb8(im, 96)).sum()) for i, im in enumerate(imgs))
