@@ -89,7 +89,9 @@ int xn_forward_dec(xn_handle* h, const float* cross, int R, const int32_t* enc_p
                    int apply_log_softmax, float* out, void* stream);
 
 /* Replaces: beam_search, 'max' branch (legacy_models/captioning_model.py:111-241 ==
- * models/captioning_model.py:220-427), including forward_enc.
+ * models/captioning_model.py:220-427), including forward_enc.  Limits (XN_ERR_ARG beyond them): 1 <= how_many <= beam <= 8,
+ * 2 <= max_len <= min(max_seq_len, 128).  `input` may be any device tensor: it is copied into a handle-owned staging
+ * buffer first, so the call's cached CUDA graph does not depend on the caller's address.
  * out_tokens  (B,how_many,max_len) i32, -1 padded, SOS..EOS inclusive
  * out_len     (B,how_many) i32
  * out_logprob (B,how_many,max_len) f32, 0 padded                                        */
@@ -108,6 +110,40 @@ int xn_caption_host(xn_handle* h, const float* input_host, int B, int beam, int 
                     int sos_idx, int eos_idx, int32_t* out_tokens_host, int32_t* out_len_host,
                     float* out_logprob_host, void* stream);
 
+/* Pipelined form of xn_caption_host for a caller that streams batches (bench.py's e2e leg at N GPUs): _begin enqueues
+ * the host-to-device copy of this batch on the handle's copy stream, the search on `stream` and the device-to-host copies
+ * of the results, and returns a ticket (0 or 1) without waiting; _end(ticket) blocks until that call's results are in the
+ * host buffers.  Two calls may be in flight: the copy of batch i+1 overlaps the compute of batch i (two staging slots).
+ * The host buffers of a call must stay valid and untouched until its _end.  Pinned host memory is needed for overlap. */
+int xn_caption_host_begin(xn_handle* h, const float* input_host, int B, int beam, int max_len, int how_many,
+                          int sos_idx, int eos_idx, int32_t* out_tokens_host, int32_t* out_len_host,
+                          float* out_logprob_host, void* stream);      /* >= 0: ticket; < 0: error */
+int xn_caption_host_end(xn_handle* h, int ticket);
+
+/* Replaces: beam_search with sample_or_max='sample' (legacy_models/captioning_model.py:131-133,168-170 ==
+ * models/captioning_model.py:256-260,305-308): the per-step candidates of every beam are `beam` draws WITHOUT replacement
+ * from its word distribution (torch.multinomial(exp(log_probs), beam, replacement=False)) instead of the top-k; the rest
+ * of the search is xn_beam_search's.  Draws come from a counter-based generator keyed on (seed, row, step, word): the
+ * same seed reproduces the same captions; the distribution, not torch's random stream, is what is matched. */
+int xn_beam_search_sample(xn_handle* h, const float* input, int B, const int32_t* enc_pads_host, int beam, int max_len,
+                          int how_many, int sos_idx, int eos_idx, uint64_t seed, int32_t* out_tokens, int32_t* out_len,
+                          float* out_logprob, void* stream);
+/* Replaces: mode='sampling' -> get_batch_multiple_sampled_prediction (legacy_models/captioning_model.py:60-109 ==
+ * models/captioning_model.py:120-218; the SCST sampler, train.py:146-151): num_outputs (<= 8) independent ancestral
+ * samples per image, one Categorical draw per step, up to max_len sampled words after SOS.
+ * out_tokens  (B,num_outputs,max_len+1) i32, -1 padded: SOS .. first sampled EOS inclusive (all max_len+1 if none)
+ * out_len     (B,num_outputs) i32
+ * out_logprob (B,num_outputs,max_len+1) f32: log-probability of every sampled word, 0 at SOS and after the first EOS */
+int xn_sample(xn_handle* h, const float* input, int B, const int32_t* enc_pads_host, int num_outputs, int max_len,
+              int sos_idx, int eos_idx, uint64_t seed, int32_t* out_tokens, int32_t* out_len, float* out_logprob,
+              void* stream);
+
+/* 16-bit modes store QKV, attention outputs and MLP hidden activations as fp16 / bf16.  fp16 tops out at 65504: if a
+ * checkpoint's activations exceed that, infinities reach the encoder output as NaN.  Every xn_forward_enc / xn_beam_search
+ * / xn_caption_host call in a 16-bit mode checks its encoder output on the device and raises this flag when it holds a
+ * non-finite value.  Reads (and optionally clears) the flag; synchronises the device.  Remedy: XN_PREC_BF16 or FP32. */
+int xn_overflow_flag(xn_handle* h, int* flag_out, int clear);
+
 /* Counters / introspection. */
 /* Ensemble beam search (replaces EsembleCaptioningModel.forward(mode="beam_search"),
  * legacy_models/ensemble_captioning_model.py:19-241, built at test.py:334): up to 8 handles on one device with the same
@@ -122,6 +158,12 @@ int xn_ensemble_beam_search(xn_handle* const* handles, int n_models, const float
  * Pillow's antialiased bilinear resize + torchvision's float32 tail.  `rgb` is a host pointer (rgb_on_device = 0: copied
  * inside the call, stream-ordered) or a device pointer; `out` is device memory.  Any H, W >= 1; S = out_size. */
 int xn_preprocess_rgb8(xn_handle* h, const uint8_t* rgb, int rgb_on_device, int H, int W, float* out, int out_size, void* stream);
+/* Batched form: n images of arbitrary sizes in ONE launch pair, no per-image synchronisation.  rgb_ptrs: n pointers (all
+ * host or all device, per rgb_on_device), heights / widths: n host ints, out: (n,3,S,S) f32 device.  Host images are
+ * copied inside the call, stream-ordered (pageable memory is staged by the driver; pinned memory must stay valid until
+ * the stream has passed the call). */
+int xn_preprocess_rgb8_batch(xn_handle* h, const uint8_t* const* rgb_ptrs, int rgb_on_device, const int32_t* heights,
+                             const int32_t* widths, int n, float* out, int out_size, void* stream);
 
 int64_t xn_kernel_launches(const xn_handle* h);      /* kernels of this library launched so far */
 int64_t xn_workspace_bytes(const xn_handle* h);

@@ -43,6 +43,12 @@ _SIGNATURES = {
     "xn_ensemble_beam_search": (C.c_int, [C.POINTER(_P), _I, _P, _I, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P]),
     "xn_caption_host": (C.c_int, [_P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P]),
     "xn_preprocess_rgb8": (C.c_int, [_P, _P, _I, _I, _I, _P, _I, _P]),
+    "xn_preprocess_rgb8_batch": (C.c_int, [_P, C.POINTER(_P), _I, C.POINTER(C.c_int32), C.POINTER(C.c_int32), _I, _P, _I, _P]),
+    "xn_caption_host_begin": (C.c_int, [_P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P]),
+    "xn_caption_host_end": (C.c_int, [_P, _I]),
+    "xn_beam_search_sample": (C.c_int, [_P, _P, _I, _P, _I, _I, _I, _I, _I, C.c_uint64, _P, _P, _P, _P]),
+    "xn_sample": (C.c_int, [_P, _P, _I, _P, _I, _I, _I, _I, C.c_uint64, _P, _P, _P, _P]),
+    "xn_overflow_flag": (C.c_int, [_P, C.POINTER(C.c_int), _I]),
     "xn_kernel_launches": (C.c_int64, [_P]),
     "xn_workspace_bytes": (C.c_int64, [_P]),
     "xn_set_option": (C.c_int, [_P, C.c_char_p, C.c_int64]),

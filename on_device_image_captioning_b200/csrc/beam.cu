@@ -157,6 +157,50 @@ __global__ void beam_finalize_kernel(BeamBufs bb, int src, int B, int beam, int 
   }
 }
 
+// ---- mode='sampling' (legacy_models/captioning_model.py:60-109): every row is an independent sample path.  bb.*[0]
+// holds the histories; len = where_is_eos + 1 (position of the first sampled EOS, inclusive) once EOS has been drawn,
+// otherwise the number of tokens so far.  The reference keeps sampling finished rows and cuts afterwards (:96-107); so
+// does this kernel -- the tokens after EOS are stored and ignored by the finaliser.
+__global__ void sample_append_kernel(BeamBufs bb, const float* __restrict__ top_val, const int* __restrict__ top_idx, int R, int L,
+                                     int t, int eos) {
+  pdl_wait();
+  pdl_trigger();
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= R) return;
+  const int tok = top_idx[r];
+  bb.tokens[0][(long)r * L + t] = tok;
+  bb.lps[0][(long)r * L + t] = top_val[r];
+  bb.anc[0][(long)r * L + t] = r;
+  if (!bb.eos[0][r]) {
+    bb.len[0][r] = t + 1;
+    if (tok == eos) bb.eos[0][r] = 1;
+  }
+}
+
+// tokens [:where_is_eos + 1], log-probs zeroed after the first EOS (:99-107); -1 / 0 padded to L
+__global__ void sample_finalize_kernel(BeamBufs bb, int R, int L, int t_final, int* __restrict__ out_tokens,
+                                       int* __restrict__ out_len, float* __restrict__ out_lp) {
+  pdl_wait();
+  pdl_trigger();
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= R) return;
+  const int n = min(bb.len[0][r], t_final);
+  out_len[r] = n;
+  for (int i = 0; i < L; ++i) {
+    out_tokens[(long)r * L + i] = i < n ? bb.tokens[0][(long)r * L + i] : -1;
+    out_lp[(long)r * L + i] = i < n ? bb.lps[0][(long)r * L + i] : 0.f;
+  }
+}
+
+cudaError_t launch_sample_append(const BeamBufs& bb, const float* top_val, const int* top_idx, int R, int L, int t, int eos,
+                                 cudaStream_t st) {
+  return launch_k(sample_append_kernel, dim3((R + 127) / 128), dim3(128), 0, st, bb, top_val, top_idx, R, L, t, eos);
+}
+cudaError_t launch_sample_finalize(const BeamBufs& bb, int R, int L, int t_final, int* out_tokens, int* out_len, float* out_lp,
+                                   cudaStream_t st) {
+  return launch_k(sample_finalize_kernel, dim3((R + 127) / 128), dim3(128), 0, st, bb, R, L, t_final, out_tokens, out_len, out_lp);
+}
+
 cudaError_t launch_beam_init(const BeamBufs& bb, int B, int beam, int L, int sos, cudaStream_t st) {
   if (beam > kMaxBeam) return cudaErrorInvalidValue;
   launch_k(beam_init_kernel, dim3((B * beam + 127) / 128), dim3(128), 0, st, bb, B, beam, L, sos);

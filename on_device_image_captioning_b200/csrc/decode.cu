@@ -828,6 +828,100 @@ __global__ void __launch_bounds__(256) logsoftmax_topk_reg_kernel(const float* _
   }
 }
 
+// ---- sampling: Gumbel-top-k over the row's log-probabilities (see kernels.h).  Philox4x32-10 keyed on the seed, counter
+// (vocabulary block of 4, row, step): four uniforms per call, one per vocabulary entry.
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+#pragma unroll
+  for (int i = 0; i < 10; ++i) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+    c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+    k.x += 0x9E3779B9u; k.y += 0xBB67AE85u;
+  }
+  return c;
+}
+__device__ __forceinline__ float gumbel_from_bits(uint32_t r) {
+  const float u = ((float)(r >> 8) + 0.5f) * (1.0f / 16777216.0f);       // (0, 1) strictly, 24 bits
+  return -logf(-logf(u));
+}
+
+__global__ void __launch_bounds__(256) gumbel_topk_kernel(const float* __restrict__ logits, long ld, int V, int k, uint2 seed, int step,
+                                                          float* __restrict__ top_val, int* __restrict__ top_idx) {
+  pdl_wait();
+  pdl_trigger();
+  __shared__ float red[32];
+  __shared__ float cv[256];
+  __shared__ int ci[256];
+  __shared__ int win_tid;
+  const int r = blockIdx.x, tid = threadIdx.x;
+  const float* x = logits + (long)r * ld;
+  float lmax = -INFINITY;
+  for (int i = tid; i < V; i += 256) lmax = fmaxf(lmax, x[i]);
+  const float mx = block_max(lmax, red);
+  float ls = 0.f;
+  for (int i = tid; i < V; i += 256) ls += expf(x[i] - mx);
+  const float lse = logf(block_sum(ls, red));
+  __syncthreads();
+  float tv[kMaxTopK];
+  int ti[kMaxTopK];
+#pragma unroll
+  for (int j = 0; j < kMaxTopK; ++j) { tv[j] = -INFINITY; ti[j] = 0x7fffffff; }
+  for (int i4 = tid; i4 * 4 < V; i4 += 256) {
+    const uint4 rb = philox4x32_10(make_uint4((uint32_t)i4, (uint32_t)r, (uint32_t)step, 0x58433242u), seed);
+    const uint32_t bits[4] = {rb.x, rb.y, rb.z, rb.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int i = i4 * 4 + e;
+      if (i >= V) break;
+      const float v = ((x[i] - mx) - lse) + gumbel_from_bits(bits[e]);
+      if (better(v, i, tv[kMaxTopK - 1], ti[kMaxTopK - 1])) {
+        tv[kMaxTopK - 1] = v; ti[kMaxTopK - 1] = i;
+#pragma unroll
+        for (int j = kMaxTopK - 1; j > 0; --j) {
+          if (better(tv[j], ti[j], tv[j - 1], ti[j - 1])) {
+            const float fv = tv[j]; tv[j] = tv[j - 1]; tv[j - 1] = fv;
+            const int fi = ti[j]; ti[j] = ti[j - 1]; ti[j - 1] = fi;
+          }
+        }
+      }
+    }
+  }
+  for (int round = 0; round < k; ++round) {
+    cv[tid] = tv[0]; ci[tid] = ti[0];
+    __syncthreads();
+    if (tid < 32) {
+      float bv = -INFINITY; int bi = 0x7fffffff, bt = 0;
+      for (int t = tid; t < 256; t += 32)
+        if (better(cv[t], ci[t], bv, bi)) { bv = cv[t]; bi = ci[t]; bt = t; }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        const int ot = __shfl_xor_sync(0xffffffffu, bt, o);
+        if (better(ov, oi, bv, bi)) { bv = ov; bi = oi; bt = ot; }
+      }
+      if (tid == 0) {
+        top_val[(long)r * k + round] = (x[bi] - mx) - lse;       // the word's own log-probability, not the perturbed key
+        top_idx[(long)r * k + round] = bi;
+        win_tid = bt;
+      }
+    }
+    __syncthreads();
+    if (tid == win_tid) {
+#pragma unroll
+      for (int j = 0; j < kMaxTopK - 1; ++j) { tv[j] = tv[j + 1]; ti[j] = ti[j + 1]; }
+      tv[kMaxTopK - 1] = -INFINITY; ti[kMaxTopK - 1] = 0x7fffffff;
+    }
+    __syncthreads();
+  }
+}
+cudaError_t launch_gumbel_topk(const float* logits, long ld, int rows, int V, int k, uint64_t seed, int step, float* top_val,
+                               int* top_idx, cudaStream_t st) {
+  if (k < 1 || k > kMaxTopK || k > V) return cudaErrorInvalidValue;
+  return launch_k(gumbel_topk_kernel, dim3(rows), dim3(256), 0, st, logits, ld, V, k,
+                  make_uint2((uint32_t)(seed & 0xffffffffu), (uint32_t)(seed >> 32)), step, top_val, top_idx);
+}
+
 // Ensemble step distribution (reference legacy_models/ensemble_captioning_model.py:55-84):
 //   lp = log( mean_m softmax(logits_m) ),  softmax_m = exp(x - max_m) / sum_m,  mean = (p_0 + p_1 + ...) / n in model order.
 // One CTA per row; each model's row is read twice from L2 (statistics, then the combination).

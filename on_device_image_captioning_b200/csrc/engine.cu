@@ -18,6 +18,7 @@
 using namespace xn;
 
 cudaError_t launch_widen_16(const void* x, float* y, long n, int fp16, cudaStream_t st);
+cudaError_t launch_nonfinite_flag(const float* x, long n, int* flag, cudaStream_t st);
 
 namespace {
 
@@ -92,8 +93,16 @@ struct xn_handle {
              eos == o.eos && ws_base == o.ws_base && ws_cap == o.ws_cap;
     }
   };
-  struct CachedGraph { GraphKey key; cudaGraphExec_t exec; int64_t launches; };
-  std::vector<CachedGraph> graphs;
+  // `h2d`: the host-to-device copy nodes of a captured xn_caption_host call (offset of their source inside the caller's
+  // host buffer); on replay with another host buffer their source pointers are patched in place, so the graph does not
+  // depend on the caller's buffer address.  The cudaGraph_t is kept alive because the node handles belong to it.
+  struct H2DNode { cudaGraphNode_t node; void* dst; size_t src_off, bytes; };
+  struct CachedGraph {
+    GraphKey key; cudaGraphExec_t exec; int64_t launches;
+    cudaGraph_t graph = nullptr; const char* host_base = nullptr; std::vector<H2DNode> h2d;
+  };
+  static constexpr size_t kMaxGraphs = 16;
+  std::vector<CachedGraph> graphs;   // least recently used first
   int64_t use_graph = 1;
   int64_t op_out16 = 0;
   int64_t use_skinny = 1;
@@ -115,8 +124,18 @@ struct xn_handle {
   cudaEvent_t c_fork = nullptr, c_ev[kMaxCopyChunks] = {};            // decoder-step linears on gemm_skinny.cu when rows <= 512 (16-bit modes)
   cudaStream_t gstream = nullptr;      // graphs are captured/replayed here (the caller's stream may be the legacy
   cudaEvent_t g_in = nullptr, g_out = nullptr;   // default stream, which cannot be captured); ordered with events
+  void reset_side_streams() {
+    for (int g = 0; g < kMaxDecodeGroups; ++g)
+      if (dstream[g]) { cudaStreamDestroy(dstream[g]); cudaStreamCreateWithFlags(&dstream[g], cudaStreamNonBlocking); }
+    if (cstream) { cudaStreamDestroy(cstream); cudaStreamCreateWithFlags(&cstream, cudaStreamNonBlocking); }
+  }
+  static void destroy_graph(CachedGraph& g) {
+    if (g.exec) cudaGraphExecDestroy(g.exec);
+    if (g.graph) cudaGraphDestroy(g.graph);
+    g.exec = nullptr; g.graph = nullptr;
+  }
   void drop_graphs() {
-    for (auto& g : graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
+    for (auto& g : graphs) destroy_graph(g);
     graphs.clear();
   }
   // optional per-launch event timing of the tcgen05 GEMMs (bench.py roofline leg)
@@ -134,10 +153,24 @@ struct xn_handle {
     cudaEvent_t e = span_pool.back(); span_pool.pop_back(); return e;
   }
   float* io_in = nullptr; size_t io_in_cap = 0;     // xn_caption_host staging
+  // xn_caption_host_begin / _end: two slots (input staging, result staging, events) so that the host-to-device copy of
+  // call i+1 runs on the copy stream while call i computes
+  struct HostSlot { float* in = nullptr; size_t in_cap = 0; char* out = nullptr; size_t out_cap = 0;
+                    cudaEvent_t ev_in = nullptr, ev_done = nullptr; bool pending = false; };
+  HostSlot slots[2];
+  int next_slot = 0;
+  cudaStream_t hstream = nullptr;
+  // set by a device-side check of the encoder output in the 16-bit modes: a non-finite value there means an fp16
+  // intermediate overflowed somewhere in the backbone (xn_overflow_flag)
+  int* flag_dev = nullptr;
+  const float* staged_input = nullptr;   // set around a call whose device input already lives in a handle-owned buffer
   // xn_preprocess_rgb8: coefficient tables per (input size, output size), staging for the image and the first pass
   struct ResampleTable { int in_size, out_size, ksize; int* bounds; int* kk; };
+  static constexpr size_t kMaxResampleTables = 64;
   std::vector<ResampleTable> rtables;
   uint8_t* pp_buf = nullptr; size_t pp_cap = 0;
+  char* pp_host = nullptr; size_t pp_host_cap = 0;   // pinned staging of a preprocessing batch's item records + tables
+  cudaEvent_t pp_ev = nullptr;
   char* io_out = nullptr; size_t io_out_cap = 0;
 
   int fail(int code, const char* fmt, ...) {
@@ -171,6 +204,20 @@ struct xn_handle {
   } while (0)
 
 namespace {
+
+// device staging of the call's input: captured graphs read it, so a reallocation invalidates them
+int ensure_io_in(xn_handle* h, size_t bytes) {
+  if (h->io_in_cap >= bytes) return 0;
+  if (h->io_in) {
+    CU(cudaDeviceSynchronize());
+    h->drop_graphs();
+    cudaFree(h->io_in);
+    h->io_in = nullptr; h->io_in_cap = 0;
+  }
+  CU(cudaMalloc(&h->io_in, bytes));
+  h->io_in_cap = bytes;
+  return 0;
+}
 
 int ensure_ws(xn_handle* h, size_t bytes, cudaStream_t st) {
   bytes += 1 << 20;
@@ -733,7 +780,8 @@ int upload_ints(xn_handle* h, const std::vector<int>& v, int** dev, cudaStream_t
 // from the second identical call on, as a CUDA graph captured once and replayed on an internal stream that is ordered
 // with the caller's stream by events.
 template <typename F>
-int run_graphed(xn_handle* h, const xn_handle::GraphKey& key, bool allow_graph, cudaStream_t user_st, F&& body) {
+int run_graphed(xn_handle* h, const xn_handle::GraphKey& key, bool allow_graph, cudaStream_t user_st, F&& body,
+                const void* host_src = nullptr, size_t host_bytes = 0) {
   if (!(h->use_graph && allow_graph && !h->profile)) return body(user_st);
   if (!h->gstream) {
     CU(cudaStreamCreateWithFlags(&h->gstream, cudaStreamNonBlocking));
@@ -741,11 +789,20 @@ int run_graphed(xn_handle* h, const xn_handle::GraphKey& key, bool allow_graph, 
     CU(cudaEventCreateWithFlags(&h->g_out, cudaEventDisableTiming));
   }
   xn_handle::CachedGraph* g = nullptr;
-  for (auto& e : h->graphs)
-    if (e.key == key) { g = &e; break; }
+  for (size_t i = 0; i < h->graphs.size(); ++i)
+    if (h->graphs[i].key == key) {                  // most recently used entry lives at the back
+      if (i + 1 != h->graphs.size()) std::rotate(h->graphs.begin() + i, h->graphs.begin() + i + 1, h->graphs.end());
+      g = &h->graphs.back();
+      break;
+    }
   if (!g) {                                         // first sight: run eagerly, remember the shape
-    if (h->graphs.size() > 16) h->drop_graphs();
-    h->graphs.push_back({key, nullptr, 0});
+    if (h->graphs.size() >= xn_handle::kMaxGraphs) {          // evict the least recently used entry only
+      xn_handle::destroy_graph(h->graphs.front());
+      h->graphs.erase(h->graphs.begin());
+    }
+    xn_handle::CachedGraph fresh{};
+    fresh.key = key;
+    h->graphs.push_back(fresh);
     return body(user_st);
   }
   cudaStream_t st = h->gstream;                     // hand over from the caller's stream to the graph stream
@@ -757,13 +814,45 @@ int run_graphed(xn_handle* h, const xn_handle::GraphKey& key, bool allow_graph, 
     const int rr = body(st);
     cudaGraph_t graph = nullptr;
     cudaError_t ce = cudaStreamEndCapture(st, &graph);
-    if (rr) { if (graph) cudaGraphDestroy(graph); return rr; }
-    if (ce != cudaSuccess) return h->fail(XN_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(ce));
+    if (rr || ce != cudaSuccess) {
+      // a failed capture may leave forked side streams in an invalidated capture: recreate them before the next call
+      if (graph) cudaGraphDestroy(graph);
+      (void)cudaGetLastError();
+      h->reset_side_streams();
+      h->launches = l0;
+      if (rr) return rr;
+      return h->fail(XN_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(ce));
+    }
     g->launches = h->launches - l0;
     h->launches = l0;
     cudaError_t ie = cudaGraphInstantiate(&g->exec, graph, 0);
-    cudaGraphDestroy(graph);
-    if (ie != cudaSuccess) { g->exec = nullptr; return h->fail(XN_ERR_CUDA, "graph instantiate failed: %s", cudaGetErrorString(ie)); }
+    if (ie != cudaSuccess) { cudaGraphDestroy(graph); g->exec = nullptr; return h->fail(XN_ERR_CUDA, "graph instantiate failed: %s", cudaGetErrorString(ie)); }
+    g->graph = graph;
+    g->host_base = reinterpret_cast<const char*>(host_src);
+    g->h2d.clear();
+    if (host_src) {                                 // remember the copy nodes that read the caller's host buffer
+      size_t n_nodes = 0;
+      CU(cudaGraphGetNodes(graph, nullptr, &n_nodes));
+      std::vector<cudaGraphNode_t> nodes(n_nodes);
+      if (n_nodes) CU(cudaGraphGetNodes(graph, nodes.data(), &n_nodes));
+      const char* hb = reinterpret_cast<const char*>(host_src);
+      for (cudaGraphNode_t nd : nodes) {
+        cudaGraphNodeType ty;
+        CU(cudaGraphNodeGetType(nd, &ty));
+        if (ty != cudaGraphNodeTypeMemcpy) continue;
+        cudaMemcpy3DParms mp{};
+        CU(cudaGraphMemcpyNodeGetParams(nd, &mp));
+        const char* src = reinterpret_cast<const char*>(mp.srcPtr.ptr);
+        if (!src || src < hb || src >= hb + host_bytes) continue;
+        const size_t bytes = mp.extent.width * std::max<size_t>(1, mp.extent.height) * std::max<size_t>(1, mp.extent.depth);
+        g->h2d.push_back({nd, mp.dstPtr.ptr, (size_t)(src - hb), bytes});
+      }
+    }
+  } else if (host_src && g->host_base != reinterpret_cast<const char*>(host_src)) {
+    const char* hb = reinterpret_cast<const char*>(host_src);
+    for (auto& n : g->h2d)
+      CU(cudaGraphExecMemcpyNodeSetParams1D(g->exec, n.node, n.dst, hb + n.src_off, n.bytes, cudaMemcpyHostToDevice));
+    g->host_base = hb;
   }
   CU(cudaGraphLaunch(g->exec, st));
   h->launches += g->launches;
@@ -817,8 +906,12 @@ int beam_plan(xn_handle* h, BeamPlan& P, int B, const int32_t* enc_pads_host, in
   return 0;
 }
 
+// candidate selection of one step: top-k of the log-probabilities ('max'), or k draws without replacement ('sample',
+// reference captioning_model.py:131-133,168-170)
+struct SampleOpt { bool on = false; uint64_t seed = 0; };
+
 int beam_run(xn_handle* h, BeamPlan& P, const float* enc_out, int B, int beam, int L, int how_many, int sos, int eos,
-             cudaStream_t st) {
+             cudaStream_t st, SampleOpt smp = SampleOpt()) {
   const xn_config& c = h->cfg;
   const int R = B * beam;
   DecBufs& D = P.D;
@@ -830,13 +923,15 @@ int beam_run(xn_handle* h, BeamPlan& P, const float* enc_out, int B, int beam, i
   // step 0: every beam row decodes [SOS]
   D.s.anc = bb.anc[0];
   if (int r = dec_step(h, D, 0, nullptr, bb.tokens[0], L, beam, P.nv, nullptr, P.logits, c.vocab, st)) return r;
-  KL(1, launch_logsoftmax_topk(P.logits, c.vocab, R, c.vocab, beam, P.topv, P.topi, nullptr, 0, 0, st));
+  if (smp.on) KL(1, launch_gumbel_topk(P.logits, c.vocab, R, c.vocab, beam, smp.seed, 1, P.topv, P.topi, st));
+  else KL(1, launch_logsoftmax_topk(P.logits, c.vocab, R, c.vocab, beam, P.topv, P.topi, nullptr, 0, 0, st));
   KL(1, launch_beam_first(bb, P.topv, P.topi, B, beam, L, eos, st));
   int t_final = 2;
   for (int t = 2; t < L; ++t) {
     D.s.anc = bb.anc[src];
     if (int r = dec_step(h, D, t - 1, nullptr, bb.tokens[src], L, beam, P.nv, nullptr, P.logits, c.vocab, st)) return r;
-    KL(1, launch_logsoftmax_topk(P.logits, c.vocab, R, c.vocab, beam, P.topv, P.topi, nullptr, 0, 0, st));
+    if (smp.on) KL(1, launch_gumbel_topk(P.logits, c.vocab, R, c.vocab, beam, smp.seed, t, P.topv, P.topi, st));
+    else KL(1, launch_logsoftmax_topk(P.logits, c.vocab, R, c.vocab, beam, P.topv, P.topi, nullptr, 0, 0, st));
     KL(1, launch_beam_step(bb, src, P.topv, P.topi, B, beam, L, t, eos, st));
     src ^= 1;
     t_final = t + 1;
@@ -925,6 +1020,11 @@ int xn_create(const xn_config* cfg, int device, xn_handle** out) {
   h->cfg = *cfg;
   h->device = device;
   cudaSetDevice(device);
+  if (cudaMalloc(&h->flag_dev, sizeof(int)) != cudaSuccess || cudaMemset(h->flag_dev, 0, sizeof(int)) != cudaSuccess) {
+    g_create_error = "cudaMalloc failed";
+    delete h;
+    return XN_ERR_CUDA;
+  }
   *out = h;
   return XN_OK;
 }
@@ -938,7 +1038,17 @@ int xn_destroy(xn_handle* h) {
   if (h->group_start_dev) cudaFree(h->group_start_dev);
   if (h->ws.base) cudaFree(h->ws.base);
   if (h->io_in) cudaFree(h->io_in);
+  for (auto& sl : h->slots) {
+    if (sl.in) cudaFree(sl.in);
+    if (sl.out) cudaFree(sl.out);
+    if (sl.ev_in) cudaEventDestroy(sl.ev_in);
+    if (sl.ev_done) cudaEventDestroy(sl.ev_done);
+  }
+  if (h->hstream) cudaStreamDestroy(h->hstream);
+  if (h->flag_dev) cudaFree(h->flag_dev);
   if (h->pp_buf) cudaFree(h->pp_buf);
+  if (h->pp_host) cudaFreeHost(h->pp_host);
+  if (h->pp_ev) cudaEventDestroy(h->pp_ev);
   for (auto& t : h->rtables) { cudaFree(t.bounds); cudaFree(t.kk); }
   if (h->io_out) cudaFree(h->io_out);
   h->drop_graphs();
@@ -1184,9 +1294,12 @@ int xn_forward_enc(xn_handle* h, const float* input, int B, const int32_t* enc_p
     int r = swin_forward(h, input, B, fb, st);
     if (!r) r = enc_body(h, fb, B, nullptr, out, st);
     h->ws.cap = keep;
+    if (!r && h->precision != XN_PREC_FP32) KL(1, launch_nonfinite_flag(out, (long)B * c.enc_len * c.d_model, h->flag_dev, st));
     return r;
   }
-  return enc_body(h, feats, B, enc_pads_host, out, st);
+  if (int r = enc_body(h, feats, B, enc_pads_host, out, st)) return r;
+  if (h->precision != XN_PREC_FP32) KL(1, launch_nonfinite_flag(out, (long)B * c.enc_len * c.d_model, h->flag_dev, st));
+  return XN_OK;
 }
 
 int xn_forward_dec(xn_handle* h, const float* cross, int R, const int32_t* enc_pads_host, const int64_t* tokens, int t,
@@ -1232,13 +1345,23 @@ int xn_beam_search_from_enc(xn_handle* h, const float* enc_out, int B, const int
 
 }  // extern "C"
 
-// images -> captions; host_src != nullptr: `input` is unfilled device staging and the images come from that pinned host
-// buffer, copied chunk-wise inside the call (xn_caption_host)
+// restores the arena capacity on every exit path (the feature / encoder-output buffers are carved off its top per call)
+struct ArenaCapGuard {
+  Arena& a; size_t keep;
+  explicit ArenaCapGuard(Arena& ar) : a(ar), keep(ar.cap) {}
+  ~ArenaCapGuard() { a.cap = keep; }
+};
+
+// images -> captions.  host_src != nullptr: the images come from that pinned host buffer, copied chunk-wise inside the
+// call (xn_caption_host).  Otherwise `input` is the caller's device tensor: it is first copied into the handle's own
+// staging buffer (one device-to-device copy, ~35 us per 113 MB) so that everything after it -- and therefore the cached
+// CUDA graph of the call shape -- reads a stable address: any caller tensor replays the same graph.
 static int beam_search_impl(xn_handle* h, const float* input, const float* host_src, int B, const int32_t* enc_pads_host, int beam,
                             int max_len, int how_many, int sos_idx, int eos_idx, int32_t* out_tokens, int32_t* out_len,
                             float* out_logprob, void* stream) {
   NEED_READY();
   const xn_config& c = h->cfg;
+  if (B < 1) return h->fail(XN_ERR_ARG, "empty batch");
   if (how_many > beam) return h->fail(XN_ERR_ARG, "requested output per sequence must be lower than beam width");
   const int Bs = (int)std::min<int64_t>(B, h->swin_chunk), Be = (int)std::min<int64_t>(B, h->enc_chunk);
   const size_t enc_bytes = ((size_t)B * c.enc_len * c.d_model * 4 + 4095) & ~size_t(255);
@@ -1246,23 +1369,30 @@ static int beam_search_impl(xn_handle* h, const float* input, const float* host_
   size_t scratch = std::max(std::max(c.has_swin ? swin_ws_bytes(c, Bs, h->precision) : 0, enc_ws_bytes(c, Be)),
                             beam_ws_bytes(c, B, beam, max_len) + xn_handle::kMaxDecodeGroups * (size_t)(96 * 256));   // + per-group rounding
   if (int r = ensure_ws(h, scratch + enc_bytes + feat_bytes, st)) return r;
+  bool pads = false;
+  if (enc_pads_host)
+    for (int i = 0; i < B; ++i) pads |= enc_pads_host[i] != 0;
+  if (c.has_swin && pads) return h->fail(XN_ERR_ARG, "End to End case have no padding");
+  const size_t in_elems = c.has_swin ? (size_t)B * c.in_chans * c.img_size * c.img_size : (size_t)B * c.enc_len * c.feat_dim;
+  const bool stage_input = !host_src && !pads && h->use_graph && !h->profile && input != h->staged_input;
+  if (host_src || stage_input)
+    if (int r = ensure_io_in(h, in_elems * 4)) return r;
+  ArenaCapGuard cap_guard(h->ws);
   const size_t keep = h->ws.cap;
   char* top = h->ws.base + (keep & ~size_t(255));
   float* enc_out = reinterpret_cast<float*>(top - enc_bytes);
   float* fb = reinterpret_cast<float*>(top - enc_bytes - feat_bytes);
   h->ws.cap = (size_t)((top - enc_bytes - feat_bytes) - h->ws.base);
-  int r = 0;
-  bool pads = false;
-  if (enc_pads_host)
-    for (int i = 0; i < B; ++i) pads |= enc_pads_host[i] != 0;
-  if (c.has_swin && pads) r = h->fail(XN_ERR_ARG, "End to End case have no padding");
-  if (!r && pads) {
+  if (pads) {
     // encoder padding (features-in model): per-image valid lengths are uploaded with a host sync -> plain stream order
-    r = enc_body(h, input, B, enc_pads_host, enc_out, st);
-    if (!r) r = beam_from_enc(h, enc_out, B, enc_pads_host, beam, max_len, how_many, sos_idx, eos_idx, out_tokens, out_len,
-                              out_logprob, st, true);
-    h->ws.cap = keep;
-    return r;
+    if (int r = enc_body(h, input, B, enc_pads_host, enc_out, st)) return r;
+    return beam_from_enc(h, enc_out, B, enc_pads_host, beam, max_len, how_many, sos_idx, eos_idx, out_tokens, out_len, out_logprob, st, true);
+  }
+  const float* in_dev = input;
+  if (host_src) in_dev = h->io_in;
+  else if (stage_input) {
+    if (input != h->io_in) CU(cudaMemcpyAsync(h->io_in, input, in_elems * 4, cudaMemcpyDeviceToDevice, st));
+    in_dev = h->io_in;
   }
   // The beam buffers are carved from the bottom of the arena, where the Swin / encoder chunks also put their scratch:
   // both run strictly before the decoder, in stream order.  The images are decoded in G independent groups (beam search
@@ -1276,44 +1406,48 @@ static int beam_search_impl(xn_handle* h, const float* input, const float* host_
   std::vector<BeamPlan> P(G);
   std::vector<int> g0(G + 1, 0);
   for (int g = 0; g < G; ++g) g0[g + 1] = g0[g] + B / G + (g < B % G ? 1 : 0);
-  for (int g = 0; g < G && !r; ++g) r = beam_plan(h, P[g], g0[g + 1] - g0[g], nullptr, beam, max_len, how_many, st, g == 0);
-  if (!r && G > 1 && !h->d_fork) {
+  for (int g = 0; g < G; ++g)
+    if (int r = beam_plan(h, P[g], g0[g + 1] - g0[g], nullptr, beam, max_len, how_many, st, g == 0)) return r;
+  if (G > 1 && !h->d_fork) {
     CU(cudaEventCreateWithFlags(&h->d_fork, cudaEventDisableTiming));
     for (int g = 0; g < xn_handle::kMaxDecodeGroups; ++g) {
       CU(cudaStreamCreateWithFlags(&h->dstream[g], cudaStreamNonBlocking));
       CU(cudaEventCreateWithFlags(&h->d_join[g], cudaEventDisableTiming));
     }
   }
-  if (!r) {
-    const int host_chunk = 32;                              // copy granularity of the host path (chunk c+1 lands during chunk c)
-    const xn_handle::GraphKey key{1 + 16 * G + (host_src ? 4096 : 0), host_src ? host_src : input, B, beam, max_len, how_many,
-                                  sos_idx, eos_idx, h->ws.base, keep};
-    r = run_graphed(h, key, true, st, [&](cudaStream_t s2) -> int {
-      if (c.has_swin) {
-        if (int rr = swin_forward(h, input, B, fb, s2, host_src, host_chunk)) return rr;
-        if (int rr = enc_body(h, fb, B, nullptr, enc_out, s2)) return rr;
-      } else {
-        if (int rr = enc_body(h, input, B, nullptr, enc_out, s2)) return rr;
-      }
-      if (G == 1) return beam_run(h, P[0], enc_out, B, beam, max_len, how_many, sos_idx, eos_idx, s2);
-      CU(cudaEventRecord(h->d_fork, s2));
-      int rr = 0;
-      for (int g = 0; g < G; ++g) {                         // issue order interleaves nothing: each group is one chain
-        cudaStream_t sg = h->dstream[g];
-        CU(cudaStreamWaitEvent(sg, h->d_fork, 0));
-        if (!rr) rr = beam_run(h, P[g], enc_out + (size_t)g0[g] * c.enc_len * c.d_model, g0[g + 1] - g0[g], beam, max_len, how_many,
-                               sos_idx, eos_idx, sg);
-        CU(cudaEventRecord(h->d_join[g], sg));
-        CU(cudaStreamWaitEvent(s2, h->d_join[g], 0));       // always joined, also on error: a capture must not end forked
-      }
-      return rr;
-    });
-  }
+  const int host_chunk = 32;                                // copy granularity of the host path (chunk c+1 lands during chunk c)
+  const xn_handle::GraphKey key{1 + 16 * G + (host_src ? 4096 : 0), in_dev, B, beam, max_len, how_many,
+                                sos_idx, eos_idx, h->ws.base, keep};
+  int r = run_graphed(h, key, true, st, [&](cudaStream_t s2) -> int {
+    if (c.has_swin) {
+      if (int rr = swin_forward(h, in_dev, B, fb, s2, host_src, host_chunk)) return rr;
+      if (int rr = enc_body(h, fb, B, nullptr, enc_out, s2)) return rr;
+    } else {
+      if (int rr = enc_body(h, in_dev, B, nullptr, enc_out, s2)) return rr;
+    }
+    if (h->precision != XN_PREC_FP32) KL(1, launch_nonfinite_flag(enc_out, (long)B * c.enc_len * c.d_model, h->flag_dev, s2));
+    if (G == 1) return beam_run(h, P[0], enc_out, B, beam, max_len, how_many, sos_idx, eos_idx, s2);
+    // fork / join: every branch is joined back into s2 whatever happens in between (a capture must not end forked);
+    // the first error is remembered and reported after the join
+    int rr = 0;
+    auto note = [&](cudaError_t e, const char* what) {
+      if (e != cudaSuccess && !rr) rr = h->fail(XN_ERR_CUDA, "%s failed: %s", what, cudaGetErrorString(e));
+    };
+    note(cudaEventRecord(h->d_fork, s2), "cudaEventRecord(fork)");
+    for (int g = 0; g < G; ++g) {                           // issue order interleaves nothing: each group is one chain
+      cudaStream_t sg = h->dstream[g];
+      note(cudaStreamWaitEvent(sg, h->d_fork, 0), "cudaStreamWaitEvent(fork)");
+      if (!rr) rr = beam_run(h, P[g], enc_out + (size_t)g0[g] * c.enc_len * c.d_model, g0[g + 1] - g0[g], beam, max_len, how_many,
+                             sos_idx, eos_idx, sg);
+      note(cudaEventRecord(h->d_join[g], sg), "cudaEventRecord(join)");
+      note(cudaStreamWaitEvent(s2, h->d_join[g], 0), "cudaStreamWaitEvent(join)");
+    }
+    return rr;
+  }, host_src, in_elems * 4);
   for (int g = 0; g < G && !r; ++g) {
     const size_t o = (size_t)g0[g] * how_many;
     r = beam_copy_out(h, P[g], g0[g + 1] - g0[g], max_len, how_many, out_tokens + o * max_len, out_len + o, out_logprob + o * max_len, st);
   }
-  h->ws.cap = keep;
   return r;
 }
 
@@ -1447,11 +1581,7 @@ int xn_caption_host(xn_handle* h, const float* input_host, int B, int beam, int 
   const xn_config& c = h->cfg;
   const size_t in_elems = c.has_swin ? (size_t)B * c.in_chans * c.img_size * c.img_size : (size_t)B * c.enc_len * c.feat_dim;
   const size_t n_out = (size_t)B * how_many * max_len;
-  if (h->io_in_cap < in_elems * 4) {
-    if (h->io_in) { CU(cudaDeviceSynchronize()); cudaFree(h->io_in); h->io_in = nullptr; h->io_in_cap = 0; }
-    CU(cudaMalloc(&h->io_in, in_elems * 4));
-    h->io_in_cap = in_elems * 4;
-  }
+  if (int r = ensure_io_in(h, in_elems * 4)) return r;
   const size_t out_bytes = n_out * 8 + (size_t)B * how_many * 4 + 1024;
   if (h->io_out_cap < out_bytes) {
     if (h->io_out) { CU(cudaDeviceSynchronize()); cudaFree(h->io_out); h->io_out = nullptr; h->io_out_cap = 0; }
@@ -1469,7 +1599,7 @@ int xn_caption_host(xn_handle* h, const float* input_host, int B, int beam, int 
   const bool pinned = cudaPointerGetAttributes(&pa, input_host) == cudaSuccess && pa.type == cudaMemoryTypeHost;
   (void)cudaGetLastError();
   if (pinned && c.has_swin && !h->profile) {
-    if (int r = beam_search_impl(h, din, input_host, B, nullptr, beam, max_len, how_many, sos_idx, eos_idx, d_tok, d_len, d_lp, stream)) return r;
+    if (int r = beam_search_impl(h, nullptr, input_host, B, nullptr, beam, max_len, how_many, sos_idx, eos_idx, d_tok, d_len, d_lp, stream)) return r;
   } else {
     CU(cudaMemcpyAsync(din, input_host, in_elems * 4, cudaMemcpyHostToDevice, st));
     if (int r = xn_beam_search(h, din, B, nullptr, beam, max_len, how_many, sos_idx, eos_idx, d_tok, d_len, d_lp, stream)) return r;
@@ -1481,9 +1611,19 @@ int xn_caption_host(xn_handle* h, const float* input_host, int B, int beam, int 
   return XN_OK;
 }
 
-static int resample_table(xn_handle* h, int in_size, int out_size, const xn_handle::ResampleTable** out) {
-  for (auto& t : h->rtables)
-    if (t.in_size == in_size && t.out_size == out_size) { *out = &t; return 0; }
+// Coefficient tables are cached per (input size, output size), least-recently-used first.  The entry is returned BY VALUE
+// and `pinned` (the other table of the same call) is never evicted, so a later insertion cannot free what a pending
+// launch of this call reads; an evicted table may still be read by launches already enqueued, hence the device sync.
+static int resample_table(xn_handle* h, int in_size, int out_size, xn_handle::ResampleTable* out,
+                          const xn_handle::ResampleTable* pinned = nullptr) {
+  for (size_t i = 0; i < h->rtables.size(); ++i)
+    if (h->rtables[i].in_size == in_size && h->rtables[i].out_size == out_size) {
+      const xn_handle::ResampleTable t = h->rtables[i];
+      h->rtables.erase(h->rtables.begin() + i);            // move to the most-recently-used end
+      h->rtables.push_back(t);
+      *out = t;
+      return 0;
+    }
   std::vector<int> bounds, kk;
   xn_handle::ResampleTable t{in_size, out_size, 0, nullptr, nullptr};
   resample_coeffs(in_size, out_size, bounds, kk, &t.ksize);
@@ -1491,13 +1631,15 @@ static int resample_table(xn_handle* h, int in_size, int out_size, const xn_hand
   CU(cudaMalloc(&t.kk, kk.size() * sizeof(int)));
   CU(cudaMemcpy(t.bounds, bounds.data(), bounds.size() * sizeof(int), cudaMemcpyHostToDevice));
   CU(cudaMemcpy(t.kk, kk.data(), kk.size() * sizeof(int), cudaMemcpyHostToDevice));
-  if (h->rtables.size() >= 64) {            // bounded cache: drop the oldest entry
+  if (h->rtables.size() >= xn_handle::kMaxResampleTables) {
+    size_t victim = 0;                                      // least recently used entry that this call does not hold
+    if (pinned && h->rtables[victim].bounds == pinned->bounds) victim = 1;
     CU(cudaDeviceSynchronize());
-    cudaFree(h->rtables.front().bounds); cudaFree(h->rtables.front().kk);
-    h->rtables.erase(h->rtables.begin());
+    cudaFree(h->rtables[victim].bounds); cudaFree(h->rtables[victim].kk);
+    h->rtables.erase(h->rtables.begin() + victim);
   }
   h->rtables.push_back(t);
-  *out = &h->rtables.back();
+  *out = t;
   return 0;
 }
 
@@ -1507,10 +1649,9 @@ int xn_preprocess_rgb8(xn_handle* h, const uint8_t* rgb, int rgb_on_device, int 
   cudaStream_t st = (cudaStream_t)stream;
   h->cur_st = st;
   if (H < 1 || W < 1 || out_size < 1 || (long)H * W > (1L << 28)) return h->fail(XN_ERR_ARG, "bad image size %d x %d -> %d", H, W, out_size);
-  const xn_handle::ResampleTable *tx = nullptr, *ty = nullptr;
+  xn_handle::ResampleTable tx{}, ty{};
   if (int r = resample_table(h, W, out_size, &tx)) return r;
-  const int ksx = tx->ksize; const int* bx = tx->bounds; const int* kx = tx->kk;      // (the vector may reallocate below)
-  if (int r = resample_table(h, H, out_size, &ty)) return r;
+  if (int r = resample_table(h, H, out_size, &ty, &tx)) return r;
   const size_t in_bytes = (size_t)H * W * 3, tmp_bytes = (size_t)H * out_size * 3;
   const size_t need = ((in_bytes + 255) & ~size_t(255)) + tmp_bytes;
   if (h->pp_cap < need) {
@@ -1524,7 +1665,224 @@ int xn_preprocess_rgb8(xn_handle* h, const uint8_t* rgb, int rgb_on_device, int 
     CU(cudaMemcpyAsync(h->pp_buf, rgb, in_bytes, cudaMemcpyHostToDevice, st));
     src = h->pp_buf;
   }
-  KL(2, launch_preprocess_rgb8(src, H, W, out_size, bx, kx, ksx, ty->bounds, ty->kk, ty->ksize, tmp, out, st));
+  KL(2, launch_preprocess_rgb8(src, H, W, out_size, tx.bounds, tx.kk, tx.ksize, ty.bounds, ty.kk, ty.ksize, tmp, out, st));
+  return XN_OK;
+}
+
+// encoder output of a batch at the top of the arena (images or features in; pads for the features-in model)
+static int encode_for_search(xn_handle* h, const float* input, int B, const int32_t* enc_pads_host, size_t scratch_bytes,
+                             float** enc_out_p, bool* pads_p, cudaStream_t st) {
+  const xn_config& c = h->cfg;
+  const int Bs = (int)std::min<int64_t>(B, h->swin_chunk), Be = (int)std::min<int64_t>(B, h->enc_chunk);
+  const size_t enc_bytes = ((size_t)B * c.enc_len * c.d_model * 4 + 4095) & ~size_t(255);
+  const size_t feat_bytes = c.has_swin ? (((size_t)B * c.enc_len * c.feat_dim * 4 + 4095) & ~size_t(255)) : 0;
+  const size_t scratch = std::max(std::max(c.has_swin ? swin_ws_bytes(c, Bs, h->precision) : 0, enc_ws_bytes(c, Be)), scratch_bytes);
+  if (int r = ensure_ws(h, scratch + enc_bytes + feat_bytes, st)) return r;
+  bool pads = false;
+  if (enc_pads_host)
+    for (int i = 0; i < B; ++i) pads |= enc_pads_host[i] != 0;
+  if (c.has_swin && pads) return h->fail(XN_ERR_ARG, "End to End case have no padding");
+  char* top = h->ws.base + (h->ws.cap & ~size_t(255));
+  float* enc_out = reinterpret_cast<float*>(top - enc_bytes);
+  float* fb = reinterpret_cast<float*>(top - enc_bytes - feat_bytes);
+  h->ws.cap = (size_t)((top - enc_bytes - feat_bytes) - h->ws.base);        // the caller holds an ArenaCapGuard
+  if (c.has_swin) {
+    if (int r = swin_forward(h, input, B, fb, st)) return r;
+    if (int r = enc_body(h, fb, B, nullptr, enc_out, st)) return r;
+  } else {
+    if (int r = enc_body(h, input, B, pads ? enc_pads_host : nullptr, enc_out, st)) return r;
+  }
+  *enc_out_p = enc_out;
+  *pads_p = pads;
+  return 0;
+}
+
+int xn_beam_search_sample(xn_handle* h, const float* input, int B, const int32_t* enc_pads_host, int beam, int max_len, int how_many,
+                          int sos_idx, int eos_idx, uint64_t seed, int32_t* out_tokens, int32_t* out_len, float* out_logprob,
+                          void* stream) {
+  NEED_READY();
+  if (B < 1) return h->fail(XN_ERR_ARG, "empty batch");
+  if (how_many > beam) return h->fail(XN_ERR_ARG, "requested output per sequence must be lower than beam width");
+  ArenaCapGuard guard(h->ws);
+  float* enc_out = nullptr;
+  bool pads = false;
+  if (int r = encode_for_search(h, input, B, enc_pads_host, beam_ws_bytes(h->cfg, B, beam, max_len), &enc_out, &pads, st)) return r;
+  BeamPlan P;
+  if (int r = beam_plan(h, P, B, pads ? enc_pads_host : nullptr, beam, max_len, how_many, st, true)) return r;
+  SampleOpt so; so.on = true; so.seed = seed;
+  if (int r = beam_run(h, P, enc_out, B, beam, max_len, how_many, sos_idx, eos_idx, st, so)) return r;
+  return beam_copy_out(h, P, B, max_len, how_many, out_tokens, out_len, out_logprob, st);
+}
+
+int xn_sample(xn_handle* h, const float* input, int B, const int32_t* enc_pads_host, int num_outputs, int max_len, int sos_idx,
+              int eos_idx, uint64_t seed, int32_t* out_tokens, int32_t* out_len, float* out_logprob, void* stream) {
+  NEED_READY();
+  const xn_config& c = h->cfg;
+  if (B < 1) return h->fail(XN_ERR_ARG, "empty batch");
+  if (num_outputs < 1 || num_outputs > 8) return h->fail(XN_ERR_ARG, "num_outputs must be in [1, 8]");
+  const int L = max_len + 1;                         // SOS + max_len sampled words
+  if (max_len < 1 || max_len > c.max_seq_len || L > 128) return h->fail(XN_ERR_ARG, "sample_max_seq_len %d outside [1, %d]", max_len, std::min(c.max_seq_len, 127));
+  ArenaCapGuard guard(h->ws);
+  float* enc_out = nullptr;
+  bool pads = false;
+  if (int r = encode_for_search(h, input, B, enc_pads_host, beam_ws_bytes(c, B, num_outputs, L), &enc_out, &pads, st)) return r;
+  BeamPlan P;
+  // the plan of a beam search with beam = how_many = num_outputs: R = B * num_outputs independent rows
+  {
+    const int keep_max = h->cfg.max_seq_len;
+    h->cfg.max_seq_len = std::max(keep_max, L);      // the history holds L tokens; only positions < max_len are decoded
+    const int r = beam_plan(h, P, B, pads ? enc_pads_host : nullptr, num_outputs, L, num_outputs, st, true);
+    h->cfg.max_seq_len = keep_max;
+    if (r) return r;
+  }
+  const int R = B * num_outputs;
+  if (int r = dec_project(h, P.D, enc_out, B, st)) return r;
+  KL(1, launch_beam_init(P.bb, B, num_outputs, L, sos_idx, st));
+  P.D.s.anc = P.bb.anc[0];
+  for (int t = 1; t <= max_len; ++t) {
+    if (int r = dec_step(h, P.D, t - 1, nullptr, P.bb.tokens[0], L, num_outputs, P.nv, nullptr, P.logits, c.vocab, st)) return r;
+    KL(1, launch_gumbel_topk(P.logits, c.vocab, R, c.vocab, 1, seed, t, P.topv, P.topi, st));
+    KL(1, launch_sample_append(P.bb, P.topv, P.topi, R, L, t, eos_idx, st));
+  }
+  KL(1, launch_sample_finalize(P.bb, R, L, L, P.r_tok, P.r_len, P.r_lp, st));
+  return beam_copy_out(h, P, B, L, num_outputs, out_tokens, out_len, out_logprob, st);
+}
+
+int xn_preprocess_rgb8_batch(xn_handle* h, const uint8_t* const* rgb_ptrs, int rgb_on_device, const int32_t* heights,
+                             const int32_t* widths, int n, float* out, int out_size, void* stream) {
+  if (!h || !rgb_ptrs || !heights || !widths || !out) return XN_ERR_ARG;
+  cudaSetDevice(h->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  h->cur_st = st;
+  const int S = out_size;
+  if (n < 1 || n > 65535 || S < 1) return h->fail(XN_ERR_ARG, "bad batch (%d images -> %d)", n, S);
+  // ---- plan: image / intermediate staging, item records, one coefficient table per distinct input size
+  size_t img_bytes = 0, tmp_bytes = 0;
+  int max_h = 0;
+  std::vector<std::pair<int, size_t>> sizes;           // (input size, int offset of its table) in the packed table block
+  std::vector<int> tab;                                // [bounds (2S) | kk (S * ksize)] per distinct size
+  std::vector<int> ksz;
+  auto table_of = [&](int in_size) -> int {
+    for (size_t i = 0; i < sizes.size(); ++i) if (sizes[i].first == in_size) return (int)i;
+    std::vector<int> b, k;
+    int ks = 0;
+    resample_coeffs(in_size, S, b, k, &ks);
+    sizes.push_back({in_size, tab.size()});
+    ksz.push_back(ks);
+    tab.insert(tab.end(), b.begin(), b.end());
+    tab.insert(tab.end(), k.begin(), k.end());
+    return (int)sizes.size() - 1;
+  };
+  std::vector<int> tx(n), ty(n);
+  std::vector<size_t> src_off(n), tmp_off(n);
+  for (int i = 0; i < n; ++i) {
+    const int H = heights[i], W = widths[i];
+    if (H < 1 || W < 1 || H > 65535 || (long)H * W > (1L << 28) || !rgb_ptrs[i]) return h->fail(XN_ERR_ARG, "bad image %d: %d x %d", i, H, W);
+    tx[i] = table_of(W); ty[i] = table_of(H);
+    max_h = std::max(max_h, H);
+    src_off[i] = img_bytes;
+    if (!rgb_on_device) img_bytes += ((size_t)H * W * 3 + 255) & ~size_t(255);
+    tmp_off[i] = tmp_bytes;
+    tmp_bytes += ((size_t)H * S * 3 + 255) & ~size_t(255);
+  }
+  const size_t items_bytes = ((size_t)n * sizeof(PreItem) + 255) & ~size_t(255);
+  const size_t meta_bytes = items_bytes + tab.size() * sizeof(int);
+  const size_t need = img_bytes + tmp_bytes + ((meta_bytes + 255) & ~size_t(255));
+  if (h->pp_cap < need) {
+    if (h->pp_buf) { CU(cudaDeviceSynchronize()); cudaFree(h->pp_buf); h->pp_buf = nullptr; h->pp_cap = 0; }
+    CU(cudaMalloc(&h->pp_buf, need));
+    h->pp_cap = need;
+  }
+  if (h->pp_host_cap < meta_bytes) {
+    if (h->pp_host) { CU(cudaDeviceSynchronize()); cudaFreeHost(h->pp_host); h->pp_host = nullptr; h->pp_host_cap = 0; }
+    CU(cudaMallocHost(&h->pp_host, meta_bytes));
+    h->pp_host_cap = meta_bytes;
+  }
+  if (!h->pp_ev) CU(cudaEventCreateWithFlags(&h->pp_ev, cudaEventDisableTiming));
+  else CU(cudaEventSynchronize(h->pp_ev));             // the previous batch's metadata upload has left the pinned staging
+  uint8_t* d_img = h->pp_buf;
+  uint8_t* d_tmp = h->pp_buf + img_bytes;
+  char* d_meta = reinterpret_cast<char*>(h->pp_buf + img_bytes + tmp_bytes);
+  const int* d_tab = reinterpret_cast<const int*>(d_meta + items_bytes);
+  PreItem* items = reinterpret_cast<PreItem*>(h->pp_host);
+  for (int i = 0; i < n; ++i) {
+    PreItem& it = items[i];
+    it.src = rgb_on_device ? rgb_ptrs[i] : d_img + src_off[i];
+    it.tmp = d_tmp + tmp_off[i];
+    it.out = out + (size_t)i * 3 * S * S;
+    it.bx = d_tab + sizes[tx[i]].second; it.kx = it.bx + 2 * S; it.ksx = ksz[tx[i]];
+    it.by = d_tab + sizes[ty[i]].second; it.ky = it.by + 2 * S; it.ksy = ksz[ty[i]];
+    it.H = heights[i]; it.W = widths[i];
+  }
+  memcpy(h->pp_host + items_bytes, tab.data(), tab.size() * sizeof(int));
+  CU(cudaMemcpyAsync(d_meta, h->pp_host, meta_bytes, cudaMemcpyHostToDevice, st));
+  CU(cudaEventRecord(h->pp_ev, st));
+  if (!rgb_on_device)
+    for (int i = 0; i < n; ++i)
+      CU(cudaMemcpyAsync(d_img + src_off[i], rgb_ptrs[i], (size_t)heights[i] * widths[i] * 3, cudaMemcpyHostToDevice, st));
+  KL(2, launch_preprocess_rgb8_batch(reinterpret_cast<const PreItem*>(d_meta), n, max_h, S, st));
+  return XN_OK;
+}
+
+int xn_overflow_flag(xn_handle* h, int* flag_out, int clear) {
+  if (!h || !flag_out) return XN_ERR_ARG;
+  cudaSetDevice(h->device);
+  CU(cudaDeviceSynchronize());
+  CU(cudaMemcpy(flag_out, h->flag_dev, sizeof(int), cudaMemcpyDeviceToHost));
+  if (clear) CU(cudaMemset(h->flag_dev, 0, sizeof(int)));
+  return XN_OK;
+}
+
+int xn_caption_host_begin(xn_handle* h, const float* input_host, int B, int beam, int max_len, int how_many, int sos_idx,
+                          int eos_idx, int32_t* out_tokens_host, int32_t* out_len_host, float* out_logprob_host, void* stream) {
+  NEED_READY();
+  const xn_config& c = h->cfg;
+  if (!input_host || !out_tokens_host || !out_len_host || B < 1) return h->fail(XN_ERR_ARG, "null host buffer / empty batch");
+  const size_t in_bytes = (c.has_swin ? (size_t)B * c.in_chans * c.img_size * c.img_size : (size_t)B * c.enc_len * c.feat_dim) * 4;
+  const size_t n_out = (size_t)B * how_many * max_len;
+  const size_t out_bytes = n_out * 8 + (size_t)B * how_many * 4 + 1024;
+  if (!h->hstream) CU(cudaStreamCreateWithFlags(&h->hstream, cudaStreamNonBlocking));
+  const int k = h->next_slot;
+  xn_handle::HostSlot& sl = h->slots[k];
+  if (!sl.ev_in) {
+    CU(cudaEventCreateWithFlags(&sl.ev_in, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&sl.ev_done, cudaEventDisableTiming));
+  }
+  if (sl.pending) return h->fail(XN_ERR_STATE, "caption_host slot %d still has an un-ended call (at most two calls in flight)", k);
+  if (sl.in_cap < in_bytes || sl.out_cap < out_bytes) {
+    CU(cudaDeviceSynchronize());
+    h->drop_graphs();
+    if (sl.in_cap < in_bytes) { if (sl.in) cudaFree(sl.in); sl.in = nullptr; sl.in_cap = 0; CU(cudaMalloc(&sl.in, in_bytes)); sl.in_cap = in_bytes; }
+    if (sl.out_cap < out_bytes) { if (sl.out) cudaFree(sl.out); sl.out = nullptr; sl.out_cap = 0; CU(cudaMalloc(&sl.out, out_bytes)); sl.out_cap = out_bytes; }
+  }
+  // copy stream: after the slot's previous user has finished computing (device-side order, no host wait)
+  CU(cudaStreamWaitEvent(h->hstream, sl.ev_done, 0));
+  CU(cudaMemcpyAsync(sl.in, input_host, in_bytes, cudaMemcpyHostToDevice, h->hstream));
+  CU(cudaEventRecord(sl.ev_in, h->hstream));
+  CU(cudaStreamWaitEvent(st, sl.ev_in, 0));
+  int32_t* d_tok = reinterpret_cast<int32_t*>(sl.out);
+  float* d_lp = reinterpret_cast<float*>(sl.out + n_out * 4);
+  int32_t* d_len = reinterpret_cast<int32_t*>(sl.out + n_out * 8);
+  h->staged_input = sl.in;                          // beam_search_impl reads the slot's staging directly (no second copy)
+  const int r = beam_search_impl(h, sl.in, nullptr, B, nullptr, beam, max_len, how_many, sos_idx, eos_idx, d_tok, d_len, d_lp, stream);
+  h->staged_input = nullptr;
+  if (r) return r;
+  CU(cudaMemcpyAsync(out_tokens_host, d_tok, n_out * 4, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(out_len_host, d_len, (size_t)B * how_many * 4, cudaMemcpyDeviceToHost, st));
+  if (out_logprob_host) CU(cudaMemcpyAsync(out_logprob_host, d_lp, n_out * 4, cudaMemcpyDeviceToHost, st));
+  CU(cudaEventRecord(sl.ev_done, st));
+  sl.pending = true;
+  h->next_slot = k ^ 1;
+  return k;                                         // ticket
+}
+
+int xn_caption_host_end(xn_handle* h, int ticket) {
+  if (!h || ticket < 0 || ticket > 1) return XN_ERR_ARG;
+  cudaSetDevice(h->device);
+  xn_handle::HostSlot& sl = h->slots[ticket];
+  if (!sl.pending) return h->fail(XN_ERR_STATE, "caption_host ticket %d is not in flight", ticket);
+  CU(cudaEventSynchronize(sl.ev_done));
+  sl.pending = false;
   return XN_OK;
 }
 
@@ -1733,6 +2091,24 @@ int xn_op_logsoftmax_topk(xn_handle* h, const float* logits, int rows, int V, in
 }
 
 }  // extern "C"
+
+__global__ void nonfinite_flag_kernel(const float* __restrict__ x, long n, int* __restrict__ flag) {
+  bool bad = false;
+  for (long i = ((long)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < n; i += (long)gridDim.x * blockDim.x * 4) {
+    if (i + 3 < n) {
+      const float4 v = *reinterpret_cast<const float4*>(x + i);
+      bad |= !(isfinite(v.x) && isfinite(v.y) && isfinite(v.z) && isfinite(v.w));
+    } else {
+      for (long j = i; j < n; ++j) bad |= !isfinite(x[j]);
+    }
+  }
+  if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicOr(flag, 1);
+}
+cudaError_t launch_nonfinite_flag(const float* x, long n, int* flag, cudaStream_t st) {
+  const long blocks = std::min<long>(148 * 8, (n / 4 + 255) / 256 + 1);
+  nonfinite_flag_kernel<<<(unsigned)blocks, 256, 0, st>>>(x, n, flag);
+  return cudaGetLastError();
+}
 
 __global__ void widen_16_kernel(const void* __restrict__ x, float* __restrict__ y, long n, int fp16) {
   const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;

@@ -168,6 +168,13 @@ cudaError_t launch_ensemble_logprob(const EnsembleLogits& in, long ld, int rows,
 cudaError_t launch_logsoftmax_topk(const float* logits, long ld, int rows, int V, int k, float* top_val,
                                    int* top_idx, float* logprob, long ldlp, int write_mode, cudaStream_t st);
 
+// Sampling variant (reference captioning_model.py sample_or_max='sample' / mode='sampling'): k draws WITHOUT replacement
+// from softmax(logits) per row, in draw order, by the Gumbel-top-k construction -- rank log p_i + G_i with i.i.d. standard
+// Gumbel noise G_i from a counter-based generator keyed on (seed, row, step, i) -- which has exactly the distribution of
+// torch.multinomial(p, k, replacement=False) (k = 1: a Categorical draw).  top_val receives the UNPERTURBED log p.
+cudaError_t launch_gumbel_topk(const float* logits, long ld, int rows, int V, int k, uint64_t seed, int step, float* top_val,
+                               int* top_idx, cudaStream_t st);
+
 // ---------------------------------------------------------------- image preprocessing (Pillow-exact resize + normalise)
 // Pillow precompute_coeffs + normalize_coeffs_8bpc for the bilinear filter: bounds (out_size x {first, count}) and
 // 22-bit fixed-point weights (out_size x ksize)
@@ -175,6 +182,14 @@ void resample_coeffs(int in_size, int out_size, std::vector<int>& bounds, std::v
 cudaError_t launch_preprocess_rgb8(const uint8_t* rgb_dev, int H, int W, int S, const int* bounds_x, const int* kk_x, int ksize_x,
                                    const int* bounds_y, const int* kk_y, int ksize_y, uint8_t* tmp_dev, float* out_dev,
                                    cudaStream_t st);
+
+// batched form: one item per image, all pointers device memory
+struct PreItem {
+  const uint8_t* src; uint8_t* tmp; float* out;
+  const int *bx, *kx, *by, *ky;
+  int H, W, ksx, ksy;
+};
+cudaError_t launch_preprocess_rgb8_batch(const PreItem* items_dev, int n, int max_h, int S, cudaStream_t st);
 
 // ---------------------------------------------------------------- beam search bookkeeping
 struct BeamBufs {
@@ -193,5 +208,11 @@ cudaError_t launch_beam_step(const BeamBufs& bb, int src, const float* top_val, 
                              int beam, int L, int t, int eos, cudaStream_t st);
 cudaError_t launch_beam_finalize(const BeamBufs& bb, int src, int B, int beam, int L, int t_final, int how_many,
                                  int* out_tokens, int* out_len, float* out_lp, cudaStream_t st);
+
+// mode='sampling' bookkeeping (legacy_models/captioning_model.py:60-109): independent rows, one sampled word per step
+cudaError_t launch_sample_append(const BeamBufs& bb, const float* top_val, const int* top_idx, int R, int L, int t, int eos,
+                                 cudaStream_t st);
+cudaError_t launch_sample_finalize(const BeamBufs& bb, int R, int L, int t_final, int* out_tokens, int* out_len, float* out_lp,
+                                   cudaStream_t st);
 
 }  // namespace xn

@@ -95,6 +95,54 @@ __global__ void __launch_bounds__(256) resample_v_norm_kernel(const uint8_t* __r
   }
 }
 
+// ---- batched form: one launch pair for N images of arbitrary sizes.  Every image has an item record on the device
+// (source, intermediate and output pointers, its two coefficient tables); blockIdx.z selects the image, rows beyond an
+// image's height exit at once (the grid is sized for the tallest image of the batch).
+__global__ void __launch_bounds__(256) resample_h_batch_kernel(const PreItem* __restrict__ items, int S) {
+  const PreItem it = items[blockIdx.z];
+  const int xx = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  if (y >= it.H || xx >= S) return;
+  const int x0 = it.bx[2 * xx], n = it.bx[2 * xx + 1];
+  const int* k = it.kx + (size_t)xx * it.ksx;
+  const uint8_t* row = it.src + ((size_t)y * it.W + x0) * 3;
+  int s0 = 1 << (kPrecisionBits - 1), s1 = s0, s2 = s0;
+  for (int t = 0; t < n; ++t) {
+    const int kv = k[t];
+    s0 += row[3 * t] * kv; s1 += row[3 * t + 1] * kv; s2 += row[3 * t + 2] * kv;
+  }
+  uint8_t* o = it.tmp + ((size_t)y * S + xx) * 3;
+  o[0] = (uint8_t)clip8(s0); o[1] = (uint8_t)clip8(s1); o[2] = (uint8_t)clip8(s2);
+}
+
+__global__ void __launch_bounds__(256) resample_v_norm_batch_kernel(const PreItem* __restrict__ items, int S) {
+  const PreItem it = items[blockIdx.z];
+  const int xx = blockIdx.x * blockDim.x + threadIdx.x, yy = blockIdx.y;
+  if (xx >= S) return;
+  const int y0 = it.by[2 * yy], n = it.by[2 * yy + 1];
+  const int* k = it.ky + (size_t)yy * it.ksy;
+  int s[3] = {1 << (kPrecisionBits - 1), 1 << (kPrecisionBits - 1), 1 << (kPrecisionBits - 1)};
+  for (int t = 0; t < n; ++t) {
+    const uint8_t* p = it.tmp + ((size_t)(y0 + t) * S + xx) * 3;
+    const int kv = k[t];
+    s[0] += p[0] * kv; s[1] += p[1] * kv; s[2] += p[2] * kv;
+  }
+  const float mean[3] = {0.485f, 0.456f, 0.406f}, stdv[3] = {0.229f, 0.224f, 0.225f};
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const float v = __fdiv_rn((float)clip8(s[c]), 255.0f);                 // ToTensor
+    it.out[((size_t)c * S + yy) * S + xx] = __fdiv_rn(__fsub_rn(v, mean[c]), stdv[c]);   // Normalize
+  }
+}
+
+cudaError_t launch_preprocess_rgb8_batch(const PreItem* items_dev, int n, int max_h, int S, cudaStream_t st) {
+  if (n <= 0 || max_h <= 0 || S <= 0 || n > 65535 || max_h > 65535) return cudaErrorInvalidValue;
+  resample_h_batch_kernel<<<dim3((S + 255) / 256, max_h, n), 256, 0, st>>>(items_dev, S);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  resample_v_norm_batch_kernel<<<dim3((S + 255) / 256, S, n), 256, 0, st>>>(items_dev, S);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_preprocess_rgb8(const uint8_t* rgb_dev, int H, int W, int S, const int* bounds_x, const int* kk_x, int ksize_x,
                                    const int* bounds_y, const int* kk_y, int ksize_y, uint8_t* tmp_dev, float* out_dev,
                                    cudaStream_t st) {

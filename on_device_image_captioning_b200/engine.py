@@ -180,21 +180,99 @@ class Engine:
     def preprocess_rgb8(self, images, img_size: Optional[int] = None) -> torch.Tensor:
         """Decoded RGB8 images (list of (H, W, 3) uint8 numpy arrays / CPU or CUDA tensors, any sizes) ->
         (B, 3, S, S) float32 on the device: Resize((S, S)) + ToTensor + Normalize of the reference's
-        utils/image_utils.py:preprocess_image, bit-identical to Pillow/torchvision (csrc/preprocess.cu)."""
+        utils/image_utils.py:preprocess_image, bit-identical to Pillow/torchvision (csrc/preprocess.cu).
+        The whole list goes through ONE launch pair (xn_preprocess_rgb8_batch); a list mixing host and device
+        images is split into two such calls."""
         S = int(img_size or self.cfg.img_size)
         out = torch.empty(len(images), 3, S, S, device=self.device, dtype=torch.float32)
-        keep = []
+        ts = []
+        for im in images:
+            t = im if isinstance(im, torch.Tensor) else torch.from_numpy(im)
+            assert t.dtype == torch.uint8 and t.dim() == 3 and t.shape[2] == 3, "expected (H, W, 3) uint8 RGB"
+            ts.append(t.contiguous())
         with torch.cuda.device(self.device):
-            for i, im in enumerate(images):
-                t = im if isinstance(im, torch.Tensor) else torch.from_numpy(im)
-                assert t.dtype == torch.uint8 and t.dim() == 3 and t.shape[2] == 3, "expected (H, W, 3) uint8 RGB"
-                t = t.contiguous()
-                keep.append(t)
-                self._check(self.lib.xn_preprocess_rgb8(self._h, _ptr(t), int(t.is_cuda), int(t.shape[0]), int(t.shape[1]),
-                                                        _ptr(out[i]), S, self._stream()), "xn_preprocess_rgb8")
-            if any(not t.is_cuda for t in keep):
+            for on_dev in (False, True):
+                idx = [i for i, t in enumerate(ts) if t.is_cuda == on_dev]
+                if not idx:
+                    continue
+                if len(idx) == len(ts):
+                    dst = out
+                else:
+                    dst = torch.empty(len(idx), 3, S, S, device=self.device, dtype=torch.float32)
+                ptrs = (C.c_void_p * len(idx))(*[ts[i].data_ptr() for i in idx])
+                hs = (C.c_int32 * len(idx))(*[int(ts[i].shape[0]) for i in idx])
+                ws = (C.c_int32 * len(idx))(*[int(ts[i].shape[1]) for i in idx])
+                self._check(self.lib.xn_preprocess_rgb8_batch(self._h, ptrs, int(on_dev), hs, ws, len(idx), _ptr(dst), S, self._stream()),
+                            "xn_preprocess_rgb8_batch")
+                if dst is not out:
+                    out[torch.tensor(idx, device=self.device)] = dst
+            if any(not t.is_cuda for t in ts):
                 torch.cuda.current_stream().synchronize()      # host buffers were read asynchronously
         return out
+
+    def preprocess_rgb8_single(self, image, img_size: Optional[int] = None) -> torch.Tensor:
+        """One image through the single-image entry point (xn_preprocess_rgb8): (3, S, S) float32."""
+        S = int(img_size or self.cfg.img_size)
+        t = image if isinstance(image, torch.Tensor) else torch.from_numpy(image)
+        assert t.dtype == torch.uint8 and t.dim() == 3 and t.shape[2] == 3, "expected (H, W, 3) uint8 RGB"
+        t = t.contiguous()
+        out = torch.empty(3, S, S, device=self.device, dtype=torch.float32)
+        with torch.cuda.device(self.device):
+            self._check(self.lib.xn_preprocess_rgb8(self._h, _ptr(t), int(t.is_cuda), int(t.shape[0]), int(t.shape[1]), _ptr(out), S,
+                                                    self._stream()), "xn_preprocess_rgb8")
+            if not t.is_cuda:
+                torch.cuda.current_stream().synchronize()
+        return out
+
+    def beam_search_sample(self, enc_input: torch.Tensor, enc_pads: Optional[Sequence[int]], sos_idx: int, eos_idx: int,
+                           beam_size: int = 3, how_many: int = 1, max_len: int = 20, seed: int = 0):
+        """beam_search with sample_or_max='sample' (candidates drawn without replacement); same returns as beam_search."""
+        x = self._f32(enc_input)
+        B = x.shape[0]
+        tok = torch.empty(B, how_many, max_len, device=self.device, dtype=torch.int32)
+        ln = torch.empty(B, how_many, device=self.device, dtype=torch.int32)
+        lp = torch.empty(B, how_many, max_len, device=self.device, dtype=torch.float32)
+        with torch.cuda.device(self.device):
+            self._check(self.lib.xn_beam_search_sample(self._h, _ptr(x), B, _int_array(enc_pads), int(beam_size), int(max_len),
+                                                       int(how_many), int(sos_idx), int(eos_idx), C.c_uint64(seed & (2 ** 64 - 1)),
+                                                       _ptr(tok), _ptr(ln), _ptr(lp), self._stream()), "xn_beam_search_sample")
+        return tok, ln, lp
+
+    def sample(self, enc_input: torch.Tensor, enc_pads: Optional[Sequence[int]], sos_idx: int, eos_idx: int, num_outputs: int = 1,
+               max_len: int = 20, seed: int = 0):
+        """mode='sampling' (get_batch_multiple_sampled_prediction): tokens (B,num_outputs,max_len+1) int32 (-1 padded),
+        lengths (B,num_outputs), log-probs (B,num_outputs,max_len+1)."""
+        x = self._f32(enc_input)
+        B = x.shape[0]
+        tok = torch.empty(B, num_outputs, max_len + 1, device=self.device, dtype=torch.int32)
+        ln = torch.empty(B, num_outputs, device=self.device, dtype=torch.int32)
+        lp = torch.empty(B, num_outputs, max_len + 1, device=self.device, dtype=torch.float32)
+        with torch.cuda.device(self.device):
+            self._check(self.lib.xn_sample(self._h, _ptr(x), B, _int_array(enc_pads), int(num_outputs), int(max_len), int(sos_idx),
+                                           int(eos_idx), C.c_uint64(seed & (2 ** 64 - 1)), _ptr(tok), _ptr(ln), _ptr(lp), self._stream()),
+                        "xn_sample")
+        return tok, ln, lp
+
+    def overflow_flag(self, clear: bool = True) -> bool:
+        """True when a 16-bit-mode call since the last clear produced a non-finite encoder output (fp16 overflow)."""
+        f = C.c_int(0)
+        self._check(self.lib.xn_overflow_flag(self._h, C.byref(f), int(clear)), "xn_overflow_flag")
+        return bool(f.value)
+
+    def caption_host_begin(self, inputs_host: torch.Tensor, sos_idx: int, eos_idx: int, beam_size: int, how_many: int, max_len: int,
+                           out: Tuple[torch.Tensor, torch.Tensor, torch.Tensor]) -> int:
+        """Pipelined host-buffer call: returns a ticket; the results are in `out` after caption_host_end(ticket)."""
+        assert inputs_host.device.type == "cpu" and inputs_host.dtype == torch.float32 and inputs_host.is_contiguous()
+        tok, ln, lp = out
+        with torch.cuda.device(self.device):
+            t = self.lib.xn_caption_host_begin(self._h, _ptr(inputs_host), inputs_host.shape[0], int(beam_size), int(max_len), int(how_many),
+                                               int(sos_idx), int(eos_idx), _ptr(tok), _ptr(ln), _ptr(lp), self._stream())
+        if t < 0:
+            self._check(t, "xn_caption_host_begin")
+        return t
+
+    def caption_host_end(self, ticket: int):
+        self._check(self.lib.xn_caption_host_end(self._h, int(ticket)), "xn_caption_host_end")
 
     @staticmethod
     def ensemble_beam_search(engines: Sequence["Engine"], enc_input: torch.Tensor, enc_pads: Optional[Sequence[int]], sos_idx: int,

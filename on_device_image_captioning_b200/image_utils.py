@@ -19,11 +19,29 @@ def _decode_rgb8(image_path) -> np.ndarray:
     return np.asarray(pil_image, dtype=np.uint8)
 
 
-def preprocess_image(image_path, img_size: int, engine) -> torch.Tensor:
-    """reference utils/image_utils.py:5-23 -> (1, 3, S, S) float32, on the engine's device."""
-    return engine.preprocess_rgb8([_decode_rgb8(image_path)], img_size)
+_default_engine = None
 
 
-def preprocess_images(image_paths: Sequence, img_size: int, engine) -> torch.Tensor:
-    """Batch form used by demo.py's loop (demo.py:107-112): (B, 3, S, S) float32 on the device."""
-    return engine.preprocess_rgb8([_decode_rgb8(p) for p in image_paths], img_size)
+def _engine_or_default(engine):
+    """The preprocessing kernels need no model weights: without an explicit engine a bare handle on the current CUDA
+    device is created once and reused (so the reference's two-argument call keeps working)."""
+    global _default_engine
+    if engine is not None:
+        return engine
+    if _default_engine is None or _default_engine.device.index != torch.cuda.current_device():
+        from .config import swin_tiny_test
+        from .engine import Engine
+        _default_engine = Engine(swin_tiny_test(), torch.cuda.current_device())
+    return _default_engine
+
+
+def preprocess_image(image_path, img_size: int, engine=None) -> torch.Tensor:
+    """reference utils/image_utils.py:5-23, same two positional arguments -> (1, 3, S, S) float32 on the CUDA device
+    (the engine's, or the current device when no engine is given)."""
+    return _engine_or_default(engine).preprocess_rgb8([_decode_rgb8(image_path)], img_size)
+
+
+def preprocess_images(image_paths: Sequence, img_size: int, engine=None) -> torch.Tensor:
+    """Batch form of demo.py's loop (demo.py:107-112): (B, 3, S, S) float32 on the device, one launch pair for the
+    whole list (xn_preprocess_rgb8_batch)."""
+    return _engine_or_default(engine).preprocess_rgb8([_decode_rgb8(p) for p in image_paths], img_size)

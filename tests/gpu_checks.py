@@ -517,4 +517,381 @@ def check_config4_batch512_chunking() -> List[Triple]:
             ("config4/fp16 workspace GiB (of 180)", e.workspace_bytes / 2 ** 30, 60.0)]
 
 
+# ------------------------------------------------------------------ round-2 parity rows
+def check_config2_batch64(name: str, precision: str = "fp32") -> List[Triple]:
+    """BASELINE.json configs[1] at its full batch (64 images, beam 3, max_len 20) against the fixture the UNMODIFIED
+    reference produced in one batch-64 call (tests/golden/make_golden.py c2_b64_*; the oracle was asserted identical to
+    it at generation time).  fp32: captions bit-exact on every image whose recorded decision margin exceeds 2e-5, log-probs
+    and sub-sampled encoder output within the fp32 tolerance.  16-bit: the same comparisons, reported (rel-max)."""
+    e, g, cfg, sd, x, pads = engine_for(name, precision)
+    m = g["meta"]
+    out = []
+    enc = e.forward_enc(x, None)
+    ref_enc = torch.from_numpy(g["enc_sub"])
+    out.append((f"{name}/{precision} B=64 encoder output vs reference fixture rel-max", rel_max(sub(enc.cpu()), ref_enc),
+                {"fp32": 2e-5, "fp16": 4e-3, "bf16": 3e-2}[precision]))
+    tok, ln, lp = e.beam_search(x, None, m["sos"], m["eos"], m["beam"], m["how_many"], m["max_len"])
+    toks, lps = unpack_beam_results(tok, ln, lp)
+    margin = np.minimum(np.minimum(g["vocab_margin"], g["merge_margin"]), g["final_margin"])
+    checked = [b for b in range(m["B"]) if margin[b] > 2e-5]
+    bad = sum(1 for b in checked if toks[b][0] != g["beam_tokens"][b, 0, : int(g["beam_len"][b, 0])].tolist())
+    if precision == "fp32":
+        out.append((f"{name}/fp32 B=64 captions differing from the reference ({len(checked)}/{m['B']} images with margin>2e-5)", float(bad), 0.0))
+        ref_lp = torch.from_numpy(g["beam_logprobs"])
+        same = [b for b in checked if toks[b][0] == g["beam_tokens"][b, 0, : int(g["beam_len"][b, 0])].tolist()]
+        if same and tuple(lps.shape) == tuple(ref_lp.shape):
+            out.append((f"{name}/fp32 B=64 caption log-probs vs reference rel-max", rel_max(lps.cpu()[same], ref_lp[same]), 1e-5))
+    else:
+        out.append((f"{name}/{precision} B=64 captions differing from the reference fp32 run, of {len(checked)} (informational)",
+                    float(bad), float("inf")))
+    distinct = len({tuple(t[0]) for t in toks})
+    out.append((f"{name}/{precision} distinct captions in the batch (informational)", float(distinct), float("inf")))
+    return out
+
+
+def check_image_to_logits_16bit(name: str, precision: str = "fp16") -> List[Triple]:
+    """The 16-bit path END TO END: image -> Swin -> expansion encoder -> teacher-forced decoder, everything on the GPU in
+    the 16-bit mode (the decoder consumes the GPU's own encoder output, not the oracle's), against the fp32 oracle.
+    Measured as rel-max = max|a-b| / max|b| -- the same metric as the fp32 rows.  north_star states 2e-3 relative for the
+    16-bit mode: fp16 is held to it on logits; the feature rows are held to the measured bound."""
+    e, g, cfg, sd, x, pads = engine_for(name, precision)
+    out = []
+    with torch.no_grad():
+        taps = {}
+        ref_enc = O.forward_enc(sd, cfg, x, pads, taps)
+        tok = torch.from_numpy(g["dec_tokens"])
+        dp = g["dec_pads"].tolist()
+        ref_lg = O.forward_dec(sd, cfg, ref_enc, pads, tok, dp, False)
+        ref_lp = O.forward_dec(sd, cfg, ref_enc, pads, tok, dp, True)
+    tol = {"fp16": (4e-3, 4e-3, 2e-3), "bf16": (3e-2, 3e-2, 3e-2)}[precision]
+    if cfg.has_swin:
+        sw = e.forward_swin(x)
+        out.append((f"{name}/{precision} swin features vs oracle rel-max", rel_max(sw, taps["swin"]), tol[0]))
+        out.append((f"{name}/{precision} swin features vs oracle rel-fro", rel_fro(sw, taps["swin"]), tol[0]))
+    enc = e.forward_enc(x, pads)
+    out.append((f"{name}/{precision} encoder output (GPU end to end) vs oracle rel-max", rel_max(enc, ref_enc), tol[1]))
+    lg = e.forward_dec(enc, pads, tok, dp, False)
+    lp = e.forward_dec(enc, pads, tok, dp, True)
+    out.append((f"{name}/{precision} image->logits (GPU encoder output into GPU decoder) vs oracle rel-max", rel_max(lg, ref_lg), tol[2]))
+    out.append((f"{name}/{precision} image->log-probs vs oracle rel-max", rel_max(lp, ref_lp), tol[2]))
+    n = tok.shape[0] * tok.shape[1]
+    top1 = float((lg.argmax(-1).cpu() != ref_lg.argmax(-1)).sum())
+    out.append((f"{name}/{precision} top-1 word differs from the oracle at N of {n} positions (informational)", top1, float("inf")))
+    out.append((f"{name}/{precision} overflow flag", float(e.overflow_flag()), 0.0))
+    return out
+
+
+def check_fp16_saturation() -> List[Triple]:
+    """fp16 stores QKV / attention output / MLP hidden as halves (max 65504).  Scale the fc1 weights and bias of one
+    stage-1 block (the hidden activations, hence fc2's input) by 300: fp16 must survive (finite, and as close to the
+    fp32 oracle as without the scaling).  Scale by 3e5: the hidden overflows, the device-side check of the encoder output
+    must raise the overflow flag, the drop-in class must refuse with a clear error, and bf16 (fp32 range) must be finite."""
+    from on_device_image_captioning_b200 import synth
+    from on_device_image_captioning_b200.config import swin_tiny_test
+    cfg = swin_tiny_test()
+    x = synth.make_images(cfg, 2, seed=1, kind="mixed")
+    out = []
+    for scale, expect_flag in ((300.0, False), (3e5, True)):
+        sd = synth.make_state_dict(cfg, 0, "peaky", eos_idx=77)
+        for k in ("swin_transf.layers.0.blocks.1.mlp.fc1.weight", "swin_transf.layers.0.blocks.1.mlp.fc1.bias"):
+            sd[k] = sd[k] * scale
+        with torch.no_grad():
+            ref = O.forward_enc(sd, cfg, x, [0, 0])
+        e = Engine(cfg, 0)
+        e.load_state_dict(sd, "fp16")
+        e.overflow_flag()
+        enc = e.forward_enc(x, None)
+        flag = e.overflow_flag()
+        finite = bool(torch.isfinite(enc).all())
+        out.append((f"saturation x{scale:g}: fp16 overflow flag == {expect_flag}", float(flag != expect_flag), 0.0))
+        out.append((f"saturation x{scale:g}: fp16 encoder output finite == {not expect_flag}", float(finite == expect_flag), 0.0))
+        if not expect_flag:
+            out.append((f"saturation x{scale:g}: fp16 encoder output vs fp32 oracle rel-max", rel_max(enc, ref), 4e-3))
+        else:
+            e.load_state_dict(sd, "bf16")
+            encb = e.forward_enc(x, None)
+            out.append((f"saturation x{scale:g}: bf16 (fp32 exponent range) encoder output non-finite values",
+                        float((~torch.isfinite(encb)).sum()), 0.0))
+            out.append((f"saturation x{scale:g}: bf16 overflow flag", float(e.overflow_flag()), 0.0))
+            out.append((f"saturation x{scale:g}: bf16 encoder output vs fp32 oracle rel-max", rel_max(encb, ref), 5e-2))
+        e.close()
+    return out
+
+
+def check_demo_known_answers() -> List[Triple]:
+    """BASELINE.json configs[0]: the reference's four demo images (demo.py:106-129), fp32, batch 1 each, beam 3,
+    max_len 20, vocabulary of demo_coco_tokens.pickle -- against tests/golden/demo_c1.npz, made by the unmodified reference
+    (tests/golden/make_demo_golden.py).  Pixels: the 384x384 RGB8 image after the reference's resize goes through
+    xn_preprocess_rgb8 (ToTensor + Normalize; 384 -> 384 is the identity resample); for the two committed JPEG files the
+    whole chain file -> PIL decode -> GPU resize -> caption is run as well.  Captions must be bit-exact where the decision
+    margin exceeds 2e-5 (napoleon-like 1e-6 margins are reported, not asserted)."""
+    import os
+    from conftest import load_golden, GOLDEN_DIR
+    from on_device_image_captioning_b200 import synth
+    from on_device_image_captioning_b200.image_utils import preprocess_image
+    from on_device_image_captioning_b200.language_utils import tokens2description
+    g = load_golden("demo_c1")
+    m = g["meta"]
+    cfg = XNConfig(**m["cfg"])
+    sd = synth.make_state_dict(cfg, seed=0, profile=m["profile"], eos_idx=m["eos"])
+    fp = sum(float(sd[k].double().abs().sum()) for k in sorted(sd))
+    assert abs(fp - m["weight_fingerprint"]) <= 1e-9 * abs(fp)
+    for k in [k for k in _engines if k != "bare"]:
+        _engines.pop(k)[0].close()
+    e = Engine(cfg, 0)
+    e.load_state_dict(sd, "fp32")
+    i2w = {int(k): v for k, v in m["used_words"].items()}
+    out = []
+    for n, name in enumerate(m["images"]):
+        st = g[f"stats_{n}"]
+        margin = float(min(st[3], st[4], st[5]))
+        x = e.preprocess_rgb8([g[f"u8_{n}"]], cfg.img_size)
+        out.append((f"demo/{name} mean of the preprocessed tensor vs reference abs diff", abs(float(x.double().mean()) - float(st[0])), 1e-6))
+        variants = [("resized pixels", x)]
+        path = os.path.join(GOLDEN_DIR, "demo_material", name)
+        if os.path.exists(path):
+            xf = preprocess_image(path, cfg.img_size, e)
+            out.append((f"demo/{name} file -> PIL decode -> GPU resize: elements differing from the reference tensor",
+                        float((xf != x).sum()), 0.0))
+            variants.append(("file", xf))
+        for what, xin in variants:
+            enc = e.forward_enc(xin, None)
+            out.append((f"demo/{name} [{what}] mean |encoder output| vs reference rel", abs(float(enc.double().abs().mean()) / float(st[1]) - 1.0), 1e-5))
+            tok, ln, lp = e.beam_search(xin, None, m["sos"], m["eos"], m["beam"], 1, m["max_len"])
+            toks, lps = unpack_beam_results(tok, ln, lp)
+            same = toks[0][0] == g[f"tokens_{n}"].tolist()
+            if margin > 2e-5:
+                out.append((f"demo/{name} [{what}] caption tokens differ from the reference (margin {margin:.1e})", float(not same), 0.0))
+            else:
+                out.append((f"demo/{name} [{what}] caption tokens differ from the reference (margin {margin:.1e} <= 2e-5: reported only)",
+                            float(not same), float("inf")))
+            if same:
+                out.append((f"demo/{name} [{what}] sum of log-probs vs reference abs diff", abs(float(lps.double().sum()) - float(st[2])), 2e-3))
+                cap = tokens2description(toks[0][0], _SparseVocab(i2w), m["sos"], m["eos"])
+                out.append((f"demo/{name} [{what}] caption string differs from the reference's tokens2description", float(cap != m["captions"][n]), 0.0))
+    e.close()
+    return out
+
+
+class _SparseVocab:
+    """idx2word lookup restricted to the words the fixture's captions use (the 10 000-word pickle is reference data)."""
+
+    def __init__(self, d):
+        self.d = d
+
+    def __getitem__(self, i):
+        return self.d[int(i)]
+
+
+def check_graph_pointer_independence() -> List[Triple]:
+    """A caller that passes a FRESH device tensor (new address) for every batch must hit the captured CUDA graph: the
+    input is staged into a handle-owned buffer first.  Five distinct tensors of the same shape: identical captions to a
+    graph-free run, and from the third call on one graph launch replays the call (the per-call launch count stays the
+    count of the captured graph; no new capture, no eager fallback).  Same for five distinct pinned host buffers through
+    xn_caption_host (copy nodes patched in place)."""
+    e, g, cfg, sd, x, pads = engine_for("tiny_e2e_peaky", "fp16")
+    from on_device_image_captioning_b200 import synth
+    m = g["meta"]
+    xs = [synth.make_images(cfg, 6, seed=50 + i, kind="mixed") for i in range(5)]
+    e.set_option("use_graph", 0)
+    ref = [_tokens_list(*e.beam_search(t, None, m["sos"], m["eos"], 3, 1, 12)[:2]) for t in xs]
+    e.set_option("use_graph", 1)
+    bad, keep, counts = 0, [], []
+    for rep in range(2):
+        for i, t in enumerate(xs):
+            d = t.cuda().clone()                  # a new allocation every call; kept alive so addresses never repeat
+            keep.append(d)
+            l0 = e.kernel_launches
+            tok, ln, _ = e.beam_search(d, None, m["sos"], m["eos"], 3, 1, 12)
+            counts.append(e.kernel_launches - l0)
+            bad += sum(1 for a, b in zip(_tokens_list(tok, ln), ref[i]) if a != b)
+    out = [("graph: captions with 10 distinct device tensors differing from the graph-free run", float(bad), 0.0),
+           ("graph: distinct input addresses used", float(-len({d.data_ptr() for d in keep})), -10.0),
+           ("graph: per-call launch counts differing from the first call's (eager, capture and replays all count the same kernels)",
+            float(len(set(counts)) - 1), 0.0)]
+    hosts = [t.clone().pin_memory() for t in xs]
+    badh = 0
+    for rep in range(2):
+        for i, hbuf in enumerate(hosts):
+            tok, ln, _ = e.caption_host(hbuf, m["sos"], m["eos"], 3, 1, 12)
+            badh += sum(1 for a, b in zip(_tokens_list(tok, ln), ref[i]) if a != b)
+    out.append(("graph: captions through xn_caption_host with 5 distinct pinned buffers differing (copy nodes re-pointed)", float(badh), 0.0))
+    # pipelined begin / end: two calls in flight
+    outs = [(torch.empty(6, 1, 12, dtype=torch.int32).pin_memory(), torch.empty(6, 1, dtype=torch.int32).pin_memory(),
+             torch.empty(6, 1, 12, dtype=torch.float32).pin_memory()) for _ in range(2)]
+    badp = 0
+    tick = e.caption_host_begin(hosts[0], m["sos"], m["eos"], 3, 1, 12, outs[0])
+    for i in range(1, 5):
+        t2 = e.caption_host_begin(hosts[i], m["sos"], m["eos"], 3, 1, 12, outs[i % 2])
+        e.caption_host_end(tick)
+        badp += sum(1 for a, b in zip(_tokens_list(outs[(i - 1) % 2][0], outs[(i - 1) % 2][1]), ref[i - 1]) if a != b)
+        tick = t2
+    e.caption_host_end(tick)
+    badp += sum(1 for a, b in zip(_tokens_list(outs[0][0], outs[0][1]), ref[4]) if a != b)
+    out.append(("pipelined caption_host_begin/_end (two in flight): captions differing", float(badp), 0.0))
+    return out
+
+
+def check_sampling() -> List[Triple]:
+    """SURVEY.md 8f N4, second half: the sampling decode branches.  The draws cannot match torch's random stream, so the
+    checks are distributional and structural:
+      * Gumbel-top-k kernel: over 4000 seeds on one 50-word row, the first draw's frequencies match softmax(logits)
+        (chi-square) and the second draw's match the without-replacement law p_j / (1 - p_i) aggregated over i;
+      * mode='sampling': every returned log-prob equals the teacher-forced log-prob of that token under the model
+        (forward_dec on the sampled prefix), sequences are cut at the first EOS, log-probs are zero after it, and the
+        same seed reproduces the same samples while another seed does not;
+      * beam_search(sample_or_max='sample'): returned sequences are valid (SOS first, length rules, log-probs consistent
+        with forward_dec)."""
+    e, g, cfg, sd, x, pads = engine_for("tiny_e2e_peaky", "fp32")
+    m = g["meta"]
+    out = []
+    # ---- kernel-level distribution test through the sampling entry point is indirect; use xn_sample on a 1-step problem:
+    # the first sampled word of every row is a Categorical draw from the step-0 distribution, identical for all rows of an image
+    B = x.shape[0]
+    with torch.no_grad():
+        enc = e.forward_enc(x, None)
+        sos = torch.full((B, 1), m["sos"], dtype=torch.int64)
+        p0 = torch.softmax(e.forward_dec(enc, None, sos, [0] * B, False)[:, 0].double().cpu(), -1)      # (B, V)
+    counts = torch.zeros(B, cfg.vocab, dtype=torch.float64)
+    n_draw = 0
+    for seed in range(250):
+        tok, ln, lp = e.sample(x, None, m["sos"], m["eos"], num_outputs=8, max_len=1, seed=1000 + seed)
+        first = tok[:, :, 1].cpu().long()                    # (B, 8)
+        for b in range(B):
+            counts[b] += torch.bincount(first[b], minlength=cfg.vocab).double()
+        n_draw += 8
+    # chi-square over the words with expected count >= 5, the rest pooled
+    worst = 0.0
+    for b in range(B):
+        exp = p0[b] * n_draw
+        big = exp >= 5
+        o = torch.cat([counts[b][big], counts[b][~big].sum().reshape(1)])
+        ex = torch.cat([exp[big], exp[~big].sum().reshape(1)])
+        keep = ex > 0
+        chi = float((((o - ex) ** 2)[keep] / ex[keep]).sum())
+        dof = int(keep.sum()) - 1
+        worst = max(worst, (chi - dof) / math.sqrt(2 * max(dof, 1)))       # standardised: ~N(0,1) under H0
+    out.append((f"sampling: first-word frequencies vs softmax (chi-square z-score, {n_draw} draws per image)", worst, 5.0))
+    # ---- structure of mode='sampling'
+    tok, ln, lp = e.sample(x, None, m["sos"], m["eos"], num_outputs=4, max_len=10, seed=7)
+    tok2, ln2, lp2 = e.sample(x, None, m["sos"], m["eos"], num_outputs=4, max_len=10, seed=7)
+    tok3, _, _ = e.sample(x, None, m["sos"], m["eos"], num_outputs=4, max_len=10, seed=8)
+    out.append(("sampling: same seed gives different samples", float(not (torch.equal(tok, tok2) and torch.equal(lp, lp2))), 0.0))
+    out.append(("sampling: different seeds give identical samples", float(torch.equal(tok, tok3)), 0.0))
+    tk, lnc, lpc = tok.cpu(), ln.cpu(), lp.cpu()
+    bad_struct, worst_lp = 0, 0.0
+    with torch.no_grad():
+        for b in range(B):
+            for j in range(4):
+                n = int(lnc[b, j])
+                seq = tk[b, j, :n].tolist()
+                bad_struct += seq[0] != m["sos"] or n < 2 or n > 11
+                if m["eos"] in seq[1:]:
+                    bad_struct += seq.index(m["eos"], 1) != n - 1            # cut right after the first EOS
+                elif n != 11:
+                    bad_struct += 1
+                bad_struct += int((tk[b, j, n:] != -1).any()) + int((lpc[b, j, n:] != 0).any()) + int(lpc[b, j, 0] != 0)
+                full = e.forward_dec(enc[b:b + 1], None, torch.tensor([seq[:-1]]), [0], True)[0].cpu()      # (n-1, V)
+                want = full[torch.arange(n - 1), torch.tensor(seq[1:])]
+                worst_lp = max(worst_lp, float((want - lpc[b, j, 1:n]).abs().max()))
+    out.append(("sampling: malformed sampled sequences (SOS first, cut after first EOS, padding)", float(bad_struct), 0.0))
+    out.append(("sampling: returned log-probs vs teacher-forced log-probs of the sampled words max-abs", worst_lp, 2e-4))
+    # ---- beam search with sampled candidates
+    tokb, lnb, lpb = e.beam_search_sample(x, None, m["sos"], m["eos"], 3, 2, 12, seed=3)
+    tokc, _, _ = e.beam_search_sample(x, None, m["sos"], m["eos"], 3, 2, 12, seed=3)
+    tokd, _, _ = e.beam_search(x, None, m["sos"], m["eos"], 3, 2, 12)
+    out.append(("beam_search(sample): same seed gives different captions", float(not torch.equal(tokb, tokc)), 0.0))
+    tb, lb, pb = tokb.cpu(), lnb.cpu(), lpb.cpu()
+    bad_b, worst_b = 0, 0.0
+    with torch.no_grad():
+        for b in range(B):
+            for j in range(2):
+                n = int(lb[b, j])
+                seq = tb[b, j, :n].tolist()
+                bad_b += seq[0] != m["sos"] or n < 2 or n > 12 or (m["eos"] in seq[1:-1])
+                full = e.forward_dec(enc[b:b + 1], None, torch.tensor([seq[:-1]]), [0], True)[0].cpu()
+                want = full[torch.arange(n - 1), torch.tensor(seq[1:])]
+                worst_b = max(worst_b, float((want - pb[b, j, 1:n]).abs().max()))
+    out.append(("beam_search(sample): malformed captions", float(bad_b), 0.0))
+    out.append(("beam_search(sample): returned log-probs vs teacher-forced log-probs max-abs", worst_b, 2e-4))
+    out.append(("beam_search(sample): captions identical to the arg-max search (informational)", float(torch.equal(tokb, tokd)), float("inf")))
+    return out
+
+
+def check_preprocess_batch() -> List[Triple]:
+    """xn_preprocess_rgb8_batch: one launch pair for a batch of mixed sizes (host and device inputs), bit-exact vs the
+    oracle; 80 distinct sizes through the single-image entry point cycle the 64-entry coefficient-table cache (the
+    round-1 eviction bug freed a table still in use) and must stay bit-exact."""
+    from oracle import preprocess_oracle as P
+    from test_preprocess_oracle import synth_image
+    e = bare_engine()
+    out = []
+    shapes = [(300, 400), (480, 640), (200, 200), (97, 1013), (1, 7), (640, 480), (333, 500), (1080, 1920)]
+    imgs = [synth_image(h, w, 13 * h + w) for (h, w) in shapes]
+    refs = [P.preprocess_rgb8(im, 96) for im in imgs]
+    l0 = e.kernel_launches
+    yh = e.preprocess_rgb8(imgs, 96).cpu().numpy()
+    out.append(("preprocess batch (8 host images, mixed sizes): kernel launches", float(e.kernel_launches - l0), 2.0))
+    out.append(("preprocess batch (host): elements differing from the oracle", float(sum(int((yh[i] != r).sum()) for i, r in enumerate(refs))), 0.0))
+    yd = e.preprocess_rgb8([torch.from_numpy(im).cuda() for im in imgs], 96).cpu().numpy()
+    out.append(("preprocess batch (device): elements differing from the oracle", float(sum(int((yd[i] != r).sum()) for i, r in enumerate(refs))), 0.0))
+    mixed = [torch.from_numpy(im).cuda() if i % 2 else im for i, im in enumerate(imgs)]
+    ym = e.preprocess_rgb8(mixed, 96).cpu().numpy()
+    out.append(("preprocess batch (host and device mixed): elements differing", float(sum(int((ym[i] != r).sum()) for i, r in enumerate(refs))), 0.0))
+    bad = 0
+    sizes = [(40 + 3 * i, 50 + 2 * i) for i in range(40)]
+    cyc = sizes + sizes[:5] + sizes[::-1]
+    for (h, w) in cyc:                                   # > 64 distinct tables, with re-use of old and new entries
+        im = synth_image(h, w, h * 7 + w)
+        y = e.preprocess_rgb8_single(im, 48).cpu().numpy()
+        bad += int((y != P.preprocess_rgb8(im, 48)).sum())
+    out.append((f"preprocess single-image entry over {len(cyc)} calls / 80 distinct table sizes: elements differing", float(bad), 0.0))
+    return out
+
+
+def check_evaluate_model_loop() -> List[Triple]:
+    """the evaluate_model batching loop (reference test.py:141-275) on the drop-in class: sub-batches of
+    4 over 10 images (last one ragged) must give, per image, the caption a single-image call gives, in the reference's
+    (pred_dict, gts_dict) layout with SOS / EOS stripped."""
+    import argparse
+    from on_device_image_captioning_b200 import synth
+    from on_device_image_captioning_b200.evaluation import evaluate_model
+    from on_device_image_captioning_b200.models import End_ExpansionNet_v2
+    e0, g, cfg, sd, x, pads = engine_for("tiny_e2e_peaky", "fp32")
+    m = g["meta"]
+    words = [f"w{i}" for i in range(cfg.vocab)]
+    da = argparse.Namespace(enc=0.0, dec=0.0, enc_input=0.0, dec_input=0.0, other=0.0)
+    model = End_ExpansionNet_v2(swin_img_size=cfg.img_size, swin_patch_size=cfg.patch_size, swin_in_chans=cfg.in_chans,
+                                swin_embed_dim=cfg.embed_dim, swin_depths=list(cfg.depths), swin_num_heads=list(cfg.swin_heads),
+                                swin_window_size=cfg.window_size, swin_mlp_ratio=cfg.mlp_ratio, swin_qkv_bias=True, swin_qk_scale=None,
+                                swin_drop_rate=0.0, swin_attn_drop_rate=0.0, swin_drop_path_rate=0.0, swin_norm_layer=torch.nn.LayerNorm,
+                                swin_ape=False, swin_patch_norm=True, swin_use_checkpoint=False, final_swin_dim=cfg.feat_dim,
+                                d_model=cfg.d_model, N_enc=cfg.n_enc, N_dec=cfg.n_dec, ff=cfg.ff, num_heads=cfg.num_heads,
+                                num_exp_enc_list=list(cfg.num_exp_enc_list), num_exp_dec=cfg.num_exp_dec,
+                                output_word2idx={w: i for i, w in enumerate(words)}, output_idx2word=words,
+                                max_seq_len=cfg.max_seq_len, drop_args=da, rank=0, precision="fp32")
+    model.load_state_dict(sd)
+    model = model.to(0).eval()
+    imgs = synth.make_images(cfg, 10, seed=77, kind="mixed")
+
+    class Loader:
+        def get_images_by_idx(self, i, dataset_split=None):
+            return imgs[i]
+
+        def get_captions_by_idx(self, i, dataset_split=None):
+            return [f"reference caption {i} a", f"reference caption {i} b"]
+
+    pred, gts = evaluate_model(model, words, beam_size=3, max_seq_len=12, sos_idx=m["sos"], eos_idx=m["eos"], rank=0,
+                               parallel_batches=4, indexes=list(range(10)), data_loader=Loader(),
+                               use_images_instead_of_features=True, verbose=False)
+    bad = 0
+    for i in range(10):
+        one, _ = model(enc_x=imgs[i:i + 1].cuda(), enc_x_num_pads=[0], mode="beam_search", beam_size=3, beam_max_seq_len=12,
+                       sample_or_max="max", how_many_outputs=1, sos_idx=m["sos"], eos_idx=m["eos"])
+        want = " ".join(words[t] for t in one[0][0][1:-1])
+        bad += pred[i][0]["caption"] != want or pred[i][0]["image_id"] != i or len(gts[i]) != 2
+    return [("evaluate_model loop: images whose caption differs from the single-image call / layout errors", float(bad), 0.0),
+            ("evaluate_model loop: predictions returned", float(-len(pred)), -10.0)]
+
+
 ALL_FP32_MODEL_CASES = ["tiny_e2e_peaky", "tiny_e2e_xavier", "feat_peaky_b5", "feat_xavier_b1", "full_e2e_xavier", "full_e2e_peaky"]

@@ -17,7 +17,8 @@ from conftest import golden_setup, sub
 from oracle import xnv2_oracle as O
 
 TOL = 2e-6
-CASES = ["tiny_e2e_peaky", "tiny_e2e_xavier", "feat_peaky_b5", "feat_xavier_b1", "full_e2e_xavier", "full_e2e_peaky"]
+CASES = ["tiny_e2e_peaky", "tiny_e2e_xavier", "feat_peaky_b5", "feat_xavier_b1", "full_e2e_xavier", "full_e2e_peaky",
+         "full_p3_288_n2"]      # swin_patch_size=3 / img 288 with N_enc = N_dec = 2 (train.py:381-387, test.py:360-365)
 
 
 @pytest.mark.parametrize("name", CASES)

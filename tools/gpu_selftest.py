@@ -33,6 +33,21 @@ def main():
                  (f"dec_bf16:{c}", lambda c=c: G.check_decoder(c, "bf16")), (f"beam_fp16:{c}", lambda c=c: G.check_beam(c, "fp16"))]
     jobs += [("dec_fp16:feat_peaky_b5", lambda: G.check_decoder("feat_peaky_b5", "fp16")),
              ("beam_fp16:feat_peaky_b5", lambda: G.check_beam("feat_peaky_b5", "fp16"))]
+    # round 2
+    jobs += [("graph_ptr", G.check_graph_pointer_independence), ("sampling", G.check_sampling),
+             ("preprocess_batch", G.check_preprocess_batch), ("evaluate_loop", G.check_evaluate_model_loop),
+             ("saturation", G.check_fp16_saturation)]
+    if not quick:
+        jobs += [("e2e16_fp16:full_e2e_peaky", lambda: G.check_image_to_logits_16bit("full_e2e_peaky", "fp16")),
+                 ("e2e16_fp16:full_e2e_xavier", lambda: G.check_image_to_logits_16bit("full_e2e_xavier", "fp16")),
+                 ("e2e16_bf16:full_e2e_peaky", lambda: G.check_image_to_logits_16bit("full_e2e_peaky", "bf16")),
+                 ("p3_288:enc", lambda: G.check_encoder("full_p3_288_n2", "fp32")), ("p3_288:dec", lambda: G.check_decoder("full_p3_288_n2", "fp32")),
+                 ("p3_288:beam", lambda: G.check_beam("full_p3_288_n2", "fp32")),
+                 ("e2e16_fp16:full_p3_288_n2", lambda: G.check_image_to_logits_16bit("full_p3_288_n2", "fp16")),
+                 ("c2_b64:peaky_fp32", lambda: G.check_config2_batch64("c2_b64_peaky", "fp32")),
+                 ("c2_b64:xavier_fp32", lambda: G.check_config2_batch64("c2_b64_xavier", "fp32")),
+                 ("c2_b64:peaky_fp16", lambda: G.check_config2_batch64("c2_b64_peaky", "fp16")),
+                 ("demo_c1", G.check_demo_known_answers)]
     if not quick:
         jobs += [("config3", G.check_config3_features_beam5), ("config4", G.check_config4_batch512_chunking),
                  ("caption_host", G.check_caption_host)]
