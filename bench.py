@@ -283,7 +283,7 @@ def run_ours(args):
                 dist.all_gather_into_tensor(gathered, outs[(i - 1) % 2][0].to(dev, non_blocking=True))
             tick = nxt
 
-    e2e_run(max(4, args.warmup))                        # both staging slots: eager, capture, replay
+    e2e_run(max(6, args.warmup))                        # both staging slots: eager, capture, replay
     barrier()
     e0.record()
     e2e_run(args.steps)

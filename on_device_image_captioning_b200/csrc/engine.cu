@@ -293,6 +293,7 @@ template <> struct ActOps<bf16> {
     return lin_tc(h, x, ldx, w, res, ldr, y, nullptr, ldy, M, 0, 0, st);
   }
   static cudaError_t attn(const bf16* qkv, const float* rpb, bf16* o, int B, int H, int C, int heads, int shift, cudaStream_t st) {
+    if (g_attn_tc && window_attention_tc_supported(B, H, C, heads, shift)) return launch_window_attention_tc<bf16>(qkv, rpb, o, B, H, C, heads, shift, st);
     return launch_window_attention_mma<bf16>(qkv, rpb, o, B, H, C, heads, shift, st);
   }
 };
@@ -304,6 +305,7 @@ template <> struct ActOps<f16> {
     return lin_tc(h, x, ldx, w, res, ldr, y, nullptr, ldy, M, 0, 1, st);
   }
   static cudaError_t attn(const f16* qkv, const float* rpb, f16* o, int B, int H, int C, int heads, int shift, cudaStream_t st) {
+    if (g_attn_tc && window_attention_tc_supported(B, H, C, heads, shift)) return launch_window_attention_tc<f16>(qkv, rpb, o, B, H, C, heads, shift, st);
     return launch_window_attention_mma<f16>(qkv, rpb, o, B, H, C, heads, shift, st);
   }
 };
@@ -1850,8 +1852,10 @@ int xn_caption_host_begin(xn_handle* h, const float* input_host, int B, int beam
   }
   if (sl.pending) return h->fail(XN_ERR_STATE, "caption_host slot %d still has an un-ended call (at most two calls in flight)", k);
   if (sl.in_cap < in_bytes || sl.out_cap < out_bytes) {
-    CU(cudaDeviceSynchronize());
-    h->drop_graphs();
+    if (sl.in || sl.out) {                            // replacing a buffer that cached graphs may read: drop them
+      CU(cudaDeviceSynchronize());
+      h->drop_graphs();
+    }
     if (sl.in_cap < in_bytes) { if (sl.in) cudaFree(sl.in); sl.in = nullptr; sl.in_cap = 0; CU(cudaMalloc(&sl.in, in_bytes)); sl.in_cap = in_bytes; }
     if (sl.out_cap < out_bytes) { if (sl.out) cudaFree(sl.out); sl.out = nullptr; sl.out_cap = 0; CU(cudaMalloc(&sl.out, out_bytes)); sl.out_cap = out_bytes; }
   }
@@ -1900,6 +1904,7 @@ int xn_set_option(xn_handle* h, const char* name, int64_t value) {
   if (n == "pdl") { g_pdl_enabled = value != 0; h->drop_graphs(); return XN_OK; }
   if (n == "tc_debug") { set_tc_debug((int)value); return XN_OK; }
   if (n == "tc_pair") { set_tc_pair((int)value); h->drop_graphs(); return XN_OK; }
+  if (n == "attn_tc") { g_attn_tc = value != 0; h->drop_graphs(); return XN_OK; }
   if (n == "profile") {
     h->profile = value; h->prof_used = 0; h->prof_flops.clear();
     for (auto& sp : h->spans) { h->span_pool.push_back(sp.e0); h->span_pool.push_back(sp.e1); }
@@ -2074,10 +2079,10 @@ int xn_op_window_attention(xn_handle* h, const float* qkv, const float* bias_tab
   bias_table = bias_t;
   if (precision == XN_PREC_FP16) {
     KL(1, launch_cast<f16>(qkv, reinterpret_cast<f16*>(qb), (long)(3 * n), st));
-    KL(1, launch_window_attention_mma<f16>(reinterpret_cast<f16*>(qb), bias_table, reinterpret_cast<f16*>(ob), B, H, C, heads, shift, st));
+    KL(1, ActOps<f16>::attn(reinterpret_cast<f16*>(qb), bias_table, reinterpret_cast<f16*>(ob), B, H, C, heads, shift, st));
   } else {
     KL(1, launch_cast<bf16>(qkv, qb, (long)(3 * n), st));
-    KL(1, launch_window_attention_mma<bf16>(qb, bias_table, ob, B, H, C, heads, shift, st));
+    KL(1, ActOps<bf16>::attn(qb, bias_table, ob, B, H, C, heads, shift, st));
   }
   KL(1, launch_widen_16(ob, out, (long)n, precision == XN_PREC_FP16, st));
   return XN_OK;

@@ -185,11 +185,19 @@ def check_linear_ln_on_load(precision: str = "fp16") -> List[Triple]:
     return out
 
 
-def check_window_attention(precision: str = "fp32") -> List[Triple]:
+def check_window_attention(precision: str = "fp32", kernel: str = "default") -> List[Triple]:
+    """kernel: "default" (the engine's choice: tcgen05 where supported in the 16-bit modes), "mma" (mma.sync kernel forced),
+    "tc" (alias of default; labels the row).  The larger shapes give every persistent CTA of the tcgen05 kernel several
+    items (both smem stages, barrier phase wrap-around) and cover masked and unmasked windows of a shifted block."""
     e = bare_engine()
     out = []
     g = torch.Generator().manual_seed(3)
-    for (B, H, heads, shift) in [(2, 24, 2, 0), (2, 24, 2, 6), (1, 48, 3, 6), (3, 12, 4, 0)]:
+    if precision != "fp32":
+        e.set_option("attn_tc", 0 if kernel == "mma" else 1)
+    shapes = [(2, 24, 2, 0), (2, 24, 2, 6), (1, 48, 3, 6), (3, 12, 4, 0)]
+    if precision != "fp32":
+        shapes += [(4, 48, 6, 6), (2, 24, 24, 6), (5, 12, 48, 0), (7, 48, 6, 0)]
+    for (B, H, heads, shift) in shapes:
         C = heads * 32
         qkv = torch.randn(B * H * H, 3 * C, generator=g)
         table = torch.randn(529, heads, generator=g) * 0.5
@@ -217,7 +225,9 @@ def check_window_attention(precision: str = "fp32") -> List[Triple]:
             o = torch.roll(o, shifts=(shift, shift), dims=(1, 2))
         ref = o.reshape(B * H * H, C)
         tol = {"fp32": 1e-5, "bf16": 1e-2, "fp16": 2e-3}[precision]
-        out.append((f"window_attention_{precision}[B{B} H{H} heads{heads} shift{shift}] rel-max", rel_max(y, ref), tol))
+        out.append((f"window_attention_{precision}/{kernel}[B{B} H{H} heads{heads} shift{shift}] rel-max", rel_max(y, ref), tol))
+    if precision != "fp32":
+        e.set_option("attn_tc", 1)
     return out
 
 

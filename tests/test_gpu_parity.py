@@ -44,6 +44,13 @@ def test_window_attention(precision):
     _assert(G.check_window_attention(precision))
 
 
+@pytest.mark.parametrize("precision", ["bf16", "fp16"])
+def test_window_attention_mma_sync_kernel(precision):
+    """The mma.sync kernel stays the fallback (odd head counts): keep it under test."""
+    import gpu_checks as G
+    _assert(G.check_window_attention(precision, "mma"))
+
+
 def test_logsoftmax_topk():
     import gpu_checks as G
     _assert(G.check_logsoftmax_topk())

@@ -21,6 +21,7 @@ def main():
             ("skinny_fp16", lambda: G.check_linear_skinny("fp16")), ("skinny_bf16", lambda: G.check_linear_skinny("bf16")),
             ("wattn_fp32", lambda: G.check_window_attention("fp32")), ("wattn_bf16", lambda: G.check_window_attention("bf16")),
             ("wattn_fp16", lambda: G.check_window_attention("fp16")),
+            ("wattn_mma_fp16", lambda: G.check_window_attention("fp16", "mma")), ("wattn_mma_bf16", lambda: G.check_window_attention("bf16", "mma")),
             ("logsoftmax_topk", G.check_logsoftmax_topk), ("preprocess", G.check_preprocess),
             ("features", G.check_feature_extraction), ("ensemble", G.check_ensemble)]
     cases = ["tiny_e2e_peaky", "tiny_e2e_xavier", "feat_peaky_b5", "feat_xavier_b1"] + ([] if quick else ["full_e2e_xavier", "full_e2e_peaky"])
