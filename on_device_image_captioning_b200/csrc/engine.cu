@@ -1172,7 +1172,7 @@ int xn_finalize_weights(xn_handle* h, int precision) {
           if (to_bf16(W.qkv) || to_bf16(W.proj) || to_bf16(W.fc1) || to_bf16(W.fc2)) return XN_ERR_CUDA;
           if (!rc) {
             float* bt = nullptr;
-            CU(cudaMalloc(&bt, (size_t)2 * 532 * S.heads * sizeof(float)));
+            CU(cudaMalloc(&bt, bias_derived_floats(S.heads) * sizeof(float)));
             h->owned.push_back(bt);
             KL(1, launch_transpose_bias(W.rpb, bt, S.heads, 0));
             W.rpb_t = bt;
@@ -1905,6 +1905,7 @@ int xn_set_option(xn_handle* h, const char* name, int64_t value) {
   if (n == "tc_debug") { set_tc_debug((int)value); return XN_OK; }
   if (n == "tc_pair") { set_tc_pair((int)value); h->drop_graphs(); return XN_OK; }
   if (n == "attn_tc") { g_attn_tc = value != 0; h->drop_graphs(); return XN_OK; }
+  if (n == "attn_tc_dbg") { g_attn_tc_dbg = (int)value; h->drop_graphs(); return XN_OK; }
   if (n == "profile") {
     h->profile = value; h->prof_used = 0; h->prof_flops.clear();
     for (auto& sp : h->spans) { h->span_pool.push_back(sp.e0); h->span_pool.push_back(sp.e1); }
@@ -2071,10 +2072,10 @@ int xn_op_window_attention(xn_handle* h, const float* qkv, const float* bias_tab
     return XN_OK;
   }
   const size_t n = (size_t)B * H * H * C;
-  if (int r = ensure_ws(h, n * 4 * 2 + 8192 + (size_t)2 * 532 * heads * 4, st)) return r;
+  if (int r = ensure_ws(h, n * 4 * 2 + 8192 + bias_derived_floats(heads) * 4, st)) return r;
   bf16* qb = h->ws.get<bf16>(3 * n);
   bf16* ob = h->ws.get<bf16>(n);
-  float* bias_t = h->ws.get<float>((size_t)2 * 532 * heads);
+  float* bias_t = h->ws.get<float>(bias_derived_floats(heads));
   KL(1, launch_transpose_bias(bias_table, bias_t, heads, st));
   bias_table = bias_t;
   if (precision == XN_PREC_FP16) {

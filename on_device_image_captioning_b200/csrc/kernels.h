@@ -119,12 +119,14 @@ template <typename T>
 cudaError_t launch_window_attention_mma(const T* qkv, const float* bias_t, T* out, int B, int H, int C,
                                         int heads, int shift, cudaStream_t st);
 cudaError_t launch_transpose_bias(const float* table, float* out, int heads, cudaStream_t st);
+inline size_t bias_derived_floats(int heads) { return (size_t)(2 * 532 + 1024) * heads; }     // layout: window_attn_mma.cu
 // tcgen05 variant (window_attn_tc.cu): scores and probabilities in TMEM, thread-per-row softmax; needs an even head count.
 // Same derived bias table as the mma.sync variant.
 bool window_attention_tc_supported(int B, int H, int C, int heads, int shift);
 template <typename T>
 cudaError_t launch_window_attention_tc(const T* qkv, const float* bias_t, T* out, int B, int H, int C, int heads, int shift,
                                        cudaStream_t st);
+extern int g_attn_tc_dbg;
 extern int g_attn_tc;      // 1: use the tcgen05 kernel where supported (default); 0: mma.sync kernel
 
 // ---------------------------------------------------------------- static expansion (encoder)

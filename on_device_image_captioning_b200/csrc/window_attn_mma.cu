@@ -327,8 +327,11 @@ template cudaError_t launch_window_attention_mma<__half>(const __half*, const fl
 }  // namespace xn
 
 namespace xn {
-// (529, heads) relative-position table -> two (heads, 532) tables / scale (scale = 32^-0.5), once per weight load:
-// plain, and shifted by the mask offset that the label MMA cancels for same-region pairs
+// (529, heads) relative-position table -> derived tables, once per weight load (kBiasDerivedFloats(heads) floats):
+//   [0, 532 heads)            (heads, 532) table / scale (scale = 32^-0.5)                       -- mma.sync kernel
+//   [532 heads, 1064 heads)   the same shifted by the mask offset the label MMA cancels           -- mma.sync kernel, seam windows
+//   [1064 heads, ...)         (heads, 1024): entry (dy + 11) * 44 + (dx + 11), / scale            -- tcgen05 kernel (window_attn_tc.cu:
+//                             the row pitch 44 = 12 mod 32 makes the softmax threads' loads bank-conflict free)
 __global__ void transpose_bias_kernel(const float* __restrict__ t, float* __restrict__ o, int heads) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < kBiasPitch * heads) {
@@ -337,9 +340,13 @@ __global__ void transpose_bias_kernel(const float* __restrict__ t, float* __rest
     o[i] = v;
     o[i + kBiasPitch * heads] = v - 2.0f * kLabelVal * kLabelVal;                   // copy for windows on the cyclic seam
   }
+  if (i < 1024 * heads) {
+    const int h = i / 1024, e = i % 1024, dy = e / 44, dx = e % 44;
+    o[2 * kBiasPitch * heads + i] = (dy < 2 * kWin - 1 && dx < 2 * kWin - 1) ? t[(dy * (2 * kWin - 1) + dx) * heads + h] * 5.656854249492380f : 0.f;
+  }
 }
 cudaError_t launch_transpose_bias(const float* table, float* out, int heads, cudaStream_t st) {
-  transpose_bias_kernel<<<(kBiasPitch * heads + 255) / 256, 256, 0, st>>>(table, out, heads);
+  transpose_bias_kernel<<<(1024 * heads + 255) / 256, 256, 0, st>>>(table, out, heads);
   return cudaGetLastError();
 }
 }  // namespace xn
