@@ -138,6 +138,18 @@ int xn_sample(xn_handle* h, const float* input, int B, const int32_t* enc_pads_h
               int sos_idx, int eos_idx, uint64_t seed, int32_t* out_tokens, int32_t* out_len, float* out_logprob,
               void* stream);
 
+/* JPEG files straight to the normalised tensor (SURVEY.md 8f N1 incl. the decode): nvJPEG decodes every stream on the GPU
+ * into RGB8, then the batched resize / ToTensor / Normalize of xn_preprocess_rgb8_batch runs on it -- the pixels never
+ * visit the host.  jpeg_ptrs_host: n host pointers to complete JPEG streams, jpeg_sizes: their byte counts.  heights_out /
+ * widths_out (n ints, may be NULL) receive the decoded sizes.  A stream that is not 3-component (grayscale, CMYK) gives the
+ * blank canvas the reference substitutes for non-RGB files (utils/image_utils.py:18-19).  nvJPEG's IDCT / chroma
+ * upsampling is not bit-identical to libjpeg's (what PIL runs in the reference): pixels differ by a few grey levels, so
+ * the bit-exact path remains "decode with PIL, xn_preprocess_rgb8_batch".  libnvjpeg is loaded with dlopen at first use;
+ * without it this call returns XN_ERR_UNSUPPORTED and xn_jpeg_available() returns 0. */
+int xn_jpeg_available(void);
+int xn_preprocess_jpeg_batch(xn_handle* h, const uint8_t* const* jpeg_ptrs_host, const int64_t* jpeg_sizes, int n,
+                             float* out, int out_size, int32_t* heights_out, int32_t* widths_out, void* stream);
+
 /* 16-bit modes store QKV, attention outputs and MLP hidden activations as fp16 / bf16.  fp16 tops out at 65504: if a
  * checkpoint's activations exceed that, infinities reach the encoder output as NaN.  Every xn_forward_enc / xn_beam_search
  * / xn_caption_host call in a 16-bit mode checks its encoder output on the device and raises this flag when it holds a

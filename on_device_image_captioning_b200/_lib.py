@@ -44,6 +44,8 @@ _SIGNATURES = {
     "xn_caption_host": (C.c_int, [_P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P]),
     "xn_preprocess_rgb8": (C.c_int, [_P, _P, _I, _I, _I, _P, _I, _P]),
     "xn_preprocess_rgb8_batch": (C.c_int, [_P, C.POINTER(_P), _I, C.POINTER(C.c_int32), C.POINTER(C.c_int32), _I, _P, _I, _P]),
+    "xn_jpeg_available": (C.c_int, []),
+    "xn_preprocess_jpeg_batch": (C.c_int, [_P, C.POINTER(_P), C.POINTER(C.c_int64), _I, _P, _I, C.POINTER(C.c_int32), C.POINTER(C.c_int32), _P]),
     "xn_caption_host_begin": (C.c_int, [_P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P]),
     "xn_caption_host_end": (C.c_int, [_P, _I]),
     "xn_beam_search_sample": (C.c_int, [_P, _P, _I, _P, _I, _I, _I, _I, _I, C.c_uint64, _P, _P, _P, _P]),

@@ -11,6 +11,8 @@
 #include <unordered_map>
 #include <algorithm>
 #include <type_traits>
+#include <dlfcn.h>
+#include <nvjpeg.h>
 
 #include "../../include/xnv2_b200.h"
 #include "kernels.h"
@@ -63,6 +65,37 @@ struct Arena {
 };
 
 }  // namespace
+
+// nvJPEG is loaded at first use with dlopen, so the library itself has no hard dependency on it: a machine without
+// libnvjpeg keeps everything but xn_preprocess_jpeg_batch (which then reports XN_ERR_UNSUPPORTED).
+struct NvJpegApi {
+  void* lib = nullptr;
+  bool tried = false;
+  decltype(&nvjpegCreateSimple) create = nullptr;
+  decltype(&nvjpegDestroy) destroy = nullptr;
+  decltype(&nvjpegJpegStateCreate) state_create = nullptr;
+  decltype(&nvjpegJpegStateDestroy) state_destroy = nullptr;
+  decltype(&nvjpegGetImageInfo) image_info = nullptr;
+  decltype(&nvjpegDecode) decode = nullptr;
+  bool load() {
+    if (tried) return lib != nullptr;
+    tried = true;
+    for (const char* name : {"libnvjpeg.so.12", "libnvjpeg.so", "/usr/local/cuda/lib64/libnvjpeg.so.12"}) {
+      lib = dlopen(name, RTLD_NOW | RTLD_LOCAL);
+      if (lib) break;
+    }
+    if (!lib) return false;
+    create = reinterpret_cast<decltype(create)>(dlsym(lib, "nvjpegCreateSimple"));
+    destroy = reinterpret_cast<decltype(destroy)>(dlsym(lib, "nvjpegDestroy"));
+    state_create = reinterpret_cast<decltype(state_create)>(dlsym(lib, "nvjpegJpegStateCreate"));
+    state_destroy = reinterpret_cast<decltype(state_destroy)>(dlsym(lib, "nvjpegJpegStateDestroy"));
+    image_info = reinterpret_cast<decltype(image_info)>(dlsym(lib, "nvjpegGetImageInfo"));
+    decode = reinterpret_cast<decltype(decode)>(dlsym(lib, "nvjpegDecode"));
+    if (!create || !destroy || !state_create || !state_destroy || !image_info || !decode) { dlclose(lib); lib = nullptr; }
+    return lib != nullptr;
+  }
+};
+static NvJpegApi g_nvjpeg;
 
 struct xn_handle {
   xn_config cfg;
@@ -170,6 +203,8 @@ struct xn_handle {
   std::vector<ResampleTable> rtables;
   uint8_t* pp_buf = nullptr; size_t pp_cap = 0;
   char* pp_host = nullptr; size_t pp_host_cap = 0;   // pinned staging of a preprocessing batch's item records + tables
+  nvjpegHandle_t jpg = nullptr; nvjpegJpegState_t jpg_state = nullptr;     // xn_preprocess_jpeg_batch
+  uint8_t* jpg_buf = nullptr; size_t jpg_cap = 0;                          // decoded RGB8 images of a batch
   cudaEvent_t pp_ev = nullptr;
   char* io_out = nullptr; size_t io_out_cap = 0;
 
@@ -1050,6 +1085,9 @@ int xn_destroy(xn_handle* h) {
   if (h->flag_dev) cudaFree(h->flag_dev);
   if (h->pp_buf) cudaFree(h->pp_buf);
   if (h->pp_host) cudaFreeHost(h->pp_host);
+  if (h->jpg_state) g_nvjpeg.state_destroy(h->jpg_state);
+  if (h->jpg) g_nvjpeg.destroy(h->jpg);
+  if (h->jpg_buf) cudaFree(h->jpg_buf);
   if (h->pp_ev) cudaEventDestroy(h->pp_ev);
   for (auto& t : h->rtables) { cudaFree(t.bounds); cudaFree(t.kk); }
   if (h->io_out) cudaFree(h->io_out);
@@ -1824,6 +1862,60 @@ int xn_preprocess_rgb8_batch(xn_handle* h, const uint8_t* const* rgb_ptrs, int r
       CU(cudaMemcpyAsync(d_img + src_off[i], rgb_ptrs[i], (size_t)heights[i] * widths[i] * 3, cudaMemcpyHostToDevice, st));
   KL(2, launch_preprocess_rgb8_batch(reinterpret_cast<const PreItem*>(d_meta), n, max_h, S, st));
   return XN_OK;
+}
+
+int xn_jpeg_available(void) { return g_nvjpeg.load() ? 1 : 0; }
+
+int xn_preprocess_jpeg_batch(xn_handle* h, const uint8_t* const* jpeg_ptrs_host, const int64_t* jpeg_sizes, int n, float* out,
+                             int out_size, int32_t* heights_out, int32_t* widths_out, void* stream) {
+  if (!h || !jpeg_ptrs_host || !jpeg_sizes || !out) return XN_ERR_ARG;
+  cudaSetDevice(h->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  h->cur_st = st;
+  if (n < 1 || n > 65535) return h->fail(XN_ERR_ARG, "bad batch (%d images)", n);
+  if (!g_nvjpeg.load()) return h->fail(XN_ERR_UNSUPPORTED, "libnvjpeg could not be loaded: decode on the host (PIL) and call xn_preprocess_rgb8_batch");
+  if (!h->jpg) {
+    if (g_nvjpeg.create(&h->jpg) != NVJPEG_STATUS_SUCCESS) { h->jpg = nullptr; return h->fail(XN_ERR_CUDA, "nvjpegCreateSimple failed"); }
+    if (g_nvjpeg.state_create(h->jpg, &h->jpg_state) != NVJPEG_STATUS_SUCCESS) return h->fail(XN_ERR_CUDA, "nvjpegJpegStateCreate failed");
+  }
+  std::vector<int> H(n), W(n), comps(n);
+  std::vector<size_t> off(n);
+  size_t total = 0;
+  for (int i = 0; i < n; ++i) {
+    int nc = 0, ws[NVJPEG_MAX_COMPONENT] = {0}, hs[NVJPEG_MAX_COMPONENT] = {0};
+    nvjpegChromaSubsampling_t sub;
+    if (!jpeg_ptrs_host[i] || jpeg_sizes[i] <= 0 ||
+        g_nvjpeg.image_info(h->jpg, jpeg_ptrs_host[i], (size_t)jpeg_sizes[i], &nc, &sub, ws, hs) != NVJPEG_STATUS_SUCCESS)
+      return h->fail(XN_ERR_ARG, "image %d is not a JPEG stream nvJPEG can parse", i);
+    H[i] = hs[0]; W[i] = ws[0]; comps[i] = nc;
+    if (H[i] < 1 || W[i] < 1 || H[i] > 65535 || (long)H[i] * W[i] > (1L << 28)) return h->fail(XN_ERR_ARG, "bad image %d: %d x %d", i, H[i], W[i]);
+    off[i] = total;
+    total += ((size_t)H[i] * W[i] * 3 + 255) & ~size_t(255);
+    if (heights_out) heights_out[i] = H[i];
+    if (widths_out) widths_out[i] = W[i];
+  }
+  if (h->jpg_cap < total) {
+    if (h->jpg_buf) { CU(cudaDeviceSynchronize()); cudaFree(h->jpg_buf); h->jpg_buf = nullptr; h->jpg_cap = 0; }
+    CU(cudaMalloc(&h->jpg_buf, total));
+    h->jpg_cap = total;
+  }
+  std::vector<const uint8_t*> ptrs(n);
+  for (int i = 0; i < n; ++i) {
+    uint8_t* dst = h->jpg_buf + off[i];
+    ptrs[i] = dst;
+    if (comps[i] == 3) {
+      nvjpegImage_t img{};
+      img.channel[0] = dst;
+      img.pitch[0] = (size_t)W[i] * 3;
+      const nvjpegStatus_t rc = g_nvjpeg.decode(h->jpg, h->jpg_state, jpeg_ptrs_host[i], (size_t)jpeg_sizes[i], NVJPEG_OUTPUT_RGBI, &img, st);
+      if (rc != NVJPEG_STATUS_SUCCESS) return h->fail(XN_ERR_CUDA, "nvjpegDecode failed on image %d (status %d)", i, (int)rc);
+    } else {
+      // reference utils/image_utils.py:18-19: a file whose PIL mode is not RGB (grayscale = 1 component, CMYK = 4) is
+      // replaced by a blank RGB canvas of the same size
+      CU(cudaMemsetAsync(dst, 0, (size_t)H[i] * W[i] * 3, st));
+    }
+  }
+  return xn_preprocess_rgb8_batch(h, ptrs.data(), 1, H.data(), W.data(), n, out, out_size, stream);
 }
 
 int xn_overflow_flag(xn_handle* h, int* flag_out, int clear) {

@@ -465,8 +465,10 @@ window_attention_tc_kernel(const T* __restrict__ qkv, const float* __restrict__ 
           for (int e = 0; e < w / 2; ++e) {
             const float p0 = ex2_ftz(fmaf(__uint_as_float(v[c & 1][2 * e]), c2, negm));
             const float p1 = ex2_ftz(fmaf(__uint_as_float(v[c & 1][2 * e + 1]), c2, negm));
-            sums[e & 1] += p0 + p1;
             pk[e] = Mma16<T>::pack(p0, p1);
+            if (std::is_same<T, __half>::value) sums[e & 1] += p0 + p1;
+            else      // bf16 keeps 8 significand bits: normalise by the sum of the ROUNDED probabilities (weights sum to 1 exactly)
+              sums[e & 1] += __uint_as_float(pk[e] << 16) + __uint_as_float(pk[e] & 0xffff0000u);
           }
           if (w == 32) tmem_st16_nc(tP + c * 16, pk);
           else tmem_st8_nc(tP + c * 16, pk);

@@ -210,6 +210,26 @@ class Engine:
                 torch.cuda.current_stream().synchronize()      # host buffers were read asynchronously
         return out
 
+    def jpeg_available(self) -> bool:
+        return bool(self.lib.xn_jpeg_available())
+
+    def preprocess_jpeg(self, jpeg_streams, img_size: Optional[int] = None) -> torch.Tensor:
+        """JPEG byte strings -> (B, 3, S, S) float32 on the device: nvJPEG decode on the GPU, then the batched resize /
+        ToTensor / Normalize (xn_preprocess_jpeg_batch).  Raises if libnvjpeg is not present."""
+        S = int(img_size or self.cfg.img_size)
+        n = len(jpeg_streams)
+        out = torch.empty(n, 3, S, S, device=self.device, dtype=torch.float32)
+        bufs = [bytes(b) for b in jpeg_streams]
+        keep = [C.create_string_buffer(b, len(b)) for b in bufs]
+        ptrs = (C.c_void_p * n)(*[C.addressof(k) for k in keep])
+        sizes = (C.c_int64 * n)(*[len(b) for b in bufs])
+        hs, ws = (C.c_int32 * n)(), (C.c_int32 * n)()
+        with torch.cuda.device(self.device):
+            self._check(self.lib.xn_preprocess_jpeg_batch(self._h, ptrs, sizes, n, _ptr(out), S, hs, ws, self._stream()), "xn_preprocess_jpeg_batch")
+            torch.cuda.current_stream().synchronize()          # the streams were read asynchronously
+        self.last_jpeg_sizes = [(int(h), int(w)) for h, w in zip(hs, ws)]
+        return out
+
     def preprocess_rgb8_single(self, image, img_size: Optional[int] = None) -> torch.Tensor:
         """One image through the single-image entry point (xn_preprocess_rgb8): (3, S, S) float32."""
         S = int(img_size or self.cfg.img_size)

@@ -1,7 +1,9 @@
 """Mirror of the reference's utils/image_utils.py for the accelerated path: same function name and return value,
 the resize / ToTensor / Normalize run on the GPU (csrc/preprocess.cu), bit-identical to Pillow + torchvision.
 
-JPEG/PNG decoding stays on the host (PIL), exactly as in the reference; nothing else does."""
+``preprocess_image`` / ``preprocess_images`` decode on the host with PIL, exactly as the reference does (bit-identical
+tensors); ``preprocess_images_nvjpeg`` decodes JPEG files on the GPU with nvJPEG as well (faster, pixels within a few grey
+levels of libjpeg's)."""
 from __future__ import annotations
 
 from typing import List, Sequence
@@ -39,6 +41,17 @@ def preprocess_image(image_path, img_size: int, engine=None) -> torch.Tensor:
     """reference utils/image_utils.py:5-23, same two positional arguments -> (1, 3, S, S) float32 on the CUDA device
     (the engine's, or the current device when no engine is given)."""
     return _engine_or_default(engine).preprocess_rgb8([_decode_rgb8(image_path)], img_size)
+
+
+def preprocess_images_nvjpeg(image_paths: Sequence, img_size: int, engine=None) -> torch.Tensor:
+    """The same for JPEG files with the DECODE on the GPU as well (nvJPEG): the files are read as bytes, nothing is decoded on
+    the host.  Pixels differ from PIL's libjpeg decode by a few grey levels (different IDCT / chroma upsampling), so this is
+    the fast path, not the bit-exact one; files nvJPEG cannot parse (PNG, ...) and hosts without libnvjpeg raise."""
+    streams = []
+    for p in image_paths:
+        with open(p, "rb") as f:
+            streams.append(f.read())
+    return _engine_or_default(engine).preprocess_jpeg(streams, img_size)
 
 
 def preprocess_images(image_paths: Sequence, img_size: int, engine=None) -> torch.Tensor:

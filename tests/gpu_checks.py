@@ -859,6 +859,44 @@ def check_preprocess_batch() -> List[Triple]:
     return out
 
 
+def check_nvjpeg_decode() -> List[Triple]:
+    """SURVEY.md 8f N1, the decode: JPEG files decoded on the GPU by nvJPEG and preprocessed in the same call
+    (xn_preprocess_jpeg_batch) against the PIL decode + the same GPU resize.  nvJPEG's IDCT / chroma upsampling is not
+    libjpeg's, so the comparison is a closeness bound on the normalised tensors (one grey level = 0.017), plus the exact
+    rules: decoded sizes, and the blank canvas for a grayscale (non-RGB) file."""
+    import io
+    import os
+    from PIL import Image
+    from conftest import GOLDEN_DIR
+    from on_device_image_captioning_b200.image_utils import preprocess_images, preprocess_images_nvjpeg
+    from test_preprocess_oracle import reference_preprocess, synth_image
+    e = bare_engine()
+    if not e.jpeg_available():
+        return [("nvJPEG not present on this host (skipped)", 0.0, 0.0)]
+    out = []
+    paths = [os.path.join(GOLDEN_DIR, "demo_material", n) for n in ("tatin.jpg", "micheal.jpg")]
+    a = preprocess_images_nvjpeg(paths, 384, e)
+    sizes = list(e.last_jpeg_sizes)
+    b = preprocess_images(paths, 384, e)
+    d = (a - b).abs()
+    out.append(("nvjpeg: decoded (H, W) differ from PIL's", float(sizes != [(960, 1280), (589, 880)]), 0.0))
+    out.append(("nvjpeg decode + GPU resize vs PIL decode + GPU resize: mean |diff| of the normalised tensor", float(d.mean()), 0.02))
+    out.append(("nvjpeg decode + GPU resize vs PIL decode + GPU resize: max |diff| (grey levels)", float(d.max()) * 0.225 * 255, 24.0))
+    # a synthetic 4:4:4 quality-95 JPEG and a grayscale one
+    rgb = synth_image(300, 420, 9)
+    buf = io.BytesIO()
+    Image.fromarray(rgb, "RGB").save(buf, format="JPEG", quality=95, subsampling=0)
+    gray = io.BytesIO()
+    Image.fromarray(rgb[..., 1], "L").save(gray, format="JPEG", quality=90)
+    y = e.preprocess_jpeg([buf.getvalue(), gray.getvalue()], 96).cpu().numpy()
+    pil = np.asarray(Image.open(io.BytesIO(buf.getvalue())).convert("RGB"))
+    ref = reference_preprocess(pil, 96)
+    out.append(("nvjpeg 4:4:4 q95 synthetic: mean |diff| vs PIL decode", float(np.abs(y[0] - ref).mean()), 0.02))
+    blank = reference_preprocess(np.zeros((300, 420, 3), dtype=np.uint8), 96)
+    out.append(("nvjpeg grayscale JPEG -> blank canvas rule: elements differing", float((y[1] != blank).sum()), 0.0))
+    return out
+
+
 def check_evaluate_model_loop() -> List[Triple]:
     """the evaluate_model batching loop (reference test.py:141-275) on the drop-in class: sub-batches of
     4 over 10 images (last one ragged) must give, per image, the caption a single-image call gives, in the reference's

@@ -248,3 +248,9 @@ def test_evaluate_model_loop():
     """test.py's evaluate_model batching loop on the drop-in class."""
     import gpu_checks as G
     _assert(G.check_evaluate_model_loop())
+
+
+def test_nvjpeg_decode_path():
+    """JPEG decode on the GPU (nvJPEG) feeding the batched preprocessing."""
+    import gpu_checks as G
+    _assert(G.check_nvjpeg_decode())
