@@ -183,6 +183,10 @@ int64_t xn_workspace_bytes(const xn_handle* h);
  *   "swin_chunk", "enc_chunk"  images per Swin / encoder chunk (64)
  *   "use_graph"                1: calls are captured into a CUDA graph on their second occurrence and replayed
  *   "decode_groups"            image groups decoded on concurrent graph branches (0 = automatic: 2 from 32 images)
+ *   "early_exit"               device-side early termination of the beam search (reference captioning_model.py:397): inside a
+ *                              captured call the decode steps are grouped into CUDA-graph IF nodes of this many steps that are
+ *                              skipped once every beam has ended (default 4; 0 = off: all steps always run, same results)
+ *   "attn_tc"                  1: window attention on the tcgen05 kernel (default), 0: the mma.sync kernel
  *   "pdl"                      programmatic dependent launch (process-wide)
  *   "tc_pair"                  CTA-pair (cta_group::2) GEMM tiles for long-K shapes (process-wide)
  *   "use_skinny"               skinny mma.sync GEMM for decoder-step linears with <= 64 rows

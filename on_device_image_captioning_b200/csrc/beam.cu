@@ -5,6 +5,7 @@
 // ties to the lower flat index), parent/word split, history append, length update.  The
 // expansion-state "gather by parent beam" is the `anc` table: per row and position, the slot
 // holding that position's cached state; reordering beams only permutes these small tables.
+#include <algorithm>
 #include "kernels.h"
 #include "common.cuh"
 
@@ -16,6 +17,8 @@ __global__ void beam_init_kernel(BeamBufs bb, int B, int beam, int L, int sos) {
   pdl_wait();
   pdl_trigger();
   const int r = blockIdx.x * blockDim.x + threadIdx.x;      // row = b*beam + k
+  if (r < L) bb.grew[r] = 0;
+  if (r == 0) { *bb.all_done = 0; *bb.final_src = 0; }
   if (r >= B * beam) return;
   for (int s = 0; s < 2; ++s) {
     for (int i = 0; i < L; ++i) {
@@ -27,7 +30,6 @@ __global__ void beam_init_kernel(BeamBufs bb, int B, int beam, int L, int sos) {
     bb.cum[s][r] = 0.f;
     bb.eos[s][r] = 0;
   }
-  if (r == 0) *bb.all_done = 0;
 }
 
 // step 0 (:242-271): all beams of an image hold [SOS]; beam k takes the k-th best first word of row (b,0).
@@ -46,6 +48,7 @@ __global__ void beam_first_kernel(BeamBufs bb, const float* __restrict__ top_val
   bb.eos[0][r] = top_idx[src] == eos;
   bb.anc[0][(long)r * L + 0] = r;                            // every slot computed identical position-0 state
   bb.anc[0][(long)r * L + 1] = r;
+  if (r == 0) *bb.final_src = 0;
 }
 
 // One loop iteration for time_step t (tokens 0..t-1 known, choosing token t)  (:295-397).  One warp per image: the
@@ -117,7 +120,8 @@ __global__ void __launch_bounds__(128) beam_step_kernel(BeamBufs bb, int src, co
       bb.len[dst][b * beam + j] = nl;
       bb.cum[dst][b * beam + j] = pick < 32 ? c0 : c1;       // = cum[parent] + word log-prob
       bb.eos[dst][b * beam + j] = pe || tokn == eos;
-      if (nl == t + 1) atomicExch(bb.all_done, 0);           // informational; the host does not poll it
+      if (nl == t + 1) bb.grew[t] = 1;                       // some beam is still growing: the search goes on (:397)
+      if (b == 0 && j == 0) *bb.final_src = dst;
     }
   }
 }
@@ -130,6 +134,7 @@ __global__ void beam_finalize_kernel(BeamBufs bb, int src, int B, int beam, int 
   pdl_trigger();
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
+  src = *bb.final_src;                    // the state after the last executed step (the host's `src` assumes none was skipped)
   const int* tk = bb.tokens[src] + (long)b * beam * L;
   const float* lp = bb.lps[src] + (long)b * beam * L;
   const int* ln = bb.len[src] + b * beam;
@@ -201,9 +206,18 @@ cudaError_t launch_sample_finalize(const BeamBufs& bb, int R, int L, int t_final
   return launch_k(sample_finalize_kernel, dim3((R + 127) / 128), dim3(128), 0, st, bb, R, L, t_final, out_tokens, out_len, out_lp);
 }
 
+__global__ void beam_set_condition_kernel(cudaGraphConditionalHandle handle, const int* __restrict__ grew_t) {
+  pdl_wait();
+  pdl_trigger();
+  if (threadIdx.x == 0) cudaGraphSetConditional(handle, *grew_t != 0 ? 1u : 0u);
+}
+cudaError_t launch_beam_set_condition(unsigned long long cond_handle, const int* grew_t, cudaStream_t st) {
+  return launch_k(beam_set_condition_kernel, dim3(1), dim3(32), 0, st, (cudaGraphConditionalHandle)cond_handle, grew_t);
+}
+
 cudaError_t launch_beam_init(const BeamBufs& bb, int B, int beam, int L, int sos, cudaStream_t st) {
   if (beam > kMaxBeam) return cudaErrorInvalidValue;
-  launch_k(beam_init_kernel, dim3((B * beam + 127) / 128), dim3(128), 0, st, bb, B, beam, L, sos);
+  launch_k(beam_init_kernel, dim3((std::max(B * beam, L) + 127) / 128), dim3(128), 0, st, bb, B, beam, L, sos);
   return cudaGetLastError();
 }
 cudaError_t launch_beam_first(const BeamBufs& bb, const float* top_val, const int* top_idx, int B, int beam, int L,

@@ -209,7 +209,11 @@ struct BeamBufs {
   float* cum[2];      // (B, beam)     running sum of the history log-probs
   int* eos[2];        // (B, beam)     history contains EOS
   int* all_done;      // [1]
+  int* grew;          // [L]  grew[t] != 0: some beam was extended at time step t (else every beam had ended: the search is over)
+  int* final_src;     // [1]  ping-pong index holding the state after the last EXECUTED step (steps may be skipped, see engine.cu)
 };
+// device-side early exit (CUDA-graph conditional nodes): sets the condition of the next step's IF node to grew[t] != 0
+cudaError_t launch_beam_set_condition(unsigned long long cond_handle, const int* grew_t, cudaStream_t st);
 cudaError_t launch_beam_init(const BeamBufs& bb, int B, int beam, int L, int sos, cudaStream_t st);
 cudaError_t launch_beam_first(const BeamBufs& bb, const float* top_val, const int* top_idx, int B, int beam,
                               int L, int eos, cudaStream_t st);

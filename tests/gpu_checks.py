@@ -717,8 +717,8 @@ def check_graph_pointer_independence() -> List[Triple]:
             bad += sum(1 for a, b in zip(_tokens_list(tok, ln), ref[i]) if a != b)
     out = [("graph: captions with 10 distinct device tensors differing from the graph-free run", float(bad), 0.0),
            ("graph: distinct input addresses used", float(-len({d.data_ptr() for d in keep})), -10.0),
-           ("graph: per-call launch counts differing from the first call's (eager, capture and replays all count the same kernels)",
-            float(len(set(counts)) - 1), 0.0)]
+           ("graph: per-call launch counts of the replays differing from the captured call's (call 1 eager, call 2 captured, then replays; "
+            "the captured graph has a few extra set-condition kernels of the early-exit IF nodes)", float(len(set(counts[1:])) - 1), 0.0)]
     hosts = [t.clone().pin_memory() for t in xs]
     badh = 0
     for rep in range(2):
@@ -856,6 +856,55 @@ def check_preprocess_batch() -> List[Triple]:
         y = e.preprocess_rgb8_single(im, 48).cpu().numpy()
         bad += int((y != P.preprocess_rgb8(im, 48)).sum())
     out.append((f"preprocess single-image entry over {len(cyc)} calls / 80 distinct table sizes: elements differing", float(bad), 0.0))
+    return out
+
+
+def check_early_exit() -> List[Triple]:
+    """Device-side early termination (reference captioning_model.py:397 breaks when no beam was extended): inside the
+    captured call the decode steps are bodies of CUDA-graph IF nodes.  A model whose EOS bias makes every caption end after
+    one word must (a) return exactly the captions of the uncaptured run and of the run with early exit disabled and
+    (b) replay measurably faster than with early exit disabled (18 of 19 decode steps are skipped); a model whose captions
+    do not end must be unaffected."""
+    import time
+    from on_device_image_captioning_b200 import synth
+    from on_device_image_captioning_b200.config import features_only
+    cfg = features_only(vocab=1000, max_seq_len=24)
+    x = synth.make_features(cfg, 48, seed=5)
+    out = []
+    for label, boost in (("captions end at once", 60.0), ("captions run to max_len", -60.0)):
+        sd = synth.make_state_dict(cfg, seed=0, profile="peaky", eos_idx=7)
+        sd["vocab_linear.bias"][7] += boost
+        e = Engine(cfg, 0)
+        e.load_state_dict(sd, "fp16")
+        res, ms = {}, {}
+        for ee in (0, 4):
+            e.set_option("early_exit", ee)
+            e.set_option("use_graph", 0)
+            t0_, l0_, _ = e.beam_search(x, [0] * 48, 5, 7, 3, 1, 20)
+            eager = _tokens_list(t0_, l0_)
+            e.set_option("use_graph", 1)
+            for _ in range(3):                              # eager, capture, replay
+                tk, ln, _ = e.beam_search(x, [0] * 48, 5, 7, 3, 1, 20)
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(5):
+                tk, ln, _ = e.beam_search(x, [0] * 48, 5, 7, 3, 1, 20)
+            b.record()
+            torch.cuda.synchronize()
+            ms[ee] = a.elapsed_time(b) / 5
+            res[ee] = _tokens_list(tk, ln)
+            out.append((f"early exit [{label}] early_exit={ee}: replayed captions differing from the uncaptured run",
+                        float(sum(1 for p_, q_ in zip(res[ee], eager) if p_ != q_)), 0.0))
+        out.append((f"early exit [{label}]: captions differing between early_exit=1 and 0", float(sum(1 for p_, q_ in zip(res[0], res[4]) if p_ != q_)), 0.0))
+        lens = sorted({len(c_) for c_ in res[4]})
+        if boost > 0:
+            out.append((f"early exit [{label}]: longest caption (tokens incl. SOS/EOS)", float(lens[-1]), 3.0))
+            out.append((f"early exit [{label}]: replay time with early exit / without ({ms[4]:.2f} / {ms[0]:.2f} ms)", ms[4] / ms[0], 0.6))
+        else:
+            out.append((f"early exit [{label}]: shortest caption", float(-lens[0]), -20.0))
+            out.append((f"early exit [{label}]: replay time with early exit / without ({ms[4]:.2f} / {ms[0]:.2f} ms) (the IF nodes' own cost)", ms[4] / ms[0], 1.08))
+        e.close()
     return out
 
 

@@ -254,3 +254,9 @@ def test_nvjpeg_decode_path():
     """JPEG decode on the GPU (nvJPEG) feeding the batched preprocessing."""
     import gpu_checks as G
     _assert(G.check_nvjpeg_decode())
+
+
+def test_device_side_early_exit():
+    """reference captioning_model.py:397: stop decoding when every beam has ended -- as graph IF nodes on the device."""
+    import gpu_checks as G
+    _assert(G.check_early_exit())

@@ -37,7 +37,7 @@ def main():
     # round 2
     jobs += [("graph_ptr", G.check_graph_pointer_independence), ("sampling", G.check_sampling),
              ("preprocess_batch", G.check_preprocess_batch), ("evaluate_loop", G.check_evaluate_model_loop),
-             ("saturation", G.check_fp16_saturation), ("nvjpeg", G.check_nvjpeg_decode)]
+             ("saturation", G.check_fp16_saturation), ("nvjpeg", G.check_nvjpeg_decode), ("early_exit", G.check_early_exit)]
     if not quick:
         jobs += [("e2e16_fp16:full_e2e_peaky", lambda: G.check_image_to_logits_16bit("full_e2e_peaky", "fp16")),
                  ("e2e16_fp16:full_e2e_xavier", lambda: G.check_image_to_logits_16bit("full_e2e_xavier", "fp16")),
