@@ -190,7 +190,8 @@ int64_t xn_workspace_bytes(const xn_handle* h);
  *   "pdl"                      programmatic dependent launch (process-wide)
  *   "tc_pair"                  CTA-pair (cta_group::2) GEMM tiles for long-K shapes (process-wide)
  *   "use_skinny"               skinny mma.sync GEMM for decoder-step linears with <= 64 rows
- *   "ln_on_load"               LayerNorm folded into the consuming tcgen05 GEMM (off: measured slower)
+ *   "ln_fuse"                  Swin norm1 / norm2 folded algebraically into the neighbouring tcgen05 GEMMs (default 1, 16-bit modes)
+ *   "ln_on_load"               decoder-step LayerNorm computed inside the consuming tcgen05 GEMM (off: measured slower)
  *   "profile"                  1: event-time every tcgen05 GEMM; 2: event-time every kernel launch (both disable graphs)
  *   "tc_debug", "op_out16"     kernel timing experiments / test hooks */
 int xn_set_option(xn_handle* h, const char* name, int64_t value);

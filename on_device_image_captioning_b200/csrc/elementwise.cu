@@ -539,4 +539,31 @@ template cudaError_t launch_selector_mix<float>(const float*, long, const float*
 template cudaError_t launch_selector_mix<bf16>(const float*, long, const bf16*, long, const float*, const float*, long, float*, long, long, int, cudaStream_t);
 template cudaError_t launch_selector_mix<f16>(const float*, long, const f16*, long, const float*, const float*, long, float*, long, long, int, cudaStream_t);
 
+// ---- LayerNorm folded into the consuming GEMM (kernels.h: TcGemmArgs::ln_stats): one warp per output row n
+//   w16[n][k] = round16(gamma[k] W[n][k] - (1/K) sum_k' gamma[k'] W[n][k'])     (centred: the row mean of x drops out)
+//   bias_out[n] = bias[n] + sum_k W[n][k] beta[k]
+template <typename T>
+__global__ void fold_ln_weight_kernel(const float* __restrict__ w, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                      const float* __restrict__ bias, T* __restrict__ w16, float* __restrict__ bias_out, int N, int K) {
+  const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (n >= N) return;
+  float s = 0.f, bb = 0.f;
+  for (int k = lane; k < K; k += 32) {
+    const float wv = w[(long)n * K + k];
+    s = fmaf(gamma[k], wv, s);
+    bb = fmaf(wv, beta[k], bb);
+  }
+  s = warp_sum(s) / (float)K;
+  bb = warp_sum(bb);
+  for (int k = lane; k < K; k += 32) w16[(long)n * K + k] = from_f32<T>(gamma[k] * w[(long)n * K + k] - s);
+  if (lane == 0) bias_out[n] = (bias ? bias[n] : 0.f) + bb;
+}
+cudaError_t launch_fold_ln_weight(const float* w, const float* gamma, const float* beta, const float* bias, void* w16,
+                                  float* bias_out, int N, int K, int fp16, cudaStream_t st) {
+  const int wpb = 8;
+  if (fp16) fold_ln_weight_kernel<f16><<<(N + wpb - 1) / wpb, wpb * 32, 0, st>>>(w, gamma, beta, bias, reinterpret_cast<f16*>(w16), bias_out, N, K);
+  else fold_ln_weight_kernel<bf16><<<(N + wpb - 1) / wpb, wpb * 32, 0, st>>>(w, gamma, beta, bias, reinterpret_cast<bf16*>(w16), bias_out, N, K);
+  return cudaGetLastError();
+}
+
 }  // namespace xn

@@ -39,7 +39,13 @@ struct LinW {
   int N = 0, K = 0;
 };
 
-struct SwinBlockW { const float *n1g, *n1b, *n2g, *n2b, *rpb, *rpb_t; LinW qkv, proj, fc1, fc2; };
+struct SwinBlockW {
+  const float *n1g, *n1b, *n2g, *n2b, *rpb, *rpb_t;
+  LinW qkv, proj, fc1, fc2;
+  LinW qkv_ln, fc1_ln;      // norm1 / norm2 folded into the weights (16-bit modes; kernels.h: TcGemmArgs::ln_stats)
+};
+// folded-LayerNorm hooks of one tcgen05 GEMM launch (producer and / or consumer side)
+struct LnFuse { float* stats_out = nullptr; void* x16_out = nullptr; long ldx16 = 0; const float* ln_stats = nullptr; int ln_k = 0; };
 struct SwinStageW {
   int C, H, heads;
   std::vector<SwinBlockW> blocks;
@@ -144,6 +150,7 @@ struct xn_handle {
   // in-kernel normalisation sits on the critical path in front of the first MMA; 64-image call 29.5 vs 28.8 ms), so it
   // is off by default (profiles/r2_decoder_gemm_ln_on_load.txt).
   int64_t ln_on_load = 0;
+  int64_t ln_fuse = 1;                // Swin norm1 / norm2 folded into the neighbouring tcgen05 GEMMs (16-bit modes)
   // the decoder step is a chain of latency-bound kernels that fills a fraction of the machine: the batch is decoded as
   // up to kMaxDecodeGroups independent image groups on concurrent streams (parallel branches of the captured graph)
   static constexpr int kMaxDecodeGroups = 8;
@@ -290,8 +297,9 @@ int lin_f32(xn_handle* h, const float* x, long ldx, const LinW& w, const float* 
 }
 int lin_tc(xn_handle* h, const void* x, long ldx, const LinW& w, const float* res, long ldr, float* yf, void* yb,
            long ldy, int M, int act, int fp16, cudaStream_t st, int w_static = 1, const float* a32 = nullptr, long lda32 = 0,
-           const float* ln_g = nullptr, const float* ln_b = nullptr) {
+           const float* ln_g = nullptr, const float* ln_b = nullptr, const LnFuse* lf = nullptr) {
   TcGemmArgs g{};
+  if (lf) { g.stats_out = lf->stats_out; g.x16_out = lf->x16_out; g.ldx16 = lf->ldx16; g.ln_stats = lf->ln_stats; g.ln_k = lf->ln_k; }
   g.w_static = w_static;
   g.a32 = a32; g.lda32 = lda32; g.ln_g = ln_g; g.ln_b = ln_b;        // LayerNorm-on-load (x is then unused)
   g.A = x; g.lda = ldx; g.W = w.wb; g.ldw = w.K; g.Cf = yf; g.Cb = yb; g.ldc = ldy; g.fp16 = fp16;
@@ -314,10 +322,10 @@ int lin_tc(xn_handle* h, const void* x, long ldx, const LinW& w, const float* re
 // activation-type dispatch used by the templated Swin forward
 template <typename T> struct ActOps;
 template <> struct ActOps<float> {
-  static int lin_act(xn_handle* h, const float* x, long ldx, const LinW& w, float* y, long ldy, int M, int act, cudaStream_t st) {
+  static int lin_act(xn_handle* h, const float* x, long ldx, const LinW& w, float* y, long ldy, int M, int act, cudaStream_t st, const LnFuse* = nullptr) {
     return lin_f32(h, x, ldx, w, nullptr, 0, y, ldy, M, act, st);
   }
-  static int lin_res(xn_handle* h, const float* x, long ldx, const LinW& w, const float* res, long ldr, float* y, long ldy, int M, cudaStream_t st) {
+  static int lin_res(xn_handle* h, const float* x, long ldx, const LinW& w, const float* res, long ldr, float* y, long ldy, int M, cudaStream_t st, const LnFuse* = nullptr) {
     return lin_f32(h, x, ldx, w, res, ldr, y, ldy, M, 0, st);
   }
   static cudaError_t attn(const float* qkv, const float* rpb, float* o, int B, int H, int C, int heads, int shift, cudaStream_t st) {
@@ -325,11 +333,11 @@ template <> struct ActOps<float> {
   }
 };
 template <> struct ActOps<bf16> {
-  static int lin_act(xn_handle* h, const bf16* x, long ldx, const LinW& w, bf16* y, long ldy, int M, int act, cudaStream_t st) {
-    return lin_tc(h, x, ldx, w, nullptr, 0, nullptr, y, ldy, M, act, 0, st);
+  static int lin_act(xn_handle* h, const bf16* x, long ldx, const LinW& w, bf16* y, long ldy, int M, int act, cudaStream_t st, const LnFuse* lf = nullptr) {
+    return lin_tc(h, x, ldx, w, nullptr, 0, nullptr, y, ldy, M, act, 0, st, 1, nullptr, 0, nullptr, nullptr, lf);
   }
-  static int lin_res(xn_handle* h, const bf16* x, long ldx, const LinW& w, const float* res, long ldr, float* y, long ldy, int M, cudaStream_t st) {
-    return lin_tc(h, x, ldx, w, res, ldr, y, nullptr, ldy, M, 0, 0, st);
+  static int lin_res(xn_handle* h, const bf16* x, long ldx, const LinW& w, const float* res, long ldr, float* y, long ldy, int M, cudaStream_t st, const LnFuse* lf = nullptr) {
+    return lin_tc(h, x, ldx, w, res, ldr, y, nullptr, ldy, M, 0, 0, st, 1, nullptr, 0, nullptr, nullptr, lf);
   }
   static cudaError_t attn(const bf16* qkv, const float* rpb, bf16* o, int B, int H, int C, int heads, int shift, cudaStream_t st) {
     if (g_attn_tc && window_attention_tc_supported(B, H, C, heads, shift)) return launch_window_attention_tc<bf16>(qkv, rpb, o, B, H, C, heads, shift, st);
@@ -337,11 +345,11 @@ template <> struct ActOps<bf16> {
   }
 };
 template <> struct ActOps<f16> {
-  static int lin_act(xn_handle* h, const f16* x, long ldx, const LinW& w, f16* y, long ldy, int M, int act, cudaStream_t st) {
-    return lin_tc(h, x, ldx, w, nullptr, 0, nullptr, y, ldy, M, act, 1, st);
+  static int lin_act(xn_handle* h, const f16* x, long ldx, const LinW& w, f16* y, long ldy, int M, int act, cudaStream_t st, const LnFuse* lf = nullptr) {
+    return lin_tc(h, x, ldx, w, nullptr, 0, nullptr, y, ldy, M, act, 1, st, 1, nullptr, 0, nullptr, nullptr, lf);
   }
-  static int lin_res(xn_handle* h, const f16* x, long ldx, const LinW& w, const float* res, long ldr, float* y, long ldy, int M, cudaStream_t st) {
-    return lin_tc(h, x, ldx, w, res, ldr, y, nullptr, ldy, M, 0, 1, st);
+  static int lin_res(xn_handle* h, const f16* x, long ldx, const LinW& w, const float* res, long ldr, float* y, long ldy, int M, cudaStream_t st, const LnFuse* lf = nullptr) {
+    return lin_tc(h, x, ldx, w, res, ldr, y, nullptr, ldy, M, 0, 1, st, 1, nullptr, 0, nullptr, nullptr, lf);
   }
   static cudaError_t attn(const f16* qkv, const float* rpb, f16* o, int B, int H, int C, int heads, int shift, cudaStream_t st) {
     if (g_attn_tc && window_attention_tc_supported(B, H, C, heads, shift)) return launch_window_attention_tc<f16>(qkv, rpb, o, B, H, C, heads, shift, st);
@@ -360,6 +368,7 @@ size_t swin_ws_bytes(const xn_config& c, int Bc, int prec) {
   b += 3 * tok * act;                                 // qkv
   b += tok * act;                                     // attention out
   b += (size_t)(c.mlp_ratio * tok) * act + 4096;      // mlp hidden
+  b += (size_t)Bc * L0 * 2 * 4;                         // per-row LayerNorm statistics (sum, sum of squares)
   return b + 16 * 256;
 }
 
@@ -381,23 +390,49 @@ int swin_forward_chunk(xn_handle* h, const float* img, int Bc, float* out, cudaS
   T* qkv = h->ws.get<T>(3 * tok0);
   T* ao = h->ws.get<T>(tok0);
   T* hid = h->ws.get<T>((size_t)(c.mlp_ratio * tok0) + 1024);
+  float* stats = h->ws.get<float>((size_t)Bc * G * G * 2);
   WS_CHECK();
+  // 16-bit modes: norm1 / norm2 are folded into the GEMMs around them (option "ln_fuse").  The GEMM that produces the
+  // residual stream (proj, fc2) also writes the raw rows in 16 bits into `xn` and their sum / sum of squares into `stats`;
+  // the GEMM that consumes the normalised rows (fc1, the next block's qkv) reads those raw rows against weights that
+  // carry gamma, are centred along K (the mean drops out) and scales its accumulator rows by 1/std.  Per block that
+  // deletes two LayerNorm launches and the second read of the fp32 residual stream.
+  const bool fuse = !std::is_same<T, float>::value && h->ln_fuse != 0;
   if (h->pe_wq) KL(1, launch_patch_embed4(img, h->pe_wq, h->pe_b, h->pe_g, h->pe_beta, x, Bc, c.in_chans, c.img_size, c.embed_dim, st));
   else KL(1, launch_patch_embed(img, h->pe_w, h->pe_b, h->pe_g, h->pe_beta, x, Bc, c.in_chans, c.img_size, c.patch_size,
                                 c.embed_dim, st));
   for (size_t si = 0; si < h->stages.size(); ++si) {
     const SwinStageW& S = h->stages[si];
     const int C = S.C, H = S.H, M = Bc * H * H;
+    bool have_x16 = false;                      // `xn` holds the raw 16-bit rows of x and `stats` their statistics
     for (size_t bi = 0; bi < S.blocks.size(); ++bi) {
       const SwinBlockW& W = S.blocks[bi];
       const int shift = (bi % 2 == 1 && H > c.window_size) ? c.window_size / 2 : 0;
-      KL(1, swin_layernorm<T>(x, C, W.n1g, W.n1b, xn, C, M, C, st));
-      if (int r = ActOps<T>::lin_act(h, xn, C, W.qkv, qkv, 3 * C, M, 0, st)) return r;
+      LnFuse consume; consume.ln_stats = stats; consume.ln_k = C;
+      LnFuse produce; produce.stats_out = stats; produce.x16_out = xn; produce.ldx16 = C;
+      if (fuse && have_x16) {
+        if (int r = ActOps<T>::lin_act(h, xn, C, W.qkv_ln, qkv, 3 * C, M, 0, st, &consume)) return r;
+      } else {
+        KL(1, swin_layernorm<T>(x, C, W.n1g, W.n1b, xn, C, M, C, st));
+        if (int r = ActOps<T>::lin_act(h, xn, C, W.qkv, qkv, 3 * C, M, 0, st)) return r;
+      }
       KL(1, ActOps<T>::attn(qkv, std::is_same<T, float>::value ? W.rpb : W.rpb_t, ao, Bc, H, C, S.heads, shift, st));
-      if (int r = ActOps<T>::lin_res(h, ao, C, W.proj, x, C, x, C, M, st)) return r;
-      KL(1, swin_layernorm<T>(x, C, W.n2g, W.n2b, xn, C, M, C, st));
-      if (int r = ActOps<T>::lin_act(h, xn, C, W.fc1, hid, W.fc1.N, M, 1, st)) return r;
-      if (int r = ActOps<T>::lin_res(h, hid, W.fc1.N, W.fc2, x, C, x, C, M, st)) return r;
+      if (fuse) {
+        CU(cudaMemsetAsync(stats, 0, (size_t)M * 2 * sizeof(float), st));
+        if (int r = ActOps<T>::lin_res(h, ao, C, W.proj, x, C, x, C, M, st, &produce)) return r;
+        if (int r = ActOps<T>::lin_act(h, xn, C, W.fc1_ln, hid, W.fc1.N, M, 1, st, &consume)) return r;
+      } else {
+        if (int r = ActOps<T>::lin_res(h, ao, C, W.proj, x, C, x, C, M, st)) return r;
+        KL(1, swin_layernorm<T>(x, C, W.n2g, W.n2b, xn, C, M, C, st));
+        if (int r = ActOps<T>::lin_act(h, xn, C, W.fc1, hid, W.fc1.N, M, 1, st)) return r;
+      }
+      have_x16 = fuse && bi + 1 < S.blocks.size();          // the last block of a stage feeds the merge / final norm (fp32)
+      if (have_x16) {
+        CU(cudaMemsetAsync(stats, 0, (size_t)M * 2 * sizeof(float), st));
+        if (int r = ActOps<T>::lin_res(h, hid, W.fc1.N, W.fc2, x, C, x, C, M, st, &produce)) return r;
+      } else {
+        if (int r = ActOps<T>::lin_res(h, hid, W.fc1.N, W.fc2, x, C, x, C, M, st)) return r;
+      }
     }
     if (S.has_merge) {
       const int M4 = Bc * (H / 2) * (H / 2);
@@ -1275,6 +1310,17 @@ int xn_finalize_weights(xn_handle* h, int precision) {
         if (precision != XN_PREC_FP32) {
           if (to_bf16(W.qkv) || to_bf16(W.proj) || to_bf16(W.fc1) || to_bf16(W.fc2)) return XN_ERR_CUDA;
           if (!rc) {
+            auto fold = [&](const LinW& src, const float* g_, const float* b_, LinW& dst) -> int {
+              void* w16 = nullptr; float* bo = nullptr;
+              CU(cudaMalloc(&w16, (size_t)src.N * src.K * 2)); h->owned.push_back(w16);
+              CU(cudaMalloc(&bo, (size_t)src.N * sizeof(float))); h->owned.push_back(bo);
+              KL(1, launch_fold_ln_weight(src.w, g_, b_, src.b, w16, bo, src.N, src.K, precision == XN_PREC_FP16, 0));
+              dst = src; dst.w = nullptr; dst.wb = w16; dst.b = bo;
+              return 0;
+            };
+            if (fold(W.qkv, W.n1g, W.n1b, W.qkv_ln) || fold(W.fc1, W.n2g, W.n2b, W.fc1_ln)) return XN_ERR_CUDA;
+          }
+          if (!rc) {
             float* bt = nullptr;
             CU(cudaMalloc(&bt, bias_derived_floats(S.heads) * sizeof(float)));
             h->owned.push_back(bt);
@@ -2058,6 +2104,7 @@ int xn_set_option(xn_handle* h, const char* name, int64_t value) {
   if (n == "op_out16") { h->op_out16 = value; return XN_OK; }
   if (n == "use_skinny") { h->use_skinny = value; h->drop_graphs(); return XN_OK; }
   if (n == "ln_on_load") { h->ln_on_load = value; h->drop_graphs(); return XN_OK; }
+  if (n == "ln_fuse") { h->ln_fuse = value; h->drop_graphs(); return XN_OK; }
   if (n == "decode_groups") { h->decode_groups = std::max<int64_t>(0, std::min<int64_t>(value, xn_handle::kMaxDecodeGroups)); h->drop_graphs(); return XN_OK; }
   if (n == "pdl") { g_pdl_enabled = value != 0; h->drop_graphs(); return XN_OK; }
   if (n == "tc_debug") { set_tc_debug((int)value); return XN_OK; }

@@ -58,6 +58,8 @@ struct TcEpilogue {
   float scale;  // accumulator multiplier (1 / div); a multiply, never a speculated division
   int w_static;        // weight tiles may be loaded before the dependency wait
   const float* a32; long lda32; const float* ln_g; const float* ln_b;   // LayerNorm-on-load source of A (or nullptr)
+  float* stats_out; void* x16_out; long ldx16;                          // producer side of the folded LayerNorm (fp32 output path)
+  const float* ln_stats; float ln_inv_k;                                // consumer side (16-bit output path)
   int use_tma_store;   // 16-bit output without residual: write through TMA (needs ldc % 8 == 0)
   int dbg;     // timing experiments only: 1 = skip the epilogue's global traffic, 2 = skip MMA issue, 4 = skip TMA loads
 };
@@ -459,6 +461,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
           if (col_base + lane < N) b_lo = ep.bias[col_base + lane];
           if (col_base + lane + 32 < N) b_hi = ep.bias[col_base + lane + 32];
         }
+        // folded LayerNorm: this lane's row scale 1/std (lane == accumulator row).  The weights were centred along K at load
+        // time, so the row mean has already dropped out of the accumulator (kernels.h: TcGemmArgs::ln_stats).
+        float ln_a = ep.scale;
+        if (ep.ln_stats != nullptr && active) {
+          const int row = m0 + q * 32 + lane;
+          if (row < M) {
+            const float2 st2 = *reinterpret_cast<const float2*>(ep.ln_stats + 2 * (long)row);
+            const float mean = st2.x * ep.ln_inv_k;
+            ln_a = 1.0f / sqrtf(fmaxf(st2.y * ep.ln_inv_k - mean * mean, 0.f) + 1e-5f);
+          }
+        }
         float* bias_s = bias_all + buf * BN + cq * 64;
         mbar_wait(tfull_bar(buf), acc_phase);
         tc_fence_after();
@@ -478,8 +491,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
 #pragma unroll
             for (int c = 0; c < 32; c += 4) {
               const float4 b4 = *reinterpret_cast<const float4*>(bias_s + half * 32 + c);
-              float t0 = fmaf(__uint_as_float(v[half][c]), ep.scale, b4.x), t1 = fmaf(__uint_as_float(v[half][c + 1]), ep.scale, b4.y);
-              float t2 = fmaf(__uint_as_float(v[half][c + 2]), ep.scale, b4.z), t3 = fmaf(__uint_as_float(v[half][c + 3]), ep.scale, b4.w);
+              float t0 = fmaf(__uint_as_float(v[half][c]), ln_a, b4.x), t1 = fmaf(__uint_as_float(v[half][c + 1]), ln_a, b4.y);
+              float t2 = fmaf(__uint_as_float(v[half][c + 2]), ln_a, b4.z), t3 = fmaf(__uint_as_float(v[half][c + 3]), ln_a, b4.w);
               if (ACT == 1) { t0 = gelu_fast(t0); t1 = gelu_fast(t1); t2 = gelu_fast(t2); t3 = gelu_fast(t3); }
               else if (ACT == 2) { t0 = fmaxf(t0, 0.f); t1 = fmaxf(t1, 0.f); t2 = fmaxf(t2, 0.f); t3 = fmaxf(t3, 0.f); }
               if (ep.fp16) {
@@ -553,6 +566,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
           const uint32_t t_base = tmem_base + ((uint32_t)(q * 32) << 16) + buf * Cfg::kAccCols + hf2 * (BN / 2);
           uint32_t v[2][16];
           tmem_ld16_nowait(t_base, v[0]);
+          float st_sum = 0.f, st_sq = 0.f;                 // folded LayerNorm, producer side: this row's partial statistics
+          const bool emit = ep.stats_out != nullptr;
+          const int my_row = row0 + lane;
 #pragma unroll
           for (int sub = 0; sub < kSub; ++sub) {
             const int cur = sub & 1;
@@ -570,6 +586,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             if (has_res) { mbar_wait(rbar[cur], rphase[cur]); rphase[cur] ^= 1u; }
             __syncwarp();
             if (!(ep.dbg & 1)) {
+              uint32_t xpk[8];
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
                 uint8_t* ptr = slab_gen[cur] + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4);
@@ -580,12 +597,33 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                 float x2 = fmaf(__uint_as_float(v[cur][4 * j + 2]), ep.scale, b4.z), x3 = fmaf(__uint_as_float(v[cur][4 * j + 3]), ep.scale, b4.w);
                 if (ACT == 1) { x0 = gelu_erf(x0); x1 = gelu_erf(x1); x2 = gelu_erf(x2); x3 = gelu_erf(x3); }
                 else if (ACT == 2) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); x2 = fmaxf(x2, 0.f); x3 = fmaxf(x3, 0.f); }
-                *reinterpret_cast<float4*>(ptr) = make_float4(x0 + r4.x, x1 + r4.y, x2 + r4.z, x3 + r4.w);
+                const float y0 = x0 + r4.x, y1 = x1 + r4.y, y2 = x2 + r4.z, y3 = x3 + r4.w;
+                *reinterpret_cast<float4*>(ptr) = make_float4(y0, y1, y2, y3);
+                if (emit) {
+                  st_sum += (y0 + y1) + (y2 + y3);
+                  st_sq = fmaf(y0, y0, fmaf(y1, y1, fmaf(y2, y2, fmaf(y3, y3, st_sq))));
+                  if (ep.fp16) {
+                    __half2 a2 = __floats2half2_rn(y0, y1), b2 = __floats2half2_rn(y2, y3);
+                    xpk[2 * j] = *reinterpret_cast<uint32_t*>(&a2); xpk[2 * j + 1] = *reinterpret_cast<uint32_t*>(&b2);
+                  } else {
+                    __nv_bfloat162 a2 = __floats2bfloat162_rn(y0, y1), b2 = __floats2bfloat162_rn(y2, y3);
+                    xpk[2 * j] = *reinterpret_cast<uint32_t*>(&a2); xpk[2 * j + 1] = *reinterpret_cast<uint32_t*>(&b2);
+                  }
+                }
+              }
+              if (emit && my_row < M && col + 15 < N) {     // the raw row rounded to the operand type (the next GEMM's A): one 32-byte sector
+                uint4* xdst = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(ep.x16_out) + (long)my_row * ep.ldx16 + col);
+                xdst[0] = make_uint4(xpk[0], xpk[1], xpk[2], xpk[3]);
+                xdst[1] = make_uint4(xpk[4], xpk[5], xpk[6], xpk[7]);
               }
               fence_async_smem();
               __syncwarp();
               if (lane == 0) tma_store_2d(&tma_c, slab_u32[cur], col, row0);
             }
+          }
+          if (emit && my_row < M && col_base < N) {
+            atomicAdd(ep.stats_out + 2 * (long)my_row, st_sum);
+            atomicAdd(ep.stats_out + 2 * (long)my_row + 1, st_sq);
           }
         }
         tc_fence_before();
@@ -819,7 +857,12 @@ static cudaError_t launch_tc(const TcGemmArgs& p, cudaStream_t st) {
       if (p.res && !make_map32(&mr, p.res, p.M, p.N, p.ldr)) return cudaErrorInvalidValue;
     }
   }
+  // the folded-LayerNorm hooks live in the two TMA-store epilogues only
+  if ((p.stats_out || p.ln_stats) && !tma_c_ok) return cudaErrorInvalidValue;
+  if (p.stats_out && (OUT != 0 || !p.x16_out || (p.ldx16 & 7) || (p.N & 15) || (reinterpret_cast<uintptr_t>(p.x16_out) & 15))) return cudaErrorInvalidValue;
+  if (p.ln_stats && (OUT != 1 || p.ln_k <= 0 || p.div != 0.f)) return cudaErrorInvalidValue;
   TcEpilogue ep{p.Cf, p.Cb, p.ldc, p.fp16, p.bias, p.res, p.ldr, p.div != 0.f ? 1.0f / p.div : 1.0f, p.w_static, p.a32, p.lda32, p.ln_g, p.ln_b,
+                p.stats_out, p.x16_out, p.ldx16, p.ln_stats, p.ln_k > 0 ? 1.0f / (float)p.ln_k : 0.f,
                 tma_c_ok ? 1 : 0, g_tc_debug};
   const int tiles = ((p.M + kBM * CTAS - 1) / (kBM * CTAS)) * ((p.N + BN - 1) / BN);
   const int slots = sm_count() / CTAS;

@@ -49,8 +49,19 @@ struct TcGemmArgs {
   // into shared memory in the UMMA layout by the epilogue warps before their epilogue role.  `A` is then unused.
   const float* a32; long lda32;
   const float *ln_g, *ln_b;
+  // LayerNorm folded ALGEBRAICALLY around the GEMM (Swin blocks).  With W' = gamma (.) W centred along K
+  // (W'_nk -= mean_k' W'_nk', so that sum_k W'_nk = 0):   LN(x) W^T + b = rstd (x W'^T) + (b + W beta)
+  // -- the row mean drops out of the contraction.  The producer of the residual stream (proj / fc2 / patch-merging
+  // reduction, fp32 output) also writes the raw rows rounded to 16 bits (x16_out) and adds their sum and sum of squares into
+  // stats_out (M x 2, zeroed by the caller); the consumer (qkv / fc1) takes those raw rows as A, the folded weights as W,
+  // b + W beta as `bias`, and scales every accumulator row by rstd from ln_stats (ln_k = LayerNorm width).
+  float* stats_out; void* x16_out; long ldx16;
+  const float* ln_stats; int ln_k;
 };
 bool tc_gemm_ln_supported(int M, int N, int K);
+// W (N x K) fp32, LayerNorm affine (gamma, beta: K) -> w16 = round16(gamma (.) W - row mean), bias_out_n = bias_n + sum_k W_nk beta_k
+cudaError_t launch_fold_ln_weight(const float* w, const float* gamma, const float* beta, const float* bias, void* w16,
+                                  float* bias_out, int N, int K, int fp16, cudaStream_t st);
 cudaError_t launch_gemm_tc(const TcGemmArgs& p, cudaStream_t st);
 bool tc_gemm_supported(int M, int N, int K);
 void set_tc_debug(int v);
