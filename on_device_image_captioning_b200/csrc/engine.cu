@@ -368,7 +368,7 @@ size_t swin_ws_bytes(const xn_config& c, int Bc, int prec) {
   b += 3 * tok * act;                                 // qkv
   b += tok * act;                                     // attention out
   b += (size_t)(c.mlp_ratio * tok) * act + 4096;      // mlp hidden
-  b += (size_t)Bc * L0 * 2 * 4;                         // per-row LayerNorm statistics (sum, sum of squares)
+  b += (size_t)Bc * L0 * 2 * 8;                         // per-row LayerNorm statistics (sum, sum of squares; 64-bit fixed point)
   return b + 16 * 256;
 }
 
@@ -390,7 +390,7 @@ int swin_forward_chunk(xn_handle* h, const float* img, int Bc, float* out, cudaS
   T* qkv = h->ws.get<T>(3 * tok0);
   T* ao = h->ws.get<T>(tok0);
   T* hid = h->ws.get<T>((size_t)(c.mlp_ratio * tok0) + 1024);
-  float* stats = h->ws.get<float>((size_t)Bc * G * G * 2);
+  float* stats = h->ws.get<float>((size_t)Bc * G * G * 4);      // (M x 2 64-bit fixed-point sums)
   WS_CHECK();
   // 16-bit modes: norm1 / norm2 are folded into the GEMMs around them (option "ln_fuse").  The GEMM that produces the
   // residual stream (proj, fc2) also writes the raw rows in 16 bits into `xn` and their sum / sum of squares into `stats`;
@@ -418,7 +418,7 @@ int swin_forward_chunk(xn_handle* h, const float* img, int Bc, float* out, cudaS
       }
       KL(1, ActOps<T>::attn(qkv, std::is_same<T, float>::value ? W.rpb : W.rpb_t, ao, Bc, H, C, S.heads, shift, st));
       if (fuse) {
-        CU(cudaMemsetAsync(stats, 0, (size_t)M * 2 * sizeof(float), st));
+        CU(cudaMemsetAsync(stats, 0, (size_t)M * 2 * sizeof(long long), st));
         if (int r = ActOps<T>::lin_res(h, ao, C, W.proj, x, C, x, C, M, st, &produce)) return r;
         if (int r = ActOps<T>::lin_act(h, xn, C, W.fc1_ln, hid, W.fc1.N, M, 1, st, &consume)) return r;
       } else {
@@ -428,7 +428,7 @@ int swin_forward_chunk(xn_handle* h, const float* img, int Bc, float* out, cudaS
       }
       have_x16 = fuse && bi + 1 < S.blocks.size();          // the last block of a stage feeds the merge / final norm (fp32)
       if (have_x16) {
-        CU(cudaMemsetAsync(stats, 0, (size_t)M * 2 * sizeof(float), st));
+        CU(cudaMemsetAsync(stats, 0, (size_t)M * 2 * sizeof(long long), st));
         if (int r = ActOps<T>::lin_res(h, hid, W.fc1.N, W.fc2, x, C, x, C, M, st, &produce)) return r;
       } else {
         if (int r = ActOps<T>::lin_res(h, hid, W.fc1.N, W.fc2, x, C, x, C, M, st)) return r;

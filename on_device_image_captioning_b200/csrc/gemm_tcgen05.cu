@@ -467,9 +467,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         if (ep.ln_stats != nullptr && active) {
           const int row = m0 + q * 32 + lane;
           if (row < M) {
-            const float2 st2 = *reinterpret_cast<const float2*>(ep.ln_stats + 2 * (long)row);
-            const float mean = st2.x * ep.ln_inv_k;
-            ln_a = 1.0f / sqrtf(fmaxf(st2.y * ep.ln_inv_k - mean * mean, 0.f) + 1e-5f);
+            const longlong2 st2 = *reinterpret_cast<const longlong2*>(reinterpret_cast<const long long*>(ep.ln_stats) + 2 * (long)row);
+            const float mean = __ll2float_rn(st2.x) * (1.0f / 16777216.0f) * ep.ln_inv_k;
+            ln_a = 1.0f / sqrtf(fmaxf(__ll2float_rn(st2.y) * (1.0f / 65536.0f) * ep.ln_inv_k - mean * mean, 0.f) + 1e-5f);
           }
         }
         float* bias_s = bias_all + buf * BN + cq * 64;
@@ -566,7 +566,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
           const uint32_t t_base = tmem_base + ((uint32_t)(q * 32) << 16) + buf * Cfg::kAccCols + hf2 * (BN / 2);
           uint32_t v[2][16];
           tmem_ld16_nowait(t_base, v[0]);
-          float st_sum = 0.f, st_sq = 0.f;                 // folded LayerNorm, producer side: this row's partial statistics
+          // folded LayerNorm, producer side: this row's partial statistics.  Every aligned group of 16 columns is summed in
+          // fp32 in a fixed order and then accumulated in 64-bit fixed point (2^-24 / 2^-16 units): integer adds commute, so
+          // the statistics -- and with them every caption -- depend neither on the tile shape chosen for this M nor on the
+          // order in which the tiles of a row finish
+          long long st_sum = 0, st_sq = 0;
           const bool emit = ep.stats_out != nullptr;
           const int my_row = row0 + lane;
 #pragma unroll
@@ -587,6 +591,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             __syncwarp();
             if (!(ep.dbg & 1)) {
               uint32_t xpk[8];
+              float g_sum = 0.f, g_sq = 0.f;
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
                 uint8_t* ptr = slab_gen[cur] + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4);
@@ -600,8 +605,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                 const float y0 = x0 + r4.x, y1 = x1 + r4.y, y2 = x2 + r4.z, y3 = x3 + r4.w;
                 *reinterpret_cast<float4*>(ptr) = make_float4(y0, y1, y2, y3);
                 if (emit) {
-                  st_sum += (y0 + y1) + (y2 + y3);
-                  st_sq = fmaf(y0, y0, fmaf(y1, y1, fmaf(y2, y2, fmaf(y3, y3, st_sq))));
+                  g_sum += (y0 + y1) + (y2 + y3);
+                  g_sq = fmaf(y0, y0, fmaf(y1, y1, fmaf(y2, y2, fmaf(y3, y3, g_sq))));
                   if (ep.fp16) {
                     __half2 a2 = __floats2half2_rn(y0, y1), b2 = __floats2half2_rn(y2, y3);
                     xpk[2 * j] = *reinterpret_cast<uint32_t*>(&a2); xpk[2 * j + 1] = *reinterpret_cast<uint32_t*>(&b2);
@@ -611,6 +616,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                   }
                 }
               }
+              if (emit) { st_sum += __float2ll_rn(g_sum * 16777216.0f); st_sq += __float2ll_rn(g_sq * 65536.0f); }
               if (emit && my_row < M && col + 15 < N) {     // the raw row rounded to the operand type (the next GEMM's A): one 32-byte sector
                 uint4* xdst = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(ep.x16_out) + (long)my_row * ep.ldx16 + col);
                 xdst[0] = make_uint4(xpk[0], xpk[1], xpk[2], xpk[3]);
@@ -622,8 +628,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             }
           }
           if (emit && my_row < M && col_base < N) {
-            atomicAdd(ep.stats_out + 2 * (long)my_row, st_sum);
-            atomicAdd(ep.stats_out + 2 * (long)my_row + 1, st_sq);
+            unsigned long long* so = reinterpret_cast<unsigned long long*>(ep.stats_out) + 2 * (long)my_row;
+            atomicAdd(so, (unsigned long long)st_sum);
+            atomicAdd(so + 1, (unsigned long long)st_sq);
           }
         }
         tc_fence_before();

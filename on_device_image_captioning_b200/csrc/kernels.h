@@ -53,7 +53,7 @@ struct TcGemmArgs {
   // (W'_nk -= mean_k' W'_nk', so that sum_k W'_nk = 0):   LN(x) W^T + b = rstd (x W'^T) + (b + W beta)
   // -- the row mean drops out of the contraction.  The producer of the residual stream (proj / fc2 / patch-merging
   // reduction, fp32 output) also writes the raw rows rounded to 16 bits (x16_out) and adds their sum and sum of squares into
-  // stats_out (M x 2, zeroed by the caller); the consumer (qkv / fc1) takes those raw rows as A, the folded weights as W,
+  // stats_out (M x 2 64-bit fixed-point integers -- order-independent, hence deterministic -- zeroed by the caller); the consumer (qkv / fc1) takes those raw rows as A, the folded weights as W,
   // b + W beta as `bias`, and scales every accumulator row by rstd from ln_stats (ln_k = LayerNorm width).
   float* stats_out; void* x16_out; long ldx16;
   const float* ln_stats; int ln_k;
