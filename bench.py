@@ -221,6 +221,8 @@ def run_ours(args):
     eng.load_state_dict(synth.make_state_dict(cfg, 0, "xavier"), args.precision)
     if args.swin_chunk:
         eng.set_option("swin_chunk", args.swin_chunk)
+    if args.early_exit is not None:
+        eng.set_option("early_exit", args.early_exit)
     B = args.batch
     n_rot = 3                                            # rotate inputs so they are never L2-resident
     host = [synth.make_images(cfg, B, seed=100 + rank * n_rot + i, kind="randn").pin_memory() for i in range(n_rot)]
@@ -529,6 +531,7 @@ def main():
     ap.add_argument("--precision", default=os.environ.get("XNV2_PRECISION", "fp16"), choices=["fp16", "bf16", "fp32"])
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--swin-chunk", type=int, default=0)
+    ap.add_argument("--early-exit", type=int, default=None, help="decode steps per conditional block (0 = no IF nodes; for profilers that cannot see into them)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-config4", action="store_true", help="skip the extra batch-512 (BASELINE configs[3] per-GPU shape) leg")
     ap.add_argument("--profile-region", action="store_true", help="cudaProfilerStart/Stop around the timed steps (for ncu launch lists)")

@@ -24,7 +24,7 @@ for i, r in enumerate(rows[2:]):
     rd = to_bytes(r[col("dram__bytes_read.sum")], units[col("dram__bytes_read.sum")])
     wr = to_bytes(r[col("dram__bytes_write.sum")], units[col("dram__bytes_write.sum")])
     name, m, n, k, ob, res = shapes[i % 4]
-    algo = (m * k + n * k) * 2 + m * n * ob + (m * n * 4 if res else 0)
+    algo = (m * k + n * k) * 2 + m * n * ob + (m * n * 4 if res else 0) + (m * n * 2 if res else 0)   # + the raw 16-bit rows the folded LayerNorm consumes
     launches.append(dict(launch=name, M=m, N=n, K=k, dram_read=rd, dram_write=wr, dram_total=rd + wr, algorithmic_bytes=algo,
                          traffic_over_algorithmic=(rd + wr) / algo, duration_us=float(r[col("gpu__time_duration.sum")]),
                          tensor_pipe_pct=float(r[col("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active")])
