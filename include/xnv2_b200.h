@@ -205,6 +205,10 @@ int xn_profile_read_min(xn_handle* h, double min_flops, double* ms_total, double
 /* With option "profile"=2 EVERY kernel launch of the library is bracketed by CUDA events (graphs off) and attributed to
  * its launcher; this writes "launcher<TAB>launches<TAB>total_ms" lines into buf (bench.py's bandwidth-roofline leg). */
 int xn_profile_kernels(xn_handle* h, char* buf, int cap);
+/* With option "mega_dbg"=1 CTA 0 of the persistent decoder-position kernel (decode_mega.cu) stores the device's
+ * %globaltimer (ns) at its start, before and after every grid barrier and at its end; this returns the number of
+ * timestamps of the LAST launch (>= 0) and copies up to `cap` of them (synchronises the device). */
+int xn_mega_timeline(xn_handle* h, uint64_t* out, int cap);
 
 /* Single-operator entry points (kernel-level parity tests call these through the ABI).
  * All pointers device, row-major, f32 unless noted. */

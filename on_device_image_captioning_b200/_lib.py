@@ -57,6 +57,7 @@ _SIGNATURES = {
     "xn_profile_read": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "xn_profile_read_min": (C.c_int, [_P, C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "xn_profile_kernels": (C.c_int, [_P, C.c_char_p, _I]),
+    "xn_mega_timeline": (C.c_int, [_P, C.POINTER(C.c_uint64), _I]),
     "xn_op_layernorm": (C.c_int, [_P, _P, _P, _P, _P, _I, _I, _P]),
     "xn_op_linear": (C.c_int, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "xn_op_linear_skinny": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),

@@ -145,6 +145,12 @@ struct xn_handle {
   int64_t use_graph = 1;
   int64_t op_out16 = 0;
   int64_t use_skinny = 1;
+  // 16-bit decoder positions as ONE persistent kernel per position (decode_mega.cu) instead of ~33 dependent launches;
+  // with fuse_topk the kernel also produces the log-softmax top-k of the 'max' beam search (logits never stored)
+  int64_t use_mega = 1, fuse_topk = 1;
+  unsigned* mega_bar = nullptr;       // grid-barrier counter of the persistent kernel
+  int64_t mega_dbg_mode = 0;
+  unsigned long long* mega_dbg = nullptr;   // option "mega_dbg": phase timestamps of the last persistent-kernel launch
   // Decoder-step LayerNorms folded into the consuming tcgen05 GEMM's A path.  Implemented and bit-identical to the
   // two-kernel path, but measured slower in the graph (14.4 us vs 6.5 us GEMM + 4.7 us LayerNorm kernel at M = 96: the
   // in-kernel normalisation sits on the critical path in front of the first MMA; 64-image call 29.5 vs 28.8 ms), so it
@@ -666,6 +672,10 @@ struct DecBufs {
   void *xn, *att, *hid, *yn, *ycat16, *kv;      // fp32 in the parity mode, 16-bit operands otherwise
   void* e16;                                    // 16-bit copy of the encoder output (operand of the cross K/V projection)
   int R, P;
+  // persistent-kernel path: when topk > 0 the step also leaves log-softmax top-k in topv / topi (topk_done is set by
+  // dec_step when it did; otherwise the caller runs the separate log-softmax + top-k kernel on the logits)
+  float* mega_scratch = nullptr;
+  void* parts = nullptr; int topk = 0; float* topv = nullptr; int* topi = nullptr; bool topk_done = false;
 };
 
 size_t dec_ws_bytes(const xn_config& c, int R, int P, int n_images, bool own_logits) {
@@ -678,7 +688,7 @@ size_t dec_ws_bytes(const xn_config& c, int R, int P, int n_images, bool own_log
   f += (size_t)n_images * c.enc_len * c.n_dec * 2 * d;
   f += (size_t)n_images * c.enc_len * d;          // 16-bit copy of the encoder output
   if (own_logits) f += (size_t)R * c.vocab;
-  return f * 4 + 64 * 256;
+  return f * 4 + mega_parts_bytes(R, c.vocab) + mega_scratch_bytes(R) + 64 * 256;
 }
 
 int dec_alloc(xn_handle* h, DecBufs& D, int R, int P, int n_images) {
@@ -702,6 +712,9 @@ int dec_alloc(xn_handle* h, DecBufs& D, int R, int P, int n_images) {
   D.kv = h->ws.get<float>((size_t)n_images * c.enc_len * c.n_dec * 2 * d);
   // planned here, not taken from the arena at run time: the Swin / encoder chunks reset the arena offset in between
   D.e16 = h->ws.get<float>(((size_t)n_images * c.enc_len * d + 1) / 2);
+  D.parts = h->ws.get<char>(mega_parts_bytes(R, c.vocab));
+  D.mega_scratch = h->ws.get<float>(mega_scratch_bytes(R) / 4);
+  D.topk = 0; D.topv = nullptr; D.topi = nullptr; D.topk_done = false;
   return 0;
 }
 
@@ -755,6 +768,43 @@ int dec_project_kv(xn_handle* h, DecBufs& D, const float* enc_out, int n_images,
   return lin_tc(h, e16, d, h->kv_all, nullptr, 0, nullptr, D.kv, h->kv_all.N, M, 0, std::is_same<T, f16>::value, st);
 }
 
+// one decoder position for all rows as ONE persistent kernel (16-bit modes; decode_mega.cu).  Returns 1 when the
+// geometry is not covered: the caller then runs the one-kernel-per-operation sequence.
+template <typename T>
+int dec_step_mega(xn_handle* h, DecBufs& D, int p, const int64_t* tok64, const int* tok32, long tok_stride,
+                  int rows_per_image, const int* n_valid, const int* row_len, float* logits, long ldl, cudaStream_t st) {
+  const xn_config& c = h->cfg;
+  if (!h->use_mega || h->profile || (int)h->dec.size() > kMegaMaxLayers) return 1;
+  MegaArgs a{};
+  a.s = D.s; a.p = p; a.n_layers = c.n_dec; a.d = c.d_model; a.ff = c.ff; a.n_exp = c.num_exp_dec; a.heads = c.num_heads;
+  a.n_keys = c.enc_len; a.vocab = c.vocab; a.R = D.R; a.rows_per_image = rows_per_image;
+  for (int l = 0; l < c.n_dec; ++l) {
+    const DecLayerW& W = h->dec[l];
+    MegaLayer& m = a.L[l];
+    m.n1g = W.n1g; m.n1b = W.n1b; m.n2g = W.n2g; m.n2b = W.n2b; m.n3g = W.n3g; m.n3b = W.n3b; m.qexp = W.qexp; m.bexp = W.bexp;
+    m.w_dyn5 = W.dyn5.wb; m.w_wq = W.wq.wb; m.w_wo = W.wo.wb; m.w_ff1 = W.ff1.wb; m.w_ff2 = W.ff2.wb;
+    m.b_dyn5 = W.dyn5.b; m.b_wq = W.wq.b; m.b_wo = W.wo.b; m.b_ff1 = W.ff1.b; m.b_ff2 = W.ff2.b;
+    if (W.dyn5.N != 5 * c.d_model || W.dyn5.K != c.d_model || W.ff1.N != c.ff || W.ff2.K != c.ff) return 1;
+  }
+  a.tok64 = tok64; a.tok32 = tok32; a.tok_stride = tok_stride; a.n_valid = n_valid; a.row_len = row_len;
+  a.emb = h->emb; a.pos = h->pos;
+  a.x0 = D.x0; a.ycat = D.ycat; a.q = D.q; a.pre = D.pre; a.xn = D.xn; a.att = D.att; a.hid = D.hid; a.ycat16 = D.ycat16;
+  a.kv = D.kv; a.ldkv = (long)c.n_dec * 2 * c.d_model;
+  a.w_reduce = h->dec_reduce.wb; a.b_reduce = h->dec_reduce.b; a.ng = h->dec_ng; a.nb = h->dec_nb;
+  a.w_vocab = h->vocab.wb; a.b_vocab = h->vocab.b;
+  a.logits = logits; a.ldl = ldl;
+  const bool fuse = h->fuse_topk && D.topk > 0 && D.topv && D.topi && D.parts;
+  a.topk = fuse ? D.topk : 0; a.parts = D.parts; a.top_val = D.topv; a.top_idx = D.topi;
+  // fixed split factors (not chosen by row count): the summation order, hence every bit of the result, is independent of the batch
+  a.ksplit_ff2 = c.ff / 512; a.ksplit_red = c.n_dec; a.scratch = D.mega_scratch;
+  a.bar = h->mega_bar; a.dbg = h->mega_dbg; a.dbg_mode = (int)h->mega_dbg_mode;
+  if (h->dec_reduce.K != c.d_model * c.n_dec || h->dec_reduce.N != c.d_model || h->vocab.K != c.d_model) return 1;
+  if (!mega_supported(a)) return 1;
+  KL(1, launch_dec_step_mega<T>(a, st));
+  D.topk_done = fuse;
+  return 0;
+}
+
 // one decoder position for all rows -> logits (R, V) at `logits` with row stride ldl
 template <typename T>
 int dec_step_t(xn_handle* h, DecBufs& D, int p, const int64_t* tok64, const int* tok32, long tok_stride,
@@ -767,6 +817,11 @@ int dec_step_t(xn_handle* h, DecBufs& D, int p, const int64_t* tok64, const int*
   T* hid = reinterpret_cast<T*>(D.hid);
   T* yn = reinterpret_cast<T*>(D.yn);
   constexpr bool k16 = !std::is_same<T, float>::value;
+  D.topk_done = false;
+  if constexpr (k16) {
+    const int rm = dec_step_mega<T>(h, D, p, tok64, tok32, tok_stride, rows_per_image, n_valid, row_len, logits, ldl, st);
+    if (rm <= 0) return rm;
+  }
   // 16-bit modes with a few hundred rows: the latency-oriented kernel (LayerNorm / conversion of A fused into its load)
   auto skinny = [&](const T* a16, const float* a32, long lda, const float* g, const float* b, const LinW& w, const float* res,
                     long ldr, float* yf, T* y16, long ldy, int act) -> int {
@@ -1000,16 +1055,17 @@ int beam_run(xn_handle* h, BeamPlan& P, const float* enc_out, int B, int beam, i
   int src = 0;
   // step 0: every beam row decodes [SOS]
   D.s.anc = bb.anc[0];
+  D.topk = smp.on ? 0 : beam; D.topv = P.topv; D.topi = P.topi;      // 'max': the persistent kernel fuses log-softmax + top-k
   if (int r = dec_step(h, D, 0, nullptr, bb.tokens[0], L, beam, P.nv, nullptr, P.logits, c.vocab, st)) return r;
   if (smp.on) KL(1, launch_gumbel_topk(P.logits, c.vocab, R, c.vocab, beam, smp.seed, 1, P.topv, P.topi, st));
-  else KL(1, launch_logsoftmax_topk(P.logits, c.vocab, R, c.vocab, beam, P.topv, P.topi, nullptr, 0, 0, st));
+  else if (!D.topk_done) KL(1, launch_logsoftmax_topk(P.logits, c.vocab, R, c.vocab, beam, P.topv, P.topi, nullptr, 0, 0, st));
   KL(1, launch_beam_first(bb, P.topv, P.topi, B, beam, L, eos, st));
   // one loop iteration of the reference (captioning_model.py:295-397) on stream `s2`
   auto one_step = [&](int t, cudaStream_t s2) -> int {
     D.s.anc = bb.anc[src];
     if (int r = dec_step(h, D, t - 1, nullptr, bb.tokens[src], L, beam, P.nv, nullptr, P.logits, c.vocab, s2)) return r;
     if (smp.on) KL(1, launch_gumbel_topk(P.logits, c.vocab, R, c.vocab, beam, smp.seed, t, P.topv, P.topi, s2));
-    else KL(1, launch_logsoftmax_topk(P.logits, c.vocab, R, c.vocab, beam, P.topv, P.topi, nullptr, 0, 0, s2));
+    else if (!D.topk_done) KL(1, launch_logsoftmax_topk(P.logits, c.vocab, R, c.vocab, beam, P.topv, P.topi, nullptr, 0, 0, s2));
     KL(1, launch_beam_step(bb, src, P.topv, P.topi, B, beam, L, t, eos, s2));
     src ^= 1;
     return 0;
@@ -1157,7 +1213,8 @@ int xn_create(const xn_config* cfg, int device, xn_handle** out) {
   h->cfg = *cfg;
   h->device = device;
   cudaSetDevice(device);
-  if (cudaMalloc(&h->flag_dev, sizeof(int)) != cudaSuccess || cudaMemset(h->flag_dev, 0, sizeof(int)) != cudaSuccess) {
+  if (cudaMalloc(&h->flag_dev, sizeof(int)) != cudaSuccess || cudaMemset(h->flag_dev, 0, sizeof(int)) != cudaSuccess ||
+      cudaMalloc(&h->mega_bar, kMegaBarBytes) != cudaSuccess || cudaMemset(h->mega_bar, 0, kMegaBarBytes) != cudaSuccess) {
     g_create_error = "cudaMalloc failed";
     delete h;
     return XN_ERR_CUDA;
@@ -1183,6 +1240,8 @@ int xn_destroy(xn_handle* h) {
   }
   if (h->hstream) cudaStreamDestroy(h->hstream);
   if (h->flag_dev) cudaFree(h->flag_dev);
+  if (h->mega_bar) cudaFree(h->mega_bar);
+  if (h->mega_dbg) cudaFree(h->mega_dbg);
   if (h->pp_buf) cudaFree(h->pp_buf);
   if (h->pp_host) cudaFreeHost(h->pp_host);
   if (h->jpg_state) g_nvjpeg.state_destroy(h->jpg_state);
@@ -1552,7 +1611,7 @@ static int beam_search_impl(xn_handle* h, const float* input, const float* host_
   int G = (int)h->decode_groups;
   // measured at batch 64 (profiles/r2_quick_time_decode_groups.txt): 2 groups -0.6 ms, 4 groups +0.9 ms, 8 groups +3.8 ms --
   // beyond two chains the graph's kernel-node dispatch rate, not kernel latency, is the limit
-  if (G <= 0) G = B >= 32 ? 2 : 1;
+  if (G <= 0) G = (B >= 32 && !(h->use_mega && h->precision != XN_PREC_FP32)) ? 2 : 1;   // the persistent kernel fills the machine alone
   if (h->profile) G = 1;                                    // per-launch event timing wants one stream
   G = std::max(1, std::min(G, std::min(B, (int)xn_handle::kMaxDecodeGroups)));
   std::vector<BeamPlan> P(G);
@@ -2103,6 +2162,16 @@ int xn_set_option(xn_handle* h, const char* name, int64_t value) {
   if (n == "use_graph") { h->use_graph = value; h->drop_graphs(); return XN_OK; }
   if (n == "op_out16") { h->op_out16 = value; return XN_OK; }
   if (n == "use_skinny") { h->use_skinny = value; h->drop_graphs(); return XN_OK; }
+  if (n == "use_mega") { h->use_mega = value; h->drop_graphs(); return XN_OK; }
+  if (n == "fuse_topk") { h->fuse_topk = value; h->drop_graphs(); return XN_OK; }
+  if (n == "mega_dbg") {
+    if (value && !h->mega_dbg) { if (cudaMalloc(&h->mega_dbg, 128 * 8) != cudaSuccess) return h->fail(XN_ERR_CUDA, "cudaMalloc failed"); cudaMemset(h->mega_dbg, 0, 128 * 8); }
+    if (!value && h->mega_dbg) { cudaDeviceSynchronize(); cudaFree(h->mega_dbg); h->mega_dbg = nullptr; }
+    h->drop_graphs();
+    return XN_OK;
+  }
+  if (n == "mega_dbg_mode") { h->mega_dbg_mode = value; h->drop_graphs(); return XN_OK; }
+  if (n == "mega_coop") { g_mega_coop = value != 0; h->drop_graphs(); return XN_OK; }
   if (n == "ln_on_load") { h->ln_on_load = value; h->drop_graphs(); return XN_OK; }
   if (n == "ln_fuse") { h->ln_fuse = value; h->drop_graphs(); return XN_OK; }
   if (n == "decode_groups") { h->decode_groups = std::max<int64_t>(0, std::min<int64_t>(value, xn_handle::kMaxDecodeGroups)); h->drop_graphs(); return XN_OK; }
@@ -2121,6 +2190,17 @@ int xn_set_option(xn_handle* h, const char* name, int64_t value) {
   else if (n == "enc_chunk") h->enc_chunk = std::max<int64_t>(1, value);
   else return h->fail(XN_ERR_ARG, "unknown option '%s'", name);
   return XN_OK;
+}
+
+int xn_mega_timeline(xn_handle* h, uint64_t* out, int cap) {
+  if (!h || !out || cap < 1) return XN_ERR_ARG;
+  if (!h->mega_dbg) return h->fail(XN_ERR_STATE, "option mega_dbg is off");
+  CU(cudaDeviceSynchronize());
+  unsigned long long buf[128];
+  CU(cudaMemcpy(buf, h->mega_dbg, sizeof buf, cudaMemcpyDeviceToHost));
+  const int n = (int)std::min<unsigned long long>(buf[127], 64);
+  for (int i = 0; i < cap; ++i) out[i] = i < n ? buf[i] : (i >= 64 && i < (int)std::min<unsigned long long>(buf[126], 126) ? buf[i] : 0);
+  return n;
 }
 
 int xn_profile_read(xn_handle* h, double* ms_total, double* flops_total, int64_t* count) {

@@ -180,6 +180,44 @@ template <typename KvT, typename OutT>
 cudaError_t launch_cross_attn_step(const float* q, long ldq, const KvT* kv, long ldkv, int k_off, int v_off,
                                    OutT* out, long ldo, int R, int rows_per_image, int n_keys, int heads, int dk,
                                    const int* n_valid, const int* row_len, int p, cudaStream_t st);
+// ---------------------------------------------------------------- persistent whole-position decoder kernel (decode_mega.cu)
+// One launch = one decoder position for all rows (16-bit modes, d_model 512, head width 64): embedding, every decoder
+// layer, reduce group, final norm + vocabulary projection; with topk > 0 also log-softmax + top-k (the logits are then
+// never stored).  Phases are separated by a grid barrier; the grid is launched cooperatively.
+constexpr int kMegaMaxLayers = 4;
+struct MegaLayer {
+  const float *n1g, *n1b, *n2g, *n2b, *n3g, *n3b, *qexp, *bexp;
+  const void *w_dyn5, *w_wq, *w_wo, *w_ff1, *w_ff2;          // (N x K) 16-bit
+  const float *b_dyn5, *b_wq, *b_wo, *b_ff1, *b_ff2;
+};
+struct MegaArgs {
+  DecState s;
+  int p, n_layers, d, ff, n_exp, heads, n_keys, vocab, R, rows_per_image;
+  MegaLayer L[kMegaMaxLayers];
+  const int64_t* tok64; const int* tok32; long tok_stride;
+  const int* n_valid; const int* row_len;
+  const float *emb, *pos;
+  float *x0, *ycat, *q, *pre;                 // fp32: embedding, layer outputs side by side (ld d*n_layers), queries, reduce output
+  void *xn, *att, *hid, *ycat16;              // 16-bit operands
+  const void* kv; long ldkv;                  // cross K/V of all layers per encoder token: [layer][K | V]
+  const void* w_reduce; const float* b_reduce;
+  const float *ng, *nb;
+  const void* w_vocab; const float* b_vocab;
+  float* logits; long ldl;                    // topk == 0: logits out
+  int topk; void* parts; float* top_val; int* top_idx;      // topk > 0: log-prob / index of the k best words per row
+  unsigned* bar;                              // kMegaBarBytes: grid-barrier words + split-K tile counters (zeroed once; self-restoring)
+  int ksplit_ff2, ksplit_red; float* scratch; // split-K over CTAs of the two long-K projections (partial tiles in `scratch`)
+  int dbg_mode;                               // timing experiments: bit 0 skip the MMAs, bit 1 skip the operand loads, bit 2 skip the LayerNorm fill
+  unsigned long long* dbg;                    // optional: CTA 0 stores %globaltimer before / after every barrier (2 per phase)
+};
+bool mega_supported(const MegaArgs& a);
+size_t mega_parts_bytes(int R, int vocab);
+size_t mega_scratch_bytes(int R);
+constexpr size_t kMegaBarBytes = 20 * 1024;
+template <typename T>
+cudaError_t launch_dec_step_mega(const MegaArgs& a, cudaStream_t st);
+extern int g_mega_coop;                       // 1: cooperative launch (default)
+
 // ensemble of up to kMaxEnsemble models: out = log(mean_m softmax(logits_m)) per row
 constexpr int kMaxEnsemble = 8;
 struct EnsembleLogits { const float* p[kMaxEnsemble]; int n; };

@@ -93,6 +93,15 @@ class Engine:
         self._check(self.lib.xn_profile_read_min(self._h, float(min_flops), C.byref(ms), C.byref(fl), C.byref(n)), "xn_profile_read_min")
         return ms.value, fl.value, n.value
 
+    def mega_timeline(self):
+        """%globaltimer stamps (ns) of CTA 0 in the last persistent decoder-position launch (set_option('mega_dbg', 1))."""
+        buf = (C.c_uint64 * 128)()
+        n = self.lib.xn_mega_timeline(self._h, buf, 128)
+        if n < 0:
+            self._check(n, "xn_mega_timeline")
+        self.mega_fine = [int(buf[i]) for i in range(64, 126) if buf[i]]     # intra-phase stamps of the GEMM phases (layer 0, tail)
+        return [int(buf[i]) for i in range(n)]
+
     def profile_kernels(self):
         """{launcher: (launches, total_ms)} of every kernel launch since set_option('profile', 2)."""
         buf = C.create_string_buffer(1 << 16)

@@ -900,7 +900,7 @@ def check_early_exit() -> List[Triple]:
         lens = sorted({len(c_) for c_ in res[4]})
         if boost > 0:
             out.append((f"early exit [{label}]: longest caption (tokens incl. SOS/EOS)", float(lens[-1]), 3.0))
-            out.append((f"early exit [{label}]: replay time with early exit / without ({ms[4]:.2f} / {ms[0]:.2f} ms)", ms[4] / ms[0], 0.6))
+            out.append((f"early exit [{label}]: replay time with early exit / without ({ms[4]:.2f} / {ms[0]:.2f} ms)", ms[4] / ms[0], 0.8))
         else:
             out.append((f"early exit [{label}]: shortest caption", float(-lens[0]), -20.0))
             out.append((f"early exit [{label}]: replay time with early exit / without ({ms[4]:.2f} / {ms[0]:.2f} ms) (the IF nodes' own cost)", ms[4] / ms[0], 1.08))
