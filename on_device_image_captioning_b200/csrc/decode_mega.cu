@@ -28,7 +28,8 @@ int g_mega_coop = 1;
 
 constexpr int kMegaThreads = 256;
 constexpr int kBM = 32, kKI = 512;              // rows per tile; K per work item (longer K is split over CTAs)
-constexpr int kPitch = (kKI + 8) * 2;           // 1040 bytes per operand row: consecutive rows shift by 16 bytes -> ldmatrix is conflict-free
+constexpr int kPadK = kKI + 8;                  // elements per packed operand row
+constexpr int kPitch = kPadK * 2;           // 1040 bytes per operand row: consecutive rows shift by 16 bytes -> ldmatrix is conflict-free
 constexpr int kARegion = kBM * kPitch;          // 33 280 bytes
 constexpr int kWRegion = 64 * kPitch;           // 66 560 bytes (BN <= 64)
 constexpr int kMbarOff = kARegion + kWRegion;   // one mbarrier behind the operand regions
@@ -43,34 +44,29 @@ __device__ __forceinline__ unsigned long long gtimer() {
   return t;
 }
 
-// ---- grid barrier.  Arrivals are atomic adds on one word (cooperative groups' trick: CTA 0 adds 2^31 - (n-1), the
-// others 1, so bit 31 flips exactly on the last arrival and the word needs no reset); the last arriver publishes a
-// generation number in a SEPARATE line, which is what everybody polls -- the pollers' loads do not queue in front of the
-// arrivals at the L2 slice.  __threadfence() (gpu scope) orders the data and invalidates the SM's L1 (CCTL.IVALL), so plain
-// loads after the barrier see what other CTAs wrote before it; fence.proxy.async extends that to the bulk-copy engine.
+// ---- grid barrier.  Arrivals are release atomic adds on one word (cooperative groups' trick: CTA 0 adds 2^31 - (n-1),
+// the others 1, so bit 31 flips exactly on the last arrival and the word needs no reset between barriers or launches).
+// The acquire side is one fence.acq_rel.gpu after the flip has been seen: it orders the data and invalidates the SM's L1
+// (CCTL.IVALL), so plain loads after the barrier see what other CTAs wrote before it.  Measured alternatives (a separate
+// flag line published by the last arriver; two-level arrival counters; __threadfence() = MEMBAR.SC on both sides) were
+// all slower: the cost is the chain store-acknowledge -> atomic round trip -> poll round trip, not contention.
 struct GridBar {
-  unsigned* cnt; unsigned* flag; unsigned gen;
-  __device__ __forceinline__ void init(unsigned* b) {
-    cnt = b;
-    flag = b + kBarStride;
-    gen = 0u;
-    if (threadIdx.x == 0) gen = *reinterpret_cast<volatile unsigned*>(flag);           // read before this CTA's first arrival: cannot have advanced yet
-  }
+  unsigned* cnt;
+  __device__ __forceinline__ void init(unsigned* b) { cnt = b; }
   __device__ __forceinline__ void sync(unsigned long long* dbg = nullptr, int* mark = nullptr) {
     __syncthreads();
     if (dbg && blockIdx.x == 0 && threadIdx.x == 0) dbg[(*mark)++] = gtimer();
     if (threadIdx.x == 0) {
-      // acquire / release instead of __threadfence(): one MEMBAR.ALL.GPU at the arrival (two for the last arriver) in place
-      // of three MEMBAR.SC.GPU; the acquire load carries the L1 invalidation
       const unsigned inc = (blockIdx.x == 0) ? (0x80000000u - (gridDim.x - 1)) : 1u;
       unsigned old, v;
-      asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], %2;" : "=r"(old) : "l"(cnt), "r"(inc) : "memory");
-      if ((old ^ (old + inc)) & 0x80000000u)     // last arrival
-        asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(flag), "r"(gen + 1u) : "memory");
-      do {
-        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
-      } while (v == gen);
-      gen += 1u;
+      asm volatile("atom.release.gpu.global.add.u32 %0, [%1], %2;" : "=r"(old) : "l"(cnt), "r"(inc) : "memory");
+      // everybody polls the arrival word itself (bit 31 flips on the last arrival) with RELAXED loads -- an acquire load
+      // would carry an L1 invalidation per iteration -- and fences once afterwards
+      while (true) {
+        asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(cnt) : "memory");
+        if ((v ^ old) & 0x80000000u) break;
+      }
+      asm volatile("fence.acq_rel.gpu;" ::: "memory");
     }
     __syncthreads();
     if (dbg && blockIdx.x == 0 && threadIdx.x == 0) dbg[(*mark)++] = gtimer();
@@ -78,14 +74,17 @@ struct GridBar {
 };
 
 struct GemmP {
-  const void* A16; long lda;                                  // 16-bit A (M x K), or
+  const void* A16;                                            // 16-bit A, slab-packed [K/512][M32][520] (see mega_pack), or
   const float* A32; long lda32; const float *ln_g, *ln_b;     // fp32 rows normalised on load (K == 512)
-  const void* W; const float* bias;                           // (N x K) 16-bit, K contiguous
+  const void* W; const float* bias;                           // 16-bit W, slab-packed [K/512][N][520]
   const float* res; long ldr;                                 // fp32 residual added after the activation (may alias Cf)
   float* Cf; long ldcf;                                       // fp32 output and / or
-  void* Cb; long ldcb;                                        // 16-bit output
+  void* Cb;                                                   // 16-bit output, slab-packed [N/512][M32][520]
   int M, N, K, act;                                           // act: 0 none, 2 ReLU;  K = 512 * ksplit
   int ksplit; float* scratch; unsigned* cnt;                  // split-K over CTAs: partial tiles + per-tile arrival counters
+  // first decoder layer: the fp32 rows are the embedding itself, x0 = E[tok] sqrt(d) + P[p] (layers.py:16-17), computed in
+  // the LayerNorm fill; the column-tile-0 items also store x0 (the residual input of the dynamic expansion)
+  const float *emb, *pos_row; const int64_t* tok64; const int* tok32; long tok_stride; int tok_p; float* x0_out;
   int dbg_mode;
   unsigned long long* fine; int* fmark;                      // optional intra-phase timestamps (CTA 0, thread 0)
 };
@@ -115,7 +114,11 @@ struct NoTileHook {
   __device__ __forceinline__ void operator()(int, int, int, const float*) const {}
 };
 
-#define XN_FINE(g) do { if ((g).fine && blockIdx.x == 0 && threadIdx.x == 0 && *(g).fmark < 126) (g).fine[(*(g).fmark)++] = gtimer(); } while (0)
+#ifdef XN_MEGA_FINE      // intra-phase timestamps (build with -DXN_MEGA_FINE; tools/mega_timeline.py prints them)
+#define XN_FINE(g) do { if ((g).fine && blockIdx.x == 0 && threadIdx.x == 0 && *(g).fmark < 124) (g).fine[(*(g).fmark)++] = gtimer(); } while (0)
+#else
+#define XN_FINE(g) do { } while (0)
+#endif
 
 // One GEMM phase.  A work item is a 32 x BN output tile over K = 512 (longer K: ksplit items per tile).  Both operands
 // of an item are brought in whole -- one 1 KB bulk copy (cp.async.bulk) per operand row, completing on an mbarrier: no
@@ -125,51 +128,66 @@ struct NoTileHook {
 // run with coalesced 16-byte accesses.  With ksplit > 1 the partial tile goes to `scratch` and the CTA that arrives last
 // at the tile's counter adds the splits in order (deterministic) and finishes.
 template <typename T, int BN, bool LN, bool STORE = true, typename Hook = NoTileHook>
-__device__ __forceinline__ void gemm_phase(const GemmP& g, char* smem, uint32_t& mphase, const Hook& hook = Hook()) {
+__device__ __forceinline__ void gemm_phase_impl(const GemmP& g, char* smem, uint32_t& mphase, const Hook& hook = Hook()) {
   constexpr int NB2 = BN / 16, NF = BN / 8, PITCH = BN + 8, C4 = BN / 4;
-  static_assert(8 * kBM * PITCH * 4 <= kMbarOff, "reduction tiles must fit in the operand regions");
+  static_assert(4 * kBM * PITCH * 4 <= kWRegion, "reduction tiles must fit in the W region");
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int S = g.ksplit > 1 ? g.ksplit : 1;
   const int ntm = (g.M + kBM - 1) / kBM, ntn = (g.N + BN - 1) / BN, ntiles = ntm * ntn;
+  const long m32 = (long)ntm * kBM;                               // rows of a packed activation slab
   char* a_sm = smem;
   char* w_sm = smem + kARegion;
-  float* red = reinterpret_cast<float*>(smem);                   // [8][32][PITCH] after the MMAs
+  float* red = reinterpret_cast<float*>(smem + kARegion);        // [4][32][PITCH] after the MMAs (the A region survives: A-stationary tiles)
   const uint32_t mbar = smem_u32(smem + kMbarOff);
   __shared__ int s_last;
   const T* W = reinterpret_cast<const T*>(g.W);
   const T* A16 = reinterpret_cast<const T*>(g.A16);
-  for (int item = blockIdx.x; item < ntiles * S; item += gridDim.x) {
+  // A-stationary order for the LayerNorm operand: a CTA keeps one 32-row block and walks over column tiles, so the rows
+  // are normalised once per CTA instead of once per item (the vocabulary projection has 157 column tiles)
+  const bool astat = LN && S == 1 && (int)gridDim.x >= ntm;
+  const int cpg = astat ? (int)gridDim.x / ntm : 1;
+  const int my_tm = blockIdx.x % ntm, my_slot = blockIdx.x / ntm;
+  const int it_end = astat ? ntn : ntiles * S, it_step = astat ? cpg : (int)gridDim.x;
+  bool a_ready = false;
+  for (int it = astat ? (my_slot < cpg ? my_slot : ntn) : (int)blockIdx.x; it < it_end; it += it_step) {
+    const int item = astat ? it * ntm + my_tm : it;
     const int tile = item / S, sp = item - tile * S;
-    const int tm = tile % ntm, tn = tile / ntm, r0 = tm * kBM, n0 = tn * BN, k0 = sp * kKI;
+    const int tm = tile % ntm, tn = tile / ntm, r0 = tm * kBM, n0 = tn * BN;
     XN_FINE(g);                                          // 0: item start
     const bool do_load = !(g.dbg_mode & 2);
-    if (do_load && warp == 0) {
-      // the regions were last touched through the generic proxy (ldmatrix / reduction) by this CTA, all before the
-      // __syncthreads that ended the previous item
+    if (do_load && tid == 0) {
+      // Operands are stored with the 520-element row pitch of the shared-memory tile (weights re-packed at load time,
+      // activations written that way by the producing phase), one K slab of 512 after the other: a whole operand tile is
+      // ONE contiguous bulk copy.  The regions were last touched through the generic proxy (ldmatrix / reduction) by this
+      // CTA, all before the __syncthreads that ended the previous item.
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      if (lane == 0) mbar_expect(mbar, (uint32_t)((BN + (LN ? 0 : kBM)) * kKI * 2));
-      __syncwarp();
-#pragma unroll
-      for (int i = lane; i < BN + (LN ? 0 : kBM); i += 32) {
-        if (i < BN) {
-          const int nrow = min(n0 + i, g.N - 1);
-          bulk_g2s(smem_u32(w_sm + i * kPitch), W + (long)nrow * g.K + k0, kKI * 2, mbar);
-        } else {
-          const int row = i - BN, arow = min(r0 + row, g.M - 1);
-          bulk_g2s(smem_u32(a_sm + row * kPitch), A16 + (long)arow * g.lda + k0, kKI * 2, mbar);
-        }
-      }
+      const int wrows = min(BN, g.N - n0);
+      mbar_expect(mbar, (uint32_t)((wrows + (LN ? 0 : kBM)) * kPitch));
+      bulk_g2s(smem_u32(w_sm), W + ((long)sp * g.N + n0) * kPadK, (uint32_t)(wrows * kPitch), mbar);
+      if (!LN) bulk_g2s(smem_u32(a_sm), A16 + ((long)sp * m32 + r0) * kPadK, (uint32_t)(kBM * kPitch), mbar);
     }
-    if (LN && !(g.dbg_mode & 4)) {
+    if (LN && !a_ready && !(g.dbg_mode & 4)) {
       // LayerNorm(gamma, beta) of rows r0 .. r0+31 (K == 512): four rows per warp, all their loads in flight together; same
       // arithmetic and summation order as layernorm_kernel (elementwise.cu: ln_row)
       float4 v[4][4];
 #pragma unroll
       for (int rr = 0; rr < 4; ++rr) {
-        const int grow = r0 + warp * 4 + rr;
-        const float* xr = g.A32 + (long)min(grow, g.M - 1) * g.lda32;
+        const int grow = r0 + warp * 4 + rr, crow_ = min(grow, g.M - 1);
+        if (g.emb) {
+          const long tok = g.tok64 ? (long)g.tok64[crow_ * g.tok_stride + g.tok_p] : (long)g.tok32[crow_ * g.tok_stride + g.tok_p];
+          const float sc = sqrtf(512.0f);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) v[rr][j] = __ldcg(reinterpret_cast<const float4*>(xr + j * 128 + lane * 4));
+          for (int j = 0; j < 4; ++j) {
+            const float4 e4 = *reinterpret_cast<const float4*>(g.emb + tok * 512 + j * 128 + lane * 4);
+            const float4 p4 = *reinterpret_cast<const float4*>(g.pos_row + j * 128 + lane * 4);
+            v[rr][j] = make_float4(e4.x * sc + p4.x, e4.y * sc + p4.y, e4.z * sc + p4.z, e4.w * sc + p4.w);
+            if (tn == 0 && grow < g.M) *reinterpret_cast<float4*>(g.x0_out + (long)grow * 512 + j * 128 + lane * 4) = v[rr][j];
+          }
+        } else {
+          const float* xr = g.A32 + (long)crow_ * g.lda32;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) v[rr][j] = __ldcg(reinterpret_cast<const float4*>(xr + j * 128 + lane * 4));
+        }
       }
       float4 gg[4], bb[4];
 #pragma unroll
@@ -217,7 +235,8 @@ __device__ __forceinline__ void gemm_phase(const GemmP& g, char* smem, uint32_t&
       tc5::mbar_wait(mbar, mphase);
       mphase ^= 1u;
     }
-    if (LN) __syncthreads();                             // the normalised rows of all warps
+    if (LN && !a_ready) __syncthreads();                 // the normalised rows of all warps
+    a_ready = astat;
     XN_FINE(g);                                          // 2: operands landed
     float acc[2][NF][4];
 #pragma unroll
@@ -248,22 +267,33 @@ __device__ __forceinline__ void gemm_phase(const GemmP& g, char* smem, uint32_t&
     }
     __syncthreads();                                     // every warp is done with the operands: they become the reduction tiles
     XN_FINE(g);                                          // 3: MMAs done
-    {
-      float* rq = red + (size_t)warp * kBM * PITCH;
+    // eight partial tiles -> four (warps 4-7 hand theirs to warps 0-3 in fragment layout) -> summed per output below
+    auto frag_io = [&](float* rq, bool add) {
 #pragma unroll
       for (int mb = 0; mb < 2; ++mb)
 #pragma unroll
         for (int nf = 0; nf < NF; ++nf) {
           const int row = mb * 16 + (lane >> 2), col = nf * 8 + (lane & 3) * 2;
-          *reinterpret_cast<float2*>(rq + row * PITCH + col) = make_float2(acc[mb][nf][0], acc[mb][nf][1]);
-          *reinterpret_cast<float2*>(rq + (row + 8) * PITCH + col) = make_float2(acc[mb][nf][2], acc[mb][nf][3]);
+          float2* p0 = reinterpret_cast<float2*>(rq + row * PITCH + col);
+          float2* p1 = reinterpret_cast<float2*>(rq + (row + 8) * PITCH + col);
+          if (add) {
+            const float2 u0 = *p0, u1 = *p1;
+            acc[mb][nf][0] += u0.x; acc[mb][nf][1] += u0.y; acc[mb][nf][2] += u1.x; acc[mb][nf][3] += u1.y;
+          }
+          if (!add || warp < 4) {
+            *p0 = make_float2(acc[mb][nf][0], acc[mb][nf][1]);
+            *p1 = make_float2(acc[mb][nf][2], acc[mb][nf][3]);
+          }
         }
-    }
+    };
+    if (warp >= 4) frag_io(red + (size_t)(warp - 4) * kBM * PITCH, false);
+    __syncthreads();
+    if (warp < 4) frag_io(red + (size_t)warp * kBM * PITCH, true);          // same lanes read and rewrite the same words
     __syncthreads();
     auto sum8 = [&](int row, int c4) {
       float4 v = *reinterpret_cast<const float4*>(red + row * PITCH + c4 * 4);
 #pragma unroll
-      for (int q = 1; q < 8; ++q) {
+      for (int q = 1; q < 4; ++q) {
         const float4 u = *reinterpret_cast<const float4*>(red + (size_t)q * kBM * PITCH + row * PITCH + c4 * 4);
         v.x += u.x; v.y += u.y; v.z += u.z; v.w += u.w;
       }
@@ -278,12 +308,12 @@ __device__ __forceinline__ void gemm_phase(const GemmP& g, char* smem, uint32_t&
         const int row = idx / C4, c4 = idx % C4;
         __stcg(reinterpret_cast<float4*>(my + row * BN + c4 * 4), sum8(row, c4));
       }
-      __threadfence();
       __syncthreads();
       if (tid == 0) {
-        const unsigned old = atomicAdd(g.cnt + tile, 1u);
+        unsigned old;
+        asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], %2;" : "=r"(old) : "l"(g.cnt + tile), "r"(1u) : "memory");
         s_last = old == (unsigned)(S - 1);
-        if (s_last) { g.cnt[tile] = 0u; __threadfence(); }
+        if (s_last) g.cnt[tile] = 0u;
       }
       __syncthreads();
       finish = s_last != 0;
@@ -312,7 +342,7 @@ __device__ __forceinline__ void gemm_phase(const GemmP& g, char* smem, uint32_t&
             if (g.Cb) {
               uint2 u;
               u.x = pack2<T>(v.x, v.y); u.y = pack2<T>(v.z, v.w);
-              *reinterpret_cast<uint2*>(reinterpret_cast<T*>(g.Cb) + (long)grow * g.ldcb + col) = u;
+              *reinterpret_cast<uint2*>(reinterpret_cast<T*>(g.Cb) + ((long)(col >> 9) * m32 + grow) * kPadK + (col & 511)) = u;
             }
           }
         } else {
@@ -332,6 +362,7 @@ __device__ __forceinline__ void gemm_phase(const GemmP& g, char* smem, uint32_t&
     XN_FINE(g);                                          // 4: epilogue done
   }
 }
+
 
 // ---- fused log-softmax / top-k over the vocabulary (K6): every 64-column tile of the vocabulary projection leaves,
 // per row, its maximum, sum of exp(x - max) and its best k (value, index) candidates; one warp per row then merges the
@@ -449,79 +480,373 @@ __device__ __forceinline__ void topk_merge_phase(const TopkParts& parts, int ntn
   }
 }
 
+// ---- dynamic expansion of one row with the history rows STAGED in shared memory by bulk copies (np <= 20 positions,
+// 16 expansion vectors, d = 512).  Same mathematics as dyn_exp_row (decode_rows.cuh), reorganised so that every round of
+// dependent L2 reads becomes one wave of 2 KB bulk copies: wave 1 = cond c_i and key K_j rows (the 2p+1 new dot products
+// then run from shared memory; q_e.K_p runs from global meanwhile), wave 2 = class-A rows over the keys (lands during the
+// scalar phase), wave 3 = class-B rows over the cond rows once their contribution is taken.
+constexpr int kDxMaxPos = 20, kDxRowB = 2048;
+constexpr int kDxScal = 13312;                                   // bytes reserved for the scalar arrays (3036 floats at P = 20)
+constexpr int kDxCs = kDxScal, kDxXs = kDxScal + kDxMaxPos * kDxRowB;
+static_assert(kDxXs + kDxMaxPos * kDxRowB <= kMbarOff, "staged dynamic expansion must fit under the mbarrier");
+
+template <typename T>
+__device__ __forceinline__ void dyn_exp_row_staged(const DecState& s, int layer, int p, const float* __restrict__ qexp,
+                                                   const float* __restrict__ bexp, const int* row_len, const float* x_in,
+                                                   long ldxi, float* x_out, long ldxo, const float* __restrict__ ln_g,
+                                                   const float* __restrict__ ln_b, T* ln_out, long ldn, int r, char* smem,
+                                                   uint32_t& mphase, uint32_t& mphase2, unsigned long long* fine = nullptr,
+                                                   int* fmark = nullptr) {
+  constexpr int d = 512, n_exp = 16;
+#ifdef XN_MEGA_FINE
+  auto stamp = [&]() { if (fine && blockIdx.x == 0 && threadIdx.x == 0 && *fmark < 124) fine[(*fmark)++] = gtimer(); };
+#else
+  auto stamp = []() {};
+#endif
+  stamp();
+  float* sm = reinterpret_cast<float*>(smem);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int P = s.P, np = p + 1;
+  // two mbarriers: wave 3 is issued while wave 2 may still be in flight
+  const uint32_t mbar = smem_u32(smem + kMbarOff), mbar2 = mbar + 8;
+  auto ln_tail = [&](float v0, float v1, float* red) {       // columns tid and tid + 256
+    float v[2] = {v0, v1};
+    float mean, rstd;
+    block_ln_stats<2>(v, d, red, mean, rstd);
+    ln_out[(long)r * ldn + tid] = from_f32<T>((v0 - mean) * rstd * ln_g[tid] + ln_b[tid]);
+    ln_out[(long)r * ldn + tid + 256] = from_f32<T>((v1 - mean) * rstd * ln_g[tid + 256] + ln_b[tid + 256]);
+  };
+  if (row_len && p >= row_len[r]) {            // padded position: the block contributes 0 (all-zero mask rows)
+    for (int c = tid; c < d; c += kMegaThreads) x_out[(long)r * ldxo + c] = x_in[(long)r * ldxi + c];
+    ln_tail(x_in[(long)r * ldxi + tid], x_in[(long)r * ldxi + tid + 256], sm);
+    return;
+  }
+  const int P4 = (P + 3) & ~3, E4 = 16;
+  int* slot = reinterpret_cast<int*>(sm);      // [P4]
+  float* ck_row = sm + P4;                     // [P4]  c_p . K_j
+  float* ck_col = ck_row + P4;                 // [P4]  c_i . K_p
+  float* qkp = ck_col + P4;                    // [E4]
+  float* af = qkp + E4;                        // [P][n_exp] forward weights of the new row-block (A), key-major
+  float* bf = af + P4 * E4;
+  float* ab = bf + P4 * E4;                    // [P][n_exp] backward weights (A)
+  float* bb = ab + P4 * E4;
+  float* wA = bb + P4 * E4;                    // [P4]
+  float* wB = wA + P4;
+  float* tA = wB + P4;
+  float* tB = tA + P4;
+  float* sA = tB + P4;                         // [E4]
+  float* sB = sA + E4;
+  float* red = sB + E4;                        // [32]
+  float* part = red + 32;                      // [2][P][P]; first the history q_e.K_j table, later the mix scratch
+  const float* Cs = reinterpret_cast<const float*>(smem + kDxCs);
+  const float* Xs = reinterpret_cast<const float*>(smem + kDxXs);
+
+  for (int i = tid; i < np; i += kMegaThreads) slot[i] = (i == p || !s.anc) ? r : s.anc[(long)r * P + i];
+  __syncthreads();
+  auto crow = [&](int i) { return s.cache + (((long)layer * P + i) * s.R + slot[i]) * s.cw; };
+  const float* cp = crow(p);
+  stamp();                                                       // slots known
+  // ---- wave 1: cond rows -> Cs, key rows -> Xs
+  if (warp == 0) {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    if (lane == 0) mbar_expect(mbar, (uint32_t)(2 * np * kDxRowB));
+    __syncwarp();
+    for (int i = lane; i < 2 * np; i += 32) {
+      const int j = i >> 1, which = i & 1;
+      bulk_g2s(smem_u32(smem + (which ? kDxXs : kDxCs) + j * kDxRowB), crow(j) + (which ? d : 0), kDxRowB, mbar);
+    }
+  }
+  // history q_e.K_j of this row's ancestry (one 64-byte read per position), selector / residual of the output
+  float4* qkh = reinterpret_cast<float4*>(part);                 // [np][16]
+  if (tid < np * 4 && (tid >> 2) != p)
+    qkh[tid] = *reinterpret_cast<const float4*>(s.qk + (((long)layer * P + (tid >> 2)) * s.R + slot[tid >> 2]) * n_exp + (tid & 3) * 4);
+  // q_e . K_p from global while the rows land: warp w takes e = w and w + 8
+  {
+    const float* Kp = cp + d;
+    float4 k4[4], q0[4], q1[4];
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      const int c = it * 128 + lane * 4;
+      k4[it] = *reinterpret_cast<const float4*>(Kp + c);
+      q0[it] = *reinterpret_cast<const float4*>(qexp + (long)warp * d + c);
+      q1[it] = *reinterpret_cast<const float4*>(qexp + (long)(warp + 8) * d + c);
+    }
+    float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      a0 = fmaf(q0[it].x, k4[it].x, a0); a0 = fmaf(q0[it].y, k4[it].y, a0); a0 = fmaf(q0[it].z, k4[it].z, a0); a0 = fmaf(q0[it].w, k4[it].w, a0);
+      a1 = fmaf(q1[it].x, k4[it].x, a1); a1 = fmaf(q1[it].y, k4[it].y, a1); a1 = fmaf(q1[it].z, k4[it].z, a1); a1 = fmaf(q1[it].w, k4[it].w, a1);
+    }
+    a0 = warp_sum(a0);
+    a1 = warp_sum(a1);
+    if (lane == 0) { qkp[warp] = a0; qkp[warp + 8] = a1; }
+  }
+  stamp();                                                       // wave 1 issued, q_e.K_p done
+  tc5::mbar_wait(mbar, mphase);
+  mphase ^= 1u;
+  stamp();                                                       // wave 1 landed
+  // ---- phase A from shared memory: c_p . K_j (j <= p) and c_i . K_p (i < p), one warp per dot product
+  for (int t = warp; t < np + p; t += kMegaThreads / 32) {
+    const float* u = t < np ? Cs + p * d : Cs + (t - np) * d;
+    const float* v = t < np ? Xs + t * d : Xs + p * d;
+    float a = 0.f;
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      const float4 x4 = *reinterpret_cast<const float4*>(u + it * 128 + lane * 4);
+      const float4 y4 = *reinterpret_cast<const float4*>(v + it * 128 + lane * 4);
+      a = fmaf(x4.x, y4.x, a); a = fmaf(x4.y, y4.y, a); a = fmaf(x4.z, y4.z, a); a = fmaf(x4.w, y4.w, a);
+    }
+    a = warp_sum(a);
+    if (lane == 0) { if (t < np) ck_row[t] = a; else ck_col[t - np] = a; }
+  }
+  __syncthreads();
+  // ---- wave 2: class-A rows over the keys (every warp is past its last key read)
+  if (warp == 0) {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    if (lane == 0) mbar_expect(mbar2, (uint32_t)(np * kDxRowB));
+    __syncwarp();
+    for (int j = lane; j < np; j += 32) bulk_g2s(smem_u32(smem + kDxXs + j * kDxRowB), crow(j) + 2 * d, kDxRowB, mbar2);
+  }
+  if (tid == 0) ck_col[p] = ck_row[p];
+  float* qk_out = s.qk + (((long)layer * P + p) * s.R + r) * n_exp;
+  if (tid < n_exp) qk_out[tid] = qkp[tid];
+  __syncthreads();
+
+  stamp();                                                       // phase A done
+  // ---- phase B: scalar work
+  const float sq = sqrtf((float)d);
+  float* fw_out = s.fw + (((long)layer * P + p) * s.R + r) * (2L * n_exp * P);
+  {
+    const float* qkh_f = reinterpret_cast<const float*>(qkh);
+    for (int e = warp; e < n_exp; e += kMegaThreads / 32) {      // forward weights of the new row-block: one warp per e (np <= 32)
+      const int j = lane;
+      float z = 0.f, sa = 0.f, sb = 0.f;
+      if (j < np) {
+        const float qk = (j == p) ? qkp[e] : qkh_f[j * 16 + e];
+        z = (qk + ck_row[j]) / sq;
+        sa = fmaxf(z, 0.f);
+        sb = fmaxf(-z, 0.f);
+      }
+      sa = warp_sum(sa) + kExpEps;
+      sb = warp_sum(sb) + kExpEps;
+      if (j < np) {
+        const float a = fmaxf(z, 0.f) / sa, b = fmaxf(-z, 0.f) / sb;
+        af[j * n_exp + e] = a; bf[j * n_exp + e] = b;
+        fw_out[j * n_exp + e] = a; fw_out[(long)n_exp * P + j * n_exp + e] = b;
+      }
+    }
+  }
+  float la = 0.f, lb = 0.f;
+  for (int i = tid; i < np * n_exp; i += kMegaThreads) {         // backward weights for output position p (column p of z)
+    const int pi = i / n_exp, e = i % n_exp;
+    const float z = (qkp[e] + ck_col[pi]) / sq;
+    const float a = fmaxf(z, 0.f), b = fmaxf(-z, 0.f);
+    ab[i] = a; bb[i] = b;
+    la += a; lb += b;
+  }
+  const float ta = block_sum(la, red) + kExpEps;
+  const float tb = block_sum(lb, red) + kExpEps;
+  __syncthreads();
+  for (int i = tid; i < np * n_exp; i += kMegaThreads) { ab[i] = ab[i] / ta; bb[i] = bb[i] / tb; }
+  __syncthreads();
+  // wA[j] = sum_{i>=j} sum_e ab[(i,e)] * Af_i[e][j]: one task per (which, i, j<=i); a thread's (<= 4) tasks load first
+  {
+    constexpr int TPT = 2;                                       // 2 * 20 * 20 = 800 <= 2 batches x 2 x 256
+#pragma unroll 1
+    for (int b0 = 0; b0 < 2; ++b0) {
+      float4 f4[TPT][4];
+      int ti[TPT], tj[TPT], tw[TPT];
+#pragma unroll
+      for (int u = 0; u < TPT; ++u) {
+        const int t = tid + (b0 * TPT + u) * kMegaThreads;
+        const int which = t / (np * np), rem = t % (np * np), i = rem / np, j = rem % np;
+        const bool ok = t < 2 * np * np && j <= i;
+        ti[u] = ok ? i : -1; tj[u] = j; tw[u] = which;
+        if (ok) {
+          const float* f = (i == p) ? (which ? bf : af)
+                                    : s.fw + (((long)layer * P + i) * s.R + slot[i]) * (2L * n_exp * P) + (which ? (long)n_exp * P : 0);
+          const float4* fj = reinterpret_cast<const float4*>(f + j * n_exp);
+          f4[u][0] = fj[0]; f4[u][1] = fj[1]; f4[u][2] = fj[2]; f4[u][3] = fj[3];
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < TPT; ++u) {
+        if (ti[u] >= 0) {
+          const float* wi = (tw[u] ? bb : ab) + ti[u] * n_exp;
+          float acc = 0.f;
+#pragma unroll
+          for (int e4 = 0; e4 < 4; ++e4) {
+            acc = fmaf(wi[e4 * 4], f4[u][e4].x, acc); acc = fmaf(wi[e4 * 4 + 1], f4[u][e4].y, acc);
+            acc = fmaf(wi[e4 * 4 + 2], f4[u][e4].z, acc); acc = fmaf(wi[e4 * 4 + 3], f4[u][e4].w, acc);
+          }
+          part[(tw[u] * P + ti[u]) * P + tj[u]] = acc;
+        }
+      }
+    }
+  }
+  __syncthreads();
+  for (int t = tid; t < 2 * np; t += kMegaThreads) {
+    const int j = t >> 1, which = t & 1;
+    float acc = 0.f;
+    for (int i = j; i < np; ++i) acc += part[(which * P + i) * P + j];
+    (which ? wB : wA)[j] = acc;
+  }
+  for (int t = tid; t < 2 * np; t += kMegaThreads) {             // tA[i] = sum_e ab[(i,e)]
+    const int i = t >> 1, which = t & 1;
+    const float* wsrc = which ? bb : ab;
+    float acc = 0.f;
+#pragma unroll
+    for (int e = 0; e < n_exp; ++e) acc += wsrc[i * n_exp + e];
+    (which ? tB : tA)[i] = acc;
+  }
+  for (int t = tid; t < 2 * n_exp; t += kMegaThreads) {          // sA[e] = sum_i ab[(i,e)]
+    const int e = t >> 1, which = t & 1;
+    const float* wsrc = which ? bb : ab;
+    float acc = 0.f;
+    for (int i = 0; i < np; ++i) acc += wsrc[i * n_exp + e];
+    (which ? sB : sA)[e] = acc;
+  }
+  __syncthreads();
+
+  stamp();                                                       // phase B done
+  // ---- phase C: the d-wide mixes.  Thread t owns columns 4 (t % 128) .. +3 and one half of the history (t / 128)
+  const int c4 = (tid & 127) * 4, half = tid >> 7;
+  const int j0 = half ? (np + 1) / 2 : 0, j1 = half ? np : (np + 1) / 2;
+  float4 sl4 = make_float4(0.f, 0.f, 0.f, 0.f), xi = sl4;
+  if (!half) {                                                   // selector and residual: in flight during the mixes
+    sl4 = *reinterpret_cast<const float4*>(cp + 4 * d + c4);
+    xi = *reinterpret_cast<const float4*>(x_in + (long)r * ldxi + c4);
+  }
+  float4 oa = make_float4(0.f, 0.f, 0.f, 0.f), ob = oa;
+  for (int j = j0; j < j1; ++j) {                                // cond rows
+    const float4 cj = *reinterpret_cast<const float4*>(Cs + j * d + c4);
+    const float ta_ = tA[j], tb_ = tB[j];
+    oa.x = fmaf(ta_, cj.x, oa.x); oa.y = fmaf(ta_, cj.y, oa.y); oa.z = fmaf(ta_, cj.z, oa.z); oa.w = fmaf(ta_, cj.w, oa.w);
+    ob.x = fmaf(tb_, cj.x, ob.x); ob.y = fmaf(tb_, cj.y, ob.y); ob.z = fmaf(tb_, cj.z, ob.z); ob.w = fmaf(tb_, cj.w, ob.w);
+  }
+  __syncthreads();                                               // the cond rows are done with
+  if (warp == 0) {                                               // ---- wave 3: class-B rows over the cond rows
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    if (lane == 0) mbar_expect(mbar, (uint32_t)(np * kDxRowB));
+    __syncwarp();
+    for (int j = lane; j < np; j += 32) bulk_g2s(smem_u32(smem + kDxCs + j * kDxRowB), crow(j) + 3 * d, kDxRowB, mbar);
+  }
+  if (half) {                                                    // expansion-bias term (weights: L2 / L1), all loads first
+#pragma unroll 1
+    for (int e0 = 0; e0 < 16; e0 += 8) {
+      float4 be[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) be[e] = *reinterpret_cast<const float4*>(bexp + (long)(e0 + e) * d + c4);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float wa = sA[e0 + e], wb = sB[e0 + e];
+        oa.x = fmaf(wa, be[e].x, oa.x); oa.y = fmaf(wa, be[e].y, oa.y); oa.z = fmaf(wa, be[e].z, oa.z); oa.w = fmaf(wa, be[e].w, oa.w);
+        ob.x = fmaf(wb, be[e].x, ob.x); ob.y = fmaf(wb, be[e].y, ob.y); ob.z = fmaf(wb, be[e].z, ob.z); ob.w = fmaf(wb, be[e].w, ob.w);
+      }
+    }
+  }
+  tc5::mbar_wait(mbar2, mphase2);                                // wave 2 (class-A rows)
+  mphase2 ^= 1u;
+  for (int j = j0; j < j1; ++j) {
+    const float4 aj = *reinterpret_cast<const float4*>(Xs + j * d + c4);
+    const float wa = wA[j];
+    oa.x = fmaf(wa, aj.x, oa.x); oa.y = fmaf(wa, aj.y, oa.y); oa.z = fmaf(wa, aj.z, oa.z); oa.w = fmaf(wa, aj.w, oa.w);
+  }
+  tc5::mbar_wait(mbar, mphase);                                  // wave 3 (class-B rows)
+  mphase ^= 1u;
+  for (int j = j0; j < j1; ++j) {
+    const float4 bj = *reinterpret_cast<const float4*>(Cs + j * d + c4);
+    const float wb = wB[j];
+    ob.x = fmaf(wb, bj.x, ob.x); ob.y = fmaf(wb, bj.y, ob.y); ob.z = fmaf(wb, bj.z, ob.z); ob.w = fmaf(wb, bj.w, ob.w);
+  }
+  stamp();                                                       // mixes done
+  float4* mix = reinterpret_cast<float4*>(part);                 // [2 (a|b)][128] partial sums of the upper half
+  if (half) {
+    mix[tid & 127] = oa;
+    mix[128 + (tid & 127)] = ob;
+  }
+  __syncthreads();
+  float* xo_s = reinterpret_cast<float*>(mix + 256);             // the row, for the LayerNorm tail's column assignment
+  if (!half) {
+    const float4 ua = mix[tid], ub = mix[128 + tid];
+    oa.x += ua.x; oa.y += ua.y; oa.z += ua.z; oa.w += ua.w;
+    ob.x += ub.x; ob.y += ub.y; ob.z += ub.z; ob.w += ub.w;
+    const float s0 = sigmoidf_(sl4.x), s1 = sigmoidf_(sl4.y), s2 = sigmoidf_(sl4.z), s3 = sigmoidf_(sl4.w);
+    float4 xo;
+    xo.x = xi.x + (s0 * oa.x + (1.0f - s0) * ob.x);
+    xo.y = xi.y + (s1 * oa.y + (1.0f - s1) * ob.y);
+    xo.z = xi.z + (s2 * oa.z + (1.0f - s2) * ob.z);
+    xo.w = xi.w + (s3 * oa.w + (1.0f - s3) * ob.w);
+    *reinterpret_cast<float4*>(x_out + (long)r * ldxo + c4) = xo;
+    *reinterpret_cast<float4*>(xo_s + c4) = xo;
+  }
+  __syncthreads();
+  ln_tail(xo_s[tid], xo_s[tid + 256], red);
+  stamp();                                                       // row stored, norm_2 written
+}
+
 template <typename T>
 __global__ void __launch_bounds__(kMegaThreads, 2) dec_step_mega_kernel(const __grid_constant__ MegaArgs a) {
   extern __shared__ __align__(128) char smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int d = 512, R = a.R, nd = a.n_layers, p = a.p;
   const long ldc = (long)d * nd;
+  const long m32 = (long)((R + kBM - 1) / kBM) * kBM;        // rows of a packed 16-bit activation slab
   T* xn = reinterpret_cast<T*>(a.xn);
   T* att = reinterpret_cast<T*>(a.att);
   T* hid = reinterpret_cast<T*>(a.hid);
   T* ycat16 = reinterpret_cast<T*>(a.ycat16);
   const T* kv = reinterpret_cast<const T*>(a.kv);
   int mark = 1, fmark = 64;
-  if (a.dbg && blockIdx.x == 0 && tid == 0) a.dbg[0] = gtimer();
+  if (a.dbg && blockIdx.x == 0 && tid == 0) { a.dbg[0] = gtimer(); a.dbg[124] = (unsigned long long)clock64(); }
   GridBar bar;
   bar.init(a.bar);
-  uint32_t mphase = 0u;                          // parity of the operand mbarrier's next completion
+  uint32_t mphase = 0u, mphase2 = 0u;            // parity of the mbarriers' next completion
   if (tid == 0) {
     tc5::mbar_init(smem_u32(smem + kMbarOff), 1);
+    tc5::mbar_init(smem_u32(smem + kMbarOff) + 8, 1);
     tc5::fence_mbar_init();
   }
   __syncthreads();
 
-  // ---- phase 0: x0 = E[tok] sqrt(d) + P[p]   (layers.py:16-17); one warp per row
-  {
-    const float sc = sqrtf((float)d);
-    for (int r = blockIdx.x * 8 + warp; r < R; r += gridDim.x * 8) {
-      const long tok = a.tok64 ? (long)a.tok64[r * a.tok_stride + p] : (long)a.tok32[r * a.tok_stride + p];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int c = j * 128 + lane * 4;
-        const float4 e4 = *reinterpret_cast<const float4*>(a.emb + tok * d + c);
-        const float4 p4 = *reinterpret_cast<const float4*>(a.pos + (long)p * d + c);
-        *reinterpret_cast<float4*>(a.x0 + (long)r * d + c) =
-            make_float4(e4.x * sc + p4.x, e4.y * sc + p4.y, e4.z * sc + p4.z, e4.w * sc + p4.w);
-      }
-    }
-  }
-  bar.sync(a.dbg, &mark);
-
-  for (int l = 0; l < nd; ++l) {
+  // Every GEMM phase is its own inlined, specialised copy of gemm_phase (null pointers and constant shapes folded away).
+  // One shared copy per tile variant driven by a run-time descriptor was measured: 17 us slower per position, although the
+  // kernel's code is fetched cold at every position (ncu: 18 % of the non-barrier warp samples are "no instruction").
+#define XN_GEMM_INIT(g)                                                                                   \
+  GemmP g{};                                                                                              \
+  g.dbg_mode = a.dbg_mode; g.fine = (a.dbg && l == 0 && !(a.dbg_mode & 16)) ? a.dbg : nullptr; g.fmark = &fmark; \
+  g.M = R; g.N = d; g.K = d;
+  int l = 0;
+  for (; l < nd; ++l) {
     const MegaLayer& W = a.L[l];
     const float* xin = l == 0 ? a.x0 : a.ycat + (size_t)(l - 1) * d;
     const long ldi = l == 0 ? d : ldc;
     float* xout = a.ycat + (size_t)l * d;
-    float* crow = a.s.cache + (((size_t)l * a.s.P + p) * R) * a.s.cw;
-    // P1: [cond | key | A | B | selector] = LN1(x) W5^T + b    (layers.py:152-170, 226-229)
-    {
-      GemmP g{};
-    g.dbg_mode = a.dbg_mode; g.fine = a.dbg; g.fmark = &fmark;
-      g.dbg_mode = a.dbg_mode; g.fine = (a.dbg && l == 0) ? a.dbg : nullptr; g.fmark = &fmark;
+    {                                            // [cond | key | A | B | selector] = LN1(x) W5^T + b    (layers.py:152-170, 226-229)
+      XN_GEMM_INIT(g)
       g.A32 = xin; g.lda32 = ldi; g.ln_g = W.n1g; g.ln_b = W.n1b;
-      g.W = W.w_dyn5; g.bias = W.b_dyn5; g.Cf = crow; g.ldcf = a.s.cw; g.M = R; g.N = 5 * d; g.K = d;
-      gemm_phase<T, 64, true>(g, smem, mphase);
+      if (l == 0) {                              // the embedding is computed in the fill (no separate phase, no barrier)
+        g.emb = a.emb; g.pos_row = a.pos + (long)p * d; g.tok64 = a.tok64; g.tok32 = a.tok32; g.tok_stride = a.tok_stride;
+        g.tok_p = p; g.x0_out = a.x0;
+      }
+      g.W = W.w_dyn5; g.bias = W.b_dyn5; g.Cf = a.s.cache + (((size_t)l * a.s.P + p) * R) * a.s.cw; g.ldcf = a.s.cw; g.N = 5 * d;
+      gemm_phase_impl<T, 64, true>(g, smem, mphase);
     }
     bar.sync(a.dbg, &mark);
-    // P2: incremental dynamic expansion of position p + residual, then norm_2 -> xn
+    // incremental dynamic expansion of position p + residual, then norm_2 -> xn
     for (int r = blockIdx.x; r < R; r += gridDim.x) {
-      dyn_exp_row<T>(a.s, l, p, W.qexp, W.bexp, a.n_exp, a.row_len, xin, ldi, xout, ldc, d, W.n2g, W.n2b, xn, d, r,
-                     reinterpret_cast<float*>(smem));
+      dyn_exp_row_staged<T>(a.s, l, p, W.qexp, W.bexp, a.row_len, xin, ldi, xout, ldc, W.n2g, W.n2b, xn, kPadK, r, smem, mphase,
+                            mphase2, (a.dbg_mode & 16) && l == 0 ? a.dbg : nullptr, &fmark);
       __syncthreads();
     }
     bar.sync(a.dbg, &mark);
-    // P3: q = xn Wq^T + b
-    {
-      GemmP g{};
-    g.dbg_mode = a.dbg_mode; g.fine = a.dbg; g.fmark = &fmark;
-      g.dbg_mode = a.dbg_mode; g.fine = (a.dbg && l == 0) ? a.dbg : nullptr; g.fmark = &fmark;
-      g.A16 = xn; g.lda = d; g.W = W.w_wq; g.bias = W.b_wq; g.Cf = a.q; g.ldcf = d; g.M = R; g.N = d; g.K = d;
-      gemm_phase<T, 32, false>(g, smem, mphase);
+    {                                            // q = xn Wq^T + b
+      XN_GEMM_INIT(g)
+      g.A16 = xn; g.W = W.w_wq; g.bias = W.b_wq; g.Cf = a.q; g.ldcf = d;
+      gemm_phase_impl<T, 32, false>(g, smem, mphase);
     }
     bar.sync(a.dbg, &mark);
-    // P4: cross attention, one item per (image, head, group of <= 4 beam rows)   (layers.py:266-295)
-    {
+    {                                            // cross attention, one item per (image, head, group of <= 4 beam rows)   (layers.py:266-295)
       const int rpi = a.rows_per_image, n_img = R / rpi, ngrp = (rpi + 3) / 4, heads = a.heads;
       const int k_off = l * 2 * d, v_off = l * 2 * d + d;
       for (int it = blockIdx.x; it < n_img * heads * ngrp; it += gridDim.x) {
@@ -529,83 +854,94 @@ __global__ void __launch_bounds__(kMegaThreads, 2) dec_step_mega_kernel(const __
         const int row0 = b * rpi + gq * 4, cnt = min(4, rpi - gq * 4);
         float* smf = reinterpret_cast<float*>(smem);
         switch (cnt) {
-          case 1: cross_attn16_item<T, 1>(a.q, d, kv, a.ldkv, k_off, v_off, att, d, a.n_keys, a.n_valid, a.row_len, p, b, hh, row0, smf); break;
-          case 2: cross_attn16_item<T, 2>(a.q, d, kv, a.ldkv, k_off, v_off, att, d, a.n_keys, a.n_valid, a.row_len, p, b, hh, row0, smf); break;
-          case 3: cross_attn16_item<T, 3>(a.q, d, kv, a.ldkv, k_off, v_off, att, d, a.n_keys, a.n_valid, a.row_len, p, b, hh, row0, smf); break;
-          default: cross_attn16_item<T, 4>(a.q, d, kv, a.ldkv, k_off, v_off, att, d, a.n_keys, a.n_valid, a.row_len, p, b, hh, row0, smf); break;
+          case 1: cross_attn16_item<T, 1>(a.q, d, kv, a.ldkv, k_off, v_off, att, kPadK, a.n_keys, a.n_valid, a.row_len, p, b, hh, row0, smf); break;
+          case 2: cross_attn16_item<T, 2>(a.q, d, kv, a.ldkv, k_off, v_off, att, kPadK, a.n_keys, a.n_valid, a.row_len, p, b, hh, row0, smf); break;
+          case 3: cross_attn16_item<T, 3>(a.q, d, kv, a.ldkv, k_off, v_off, att, kPadK, a.n_keys, a.n_valid, a.row_len, p, b, hh, row0, smf); break;
+          default: cross_attn16_item<T, 4>(a.q, d, kv, a.ldkv, k_off, v_off, att, kPadK, a.n_keys, a.n_valid, a.row_len, p, b, hh, row0, smf); break;
         }
         __syncthreads();
       }
     }
     bar.sync(a.dbg, &mark);
-    // P5: x = x + att Wo^T + b
-    {
-      GemmP g{};
-    g.dbg_mode = a.dbg_mode; g.fine = a.dbg; g.fmark = &fmark;
-      g.dbg_mode = a.dbg_mode; g.fine = (a.dbg && l == 0) ? a.dbg : nullptr; g.fmark = &fmark;
-      g.A16 = att; g.lda = d; g.W = W.w_wo; g.bias = W.b_wo; g.res = xout; g.ldr = ldc; g.Cf = xout; g.ldcf = ldc;
-      g.M = R; g.N = d; g.K = d;
-      gemm_phase<T, 32, false>(g, smem, mphase);
+    {                                            // x = x + att Wo^T + b
+      XN_GEMM_INIT(g)
+      g.A16 = att; g.W = W.w_wo; g.bias = W.b_wo; g.res = xout; g.ldr = ldc; g.Cf = xout; g.ldcf = ldc;
+      gemm_phase_impl<T, 32, false>(g, smem, mphase);
     }
     bar.sync(a.dbg, &mark);
-    // P6: hid = relu(LN3(x) W1^T + b)
-    {
-      GemmP g{};
-    g.dbg_mode = a.dbg_mode; g.fine = a.dbg; g.fmark = &fmark;
-      g.dbg_mode = a.dbg_mode; g.fine = (a.dbg && l == 0) ? a.dbg : nullptr; g.fmark = &fmark;
+    {                                            // hid = relu(LN3(x) W1^T + b)
+      XN_GEMM_INIT(g)
       g.A32 = xout; g.lda32 = ldc; g.ln_g = W.n3g; g.ln_b = W.n3b;
-      g.W = W.w_ff1; g.bias = W.b_ff1; g.Cb = hid; g.ldcb = a.ff; g.M = R; g.N = a.ff; g.K = d; g.act = 2;
-      gemm_phase<T, 64, true>(g, smem, mphase);
+      g.W = W.w_ff1; g.bias = W.b_ff1; g.Cb = hid; g.N = a.ff; g.act = 2;
+      gemm_phase_impl<T, 64, true>(g, smem, mphase);
     }
     bar.sync(a.dbg, &mark);
-    // P7: x = x + hid W2^T + b   (also kept in 16 bits: operand of the reduce group)
-    {
-      GemmP g{};
-    g.dbg_mode = a.dbg_mode; g.fine = a.dbg; g.fmark = &fmark;
-      g.dbg_mode = a.dbg_mode; g.fine = (a.dbg && l == 0) ? a.dbg : nullptr; g.fmark = &fmark;
-      g.A16 = hid; g.lda = a.ff; g.W = W.w_ff2; g.bias = W.b_ff2; g.res = xout; g.ldr = ldc; g.Cf = xout; g.ldcf = ldc;
-      g.Cb = ycat16 + (size_t)l * d; g.ldcb = ldc; g.M = R; g.N = d; g.K = a.ff;
+    {                                            // x = x + hid W2^T + b   (also kept in 16 bits: operand of the reduce group)
+      XN_GEMM_INIT(g)
+      g.A16 = hid; g.W = W.w_ff2; g.bias = W.b_ff2; g.res = xout; g.ldr = ldc; g.Cf = xout; g.ldcf = ldc;
+      g.Cb = ycat16 + (size_t)l * m32 * kPadK; g.K = a.ff;
       g.ksplit = a.ksplit_ff2; g.scratch = a.scratch; g.cnt = a.bar + kSplitCntOff;
-      gemm_phase<T, 64, false>(g, smem, mphase);
+      gemm_phase_impl<T, 64, false>(g, smem, mphase);
     }
     bar.sync(a.dbg, &mark);
   }
-  // P8: reduce group: pre = x_last + [y_1 | .. | y_n] Wr^T + b   (End_ExpansionNet_v2.py:196-199)
-  {
-    GemmP g{};
-    g.dbg_mode = a.dbg_mode; g.fine = a.dbg; g.fmark = &fmark;
-    g.A16 = ycat16; g.lda = ldc; g.W = a.w_reduce; g.bias = a.b_reduce; g.res = a.ycat + (size_t)(nd - 1) * d; g.ldr = ldc;
-    g.Cf = a.pre; g.ldcf = d; g.M = R; g.N = d; g.K = d * nd;
+  l = nd - 1;
+  {                                              // reduce group: pre = x_last + [y_1 | .. | y_n] Wr^T + b   (End_ExpansionNet_v2.py:196-199)
+    XN_GEMM_INIT(g)
+    g.A16 = ycat16; g.W = a.w_reduce; g.bias = a.b_reduce; g.res = a.ycat + (size_t)(nd - 1) * d; g.ldr = ldc;
+    g.Cf = a.pre; g.ldcf = d; g.K = d * nd;
     g.ksplit = a.ksplit_red; g.scratch = a.scratch; g.cnt = a.bar + kSplitCntOff;
-    gemm_phase<T, 64, false>(g, smem, mphase);
+    gemm_phase_impl<T, 64, false>(g, smem, mphase);
   }
   bar.sync(a.dbg, &mark);
-  // P9: logits = LN(pre) Wv^T + b    (End_ExpansionNet_v2.py:200-204)
-  {
-    GemmP g{};
-    g.dbg_mode = a.dbg_mode; g.fine = a.dbg; g.fmark = &fmark;
+  {                                              // logits = LN(pre) Wv^T + b    (End_ExpansionNet_v2.py:200-204)
+    XN_GEMM_INIT(g)
     g.A32 = a.pre; g.lda32 = d; g.ln_g = a.ng; g.ln_b = a.nb;
-    g.W = a.w_vocab; g.bias = a.b_vocab; g.M = R; g.N = a.vocab; g.K = d;
+    g.W = a.w_vocab; g.bias = a.b_vocab; g.N = a.vocab;
     if (a.topk > 0) {
-      const int ntn = (a.vocab + 63) / 64;
-      TopkHook<64> hook{TopkParts{reinterpret_cast<float*>(a.parts), (long)R * ntn}, ntn, R, a.vocab, a.topk};
-      gemm_phase<T, 64, true, false>(g, smem, mphase, hook);
+      const int ntn_v = (a.vocab + 63) / 64;
+      TopkHook<64> hook{TopkParts{reinterpret_cast<float*>(a.parts), (long)R * ntn_v}, ntn_v, R, a.vocab, a.topk};
+      gemm_phase_impl<T, 64, true, false, TopkHook<64>>(g, smem, mphase, hook);
       bar.sync(a.dbg, &mark);
-      topk_merge_phase(TopkParts{reinterpret_cast<float*>(a.parts), (long)R * ntn}, ntn, R, a.topk, a.top_val, a.top_idx);
+      topk_merge_phase(TopkParts{reinterpret_cast<float*>(a.parts), (long)R * ntn_v}, ntn_v, R, a.topk, a.top_val, a.top_idx);
     } else {
       g.Cf = a.logits; g.ldcf = a.ldl;
-      gemm_phase<T, 64, true>(g, smem, mphase);
+      gemm_phase_impl<T, 64, true>(g, smem, mphase);
     }
   }
-  if (a.dbg && blockIdx.x == 0 && tid == 0) { a.dbg[mark++] = gtimer(); a.dbg[127] = (unsigned long long)mark; a.dbg[126] = (unsigned long long)fmark; }
+#undef XN_GEMM_INIT
+  if (a.dbg && blockIdx.x == 0 && tid == 0) { a.dbg[mark++] = gtimer(); a.dbg[127] = (unsigned long long)mark; a.dbg[126] = (unsigned long long)fmark; a.dbg[125] = (unsigned long long)clock64(); }
 }
 
+// fp32 (N x K) -> 16-bit slabs [K/512][N][520] (pad columns zero): the layout gemm_phase copies whole tiles from
+template <typename T>
+__global__ void mega_pack_kernel(const float* __restrict__ w, T* __restrict__ out, int N, int K) {
+  const long total = (long)(K / kKI) * N * kPadK;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % kPadK);
+    const long rn = i / kPadK;
+    const int n = (int)(rn % N), sp = (int)(rn / N);
+    out[i] = from_f32<T>(c < kKI ? w[(long)n * K + sp * kKI + c] : 0.f);
+  }
+}
+size_t mega_packed_bytes(int N, int K) { return (size_t)(K / kKI) * N * kPadK * 2; }
+cudaError_t launch_mega_pack_weight(const float* w, void* out, int N, int K, int fp16, cudaStream_t st) {
+  if (K % kKI) return cudaErrorInvalidValue;
+  if (fp16) mega_pack_kernel<f16><<<592, 256, 0, st>>>(w, reinterpret_cast<f16*>(out), N, K);
+  else mega_pack_kernel<bf16><<<592, 256, 0, st>>>(w, reinterpret_cast<bf16*>(out), N, K);
+  return cudaGetLastError();
+}
+// packed 16-bit activations of one decoder position: xn | att | hid (ff/512 slabs) | layer outputs (n_layers slabs)
+size_t mega_act_bytes(int R, int ff, int n_layers) {
+  const size_t m32 = (size_t)((R + kBM - 1) / kBM) * kBM;
+  return (size_t)(2 + ff / kKI + n_layers) * m32 * kPitch;
+}
 size_t mega_scratch_bytes(int R) { return (size_t)((R + kBM - 1) / kBM) * (512 / 64) * 4 * (kBM * 64 * sizeof(float)); }
 size_t mega_parts_bytes(int R, int vocab) { return (size_t)R * ((vocab + 63) / 64) * (2 + 2 * kTopC) * sizeof(float); }
 
 bool mega_supported(const MegaArgs& a) {
   if (a.d != 512 || a.heads * 64 != a.d || a.n_keys > kCaMaxKeys || a.n_layers < 1 || a.n_layers > kMegaMaxLayers) return false;
-  if (a.ff % 128 || a.vocab % 4 || a.s.P > 128 || a.n_exp > 64 || a.rows_per_image < 1 || a.R % a.rows_per_image) return false;
+  if (a.ff % 128 || a.vocab % 4 || a.s.P > kDxMaxPos || a.n_exp != 16 || a.rows_per_image < 1 || a.R % a.rows_per_image) return false;
   if (((a.R + kBM - 1) / kBM) * (a.d / 64) > kMaxSplitTiles && (a.ksplit_ff2 > 1 || a.ksplit_red > 1)) return false;
   if (a.ksplit_ff2 > 4 || a.ksplit_red > 4 || a.ff != kKI * std::max(1, a.ksplit_ff2) || a.d * a.n_layers != kKI * std::max(1, a.ksplit_red)) return false;
   if (a.s.cw != 5 * a.d || (a.ldkv & 7) || (a.vocab + 63) / 64 > 256 || a.topk > kTopC) return false;

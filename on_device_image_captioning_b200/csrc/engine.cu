@@ -35,6 +35,7 @@ struct DevTensor {
 struct LinW {
   const float* w = nullptr;   // (N, K) fp32
   const void* wb = nullptr;   // (N, K) 16-bit copy (bf16 / fp16 modes)
+  const void* wp = nullptr;   // slab-packed 16-bit copy for the persistent decoder kernel (decode_mega.cu)
   const float* b = nullptr;   // (N) or null
   int N = 0, K = 0;
 };
@@ -674,7 +675,7 @@ struct DecBufs {
   int R, P;
   // persistent-kernel path: when topk > 0 the step also leaves log-softmax top-k in topv / topi (topk_done is set by
   // dec_step when it did; otherwise the caller runs the separate log-softmax + top-k kernel on the logits)
-  float* mega_scratch = nullptr;
+  float* mega_scratch = nullptr; void* mega_act = nullptr;
   void* parts = nullptr; int topk = 0; float* topv = nullptr; int* topi = nullptr; bool topk_done = false;
 };
 
@@ -688,7 +689,7 @@ size_t dec_ws_bytes(const xn_config& c, int R, int P, int n_images, bool own_log
   f += (size_t)n_images * c.enc_len * c.n_dec * 2 * d;
   f += (size_t)n_images * c.enc_len * d;          // 16-bit copy of the encoder output
   if (own_logits) f += (size_t)R * c.vocab;
-  return f * 4 + mega_parts_bytes(R, c.vocab) + mega_scratch_bytes(R) + 64 * 256;
+  return f * 4 + mega_parts_bytes(R, c.vocab) + mega_scratch_bytes(R) + mega_act_bytes(R, c.ff, c.n_dec) + 64 * 256;
 }
 
 int dec_alloc(xn_handle* h, DecBufs& D, int R, int P, int n_images) {
@@ -714,6 +715,7 @@ int dec_alloc(xn_handle* h, DecBufs& D, int R, int P, int n_images) {
   D.e16 = h->ws.get<float>(((size_t)n_images * c.enc_len * d + 1) / 2);
   D.parts = h->ws.get<char>(mega_parts_bytes(R, c.vocab));
   D.mega_scratch = h->ws.get<float>(mega_scratch_bytes(R) / 4);
+  D.mega_act = (c.ff % 512 == 0) ? h->ws.get<char>(mega_act_bytes(R, c.ff, c.n_dec)) : nullptr;
   D.topk = 0; D.topv = nullptr; D.topi = nullptr; D.topk_done = false;
   return 0;
 }
@@ -782,16 +784,23 @@ int dec_step_mega(xn_handle* h, DecBufs& D, int p, const int64_t* tok64, const i
     const DecLayerW& W = h->dec[l];
     MegaLayer& m = a.L[l];
     m.n1g = W.n1g; m.n1b = W.n1b; m.n2g = W.n2g; m.n2b = W.n2b; m.n3g = W.n3g; m.n3b = W.n3b; m.qexp = W.qexp; m.bexp = W.bexp;
-    m.w_dyn5 = W.dyn5.wb; m.w_wq = W.wq.wb; m.w_wo = W.wo.wb; m.w_ff1 = W.ff1.wb; m.w_ff2 = W.ff2.wb;
+    m.w_dyn5 = W.dyn5.wp; m.w_wq = W.wq.wp; m.w_wo = W.wo.wp; m.w_ff1 = W.ff1.wp; m.w_ff2 = W.ff2.wp;
+    if (!m.w_dyn5 || !m.w_wq || !m.w_wo || !m.w_ff1 || !m.w_ff2) return 1;
     m.b_dyn5 = W.dyn5.b; m.b_wq = W.wq.b; m.b_wo = W.wo.b; m.b_ff1 = W.ff1.b; m.b_ff2 = W.ff2.b;
     if (W.dyn5.N != 5 * c.d_model || W.dyn5.K != c.d_model || W.ff1.N != c.ff || W.ff2.K != c.ff) return 1;
   }
   a.tok64 = tok64; a.tok32 = tok32; a.tok_stride = tok_stride; a.n_valid = n_valid; a.row_len = row_len;
   a.emb = h->emb; a.pos = h->pos;
-  a.x0 = D.x0; a.ycat = D.ycat; a.q = D.q; a.pre = D.pre; a.xn = D.xn; a.att = D.att; a.hid = D.hid; a.ycat16 = D.ycat16;
+  a.x0 = D.x0; a.ycat = D.ycat; a.q = D.q; a.pre = D.pre;
+  {
+    const size_t slab = (size_t)((D.R + 31) / 32) * 32 * 520 * 2;          // one packed 16-bit slab (rows of 520 elements)
+    char* base = reinterpret_cast<char*>(D.mega_act);
+    a.xn = base; a.att = base + slab; a.hid = base + 2 * slab; a.ycat16 = base + (2 + (size_t)c.ff / 512) * slab;
+  }
   a.kv = D.kv; a.ldkv = (long)c.n_dec * 2 * c.d_model;
-  a.w_reduce = h->dec_reduce.wb; a.b_reduce = h->dec_reduce.b; a.ng = h->dec_ng; a.nb = h->dec_nb;
-  a.w_vocab = h->vocab.wb; a.b_vocab = h->vocab.b;
+  a.w_reduce = h->dec_reduce.wp; a.b_reduce = h->dec_reduce.b; a.ng = h->dec_ng; a.nb = h->dec_nb;
+  a.w_vocab = h->vocab.wp;
+  if (!a.w_reduce || !a.w_vocab || !D.mega_act) return 1; a.b_vocab = h->vocab.b;
   a.logits = logits; a.ldl = ldl;
   const bool fuse = h->fuse_topk && D.topk > 0 && D.topv && D.topi && D.parts;
   a.topk = fuse ? D.topk : 0; a.parts = D.parts; a.top_val = D.topv; a.top_idx = D.topi;
@@ -1318,6 +1327,15 @@ int xn_finalize_weights(xn_handle* h, int precision) {
     l.wb = p;
     return 0;
   };
+  auto to_packed = [&](LinW& l) -> int {    // decoder linears: also the persistent kernel's slab-packed layout
+    if (rc || !l.w || (l.K % 512)) return rc;
+    void* p = nullptr;
+    CU(cudaMalloc(&p, mega_packed_bytes(l.N, l.K)));
+    h->owned.push_back(p);
+    KL(1, launch_mega_pack_weight(l.w, p, l.N, l.K, precision == XN_PREC_FP16, 0));
+    l.wp = p;
+    return 0;
+  };
   // concatenate row blocks of several (N_i x K) weights (+ biases) into one (sum N_i x K) weight
   auto concat = [&](const std::vector<LinW>& parts, LinW& outl) -> int {
     if (rc) return rc;
@@ -1452,6 +1470,7 @@ int xn_finalize_weights(xn_handle* h, int precision) {
     if (rc) return rc;
     if (concat(parts, W.dyn5)) return XN_ERR_CUDA;
     if (precision != XN_PREC_FP32 && (to_bf16(W.dyn5) || to_bf16(W.wq) || to_bf16(W.wo) || to_bf16(W.ff1) || to_bf16(W.ff2))) return XN_ERR_CUDA;
+    if (precision != XN_PREC_FP32 && (to_packed(W.dyn5) || to_packed(W.wq) || to_packed(W.wo) || to_packed(W.ff1) || to_packed(W.ff2))) return XN_ERR_CUDA;
     h->dec.push_back(W);
   }
   h->input_linear = lin("input_linear", d, c.feat_dim);
@@ -1466,6 +1485,7 @@ int xn_finalize_weights(xn_handle* h, int precision) {
   if (rc) return rc;
   if (concat(kvparts, h->kv_all)) return XN_ERR_CUDA;
   if (precision != XN_PREC_FP32 && (to_bf16(h->kv_all) || to_bf16(h->vocab) || to_bf16(h->dec_reduce))) return XN_ERR_CUDA;
+  if (precision != XN_PREC_FP32 && (to_packed(h->vocab) || to_packed(h->dec_reduce))) return XN_ERR_CUDA;
   CU(cudaDeviceSynchronize());
   h->precision = precision;
   return XN_OK;
@@ -2199,7 +2219,7 @@ int xn_mega_timeline(xn_handle* h, uint64_t* out, int cap) {
   unsigned long long buf[128];
   CU(cudaMemcpy(buf, h->mega_dbg, sizeof buf, cudaMemcpyDeviceToHost));
   const int n = (int)std::min<unsigned long long>(buf[127], 64);
-  for (int i = 0; i < cap; ++i) out[i] = i < n ? buf[i] : (i >= 64 && i < (int)std::min<unsigned long long>(buf[126], 126) ? buf[i] : 0);
+  for (int i = 0; i < cap; ++i) out[i] = i < n ? buf[i] : (i >= 64 && i < (int)std::min<unsigned long long>(buf[126], 124) ? buf[i] : (i == 124 || i == 125 ? buf[i] : 0));
   return n;
 }
 

@@ -187,7 +187,7 @@ cudaError_t launch_cross_attn_step(const float* q, long ldq, const KvT* kv, long
 constexpr int kMegaMaxLayers = 4;
 struct MegaLayer {
   const float *n1g, *n1b, *n2g, *n2b, *n3g, *n3b, *qexp, *bexp;
-  const void *w_dyn5, *w_wq, *w_wo, *w_ff1, *w_ff2;          // (N x K) 16-bit
+  const void *w_dyn5, *w_wq, *w_wo, *w_ff1, *w_ff2;          // 16-bit, slab-packed (launch_mega_pack_weight)
   const float *b_dyn5, *b_wq, *b_wo, *b_ff1, *b_ff2;
 };
 struct MegaArgs {
@@ -198,7 +198,7 @@ struct MegaArgs {
   const int* n_valid; const int* row_len;
   const float *emb, *pos;
   float *x0, *ycat, *q, *pre;                 // fp32: embedding, layer outputs side by side (ld d*n_layers), queries, reduce output
-  void *xn, *att, *hid, *ycat16;              // 16-bit operands
+  void *xn, *att, *hid, *ycat16;              // 16-bit operands, slab-packed (mega_act_bytes): rows of 520, K slabs of 512
   const void* kv; long ldkv;                  // cross K/V of all layers per encoder token: [layer][K | V]
   const void* w_reduce; const float* b_reduce;
   const float *ng, *nb;
@@ -213,6 +213,9 @@ struct MegaArgs {
 bool mega_supported(const MegaArgs& a);
 size_t mega_parts_bytes(int R, int vocab);
 size_t mega_scratch_bytes(int R);
+size_t mega_packed_bytes(int N, int K);          // slab-packed 16-bit copy of an (N x K) weight, K % 512 == 0
+cudaError_t launch_mega_pack_weight(const float* w, void* out, int N, int K, int fp16, cudaStream_t st);
+size_t mega_act_bytes(int R, int ff, int n_layers);
 constexpr size_t kMegaBarBytes = 20 * 1024;
 template <typename T>
 cudaError_t launch_dec_step_mega(const MegaArgs& a, cudaStream_t st);

@@ -99,7 +99,8 @@ class Engine:
         n = self.lib.xn_mega_timeline(self._h, buf, 128)
         if n < 0:
             self._check(n, "xn_mega_timeline")
-        self.mega_fine = [int(buf[i]) for i in range(64, 126) if buf[i]]     # intra-phase stamps of the GEMM phases (layer 0, tail)
+        self.mega_clock = (int(buf[124]), int(buf[125]))                       # clock64 at the kernel's start / end (CTA 0)
+        self.mega_fine = [int(buf[i]) for i in range(64, 124) if buf[i]]     # intra-phase stamps of the GEMM phases (layer 0, tail)
         return [int(buf[i]) for i in range(n)]
 
     def profile_kernels(self):

@@ -7,7 +7,7 @@ import torch
 from on_device_image_captioning_b200 import config as C, synth
 from on_device_image_captioning_b200.engine import Engine
 
-PHASES = ["embed"] + [f"L{l}.{n}" for l in range(3) for n in ("dyn5", "dynexp", "wq", "cross", "wo", "ff1", "ff2")] + ["reduce", "vocab", "merge"]
+PHASES = [f"L{l}.{n}" for l in range(3) for n in ("dyn5", "dynexp", "wq", "cross", "wo", "ff1", "ff2")] + ["reduce", "vocab", "merge"]
 
 def main():
     B = int(sys.argv[1]) if len(sys.argv) > 1 else 64
@@ -42,6 +42,8 @@ def main():
         print(f"  {name:10s} work(CTA0) {1e-3 * (t[i] - prev):7.2f} us   (last phase)")
     print("phase boundaries (us since kernel start): " + " ".join(f"{1e-3 * (v - t[0]):.2f}" for v in t))
 
+    c0, c1 = e.mega_clock
+    print(f"SM clock during the kernel: {(c1 - c0) / (t[-1] - t[0]) * 1e3:.0f} MHz ({c1 - c0} cycles)")
     f = e.mega_fine
     print("fine stamps (GEMM phases of layer 0, then reduce / vocab; us since kernel start):")
     print("  " + " ".join(f"{1e-3 * (v - t[0]):.2f}" for v in f))
