@@ -192,6 +192,13 @@ int64_t xn_workspace_bytes(const xn_handle* h);
  *   "use_skinny"               skinny mma.sync GEMM for decoder-step linears with <= 64 rows
  *   "ln_fuse"                  Swin norm1 / norm2 folded algebraically into the neighbouring tcgen05 GEMMs (default 1, 16-bit modes)
  *   "ln_on_load"               decoder-step LayerNorm computed inside the consuming tcgen05 GEMM (off: measured slower)
+ *   "use_mega"                 1: every decoder position of the 16-bit modes (d_model 512, head width 64, <= 20 positions,
+ *                              16 expansion vectors) runs as ONE persistent cooperative kernel with grid barriers between its
+ *                              phases (csrc/decode_mega.cu) instead of ~33 launches; default 0 (measured: a tie at <= 192 rows,
+ *                              slower beyond).  "fuse_topk" (1): that kernel also does log-softmax + top-k of the 'max' search,
+ *                              the R x V logits are never stored.  "mega_search" (0): all time steps of the search in one launch
+ *                              (measured slower).  "mega_coop" (1): cooperative launch.  "mega_dbg": phase timestamps for
+ *                              xn_mega_timeline; "mega_dbg_mode": timing experiments (skip MMAs / loads / fills)
  *   "profile"                  1: event-time every tcgen05 GEMM; 2: event-time every kernel launch (both disable graphs)
  *   "tc_debug", "op_out16"     kernel timing experiments / test hooks */
 int xn_set_option(xn_handle* h, const char* name, int64_t value);

@@ -21,6 +21,7 @@
 #include "mma16_frag.cuh"
 #include "tcgen05_ptx.cuh"
 #include "decode_rows.cuh"
+#include "beam_rows.cuh"
 
 namespace xn {
 
@@ -128,7 +129,8 @@ struct NoTileHook {
 // run with coalesced 16-byte accesses.  With ksplit > 1 the partial tile goes to `scratch` and the CTA that arrives last
 // at the tile's counter adds the splits in order (deterministic) and finishes.
 template <typename T, int BN, bool LN, bool STORE = true, typename Hook = NoTileHook>
-__device__ __forceinline__ void gemm_phase_impl(const GemmP& g, char* smem, uint32_t& mphase, const Hook& hook = Hook()) {
+__device__ __forceinline__ void gemm_phase_impl(const GemmP& g, char* smem, uint32_t& mphase, uint32_t& mphase2, bool& w_ready,
+                                                const Hook& hook = Hook()) {
   constexpr int NB2 = BN / 16, NF = BN / 8, PITCH = BN + 8, C4 = BN / 4;
   static_assert(4 * kBM * PITCH * 4 <= kWRegion, "reduction tiles must fit in the W region");
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -159,13 +161,20 @@ __device__ __forceinline__ void gemm_phase_impl(const GemmP& g, char* smem, uint
       // Operands are stored with the 520-element row pitch of the shared-memory tile (weights re-packed at load time,
       // activations written that way by the producing phase), one K slab of 512 after the other: a whole operand tile is
       // ONE contiguous bulk copy.  The regions were last touched through the generic proxy (ldmatrix / reduction) by this
-      // CTA, all before the __syncthreads that ended the previous item.
+      // CTA, all before the __syncthreads that ended the previous item.  W and A complete on separate mbarriers: the W
+      // tile of a phase's first item is usually already in flight (prefetch_w, issued before the preceding grid barrier).
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      const int wrows = min(BN, g.N - n0);
-      mbar_expect(mbar, (uint32_t)((wrows + (LN ? 0 : kBM)) * kPitch));
-      bulk_g2s(smem_u32(w_sm), W + ((long)sp * g.N + n0) * kPadK, (uint32_t)(wrows * kPitch), mbar);
-      if (!LN) bulk_g2s(smem_u32(a_sm), A16 + ((long)sp * m32 + r0) * kPadK, (uint32_t)(kBM * kPitch), mbar);
+      if (!w_ready) {
+        const int wrows = min(BN, g.N - n0);
+        mbar_expect(mbar, (uint32_t)(wrows * kPitch));
+        bulk_g2s(smem_u32(w_sm), W + ((long)sp * g.N + n0) * kPadK, (uint32_t)(wrows * kPitch), mbar);
+      }
+      if (!LN) {
+        mbar_expect(mbar + 8, (uint32_t)(kBM * kPitch));
+        bulk_g2s(smem_u32(a_sm), A16 + ((long)sp * m32 + r0) * kPadK, (uint32_t)(kBM * kPitch), mbar + 8);
+      }
     }
+    w_ready = false;
     if (LN && !a_ready && !(g.dbg_mode & 4)) {
       // LayerNorm(gamma, beta) of rows r0 .. r0+31 (K == 512): four rows per warp, all their loads in flight together; same
       // arithmetic and summation order as layernorm_kernel (elementwise.cu: ln_row)
@@ -234,6 +243,10 @@ __device__ __forceinline__ void gemm_phase_impl(const GemmP& g, char* smem, uint
     if (do_load) {
       tc5::mbar_wait(mbar, mphase);
       mphase ^= 1u;
+      if (!LN) {
+        tc5::mbar_wait(mbar + 8, mphase2);
+        mphase2 ^= 1u;
+      }
     }
     if (LN && !a_ready) __syncthreads();                 // the normalised rows of all warps
     a_ready = astat;
@@ -364,6 +377,37 @@ __device__ __forceinline__ void gemm_phase_impl(const GemmP& g, char* smem, uint
 }
 
 
+
+// Issue the W tile of the first item this CTA will take in the NEXT GEMM phase (same item order as gemm_phase_impl).
+// Weights do not depend on the grid barrier in between, so the copy flies during the barrier (and, for the output
+// projection, during the whole cross-attention phase, which leaves the W region alone).  Returns whether a copy is in flight.
+template <typename T, int BN, bool LN>
+__device__ __forceinline__ bool prefetch_w(const void* Wv, int M, int N, int S, char* smem, int dbg_mode) {
+  if (dbg_mode & (2 | 32)) return false;
+  const int ntm = (M + kBM - 1) / kBM, ntn = (N + BN - 1) / BN;
+  const bool astat = LN && S == 1 && (int)gridDim.x >= ntm;
+  int tn, sp = 0;
+  if (astat) {
+    const int cpg = (int)gridDim.x / ntm, slot = blockIdx.x / ntm;
+    if (slot >= cpg || slot >= ntn) return false;
+    tn = slot;
+  } else {
+    const int item = blockIdx.x;
+    if (item >= ntm * ntn * S) return false;
+    const int tile = item / S;
+    sp = item - tile * S;
+    tn = tile / ntm;
+  }
+  if (threadIdx.x == 0) {
+    const uint32_t mbar = smem_u32(smem + kMbarOff);
+    const int n0 = tn * BN, wrows = min(BN, N - n0);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    mbar_expect(mbar, (uint32_t)(wrows * kPitch));
+    bulk_g2s(smem_u32(smem + kARegion), reinterpret_cast<const T*>(Wv) + ((long)sp * N + n0) * kPadK, (uint32_t)(wrows * kPitch), mbar);
+  }
+  return true;
+}
+
 // ---- fused log-softmax / top-k over the vocabulary (K6): every 64-column tile of the vocabulary projection leaves,
 // per row, its maximum, sum of exp(x - max) and its best k (value, index) candidates; one warp per row then merges the
 // tiles' partials: lse = M + log(sum_t s_t exp(m_t - M)), lp = (x - M) - lse.  The R x V logits are never stored.
@@ -427,10 +471,9 @@ struct TopkHook {
 // merge of the per-tile partials: one warp per row.  Round r picks the best candidate that ranks strictly after round
 // r-1's winner in the order (value descending, index ascending) -- no cursors, every lane rescans its tiles' k entries
 // (L1 hits after the first round).
-__device__ __forceinline__ void topk_merge_phase(const TopkParts& parts, int ntn, int R, int k, float* top_val, int* top_idx) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+__device__ __forceinline__ void topk_merge_row(const TopkParts& parts, int ntn, int r, int k, float* top_val, int* top_idx, int lane) {
   constexpr int TPL = 8;                                        // tiles per lane (ntn <= 256)
-  for (int r = blockIdx.x * (kMegaThreads / 32) + warp; r < R; r += gridDim.x * (kMegaThreads / 32)) {
+  {
     const long base = (long)r * ntn;
     float m[TPL], sm_[TPL];
 #pragma unroll
@@ -478,6 +521,12 @@ __device__ __forceinline__ void topk_merge_phase(const TopkParts& parts, int ntn
       }
     }
   }
+}
+
+__device__ __forceinline__ void topk_merge_phase(const TopkParts& parts, int ntn, int R, int k, float* top_val, int* top_idx) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int r = blockIdx.x * (kMegaThreads / 32) + warp; r < R; r += gridDim.x * (kMegaThreads / 32))
+    topk_merge_row(parts, ntn, r, k, top_val, top_idx, lane);
 }
 
 // ---- dynamic expansion of one row with the history rows STAGED in shared memory by bulk copies (np <= 20 positions,
@@ -785,11 +834,14 @@ __device__ __forceinline__ void dyn_exp_row_staged(const DecState& s, int layer,
   stamp();                                                       // row stored, norm_2 written
 }
 
+// One decoder position: all phases up to the vocabulary projection (and, with merge_rows, the row-wise top-k merge).
+// p, the token table and the ancestry table are arguments: the whole-search kernel calls this once per time step.
 template <typename T>
-__global__ void __launch_bounds__(kMegaThreads, 2) dec_step_mega_kernel(const __grid_constant__ MegaArgs a) {
-  extern __shared__ __align__(128) char smem[];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int d = 512, R = a.R, nd = a.n_layers, p = a.p;
+__device__ __forceinline__ void mega_position(const MegaArgs& a, const DecState& st, int p, const int64_t* tok64, const int* tok32,
+                                              bool merge_rows, GridBar& bar, char* smem, uint32_t& mphase, uint32_t& mphase2, int& mark,
+                                              int& fmark) {
+  const int tid = threadIdx.x;
+  const int d = 512, R = a.R, nd = a.n_layers;
   const long ldc = (long)d * nd;
   const long m32 = (long)((R + kBM - 1) / kBM) * kBM;        // rows of a packed 16-bit activation slab
   T* xn = reinterpret_cast<T*>(a.xn);
@@ -797,18 +849,7 @@ __global__ void __launch_bounds__(kMegaThreads, 2) dec_step_mega_kernel(const __
   T* hid = reinterpret_cast<T*>(a.hid);
   T* ycat16 = reinterpret_cast<T*>(a.ycat16);
   const T* kv = reinterpret_cast<const T*>(a.kv);
-  int mark = 1, fmark = 64;
-  if (a.dbg && blockIdx.x == 0 && tid == 0) { a.dbg[0] = gtimer(); a.dbg[124] = (unsigned long long)clock64(); }
-  GridBar bar;
-  bar.init(a.bar);
-  uint32_t mphase = 0u, mphase2 = 0u;            // parity of the mbarriers' next completion
-  if (tid == 0) {
-    tc5::mbar_init(smem_u32(smem + kMbarOff), 1);
-    tc5::mbar_init(smem_u32(smem + kMbarOff) + 8, 1);
-    tc5::fence_mbar_init();
-  }
-  __syncthreads();
-
+  (void)tid;
   // Every GEMM phase is its own inlined, specialised copy of gemm_phase (null pointers and constant shapes folded away).
   // One shared copy per tile variant driven by a run-time descriptor was measured: 17 us slower per position, although the
   // kernel's code is fetched cold at every position (ncu: 18 % of the non-barrier warp samples are "no instruction").
@@ -816,6 +857,7 @@ __global__ void __launch_bounds__(kMegaThreads, 2) dec_step_mega_kernel(const __
   GemmP g{};                                                                                              \
   g.dbg_mode = a.dbg_mode; g.fine = (a.dbg && l == 0 && !(a.dbg_mode & 16)) ? a.dbg : nullptr; g.fmark = &fmark; \
   g.M = R; g.N = d; g.K = d;
+  bool w_ready = false;                          // the next GEMM phase's first W tile is already in flight
   int l = 0;
   for (; l < nd; ++l) {
     const MegaLayer& W = a.L[l];
@@ -826,25 +868,27 @@ __global__ void __launch_bounds__(kMegaThreads, 2) dec_step_mega_kernel(const __
       XN_GEMM_INIT(g)
       g.A32 = xin; g.lda32 = ldi; g.ln_g = W.n1g; g.ln_b = W.n1b;
       if (l == 0) {                              // the embedding is computed in the fill (no separate phase, no barrier)
-        g.emb = a.emb; g.pos_row = a.pos + (long)p * d; g.tok64 = a.tok64; g.tok32 = a.tok32; g.tok_stride = a.tok_stride;
+        g.emb = a.emb; g.pos_row = a.pos + (long)p * d; g.tok64 = tok64; g.tok32 = tok32; g.tok_stride = a.tok_stride;
         g.tok_p = p; g.x0_out = a.x0;
       }
-      g.W = W.w_dyn5; g.bias = W.b_dyn5; g.Cf = a.s.cache + (((size_t)l * a.s.P + p) * R) * a.s.cw; g.ldcf = a.s.cw; g.N = 5 * d;
-      gemm_phase_impl<T, 64, true>(g, smem, mphase);
+      g.W = W.w_dyn5; g.bias = W.b_dyn5; g.Cf = st.cache + (((size_t)l * st.P + p) * R) * st.cw; g.ldcf = st.cw; g.N = 5 * d;
+      gemm_phase_impl<T, 64, true>(g, smem, mphase, mphase2, w_ready);
     }
     bar.sync(a.dbg, &mark);
     // incremental dynamic expansion of position p + residual, then norm_2 -> xn
     for (int r = blockIdx.x; r < R; r += gridDim.x) {
-      dyn_exp_row_staged<T>(a.s, l, p, W.qexp, W.bexp, a.row_len, xin, ldi, xout, ldc, W.n2g, W.n2b, xn, kPadK, r, smem, mphase,
+      dyn_exp_row_staged<T>(st, l, p, W.qexp, W.bexp, a.row_len, xin, ldi, xout, ldc, W.n2g, W.n2b, xn, kPadK, r, smem, mphase,
                             mphase2, (a.dbg_mode & 16) && l == 0 ? a.dbg : nullptr, &fmark);
       __syncthreads();
     }
+    w_ready = prefetch_w<T, 32, false>(W.w_wq, R, d, 1, smem, a.dbg_mode);
     bar.sync(a.dbg, &mark);
     {                                            // q = xn Wq^T + b
       XN_GEMM_INIT(g)
       g.A16 = xn; g.W = W.w_wq; g.bias = W.b_wq; g.Cf = a.q; g.ldcf = d;
-      gemm_phase_impl<T, 32, false>(g, smem, mphase);
+      gemm_phase_impl<T, 32, false>(g, smem, mphase, mphase2, w_ready);
     }
+    w_ready = prefetch_w<T, 32, false>(W.w_wo, R, d, 1, smem, a.dbg_mode);      // lands during the cross attention
     bar.sync(a.dbg, &mark);
     {                                            // cross attention, one item per (image, head, group of <= 4 beam rows)   (layers.py:266-295)
       const int rpi = a.rows_per_image, n_img = R / rpi, ngrp = (rpi + 3) / 4, heads = a.heads;
@@ -866,23 +910,27 @@ __global__ void __launch_bounds__(kMegaThreads, 2) dec_step_mega_kernel(const __
     {                                            // x = x + att Wo^T + b
       XN_GEMM_INIT(g)
       g.A16 = att; g.W = W.w_wo; g.bias = W.b_wo; g.res = xout; g.ldr = ldc; g.Cf = xout; g.ldcf = ldc;
-      gemm_phase_impl<T, 32, false>(g, smem, mphase);
+      gemm_phase_impl<T, 32, false>(g, smem, mphase, mphase2, w_ready);
     }
+    w_ready = prefetch_w<T, 64, true>(W.w_ff1, R, a.ff, 1, smem, a.dbg_mode);
     bar.sync(a.dbg, &mark);
     {                                            // hid = relu(LN3(x) W1^T + b)
       XN_GEMM_INIT(g)
       g.A32 = xout; g.lda32 = ldc; g.ln_g = W.n3g; g.ln_b = W.n3b;
       g.W = W.w_ff1; g.bias = W.b_ff1; g.Cb = hid; g.N = a.ff; g.act = 2;
-      gemm_phase_impl<T, 64, true>(g, smem, mphase);
+      gemm_phase_impl<T, 64, true>(g, smem, mphase, mphase2, w_ready);
     }
+    w_ready = prefetch_w<T, 64, false>(W.w_ff2, R, d, a.ksplit_ff2 > 1 ? a.ksplit_ff2 : 1, smem, a.dbg_mode);
     bar.sync(a.dbg, &mark);
     {                                            // x = x + hid W2^T + b   (also kept in 16 bits: operand of the reduce group)
       XN_GEMM_INIT(g)
       g.A16 = hid; g.W = W.w_ff2; g.bias = W.b_ff2; g.res = xout; g.ldr = ldc; g.Cf = xout; g.ldcf = ldc;
       g.Cb = ycat16 + (size_t)l * m32 * kPadK; g.K = a.ff;
       g.ksplit = a.ksplit_ff2; g.scratch = a.scratch; g.cnt = a.bar + kSplitCntOff;
-      gemm_phase_impl<T, 64, false>(g, smem, mphase);
+      gemm_phase_impl<T, 64, false>(g, smem, mphase, mphase2, w_ready);
     }
+    if (l + 1 < nd) w_ready = prefetch_w<T, 64, true>(a.L[l + 1].w_dyn5, R, 5 * d, 1, smem, a.dbg_mode);
+    else w_ready = prefetch_w<T, 64, false>(a.w_reduce, R, d, a.ksplit_red > 1 ? a.ksplit_red : 1, smem, a.dbg_mode);
     bar.sync(a.dbg, &mark);
   }
   l = nd - 1;
@@ -891,8 +939,9 @@ __global__ void __launch_bounds__(kMegaThreads, 2) dec_step_mega_kernel(const __
     g.A16 = ycat16; g.W = a.w_reduce; g.bias = a.b_reduce; g.res = a.ycat + (size_t)(nd - 1) * d; g.ldr = ldc;
     g.Cf = a.pre; g.ldcf = d; g.K = d * nd;
     g.ksplit = a.ksplit_red; g.scratch = a.scratch; g.cnt = a.bar + kSplitCntOff;
-    gemm_phase_impl<T, 64, false>(g, smem, mphase);
+    gemm_phase_impl<T, 64, false>(g, smem, mphase, mphase2, w_ready);
   }
+  w_ready = prefetch_w<T, 64, true>(a.w_vocab, R, a.vocab, 1, smem, a.dbg_mode);
   bar.sync(a.dbg, &mark);
   {                                              // logits = LN(pre) Wv^T + b    (End_ExpansionNet_v2.py:200-204)
     XN_GEMM_INIT(g)
@@ -901,15 +950,85 @@ __global__ void __launch_bounds__(kMegaThreads, 2) dec_step_mega_kernel(const __
     if (a.topk > 0) {
       const int ntn_v = (a.vocab + 63) / 64;
       TopkHook<64> hook{TopkParts{reinterpret_cast<float*>(a.parts), (long)R * ntn_v}, ntn_v, R, a.vocab, a.topk};
-      gemm_phase_impl<T, 64, true, false, TopkHook<64>>(g, smem, mphase, hook);
+      gemm_phase_impl<T, 64, true, false, TopkHook<64>>(g, smem, mphase, mphase2, w_ready, hook);
       bar.sync(a.dbg, &mark);
-      topk_merge_phase(TopkParts{reinterpret_cast<float*>(a.parts), (long)R * ntn_v}, ntn_v, R, a.topk, a.top_val, a.top_idx);
+      if (merge_rows) topk_merge_phase(TopkParts{reinterpret_cast<float*>(a.parts), (long)R * ntn_v}, ntn_v, R, a.topk, a.top_val, a.top_idx);
     } else {
       g.Cf = a.logits; g.ldcf = a.ldl;
-      gemm_phase_impl<T, 64, true>(g, smem, mphase);
+      gemm_phase_impl<T, 64, true>(g, smem, mphase, mphase2, w_ready);
     }
   }
 #undef XN_GEMM_INIT
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kMegaThreads, 2) dec_step_mega_kernel(const __grid_constant__ MegaArgs a) {
+  extern __shared__ __align__(128) char smem[];
+  const int tid = threadIdx.x;
+  int mark = 1, fmark = 64;
+  if (a.dbg && blockIdx.x == 0 && tid == 0) { a.dbg[0] = gtimer(); a.dbg[124] = (unsigned long long)clock64(); }
+  GridBar bar;
+  bar.init(a.bar);
+  uint32_t mphase = 0u, mphase2 = 0u;            // parity of the mbarriers' next completion
+  if (tid == 0) {
+    tc5::mbar_init(smem_u32(smem + kMbarOff), 1);
+    tc5::mbar_init(smem_u32(smem + kMbarOff) + 8, 1);
+    tc5::fence_mbar_init();
+  }
+  __syncthreads();
+  mega_position<T>(a, a.s, a.p, a.tok64, a.tok32, true, bar, smem, mphase, mphase2, mark, fmark);
+  if (a.dbg && blockIdx.x == 0 && tid == 0) { a.dbg[mark++] = gtimer(); a.dbg[127] = (unsigned long long)mark; a.dbg[126] = (unsigned long long)fmark; a.dbg[125] = (unsigned long long)clock64(); }
+}
+
+// ---- the whole beam search ('max' branch) in ONE launch: time steps loop inside the kernel, the bookkeeping of a step
+// (captioning_model.py:295-397) runs per image right after the image's rows have merged their top-k, and the reference's
+// early `break` (:397, "no beam was extended") is a grid-uniform branch on a flag read after the step's barrier.  Against
+// one launch per position this removes the launch gaps (20-40 us per step in a graph) and the conditional graph nodes --
+// but MEASURED SLOWER (B200, 64 images x beam 3: 307 vs 265 us per position, 5.8 vs 5.4 ms per search): inside the
+// time-step loop the compiler hoists the position's loop-invariant address arithmetic across the loop and spills it in the
+// hot phases; as an out-of-line function (ABI register limits: 1.4 KB of spills) it is 391 us.  Kept behind the option
+// "mega_search" (default off), under test.
+template <typename T>
+__global__ void __launch_bounds__(kMegaThreads, 2) dec_search_mega_kernel(const __grid_constant__ MegaArgs a,
+                                                                           const __grid_constant__ MegaSearch q) {
+  extern __shared__ __align__(128) char smem[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  int mark = 1, fmark = 64;
+  if (a.dbg && blockIdx.x == 0 && tid == 0) { a.dbg[0] = gtimer(); a.dbg[124] = (unsigned long long)clock64(); }
+  GridBar bar;
+  bar.init(a.bar);
+  uint32_t mphase = 0u, mphase2 = 0u;
+  if (tid == 0) {
+    tc5::mbar_init(smem_u32(smem + kMbarOff), 1);
+    tc5::mbar_init(smem_u32(smem + kMbarOff) + 8, 1);
+    tc5::fence_mbar_init();
+  }
+  __syncthreads();
+  const int beam = q.beam, L = q.L, B = a.R / beam, ntn_v = (a.vocab + 63) / 64;
+  const TopkParts parts{reinterpret_cast<float*>(a.parts), (long)a.R * ntn_v};
+  int src = 0;
+  for (int t = 1; t < L; ++t) {                  // choosing token t: decode position t - 1
+    DecState st = a.s;
+    st.anc = q.bb.anc[src];
+    if (a.dbg && blockIdx.x == 0 && tid == 0) a.dbg[0] = gtimer();       // the timeline keeps the last executed step
+    mark = 1;
+    mega_position<T>(a, st, t - 1, nullptr, q.bb.tokens[src], false, bar, smem, mphase, mphase2, mark, fmark);
+    // per image: its beam rows merge their top-k (one warp per row), then one warp runs the step's bookkeeping
+    for (int b = blockIdx.x; b < B; b += gridDim.x) {
+      if (warp < beam) topk_merge_row(parts, ntn_v, b * beam + warp, a.topk, a.top_val, a.top_idx, lane);
+      __syncthreads();
+      if (t == 1) { if (tid < beam) beam_first_row(q.bb, a.top_val, a.top_idx, beam, L, q.eos, b * beam + tid); }
+      else if (warp == 0) beam_step_image(q.bb, src, a.top_val, a.top_idx, beam, L, t, q.eos, b, lane);
+      __syncthreads();
+    }
+    bar.sync(a.dbg, &mark);
+    if (t > 1) {
+      src ^= 1;
+      if (q.early_exit && *reinterpret_cast<volatile int*>(q.bb.grew + t) == 0) break;     // every beam had ended (:397)
+    }
+  }
+  for (int b = blockIdx.x * kMegaThreads + tid; b < B; b += gridDim.x * kMegaThreads)
+    beam_finalize_image(q.bb, beam, L, L, q.how_many, q.r_tok, q.r_len, q.r_lp, b);
   if (a.dbg && blockIdx.x == 0 && tid == 0) { a.dbg[mark++] = gtimer(); a.dbg[127] = (unsigned long long)mark; a.dbg[126] = (unsigned long long)fmark; a.dbg[125] = (unsigned long long)clock64(); }
 }
 
@@ -948,38 +1067,58 @@ bool mega_supported(const MegaArgs& a) {
   return true;
 }
 
-template <typename T>
-cudaError_t launch_dec_step_mega(const MegaArgs& a, cudaStream_t st) {
-  if (!mega_supported(a)) return cudaErrorInvalidValue;
-  struct DevInfo { int grid = 0; size_t smem = 0; };
-  static DevInfo info[32];
+template <typename K>
+static cudaError_t mega_launch_config(K kernel, const MegaArgs& a, cudaLaunchConfig_t& cfg, cudaLaunchAttribute* attr, int which) {
+  struct DevInfo { int grid = 0; size_t smem = 0; int sms = 0; };
+  static DevInfo info[2][32];
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev < 0 || dev >= 32) dev = 0;
-  const size_t smem_gemm = kGemmSmem;
   const size_t smem_rows = dyn_exp_smem_floats(a.s.P, a.n_exp) * sizeof(float);
-  const size_t smem = std::max(smem_gemm, smem_rows);
-  if (info[dev].grid == 0 || info[dev].smem < smem) {
-    if (cudaError_t e = cudaFuncSetAttribute(dec_step_mega_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) return e;
+  const size_t smem = std::max((size_t)kGemmSmem, smem_rows);
+  DevInfo& di = info[which][dev];
+  if (di.grid == 0 || di.smem < smem) {
+    if (cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) return e;
     int per_sm = 0, sms = 0;
-    if (cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dec_step_mega_kernel<T>, kMegaThreads, smem)) return e;
+    if (cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kMegaThreads, smem)) return e;
     if (cudaError_t e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) return e;
     if (per_sm < 1) return cudaErrorLaunchOutOfResources;
-    info[dev].grid = std::min(per_sm, 2) * sms;
-    info[dev].smem = smem;
+    di.grid = std::min(per_sm, 2) * sms;
+    di.smem = smem;
+    di.sms = sms;
   }
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(info[dev].grid);
+  cfg = cudaLaunchConfig_t{};
+  cfg.gridDim = dim3(a.max_ctas_per_sm == 1 ? di.sms : di.grid);
   cfg.blockDim = dim3(kMegaThreads);
-  cfg.dynamicSmemBytes = info[dev].smem;
-  cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cfg.dynamicSmemBytes = di.smem;
   attr[0].id = cudaLaunchAttributeCooperative;          // all CTAs co-resident or the launch fails: the grid barrier cannot deadlock
   attr[0].val.cooperative = 1;
   cfg.attrs = attr;
   cfg.numAttrs = g_mega_coop ? 1 : 0;
+  return cudaSuccess;
+}
+
+template <typename T>
+cudaError_t launch_dec_step_mega(const MegaArgs& a, cudaStream_t st) {
+  if (!mega_supported(a)) return cudaErrorInvalidValue;
+  cudaLaunchConfig_t cfg;
+  cudaLaunchAttribute attr[1];
+  if (cudaError_t e = mega_launch_config(dec_step_mega_kernel<T>, a, cfg, attr, std::is_same<T, f16>::value ? 0 : 1)) return e;
+  cfg.stream = st;
   return cudaLaunchKernelEx(&cfg, dec_step_mega_kernel<T>, a);
 }
+template <typename T>
+cudaError_t launch_dec_search_mega(const MegaArgs& a, const MegaSearch& q, cudaStream_t st) {
+  if (!mega_supported(a) || a.topk != q.beam || q.beam < 1 || q.beam > kMaxBeam || a.rows_per_image != q.beam) return cudaErrorInvalidValue;
+  cudaLaunchConfig_t cfg;
+  cudaLaunchAttribute attr[1];
+  static_assert(kMegaThreads / 32 >= kMaxBeam, "one warp per beam row of an image");
+  if (cudaError_t e = mega_launch_config(dec_search_mega_kernel<T>, a, cfg, attr, std::is_same<T, f16>::value ? 0 : 1)) return e;
+  cfg.stream = st;
+  return cudaLaunchKernelEx(&cfg, dec_search_mega_kernel<T>, a, q);
+}
+template cudaError_t launch_dec_search_mega<f16>(const MegaArgs&, const MegaSearch&, cudaStream_t);
+template cudaError_t launch_dec_search_mega<bf16>(const MegaArgs&, const MegaSearch&, cudaStream_t);
 template cudaError_t launch_dec_step_mega<f16>(const MegaArgs&, cudaStream_t);
 template cudaError_t launch_dec_step_mega<bf16>(const MegaArgs&, cudaStream_t);
 

@@ -146,9 +146,14 @@ struct xn_handle {
   int64_t use_graph = 1;
   int64_t op_out16 = 0;
   int64_t use_skinny = 1;
-  // 16-bit decoder positions as ONE persistent kernel per position (decode_mega.cu) instead of ~33 dependent launches;
-  // with fuse_topk the kernel also produces the log-softmax top-k of the 'max' beam search (logits never stored)
-  int64_t use_mega = 1, fuse_topk = 1;
+  // 16-bit decoder positions as ONE persistent cooperative kernel per position (decode_mega.cu) instead of ~33 dependent
+  // launches; with fuse_topk the kernel also produces the log-softmax top-k of the 'max' beam search (logits never
+  // stored).  OFF by default: measured on B200 it ties the per-operation path at 64 images x beam 3 (25.98 vs 26.14 ms per
+  // call) and at batch 1 (5.89 vs 5.93 ms), and loses where the decoder has many rows (config 3, 1280 rows: 26.9 vs 19.3 ms;
+  // config 4, 1536 rows: 199.6 vs 194.8 ms) -- its GEMM phases are mma.sync tiles, the per-operation path runs tcgen05
+  // there.  DESIGN.md section 5 has the phase timeline and the ncu evidence.
+  int64_t use_mega = 0, fuse_topk = 1;
+  int64_t mega_search = 0;            // 1: the whole 'max' beam search in one launch (measured slower than one persistent launch per position: decode_mega.cu)
   unsigned* mega_bar = nullptr;       // grid-barrier counter of the persistent kernel
   int64_t mega_dbg_mode = 0;
   unsigned long long* mega_dbg = nullptr;   // option "mega_dbg": phase timestamps of the last persistent-kernel launch
@@ -770,15 +775,14 @@ int dec_project_kv(xn_handle* h, DecBufs& D, const float* enc_out, int n_images,
   return lin_tc(h, e16, d, h->kv_all, nullptr, 0, nullptr, D.kv, h->kv_all.N, M, 0, std::is_same<T, f16>::value, st);
 }
 
-// one decoder position for all rows as ONE persistent kernel (16-bit modes; decode_mega.cu).  Returns 1 when the
+// Arguments of the persistent decoder kernels (decode_mega.cu) for this handle / decode buffers.  Returns 1 when the
 // geometry is not covered: the caller then runs the one-kernel-per-operation sequence.
-template <typename T>
-int dec_step_mega(xn_handle* h, DecBufs& D, int p, const int64_t* tok64, const int* tok32, long tok_stride,
-                  int rows_per_image, const int* n_valid, const int* row_len, float* logits, long ldl, cudaStream_t st) {
+int mega_build_args(xn_handle* h, DecBufs& D, int rows_per_image, const int* n_valid, const int* row_len, MegaArgs& a,
+                    cudaStream_t st = nullptr) {
   const xn_config& c = h->cfg;
-  if (!h->use_mega || h->profile || (int)h->dec.size() > kMegaMaxLayers) return 1;
-  MegaArgs a{};
-  a.s = D.s; a.p = p; a.n_layers = c.n_dec; a.d = c.d_model; a.ff = c.ff; a.n_exp = c.num_exp_dec; a.heads = c.num_heads;
+  if (!h->use_mega || (int)h->dec.size() > kMegaMaxLayers || c.ff % 512 || !D.mega_act) return 1;
+  a = MegaArgs{};
+  a.s = D.s; a.n_layers = c.n_dec; a.d = c.d_model; a.ff = c.ff; a.n_exp = c.num_exp_dec; a.heads = c.num_heads;
   a.n_keys = c.enc_len; a.vocab = c.vocab; a.R = D.R; a.rows_per_image = rows_per_image;
   for (int l = 0; l < c.n_dec; ++l) {
     const DecLayerW& W = h->dec[l];
@@ -789,7 +793,7 @@ int dec_step_mega(xn_handle* h, DecBufs& D, int p, const int64_t* tok64, const i
     m.b_dyn5 = W.dyn5.b; m.b_wq = W.wq.b; m.b_wo = W.wo.b; m.b_ff1 = W.ff1.b; m.b_ff2 = W.ff2.b;
     if (W.dyn5.N != 5 * c.d_model || W.dyn5.K != c.d_model || W.ff1.N != c.ff || W.ff2.K != c.ff) return 1;
   }
-  a.tok64 = tok64; a.tok32 = tok32; a.tok_stride = tok_stride; a.n_valid = n_valid; a.row_len = row_len;
+  a.n_valid = n_valid; a.row_len = row_len;
   a.emb = h->emb; a.pos = h->pos;
   a.x0 = D.x0; a.ycat = D.ycat; a.q = D.q; a.pre = D.pre;
   {
@@ -799,15 +803,33 @@ int dec_step_mega(xn_handle* h, DecBufs& D, int p, const int64_t* tok64, const i
   }
   a.kv = D.kv; a.ldkv = (long)c.n_dec * 2 * c.d_model;
   a.w_reduce = h->dec_reduce.wp; a.b_reduce = h->dec_reduce.b; a.ng = h->dec_ng; a.nb = h->dec_nb;
-  a.w_vocab = h->vocab.wp;
-  if (!a.w_reduce || !a.w_vocab || !D.mega_act) return 1; a.b_vocab = h->vocab.b;
-  a.logits = logits; a.ldl = ldl;
-  const bool fuse = h->fuse_topk && D.topk > 0 && D.topv && D.topi && D.parts;
-  a.topk = fuse ? D.topk : 0; a.parts = D.parts; a.top_val = D.topv; a.top_idx = D.topi;
+  a.w_vocab = h->vocab.wp; a.b_vocab = h->vocab.b;
+  if (!a.w_reduce || !a.w_vocab) return 1;
+  a.parts = D.parts;
   // fixed split factors (not chosen by row count): the summation order, hence every bit of the result, is independent of the batch
   a.ksplit_ff2 = c.ff / 512; a.ksplit_red = c.n_dec; a.scratch = D.mega_scratch;
-  a.bar = h->mega_bar; a.dbg = h->mega_dbg; a.dbg_mode = (int)h->mega_dbg_mode;
+  // decode groups run on their own streams: each gets its own barrier words, and one CTA per SM so that two groups' kernels
+  // are resident side by side (the phases are latency-bound: two interleaved chains fill the gaps)
+  int slot = 0;
+  for (int g = 0; g < xn_handle::kMaxDecodeGroups; ++g) if (st && st == h->dstream[g]) slot = g + 1;
+  for (int g = 0; g <= xn_handle::kMaxDecodeGroups; ++g) if (st && st == h->bstream[g]) slot = g;
+  a.bar = h->mega_bar + (size_t)slot * (kMegaBarBytes / sizeof(unsigned));
+  a.max_ctas_per_sm = slot > 0 ? 1 : 2;
+  a.dbg = slot <= 1 ? h->mega_dbg : nullptr; a.dbg_mode = (int)h->mega_dbg_mode;
   if (h->dec_reduce.K != c.d_model * c.n_dec || h->dec_reduce.N != c.d_model || h->vocab.K != c.d_model) return 1;
+  return 0;
+}
+
+// one decoder position for all rows as ONE persistent kernel (16-bit modes)
+template <typename T>
+int dec_step_mega(xn_handle* h, DecBufs& D, int p, const int64_t* tok64, const int* tok32, long tok_stride,
+                  int rows_per_image, const int* n_valid, const int* row_len, float* logits, long ldl, cudaStream_t st) {
+  MegaArgs a;
+  if (mega_build_args(h, D, rows_per_image, n_valid, row_len, a, st)) return 1;
+  a.p = p; a.tok64 = tok64; a.tok32 = tok32; a.tok_stride = tok_stride;
+  a.logits = logits; a.ldl = ldl;
+  const bool fuse = h->fuse_topk && D.topk > 0 && D.topv && D.topi && D.parts;
+  a.topk = fuse ? D.topk : 0; a.top_val = D.topv; a.top_idx = D.topi;
   if (!mega_supported(a)) return 1;
   KL(1, launch_dec_step_mega<T>(a, st));
   D.topk_done = fuse;
@@ -1061,6 +1083,24 @@ int beam_run(xn_handle* h, BeamPlan& P, const float* enc_out, int B, int beam, i
   // cross K/V of all decoder layers, once per image (shared by the beams)
   if (int r = dec_project(h, D, enc_out, B, st)) return r;
   KL(1, launch_beam_init(bb, B, beam, L, sos, st));
+  // 16-bit 'max' search on the covered geometry: ALL time steps in one persistent launch (decode_mega.cu); the early
+  // `break` of the reference is a branch inside the kernel
+  if (!smp.on && h->precision != XN_PREC_FP32 && h->mega_search && h->fuse_topk) {
+    MegaArgs a;
+    D.s.anc = bb.anc[0];
+    if (mega_build_args(h, D, beam, P.nv, nullptr, a, st) == 0) {
+      a.p = 0; a.tok32 = bb.tokens[0]; a.tok_stride = L;
+      a.topk = beam; a.top_val = P.topv; a.top_idx = P.topi;
+      MegaSearch q{};
+      q.bb = bb; q.beam = beam; q.L = L; q.eos = eos; q.how_many = how_many; q.early_exit = h->early_exit != 0;
+      q.r_tok = P.r_tok; q.r_len = P.r_len; q.r_lp = P.r_lp;
+      if (mega_supported(a)) {
+        if (h->precision == XN_PREC_FP16) KL(1, launch_dec_search_mega<f16>(a, q, st));
+        else KL(1, launch_dec_search_mega<bf16>(a, q, st));
+        return 0;
+      }
+    }
+  }
   int src = 0;
   // step 0: every beam row decodes [SOS]
   D.s.anc = bb.anc[0];
@@ -1223,7 +1263,8 @@ int xn_create(const xn_config* cfg, int device, xn_handle** out) {
   h->device = device;
   cudaSetDevice(device);
   if (cudaMalloc(&h->flag_dev, sizeof(int)) != cudaSuccess || cudaMemset(h->flag_dev, 0, sizeof(int)) != cudaSuccess ||
-      cudaMalloc(&h->mega_bar, kMegaBarBytes) != cudaSuccess || cudaMemset(h->mega_bar, 0, kMegaBarBytes) != cudaSuccess) {
+      cudaMalloc(&h->mega_bar, kMegaBarBytes * (xn_handle::kMaxDecodeGroups + 1)) != cudaSuccess ||
+      cudaMemset(h->mega_bar, 0, kMegaBarBytes * (xn_handle::kMaxDecodeGroups + 1)) != cudaSuccess) {
     g_create_error = "cudaMalloc failed";
     delete h;
     return XN_ERR_CUDA;
@@ -1631,7 +1672,7 @@ static int beam_search_impl(xn_handle* h, const float* input, const float* host_
   int G = (int)h->decode_groups;
   // measured at batch 64 (profiles/r2_quick_time_decode_groups.txt): 2 groups -0.6 ms, 4 groups +0.9 ms, 8 groups +3.8 ms --
   // beyond two chains the graph's kernel-node dispatch rate, not kernel latency, is the limit
-  if (G <= 0) G = (B >= 32 && !(h->use_mega && h->precision != XN_PREC_FP32)) ? 2 : 1;   // the persistent kernel fills the machine alone
+  if (G <= 0) G = B >= 32 ? 2 : 1;
   if (h->profile) G = 1;                                    // per-launch event timing wants one stream
   G = std::max(1, std::min(G, std::min(B, (int)xn_handle::kMaxDecodeGroups)));
   std::vector<BeamPlan> P(G);
@@ -2183,6 +2224,7 @@ int xn_set_option(xn_handle* h, const char* name, int64_t value) {
   if (n == "op_out16") { h->op_out16 = value; return XN_OK; }
   if (n == "use_skinny") { h->use_skinny = value; h->drop_graphs(); return XN_OK; }
   if (n == "use_mega") { h->use_mega = value; h->drop_graphs(); return XN_OK; }
+  if (n == "mega_search") { h->mega_search = value; h->drop_graphs(); return XN_OK; }
   if (n == "fuse_topk") { h->fuse_topk = value; h->drop_graphs(); return XN_OK; }
   if (n == "mega_dbg") {
     if (value && !h->mega_dbg) { if (cudaMalloc(&h->mega_dbg, 128 * 8) != cudaSuccess) return h->fail(XN_ERR_CUDA, "cudaMalloc failed"); cudaMemset(h->mega_dbg, 0, 128 * 8); }

@@ -180,6 +180,19 @@ template <typename KvT, typename OutT>
 cudaError_t launch_cross_attn_step(const float* q, long ldq, const KvT* kv, long ldkv, int k_off, int v_off,
                                    OutT* out, long ldo, int R, int rows_per_image, int n_keys, int heads, int dk,
                                    const int* n_valid, const int* row_len, int p, cudaStream_t st);
+// beam-search state (beam.cu); declared here because the persistent whole-search kernel takes it too
+struct BeamBufs {
+  int* tokens[2];     // (B, beam, L) ping-pong
+  float* lps[2];      // (B, beam, L)
+  int* len[2];        // (B, beam)
+  int* anc[2];        // (B*beam, L)   slot is local (0..beam-1) + b*beam
+  float* cum[2];      // (B, beam)     running sum of the history log-probs
+  int* eos[2];        // (B, beam)     history contains EOS
+  int* all_done;      // [1]
+  int* grew;          // [L]  grew[t] != 0: some beam was extended at time step t (else every beam had ended: the search is over)
+  int* final_src;     // [1]  ping-pong index holding the state after the last EXECUTED step (steps may be skipped, see engine.cu)
+};
+
 // ---------------------------------------------------------------- persistent whole-position decoder kernel (decode_mega.cu)
 // One launch = one decoder position for all rows (16-bit modes, d_model 512, head width 64): embedding, every decoder
 // layer, reduce group, final norm + vocabulary projection; with topk > 0 also log-softmax + top-k (the logits are then
@@ -206,6 +219,7 @@ struct MegaArgs {
   float* logits; long ldl;                    // topk == 0: logits out
   int topk; void* parts; float* top_val; int* top_idx;      // topk > 0: log-prob / index of the k best words per row
   unsigned* bar;                              // kMegaBarBytes: grid-barrier words + split-K tile counters (zeroed once; self-restoring)
+  int max_ctas_per_sm;                        // 0 / 2: two CTAs per SM; 1: one (two decode groups run two of these kernels side by side)
   int ksplit_ff2, ksplit_red; float* scratch; // split-K over CTAs of the two long-K projections (partial tiles in `scratch`)
   int dbg_mode;                               // timing experiments: bit 0 skip the MMAs, bit 1 skip the operand loads, bit 2 skip the LayerNorm fill
   unsigned long long* dbg;                    // optional: CTA 0 stores %globaltimer before / after every barrier (2 per phase)
@@ -219,6 +233,14 @@ size_t mega_act_bytes(int R, int ff, int n_layers);
 constexpr size_t kMegaBarBytes = 20 * 1024;
 template <typename T>
 cudaError_t launch_dec_step_mega(const MegaArgs& a, cudaStream_t st);
+// the whole 'max' beam search over an encoder output in one launch (time steps loop inside the kernel); `a` as for one
+// position with topk = beam, tokens / ancestry taken from bb (initialised by launch_beam_init)
+struct MegaSearch {
+  BeamBufs bb; int beam, L, eos, how_many, early_exit;
+  int* r_tok; int* r_len; float* r_lp;         // results as launch_beam_finalize writes them
+};
+template <typename T>
+cudaError_t launch_dec_search_mega(const MegaArgs& a, const MegaSearch& q, cudaStream_t st);
 extern int g_mega_coop;                       // 1: cooperative launch (default)
 
 // ensemble of up to kMaxEnsemble models: out = log(mean_m softmax(logits_m)) per row
@@ -253,17 +275,6 @@ struct PreItem {
 cudaError_t launch_preprocess_rgb8_batch(const PreItem* items_dev, int n, int max_h, int S, cudaStream_t st);
 
 // ---------------------------------------------------------------- beam search bookkeeping
-struct BeamBufs {
-  int* tokens[2];     // (B, beam, L) ping-pong
-  float* lps[2];      // (B, beam, L)
-  int* len[2];        // (B, beam)
-  int* anc[2];        // (B*beam, L)   slot is local (0..beam-1) + b*beam
-  float* cum[2];      // (B, beam)     running sum of the history log-probs
-  int* eos[2];        // (B, beam)     history contains EOS
-  int* all_done;      // [1]
-  int* grew;          // [L]  grew[t] != 0: some beam was extended at time step t (else every beam had ended: the search is over)
-  int* final_src;     // [1]  ping-pong index holding the state after the last EXECUTED step (steps may be skipped, see engine.cu)
-};
 // device-side early exit (CUDA-graph conditional nodes): sets the condition of the next step's IF node to grew[t] != 0
 cudaError_t launch_beam_set_condition(unsigned long long cond_handle, const int* grew_t, cudaStream_t st);
 cudaError_t launch_beam_init(const BeamBufs& bb, int B, int beam, int L, int sos, cudaStream_t st);

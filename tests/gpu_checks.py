@@ -992,3 +992,97 @@ def check_evaluate_model_loop() -> List[Triple]:
 
 
 ALL_FP32_MODEL_CASES = ["tiny_e2e_peaky", "tiny_e2e_xavier", "feat_peaky_b5", "feat_xavier_b1", "full_e2e_xavier", "full_e2e_peaky"]
+
+
+def check_mega_decoder(name: str = "full_e2e_peaky", precision: str = "fp16") -> List[Triple]:
+    """The persistent decoder-position kernel (csrc/decode_mega.cu, option use_mega=1) against the default
+    one-kernel-per-operation path (same 16-bit arithmetic, different tiling / summation order) and its fused log-softmax +
+    top-k against the separate kernel; also that the option really switches paths (launch counts)."""
+    e, g, cfg, sd, x, pads = engine_for(name, precision)
+    m = g["meta"]
+    out = []
+    with torch.no_grad():
+        enc = O.forward_enc(sd, cfg, x, pads)
+    tok = torch.from_numpy(g["dec_tokens"])
+    dp = g["dec_pads"].tolist()
+    try:
+        e.set_option("use_graph", 0)
+        e.set_option("use_mega", 1)
+        l0 = e.kernel_launches
+        lg_mega = e.forward_dec(enc, pads, tok, dp, False).cpu()
+        n_mega = e.kernel_launches - l0
+        cap_fused = unpack_beam_results(*e.beam_search(x, pads, m["sos"], m["eos"], m["beam"], m["how_many"], m["max_len"]))
+        e.set_option("fuse_topk", 0)
+        cap_unfused = unpack_beam_results(*e.beam_search(x, pads, m["sos"], m["eos"], m["beam"], m["how_many"], m["max_len"]))
+        e.set_option("fuse_topk", 1)
+        e.set_option("use_mega", 0)
+        l0 = e.kernel_launches
+        lg_ops = e.forward_dec(enc, pads, tok, dp, False).cpu()
+        n_ops = e.kernel_launches - l0
+        cap_ops = unpack_beam_results(*e.beam_search(x, pads, m["sos"], m["eos"], m["beam"], m["how_many"], m["max_len"]))
+    finally:
+        e.set_option("use_mega", 0)
+        e.set_option("fuse_topk", 1)
+        e.set_option("use_graph", 1)
+    t = tok.shape[1]
+    # one launch per position (+ the cross K/V projection and its cast) against ~33 per position
+    out.append((f"{name}/{precision} persistent path: launches of a {t}-position teacher-forced decode ({n_mega} vs {n_ops} per-operation)",
+                float(n_mega), float(t + 8)))
+    out.append((f"{name}/{precision} persistent vs per-operation logits rel-max", rel_max(lg_mega, lg_ops), 2e-3))
+    out.append((f"{name}/{precision} fused top-k: caption tokens differing from the separate log-softmax/top-k kernel",
+                float(sum(a != b for a, b in zip(cap_fused[0], cap_unfused[0]))), 0.0))
+    if tuple(cap_fused[1].shape) == tuple(cap_unfused[1].shape):
+        out.append((f"{name}/{precision} fused top-k: caption log-probs vs the separate kernel max-abs",
+                    float((cap_fused[1] - cap_unfused[1]).abs().max()), 2e-5))
+    out.append((f"{name}/{precision} persistent vs per-operation caption tokens differing (informational)",
+                float(sum(a != b for a, b in zip(cap_fused[0], cap_ops[0]))), float("inf")))
+    return out
+
+
+def check_mega_timeline() -> List[Triple]:
+    """xn_mega_timeline: CTA 0's %globaltimer stamps of the last persistent-kernel launch are complete and ordered."""
+    e, g, cfg, sd, x, pads = engine_for("full_e2e_peaky", "fp16")
+    m = g["meta"]
+    try:
+        e.set_option("use_mega", 1)
+        e.set_option("mega_dbg", 1)
+        e.beam_search(x, pads, m["sos"], m["eos"], m["beam"], m["how_many"], m["max_len"])
+        t = e.mega_timeline()
+    finally:
+        e.set_option("mega_dbg", 0)
+        e.set_option("use_mega", 0)
+    n_expected = 2 * (7 * cfg.n_dec + 2) + 2          # start, (before, after) per barrier, end
+    out = [("mega timeline: stamps missing", float(abs(len(t) - n_expected)), 0.0),
+           ("mega timeline: stamps out of order", float(sum(b < a for a, b in zip(t, t[1:]))), 0.0)]
+    if len(t) > 1:
+        out.append(("mega timeline: kernel longer than 5 ms", float(t[-1] - t[0]) * 1e-6, 5.0))
+    return out
+
+
+def check_mega_search(name: str = "full_e2e_peaky", precision: str = "fp16") -> List[Triple]:
+    """Option mega_search=1 (all time steps of the 'max' search in one launch, bookkeeping and early exit inside the kernel)
+    gives the captions of the default one-launch-per-position path."""
+    e, g, cfg, sd, x, pads = engine_for(name, precision)
+    m = g["meta"]
+    args = (x, pads, m["sos"], m["eos"], m["beam"], m["how_many"], m["max_len"])
+    e.set_option("use_mega", 1)
+    ref = unpack_beam_results(*e.beam_search(*args))
+    try:
+        e.set_option("mega_search", 1)
+        l0 = e.kernel_launches
+        e.set_option("use_graph", 0)
+        got = unpack_beam_results(*e.beam_search(*args))
+        e.set_option("use_graph", 1)
+        for _ in range(3):
+            got_g = unpack_beam_results(*e.beam_search(*args))
+    finally:
+        e.set_option("mega_search", 0)
+        e.set_option("use_mega", 0)
+        e.set_option("use_graph", 1)
+    out = [(f"{name}/{precision} whole-search kernel: caption tokens differing from the per-position path",
+            float(sum(a != b for a, b in zip(got[0], ref[0]))), 0.0),
+           (f"{name}/{precision} whole-search kernel (graph replay): caption tokens differing",
+            float(sum(a != b for a, b in zip(got_g[0], ref[0]))), 0.0)]
+    if tuple(got[1].shape) == tuple(ref[1].shape):
+        out.append((f"{name}/{precision} whole-search kernel: caption log-probs max-abs diff", float((got[1] - ref[1]).abs().max()), 1e-6))
+    return out

@@ -260,3 +260,25 @@ def test_device_side_early_exit():
     """reference captioning_model.py:397: stop decoding when every beam has ended -- as graph IF nodes on the device."""
     import gpu_checks as G
     _assert(G.check_early_exit())
+
+
+@pytest.mark.parametrize("precision", ["fp16", "bf16"])
+def test_persistent_decoder_kernel_vs_per_operation_path(precision):
+    import gpu_checks as G
+    _assert(G.check_mega_decoder("full_e2e_peaky", precision))
+
+
+def test_persistent_decoder_kernel_features_in_model_with_pads():
+    """features-in model: encoder pads (n_valid) and decoder pads (row_len) through the persistent kernel"""
+    import gpu_checks as G
+    _assert(G.check_mega_decoder("feat_peaky_b5", "fp16"))
+
+
+def test_persistent_decoder_kernel_timeline_hook():
+    import gpu_checks as G
+    _assert(G.check_mega_timeline())
+
+
+def test_whole_search_kernel_option():
+    import gpu_checks as G
+    _assert(G.check_mega_search())

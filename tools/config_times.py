@@ -19,14 +19,20 @@ def timeit(fn, n=10, warm=3):
     return a.elapsed_time(b) / n
 
 prec = sys.argv[1] if len(sys.argv) > 1 else "fp16"
+OPTS = {o: int(os.environ["XNV2_" + o.upper()]) for o in ("use_mega", "mega_search", "fuse_topk", "decode_groups") if os.environ.get("XNV2_" + o.upper()) is not None}
+print("options:", OPTS, flush=True)
 cfg3 = C.features_only()
-e3 = Engine(cfg3, 0); e3.load_state_dict(synth.make_state_dict(cfg3, 0, "xavier"), prec)
+e3 = Engine(cfg3, 0)
+for o, v in OPTS.items(): e3.set_option(o, v)
+e3.load_state_dict(synth.make_state_dict(cfg3, 0, "xavier"), prec)
 f = synth.make_features(cfg3, 256, 1).cuda()
 ms = timeit(lambda: e3.beam_search(f, [0] * 256, 79, 77, 5, 1, 20))
 print(f"C3 {prec} features-in B=256 beam 5 max_len 20: {ms:.2f} ms -> {256 / ms * 1e3:.0f} captions/s", flush=True)
 e3.close()
 cfg = C.swin_l_384()
-e = Engine(cfg, 0); e.load_state_dict(synth.make_state_dict(cfg, 0, "xavier"), prec)
+e = Engine(cfg, 0)
+for o, v in OPTS.items(): e.set_option(o, v)
+e.load_state_dict(synth.make_state_dict(cfg, 0, "xavier"), prec)
 x = synth.make_images(cfg, 512, 1, "randn").cuda()
 ms = timeit(lambda: e.beam_search(x, None, 79, 77, 3, 1, 20), n=5)
 print(f"C4 {prec} end-to-end B=512 beam 3 max_len 20 (per-GPU shape): {ms:.1f} ms -> {512 / ms * 1e3:.0f} captions/s, workspace {e.workspace_bytes / 2**30:.2f} GiB", flush=True)

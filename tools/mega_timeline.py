@@ -7,7 +7,7 @@ import torch
 from on_device_image_captioning_b200 import config as C, synth
 from on_device_image_captioning_b200.engine import Engine
 
-PHASES = [f"L{l}.{n}" for l in range(3) for n in ("dyn5", "dynexp", "wq", "cross", "wo", "ff1", "ff2")] + ["reduce", "vocab", "merge"]
+PHASES = [f"L{l}.{n}" for l in range(3) for n in ("dyn5", "dynexp", "wq", "cross", "wo", "ff1", "ff2")] + ["reduce", "vocab", "merge+beam", "(finalise)"]
 
 def main():
     B = int(sys.argv[1]) if len(sys.argv) > 1 else 64
@@ -17,7 +17,8 @@ def main():
     x = synth.make_images(cfg, B, 1, "randn").cuda()
     e = Engine(cfg, 0)
     e.load_state_dict(sd, "fp16")
-    for opt in ("fuse_topk", "mega_coop", "mega_dbg_mode"):
+    e.set_option("use_mega", 1)
+    for opt in ("fuse_topk", "mega_coop", "mega_dbg_mode", "mega_search", "early_exit"):
         if os.environ.get("XNV2_" + opt.upper()) is not None:
             e.set_option(opt, int(os.environ["XNV2_" + opt.upper()]))
     enc = e.forward_enc(x)

@@ -13,6 +13,7 @@ sd = synth.make_state_dict(cfg, 0, "xavier")
 x = synth.make_images(cfg, B, 1, "randn").cuda()
 e = Engine(cfg, 0)
 e.load_state_dict(sd, "fp16")
+e.set_option("use_mega", 1)
 e.set_option("use_graph", 0)
 enc = e.forward_enc(x)
 for _ in range(4):
