@@ -190,7 +190,8 @@ int64_t xn_workspace_bytes(const xn_handle* h);
  *   "pdl"                      programmatic dependent launch (process-wide)
  *   "tc_pair"                  CTA-pair (cta_group::2) GEMM tiles for long-K shapes (process-wide)
  *   "use_skinny"               skinny mma.sync GEMM for decoder-step linears with <= 64 rows
- *   "ln_fuse"                  Swin norm1 / norm2 folded algebraically into the neighbouring tcgen05 GEMMs (default 1, 16-bit modes)
+ *   "ln_fuse"                  Swin norm1 / norm2 folded algebraically into the neighbouring tcgen05 GEMMs (16-bit modes): 1 = all but
+ *                              each stage's first norm1, 2 (default) = those too (produced by the patch embedding / merge GEMM)
  *   "ln_on_load"               decoder-step LayerNorm computed inside the consuming tcgen05 GEMM (off: measured slower)
  *   "use_mega"                 1: every decoder position of the 16-bit modes (d_model 512, head width 64, <= 20 positions,
  *                              16 expansion vectors) runs as ONE persistent cooperative kernel with grid barriers between its

@@ -291,10 +291,15 @@ __global__ void __launch_bounds__(256) patch_embed_kernel(const float* __restric
 // registers (the generic kernel above issues 10 loads per 24 FMAs and re-transposes the filter bank in every CTA).
 constexpr int kPe4Patches = 6;
 
+// x16 != nullptr (16-bit modes, folded LayerNorm): the kernel is also the PRODUCER of the first Swin block's norm1 -- it
+// writes the rows rounded to 16 bits and their sum / sum of squares in the 64-bit fixed-point format of the tcgen05
+// GEMM's producer epilogue (gemm_tcgen05.cu), so the first qkv GEMM runs against the folded weights like every other
+// block and the stage-1 LayerNorm launch (the largest one: 453 MB read) disappears.
 __global__ void __launch_bounds__(256) patch_embed4_kernel(const float* __restrict__ img, const float4* __restrict__ wq,
                                                            const float* __restrict__ bias, const float* __restrict__ g,
                                                            const float* __restrict__ be, float* __restrict__ out,
-                                                           int Cin, int S, int E) {
+                                                           int Cin, int S, int E, void* __restrict__ x16, int fp16,
+                                                           unsigned long long* __restrict__ stats) {
   pdl_wait();
   pdl_trigger();
   extern __shared__ float4 sm4[];
@@ -357,10 +362,29 @@ __global__ void __launch_bounds__(256) patch_embed4_kernel(const float* __restri
 #pragma unroll
         for (int j = 0; j < 8; ++j) if (j < EP) { const float dd = acc[q][j] - mean; qv += dd * dd; }
         const float rstd = 1.0f / sqrtf(warp_sum(qv) / (float)E + kLnEps);
-        float* o = out + (((long)b * G + py) * G + px) * E;
+        const long row = ((long)b * G + py) * G + px;
+        float* o = out + row * E;
+        float ys = 0.f, yq = 0.f;
 #pragma unroll
         for (int j = 0; j < 8; ++j)
-          if (j < EP) o[lane + 32 * j] = (acc[q][j] - mean) * rstd * gam[j] + bet[j];
+          if (j < EP) {
+            const float y = (acc[q][j] - mean) * rstd * gam[j] + bet[j];
+            o[lane + 32 * j] = y;
+            if (x16) {
+              ys += y; yq = fmaf(y, y, yq);
+              if (fp16) reinterpret_cast<__half*>(x16)[row * E + lane + 32 * j] = __float2half_rn(y);
+              else reinterpret_cast<__nv_bfloat16*>(x16)[row * E + lane + 32 * j] = __float2bfloat16_rn(y);
+            }
+          }
+        if (x16) {                                  // integer adds: the statistics do not depend on the reduction order
+          long long s_sum = __float2ll_rn(ys * 16777216.0f), s_sq = __float2ll_rn(yq * 65536.0f);
+#pragma unroll
+          for (int o2 = 16; o2 > 0; o2 >>= 1) {
+            s_sum += __shfl_xor_sync(0xffffffffu, s_sum, o2);
+            s_sq += __shfl_xor_sync(0xffffffffu, s_sq, o2);
+          }
+          if (lane == 0) { stats[2 * row] = (unsigned long long)s_sum; stats[2 * row + 1] = (unsigned long long)s_sq; }
+        }
       }
     }
   }
@@ -379,7 +403,7 @@ cudaError_t launch_patch_filter_pack4(const float* w, float* wq, int Cin, int E,
 }
 
 cudaError_t launch_patch_embed4(const float* img, const float* wq, const float* b, const float* gamma, const float* beta,
-                                float* out, int B, int Cin, int S, int E, cudaStream_t st) {
+                                float* out, int B, int Cin, int S, int E, cudaStream_t st, void* x16, int fp16, float* stats) {
   if (E % 32 || E > 256 || S % 16) return cudaErrorInvalidValue;
   const int G = S / 4;
   const size_t smem = ((size_t)Cin * 4 * G + (size_t)Cin * 4 * E) * sizeof(float4);
@@ -387,7 +411,7 @@ cudaError_t launch_patch_embed4(const float* img, const float* wq, const float* 
   if (cudaError_t e = ensure_dyn_smem(patch_embed4_kernel, smem, smem_state)) return e;
   const int groups = (G + kPeRows - 1) / kPeRows;
   return launch_k(patch_embed4_kernel, dim3(B * groups), dim3(256), smem, st, img, reinterpret_cast<const float4*>(wq), b, gamma, beta,
-                  out, Cin, S, E);
+                  out, Cin, S, E, x16, fp16, reinterpret_cast<unsigned long long*>(stats));
 }
 
 cudaError_t launch_patch_embed(const float* img, const float* w, const float* b, const float* gamma,

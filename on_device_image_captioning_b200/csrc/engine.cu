@@ -162,7 +162,7 @@ struct xn_handle {
   // in-kernel normalisation sits on the critical path in front of the first MMA; 64-image call 29.5 vs 28.8 ms), so it
   // is off by default (profiles/r2_decoder_gemm_ln_on_load.txt).
   int64_t ln_on_load = 0;
-  int64_t ln_fuse = 1;                // Swin norm1 / norm2 folded into the neighbouring tcgen05 GEMMs (16-bit modes)
+  int64_t ln_fuse = 2;                // Swin norm1 / norm2 folded into the neighbouring tcgen05 GEMMs (16-bit modes); 2: also each stage's first norm1 (produced by the patch embedding / patch-merging reduction)
   // the decoder step is a chain of latency-bound kernels that fills a fraction of the machine: the batch is decoded as
   // up to kMaxDecodeGroups independent image groups on concurrent streams (parallel branches of the captured graph)
   static constexpr int kMaxDecodeGroups = 8;
@@ -410,9 +410,17 @@ int swin_forward_chunk(xn_handle* h, const float* img, int Bc, float* out, cudaS
   // carry gamma, are centred along K (the mean drops out) and scales its accumulator rows by 1/std.  Per block that
   // deletes two LayerNorm launches and the second read of the fp32 residual stream.
   const bool fuse = !std::is_same<T, float>::value && h->ln_fuse != 0;
-  if (h->pe_wq) KL(1, launch_patch_embed4(img, h->pe_wq, h->pe_b, h->pe_g, h->pe_beta, x, Bc, c.in_chans, c.img_size, c.embed_dim, st));
-  else KL(1, launch_patch_embed(img, h->pe_w, h->pe_b, h->pe_g, h->pe_beta, x, Bc, c.in_chans, c.img_size, c.patch_size,
-                                c.embed_dim, st));
+  // The producers of a stage's FIRST norm1 are the patch embedding (stage 1) and the patch-merging reduction (later
+  // stages): they emit the raw 16-bit rows and the row statistics too, so no LayerNorm launch is left in front of a qkv
+  // GEMM (option "ln_fuse" >= 2, the default).  The raw rows of a stage's first block live in `ao` (the merge reads `xn`).
+  const bool fuse_first = fuse && h->ln_fuse >= 2 && (c.embed_dim % 16 == 0);
+  bool first_x16 = false;
+  if (h->pe_wq) {
+    first_x16 = fuse_first;
+    KL(1, launch_patch_embed4(img, h->pe_wq, h->pe_b, h->pe_g, h->pe_beta, x, Bc, c.in_chans, c.img_size, c.embed_dim, st,
+                              first_x16 ? (void*)ao : nullptr, std::is_same<T, f16>::value, first_x16 ? stats : nullptr));
+  } else KL(1, launch_patch_embed(img, h->pe_w, h->pe_b, h->pe_g, h->pe_beta, x, Bc, c.in_chans, c.img_size, c.patch_size,
+                                  c.embed_dim, st));
   for (size_t si = 0; si < h->stages.size(); ++si) {
     const SwinStageW& S = h->stages[si];
     const int C = S.C, H = S.H, M = Bc * H * H;
@@ -422,7 +430,9 @@ int swin_forward_chunk(xn_handle* h, const float* img, int Bc, float* out, cudaS
       const int shift = (bi % 2 == 1 && H > c.window_size) ? c.window_size / 2 : 0;
       LnFuse consume; consume.ln_stats = stats; consume.ln_k = C;
       LnFuse produce; produce.stats_out = stats; produce.x16_out = xn; produce.ldx16 = C;
-      if (fuse && have_x16) {
+      if (fuse && bi == 0 && first_x16) {
+        if (int r = ActOps<T>::lin_act(h, ao, C, W.qkv_ln, qkv, 3 * C, M, 0, st, &consume)) return r;
+      } else if (fuse && have_x16) {
         if (int r = ActOps<T>::lin_act(h, xn, C, W.qkv_ln, qkv, 3 * C, M, 0, st, &consume)) return r;
       } else {
         KL(1, swin_layernorm<T>(x, C, W.n1g, W.n1b, xn, C, M, C, st));
@@ -449,7 +459,12 @@ int swin_forward_chunk(xn_handle* h, const float* img, int Bc, float* out, cudaS
     if (S.has_merge) {
       const int M4 = Bc * (H / 2) * (H / 2);
       KL(1, launch_merge_layernorm<T>(x, S.mg, S.mb, xn, Bc, H, C, st));     // xn viewed as (M4, 4C)
-      if (int r = ActOps<T>::lin_res(h, xn, 4 * C, S.red, nullptr, 0, x2, 2 * C, M4, st)) return r;
+      first_x16 = fuse_first && ((2 * C) % 16 == 0);
+      if (first_x16) {
+        LnFuse produce; produce.stats_out = stats; produce.x16_out = ao; produce.ldx16 = 2 * C;
+        CU(cudaMemsetAsync(stats, 0, (size_t)M4 * 2 * sizeof(long long), st));
+        if (int r = ActOps<T>::lin_res(h, xn, 4 * C, S.red, nullptr, 0, x2, 2 * C, M4, st, &produce)) return r;
+      } else if (int r = ActOps<T>::lin_res(h, xn, 4 * C, S.red, nullptr, 0, x2, 2 * C, M4, st)) return r;
       std::swap(x, x2);
     }
   }

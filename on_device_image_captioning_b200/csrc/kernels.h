@@ -114,8 +114,11 @@ cudaError_t launch_patch_embed(const float* img, const float* w, const float* b,
                                cudaStream_t st);
 // patch width 4: filter bank pre-packed by launch_patch_filter_pack4 into float4-over-dx rows
 cudaError_t launch_patch_filter_pack4(const float* w, float* wq, int Cin, int E, cudaStream_t st);
+// x16 / stats != nullptr: also the raw rows in 16 bits and their 64-bit fixed-point sum / sum of squares (producer of the
+// first block's folded norm1, see TcGemmArgs::stats_out)
 cudaError_t launch_patch_embed4(const float* img, const float* wq, const float* b, const float* gamma, const float* beta,
-                                float* out, int B, int Cin, int S, int E, cudaStream_t st);
+                                float* out, int B, int Cin, int S, int E, cudaStream_t st, void* x16 = nullptr, int fp16 = 0,
+                                float* stats = nullptr);
 template <typename T>
 cudaError_t launch_cast(const float* x, T* y, long n, cudaStream_t st);
 
