@@ -46,7 +46,7 @@ struct SwinBlockW {
   LinW qkv_ln, fc1_ln;      // norm1 / norm2 folded into the weights (16-bit modes; kernels.h: TcGemmArgs::ln_stats)
 };
 // folded-LayerNorm hooks of one tcgen05 GEMM launch (producer and / or consumer side)
-struct LnFuse { float* stats_out = nullptr; void* x16_out = nullptr; long ldx16 = 0; const float* ln_stats = nullptr; int ln_k = 0; };
+struct LnFuse { float* stats_out = nullptr; void* x16_out = nullptr; long ldx16 = 0; const float* ln_stats = nullptr; int ln_k = 0; float* stats_zero = nullptr; };
 struct SwinStageW {
   int C, H, heads;
   std::vector<SwinBlockW> blocks;
@@ -311,7 +311,7 @@ int lin_tc(xn_handle* h, const void* x, long ldx, const LinW& w, const float* re
            long ldy, int M, int act, int fp16, cudaStream_t st, int w_static = 1, const float* a32 = nullptr, long lda32 = 0,
            const float* ln_g = nullptr, const float* ln_b = nullptr, const LnFuse* lf = nullptr) {
   TcGemmArgs g{};
-  if (lf) { g.stats_out = lf->stats_out; g.x16_out = lf->x16_out; g.ldx16 = lf->ldx16; g.ln_stats = lf->ln_stats; g.ln_k = lf->ln_k; }
+  if (lf) { g.stats_out = lf->stats_out; g.x16_out = lf->x16_out; g.ldx16 = lf->ldx16; g.ln_stats = lf->ln_stats; g.ln_k = lf->ln_k; g.stats_zero = lf->stats_zero; }
   g.w_static = w_static;
   g.a32 = a32; g.lda32 = lda32; g.ln_g = ln_g; g.ln_b = ln_b;        // LayerNorm-on-load (x is then unused)
   g.A = x; g.lda = ldx; g.W = w.wb; g.ldw = w.K; g.Cf = yf; g.Cb = yb; g.ldc = ldy; g.fp16 = fp16;
@@ -380,8 +380,8 @@ size_t swin_ws_bytes(const xn_config& c, int Bc, int prec) {
   b += 3 * tok * act;                                 // qkv
   b += tok * act;                                     // attention out
   b += (size_t)(c.mlp_ratio * tok) * act + 4096;      // mlp hidden
-  b += (size_t)Bc * L0 * 2 * 8;                         // per-row LayerNorm statistics (sum, sum of squares; 64-bit fixed point)
-  return b + 16 * 256;
+  b += 2 * (size_t)Bc * L0 * 2 * 8;                     // per-row LayerNorm statistics (sum, sum of squares; 64-bit fixed point), norm1 and norm2
+  return b + 17 * 256;
 }
 
 // the Swin LayerNorms under their own launcher name, so that the per-launcher profile (xn_profile_kernels) separates the
@@ -402,7 +402,8 @@ int swin_forward_chunk(xn_handle* h, const float* img, int Bc, float* out, cudaS
   T* qkv = h->ws.get<T>(3 * tok0);
   T* ao = h->ws.get<T>(tok0);
   T* hid = h->ws.get<T>((size_t)(c.mlp_ratio * tok0) + 1024);
-  float* stats = h->ws.get<float>((size_t)Bc * G * G * 4);      // (M x 2 64-bit fixed-point sums)
+  float* stats = h->ws.get<float>((size_t)Bc * G * G * 4);      // (M x 2 64-bit fixed-point sums): norm1 statistics
+  float* stats2 = h->ws.get<float>((size_t)Bc * G * G * 4);     // the same for norm2 (two buffers: see `alt` below)
   WS_CHECK();
   // 16-bit modes: norm1 / norm2 are folded into the GEMMs around them (option "ln_fuse").  The GEMM that produces the
   // residual stream (proj, fc2) also writes the raw rows in 16 bits into `xn` and their sum / sum of squares into `stats`;
@@ -414,11 +415,18 @@ int swin_forward_chunk(xn_handle* h, const float* img, int Bc, float* out, cudaS
   // stages): they emit the raw 16-bit rows and the row statistics too, so no LayerNorm launch is left in front of a qkv
   // GEMM (option "ln_fuse" >= 2, the default).  The raw rows of a stage's first block live in `ao` (the merge reads `xn`).
   const bool fuse_first = fuse && h->ln_fuse >= 2 && (c.embed_dim % 16 == 0);
+  // `alt`: the statistics of norm1 (fc2 / patch embedding / merge -> qkv) and of norm2 (proj -> fc1) live in two buffers,
+  // and each is cleared for its next producer by the GEMM that runs after its consumer (proj clears the norm1 buffer,
+  // fc2 the norm2 buffer: TcGemmArgs::stats_zero) -- no memset node between the kernels of a block.
+  const bool alt = fuse_first;
+  float* st1 = stats;
+  float* st2 = alt ? stats2 : stats;
+  if (alt) CU(cudaMemsetAsync(st2, 0, (size_t)Bc * G * G * 2 * sizeof(long long), st));
   bool first_x16 = false;
   if (h->pe_wq) {
     first_x16 = fuse_first;
     KL(1, launch_patch_embed4(img, h->pe_wq, h->pe_b, h->pe_g, h->pe_beta, x, Bc, c.in_chans, c.img_size, c.embed_dim, st,
-                              first_x16 ? (void*)ao : nullptr, std::is_same<T, f16>::value, first_x16 ? stats : nullptr));
+                              first_x16 ? (void*)ao : nullptr, std::is_same<T, f16>::value, first_x16 ? st1 : nullptr));
   } else KL(1, launch_patch_embed(img, h->pe_w, h->pe_b, h->pe_g, h->pe_beta, x, Bc, c.in_chans, c.img_size, c.patch_size,
                                   c.embed_dim, st));
   for (size_t si = 0; si < h->stages.size(); ++si) {
@@ -428,21 +436,23 @@ int swin_forward_chunk(xn_handle* h, const float* img, int Bc, float* out, cudaS
     for (size_t bi = 0; bi < S.blocks.size(); ++bi) {
       const SwinBlockW& W = S.blocks[bi];
       const int shift = (bi % 2 == 1 && H > c.window_size) ? c.window_size / 2 : 0;
-      LnFuse consume; consume.ln_stats = stats; consume.ln_k = C;
-      LnFuse produce; produce.stats_out = stats; produce.x16_out = xn; produce.ldx16 = C;
+      LnFuse consume1; consume1.ln_stats = st1; consume1.ln_k = C;
+      LnFuse consume2; consume2.ln_stats = st2; consume2.ln_k = C;
+      LnFuse produce2; produce2.stats_out = st2; produce2.x16_out = xn; produce2.ldx16 = C; produce2.stats_zero = alt ? st1 : nullptr;
+      LnFuse produce1; produce1.stats_out = st1; produce1.x16_out = xn; produce1.ldx16 = C; produce1.stats_zero = alt ? st2 : nullptr;
       if (fuse && bi == 0 && first_x16) {
-        if (int r = ActOps<T>::lin_act(h, ao, C, W.qkv_ln, qkv, 3 * C, M, 0, st, &consume)) return r;
+        if (int r = ActOps<T>::lin_act(h, ao, C, W.qkv_ln, qkv, 3 * C, M, 0, st, &consume1)) return r;
       } else if (fuse && have_x16) {
-        if (int r = ActOps<T>::lin_act(h, xn, C, W.qkv_ln, qkv, 3 * C, M, 0, st, &consume)) return r;
+        if (int r = ActOps<T>::lin_act(h, xn, C, W.qkv_ln, qkv, 3 * C, M, 0, st, &consume1)) return r;
       } else {
         KL(1, swin_layernorm<T>(x, C, W.n1g, W.n1b, xn, C, M, C, st));
         if (int r = ActOps<T>::lin_act(h, xn, C, W.qkv, qkv, 3 * C, M, 0, st)) return r;
       }
       KL(1, ActOps<T>::attn(qkv, std::is_same<T, float>::value ? W.rpb : W.rpb_t, ao, Bc, H, C, S.heads, shift, st));
       if (fuse) {
-        CU(cudaMemsetAsync(stats, 0, (size_t)M * 2 * sizeof(long long), st));
-        if (int r = ActOps<T>::lin_res(h, ao, C, W.proj, x, C, x, C, M, st, &produce)) return r;
-        if (int r = ActOps<T>::lin_act(h, xn, C, W.fc1_ln, hid, W.fc1.N, M, 1, st, &consume)) return r;
+        if (!alt) CU(cudaMemsetAsync(st2, 0, (size_t)M * 2 * sizeof(long long), st));
+        if (int r = ActOps<T>::lin_res(h, ao, C, W.proj, x, C, x, C, M, st, &produce2)) return r;
+        if (int r = ActOps<T>::lin_act(h, xn, C, W.fc1_ln, hid, W.fc1.N, M, 1, st, &consume2)) return r;
       } else {
         if (int r = ActOps<T>::lin_res(h, ao, C, W.proj, x, C, x, C, M, st)) return r;
         KL(1, swin_layernorm<T>(x, C, W.n2g, W.n2b, xn, C, M, C, st));
@@ -450,8 +460,11 @@ int swin_forward_chunk(xn_handle* h, const float* img, int Bc, float* out, cudaS
       }
       have_x16 = fuse && bi + 1 < S.blocks.size();          // the last block of a stage feeds the merge / final norm (fp32)
       if (have_x16) {
-        CU(cudaMemsetAsync(stats, 0, (size_t)M * 2 * sizeof(long long), st));
-        if (int r = ActOps<T>::lin_res(h, hid, W.fc1.N, W.fc2, x, C, x, C, M, st, &produce)) return r;
+        if (!alt) CU(cudaMemsetAsync(st1, 0, (size_t)M * 2 * sizeof(long long), st));
+        if (int r = ActOps<T>::lin_res(h, hid, W.fc1.N, W.fc2, x, C, x, C, M, st, &produce1)) return r;
+      } else if (alt) {
+        LnFuse clear2; clear2.stats_zero = st2;              // not a producer, but the norm2 buffer still has to be cleared
+        if (int r = ActOps<T>::lin_res(h, hid, W.fc1.N, W.fc2, x, C, x, C, M, st, &clear2)) return r;
       } else {
         if (int r = ActOps<T>::lin_res(h, hid, W.fc1.N, W.fc2, x, C, x, C, M, st)) return r;
       }
@@ -461,8 +474,8 @@ int swin_forward_chunk(xn_handle* h, const float* img, int Bc, float* out, cudaS
       KL(1, launch_merge_layernorm<T>(x, S.mg, S.mb, xn, Bc, H, C, st));     // xn viewed as (M4, 4C)
       first_x16 = fuse_first && ((2 * C) % 16 == 0);
       if (first_x16) {
-        LnFuse produce; produce.stats_out = stats; produce.x16_out = ao; produce.ldx16 = 2 * C;
-        CU(cudaMemsetAsync(stats, 0, (size_t)M4 * 2 * sizeof(long long), st));
+        // the norm1 buffer is clear here: the stage's last proj cleared it and its last fc2 produced nothing
+        LnFuse produce; produce.stats_out = st1; produce.x16_out = ao; produce.ldx16 = 2 * C;
         if (int r = ActOps<T>::lin_res(h, xn, 4 * C, S.red, nullptr, 0, x2, 2 * C, M4, st, &produce)) return r;
       } else if (int r = ActOps<T>::lin_res(h, xn, 4 * C, S.red, nullptr, 0, x2, 2 * C, M4, st)) return r;
       std::swap(x, x2);

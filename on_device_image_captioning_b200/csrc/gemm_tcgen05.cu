@@ -59,6 +59,7 @@ struct TcEpilogue {
   int w_static;        // weight tiles may be loaded before the dependency wait
   const float* a32; long lda32; const float* ln_g; const float* ln_b;   // LayerNorm-on-load source of A (or nullptr)
   float* stats_out; void* x16_out; long ldx16;                          // producer side of the folded LayerNorm (fp32 output path)
+  float* stats_zero;                                                    // the OTHER statistics buffer: its rows are zeroed here (fp32 output path)
   const float* ln_stats; float ln_inv_k;                                // consumer side (16-bit output path)
   int use_tma_store;   // 16-bit output without residual: write through TMA (needs ldc % 8 == 0)
   int dbg;     // timing experiments only: 1 = skip the epilogue's global traffic, 2 = skip MMA issue, 4 = skip TMA loads
@@ -632,6 +633,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             atomicAdd(so, (unsigned long long)st_sum);
             atomicAdd(so + 1, (unsigned long long)st_sq);
           }
+          // The two statistics buffers of a Swin block alternate (proj -> fc1 uses one, fc2 -> next qkv the other); the
+          // GEMM that runs after a buffer's consumer clears it for its next producer, so no memset node sits between the
+          // kernels of a block (a memset also breaks the programmatic dependent launch chain).  First column tile only.
+          if (ep.stats_zero && col_base == 0 && my_row < M)
+            *reinterpret_cast<ulonglong2*>(reinterpret_cast<unsigned long long*>(ep.stats_zero) + 2 * (long)my_row) = make_ulonglong2(0ull, 0ull);
         }
         tc_fence_before();
         __syncwarp();
@@ -865,11 +871,12 @@ static cudaError_t launch_tc(const TcGemmArgs& p, cudaStream_t st) {
     }
   }
   // the folded-LayerNorm hooks live in the two TMA-store epilogues only
-  if ((p.stats_out || p.ln_stats) && !tma_c_ok) return cudaErrorInvalidValue;
+  if ((p.stats_out || p.ln_stats || p.stats_zero) && !tma_c_ok) return cudaErrorInvalidValue;
+  if (p.stats_zero && OUT != 0) return cudaErrorInvalidValue;
   if (p.stats_out && (OUT != 0 || !p.x16_out || (p.ldx16 & 7) || (p.N & 15) || (reinterpret_cast<uintptr_t>(p.x16_out) & 15))) return cudaErrorInvalidValue;
   if (p.ln_stats && (OUT != 1 || p.ln_k <= 0 || p.div != 0.f)) return cudaErrorInvalidValue;
   TcEpilogue ep{p.Cf, p.Cb, p.ldc, p.fp16, p.bias, p.res, p.ldr, p.div != 0.f ? 1.0f / p.div : 1.0f, p.w_static, p.a32, p.lda32, p.ln_g, p.ln_b,
-                p.stats_out, p.x16_out, p.ldx16, p.ln_stats, p.ln_k > 0 ? 1.0f / (float)p.ln_k : 0.f,
+                p.stats_out, p.x16_out, p.ldx16, p.stats_zero, p.ln_stats, p.ln_k > 0 ? 1.0f / (float)p.ln_k : 0.f,
                 tma_c_ok ? 1 : 0, g_tc_debug};
   const int tiles = ((p.M + kBM * CTAS - 1) / (kBM * CTAS)) * ((p.N + BN - 1) / BN);
   const int slots = sm_count() / CTAS;

@@ -56,6 +56,7 @@ struct TcGemmArgs {
   // stats_out (M x 2 64-bit fixed-point integers -- order-independent, hence deterministic -- zeroed by the caller); the consumer (qkv / fc1) takes those raw rows as A, the folded weights as W,
   // b + W beta as `bias`, and scales every accumulator row by rstd from ln_stats (ln_k = LayerNorm width).
   float* stats_out; void* x16_out; long ldx16;
+  float* stats_zero;                 // fp32-output launches: rows of this (other) statistics buffer are cleared by the first column tile
   const float* ln_stats; int ln_k;
 };
 bool tc_gemm_ln_supported(int M, int N, int K);
