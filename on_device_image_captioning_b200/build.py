@@ -9,7 +9,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libxnv2_b200.so")
-SOURCES = ["engine.cu", "gemm_f32.cu", "gemm_tcgen05.cu", "gemm_mma16.cu", "gemm_skinny.cu", "elementwise.cu", "window_attn.cu", "window_attn_mma.cu", "window_attn_tc.cu", "decode.cu", "decode_mega.cu", "beam.cu", "preprocess.cu"]
+SOURCES = ["engine.cu", "gemm_f32.cu", "gemm_tcgen05.cu", "gemm_mma16.cu", "gemm_skinny.cu", "elementwise.cu", "static_exp.cu", "window_attn.cu", "window_attn_mma.cu", "window_attn_tc.cu", "decode.cu", "decode_mega.cu", "beam.cu", "preprocess.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "--use_fast_math=false"]
 

@@ -54,7 +54,7 @@ struct SwinStageW {
   const float *mg = nullptr, *mb = nullptr;
   LinW red;
 };
-struct EncLayerW { const float *n1g, *n1b, *n2g, *n2b, *qexp, *bexp; const void* qexp16; LinW kabs, ff1, ff2; };
+struct EncLayerW { const float *n1g, *n1b, *n2g, *n2b, *qexp, *bexp; const void* qexp16; const float* bexpT; LinW kabs, ff1, ff2; };
 struct DecLayerW { const float *n1g, *n1b, *n2g, *n2b, *n3g, *n3b, *qexp, *bexp; LinW dyn5, wq, wo, ff1, ff2; };
 
 struct Arena {
@@ -121,6 +121,8 @@ struct xn_handle {
   const float *enc_ng, *enc_nb, *dec_ng, *dec_nb, *emb, *pos;
   int* group_start_dev = nullptr;
   int n_exp_total = 0, exp_chunk = 8;
+  bool se_t_ok = false;               // group layout admits the transposed-score static-expansion kernels (static_exp.cu)
+  int64_t se_tc = 2;                  // 16-bit modes: 0 = (B,E,N) kernels + mma.sync contractions, 1 = scores on tcgen05 + slab kernels, 2 = + tcgen05 class / out contractions
   Arena ws;
   int64_t launches = 0;
   int64_t swin_chunk = 64, enc_chunk = 64;
@@ -309,13 +311,13 @@ int lin_f32(xn_handle* h, const float* x, long ldx, const LinW& w, const float* 
 }
 int lin_tc(xn_handle* h, const void* x, long ldx, const LinW& w, const float* res, long ldr, float* yf, void* yb,
            long ldy, int M, int act, int fp16, cudaStream_t st, int w_static = 1, const float* a32 = nullptr, long lda32 = 0,
-           const float* ln_g = nullptr, const float* ln_b = nullptr, const LnFuse* lf = nullptr) {
+           const float* ln_g = nullptr, const float* ln_b = nullptr, const LnFuse* lf = nullptr, float div = 0.f) {
   TcGemmArgs g{};
   if (lf) { g.stats_out = lf->stats_out; g.x16_out = lf->x16_out; g.ldx16 = lf->ldx16; g.ln_stats = lf->ln_stats; g.ln_k = lf->ln_k; g.stats_zero = lf->stats_zero; }
   g.w_static = w_static;
   g.a32 = a32; g.lda32 = lda32; g.ln_g = ln_g; g.ln_b = ln_b;        // LayerNorm-on-load (x is then unused)
   g.A = x; g.lda = ldx; g.W = w.wb; g.ldw = w.K; g.Cf = yf; g.Cb = yb; g.ldc = ldy; g.fp16 = fp16;
-  g.bias = w.b; g.res = res; g.ldr = ldr; g.M = M; g.N = w.N; g.K = w.K; g.div = 0.f; g.act = act;
+  g.bias = w.b; g.res = res; g.ldr = ldr; g.M = M; g.N = w.N; g.K = w.K; g.div = div; g.act = act;
   if (h->profile == 1) {
     if (h->prof_used + 2 > h->prof_ev.size()) {
       for (int i = 0; i < 2; ++i) { cudaEvent_t e; CU(cudaEventCreate(&e)); h->prof_ev.push_back(e); }
@@ -541,6 +543,8 @@ size_t enc_ws_bytes(const xn_config& c, int Bc) {
   f += 2 * M * d;                   // outA, outB
   f += M * c.ff;                    // ff hidden
   f += (size_t)Bc * c.n_exp_groups * 2 * N;   // group sums
+  f += (size_t)Bc * ((N + 15) / 16) * 2 * e;  // per-slab column partials (transposed-score path)
+  f += M * d;                                 // class_a / class_b projections transposed (16-bit, 2 d columns)
   f += M * d;                       // pre-norm output
   f += M * std::max<size_t>(d, c.feat_dim) + M * d * c.n_enc;   // 16-bit staging (counted at 4 B)
   return f * 4 + Bc * 4 + 40 * 256;
@@ -570,6 +574,8 @@ int enc_body_chunk(xn_handle* h, const float* feats, int Bc, const int* n_valid_
   float* oB = h->ws.get<float>((size_t)M * d);
   T* hid = h->ws.get<T>((size_t)M * c.ff);
   float* gs = h->ws.get<float>((size_t)Bc * c.n_exp_groups * 2 * N);
+  float* colpart = h->ws.get<float>((size_t)Bc * ((N + 15) / 16) * 2 * E);
+  T* abt = kF32 ? nullptr : h->ws.get<T>((size_t)M * 2 * d);       // [b][2 d][N]
   float* pre = h->ws.get<float>((size_t)M * d);
   WS_CHECK();
   const long ldc = (long)d * ne;
@@ -625,6 +631,14 @@ int enc_body_chunk(xn_handle* h, const float* feats, int Bc, const int* n_valid_
       KL(1, launch_selector_mix<float>(xin, ldi, k32 + 3 * (size_t)d, 4 * d, oA, oB, d, xout, ldc, M, d, st));
     } else {
       if (int r = lin_tc(h, xn, d, W.kabs, nullptr, 0, nullptr, kabs, 4 * d, M, 0, fp16, st)) return r;
+      if (!kF32 && h->se_tc >= 1 && h->se_t_ok) {
+        // scores transposed, zT[b n][e] = key . q_e / sqrt(d): ONE linear-layer launch on tcgen05 over all images
+        LinW qe{};
+        qe.wb = W.qexp16; qe.N = E; qe.K = d;
+        if (int r = lin_tc(h, kabs, 4 * d, qe, nullptr, 0, z, nullptr, E, M, 0, fp16, st, 1, nullptr, 0, nullptr, nullptr, nullptr, sqrtf((float)d))) return r;
+        if constexpr (!kF32)
+          KL(2, launch_static_exp_weights_t<T>(z, n_valid_dev, h->group_start_dev, c.n_exp_groups, afw, bfw, abw, bbw, gs, colpart, Bc, E, N, st));
+      } else {
       Mma16Args g{};
       g.A = W.qexp16; g.lda = d; g.sA = 0;
       g.B = kabs; g.ldb = 4 * d; g.sB = (long)N * 4 * d; g.b_kn = 0;
@@ -633,6 +647,33 @@ int enc_body_chunk(xn_handle* h, const float* feats, int Bc, const int* n_valid_
       KL(1, (launch_gemm_mma16<T, float>(g, st)));
       KL(2, launch_static_exp_weights<T>(z, n_valid_dev, h->group_start_dev, c.n_exp_groups, afw, bfw, abw, bbw, gs, Bc, E, N,
                                          h->exp_chunk, st));
+      }
+      const bool se_tc2 = h->se_tc >= 2 && h->se_t_ok && (d % 64) == 0;
+      if (se_tc2) {
+        if constexpr (!kF32) {
+          // class^T[b] (d x E) = A^T[b] (d x N) . fw[b]^T + bias_exp^T ;  out^T[b] (d x N) = class^T[b] . bw[b]^T / n_groups:
+          // every operand K-major, batched over the images on tcgen05 (layers.py:62-63,82-83)
+          KL(1, launch_transpose_ab<T>(kabs, 4 * d, d, abt, Bc, 2 * d, N, st));
+          for (int ab = 0; ab < 2; ++ab) {
+            TcGemmArgs q{};
+            q.A = abt + (size_t)ab * d * N; q.lda = N; q.sA = (long)2 * d * N;
+            q.W = ab ? bfw : afw; q.ldw = N; q.sW = (long)E * N;
+            q.Cb = ab ? CB : CA; q.ldc = E; q.sC = (long)d * E; q.fp16 = fp16;
+            q.res = W.bexpT; q.ldr = E; q.sR = 0;
+            q.M = d; q.N = E; q.K = N; q.batch = Bc;
+            KL(1, launch_gemm_tc(q, st));
+          }
+          for (int ab = 0; ab < 2; ++ab) {
+            TcGemmArgs q{};
+            q.A = ab ? CB : CA; q.lda = E; q.sA = (long)d * E;
+            q.W = ab ? bbw : abw; q.ldw = E; q.sW = (long)N * E;
+            q.Cf = ab ? oB : oA; q.ldc = N; q.sC = (long)d * N; q.fp16 = fp16;
+            q.M = d; q.N = N; q.K = E; q.batch = Bc; q.div = (float)c.n_exp_groups;
+            KL(1, launch_gemm_tc(q, st));
+          }
+          KL(1, launch_selector_mix_t<T>(xin, ldi, kabs + 3 * (size_t)d, 4 * d, oA, oB, xout, ldc, Bc, N, d, st));
+        }
+      } else {
       for (int ab = 0; ab < 2; ++ab) {
         Mma16Args q{};
         q.A = ab ? bfw : afw; q.lda = N; q.sA = (long)E * N;
@@ -651,6 +692,7 @@ int enc_body_chunk(xn_handle* h, const float* feats, int Bc, const int* n_valid_
         KL(1, (launch_gemm_mma16<T, float>(q, st)));
       }
       KL(1, launch_selector_mix<T>(xin, ldi, kabs + 3 * (size_t)d, 4 * d, oA, oB, d, xout, ldc, M, d, st));
+      }
     }
     KL(1, launch_layernorm<T>(xout, ldc, W.n2g, W.n2b, xn, d, M, d, st));
     if (kF32) {
@@ -1495,6 +1537,7 @@ int xn_finalize_weights(xn_handle* h, int precision) {
   auto gcdf = [](int a, int b) { while (b) { int t = a % b; a = b; b = t; } return a; };
   for (int v : gstart) if (v) gcd = gcdf(gcd, v);
   h->n_exp_total = (int)E; h->exp_chunk = gcd;
+  h->se_t_ok = static_exp_t_supported(gstart.data(), c.n_exp_groups, (int)E, c.enc_len);
   if (h->group_start_dev) cudaFree(h->group_start_dev);
   CU(cudaMalloc(&h->group_start_dev, gstart.size() * sizeof(int)));
   CU(cudaMemcpy(h->group_start_dev, gstart.data(), gstart.size() * sizeof(int), cudaMemcpyHostToDevice));
@@ -1511,12 +1554,16 @@ int xn_finalize_weights(xn_handle* h, int precision) {
     W.ff1 = lin(q + "ff.linear_1", ff, d); W.ff2 = lin(q + "ff.linear_2", d, ff);
     if (rc) return rc;
     if (concat(parts, W.kabs)) return XN_ERR_CUDA;
-    W.qexp16 = nullptr;
+    W.qexp16 = nullptr; W.bexpT = nullptr;
     if (precision != XN_PREC_FP32) {
       if (to_bf16(W.kabs) || to_bf16(W.ff1) || to_bf16(W.ff2)) return XN_ERR_CUDA;
       LinW qe; qe.w = W.qexp; qe.N = (int)E; qe.K = (int)d;       // 16-bit copy of the expansion queries (left operand of z)
       if (to_bf16(qe)) return XN_ERR_CUDA;
       W.qexp16 = qe.wb;
+      float* bt = nullptr;                                          // bias_exp transposed [d][E]: residual of class^T
+      CU(cudaMalloc(&bt, (size_t)E * d * sizeof(float))); h->owned.push_back(bt);
+      CU(launch_transpose_f32(W.bexp, bt, (int)E, (int)d, nullptr));
+      W.bexpT = bt;
     }
     h->enc.push_back(W);
   }
@@ -2263,6 +2310,7 @@ int xn_set_option(xn_handle* h, const char* name, int64_t value) {
   if (n == "mega_dbg_mode") { h->mega_dbg_mode = value; h->drop_graphs(); return XN_OK; }
   if (n == "mega_coop") { g_mega_coop = value != 0; h->drop_graphs(); return XN_OK; }
   if (n == "ln_on_load") { h->ln_on_load = value; h->drop_graphs(); return XN_OK; }
+  if (n == "se_tc") { h->se_tc = value; h->drop_graphs(); return XN_OK; }
   if (n == "ln_fuse") { h->ln_fuse = value; h->drop_graphs(); return XN_OK; }
   if (n == "decode_groups") { h->decode_groups = std::max<int64_t>(0, std::min<int64_t>(value, xn_handle::kMaxDecodeGroups)); h->drop_graphs(); return XN_OK; }
   if (n == "pdl") { g_pdl_enabled = value != 0; h->drop_graphs(); return XN_OK; }

@@ -1,10 +1,11 @@
-// BF16 GEMM on the 5th-generation tensor cores: tcgen05.mma with the accumulator in TMEM,
+// 16-bit (fp16 by default, or bf16) GEMM on the 5th-generation tensor cores: tcgen05.mma with the accumulator in TMEM,
 // operands staged in shared memory by TMA (128B swizzle), warp-specialised and persistent.
 //
 //   C (M x N) = act( A (M x K) . W^T (N x K) / div + bias ) + res
 //
-// A and W are bf16 with K contiguous (nn.Linear layout on both sides), accumulation is fp32.
-// This is the contraction behind every nn.Linear of the Swin backbone in the bf16 mode
+// A and W are fp16 or bf16 (ep.fp16) with K contiguous (nn.Linear layout on both sides), accumulation is fp32.
+// This is the contraction behind every nn.Linear of the path in the 16-bit modes, and (batched: TcGemmArgs::batch) the
+// per-image contractions of the static-expansion block
 // (reference models/swin_transformer_mod.py:214-216,229-233,270 qkv/proj; :109-119 fc1/fc2;
 // :479,499 patch-merging reduction).
 //
@@ -63,6 +64,7 @@ struct TcEpilogue {
   const float* ln_stats; float ln_inv_k;                                // consumer side (16-bit output path)
   int use_tma_store;   // 16-bit output without residual: write through TMA (needs ldc % 8 == 0)
   int dbg;     // timing experiments only: 1 = skip the epilogue's global traffic, 2 = skip MMA issue, 4 = skip TMA loads
+  int batch; long sC, sR;   // batched mode (3-D operand maps, generic epilogue): C / res element strides between problems
 };
 
 // ---------------------------------------------------------------- PTX wrappers
@@ -93,6 +95,12 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
       : "memory");
 }
 // CTA-pair variants: the transaction bytes of both CTAs' loads land on the LEADER's barrier (shared::cluster address)
@@ -246,7 +254,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m_tiles = (M + kTileM - 1) / kTileM, n_tiles = (N + BN - 1) / BN;
-  const int total_tiles = m_tiles * n_tiles;
+  const int tiles_pb = m_tiles * n_tiles;                              // tiles per problem
+  const int total_tiles = tiles_pb * (ep.batch > 0 ? ep.batch : 1);
   const int nkb = (K + kBK - 1) / kBK;
   const uint32_t rank = CTAS == 2 ? cluster_ctarank() : 0u;           // 0 = leader (issues the MMAs)
   const int tile0 = blockIdx.x / CTAS, tile_step = gridDim.x / CTAS;   // persistent loop over (pair) tiles
@@ -309,7 +318,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = tile0; tile < total_tiles; tile += tile_step) {
-        const int m0 = (tile / n_tiles) * kTileM + row_off, n0 = (tile % n_tiles) * BN + (int)rank * (BN / CTAS);
+        const int bz = ep.batch > 0 ? tile / tiles_pb : 0, tl = tile - bz * tiles_pb;
+        const int m0 = (tl / n_tiles) * kTileM + row_off, n0 = (tl % n_tiles) * BN + (int)rank * (BN / CTAS);
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
           const uint32_t sa = base + stage * Cfg::kStageBytes;
@@ -331,6 +341,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             } else if (pre_stages > 0) {                // W tile and byte count of this stage were issued before the wait
               --pre_stages;
               tma_load_2d(sa, &tma_a, kb * kBK, m0, full_bar(stage));
+            } else if (ep.batch > 0) {                  // batched problems: 3-D maps (k, row, problem), edges clipped per problem
+              mbar_expect_tx(full_bar(stage), Cfg::kStageBytes);
+              tma_load_3d(sa, &tma_a, kb * kBK, m0, bz, full_bar(stage));
+              tma_load_3d(sa + kABytes, &tma_b, kb * kBK, n0, bz, full_bar(stage));
             } else {
               mbar_expect_tx(full_bar(stage), Cfg::kStageBytes);
               tma_load_2d(sa, &tma_a, kb * kBK, m0, full_bar(stage));
@@ -655,9 +669,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     for (int tile = tile0; tile < total_tiles; tile += tile_step, ++it) {
       const int buf = it & 1;
       const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
-      const int m0 = (tile / n_tiles) * kTileM + row_off, n0 = (tile % n_tiles) * BN;
+      const int bz = ep.batch > 0 ? tile / tiles_pb : 0, tl = tile - bz * tiles_pb;
+      const int m0 = (tl / n_tiles) * kTileM + row_off, n0 = (tl % n_tiles) * BN;
       const int row_base = m0 + q * 32;
       const int col_base = n0 + hf * kColsPerWarp;
+      const float* res_b = ep.res ? ep.res + (long)bz * ep.sR : nullptr;
       // this lane's bias values for all steps of the tile, fetched before waiting for the accumulator (the L1 is
       // carved out for smem, so an in-loop bias load costs an exposed L2 round trip per step: measured 2.5k cycles/step)
       float4 bcol[kSteps];
@@ -681,8 +697,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         for (int i = 0; i < 4; ++i) {
           r[i] = make_float4(0.f, 0.f, 0.f, 0.f);
           const int row = row_base + i * 8 + sub_r;
-          if (ep.res && row < M && col < N) {
-            const float* src = ep.res + (long)row * ep.ldr + col;
+          if (res_b && row < M && col < N) {
+            const float* src = res_b + (long)row * ep.ldr + col;
             if (ld_vec && col + 3 < N) r[i] = *reinterpret_cast<const float4*>(src);
             else {
               r[i].x = src[0];
@@ -735,7 +751,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             if ((ep.dbg & 8) && x[0] != 1234567.f) continue;     // timing experiment: all the math, no global stores
             if (row < M) {
               if (OUT == 0) {
-                float* dst = ep.Cf + (long)row * ep.ldc + col;
+                float* dst = ep.Cf + (long)bz * ep.sC + (long)row * ep.ldc + col;
                 if (vec_ok) *reinterpret_cast<float4*>(dst) = make_float4(x[0], x[1], x[2], x[3]);
                 else for (int e = 0; e < 4; ++e) if (col + e < N) dst[e] = x[e];
               } else {
@@ -747,7 +763,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                   __nv_bfloat162 a2 = __floats2bfloat162_rn(x[0], x[1]), b2 = __floats2bfloat162_rn(x[2], x[3]);
                   lo = *reinterpret_cast<uint32_t*>(&a2); hi = *reinterpret_cast<uint32_t*>(&b2);
                 }
-                uint16_t* dst = reinterpret_cast<uint16_t*>(ep.Cb) + (long)row * ep.ldc + col;
+                uint16_t* dst = reinterpret_cast<uint16_t*>(ep.Cb) + (long)bz * ep.sC + (long)row * ep.ldc + col;
                 if (vec_ok) *reinterpret_cast<uint2*>(dst) = make_uint2(lo, hi);
                 else {
                   const uint16_t h4[4] = {(uint16_t)(lo & 0xffffu), (uint16_t)(lo >> 16), (uint16_t)(hi & 0xffffu), (uint16_t)(hi >> 16)};
@@ -808,6 +824,20 @@ static bool make_map(CUtensorMap* map, const void* ptr, long rows, long cols, lo
   return r == CUDA_SUCCESS;
 }
 
+// (k, row, problem) view of `batch` stacked K-major matrices: rows x cols each, row pitch ld, problem pitch bs (elements)
+static bool make_map3(CUtensorMap* map, const void* ptr, long rows, long cols, long ld, long bs, long batch, int box_rows, int fp16) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return false;
+  cuuint64_t gdim[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)batch};
+  cuuint64_t gstride[2] = {(cuuint64_t)ld * 2, (cuuint64_t)bs * 2};
+  cuuint32_t box[3] = {(cuuint32_t)kBK, (cuuint32_t)box_rows, 1u};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(map, fp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
 int g_tc_debug = 0;
 int g_pdl_enabled = 1;
 void set_tc_debug(int v) { g_tc_debug = v; }
@@ -854,16 +884,20 @@ static cudaError_t launch_tc(const TcGemmArgs& p, cudaStream_t st) {
   static DynSmemState smem_state;
   if (cudaError_t e = ensure_dyn_smem(gemm_tc_kernel<BN, OUT, ACT, CTAS>, Cfg::kSmemBytes, smem_state)) return e;
   CUtensorMap ma, mb;
-  if (!make_map(&ma, p.A, p.M, p.K, p.lda, kBM, p.fp16) || !make_map(&mb, p.W, p.N, p.K, p.ldw, BN / CTAS, p.fp16)) return cudaErrorInvalidValue;
+  if (p.batch > 0) {
+    if (CTAS != 1 || p.a32 || p.stats_out || p.ln_stats || p.stats_zero) return cudaErrorInvalidValue;
+    if (!make_map3(&ma, p.A, p.M, p.K, p.lda, p.sA, p.batch, kBM, p.fp16) || !make_map3(&mb, p.W, p.N, p.K, p.ldw, p.sW, p.batch, BN, p.fp16))
+      return cudaErrorInvalidValue;
+  } else if (!make_map(&ma, p.A, p.M, p.K, p.lda, kBM, p.fp16) || !make_map(&mb, p.W, p.N, p.K, p.ldw, BN / CTAS, p.fp16)) return cudaErrorInvalidValue;
   // 16-bit outputs without a residual leave through TMA stores: 32 x 32 boxes, 64-byte swizzle
   bool tma_c_ok = false;
   CUtensorMap mc = ma, mr = ma;
   if (OUT == 1) {
-    tma_c_ok = !p.res && (p.ldc % 8) == 0 && (reinterpret_cast<uintptr_t>(p.Cb) & 15) == 0 && !(g_tc_debug & 16);
+    tma_c_ok = p.batch <= 0 && !p.res && (p.ldc % 8) == 0 && (reinterpret_cast<uintptr_t>(p.Cb) & 15) == 0 && !(g_tc_debug & 16);
     if (tma_c_ok && !make_map(&mc, p.Cb, p.M, p.N, p.ldc, 32, p.fp16, 32, CU_TENSOR_MAP_SWIZZLE_64B)) return cudaErrorInvalidValue;
   } else {
     // fp32 output (+ fp32 residual): 32-row x 16-column boxes (64 bytes per row), 64-byte swizzle
-    tma_c_ok = (p.ldc % 4) == 0 && (reinterpret_cast<uintptr_t>(p.Cf) & 15) == 0 && !(g_tc_debug & 32) &&
+    tma_c_ok = p.batch <= 0 && (p.ldc % 4) == 0 && (reinterpret_cast<uintptr_t>(p.Cf) & 15) == 0 && !(g_tc_debug & 32) &&
                (!p.res || ((p.ldr % 4) == 0 && (reinterpret_cast<uintptr_t>(p.res) & 15) == 0));
     if (tma_c_ok) {
       if (!make_map32(&mc, p.Cf, p.M, p.N, p.ldc)) return cudaErrorInvalidValue;
@@ -877,8 +911,9 @@ static cudaError_t launch_tc(const TcGemmArgs& p, cudaStream_t st) {
   if (p.ln_stats && (OUT != 1 || p.ln_k <= 0 || p.div != 0.f)) return cudaErrorInvalidValue;
   TcEpilogue ep{p.Cf, p.Cb, p.ldc, p.fp16, p.bias, p.res, p.ldr, p.div != 0.f ? 1.0f / p.div : 1.0f, p.w_static, p.a32, p.lda32, p.ln_g, p.ln_b,
                 p.stats_out, p.x16_out, p.ldx16, p.stats_zero, p.ln_stats, p.ln_k > 0 ? 1.0f / (float)p.ln_k : 0.f,
-                tma_c_ok ? 1 : 0, g_tc_debug};
-  const int tiles = ((p.M + kBM * CTAS - 1) / (kBM * CTAS)) * ((p.N + BN - 1) / BN);
+                tma_c_ok ? 1 : 0, g_tc_debug, p.batch > 0 ? p.batch : 0, p.sC, p.sR};
+  if (p.batch > 0) ep.w_static = 0;
+  const int tiles = ((p.M + kBM * CTAS - 1) / (kBM * CTAS)) * ((p.N + BN - 1) / BN) * (p.batch > 0 ? p.batch : 1);
   const int slots = sm_count() / CTAS;
   const int grid = CTAS * (tiles < slots ? tiles : slots);
   cudaLaunchConfig_t cfg = {};
@@ -931,6 +966,20 @@ cudaError_t launch_gemm_tc(const TcGemmArgs& p, cudaStream_t st) {
   if (!tc_gemm_supported(p.M, p.N, p.K) || (p.lda % 8) || (p.ldw % 8) || ((p.Cf != nullptr) == (p.Cb != nullptr)))
     return cudaErrorInvalidValue;
   if ((reinterpret_cast<uintptr_t>(p.A) & 15) || (reinterpret_cast<uintptr_t>(p.W) & 15)) return cudaErrorInvalidValue;
+  if (p.batch > 0) {
+    // per-image contractions of the static-expansion block: independent problems of one shape, operands stacked with the
+    // pitches sA / sW.  Tile width with the least padding (ties to the wider tile); single-CTA tiles, generic epilogue.
+    if ((p.sA % 8) || (p.sW % 8) || p.act < 0 || p.act > 2) return cudaErrorInvalidValue;
+    int bn = 256;
+    long waste = -1;
+    for (int c : {256, 192, 128}) {
+      const long w = (long)((p.N + c - 1) / c) * c - p.N;
+      if (waste < 0 || w < waste) { bn = c; waste = w; }
+    }
+    if (bn == 256) return launch_tc_bn<256, 1>(p, st);
+    if (bn == 192) return launch_tc_bn<192, 1>(p, st);
+    return launch_tc_bn<128, 1>(p, st);
+  }
   // pick the tile width with the least padded work; ties go to the wider tile.  With only a few waves of tiles over the
   // persistent grid the wave count decides instead (a nearly empty second wave doubles the time): cost = waves x width.
   const int cands[3] = {256, 192, 128};

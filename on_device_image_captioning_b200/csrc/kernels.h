@@ -58,6 +58,10 @@ struct TcGemmArgs {
   float* stats_out; void* x16_out; long ldx16;
   float* stats_zero;                 // fp32-output launches: rows of this (other) statistics buffer are cleared by the first column tile
   const float* ln_stats; int ln_k;
+  // Batched mode (batch > 0): `batch` independent problems of the same M x N x K, operands stacked with the element
+  // pitches sA / sW (3-D tensor maps: the M / N / K edges are clipped per problem), outputs with sC, the fp32 residual
+  // with sR (0 = shared).  Single-CTA tiles and the generic epilogue only; no LayerNorm hooks.
+  int batch; long sA, sW, sC, sR;
 };
 bool tc_gemm_ln_supported(int M, int N, int K);
 // W (N x K) fp32, LayerNorm affine (gamma, beta: K) -> w16 = round16(gamma (.) W - row mean), bias_out_n = bias_n + sum_k W_nk beta_k
@@ -156,6 +160,22 @@ template <typename ST>
 cudaError_t launch_selector_mix(const float* x_in, long ldxi, const ST* sel, long lds, const float* out_a,
                                 const float* out_b, long ldo, float* x_out, long ldxo, long rows, int d,
                                 cudaStream_t st);
+
+// Transposed-score variants for the tcgen05 path (static_exp.cu): zT (B, N, E) from the linear-layer GEMM; same outputs
+// as launch_static_exp_weights; colpart_scratch holds B * (N / 16) * 2 * E floats.
+bool static_exp_t_supported(const int* group_start_host, int n_groups, int E, int N);
+template <typename T>
+cudaError_t launch_static_exp_weights_t(const float* zT, const int* n_valid, const int* group_start, int n_groups, T* a_fw,
+                                        T* b_fw, T* a_bw, T* b_bw, float* gsum_scratch, float* colpart_scratch, int B, int E,
+                                        int N, cudaStream_t st);
+// src [b * N + n][ld], columns c0 .. c0 + C (16-bit)  ->  dst [b][C][N]
+template <typename T>
+cudaError_t launch_transpose_ab(const T* src, long ld, int c0, T* dst, int B, int C, int N, cudaStream_t st);
+cudaError_t launch_transpose_f32(const float* in, float* out, int R, int C, cudaStream_t st);   // out[c][r] = in[r][c]
+// selector mix with out_a / out_b given transposed: [b][d][N]
+template <typename ST>
+cudaError_t launch_selector_mix_t(const float* x_in, long ldxi, const ST* sel, long lds, const float* out_a_t, const float* out_b_t,
+                                  float* x_out, long ldxo, int B, int N, int d, cudaStream_t st);
 
 // ---------------------------------------------------------------- decoder step
 struct DecState {

@@ -24,7 +24,7 @@ sp = e.profile_kernels()
 e.set_option("profile", 0)
 tot = sum(v[1] for v in sp.values())
 print(f"options {sys.argv[2:]}: eager step {tot:.3f} ms over {sum(v[0] for v in sp.values())} launches")
-for k, (n, ms) in sorted(sp.items(), key=lambda kv: -kv[1][1])[:14]:
+for k, (n, ms) in sorted(sp.items(), key=lambda kv: -kv[1][1])[:int(os.environ.get("SPANS_TOP", "14"))]:
     print(f"   {ms:8.3f} ms {n:5d}x  {k}")
 # the tcgen05 GEMMs one by one
 e.set_option("profile", 1)
