@@ -371,13 +371,13 @@ def run_ours(args):
             lc = sum(cfg.depths[i] * (G >> i) ** 2 * (cfg.embed_dim << i) for i in range(len(cfg.depths)))   # sum over blocks of L*C
             R = B * BEAM
             algo = {   # launcher -> (what, algorithmic bytes per step)
-                "ActOps<T>::attn": ("window_attention_mma_kernel: read QKV + write O, 16-bit", 8.0 * lc * B),
-                "swin_layernorm<T>": ("layernorm_rows_kernel (Swin, 2 per block: fp32 residual in, 16-bit operand out)", 2 * 6.0 * lc * B),
+                "ActOps<T>::attn": ("window_attention_tc_kernel (tcgen05, scores in TMEM): read QKV + write O, 16-bit", 8.0 * lc * B),
+                # (the Swin norm1 / norm2 launches of round 1 are gone: folded into the neighbouring tcgen05 GEMMs)
                 "launch_logsoftmax_topk": ("logsoftmax_topk_reg_kernel: read R x V logits once", 4.0 * R * cfg.vocab * (MAX_LEN - 1)),
                 "launch_cross_attn_step<T, T>": ("cross_attn_step16_kernel: K/V of one layer per launch (KV-cache read by beam rows)",
                                                  2.0 * 2 * cfg.enc_len * cfg.d_model * B * cfg.n_dec * (MAX_LEN - 1)),
-                "launch_patch_embed4": ("patch_embed4_kernel: read image fp32, write tokens fp32",
-                                       4.0 * B * (cfg.in_chans * cfg.img_size ** 2 + G * G * cfg.embed_dim)),
+                "launch_patch_embed4": ("patch_embed4_kernel: read image fp32, write tokens fp32 + the same rows in 16 bits",
+                                       B * (4.0 * cfg.in_chans * cfg.img_size ** 2 + 6.0 * G * G * cfg.embed_dim)),
             }
             hbm_kernels = []
             for key, (what, nbytes) in algo.items():

@@ -295,6 +295,9 @@ constexpr int kPe4Patches = 6;
 // writes the rows rounded to 16 bits and their sum / sum of squares in the 64-bit fixed-point format of the tcgen05
 // GEMM's producer epilogue (gemm_tcgen05.cu), so the first qkv GEMM runs against the folded weights like every other
 // block and the stage-1 LayerNorm launch (the largest one: 453 MB read) disappears.
+// EPT > 0: E / 32 known at compile time (Swin-L: 6), so the per-lane channel loops carry no guards (the runtime-EP
+// form spent half of its 413 M warp instructions on ISETP / BRA / CS2R around 190 M FFMAs: profiles/r2s3_ncu_misc_summary.txt)
+template <int EPT>
 __global__ void __launch_bounds__(256) patch_embed4_kernel(const float* __restrict__ img, const float4* __restrict__ wq,
                                                            const float* __restrict__ bias, const float* __restrict__ g,
                                                            const float* __restrict__ be, float* __restrict__ out,
@@ -310,7 +313,7 @@ __global__ void __launch_bounds__(256) patch_embed4_kernel(const float* __restri
   const int b = blockIdx.x / groups, py0 = (blockIdx.x % groups) * kPeRows;
   for (int i = threadIdx.x; i < KG * E; i += blockDim.x) wt[i] = wq[i];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  const int EP = E / 32;                        // channels per lane (E % 32 == 0, E <= 256)
+  const int EP = EPT > 0 ? EPT : E / 32;        // channels per lane (E % 32 == 0, E <= 256)
   float gam[8], bet[8], bia[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
@@ -407,10 +410,16 @@ cudaError_t launch_patch_embed4(const float* img, const float* wq, const float* 
   if (E % 32 || E > 256 || S % 16) return cudaErrorInvalidValue;
   const int G = S / 4;
   const size_t smem = ((size_t)Cin * 4 * G + (size_t)Cin * 4 * E) * sizeof(float4);
-  static DynSmemState smem_state;
-  if (cudaError_t e = ensure_dyn_smem(patch_embed4_kernel, smem, smem_state)) return e;
   const int groups = (G + kPeRows - 1) / kPeRows;
-  return launch_k(patch_embed4_kernel, dim3(B * groups), dim3(256), smem, st, img, reinterpret_cast<const float4*>(wq), b, gamma, beta,
+  if (E == 192) {
+    static DynSmemState smem_state6;
+    if (cudaError_t e = ensure_dyn_smem(patch_embed4_kernel<6>, smem, smem_state6)) return e;
+    return launch_k(patch_embed4_kernel<6>, dim3(B * groups), dim3(256), smem, st, img, reinterpret_cast<const float4*>(wq), b, gamma, beta,
+                    out, Cin, S, E, x16, fp16, reinterpret_cast<unsigned long long*>(stats));
+  }
+  static DynSmemState smem_state;
+  if (cudaError_t e = ensure_dyn_smem(patch_embed4_kernel<0>, smem, smem_state)) return e;
+  return launch_k(patch_embed4_kernel<0>, dim3(B * groups), dim3(256), smem, st, img, reinterpret_cast<const float4*>(wq), b, gamma, beta,
                   out, Cin, S, E, x16, fp16, reinterpret_cast<unsigned long long*>(stats));
 }
 

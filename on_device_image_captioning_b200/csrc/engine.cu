@@ -2324,8 +2324,8 @@ int xn_set_option(xn_handle* h, const char* name, int64_t value) {
     for (auto& sp : h->spans) { h->span_pool.push_back(sp.e0); h->span_pool.push_back(sp.e1); }
     h->spans.clear();
   }
-  else if (n == "swin_chunk") h->swin_chunk = std::max<int64_t>(1, value);
-  else if (n == "enc_chunk") h->enc_chunk = std::max<int64_t>(1, value);
+  else if (n == "swin_chunk") { h->swin_chunk = std::max<int64_t>(1, value); h->drop_graphs(); }
+  else if (n == "enc_chunk") { h->enc_chunk = std::max<int64_t>(1, value); h->drop_graphs(); }
   else return h->fail(XN_ERR_ARG, "unknown option '%s'", name);
   return XN_OK;
 }
