@@ -2,6 +2,7 @@
 // weight normalisation, selector mix, casts.  All reductions are fp32.
 #include "kernels.h"
 #include "common.cuh"
+#include "mma16_frag.cuh"
 
 namespace xn {
 
@@ -421,6 +422,164 @@ cudaError_t launch_patch_embed4(const float* img, const float* wq, const float* 
   if (cudaError_t e = ensure_dyn_smem(patch_embed4_kernel<0>, smem, smem_state)) return e;
   return launch_k(patch_embed4_kernel<0>, dim3(B * groups), dim3(256), smem, st, img, reinterpret_cast<const float4*>(wq), b, gamma, beta,
                   out, Cin, S, E, x16, fp16, reinterpret_cast<unsigned long long*>(stats));
+}
+
+// ------------------------------------------------------------------------------------------
+// Patch width 4 on the tensor cores (16-bit modes): the convolution is a (patches x 16 Cin) . (16 Cin x E) contraction;
+// per warp one m16 tile of patches against all E channels with mma.sync.m16n8k8 TF32 (inputs rounded to the 10-bit
+// TF32 significand -- the same 2^-11 relative rounding every other operand of the 16-bit modes gets; the fp32 parity mode
+// keeps the exact CUDA-core kernels above).  The CUDA-core kernel is bound by shared-memory wavefronts (61.6 M per
+// launch for 190 M FFMAs: profiles/round2_ncu_misc_kernels_summary.txt); here a k8 step is 4 + 2 NT conflict-free LDS.32
+// for NT tensor-core instructions, and the kernel is bound by its HBM traffic.
+// One CTA = one patch row at a time (G / 16 warps, one tile each), kPeRows rows per CTA.  Fragment layouts (PTX ISA,
+// m16n8k8 .tf32): g = lane >> 2, t = lane & 3; A: a0 (g, t) a1 (g + 8, t) a2 (g, t + 4) a3 (g + 8, t + 4);
+// B: b0 (k = t, n = g) b1 (k = t + 4, n = g); C: c0 (g, 2t) c1 (g, 2t + 1) c2 (g + 8, 2t) c3 (g + 8, 2t + 1).
+// Taps of k8 step ks: (c, dy) rows 2 ks and 2 ks + 1 of the slab, dx = 0..3 -- the conv weight's own (c, dy, dx) order.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t to_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return r;
+}
+constexpr int kPeTcWPitch = 8;        // weight row pitch = E + 8 words: the 4 k rows of a B fragment hit different banks
+
+template <int NT>                     // NT = E / 8 channel tiles
+__global__ void __launch_bounds__(256) patch_embed4_tf32_kernel(const float* __restrict__ img, const float4* __restrict__ wq,
+                                                                const float* __restrict__ bias, const float* __restrict__ g,
+                                                                const float* __restrict__ be, float* __restrict__ out,
+                                                                int Cin, int S, void* __restrict__ x16, int fp16,
+                                                                unsigned long long* __restrict__ stats) {
+  pdl_wait();
+  pdl_trigger();
+  constexpr int E = NT * 8, WP = E + kPeTcWPitch;
+  extern __shared__ float4 sm4[];
+  const int G = S / 4, KG = Cin * 4;
+  float* slab0 = reinterpret_cast<float*>(sm4);                // [2][KG][G][4]   two patch rows of pixels (double buffer)
+  uint32_t* wt = reinterpret_cast<uint32_t*>(slab0 + 2 * KG * G * 4);   // [KG * 4][WP]  tf32 filter bank, k-major
+  float* prm = reinterpret_cast<float*>(wt + KG * 4 * WP);     // bias | gamma | beta  [3][E]
+  const int groups = (G + kPeRows - 1) / kPeRows;
+  const int b = blockIdx.x / groups, py0 = (blockIdx.x % groups) * kPeRows;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+  for (int i = tid; i < KG * E; i += blockDim.x) {
+    const int r = i / E, e = i - r * E;
+    const float4 v = wq[i];
+    wt[(r * 4 + 0) * WP + e] = to_tf32(v.x); wt[(r * 4 + 1) * WP + e] = to_tf32(v.y);
+    wt[(r * 4 + 2) * WP + e] = to_tf32(v.z); wt[(r * 4 + 3) * WP + e] = to_tf32(v.w);
+  }
+  for (int i = tid; i < E; i += blockDim.x) { prm[i] = bias[i]; prm[E + i] = g[i]; prm[2 * E + i] = be[i]; }
+  const int gq = lane >> 2, t = lane & 3;
+  const int tiles = G / 16;
+  const uint32_t slab_u = (uint32_t)__cvta_generic_to_shared(slab0);
+  // the pixels of patch row py0 + pr stream into buffer pr & 1 (cp.async) while the previous row is on the tensor cores
+  auto load_row = [&](int pr) {
+    const int py = py0 + pr;
+    if (pr < kPeRows && py < G) {
+      const uint32_t dst = slab_u + (uint32_t)((pr & 1) * KG * G * 16);
+      for (int i = tid; i < KG * G; i += blockDim.x) {
+        const int r = i / G, px = i - r * G, c = r >> 2, dy = r & 3;
+        cp_async16(dst + i * 16, &img[(((long)b * Cin + c) * S + (py * 4 + dy)) * S + px * 4]);
+      }
+    }
+    cp_async_commit();
+  };
+  load_row(0);
+  for (int pr = 0; pr < kPeRows && py0 + pr < G; ++pr) {
+    const int py = py0 + pr;
+    load_row(pr + 1);
+    cp_async_wait<1>();
+    __syncthreads();
+    const float* slab = slab0 + (pr & 1) * KG * G * 4;
+    for (int tile = warp; tile < tiles; tile += nw) {
+      const int p0 = tile * 16;
+      float acc[NT][4];
+#pragma unroll
+      for (int j = 0; j < NT; ++j) {
+        const float2 bb = *reinterpret_cast<const float2*>(prm + 8 * j + 2 * t);
+        acc[j][0] = bb.x; acc[j][1] = bb.y; acc[j][2] = bb.x; acc[j][3] = bb.y;
+      }
+      for (int ks = 0; ks < KG / 2; ++ks) {
+        const float* s0 = slab + ((2 * ks) * G + p0 + gq) * 4 + t;
+        const float* s1 = s0 + G * 4;
+        const uint32_t a0 = to_tf32(s0[0]), a1 = to_tf32(s0[32]), a2 = to_tf32(s1[0]), a3 = to_tf32(s1[32]);
+        const uint32_t* wr = wt + (8 * ks + t) * WP + gq;
+#pragma unroll
+        for (int j = 0; j < NT; ++j) {
+          const uint32_t b0 = wr[8 * j], b1 = wr[4 * WP + 8 * j];
+          asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                       : "+f"(acc[j][0]), "+f"(acc[j][1]), "+f"(acc[j][2]), "+f"(acc[j][3])
+                       : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+        }
+      }
+      // LayerNorm over the E channels of rows gq and gq + 8: quad reductions
+      float s_lo = 0.f, s_hi = 0.f;
+#pragma unroll
+      for (int j = 0; j < NT; ++j) { s_lo += acc[j][0] + acc[j][1]; s_hi += acc[j][2] + acc[j][3]; }
+      s_lo += __shfl_xor_sync(0xffffffffu, s_lo, 1); s_lo += __shfl_xor_sync(0xffffffffu, s_lo, 2);
+      s_hi += __shfl_xor_sync(0xffffffffu, s_hi, 1); s_hi += __shfl_xor_sync(0xffffffffu, s_hi, 2);
+      const float m_lo = s_lo / (float)E, m_hi = s_hi / (float)E;
+      float q_lo = 0.f, q_hi = 0.f;
+#pragma unroll
+      for (int j = 0; j < NT; ++j) {
+        const float d0 = acc[j][0] - m_lo, d1 = acc[j][1] - m_lo, d2 = acc[j][2] - m_hi, d3 = acc[j][3] - m_hi;
+        q_lo += d0 * d0 + d1 * d1; q_hi += d2 * d2 + d3 * d3;
+      }
+      q_lo += __shfl_xor_sync(0xffffffffu, q_lo, 1); q_lo += __shfl_xor_sync(0xffffffffu, q_lo, 2);
+      q_hi += __shfl_xor_sync(0xffffffffu, q_hi, 1); q_hi += __shfl_xor_sync(0xffffffffu, q_hi, 2);
+      const float r_lo = 1.0f / sqrtf(q_lo / (float)E + kLnEps), r_hi = 1.0f / sqrtf(q_hi / (float)E + kLnEps);
+      const long row_lo = ((long)b * G + py) * G + p0 + gq, row_hi = row_lo + 8;
+      float* o_lo = out + row_lo * E + 2 * t;
+      float* o_hi = out + row_hi * E + 2 * t;
+      float ys_lo = 0.f, yq_lo = 0.f, ys_hi = 0.f, yq_hi = 0.f;
+#pragma unroll
+      for (int j = 0; j < NT; ++j) {
+        const float2 ga = *reinterpret_cast<const float2*>(prm + E + 8 * j + 2 * t), bt = *reinterpret_cast<const float2*>(prm + 2 * E + 8 * j + 2 * t);
+        const float y0 = (acc[j][0] - m_lo) * r_lo * ga.x + bt.x, y1 = (acc[j][1] - m_lo) * r_lo * ga.y + bt.y;
+        const float y2 = (acc[j][2] - m_hi) * r_hi * ga.x + bt.x, y3 = (acc[j][3] - m_hi) * r_hi * ga.y + bt.y;
+        *reinterpret_cast<float2*>(o_lo + 8 * j) = make_float2(y0, y1);
+        *reinterpret_cast<float2*>(o_hi + 8 * j) = make_float2(y2, y3);
+        if (x16) {
+          ys_lo += y0 + y1; yq_lo = fmaf(y0, y0, fmaf(y1, y1, yq_lo));
+          ys_hi += y2 + y3; yq_hi = fmaf(y2, y2, fmaf(y3, y3, yq_hi));
+          if (fp16) {
+            *reinterpret_cast<__half2*>(reinterpret_cast<__half*>(x16) + row_lo * E + 8 * j + 2 * t) = __floats2half2_rn(y0, y1);
+            *reinterpret_cast<__half2*>(reinterpret_cast<__half*>(x16) + row_hi * E + 8 * j + 2 * t) = __floats2half2_rn(y2, y3);
+          } else {
+            *reinterpret_cast<__nv_bfloat162*>(reinterpret_cast<__nv_bfloat16*>(x16) + row_lo * E + 8 * j + 2 * t) = __floats2bfloat162_rn(y0, y1);
+            *reinterpret_cast<__nv_bfloat162*>(reinterpret_cast<__nv_bfloat16*>(x16) + row_hi * E + 8 * j + 2 * t) = __floats2bfloat162_rn(y2, y3);
+          }
+        }
+      }
+      if (x16) {                                  // 64-bit fixed-point row statistics (integer adds: order-independent)
+        long long a_lo = __float2ll_rn(ys_lo * 16777216.0f), b_lo = __float2ll_rn(yq_lo * 65536.0f);
+        long long a_hi = __float2ll_rn(ys_hi * 16777216.0f), b_hi = __float2ll_rn(yq_hi * 65536.0f);
+#pragma unroll
+        for (int o2 = 1; o2 <= 2; o2 <<= 1) {
+          a_lo += __shfl_xor_sync(0xffffffffu, a_lo, o2); b_lo += __shfl_xor_sync(0xffffffffu, b_lo, o2);
+          a_hi += __shfl_xor_sync(0xffffffffu, a_hi, o2); b_hi += __shfl_xor_sync(0xffffffffu, b_hi, o2);
+        }
+        if (t == 0) {
+          stats[2 * row_lo] = (unsigned long long)a_lo; stats[2 * row_lo + 1] = (unsigned long long)b_lo;
+          stats[2 * row_hi] = (unsigned long long)a_hi; stats[2 * row_hi + 1] = (unsigned long long)b_hi;
+        }
+      }
+    }
+    __syncthreads();                              // the buffer read here is refilled by the next iteration's prefetch
+  }
+}
+
+bool patch_embed4_tc_supported(int Cin, int S, int E) { return E == 192 && S % 64 == 0 && Cin >= 1 && Cin <= 4; }
+
+cudaError_t launch_patch_embed4_tc(const float* img, const float* wq, const float* b, const float* gamma, const float* beta,
+                                   float* out, int B, int Cin, int S, int E, cudaStream_t st, void* x16, int fp16, float* stats) {
+  if (!patch_embed4_tc_supported(Cin, S, E)) return cudaErrorInvalidValue;
+  const int G = S / 4;
+  const size_t smem = ((size_t)2 * Cin * 4 * G * 4 + (size_t)Cin * 16 * (E + kPeTcWPitch) + 3 * (size_t)E) * sizeof(float);
+  static DynSmemState smem_state;
+  if (cudaError_t e = ensure_dyn_smem(patch_embed4_tf32_kernel<24>, smem, smem_state)) return e;
+  const int groups = (G + kPeRows - 1) / kPeRows;
+  const int threads = 32 * (G / 16 < 8 ? G / 16 : 8);
+  return launch_k(patch_embed4_tf32_kernel<24>, dim3(B * groups), dim3(threads), smem, st, img, reinterpret_cast<const float4*>(wq), b, gamma,
+                  beta, out, Cin, S, x16, fp16, reinterpret_cast<unsigned long long*>(stats));
 }
 
 cudaError_t launch_patch_embed(const float* img, const float* w, const float* b, const float* gamma,

@@ -122,6 +122,7 @@ struct xn_handle {
   int* group_start_dev = nullptr;
   int n_exp_total = 0, exp_chunk = 8;
   bool se_t_ok = false;               // group layout admits the transposed-score static-expansion kernels (static_exp.cu)
+  int64_t pe_tc = 1;                  // 16-bit modes: patch embedding on the tensor cores (TF32 mma.sync)
   int64_t se_tc = 2;                  // 16-bit modes: 0 = (B,E,N) kernels + mma.sync contractions, 1 = scores on tcgen05 + slab kernels, 2 = + tcgen05 class / out contractions
   Arena ws;
   int64_t launches = 0;
@@ -427,6 +428,10 @@ int swin_forward_chunk(xn_handle* h, const float* img, int Bc, float* out, cudaS
   bool first_x16 = false;
   if (h->pe_wq) {
     first_x16 = fuse_first;
+    if (!std::is_same<T, float>::value && h->pe_tc && patch_embed4_tc_supported(c.in_chans, c.img_size, c.embed_dim))
+      KL(1, launch_patch_embed4_tc(img, h->pe_wq, h->pe_b, h->pe_g, h->pe_beta, x, Bc, c.in_chans, c.img_size, c.embed_dim, st,
+                                   first_x16 ? (void*)ao : nullptr, std::is_same<T, f16>::value, first_x16 ? st1 : nullptr));
+    else
     KL(1, launch_patch_embed4(img, h->pe_wq, h->pe_b, h->pe_g, h->pe_beta, x, Bc, c.in_chans, c.img_size, c.embed_dim, st,
                               first_x16 ? (void*)ao : nullptr, std::is_same<T, f16>::value, first_x16 ? st1 : nullptr));
   } else KL(1, launch_patch_embed(img, h->pe_w, h->pe_b, h->pe_g, h->pe_beta, x, Bc, c.in_chans, c.img_size, c.patch_size,
@@ -2310,6 +2315,7 @@ int xn_set_option(xn_handle* h, const char* name, int64_t value) {
   if (n == "mega_dbg_mode") { h->mega_dbg_mode = value; h->drop_graphs(); return XN_OK; }
   if (n == "mega_coop") { g_mega_coop = value != 0; h->drop_graphs(); return XN_OK; }
   if (n == "ln_on_load") { h->ln_on_load = value; h->drop_graphs(); return XN_OK; }
+  if (n == "pe_tc") { h->pe_tc = value; h->drop_graphs(); return XN_OK; }
   if (n == "se_tc") { h->se_tc = value; h->drop_graphs(); return XN_OK; }
   if (n == "ln_fuse") { h->ln_fuse = value; h->drop_graphs(); return XN_OK; }
   if (n == "decode_groups") { h->decode_groups = std::max<int64_t>(0, std::min<int64_t>(value, xn_handle::kMaxDecodeGroups)); h->drop_graphs(); return XN_OK; }

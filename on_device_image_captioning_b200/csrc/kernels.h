@@ -124,6 +124,10 @@ cudaError_t launch_patch_filter_pack4(const float* w, float* wq, int Cin, int E,
 cudaError_t launch_patch_embed4(const float* img, const float* wq, const float* b, const float* gamma, const float* beta,
                                 float* out, int B, int Cin, int S, int E, cudaStream_t st, void* x16 = nullptr, int fp16 = 0,
                                 float* stats = nullptr);
+// the same on the tensor cores (mma.sync TF32; 16-bit modes): E == 192, S % 64 == 0
+bool patch_embed4_tc_supported(int Cin, int S, int E);
+cudaError_t launch_patch_embed4_tc(const float* img, const float* wq, const float* b, const float* gamma, const float* beta,
+                                   float* out, int B, int Cin, int S, int E, cudaStream_t st, void* x16, int fp16, float* stats);
 template <typename T>
 cudaError_t launch_cast(const float* x, T* y, long n, cudaStream_t st);
 

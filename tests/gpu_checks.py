@@ -591,6 +591,32 @@ def check_image_to_logits_16bit(name: str, precision: str = "fp16") -> List[Trip
     return out
 
 
+def check_tensor_core_options(name: str = "full_e2e_xavier", precision: str = "fp16") -> List[Triple]:
+    """Round-2 tensor-core variants against the kernels they replace, same weights and images: the static-expansion
+    scores / class / out contractions on tcgen05 (option se_tc = 2 vs 0: mma.sync + (B,E,N)-layout kernels) and the
+    TF32 tensor-core patch embedding (pe_tc = 1 vs 0: CUDA-core fp32).  Both variants must meet the 16-bit tolerance
+    against the fp32 oracle; the difference between them is reported."""
+    e, g, cfg, sd, x, pads = engine_for(name, precision)
+    out = []
+    with torch.no_grad():
+        taps = {}
+        ref = O.forward_enc(sd, cfg, x, pads, taps)
+    res = {}
+    for tag, se, pe in (("se_tc=0,pe_tc=0", 0, 0), ("se_tc=1,pe_tc=0", 1, 0), ("se_tc=2,pe_tc=1", 2, 1)):
+        e.set_option("se_tc", se)
+        e.set_option("pe_tc", pe)
+        if cfg.has_swin:
+            sw = e.forward_swin(x).clone()
+            out.append((f"{name}/{precision} [{tag}] swin features vs oracle rel-max", rel_max(sw, taps["swin"]), 4e-3))
+        enc = e.forward_enc(x, pads).clone()
+        res[tag] = enc
+        out.append((f"{name}/{precision} [{tag}] encoder output vs oracle rel-max", rel_max(enc, ref), 4e-3))
+    out.append((f"{name}/{precision} encoder output, tensor-core options on vs off, rel-max", rel_max(res["se_tc=2,pe_tc=1"], res["se_tc=0,pe_tc=0"]), 4e-3))
+    e.set_option("se_tc", 2)
+    e.set_option("pe_tc", 1)
+    return out
+
+
 def check_fp16_saturation() -> List[Triple]:
     """fp16 stores QKV / attention output / MLP hidden as halves (max 65504).  Scale the fc1 weights and bias of one
     stage-1 block (the hidden activations, hence fc2's input) by 300: fp16 must survive (finite, and as close to the

@@ -210,6 +210,13 @@ def test_fp16_image_to_logits_rel_max(name):
     _assert(G.check_image_to_logits_16bit(name, "fp16"))
 
 
+@pytest.mark.parametrize("name", ["full_e2e_xavier", "feat_peaky_b5"])
+def test_round2_tensor_core_options_vs_round1_kernels(name):
+    """Static expansion on tcgen05 (se_tc) and the TF32 patch embedding (pe_tc) against the kernels they replace."""
+    import gpu_checks as G
+    _assert(G.check_tensor_core_options(name, "fp16"))
+
+
 def test_bf16_image_to_logits_regression_bound():
     """bf16 operands do NOT meet north_star's 2e-3 (one rounding of an 8-bit significand is already 2e-3): this is a
     regression bound on the measured error, not a parity claim."""
