@@ -192,6 +192,12 @@ int64_t xn_workspace_bytes(const xn_handle* h);
  *   "use_skinny"               skinny mma.sync GEMM for decoder-step linears with <= 64 rows
  *   "ln_fuse"                  Swin norm1 / norm2 folded algebraically into the neighbouring tcgen05 GEMMs (16-bit modes): 1 = all but
  *                              each stage's first norm1, 2 (default) = those too (produced by the patch embedding / merge GEMM)
+ *   "se_tc"                    static-expansion block of the encoder in the 16-bit modes (reference models/layers.py:20-102):
+ *                              0 = per-image mma.sync contractions + (B,E,N)-layout normaliser kernels (round 1);
+ *                              1 = scores as ONE transposed linear-layer launch on tcgen05 + 16-token slab kernels;
+ *                              2 (default) = also class^T / out^T as batched tcgen05 GEMMs (3-D tensor maps, every operand K-major)
+ *   "pe_tc"                    1 (default): patch embedding of the 16-bit modes on the tensor cores (TF32 mma.sync, patch width 4,
+ *                              embed_dim 192, image side % 64 == 0); 0: the fp32 CUDA-core kernel (always used by the fp32 mode)
  *   "ln_on_load"               decoder-step LayerNorm computed inside the consuming tcgen05 GEMM (off: measured slower)
  *   "use_mega"                 1: every decoder position of the 16-bit modes (d_model 512, head width 64, <= 20 positions,
  *                              16 expansion vectors) runs as ONE persistent cooperative kernel with grid barriers between its

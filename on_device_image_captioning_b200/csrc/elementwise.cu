@@ -297,7 +297,7 @@ constexpr int kPe4Patches = 6;
 // GEMM's producer epilogue (gemm_tcgen05.cu), so the first qkv GEMM runs against the folded weights like every other
 // block and the stage-1 LayerNorm launch (the largest one: 453 MB read) disappears.
 // EPT > 0: E / 32 known at compile time (Swin-L: 6), so the per-lane channel loops carry no guards (the runtime-EP
-// form spent half of its 413 M warp instructions on ISETP / BRA / CS2R around 190 M FFMAs: profiles/r2s3_ncu_misc_summary.txt)
+// form spent half of its 413 M warp instructions on ISETP / BRA / CS2R around 190 M FFMAs: profiles/round2_s3_ncu_misc_kernels_summary.txt)
 template <int EPT>
 __global__ void __launch_bounds__(256) patch_embed4_kernel(const float* __restrict__ img, const float4* __restrict__ wq,
                                                            const float* __restrict__ bias, const float* __restrict__ g,
@@ -429,7 +429,7 @@ cudaError_t launch_patch_embed4(const float* img, const float* wq, const float* 
 // per warp one m16 tile of patches against all E channels with mma.sync.m16n8k8 TF32 (inputs rounded to the 10-bit
 // TF32 significand -- the same 2^-11 relative rounding every other operand of the 16-bit modes gets; the fp32 parity mode
 // keeps the exact CUDA-core kernels above).  The CUDA-core kernel is bound by shared-memory wavefronts (61.6 M per
-// launch for 190 M FFMAs: profiles/round2_ncu_misc_kernels_summary.txt); here a k8 step is 4 + 2 NT conflict-free LDS.32
+// launch for 190 M FFMAs: profiles/round2_s3_ncu_misc_kernels_summary.txt); here a k8 step is 4 + 2 NT conflict-free LDS.32
 // for NT tensor-core instructions, and the kernel is bound by its HBM traffic.
 // One CTA = one patch row at a time (G / 16 warps, one tile each), kPeRows rows per CTA.  Fragment layouts (PTX ISA,
 // m16n8k8 .tf32): g = lane >> 2, t = lane & 3; A: a0 (g, t) a1 (g + 8, t) a2 (g, t + 4) a3 (g + 8, t + 4);
