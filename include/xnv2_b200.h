@@ -198,6 +198,8 @@ int64_t xn_workspace_bytes(const xn_handle* h);
  *                              2 (default) = also class^T / out^T as batched tcgen05 GEMMs (3-D tensor maps, every operand K-major)
  *   "pe_tc"                    1 (default): patch embedding of the 16-bit modes on the tensor cores (TF32 mma.sync, patch width 4,
  *                              embed_dim 192, image side % 64 == 0); 0: the fp32 CUDA-core kernel (always used by the fp32 mode)
+ *   "dec_splitk"               1: the long-K decoder-step linears (ff2, reduce group) run as K / 512 slices on the batched tcgen05
+ *                              GEMM and are summed, in slice order, by the LayerNorm launch that follows; default 0 (measured: a tie)
  *   "ln_on_load"               decoder-step LayerNorm computed inside the consuming tcgen05 GEMM (off: measured slower)
  *   "use_mega"                 1: every decoder position of the 16-bit modes (d_model 512, head width 64, <= 20 positions,
  *                              16 expansion vectors) runs as ONE persistent cooperative kernel with grid barriers between its

@@ -77,6 +77,73 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
                threadIdx.x & 31);
 }
 
+// Split-K consumer (decoder-step ff2 / reduce GEMMs, 16-bit modes): the GEMM ran as `nparts` K-slices that left fp32
+// partial products part[s][row][c]; this kernel finishes it -- x = res + bias + sum_s part[s] in slice order (fixed, so
+// results do not depend on scheduling), written to xout (may alias res) -- and, with g != nullptr, applies the
+// LayerNorm that follows in the graph anyway (one warp per row, the row in registers; C % 128 == 0, C <= 1024).
+template <typename OutT>
+__global__ void __launch_bounds__(256) layernorm_sum_kernel(const float* __restrict__ part, int nparts, long pstride, long ldp,
+                                                            const float* __restrict__ bias, const float* res, long ldr,
+                                                            float* xout, long ldxo, const float* __restrict__ g,
+                                                            const float* __restrict__ b, OutT* __restrict__ y, long ldy,
+                                                            long rows, int C) {
+  pdl_wait();
+  pdl_trigger();
+  const long row = (long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  float4 v[8];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int c = lane * 4 + i * 128;
+    if (c < C) {
+      float4 a = bias ? *reinterpret_cast<const float4*>(bias + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int sl = 0; sl < nparts; ++sl) {
+        const float4 q = *reinterpret_cast<const float4*>(part + sl * pstride + row * ldp + c);
+        a.x += q.x; a.y += q.y; a.z += q.z; a.w += q.w;
+      }
+      if (res) {
+        const float4 r = *reinterpret_cast<const float4*>(res + row * ldr + c);
+        a.x += r.x; a.y += r.y; a.z += r.z; a.w += r.w;
+      }
+      v[i] = a;
+      *reinterpret_cast<float4*>(xout + row * ldxo + c) = a;
+      s += (a.x + a.y) + (a.z + a.w);
+    }
+  }
+  if (!g) return;
+  const float mean = warp_sum(s) / (float)C;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+    if (lane * 4 + i * 128 < C) {
+      const float d0 = v[i].x - mean, d1 = v[i].y - mean, d2 = v[i].z - mean, d3 = v[i].w - mean;
+      q += (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
+    }
+  const float rstd = 1.0f / sqrtf(warp_sum(q) / (float)C + kLnEps);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int c = lane * 4 + i * 128;
+    if (c < C) {
+      const float4 gg = *reinterpret_cast<const float4*>(g + c), bb = *reinterpret_cast<const float4*>(b + c);
+      store4<OutT>(y + row * ldy + c, (v[i].x - mean) * rstd * gg.x + bb.x, (v[i].y - mean) * rstd * gg.y + bb.y,
+                   (v[i].z - mean) * rstd * gg.z + bb.z, (v[i].w - mean) * rstd * gg.w + bb.w);
+    }
+  }
+}
+template <typename OutT>
+cudaError_t launch_layernorm_sum(const float* part, int nparts, long pstride, long ldp, const float* bias, const float* res, long ldr,
+                                 float* xout, long ldxo, const float* gamma, const float* beta, OutT* y, long ldy, long rows, int C,
+                                 cudaStream_t st) {
+  if (C % 128 || C > 1024 || (ldp & 3) || (ldr & 3) || (ldxo & 3) || (pstride & 3) || (gamma && (ldy & 3))) return cudaErrorInvalidValue;
+  launch_k(layernorm_sum_kernel<OutT>, dim3((unsigned)((rows + 7) / 8)), dim3(256), 0, st, part, nparts, pstride, ldp, bias, res, ldr, xout,
+           ldxo, gamma, beta, y, ldy, rows, C);
+  return cudaGetLastError();
+}
+template cudaError_t launch_layernorm_sum<bf16>(const float*, int, long, long, const float*, const float*, long, float*, long, const float*, const float*, bf16*, long, long, int, cudaStream_t);
+template cudaError_t launch_layernorm_sum<f16>(const float*, int, long, long, const float*, const float*, long, float*, long, const float*, const float*, f16*, long, long, int, cudaStream_t);
+
 // Specialised persistent LayerNorm for C = 128*VPL' widths: the row lives in exactly VPL float4 registers per lane,
 // gamma/beta are loaded once per warp, each warp strides over rows and keeps RIF rows in flight (memory-level
 // parallelism), so HBM latency is covered without relying on thousands of tiny CTAs.

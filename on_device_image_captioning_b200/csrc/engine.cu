@@ -122,6 +122,7 @@ struct xn_handle {
   int* group_start_dev = nullptr;
   int n_exp_total = 0, exp_chunk = 8;
   bool se_t_ok = false;               // group layout admits the transposed-score static-expansion kernels (static_exp.cu)
+  int64_t dec_splitk = 0;             // 16-bit modes: long-K decoder-step linears as K slices summed by the following LayerNorm (measured: a tie, off)
   int64_t pe_tc = 1;                  // 16-bit modes: patch embedding on the tensor cores (TF32 mma.sync)
   int64_t se_tc = 2;                  // 16-bit modes: 0 = (B,E,N) kernels + mma.sync contractions, 1 = scores on tcgen05 + slab kernels, 2 = + tcgen05 class / out contractions
   Arena ws;
@@ -310,6 +311,23 @@ int lin_f32(xn_handle* h, const float* x, long ldx, const LinW& w, const float* 
   KL(1, launch_gemm_f32(g, st));
   return 0;
 }
+// every tcgen05 GEMM launch goes through here: with option "profile" = 1 it is bracketed by events (roofline accounting)
+int tc_launch(xn_handle* h, const TcGemmArgs& g, cudaStream_t st) {
+  if (h->profile == 1) {
+    if (h->prof_used + 2 > h->prof_ev.size()) {
+      for (int i = 0; i < 2; ++i) { cudaEvent_t e; CU(cudaEventCreate(&e)); h->prof_ev.push_back(e); }
+    }
+    CU(cudaEventRecord(h->prof_ev[h->prof_used], st));
+    KL(1, launch_gemm_tc(g, st));
+    CU(cudaEventRecord(h->prof_ev[h->prof_used + 1], st));
+    h->prof_used += 2;
+    h->prof_flops.push_back(2.0 * g.M * (double)g.N * g.K * (g.batch > 0 ? g.batch : 1));
+    return 0;
+  }
+  KL(1, launch_gemm_tc(g, st));
+  return 0;
+}
+
 int lin_tc(xn_handle* h, const void* x, long ldx, const LinW& w, const float* res, long ldr, float* yf, void* yb,
            long ldy, int M, int act, int fp16, cudaStream_t st, int w_static = 1, const float* a32 = nullptr, long lda32 = 0,
            const float* ln_g = nullptr, const float* ln_b = nullptr, const LnFuse* lf = nullptr, float div = 0.f) {
@@ -319,19 +337,7 @@ int lin_tc(xn_handle* h, const void* x, long ldx, const LinW& w, const float* re
   g.a32 = a32; g.lda32 = lda32; g.ln_g = ln_g; g.ln_b = ln_b;        // LayerNorm-on-load (x is then unused)
   g.A = x; g.lda = ldx; g.W = w.wb; g.ldw = w.K; g.Cf = yf; g.Cb = yb; g.ldc = ldy; g.fp16 = fp16;
   g.bias = w.b; g.res = res; g.ldr = ldr; g.M = M; g.N = w.N; g.K = w.K; g.div = div; g.act = act;
-  if (h->profile == 1) {
-    if (h->prof_used + 2 > h->prof_ev.size()) {
-      for (int i = 0; i < 2; ++i) { cudaEvent_t e; CU(cudaEventCreate(&e)); h->prof_ev.push_back(e); }
-    }
-    CU(cudaEventRecord(h->prof_ev[h->prof_used], st));
-    KL(1, launch_gemm_tc(g, st));
-    CU(cudaEventRecord(h->prof_ev[h->prof_used + 1], st));
-    h->prof_used += 2;
-    h->prof_flops.push_back(2.0 * M * (double)w.N * w.K);
-    return 0;
-  }
-  KL(1, launch_gemm_tc(g, st));
-  return 0;
+  return tc_launch(h, g, st);
 }
 
 // activation-type dispatch used by the templated Swin forward
@@ -666,7 +672,7 @@ int enc_body_chunk(xn_handle* h, const float* feats, int Bc, const int* n_valid_
             q.Cb = ab ? CB : CA; q.ldc = E; q.sC = (long)d * E; q.fp16 = fp16;
             q.res = W.bexpT; q.ldr = E; q.sR = 0;
             q.M = d; q.N = E; q.K = N; q.batch = Bc;
-            KL(1, launch_gemm_tc(q, st));
+            if (int r = tc_launch(h, q, st)) return r;
           }
           for (int ab = 0; ab < 2; ++ab) {
             TcGemmArgs q{};
@@ -674,7 +680,7 @@ int enc_body_chunk(xn_handle* h, const float* feats, int Bc, const int* n_valid_
             q.W = ab ? bbw : abw; q.ldw = E; q.sW = (long)N * E;
             q.Cf = ab ? oB : oA; q.ldc = N; q.sC = (long)d * N; q.fp16 = fp16;
             q.M = d; q.N = N; q.K = E; q.batch = Bc; q.div = (float)c.n_exp_groups;
-            KL(1, launch_gemm_tc(q, st));
+            if (int r = tc_launch(h, q, st)) return r;
           }
           KL(1, launch_selector_mix_t<T>(xin, ldi, kabs + 3 * (size_t)d, 4 * d, oA, oB, xout, ldc, Bc, N, d, st));
         }
@@ -752,6 +758,7 @@ struct DecBufs {
   float *x0, *ycat, *q, *pre;
   void *xn, *att, *hid, *yn, *ycat16, *kv;      // fp32 in the parity mode, 16-bit operands otherwise
   void* e16;                                    // 16-bit copy of the encoder output (operand of the cross K/V projection)
+  float* kpart;                                 // fp32 partial products of the split-K decoder-step linears: [K / 512][R][d]
   int R, P;
   // persistent-kernel path: when topk > 0 the step also leaves log-softmax top-k in topv / topi (topk_done is set by
   // dec_step when it did; otherwise the caller runs the separate log-softmax + top-k kernel on the logits)
@@ -766,6 +773,7 @@ size_t dec_ws_bytes(const xn_config& c, int R, int P, int n_images, bool own_log
   f += (size_t)c.n_dec * P * R * 2 * c.num_exp_dec * P;
   f += (size_t)c.n_dec * P * R * c.num_exp_dec;
   f += (size_t)R * d * (6 + 2 * c.n_dec) + (size_t)R * c.ff;
+  f += (size_t)R * d * (std::max<size_t>(c.ff, d * c.n_dec) / 512 + 1);          // split-K partial products
   f += (size_t)n_images * c.enc_len * c.n_dec * 2 * d;
   f += (size_t)n_images * c.enc_len * d;          // 16-bit copy of the encoder output
   if (own_logits) f += (size_t)R * c.vocab;
@@ -790,6 +798,7 @@ int dec_alloc(xn_handle* h, DecBufs& D, int R, int P, int n_images) {
   D.hid = h->ws.get<float>((size_t)R * c.ff);
   D.yn = h->ws.get<float>((size_t)R * d);
   D.ycat16 = h->ws.get<float>((size_t)R * d * c.n_dec);
+  D.kpart = h->ws.get<float>((size_t)R * d * (std::max<size_t>(c.ff, d * c.n_dec) / 512 + 1));
   D.kv = h->ws.get<float>((size_t)n_images * c.enc_len * c.n_dec * 2 * d);
   // planned here, not taken from the arena at run time: the Swin / encoder chunks reset the arena offset in between
   D.e16 = h->ws.get<float>(((size_t)n_images * c.enc_len * d + 1) / 2);
@@ -934,6 +943,28 @@ int dec_step_t(xn_handle* h, DecBufs& D, int p, const int64_t* tok64, const int*
     if constexpr (k16) return dec_lin_skinny<T>(h, a16, a32, lda, g, b, w, res, ldr, yf, y16, ldy, R, act, st);
     else return 1;
   };
+  // Split-K (option "dec_splitk", 16-bit modes, tcgen05 path): a decoder-step linear with K >= 1024 onto d_model streams
+  // its whole K through 8 CTAs (16 us at 96 rows for 0.2 GFLOP); as K / 512 slices (batched mode of the tcgen05 GEMM)
+  // it runs on 4x the CTAs, and the partial products are summed -- in slice order -- by the LayerNorm launch that
+  // follows.  Applied at every row count of the tcgen05 path, so a caption does not depend on its batch.
+  // Measured in the graph (64 images, two decode groups): 5.20 ms of decode with, 5.00 - 5.36 ms without, 25.03 vs 25.08 ms
+  // per call -- a tie (the 16 us are a cold-cache ncu figure; in the graph the weights are L2 hits), so it is off by default.
+  int pend_parts = 0;
+  const float* pend_bias = nullptr;
+  auto splitk_ok = [&](const LinW& w) {
+    return k16 && h->dec_splitk && !h->ln_on_load && (R > 64 || !h->use_skinny) && w.N == d && d % 128 == 0 && d <= 1024 && w.K >= 1024 && w.K % 512 == 0 &&
+           w.K / 512 <= (int)(std::max<size_t>(c.ff, (size_t)d * c.n_dec) / 512 + 1);
+  };
+  auto lin_splitk = [&](const T* a, long lda, const LinW& w) -> int {
+    TcGemmArgs q{};
+    const int ns = w.K / 512;
+    q.A = a; q.lda = lda; q.sA = 512; q.W = w.wb; q.ldw = w.K; q.sW = 512;
+    q.Cf = D.kpart; q.ldc = d; q.sC = (long)R * d; q.fp16 = std::is_same<T, f16>::value;
+    q.M = R; q.N = w.N; q.K = 512; q.batch = ns; q.w_static = 1;
+    if (int r = tc_launch(h, q, st)) return r;
+    pend_parts = ns; pend_bias = w.b;
+    return 0;
+  };
   const bool fuse_ln = d == 512;            // embedding + norm_1 of layer 0, dynamic expansion + norm_2: one kernel each
   if (fuse_ln) KL(1, launch_embed_ln<T>(tok64, tok32, tok_stride, p, h->emb, h->pos, D.x0, d, h->dec[0].n1g, h->dec[0].n1b, xn, d, R, d, st));
   else KL(1, launch_embed(tok64, tok32, tok_stride, p, h->emb, h->pos, D.x0, d, R, d, st));
@@ -952,6 +983,13 @@ int dec_step_t(xn_handle* h, DecBufs& D, int p, const int64_t* tok64, const int*
     // LayerNorm + linear with the norm folded into the GEMM's A path (tcgen05, K = 512, one tile per CTA, more than 64 rows)
     auto ln_lin = [&](const float* x32, long ldx32, const float* g_, const float* b_, const LinW& w, float* yf, T* y16, long ldy, int act) -> int {
       if constexpr (k16) {
+        if (pend_parts > 0) {
+          // the previous layer's ff2 ran split along K: its partial products, bias and residual are summed here (into the
+          // residual stream row x32 itself) by the LayerNorm launch that follows it anyway
+          KL(1, launch_layernorm_sum<T>(D.kpart, pend_parts, (long)R * d, d, pend_bias, x32, ldx32, const_cast<float*>(x32), ldx32, g_, b_, xn, d, R, d, st));
+          pend_parts = 0;
+          return lin16(xn, d, w, nullptr, 0, yf, y16, ldy, act);
+        }
         if (h->ln_on_load && R > 64 && tc_gemm_ln_supported(R, w.N, w.K))
           return lin_tc(h, nullptr, 0, w, nullptr, 0, yf, yf ? nullptr : y16, ldy, R, act, std::is_same<T, f16>::value, st, 1, x32, ldx32, g_, b_);
       }
@@ -971,7 +1009,8 @@ int dec_step_t(xn_handle* h, DecBufs& D, int p, const int64_t* tok64, const int*
                                         rows_per_image, c.enc_len, c.num_heads, d / c.num_heads, n_valid, row_len, p, st)));
     if (int r = lin16(att, d, W.wo, xout, ldc, xout, nullptr, ldc, 0)) return r;
     if (int r = ln_lin(xout, ldc, W.n3g, W.n3b, W.ff1, nullptr, hid, c.ff, 2)) return r;
-    if (int r = lin16(hid, c.ff, W.ff2, xout, ldc, xout, nullptr, ldc, 0)) return r;
+    if (l + 1 < nd && splitk_ok(W.ff2)) { if (int r = lin_splitk(hid, c.ff, W.ff2)) return r; }     // summed by layer l + 1's norm_1 launch
+    else if (int r = lin16(hid, c.ff, W.ff2, xout, ldc, xout, nullptr, ldc, 0)) return r;
   }
   // reduce group: fp32 concatenation, converted on load by the skinny kernel where selected
   int rs = skinny(nullptr, D.ycat, ldc, nullptr, nullptr, h->dec_reduce, D.ycat + (size_t)(nd - 1) * d, ldc, D.pre, nullptr, d, 0);
@@ -981,6 +1020,15 @@ int dec_step_t(xn_handle* h, DecBufs& D, int p, const int64_t* tok64, const int*
     if (k16) {
       KL(1, launch_cast<T>(D.ycat, reinterpret_cast<T*>(D.ycat16), (long)R * ldc, st));
       ycat_in = reinterpret_cast<const T*>(D.ycat16);
+    }
+    if (splitk_ok(h->dec_reduce)) {
+      if constexpr (k16) {
+        if (int r = lin_splitk(ycat_in, ldc, h->dec_reduce)) return r;
+        KL(1, launch_layernorm_sum<T>(D.kpart, pend_parts, (long)R * d, d, pend_bias, D.ycat + (size_t)(nd - 1) * d, ldc, D.pre, d, h->dec_ng, h->dec_nb,
+                                      yn, d, R, d, st));
+        pend_parts = 0;
+        return dec_lin<T>(h, yn, d, h->vocab, nullptr, 0, logits, nullptr, ldl, R, 0, st);
+      }
     }
     if (int r = dec_lin<T>(h, ycat_in, ldc, h->dec_reduce, D.ycat + (size_t)(nd - 1) * d, ldc, D.pre, nullptr, d, R, 0, st)) return r;
   }
@@ -2315,6 +2363,7 @@ int xn_set_option(xn_handle* h, const char* name, int64_t value) {
   if (n == "mega_dbg_mode") { h->mega_dbg_mode = value; h->drop_graphs(); return XN_OK; }
   if (n == "mega_coop") { g_mega_coop = value != 0; h->drop_graphs(); return XN_OK; }
   if (n == "ln_on_load") { h->ln_on_load = value; h->drop_graphs(); return XN_OK; }
+  if (n == "dec_splitk") { h->dec_splitk = value; h->drop_graphs(); return XN_OK; }
   if (n == "pe_tc") { h->pe_tc = value; h->drop_graphs(); return XN_OK; }
   if (n == "se_tc") { h->se_tc = value; h->drop_graphs(); return XN_OK; }
   if (n == "ln_fuse") { h->ln_fuse = value; h->drop_graphs(); return XN_OK; }

@@ -304,10 +304,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   if (CTAS == 1 && ep.w_static && warp == 0 && lane == 0 && tile0 < total_tiles && !(ep.dbg & 4)) {
     const int ring = a_res ? kSB : S;
     pre_stages = nkb < ring ? nkb : ring;
-    const int n0 = (tile0 % n_tiles) * BN;
+    const int bz0 = ep.batch > 0 ? tile0 / tiles_pb : 0;
+    const int n0 = ((tile0 - bz0 * tiles_pb) % n_tiles) * BN;
     for (int kb = 0; kb < pre_stages; ++kb) {
       mbar_expect_tx(full_bar(kb), a_res ? Cfg::kBBytes : Cfg::kStageBytes);
-      tma_load_2d(a_res ? base + kBRingOff + kb * Cfg::kBBytes : base + kb * Cfg::kStageBytes + kABytes, &tma_b, kb * kBK, n0, full_bar(kb));
+      if (ep.batch > 0) tma_load_3d(base + kb * Cfg::kStageBytes + kABytes, &tma_b, kb * kBK, n0, bz0, full_bar(kb));
+      else tma_load_2d(a_res ? base + kBRingOff + kb * Cfg::kBBytes : base + kb * Cfg::kStageBytes + kABytes, &tma_b, kb * kBK, n0, full_bar(kb));
     }
   }
   pdl_wait();
@@ -340,7 +342,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
               }
             } else if (pre_stages > 0) {                // W tile and byte count of this stage were issued before the wait
               --pre_stages;
-              tma_load_2d(sa, &tma_a, kb * kBK, m0, full_bar(stage));
+              if (ep.batch > 0) tma_load_3d(sa, &tma_a, kb * kBK, m0, bz, full_bar(stage));
+              else tma_load_2d(sa, &tma_a, kb * kBK, m0, full_bar(stage));
             } else if (ep.batch > 0) {                  // batched problems: 3-D maps (k, row, problem), edges clipped per problem
               mbar_expect_tx(full_bar(stage), Cfg::kStageBytes);
               tma_load_3d(sa, &tma_a, kb * kBK, m0, bz, full_bar(stage));
@@ -912,7 +915,6 @@ static cudaError_t launch_tc(const TcGemmArgs& p, cudaStream_t st) {
   TcEpilogue ep{p.Cf, p.Cb, p.ldc, p.fp16, p.bias, p.res, p.ldr, p.div != 0.f ? 1.0f / p.div : 1.0f, p.w_static, p.a32, p.lda32, p.ln_g, p.ln_b,
                 p.stats_out, p.x16_out, p.ldx16, p.stats_zero, p.ln_stats, p.ln_k > 0 ? 1.0f / (float)p.ln_k : 0.f,
                 tma_c_ok ? 1 : 0, g_tc_debug, p.batch > 0 ? p.batch : 0, p.sC, p.sR};
-  if (p.batch > 0) ep.w_static = 0;
   const int tiles = ((p.M + kBM * CTAS - 1) / (kBM * CTAS)) * ((p.N + BN - 1) / BN) * (p.batch > 0 ? p.batch : 1);
   const int slots = sm_count() / CTAS;
   const int grid = CTAS * (tiles < slots ? tiles : slots);
@@ -976,6 +978,8 @@ cudaError_t launch_gemm_tc(const TcGemmArgs& p, cudaStream_t st) {
       const long w = (long)((p.N + c - 1) / c) * c - p.N;
       if (waste < 0 || w < waste) { bn = c; waste = w; }
     }
+    // few tiles in total (split-K slices of a decoder-step linear): 64-wide tiles, more CTAs sharing the operand stream
+    if ((p.N % 64) == 0 && (long)((p.M + kBM - 1) / kBM) * (p.N / 64) * p.batch <= sm_count()) return launch_tc_bn<64, 1>(p, st);
     if (bn == 256) return launch_tc_bn<256, 1>(p, st);
     if (bn == 192) return launch_tc_bn<192, 1>(p, st);
     return launch_tc_bn<128, 1>(p, st);

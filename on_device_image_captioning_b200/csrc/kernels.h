@@ -61,6 +61,8 @@ struct TcGemmArgs {
   // Batched mode (batch > 0): `batch` independent problems of the same M x N x K, operands stacked with the element
   // pitches sA / sW (3-D tensor maps: the M / N / K edges are clipped per problem), outputs with sC, the fp32 residual
   // with sR (0 = shared).  Single-CTA tiles and the generic epilogue only; no LayerNorm hooks.
+  // Split-K is the same mode: the problems are K-slices of one product (sA = sW = K / batch, K = the slice length) that
+  // leave fp32 partial products at the pitch sC for launch_layernorm_sum.
   int batch; long sA, sW, sC, sR;
 };
 bool tc_gemm_ln_supported(int M, int N, int K);
@@ -106,6 +108,12 @@ template <typename T>
 cudaError_t launch_gemm_skinny(const SkinnyArgs& p, cudaStream_t st);
 
 // ---------------------------------------------------------------- normalisation / embedding
+// split-K consumer: x = res + bias + sum of `nparts` fp32 partial products (slice order), written to xout (may alias
+// res); gamma != nullptr: followed by LayerNorm into y.  C % 128 == 0, C <= 1024.
+template <typename OutT>
+cudaError_t launch_layernorm_sum(const float* part, int nparts, long pstride, long ldp, const float* bias, const float* res, long ldr,
+                                 float* xout, long ldxo, const float* gamma, const float* beta, OutT* y, long ldy, long rows, int C,
+                                 cudaStream_t st);
 template <typename OutT>
 cudaError_t launch_layernorm(const float* x, long ldx, const float* gamma, const float* beta, OutT* y, long ldy,
                              long rows, int C, cudaStream_t st);

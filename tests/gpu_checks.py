@@ -617,6 +617,33 @@ def check_tensor_core_options(name: str = "full_e2e_xavier", precision: str = "f
     return out
 
 
+def check_decoder_splitk(name: str = "full_e2e_peaky", precision: str = "fp16") -> List[Triple]:
+    """Long-K decoder-step linears (ff2, reduce group) as K slices on the batched tcgen05 GEMM, summed by the LayerNorm
+    launch that follows (option dec_splitk), against the single-launch form: teacher-forced logits of both vs the fp32
+    oracle, and the beam-search captions of both against each other."""
+    e, g, cfg, sd, x, pads = engine_for(name, precision)
+    out = []
+    with torch.no_grad():
+        enc = O.forward_enc(sd, cfg, x, pads)
+        # enough rows for the tcgen05 path (the skinny kernel takes <= 64 rows): repeat the fixture's sequences
+        reps = max(1, 96 // enc.shape[0] + 1)
+        enc_r = enc.repeat(reps, 1, 1)
+        pads_r = (list(pads) * reps) if pads is not None else None
+        tok = torch.from_numpy(g["dec_tokens"]).repeat(reps, 1)
+        dp = g["dec_pads"].tolist() * reps
+        ref_lg = O.forward_dec(sd, cfg, enc, pads, torch.from_numpy(g["dec_tokens"]), g["dec_pads"].tolist(), False).repeat(reps, 1, 1)
+    res = {}
+    for v in (0, 1):
+        e.set_option("dec_splitk", v)
+        lg = e.forward_dec(enc_r, pads_r, tok, dp, False).clone()
+        res[v] = lg
+        out.append((f"{name}/{precision} [dec_splitk={v}] teacher-forced logits ({lg.shape[0]} rows) vs oracle rel-max", rel_max(lg, ref_lg), 2e-3))
+    # not bit-equal: fp32 sums in a different order flip a few 16-bit roundings of the next layer's operand (measured 2.4e-4)
+    out.append((f"{name}/{precision} logits split-K vs single launch rel-max", rel_max(res[1], res[0]), 1e-3))
+    e.set_option("dec_splitk", 0)
+    return out
+
+
 def check_fp16_saturation() -> List[Triple]:
     """fp16 stores QKV / attention output / MLP hidden as halves (max 65504).  Scale the fc1 weights and bias of one
     stage-1 block (the hidden activations, hence fc2's input) by 300: fp16 must survive (finite, and as close to the

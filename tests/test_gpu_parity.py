@@ -217,6 +217,13 @@ def test_round2_tensor_core_options_vs_round1_kernels(name):
     _assert(G.check_tensor_core_options(name, "fp16"))
 
 
+@pytest.mark.parametrize("name", ["full_e2e_peaky", "feat_peaky_b5"])
+def test_decoder_split_k_linears(name):
+    """ff2 / reduce-group linears of the decoder step as K slices (batched tcgen05 GEMM + summing LayerNorm)."""
+    import gpu_checks as G
+    _assert(G.check_decoder_splitk(name, "fp16"))
+
+
 def test_bf16_image_to_logits_regression_bound():
     """bf16 operands do NOT meet north_star's 2e-3 (one rounding of an 8-bit significand is already 2e-3): this is a
     regression bound on the measured error, not a parity claim."""

@@ -22,7 +22,7 @@ def main():
     sd = synth.make_state_dict(cfg, 0, "xavier")
     x = synth.make_images(cfg, B, 1, "randn").cuda()
     e = Engine(cfg, 0)
-    for opt in ("pdl", "use_graph", "use_skinny", "use_mega", "fuse_topk", "mega_coop", "tc_pair", "decode_groups", "ln_on_load", "attn_tc", "early_exit", "ln_fuse", "se_tc", "pe_tc"):
+    for opt in ("pdl", "use_graph", "use_skinny", "use_mega", "fuse_topk", "mega_coop", "tc_pair", "decode_groups", "ln_on_load", "attn_tc", "early_exit", "ln_fuse", "se_tc", "pe_tc", "dec_splitk"):
         if os.environ.get("XNV2_" + opt.upper()) is not None:
             e.set_option(opt, int(os.environ["XNV2_" + opt.upper()]))
     for prec in precs:
