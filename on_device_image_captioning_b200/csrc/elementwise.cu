@@ -253,11 +253,59 @@ __global__ void __launch_bounds__(256) merge_layernorm_kernel(const float* __res
   ln_row<OutT>(src, g, b, y + row * 4L * C, 4 * C, threadIdx.x & 31);
 }
 
+// The same with the 4C-wide row held in registers (VPL float4 per lane, C = 32 * VPL): the four source tokens are read
+// once, all loads of a row in flight together, and the quadrant of a column is a compile-time division.  Summation
+// order and formulas are those of ln_row, so the results are bit-identical to the generic kernel.
+template <typename OutT, int VPL>
+__global__ void __launch_bounds__(256) merge_layernorm_reg_kernel(const float* __restrict__ x, const float* __restrict__ g,
+                                                                  const float* __restrict__ b, OutT* __restrict__ y,
+                                                                  int B, int H) {
+  pdl_wait();
+  pdl_trigger();
+  constexpr int C = 32 * VPL, C4 = 4 * C;
+  const int H2 = H / 2, lane = threadIdx.x & 31;
+  const long rows = (long)B * H2 * H2;
+  const long row = (long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int bi = (int)(row / (H2 * H2)), rem = (int)(row % (H2 * H2));
+  const int i = rem / H2, j = rem % H2;
+  const float* base = x + (((long)bi * H + 2 * i) * H + 2 * j) * C;
+  float4 v[VPL];
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < VPL; ++k) {
+    const int c = lane * 4 + k * 128, q = c / C, cc = c - q * C;
+    v[k] = *reinterpret_cast<const float4*>(base + ((long)(q & 1) * H + (q >> 1)) * C + cc);
+  }
+#pragma unroll
+  for (int k = 0; k < VPL; ++k) s += (v[k].x + v[k].y) + (v[k].z + v[k].w);
+  const float mean = warp_sum(s) / (float)C4;
+  float qs = 0.f;
+#pragma unroll
+  for (int k = 0; k < VPL; ++k) {
+    const float d0 = v[k].x - mean, d1 = v[k].y - mean, d2 = v[k].z - mean, d3 = v[k].w - mean;
+    qs += (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
+  }
+  const float rstd = 1.0f / sqrtf(warp_sum(qs) / (float)C4 + kLnEps);
+  OutT* yr = y + row * (long)C4;
+#pragma unroll
+  for (int k = 0; k < VPL; ++k) {
+    const int c = lane * 4 + k * 128;
+    const float4 gg = *reinterpret_cast<const float4*>(g + c);
+    const float4 bb = *reinterpret_cast<const float4*>(b + c);
+    store4<OutT>(yr + c, (v[k].x - mean) * rstd * gg.x + bb.x, (v[k].y - mean) * rstd * gg.y + bb.y,
+                 (v[k].z - mean) * rstd * gg.z + bb.z, (v[k].w - mean) * rstd * gg.w + bb.w);
+  }
+}
+
 template <typename OutT>
 cudaError_t launch_merge_layernorm(const float* x, const float* gamma, const float* beta, OutT* y, int B, int H,
                                    int C, cudaStream_t st) {
   if (C & 3) return cudaErrorInvalidValue;
   const long rows = (long)B * (H / 2) * (H / 2);
+#define XN_MLN(V) if (C == 32 * V) { launch_k(merge_layernorm_reg_kernel<OutT, V>, dim3((unsigned)((rows + 7) / 8)), dim3(256), 0, st, x, gamma, beta, y, B, H); return cudaGetLastError(); }
+  XN_MLN(6) XN_MLN(12) XN_MLN(24)
+#undef XN_MLN
   launch_k(merge_layernorm_kernel<OutT>, dim3((unsigned)((rows + 7) / 8)), dim3(256), 0, st, x, gamma, beta, y, B, H, C);
   return cudaGetLastError();
 }
