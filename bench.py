@@ -312,6 +312,35 @@ def run_ours(args):
     h2d = host[0].numel() * 4
     d2h = sum(o.numel() * o.element_size() for o in outs[0])
 
+    # ---- the same end-to-end loop through an EnginePair (two handles taking alternate calls, four calls in flight): the
+    # decode chains of two calls run side by side.  Reported beside `e2e.value` (which stays the single handle's number).
+    e2e_pair = None
+    if world == 1 and not args.no_pair:
+        from on_device_image_captioning_b200.engine import EnginePair
+        pair = EnginePair(cfg, local)
+        pair.load_state_dict(synth.make_state_dict(cfg, 0, "xavier"), args.precision)
+        outs4 = outs + [tuple(torch.empty_like(o).pin_memory() for o in outs[0]) for _ in range(2)]
+
+        def pair_run(n_steps):
+            q = []
+            for i in range(n_steps):
+                q.append(pair.caption_host_begin(host[i % n_rot], SOS, EOS, BEAM, 1, MAX_LEN, outs4[i % 4]))
+                if len(q) == 4:
+                    pair.caption_host_end(q.pop(0))
+            for tk in q:
+                pair.caption_host_end(tk)
+
+        pair_run(12)                                     # both handles, both slots: eager, capture, replay
+        torch.cuda.synchronize()
+        e0.record()
+        pair_run(args.steps)                             # every call host-synchronised by its caption_host_end
+        e1.record()
+        torch.cuda.synchronize()
+        e2e_pair = dict(value=B * args.steps / (e0.elapsed_time(e1) / 1e3), unit=UNIT,
+                        api="EnginePair: two xn handles, alternate xn_caption_host_begin/_end calls, four in flight")
+        pair.close()
+        del pair
+
     # ---- BASELINE.json configs[3]'s per-GPU shape: 512 images per call and GPU (8 Swin chunks of 64, 1536 decoder rows)
     c4 = None
     if not args.no_config4:
@@ -487,7 +516,7 @@ def run_ours(args):
                                 if args.precision != "fp32" else "all fp32 (parity mode, CUDA-core FFMA GEMMs)"),
                     e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
                              api="xn_caption_host_begin/_end (pinned host buffers; two calls in flight, copies inside the timed region)",
-                             blocking_call_value=e2e_blocking, numa_node=numa),
+                             blocking_call_value=e2e_blocking, two_handles=e2e_pair, numa_node=numa),
                     config4_batch512=c4,
                     gpu_launches=int(launches), roofline=roofline,
                     whole_path=dict(algorithmic_tflops_per_gpu=whole_tflops, frac_of_tensor_peak=whole_tflops / peaks["bf16_sustained"],
@@ -533,6 +562,7 @@ def main():
     ap.add_argument("--swin-chunk", type=int, default=0)
     ap.add_argument("--early-exit", type=int, default=None, help="decode steps per conditional block (0 = no IF nodes; for profilers that cannot see into them)")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-pair", action="store_true", help="skip the EnginePair (two handles) end-to-end leg")
     ap.add_argument("--no-config4", action="store_true", help="skip the extra batch-512 (BASELINE configs[3] per-GPU shape) leg")
     ap.add_argument("--profile-region", action="store_true", help="cudaProfilerStart/Stop around the timed steps (for ncu launch lists)")
     ap.add_argument("--verbose", action="store_true")

@@ -11,7 +11,7 @@ def __getattr__(name):
     if name in ("End_ExpansionNet_v2", "ExpansionNet_v2", "E2E_ExpansionNet_Captioner", "EsembleCaptioningModel"):
         from . import models
         return getattr(models, name)
-    if name == "Engine":
-        from .engine import Engine
-        return Engine
+    if name in ("Engine", "EnginePair"):
+        from . import engine
+        return getattr(engine, name)
     raise AttributeError(name)

@@ -397,6 +397,59 @@ class Engine:
         return tv, ti, lp
 
 
+class EnginePair:
+    """Two engine handles with the same weights on one GPU that take alternate host-buffer calls, each on its own CUDA
+    stream, up to four calls in flight (two per handle: xn_caption_host_begin's staging slots).
+
+    One call is a throughput-bound Swin phase followed by a latency-bound decode phase (two chains of ~300 small dependent
+    kernels); with two handles the decode chains of two calls run side by side, which measured +5.5 ... 6.7 % captions/s
+    over the pipelined single handle at batch 64 (profiles/round2_s4_twin_handles_*.txt, tools/twin_probe.py).  The results
+    do not depend on the call pattern (every handle is deterministic and batch-invariant).  Costs a second copy of the
+    weights (0.5 GB in 16-bit) and a second workspace."""
+
+    def __init__(self, cfg: XNConfig, device: int = 0):
+        self.engines = [Engine(cfg, device), Engine(cfg, device)]
+        self.device = self.engines[0].device
+        with torch.cuda.device(self.device):
+            self.streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+        self._next = 0
+        self._inflight: Dict[int, Tuple[int, int]] = {}
+        self._serial = 0
+
+    def load_state_dict(self, sd: Dict[str, torch.Tensor], precision: str = "fp32"):
+        for e in self.engines:
+            e.load_state_dict(sd, precision)
+
+    def set_option(self, name: str, value: int):
+        for e in self.engines:
+            e.set_option(name, value)
+
+    @property
+    def kernel_launches(self) -> int:
+        return sum(e.kernel_launches for e in self.engines)
+
+    def caption_host_begin(self, inputs_host: torch.Tensor, sos_idx: int, eos_idx: int, beam_size: int, how_many: int, max_len: int,
+                           out: Tuple[torch.Tensor, torch.Tensor, torch.Tensor]) -> int:
+        """Same contract as Engine.caption_host_begin; tickets are ended in any order, at most four in flight."""
+        k = self._next
+        with torch.cuda.stream(self.streams[k]):
+            t = self.engines[k].caption_host_begin(inputs_host, sos_idx, eos_idx, beam_size, how_many, max_len, out)
+        self._next = k ^ 1
+        self._serial += 1
+        self._inflight[self._serial] = (k, t)
+        return self._serial
+
+    def caption_host_end(self, ticket: int):
+        if ticket not in self._inflight:
+            raise RuntimeError(f"caption_host ticket {ticket} is not in flight")
+        k, t = self._inflight.pop(ticket)
+        self.engines[k].caption_host_end(t)
+
+    def close(self):
+        for e in self.engines:
+            e.close()
+
+
 def unpack_beam_results(tok: torch.Tensor, ln: torch.Tensor, lp: torch.Tensor) -> Tuple[List[List[List[int]]], torch.Tensor]:
     """Device/host result buffers -> the reference's return convention: nested token lists (SOS..EOS
     inclusive, cut at length) and a (B, how_many, max_len_in_batch) zero-padded log-prob tensor

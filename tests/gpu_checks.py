@@ -467,6 +467,51 @@ def check_caption_host() -> List[Triple]:
     return out
 
 
+def check_engine_pair() -> List[Triple]:
+    """EnginePair (two handles taking alternate pipelined host-buffer calls, up to four in flight): every call must return
+    exactly what the single handle's device-input beam search returns for that batch, over eager / capture / replay of
+    both handles and with tickets ended out of order."""
+    from on_device_image_captioning_b200 import synth
+    from on_device_image_captioning_b200.engine import EnginePair
+    e, g, cfg, sd, x, pads = engine_for("full_e2e_peaky", "fp16")
+    m = g["meta"]
+    B, L = 5, 20
+    hosts = [synth.make_images(cfg, B, seed=40 + i, kind="mixed").pin_memory() for i in range(3)]
+    refs = []
+    for hst in hosts:
+        t_ref, l_ref, _ = e.beam_search(hst, None, m["sos"], m["eos"], 3, 1, L)
+        refs.append(_tokens_list(t_ref, l_ref))
+    pair = EnginePair(cfg, 0)
+    pair.load_state_dict(sd, "fp16")
+    outs = [(torch.empty(B, 1, L, dtype=torch.int32).pin_memory(), torch.empty(B, 1, dtype=torch.int32).pin_memory(),
+             torch.empty(B, 1, L, dtype=torch.float32).pin_memory()) for _ in range(4)]
+    bad, n_calls, q = 0, 14, []
+
+    def end(idx):
+        nonlocal bad
+        i, t = q.pop(idx)
+        pair.caption_host_end(t)
+        tok, ln, _ = outs[i % 4]
+        bad += sum(1 for b, tl in enumerate(_tokens_list(tok, ln)) if tl != refs[i % 3][b])
+
+    for i in range(n_calls):
+        q.append((i, pair.caption_host_begin(hosts[i % 3], m["sos"], m["eos"], 3, 1, L, outs[i % 4])))
+        if len(q) == 4:
+            end(1 if i % 5 == 0 else 0)          # now and then a younger ticket first (the other handle's)
+            end(0)
+    while q:
+        end(0)
+    err = 0.0
+    try:
+        pair.caption_host_end(12345)
+        err = 1.0
+    except RuntimeError:
+        pass
+    pair.close()
+    return [(f"EnginePair: captions differing from the single handle over {n_calls} pipelined calls", float(bad), 0.0),
+            ("EnginePair: unknown ticket accepted", err, 0.0)]
+
+
 # ------------------------------------------------------------------ BASELINE.json configurations at full size
 def _tokens_list(tok, ln):
     tok, ln = tok.cpu(), ln.cpu()

@@ -191,6 +191,12 @@ def test_caption_host_paths():
     _assert(G.check_caption_host())
 
 
+def test_engine_pair_alternating_pipelined_calls():
+    """Two handles taking alternate host-buffer calls (four in flight) return the single handle's captions."""
+    import gpu_checks as G
+    _assert(G.check_engine_pair())
+
+
 @pytest.mark.parametrize("name", ["c2_b64_peaky", "c2_b64_xavier"])
 def test_config2_batch64_fp32_vs_reference(name):
     """BASELINE.json configs[1] at batch 64, fp32: bit-exact captions vs the unmodified reference's batch-64 run."""
