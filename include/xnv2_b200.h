@@ -19,7 +19,11 @@
  * DEVICE pointers unless the name says host; work is enqueued on the given CUDA stream
  * (passed as void* == cudaStream_t) and is stream-ordered: the caller synchronises the
  * stream before reading results.  A handle is bound to one device and is not
- * thread-safe.  There is no CPU fallback: without a CUDA device xn_create fails.
+ * thread-safe.  Handles are independent of each other: calls on DIFFERENT handles may be
+ * in flight at the same time on different streams (two handles with the same weights
+ * taking alternate xn_caption_host_begin calls is the throughput serving pattern, see
+ * INTEGRATION.md); xn_set_option names marked process-wide in the list below affect
+ * every handle.  There is no CPU fallback: without a CUDA device xn_create fails.
  */
 #ifndef XNV2_B200_H
 #define XNV2_B200_H
@@ -186,7 +190,7 @@ int64_t xn_workspace_bytes(const xn_handle* h);
  *   "early_exit"               device-side early termination of the beam search (reference captioning_model.py:397): inside a
  *                              captured call the decode steps are grouped into CUDA-graph IF nodes of this many steps that are
  *                              skipped once every beam has ended (default 4; 0 = off: all steps always run, same results)
- *   "attn_tc"                  1: window attention on the tcgen05 kernel (default), 0: the mma.sync kernel
+ *   "attn_tc"                  1: window attention on the tcgen05 kernel (default), 0: the mma.sync kernel (process-wide)
  *   "pdl"                      programmatic dependent launch (process-wide)
  *   "tc_pair"                  CTA-pair (cta_group::2) GEMM tiles for long-K shapes (process-wide)
  *   "use_skinny"               skinny mma.sync GEMM for decoder-step linears with <= 64 rows
@@ -206,7 +210,7 @@ int64_t xn_workspace_bytes(const xn_handle* h);
  *                              phases (csrc/decode_mega.cu) instead of ~33 launches; default 0 (measured: a tie at <= 192 rows,
  *                              slower beyond).  "fuse_topk" (1): that kernel also does log-softmax + top-k of the 'max' search,
  *                              the R x V logits are never stored.  "mega_search" (0): all time steps of the search in one launch
- *                              (measured slower).  "mega_coop" (1): cooperative launch.  "mega_dbg": phase timestamps for
+ *                              (measured slower).  "mega_coop" (1): cooperative launch (process-wide).  "mega_dbg": phase timestamps for
  *                              xn_mega_timeline; "mega_dbg_mode": timing experiments (skip MMAs / loads / fills)
  *   "profile"                  1: event-time every tcgen05 GEMM; 2: event-time every kernel launch (both disable graphs)
  *   "tc_debug", "op_out16"     kernel timing experiments / test hooks */
