@@ -20,8 +20,9 @@ B = int(sys.argv[1]) if len(sys.argv) > 1 else 64
 STEPS = int(sys.argv[2]) if len(sys.argv) > 2 else 20
 cfg = C.swin_l_384()
 sd = synth.make_state_dict(cfg, 0, "xavier")
-engs = [Engine(cfg, 0) for _ in range(2)]
-streams = [torch.cuda.Stream() for _ in range(2)]      # a handle's call is ordered on the caller's stream: one stream per handle
+NH = int(os.environ.get("XNV2_HANDLES", "2"))           # handles in the rotation of the "twin" pattern
+engs = [Engine(cfg, 0) for _ in range(NH)]
+streams = [torch.cuda.Stream() for _ in range(NH)]      # a handle's call is ordered on the caller's stream: one stream per handle
 for e in engs:
     e.load_state_dict(sd, "fp16")
     if os.environ.get("XNV2_USE_GRAPH") is not None:      # 0: eager launches (plain stream-event semantics for front_chain)
@@ -29,16 +30,16 @@ for e in engs:
 host = [synth.make_images(cfg, B, 10 + i, "randn").pin_memory() for i in range(3)]
 L = 20
 outs = [(torch.empty(B, 1, L, dtype=torch.int32).pin_memory(), torch.empty(B, 1, dtype=torch.int32).pin_memory(),
-         torch.empty(B, 1, L, dtype=torch.float32).pin_memory()) for _ in range(4)]
+         torch.empty(B, 1, L, dtype=torch.float32).pin_memory()) for _ in range(2 * max(NH, 2))]
 
 
 def run(n, twin, depth):
     """`depth` calls in flight; call i goes to handle i % 2 when twin."""
     q = []
     for i in range(n):
-        e = engs[i % 2] if twin else engs[0]
-        with torch.cuda.stream(streams[i % 2] if twin else streams[0]):
-            q.append((e, e.caption_host_begin(host[i % 3], 79, 77, 3, 1, L, outs[i % 4])))
+        e = engs[i % NH] if twin else engs[0]
+        with torch.cuda.stream(streams[i % NH] if twin else streams[0]):
+            q.append((e, e.caption_host_begin(host[i % 3], 79, 77, 3, 1, L, outs[i % len(outs)])))
         if len(q) >= depth:
             e0, t0 = q.pop(0)
             e0.caption_host_end(t0)
@@ -65,12 +66,12 @@ def tokens_of(twin, depth):
     def end_one():
         e0, t0, i0 = q.pop(0)
         e0.caption_host_end(t0)
-        res.append(outs[i0 % 4][0].clone())
+        res.append(outs[i0 % len(outs)][0].clone())
 
     for i in range(3):
-        e = engs[i % 2] if twin else engs[0]
-        with torch.cuda.stream(streams[i % 2] if twin else streams[0]):
-            q.append((e, e.caption_host_begin(host[i % 3], 79, 77, 3, 1, L, outs[i % 4]), i))
+        e = engs[i % NH] if twin else engs[0]
+        with torch.cuda.stream(streams[i % NH] if twin else streams[0]):
+            q.append((e, e.caption_host_begin(host[i % 3], 79, 77, 3, 1, L, outs[i % len(outs)]), i))
         if len(q) >= depth:
             end_one()
     while q:
@@ -80,7 +81,8 @@ def tokens_of(twin, depth):
 
 want = tokens_of(False, 2)
 s1 = timed(False, 2)
-t2 = timed(True, 2)
-t4 = timed(True, 4)
-same = all(torch.equal(a, b) for a, b in zip(want, tokens_of(True, 4)))
-print(f"single {s1:7.1f}   twin depth2 {t2:7.1f}   twin depth4 {t4:7.1f} captions/s   tokens {'identical' if same else 'DIFFER'}", flush=True)
+t2 = timed(True, NH)
+t4 = timed(True, 2 * NH)
+same = all(torch.equal(a, b) for a, b in zip(want, tokens_of(True, 2 * NH)))
+print(f"{NH} handles: single {s1:7.1f}   rotation, {NH} in flight {t2:7.1f}   rotation, {2 * NH} in flight {t4:7.1f} captions/s"
+      f"   tokens {'identical' if same else 'DIFFER'}", flush=True)
