@@ -174,3 +174,39 @@ def test_pad_rule_for_end_to_end_models():
     _check_no_enc_pads([0, 0, 0], "m")
     with pytest.raises(AssertionError, match="End to End case have no padding"):
         _check_no_enc_pads([0, 2], "End to End case have no padding")
+
+
+def test_engine_pair_ticket_bookkeeping_without_a_gpu():
+    """EnginePair's host logic (alternation between the two handles, tickets ended in any order, unknown tickets refused)
+    on stand-in handles: the real handles need a GPU (tests/test_gpu_parity.py::test_engine_pair_alternating_pipelined_calls)."""
+    from on_device_image_captioning_b200.engine import EnginePair
+
+    class FakeHandle:
+        def __init__(self, name):
+            self.name, self.begun, self.ended, self.slot = name, [], [], 0
+
+        def caption_host_begin(self, x, *a):
+            self.begun.append(x)
+            self.slot ^= 1
+            return self.slot ^ 1                       # the C ABI's ticket: the staging slot, 0 / 1 alternating
+
+        def caption_host_end(self, t):
+            self.ended.append(t)
+
+    pair = object.__new__(EnginePair)
+    pair.engines = [FakeHandle("a"), FakeHandle("b")]
+    pair.streams = [None, None]                        # torch.cuda.stream(None) is a no-op context
+    pair.device, pair._next, pair._inflight, pair._serial = 0, 0, {}, 0
+    tickets = [pair.caption_host_begin(i, 1, 2, 3, 1, 20, None) for i in range(4)]
+    assert len(set(tickets)) == 4
+    assert pair.engines[0].begun == [0, 2] and pair.engines[1].begun == [1, 3]
+    pair.caption_host_end(tickets[2])                  # out of order: handle a's second slot
+    pair.caption_host_end(tickets[1])
+    assert pair.engines[0].ended == [1] and pair.engines[1].ended == [0]
+    with pytest.raises(RuntimeError):
+        pair.caption_host_end(tickets[2])              # already ended
+    with pytest.raises(RuntimeError):
+        pair.caption_host_end(999)
+    pair.caption_host_end(tickets[0])
+    pair.caption_host_end(tickets[3])
+    assert not pair._inflight
