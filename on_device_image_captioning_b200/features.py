@@ -76,3 +76,62 @@ def extract_features(engine, images: Sequence[Union[str, np.ndarray, torch.Tenso
             w.add(img_id, f[i])
     w.close()
     return w.container
+
+
+def shard_path(out_path: str, rank: int, world: int) -> str:
+    """Per-rank container name: "<base>.rank<r>of<W><ext>" (the plain path for a single process)."""
+    if world <= 1:
+        return out_path
+    base, ext = os.path.splitext(out_path)
+    return f"{base}.rank{rank}of{world}{ext}"
+
+
+def extract_features_sharded(engine, images: Sequence[Union[str, np.ndarray, torch.Tensor]], img_ids: Sequence, out_path: str,
+                             rank: int = None, world: int = None, batch_size: int = 64, img_size: int = None) -> str:
+    """One process per GPU: rank r extracts images r, r + W, r + 2W, ... (dist.shard_indices, the same split the
+    captioning path uses) into its own container shard_path(out_path, r, W); no collective is involved, the ranks only
+    meet at a barrier at the end when a process group is up.  The reference runs data_generator.py:96-160 in a single
+    process.  Returns this rank's path; FeatureShards reads the set back by key."""
+    import torch.distributed as td
+    from .dist import shard_indices
+    up = td.is_available() and td.is_initialized()
+    rank = (td.get_rank() if up else 0) if rank is None else rank
+    world = (td.get_world_size() if up else 1) if world is None else world
+    assert len(images) == len(img_ids)
+    idx = shard_indices(len(images), rank, world)
+    path = shard_path(out_path, rank, world)
+    extract_features(engine, [images[i] for i in idx], [img_ids[i] for i in idx], path, batch_size, img_size)
+    if up:
+        td.barrier()
+    return path
+
+
+class FeatureShards:
+    """Read-side view over the per-rank containers of extract_features_sharded: features by image id, whichever rank
+    wrote them (the data loader of the reference, coco_dataloader.py:446,517, looks features up by key only)."""
+
+    def __init__(self, out_path: str, world: int):
+        self.paths = [shard_path(out_path, r, world) for r in range(world)]
+        self._where: Dict[str, str] = {}
+        for p in self.paths:
+            for k in self._keys(p):
+                self._where[k] = p
+
+    @staticmethod
+    def _keys(path: str) -> List[str]:
+        try:
+            import h5py
+            with h5py.File(path, "r") as f:
+                return list(f.keys())
+        except ImportError:
+            with np.load(path) as z:
+                return list(z.files)
+
+    def __len__(self) -> int:
+        return len(self._where)
+
+    def __contains__(self, img_id) -> bool:
+        return feature_key(img_id) in self._where
+
+    def read(self, img_id) -> np.ndarray:
+        return read_features(self._where[feature_key(img_id)], img_id)
