@@ -415,6 +415,10 @@ def run_ours(args):
                             traffic=(_traffic() or {}).get("dram_bytes_per_launch"),
                             traffic_detail=_traffic(), peak_source=peaks["source"] + ", sustained figure (kernel timed inside a long step)",
                             launches_timed=g_n, gemm_ms_per_step=g_ms, gemm_share_of_step=g_ms / (ms / args.steps),
+                            share_note=("gemm_share_of_step divides the event-timed EAGER GEMM launches by the GRAPHED step time (the ~320 "
+                                        "decoder-step launches take 2x longer eager than as graph nodes, so it overstates the share); the "
+                                        "like-for-like share, comparable with the ncu launch lists under profiles/, is "
+                                        "launcher_time_shares_eager_step.launch_gemm_tc"),
                             algorithmic_tflop_per_step=g_fl / 1e12,
                             # the same figure over the launches of >= 1 GFLOP (Swin, encoder, cross K/V: throughput-bound);
                             # the remainder are the decoder-step GEMMs, bounded by latency (5-13 us each for < 0.1 GFLOP)
