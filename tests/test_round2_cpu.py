@@ -210,3 +210,21 @@ def test_engine_pair_ticket_bookkeeping_without_a_gpu():
     pair.caption_host_end(tickets[0])
     pair.caption_host_end(tickets[3])
     assert not pair._inflight
+
+
+def test_bench_clock_sampler_summary_uses_only_active_samples():
+    """bench.py's clock sampler: rows are kept only while a timed region is active, the reported SM clock is their plain
+    median (idle phases read the maximum clock and must not mask a power-capped run), throttle reasons are collected."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(os.path.dirname(GOLDEN_DIR), "..", "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    s = bench.ClockSampler(0)
+    assert not s.active.is_set()
+    assert s.summary()["sm_mhz"] is None and s.summary()["samples"] == 0
+    na, act = "Not Active", "Active"
+    s.rows = [["1800", "1965", "900.0", na, na, na, act], ["1750", "1965", "950.0", na, na, na, act],
+              ["1965", "1965", "300.0", na, na, na, na]]
+    out = s.summary()
+    assert out["sm_mhz"] == 1800.0 and out["sm_max_mhz"] == 1965.0 and out["samples"] == 3
+    assert out["reasons"] == ["sw_power_cap"]
